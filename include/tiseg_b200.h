@@ -1,0 +1,131 @@
+/*
+ * tiseg_b200.h — C ABI of libtiseg_b200.so: the sm_100a (B200) implementation of the test-time
+ * instance pipeline (post-process + evaluation) of clownrat6/Tissue-Image-Segmentation (`tiseg`).
+ *
+ * This is the drop-in boundary.  Every entry point is batched over N independent tiles
+ * ([N, H, W] C-contiguous arrays, row pitch W), stream-ordered on the context's CUDA stream, and
+ * takes plain pointers and sizes.  A pointer may be a DEVICE pointer (zero-copy, asynchronous,
+ * nothing is synchronised) or a HOST pointer (numpy buffer: the library stages it host<->device
+ * on the context stream and synchronises before returning) — detected per pointer with
+ * cudaPointerGetAttributes.  There is NO CPU implementation behind any of them: without a CUDA
+ * device tiseg_create fails and nothing else can be called.
+ *
+ * Each function names the reference code (file:line under the reference repository) it replaces.
+ * All return TISEG_OK (0) or an error code; tiseg_last_error() gives the message (thread-local).
+ */
+#ifndef TISEG_B200_H
+#define TISEG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TISEG_OK 0
+#define TISEG_ERR_CUDA 1   /* a CUDA runtime call or kernel launch failed                     */
+#define TISEG_ERR_ARG 2    /* bad argument (null pointer, non-positive size, unknown option)  */
+#define TISEG_ERR_NOGPU 3  /* no CUDA device: there is no CPU fallback                        */
+#define TISEG_ERR_LIMIT 4  /* an internal capacity (pair table, queue) was exceeded           */
+
+typedef struct tiseg_ctx tiseg_ctx;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int tiseg_create(tiseg_ctx** out, int device);
+int tiseg_destroy(tiseg_ctx* ctx);
+/* run on an existing cudaStream_t (e.g. torch's current stream; NULL = the legacy default stream).
+ * A fresh context owns a private non-blocking stream until this is called. */
+int tiseg_set_stream(tiseg_ctx* ctx, void* cuda_stream);
+int tiseg_synchronize(tiseg_ctx* ctx);
+const char* tiseg_last_error(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long tiseg_launch_count(tiseg_ctx* ctx);
+int tiseg_version(void);
+
+/* ---- A1: softmax / TTA mean / argmax ---------------------------------------------------------
+ * tiseg/models/segmentors/base.py:321-339 (F.softmax per TTA variant, sum/len, resize == identity
+ * at ori_hw) followed by `sem_logit.argmax(dim=1)` (unet.py:62, dist.py:266, hovernet.py:271).
+ * logits [N, T, C, H, W] fp32; prob [N, C, H, W] fp32 or NULL; cls [N, H, W] uint8 or NULL
+ * (first maximum wins, like torch.argmax). */
+int tiseg_softmax_argmax(tiseg_ctx* ctx, const float* logits, int N, int T, int C, int H, int W,
+                         float* prob, uint8_t* cls);
+
+/* ---- A5 / A6 / A15: connected-component labelling ---------------------------------------------
+ * skimage.measure.label(img, background=bg, connectivity=conn) (unet.py:85, dist.py:107,123,
+ * multi_task_unet.py:101, inst_metrics.py:12-13,142-143) and scipy.ndimage.label (hovernet.py:296,358;
+ * conn=1).  Equal-valued neighbouring non-background pixels are connected; conn 1 = 4-neighbourhood,
+ * 2 = 8-neighbourhood; ids 1..K in raster order of each component's first pixel.  Because the ids are
+ * canonical, this is also re_instance (datasets/utils/instance_semantic.py:5-15) composed with the
+ * label call inside every metric.  img / out [N,H,W] int32; count [N] int32 (K per tile) or NULL. */
+int tiseg_label(tiseg_ctx* ctx, const int32_t* img, int N, int H, int W, int32_t background,
+                int connectivity, int32_t* out, int32_t* count);
+/* same on a uint8 image (masks, class maps) */
+int tiseg_label_u8(tiseg_ctx* ctx, const uint8_t* img, int N, int H, int W, int32_t background,
+                   int connectivity, int32_t* out, int32_t* count);
+/* re_instance alone (instance_semantic.py:5-15): sorted unique non-zero ids -> 1..K, order-preserving */
+int tiseg_re_instance(tiseg_ctx* ctx, const int32_t* img, int N, int H, int W, int32_t* out, int32_t* count);
+
+/* ---- A3: scipy.ndimage.binary_fill_holes (unet.py:83, hovernet.py:355, multi_task_unet.py:95) ---
+ * mask / out [N,H,W] uint8 (non-zero = foreground; out is 0/1). */
+int tiseg_fill_holes(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, uint8_t* out);
+
+/* ---- A4: skimage.morphology.remove_small_objects ------------------------------------------------
+ * bool input (unet.py:84): components of `connectivity` (1 -> 4-neighbourhood), size < min_size zeroed. */
+int tiseg_remove_small_objects(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, int min_size,
+                               int connectivity, uint8_t* out);
+/* int input (hovernet.py:297,359): the values are the component ids; ids with count < min_size zeroed. */
+int tiseg_remove_small_labels(tiseg_ctx* ctx, const int32_t* lab, int N, int H, int W, int min_size,
+                              int32_t* out);
+
+/* ---- A7: skimage.morphology.dilation / erosion on label images (unet.py:86, dist.py:88-94) -------
+ * footprint 0 = disk(radius) {x^2+y^2<=r^2}, 1 = square(2*radius+1); out-of-image taps ignored
+ * (== ndimage 'reflect' for these symmetric footprints).  radius <= 3. */
+int tiseg_dilate_labels(tiseg_ctx* ctx, const int32_t* lab, int N, int H, int W, int footprint,
+                        int radius, int32_t* out);
+int tiseg_erode_labels(tiseg_ctx* ctx, const int32_t* lab, int N, int H, int W, int footprint,
+                       int radius, int32_t* out);
+
+/* ---- A2: UNet-family postprocess ----------------------------------------------------------------
+ * unet.py:71-93, micronet.py:185-207 (radius 1); cunet.py:70-93, cdnet.py:96-119, fullnet.py:190-213,
+ * cmicronet.py:186-209 (radius 3, edge_id = num_classes zeroed IN PLACE in `cls`); dcan.py:193-217.
+ * cls [N,H,W] uint8 class map (argmax output; mutated when edge_id >= 0); for each class id present,
+ * ascending: fill holes -> remove_small_objects(5) -> label -> dilation(disk(radius)) -> overwrite.
+ * sem_out [N,H,W] uint8, inst_out [N,H,W] int32. max_class = largest class id that can occur (<= 63);
+ * edge_id < 0 = none; kill (NULL or [N,H,W] uint8) = DCAN's contour map: cls[kill > 0] = 0 in place
+ * (dcan.py:196). */
+int tiseg_postproc_unet(tiseg_ctx* ctx, uint8_t* cls, int N, int H, int W, int max_class, int radius,
+                        int edge_id, const uint8_t* kill, uint8_t* sem_out, int32_t* inst_out);
+
+/* ---- A10: skimage.segmentation.watershed(image, markers, mask) -----------------------------------
+ * connectivity 1, compactness 0, no lines (dist.py:124, hovernet.py:361).  Ordered (value, age) flood,
+ * 4-neighbours visited up/left/right/down, label-at-push; seeds ordered by (value, flat index).
+ * image [N,H,W] uint8 / fp64; markers int32; mask uint8 (NULL = all); out int32. */
+int tiseg_watershed_u8(tiseg_ctx* ctx, const uint8_t* image, const int32_t* markers, const uint8_t* mask,
+                       int N, int H, int W, int32_t* out);
+int tiseg_watershed_f64(tiseg_ctx* ctx, const double* image, const int32_t* markers, const uint8_t* mask,
+                        int N, int H, int W, int32_t* out);
+
+/* ---- A8: DIST postprocess (dist.py:275-284 -> dynamic_watershed_alias :114-129) ---------------------
+ * dist [N,H,W] fp32 raw distance-head output; inst_out [N,H,W] int32 (the reference returns int64
+ * with the same values).  Optional debug outputs (NULL to skip): markers int32, ws int32 (raw flood). */
+int tiseg_postproc_dist(tiseg_ctx* ctx, const float* dist, int N, int H, int W, int32_t* inst_out,
+                        int32_t* markers_out, int32_t* ws_out);
+
+/* ---- A16 / A17: pre_eval_bin_aji + pre_eval_bin_pq (inst_metrics.py:10-92, 138-229) ---------------
+ * pred / gt [N,H,W] int32 instance maps with arbitrary ids (the relabelling the reference does with
+ * re_instance + measure.label is done inside).  aji [N,2] fp64 = (overall_inter, overall_union);
+ * pq [N,4] fp64 = (tp, fp, fn, iou_sum).  Either output may be NULL.  match_iou is fixed at the
+ * reference default 0.5 (the Hungarian branch is unreachable with it). */
+int tiseg_pair_metrics_bin(tiseg_ctx* ctx, const int32_t* pred, const int32_t* gt, int N, int H, int W,
+                           double* aji, double* pq);
+
+/* ---- A19: pre_eval_all_semantic_metric (sem_metrics.py:16-53) --------------------------------------
+ * pred / gt [N,H,W] uint8; counts [N, 5, C] int64 = TP, FP, FN, Pred, GT per class (TN derived on the
+ * host as N_valid - (TP+FP+FN)); valid [N] int64 = pixels with gt != ignore_index. */
+int tiseg_sem_counts(tiseg_ctx* ctx, const uint8_t* pred, const uint8_t* gt, int N, int H, int W, int C,
+                     int ignore_index, int64_t* counts, int64_t* valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

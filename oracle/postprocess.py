@@ -1,0 +1,313 @@
+"""CPU oracle: per-model test-time post-processing (TEST INFRASTRUCTURE ONLY).
+
+Restates, function by function, what the reference's segmentors do between the network logits
+and ``{'sem_pred', 'inst_pred'}``; every function cites the reference lines it follows.
+scipy.ndimage and OpenCV are called exactly as the reference calls them; the scikit-image
+functions come from ``skimage_port`` (C restatement) and the thin wrappers below.
+"""
+import math
+import warnings
+
+import numpy as np
+from scipy import ndimage as ndi
+
+from .skimage_port import label as sk_label
+from .skimage_port import watershed as sk_watershed
+from .skimage_port import reconstruction_erosion, align_foreground
+
+try:  # OpenCV is only needed by the HoVer-Net path
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+# --------------------------------------------------------------------------- skimage wrappers
+def disk(radius):
+    """skimage.morphology.disk: {(x, y): x^2 + y^2 <= r^2} as uint8."""
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return ((X * X + Y * Y) <= radius * radius).astype(np.uint8)
+
+
+def square(width):
+    return np.ones((width, width), np.uint8)
+
+
+def dilation(image, selem):
+    """skimage.morphology.dilation == ndi.grey_dilation(image, footprint=selem) (symmetric selem)."""
+    return ndi.grey_dilation(image, footprint=np.asarray(selem)[::-1, ::-1])
+
+
+def erosion(image, selem):
+    """skimage.morphology.erosion == ndi.grey_erosion(image, footprint=selem)."""
+    return ndi.grey_erosion(image, footprint=np.asarray(selem))
+
+
+def remove_small_objects(ar, min_size=64, connectivity=1):
+    """skimage.morphology.remove_small_objects (0.18.3 semantics).
+
+    bool input: components of the given connectivity (default 1 -> 4-neighbourhood) found with
+    ``ndi.label``; int input: the values themselves are the component ids.  Components with
+    ``size < min_size`` are zeroed.  Returns a copy.
+    """
+    out = np.array(ar, copy=True)
+    if min_size == 0:
+        return out
+    if out.dtype == bool:
+        selem = ndi.generate_binary_structure(ar.ndim, connectivity)
+        ccs = np.zeros(ar.shape, np.int32)
+        ndi.label(ar, selem, output=ccs)
+    else:
+        ccs = out
+    sizes = np.bincount(ccs.ravel())
+    too_small = sizes < min_size
+    out[too_small[ccs]] = 0
+    return out
+
+
+# --------------------------------------------------------------------------- A1 softmax / argmax
+def softmax(logits, axis=0):
+    """fp32 softmax over the channel axis (torch ``F.softmax``: exp(x - max) / sum)."""
+    x = np.asarray(logits, np.float32)
+    m = x.max(axis=axis, keepdims=True)
+    e = np.exp(x - m, dtype=np.float32)
+    return (e / e.sum(axis=axis, keepdims=True, dtype=np.float32)).astype(np.float32)
+
+
+def softmax_tta_mean(logit_list):
+    """base.py:321-336: softmax each TTA variant, then ``sum(list) / len(list)`` in fp32."""
+    acc = None
+    for lg in logit_list:
+        p = softmax(lg, axis=0)
+        acc = p if acc is None else (acc + p).astype(np.float32)
+    return (acc / np.float32(len(logit_list))).astype(np.float32)
+
+
+def argmax_classes(prob):
+    """``sem_logit.argmax(dim=1)``: first maximum wins."""
+    return np.argmax(prob, axis=0).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- A2 UNet family
+def unet_family_postprocess(pred, radius=1, edge_id=None):
+    """unet.py:71-93 (radius 1), micronet.py:185-207; with ``edge_id`` (= num_classes) the
+    variants cunet.py:70-93, cdnet.py:96-119, fullnet.py:190-213, cmicronet.py:186-209
+    (radius 3) which first zero the edge class in place.
+
+    For each class id present (ascending, 0 skipped): mask -> binary_fill_holes ->
+    remove_small_objects(5) -> measure.label -> dilation(disk(radius)) -> + cur -> overwrite
+    into inst_pred; cur += len(unique(dilated)); sem_pred[dilated > 0] = id.
+    """
+    if edge_id is not None:
+        pred[pred == edge_id] = 0
+    inst_pred = np.zeros(pred.shape, np.int32)
+    sem_pred = np.zeros(pred.shape, np.uint8)
+    cur = 0
+    for sem_id in np.unique(pred):
+        if sem_id == 0:
+            continue
+        m = ndi.binary_fill_holes(pred == sem_id)
+        m = remove_small_objects(m, 5)
+        lab = dilation(sk_label(m), disk(radius))
+        hit = lab > 0
+        lab[hit] += cur
+        inst_pred[hit] = 0
+        inst_pred += lab.astype(np.int32)
+        cur += len(np.unique(lab))
+        sem_pred[hit] = sem_id
+    return sem_pred, inst_pred
+
+
+def dcan_postprocess(cell_pred, cont_pred, radius=3):
+    """dcan.py:193-217: contour prediction splits cells (in place), then the UNet-family loop."""
+    cell_pred[cont_pred > 0] = 0
+    return unet_family_postprocess(cell_pred, radius=radius)
+
+
+# --------------------------------------------------------------------------- A8 DIST
+def _h_reconstruction_erosion(prob_img, h, literal=True):
+    """dist.py:43-57.  ``literal`` keeps the reference's per-pixel ``np.vectorize`` (its real cost
+    on the CPU baseline); the fast form is value-identical."""
+    if literal:
+        # int(x): numpy >= 2 would wrap uint8(255) + 1; the reference's pinned numpy 1.20 promotes
+        shifted = np.vectorize(lambda x, lamb=h: min(255, int(x) + lamb))(prob_img)
+    else:
+        shifted = np.minimum(255, prob_img.astype(np.float64) + h)
+    return reconstruction_erosion(shifted, prob_img).astype(np.ubyte)
+
+
+def _find_maxima(img, mask, literal=True):
+    """dist.py:60-71 with convertuint8=False, inverse=False."""
+    res = _h_reconstruction_erosion(img, 1, literal) - img
+    res[mask == 0] = 0
+    return res
+
+
+def _arrange_label(mat):
+    """dist.py:101-111: relabel with the most frequent value as background."""
+    val, counts = np.unique(mat, return_counts=True)
+    bg = val[np.argmax(counts)]
+    return sk_label(mat, background=bg)
+
+
+def _generate_wsl(ws):
+    """dist.py:83-98: 255 where the 3x3 window of a non-zero pixel holds >= 2 different
+    non-zero labels."""
+    se = square(3)
+    ero = ws.copy()
+    ero[ero == 0] = ero.max() + 1
+    ero = erosion(ero, se)
+    ero[ws == 0] = 0
+    grad = dilation(ws, se) - ero
+    grad[ws == 0] = 0
+    grad[grad > 0] = 255
+    return grad.astype(np.uint8)
+
+
+def dist_dynamic_watershed(p_img, lamb=0.0, p_thresh=0.5, literal=True):
+    """dist.py:114-129 ``dynamic_watershed_alias``."""
+    b_img = (p_img > p_thresh) + 0
+    probs_inv = 255 - p_img.astype(np.uint8)
+    hrecons = _h_reconstruction_erosion(probs_inv, lamb, literal)
+    markers = sk_label(_find_maxima(hrecons, b_img, literal))
+    ws = sk_watershed(hrecons, markers, mask=b_img)
+    arranged = _arrange_label(ws)
+    wsl = _generate_wsl(arranged)
+    arranged[wsl > 0] = 0
+    return arranged
+
+
+def dist_postprocess(sem_pred, dist_logit, literal=True):
+    """dist.py:275-284: clip to [0, 255], truncate to int32, dynamic watershed (lambda = 0.0,
+    threshold 0.5).  ``sem_pred`` passes through untouched."""
+    d = np.copy(dist_logit)
+    d[d > 255] = 255
+    d[d < 0] = 0
+    d = d.astype("int32")
+    return sem_pred, dist_dynamic_watershed(d, 0.0, 0.5, literal)
+
+
+# --------------------------------------------------------------------------- A11 HoVer-Net
+def hover_post_proc(fore_map, hv_map, fx=1, scale_factor=1):
+    """hovernet.py:283-365 with OpenCV / scipy called as the reference does."""
+    assert cv2 is not None, "OpenCV is required for the HoVer-Net oracle"
+    raw_h, raw_w = hv_map.shape[:2]
+    fore_map = cv2.resize(fore_map, (0, 0), fx=scale_factor, fy=scale_factor)
+    hv_map = cv2.resize(hv_map, (0, 0), fx=scale_factor, fy=scale_factor)
+    h_raw, v_raw = hv_map[:, :, 0], hv_map[:, :, 1]
+
+    blb = np.array(fore_map >= 0.5, dtype=np.int32)
+    blb = ndi.label(blb)[0]
+    blb = remove_small_objects(blb, min_size=10)
+    blb[blb > 0] = 1
+
+    def mm(x):
+        return cv2.normalize(x, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+
+    h_dir, v_dir = mm(h_raw), mm(v_raw)
+    ksize = int((20 * fx) + 1)
+    obj_size = math.ceil(10 * (fx ** 2))
+    sobelh = 1 - mm(cv2.Sobel(h_dir, cv2.CV_64F, 1, 0, ksize=ksize))
+    sobelv = 1 - mm(cv2.Sobel(v_dir, cv2.CV_64F, 0, 1, ksize=ksize))
+
+    overall = np.maximum(sobelh, sobelv)
+    overall = overall - (1 - blb)
+    overall[overall < 0] = 0
+    dist = (1.0 - overall) * blb
+    dist = -cv2.GaussianBlur(dist, (3, 3), 0)
+    overall = np.array(overall >= 0.4, dtype=np.int32)
+
+    marker = blb - overall
+    marker[marker < 0] = 0
+    marker = ndi.binary_fill_holes(marker).astype("uint8")
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5))
+    marker = cv2.morphologyEx(marker, cv2.MORPH_OPEN, kernel)
+    marker = ndi.label(marker)[0]
+    marker = remove_small_objects(marker, min_size=obj_size)
+    out = sk_watershed(dist, markers=marker, mask=blb)
+    out = cv2.resize(out, (raw_w, raw_h), interpolation=cv2.INTER_NEAREST)
+    return out, dict(blb=blb, dist=dist, marker=marker, overall=overall)
+
+
+# --------------------------------------------------------------------------- A12 CDNet DDM
+_DIR9 = np.array([[0, 0], [0, -1], [-1, -1], [-1, 0], [-1, 1], [0, 1], [1, 1], [1, 0], [1, -1]], np.float32)
+
+
+def direction_differential_map(dir_map, direction_classes=9):
+    """direct_diff_map.py:95-167 for 9 direction classes, fp32 arithmetic like the torch code:
+    label -> 2-vector, cosine similarity with the 8 circularly shifted neighbours, min over the 8,
+    background -> 1, ``1 - round``, min-max normalise (all-zero map returned as is)."""
+    assert direction_classes == 9
+    dm = np.asarray(dir_map)
+    va = _DIR9[dm]  # H, W, 2
+    a0, a1 = va[..., 0], va[..., 1]
+    shifts = [(1, 0), (1, 1), (0, 1), (-1, 1), (-1, 0), (-1, -1), (0, -1), (1, -1)]
+    na = np.sqrt(a0 * a0 + a1 * a1, dtype=np.float32)
+    best = None
+    for sv, sh in shifts:
+        f0 = np.roll(a0, (sv, sh), axis=(0, 1))
+        f1 = np.roll(a1, (sv, sh), axis=(0, 1))
+        num = a0 * f0 + a1 * f1
+        den = na * np.sqrt(f0 * f0 + f1 * f1, dtype=np.float32) + np.float32(0.000001)
+        c = (num / den).astype(np.float32)
+        best = c if best is None else np.minimum(best, c)
+    best[dm == 0] = 1
+    lv = (1 - np.round(best)).astype(np.float32)
+    mx, mn = lv.max(), lv.min()
+    if mx == 0:
+        return lv
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return ((lv - mn) / (mx - mn)).astype(np.float32)
+
+
+def cdnet_inference_tail(sem_logit_list, dir_logit_list, point_logit_list, if_ddm=True):
+    """cdnet.py:175-217 (after the CNN): softmax + TTA mean of sem; point mean; per variant
+    ``dir[:,0] *= sem[:,0]`` -> argmax -> DDM; mean DDM; optional ``_ddm_enhencement``
+    (cdnet.py:354-367).  Inputs are lists of [C,H,W] fp32 logits.  Returns (sem_prob[C,H,W],
+    dir_map of the first variant, dd_map)."""
+    sem = softmax_tta_mean(sem_logit_list)
+    point = None
+    for p in point_logit_list:
+        point = p.astype(np.float32) if point is None else (point + p).astype(np.float32)
+    point = (point / np.float32(len(point_logit_list))).astype(np.float32)
+    dd_sum, dir_maps = None, []
+    for dl in dir_logit_list:
+        d = softmax(dl, axis=0)
+        d[0] = d[0] * sem[0]
+        dir_map = np.argmax(d, axis=0)
+        dir_maps.append(dir_map)
+        dd = direction_differential_map(dir_map, 9)
+        dd_sum = dd if dd_sum is None else (dd_sum + dd).astype(np.float32)
+    dd_map = (dd_sum / np.float32(len(dir_logit_list))).astype(np.float32)
+    if if_ddm:
+        pl = point[0]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            point_map = (pl / pl.max()) > 0.2
+        dd2 = (dd_map - (dd_map * point_map.astype(np.float32))).astype(np.float32)
+        sem = sem.copy()
+        sem[-1] = ((sem[-1] + dd2).astype(np.float32) * (np.float32(1) + dd2)).astype(np.float32)
+    return sem, dir_maps[0], dd_map
+
+
+# --------------------------------------------------------------------------- A13 multi-task
+def multitask_postprocess(inner_pred, sem_pred, variant="unet"):
+    """multi_task_unet.py:84-106, multi_task_cunet.py:86-108 (variant 'cunet': tc map with edge
+    class 2 zeroed first, returns canvas), multi_task_cdnet.py:222-243 (variant 'cdnet': same but
+    returns the RAW sem_pred).  sem canvas: per class remove_small_objects(5) THEN
+    binary_fill_holes; instances: measure.label(connectivity=1) + align_foreground(.., 20)."""
+    canvas = np.zeros(sem_pred.shape, np.uint8)
+    for sem_id in np.unique(sem_pred):
+        if sem_id == 0:
+            continue
+        m = remove_small_objects(sem_pred == sem_id, 5)
+        m = ndi.binary_fill_holes(m)
+        canvas[m > 0] = sem_id
+    bin_pred = inner_pred.copy()
+    if variant in ("cunet", "cdnet"):
+        bin_pred[bin_pred == 2] = 0
+    inst = sk_label(bin_pred, connectivity=1)
+    inst = align_foreground(np.ascontiguousarray(inst), canvas > 0, 20)
+    return (sem_pred if variant == "cdnet" else canvas), inst
+
+
+warnings.filterwarnings("ignore", category=DeprecationWarning, module="scipy")

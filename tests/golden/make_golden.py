@@ -1,0 +1,184 @@
+"""Generate ``tests/golden/*.npz`` by running the REFERENCE's own code (authoring container only).
+
+Imports, by file path, the parts of /root/reference that load in this image:
+  tiseg/utils/misc.py + tiseg/utils/inst_metrics.py     (stub ``mmcv``; ``skimage.measure.label``
+                                                          replaced by an independent scipy-based
+                                                          labelling, since scikit-image is absent)
+  tiseg/utils/sem_metrics.py                             (stub ``mmcv``; real torch.histc)
+  tiseg/datasets/utils/instance_semantic.py              (stub ``skimage.morphology``)
+  tiseg/models/utils/postprocess.py                      (numba align_foreground)
+  tiseg/models/utils/direct_diff_map.py                  (torch, CPU)
+and stores seeded inputs together with the reference outputs.  /root/reference does not exist
+on the GPU box, so the tests only read the committed .npz files.
+
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+from scipy import ndimage as ndi
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+
+def scipy_label(img, background=0, connectivity=None, return_num=False):
+    """Independent stand-in for skimage.measure.label: per value, scipy binary labelling, then ids
+    renumbered in raster order of first pixel."""
+    img = np.asarray(img)
+    st = ndi.generate_binary_structure(2, 2 if connectivity in (None, 2) else 1)
+    comp = np.zeros(img.shape, np.int64)
+    nxt = 0
+    for v in np.unique(img):
+        if v == background:
+            continue
+        lab, k = ndi.label(img == v, st)
+        comp[lab > 0] = lab[lab > 0] + nxt
+        nxt += k
+    flat = comp.ravel()
+    nz = flat > 0
+    _, first = np.unique(flat[nz], return_index=True)
+    order = flat[nz][np.sort(first)]
+    lut = np.zeros(nxt + 1, np.int64)
+    lut[order] = np.arange(1, len(order) + 1)
+    out = lut[comp]
+    return (out, len(order)) if return_num else out
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def load_reference():
+    _stub("mmcv")
+    sk = _stub("skimage")
+    sk.measure = _stub("skimage.measure", label=scipy_label)
+    sk.morphology = _stub("skimage.morphology", remove_small_objects=None)
+    pkg = types.ModuleType("refutils")
+    pkg.__path__ = [os.path.join(REF, "tiseg", "utils")]
+    sys.modules["refutils"] = pkg
+
+    def load(modname, path, package=None):
+        spec = importlib.util.spec_from_file_location(modname, path)
+        mod = importlib.util.module_from_spec(spec)
+        if package:
+            mod.__package__ = package
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    misc = load("refutils.misc", os.path.join(REF, "tiseg/utils/misc.py"), "refutils")
+    inst = load("refutils.inst_metrics", os.path.join(REF, "tiseg/utils/inst_metrics.py"), "refutils")
+    sem = load("refutils.sem_metrics", os.path.join(REF, "tiseg/utils/sem_metrics.py"), "refutils")
+    isem = load("ref_instance_semantic", os.path.join(REF, "tiseg/datasets/utils/instance_semantic.py"))
+    pp = load("ref_postprocess", os.path.join(REF, "tiseg/models/utils/postprocess.py"))
+    ddm = load("ref_ddm", os.path.join(REF, "tiseg/models/utils/direct_diff_map.py"))
+    return misc, inst, sem, isem, pp, ddm
+
+
+def main():
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import synth
+
+    misc, inst, sem, isem, pp, ddm = load_reference()
+    import torch
+
+    # ---- instance metrics (binary) on seeded synthetic pairs + hand-made edge cases
+    cases = {}
+    shapes = [(64, 80), (96, 96), (128, 100), (256, 256)]
+    k = 0
+    for si, (H, W) in enumerate(shapes):
+        for j in range(3):
+            t = synth.gt_and_pred(9000 + 10 * si + j, H, W, n=max(3, H * W // 900), num_classes=4)
+            cases["c%d" % k] = (t["pred_inst"], t["gt_inst"], t["pred_sem"], t["gt_sem"])
+            k += 1
+    z = np.zeros((32, 32), np.int32)
+    a = z.copy(); a[4:12, 4:12] = 1; a[20:28, 20:30] = 7
+    b = z.copy(); b[6:14, 6:14] = 3; b[20:28, 18:26] = 3      # one pred id, two components
+    cases["c%d" % k] = (a, b, (a > 0).astype(np.uint8), (b > 0).astype(np.uint8)); k += 1
+    cases["c%d" % k] = (z, b, z.astype(np.uint8), (b > 0).astype(np.uint8)); k += 1      # empty pred
+    cases["c%d" % k] = (a, z, (a > 0).astype(np.uint8), z.astype(np.uint8)); k += 1      # empty gt
+    d1 = z.copy(); d1[5, 5] = 1; d1[6, 6] = 1; d1[10:14, 10:14] = 2; d1[14:18, 14:18] = 2  # diagonal touches
+    cases["c%d" % k] = (d1, a, (d1 > 0).astype(np.uint8), (a > 0).astype(np.uint8)); k += 1
+
+    out = {}
+    for name, (p, g, ps, gs) in cases.items():
+        out[name + "_pred"] = p.astype(np.int32)
+        out[name + "_gt"] = g.astype(np.int32)
+        out[name + "_pred_sem"] = ps.astype(np.uint8)
+        out[name + "_gt_sem"] = gs.astype(np.uint8)
+        aji = inst.pre_eval_bin_aji(p, g)
+        pq = inst.pre_eval_bin_pq(p, g)
+        out[name + "_bin_aji"] = np.array(aji, np.float64)
+        out[name + "_bin_pq"] = np.array(pq, np.float64)
+        # multi-class (CoNIC path): re_instance -> assign classes -> pre_eval_aji / pre_eval_pq
+        C = 4
+        rp, rg = isem.re_instance(p), isem.re_instance(g)
+        out[name + "_re_pred"] = rp
+        dp = isem.assign_sem_class_to_insts(rp, ps, C)
+        dg = isem.assign_sem_class_to_insts(rg, gs, C)
+        # flatten dicts as (class, id) rows in dict order
+        out[name + "_cls_pred"] = np.array([(c, i) for c, ids in dp.items() for i in ids], np.int64).reshape(-1, 2)
+        out[name + "_cls_gt"] = np.array([(c, i) for c, ids in dg.items() for i in ids], np.int64).reshape(-1, 2)
+        out[name + "_aji"] = np.stack(inst.pre_eval_aji(rp, rg, dp, dg, C))
+        out[name + "_pq"] = np.stack(inst.pre_eval_pq(rp, rg, dp, dg, C))
+        sres = sem.pre_eval_all_semantic_metric(ps, gs, C)
+        out[name + "_sem"] = np.stack([x.numpy() for x in sres])
+    gs_ign = cases["c0"][3].copy(); gs_ign[:5] = 255
+    out["ign_gt_sem"] = gs_ign
+    out["ign_sem"] = np.stack([x.numpy() for x in sem.pre_eval_all_semantic_metric(cases["c0"][2], gs_ign, 4)])
+    out["n_cases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "metrics_ref.npz"), **out)
+
+    # ---- reducers on the list of per-case results
+    names = ["c%d" % i for i in range(k)]
+    aji_list = [tuple(out[n + "_bin_aji"]) for n in names]
+    pq_list = [tuple(out[n + "_bin_pq"]) for n in names]
+    sem_list = [tuple(torch.from_numpy(r) for r in out[n + "_sem"]) for n in names]
+    red = dict(
+        to_aji=np.float64(inst.pre_eval_to_aji(aji_list)["Aji"]),
+        to_bin_aji=np.float64(inst.pre_eval_to_bin_aji(aji_list)["Aji"]),
+        to_imw_aji=inst.pre_eval_to_imw_aji(aji_list)["Aji"],
+        to_pq=np.array([inst.pre_eval_to_pq(pq_list)[m] for m in ("DQ", "SQ", "PQ")]),
+        to_bin_pq=np.array([inst.pre_eval_to_bin_pq(pq_list)[m] for m in ("DQ", "SQ", "PQ")]),
+        to_imw_pq=np.stack([inst.pre_eval_to_imw_pq(pq_list)[m] for m in ("DQ", "SQ", "PQ")]),
+        to_inst_dice=np.float64(inst.pre_eval_to_inst_dice(pq_list)["InstDice"]),
+        to_imw_inst_dice=inst.pre_eval_to_imw_inst_dice(pq_list)["InstDice"],
+    )
+    sm = sem.pre_eval_to_sem_metrics(sem_list, metrics=["Dice", "Precision", "Recall"])
+    red.update({"sem_" + m: sm[m] for m in sm})
+    im = sem.pre_eval_to_imw_sem_metrics(sem_list, metrics=["Dice", "Precision", "Recall"])
+    red.update({"imw_sem_" + m: im[m] for m in im})
+    np.savez_compressed(os.path.join(HERE, "reducers_ref.npz"), **red)
+
+    # ---- align_foreground (numba) and the direction differential map (torch)
+    out = {}
+    rng = np.random.default_rng(77)
+    for j, (H, W) in enumerate([(40, 52), (96, 96), (128, 160)]):
+        t = synth.gt_and_pred(9500 + j, H, W, n=max(3, H * W // 700))
+        fg = ndi.binary_dilation(t["pred_inst"] > 0, iterations=3) | (rng.random((H, W)) < 0.02)
+        seeds = np.where(ndi.binary_erosion(t["pred_inst"] > 0, iterations=2), t["pred_inst"], 0).astype(np.int64)
+        seeds = scipy_label(seeds, connectivity=1)
+        out["af%d_seed" % j] = seeds.copy()
+        out["af%d_fg" % j] = fg
+        out["af%d_out" % j] = pp.align_foreground(seeds.copy(), fg, 20)
+        out["af%d_out5" % j] = pp.align_foreground(seeds.copy(), fg, 5)
+        dl, _ = synth.direction_logits(np.random.default_rng(9600 + j), t["pred_inst"])
+        dm = np.argmax(dl, 0).astype(np.int64)
+        out["dd%d_dir" % j] = dm
+        out["dd%d_out" % j] = ddm.generate_direction_differential_map(torch.from_numpy(dm)[None], 9)[0].numpy()
+    zero = np.zeros((16, 16), np.int64)
+    out["dd_zero_out"] = ddm.generate_direction_differential_map(torch.from_numpy(zero)[None], 9)[0].numpy()
+    np.savez_compressed(os.path.join(HERE, "ordered_ref.npz"), **out)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

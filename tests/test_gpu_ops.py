@@ -1,0 +1,270 @@
+"""GPU parity tests: every operator of the C-ABI CUDA library against the CPU oracle (and scipy where the
+reference calls scipy directly) on seeded inputs.  Integer outputs must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+pytestmark = pytest.mark.gpu
+
+import tiseg_b200  # noqa: E402,F401
+from tiseg_b200 import ops, synth  # noqa: E402
+from oracle import metrics as om  # noqa: E402
+from oracle import postprocess as opp  # noqa: E402
+from oracle import skimage_port as sk  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+SHAPES = [(1, 1), (1, 40), (37, 1), (5, 33), (64, 64), (50, 97), (130, 257)]
+
+
+def _diff(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, "%s: shape %r vs %r" % (what, a.shape, b.shape)
+    bad = np.argwhere(a != b)
+    assert len(bad) == 0, "%s: %d mismatching elements, first at %r: got %r want %r" % (
+        what, len(bad), tuple(bad[0]), a[tuple(bad[0])], b[tuple(bad[0])])
+
+
+# --------------------------------------------------------------------------- CCL
+@pytest.mark.parametrize("conn", [1, 2])
+def test_label_binary(conn):
+    rng = np.random.default_rng(10 + conn)
+    for shape in SHAPES:
+        for dens in (0.15, 0.5, 0.62, 0.9):
+            m = (rng.random(shape) < dens).astype(np.uint8)
+            want, k = sk.label(m, connectivity=conn, return_num=True)
+            got, kk = ops.label(m, connectivity=conn, return_num=True)
+            _diff(got, want, "label %r dens %.2f conn %d" % (shape, dens, conn))
+            assert kk == k
+
+
+@pytest.mark.parametrize("conn", [1, 2])
+def test_label_equal_value_int32_batched(conn):
+    rng = np.random.default_rng(20 + conn)
+    imgs = rng.integers(0, 5, (6, 70, 101)).astype(np.int32)
+    for bg in (0, 3):
+        want = np.stack([sk.label(x, background=bg, connectivity=conn) for x in imgs])
+        got, cnt = ops.label(imgs, background=bg, connectivity=conn, return_num=True)
+        _diff(got, want, "batched equal-value label bg=%d" % bg)
+        _diff(cnt, want.reshape(6, -1).max(1), "label counts")
+
+
+def test_label_adversarial():
+    # spiral, checkerboard, comb: long union chains and many diagonal-only contacts
+    H = W = 96
+    spiral = np.zeros((H, W), np.uint8)
+    y = x = 0; dy, dx = 0, 1; lo_y, hi_y, lo_x, hi_x = 0, H - 1, 0, W - 1
+    for _ in range(H * W):
+        spiral[y, x] = 1
+        ny, nx = y + dy, x + dx
+        if not (lo_y <= ny <= hi_y and lo_x <= nx <= hi_x):
+            if (dy, dx) == (0, 1): lo_y += 2
+            elif (dy, dx) == (1, 0): hi_x -= 2
+            elif (dy, dx) == (0, -1): hi_y -= 2
+            else: lo_x += 2
+            dy, dx = dx, -dy
+            ny, nx = y + dy, x + dx
+            if not (lo_y - 0 <= ny <= hi_y and lo_x <= nx <= hi_x):
+                break
+        y, x = ny, nx
+    checker = (np.indices((H, W)).sum(0) % 2).astype(np.uint8)
+    comb = np.zeros((H, W), np.uint8); comb[::2, :] = 1; comb[:, 0] = 1
+    for name, m in (("spiral", spiral), ("checker", checker), ("comb", comb)):
+        for conn in (1, 2):
+            _diff(ops.label(m, connectivity=conn), sk.label(m, connectivity=conn), "%s conn %d" % (name, conn))
+
+
+def test_label_big_tile_and_device_pointers():
+    import torch
+    t = synth.gt_and_pred(77, 1000, 1000)
+    want = sk.label(t["pred_inst"])
+    got_host = ops.label(t["pred_inst"])
+    _diff(got_host, want, "1000^2 label (host buffers)")
+    dev = torch.from_numpy(t["pred_inst"]).cuda()
+    got_dev = ops.label(dev)
+    assert got_dev.is_cuda
+    _diff(got_dev.cpu().numpy(), want, "1000^2 label (device pointers)")
+
+
+def test_re_instance():
+    rng = np.random.default_rng(5)
+    img = rng.choice(np.array([0, 3, 9, 10, 500, 70000], np.int32), (3, 40, 50))
+    want = np.stack([om.re_instance(x) for x in img])
+    _diff(ops.re_instance(img), want, "re_instance")
+
+
+# --------------------------------------------------------------------------- morphology
+def test_fill_holes_remove_small_dilate():
+    rng = np.random.default_rng(30)
+    for shape in SHAPES:
+        for dens in (0.3, 0.55, 0.8):
+            m = rng.random(shape) < dens
+            _diff(ops.binary_fill_holes(m), ndi.binary_fill_holes(m).astype(np.uint8), "fill_holes %r %.2f" % (shape, dens))
+            for conn in (1, 2):
+                _diff(ops.remove_small_objects(m, 5, conn).astype(bool), opp.remove_small_objects(m, 5, conn),
+                      "remove_small_objects %r conn %d" % (shape, conn))
+            lab = sk.label(m).astype(np.int32)
+            _diff(ops.remove_small_objects(lab, 10), opp.remove_small_objects(lab, 10), "remove_small labels %r" % (shape,))
+            for r in (1, 2, 3):
+                _diff(ops.dilation(lab, "disk", r), opp.dilation(lab, opp.disk(r)), "dilation disk %d %r" % (r, shape))
+            _diff(ops.dilation(lab, "square", 1), opp.dilation(lab, opp.square(3)), "dilation square3 %r" % (shape,))
+            _diff(ops.erosion(lab, "square", 1), opp.erosion(lab, opp.square(3)), "erosion square3 %r" % (shape,))
+
+
+# --------------------------------------------------------------------------- A1
+def test_softmax_argmax():
+    rng = np.random.default_rng(40)
+    for (T, C, H, W) in [(1, 2, 33, 47), (3, 3, 64, 64), (8, 7, 40, 50), (2, 9, 31, 65)]:
+        lg = (rng.standard_normal((2, T, C, H, W)) * 3).astype(np.float32)
+        cls, prob = ops.softmax_argmax(lg, want_prob=True)
+        for n in range(2):
+            want_p = opp.softmax_tta_mean(list(lg[n]))
+            np.testing.assert_allclose(prob[n], want_p, rtol=1e-5, atol=1e-7)     # north_star: 1e-5 relative
+            want_c = opp.argmax_classes(want_p)
+            top2 = np.sort(want_p, axis=0)[-2:]
+            clear = (top2[1] - top2[0]) > 1e-6                                     # away from float ties
+            assert np.array_equal(cls[n][clear], want_c[clear].astype(np.uint8))
+            assert clear.mean() > 0.999
+
+
+# --------------------------------------------------------------------------- A2
+@pytest.mark.parametrize("C,radius,edge", [(2, 1, None), (4, 1, None), (3, 3, 2), (7, 1, None)])
+def test_postproc_unet(C, radius, edge):
+    for j, (H, W) in enumerate([(64, 80), (128, 100), (256, 256)]):
+        t = synth.gt_and_pred(3000 + 10 * C + j, H, W, num_classes=C)
+        pred = t["pred_sem"].copy()
+        if edge is not None:
+            pred = np.where(synth.three_class_map(t["pred_inst"]) == 2, edge, (t["pred_inst"] > 0) * 1).astype(np.uint8)
+        want_sem, want_inst = opp.unet_family_postprocess(pred.astype(np.int64), radius=radius, edge_id=edge)
+        got_sem, got_inst = ops.postproc_unet(pred.copy(), C - 1 if edge is None else edge, radius, edge)
+        _diff(got_inst, want_inst, "unet inst C=%d r=%d %dx%d" % (C, radius, H, W))
+        _diff(got_sem, want_sem, "unet sem C=%d r=%d %dx%d" % (C, radius, H, W))
+
+
+def test_postproc_unet_batched_and_dcan():
+    tiles = [synth.gt_and_pred(3100 + j, 96, 96, num_classes=3) for j in range(5)]
+    pred = np.stack([t["pred_sem"] for t in tiles])
+    got_sem, got_inst = ops.postproc_unet(pred.copy(), 2, 1)
+    for j in range(5):
+        ws, wi = opp.unet_family_postprocess(pred[j].astype(np.int64), radius=1)
+        _diff(got_inst[j], wi, "batched unet inst %d" % j)
+        _diff(got_sem[j], ws, "batched unet sem %d" % j)
+    cell = (tiles[0]["pred_inst"] > 0).astype(np.uint8)
+    cont = (synth.three_class_map(tiles[0]["pred_inst"]) == 2).astype(np.uint8)
+    ws, wi = opp.dcan_postprocess(cell.astype(np.int64), cont, radius=3)
+    gs, gi = ops.postproc_unet(cell.copy(), 1, 3, None, kill=cont)
+    _diff(gi, wi, "dcan inst")
+    _diff(gs, ws, "dcan sem")
+
+
+# --------------------------------------------------------------------------- A10
+def _random_ws_case(rng, H, W, levels, nmark):
+    img = ndi.uniform_filter(rng.random((H, W)), 5)
+    img = np.floor(img / img.max() * (levels - 1)).astype(np.uint8)
+    mk = np.zeros((H, W), np.int32)
+    ys, xs = rng.integers(0, H, nmark), rng.integers(0, W, nmark)
+    mk[ys, xs] = np.arange(1, nmark + 1)
+    mk = ndi.grey_dilation(mk, size=(2, 2))
+    mask = ndi.binary_opening(rng.random((H, W)) < 0.85, iterations=1) | (mk > 0)
+    return img, mk, mask.astype(np.uint8)
+
+
+def test_watershed_u8():
+    rng = np.random.default_rng(50)
+    for (H, W, levels, nmark) in [(1, 9, 3, 2), (20, 31, 4, 5), (64, 64, 8, 12), (100, 130, 256, 40), (128, 128, 2, 30)]:
+        img, mk, mask = _random_ws_case(rng, H, W, levels, nmark)
+        _diff(ops.watershed(img, mk, mask), sk.watershed(img, mk, mask), "watershed u8 masked %dx%d" % (H, W))
+        _diff(ops.watershed(img, mk), sk.watershed(img, mk), "watershed u8 unmasked %dx%d" % (H, W))
+
+
+def test_watershed_f64():
+    rng = np.random.default_rng(51)
+    for (H, W, nmark) in [(1, 9, 2), (20, 31, 5), (64, 64, 12), (100, 130, 40)]:
+        img, mk, mask = _random_ws_case(rng, H, W, 16, nmark)
+        f = -ndi.gaussian_filter(img.astype(np.float64), 1.0)
+        f[::3] = np.round(f[::3], 1)          # plateaus of equal doubles
+        _diff(ops.watershed(f, mk, mask), sk.watershed(f, mk, mask), "watershed f64 masked %dx%d" % (H, W))
+        _diff(ops.watershed(f, mk), sk.watershed(f, mk), "watershed f64 unmasked %dx%d" % (H, W))
+
+
+# --------------------------------------------------------------------------- A8
+@pytest.mark.parametrize("H,W,idx", [(120, 130, 3), (256, 256, 0), (256, 256, 1), (300, 517, 2)])
+def test_postproc_dist(H, W, idx):
+    t = synth.tile_dist(2, idx, H=H, W=W)
+    _, want = opp.dist_postprocess(None, t["dist_logit"], literal=False)
+    got, mk, ws = ops.postproc_dist(t["dist_logit"], debug=True)
+    # stage by stage, so a mismatch names the stage
+    d = np.clip(t["dist_logit"], 0, 255).astype("int32")
+    inv = 255 - d.astype(np.uint8)
+    want_mk = sk.label(opp._find_maxima(inv, (d > 0.5) + 0, literal=False))
+    _diff(mk, want_mk, "dist markers")
+    _diff(ws, sk.watershed(inv, want_mk, mask=(d > 0.5) + 0), "dist raw flood")
+    _diff(got, want, "dist inst")
+    assert got.max() > 3
+
+
+def test_postproc_dist_full_tile_and_batch():
+    tiles = [synth.tile_dist(2, j) for j in range(2)]
+    dist = np.stack([t["dist_logit"] for t in tiles])
+    got = ops.postproc_dist(dist)
+    for j in range(2):
+        _, want = opp.dist_postprocess(None, dist[j], literal=False)
+        _diff(got[j], want, "dist inst 1000^2 tile %d" % j)
+
+
+def test_postproc_dist_edge_cases():
+    z = np.zeros((40, 50), np.float32)
+    _diff(ops.postproc_dist(z), opp.dist_postprocess(None, z, literal=False)[1], "all-background dist")
+    full = np.full((40, 50), 7.3, np.float32)          # one plateau covering everything: bg becomes the label
+    _diff(ops.postproc_dist(full), opp.dist_postprocess(None, full, literal=False)[1], "all-foreground dist")
+    big = np.full((30, 30), 300.0, np.float32); big[0, 0] = -5
+    _diff(ops.postproc_dist(big), opp.dist_postprocess(None, big, literal=False)[1], "clipped dist")
+
+
+# --------------------------------------------------------------------------- A16 / A17 / A19
+def test_pair_metrics_golden():
+    mref = np.load(os.path.join(G, "metrics_ref.npz"))
+    for i in range(int(mref["n_cases"])):
+        n = "c%d" % i
+        aji, pq = ops.pair_metrics_bin(mref[n + "_pred"], mref[n + "_gt"])
+        assert tuple(aji) == tuple(mref[n + "_bin_aji"]), (n, aji, mref[n + "_bin_aji"])
+        assert tuple(pq) == tuple(mref[n + "_bin_pq"]), (n, pq, mref[n + "_bin_pq"])
+
+
+def test_pair_metrics_batched_vs_oracle():
+    tiles = [synth.gt_and_pred(6000 + j, 256, 256) for j in range(8)]
+    p = np.stack([t["pred_inst"] for t in tiles]); g = np.stack([t["gt_inst"] for t in tiles])
+    aji, pq = ops.pair_metrics_bin(p, g)
+    for j in range(8):
+        assert tuple(aji[j]) == tuple(np.float64(om.pre_eval_bin_aji(p[j], g[j], literal=False))), j
+        assert tuple(pq[j]) == tuple(np.float64(om.pre_eval_bin_pq(p[j], g[j], literal=False))), j
+
+
+def test_pair_metrics_full_tile_and_noise():
+    t = synth.gt_and_pred(6100, 1000, 1000)
+    aji, pq = ops.pair_metrics_bin(t["pred_inst"], t["gt_inst"])
+    assert tuple(aji) == tuple(np.float64(om.pre_eval_bin_aji(t["pred_inst"], t["gt_inst"], literal=False)))
+    assert tuple(pq) == tuple(np.float64(om.pre_eval_bin_pq(t["pred_inst"], t["gt_inst"], literal=False)))
+    # pathological: per-pixel random ids overflow the small pair table and take the retry path
+    rng = np.random.default_rng(1)
+    p = rng.integers(0, 400, (96, 96)).astype(np.int32); g = rng.integers(0, 400, (96, 96)).astype(np.int32)
+    aji, pq = ops.pair_metrics_bin(p, g)
+    assert tuple(aji) == tuple(np.float64(om.pre_eval_bin_aji(p, g, literal=False)))
+    assert tuple(pq) == tuple(np.float64(om.pre_eval_bin_pq(p, g, literal=False)))
+
+
+def test_sem_counts_golden():
+    mref = np.load(os.path.join(G, "metrics_ref.npz"))
+    C = 4
+    for i in range(int(mref["n_cases"])):
+        n = "c%d" % i
+        counts, valid = ops.sem_counts(mref[n + "_pred_sem"], mref[n + "_gt_sem"], C)
+        tp, fp, fn, pr, gt = (counts[k].astype(np.float32) for k in range(5))
+        tn = np.float32(valid) - (tp + fp + fn)
+        res = np.stack([tp, tn, fp, fn, pr, gt])[:, 1:]
+        assert np.array_equal(res, mref[n + "_sem"]), n
+    counts, valid = ops.sem_counts(mref["c0_pred_sem"], mref["ign_gt_sem"], C)
+    tp, fp, fn, pr, gt = (counts[k].astype(np.float32) for k in range(5))
+    res = np.stack([tp, np.float32(valid) - (tp + fp + fn), fp, fn, pr, gt])[:, 1:]
+    assert np.array_equal(res, mref["ign_sem"])

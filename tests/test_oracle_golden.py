@@ -1,0 +1,161 @@
+"""CPU suite: the oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py) and against independent scipy implementations."""
+import os
+
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+from oracle import metrics as om
+from oracle import postprocess as opp
+from oracle import skimage_port as sk
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def mref():
+    return np.load(os.path.join(G, "metrics_ref.npz"))
+
+
+def _cases(mref):
+    return ["c%d" % i for i in range(int(mref["n_cases"]))]
+
+
+def test_bin_aji_pq_match_reference(mref):
+    for n in _cases(mref):
+        p, g = mref[n + "_pred"], mref[n + "_gt"]
+        for literal in (True, False):
+            aji = om.pre_eval_bin_aji(p, g, literal=literal)
+            pq = om.pre_eval_bin_pq(p, g, literal=literal)
+            assert tuple(np.float64(aji)) == tuple(mref[n + "_bin_aji"]), n
+            assert tuple(np.float64(pq)) == tuple(mref[n + "_bin_pq"]), n
+
+
+def test_multiclass_aji_pq_match_reference(mref):
+    C = 4
+    for n in _cases(mref):
+        p, g = mref[n + "_pred"], mref[n + "_gt"]
+        ps, gs = mref[n + "_pred_sem"], mref[n + "_gt_sem"]
+        rp, rg = om.re_instance(p), om.re_instance(g)
+        assert np.array_equal(rp, mref[n + "_re_pred"]) and rp.dtype == np.int32
+        dp = om.assign_sem_class_to_insts(rp, ps, C)
+        dg = om.assign_sem_class_to_insts(rg, gs, C)
+        flat = np.array([(c, i) for c, ids in dp.items() for i in ids], np.int64).reshape(-1, 2)
+        assert np.array_equal(flat, mref[n + "_cls_pred"]), n
+        aji = np.stack(om.pre_eval_aji(rp, rg, dp, dg, C, literal=False))
+        pq = np.stack(om.pre_eval_pq(rp, rg, dp, dg, C, literal=False))
+        assert np.array_equal(aji, mref[n + "_aji"]), n
+        assert np.array_equal(pq, mref[n + "_pq"]), n
+
+
+def test_semantic_counts_match_reference(mref):
+    for n in _cases(mref):
+        res = np.stack(om.pre_eval_all_semantic_metric(mref[n + "_pred_sem"], mref[n + "_gt_sem"], 4))
+        assert np.array_equal(res, mref[n + "_sem"]), n
+    res = np.stack(om.pre_eval_all_semantic_metric(mref["c0_pred_sem"], mref["ign_gt_sem"], 4))
+    assert np.array_equal(res, mref["ign_sem"])
+
+
+def test_align_foreground_matches_numba_reference():
+    o = np.load(os.path.join(G, "ordered_ref.npz"))
+    for j in range(3):
+        for key, t in (("out", 20), ("out5", 5)):
+            got = sk.align_foreground(o["af%d_seed" % j].copy(), o["af%d_fg" % j], t)
+            assert np.array_equal(got, o["af%d_%s" % (j, key)])
+
+
+def test_ddm_matches_torch_reference():
+    o = np.load(os.path.join(G, "ordered_ref.npz"))
+    for j in range(3):
+        got = opp.direction_differential_map(o["dd%d_dir" % j], 9)
+        assert np.array_equal(got, o["dd%d_out" % j])
+    assert np.array_equal(opp.direction_differential_map(np.zeros((16, 16), np.int64), 9), o["dd_zero_out"])
+
+
+# ----------------------------------------------------------------- C restatement vs scipy
+def _canon(lab):
+    flat = lab.ravel()
+    nz = flat > 0
+    if not nz.any():
+        return lab.astype(np.int64)
+    vals, first = np.unique(flat[nz], return_index=True)
+    lut = np.zeros(int(flat.max()) + 1, np.int64)
+    lut[flat[nz][np.sort(first)]] = np.arange(1, len(vals) + 1)
+    return lut[lab]
+
+
+@pytest.mark.parametrize("conn", [1, 2])
+def test_label_binary_matches_scipy(conn):
+    rng = np.random.default_rng(conn)
+    for shape in [(1, 1), (1, 17), (23, 1), (37, 41), (64, 64)]:
+        for dens in (0.2, 0.5, 0.7):
+            m = rng.random(shape) < dens
+            ref, k = ndi.label(m, ndi.generate_binary_structure(2, conn))
+            got, kk = sk.label(m, connectivity=conn, return_num=True)
+            assert kk == k and np.array_equal(got, ref)
+
+
+def test_label_equal_value_and_background():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 4, (40, 50))
+    for bg in (0, 2):
+        got = sk.label(img, background=bg)
+        comp = np.zeros(img.shape, np.int64)
+        nxt = 0
+        for v in np.unique(img):
+            if v == bg:
+                continue
+            lab, k = ndi.label(img == v, np.ones((3, 3)))
+            comp[lab > 0] = lab[lab > 0] + nxt
+            nxt += k
+        assert np.array_equal(got, _canon(comp))
+
+
+def test_reconstruction_erosion_fixed_point():
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 256, (30, 33)).astype(np.float64)
+    seed = np.minimum(255, x + 7)
+    r = seed.copy()
+    for _ in range(200):
+        n = np.maximum(ndi.grey_erosion(r, size=(3, 3)), x)
+        if np.array_equal(n, r):
+            break
+        r = n
+    assert np.array_equal(sk.reconstruction_erosion(seed, x), r)
+
+
+def test_regional_minima_identity():
+    """find_maxima (dist.py:60-71) == 8-connected regional-minimum plateaus with value < 255."""
+    rng = np.random.default_rng(4)
+    x = ndi.uniform_filter(rng.integers(0, 256, (60, 70)).astype(np.float64), 5).astype(np.uint8)
+    x[:5] = 255
+    res = opp._find_maxima(x, np.ones_like(x), literal=False)
+    plate = sk.label(x.astype(np.int64) + 1, background=-1)
+    mn = ndi.grey_erosion(x, size=(3, 3))
+    has_lower = ndi.maximum(mn < x, plate, np.arange(1, plate.max() + 1)).astype(bool)
+    expect = (~has_lower[plate - 1]) & (x < 255)
+    assert np.array_equal(res.astype(bool), expect)
+
+
+def test_watershed_known_answers():
+    # two seeds on a flat image: BFS rings, ties resolved by (value, age): seed with lower index first
+    img = np.zeros((1, 7))
+    mk = np.zeros((1, 7), np.int32); mk[0, 0] = 1; mk[0, 6] = 2
+    assert sk.watershed(img, mk).tolist() == [[1, 1, 1, 1, 2, 2, 2]]
+    # a ridge keeps basins apart until both sides are flooded
+    img = np.array([[0, 1, 2, 9, 2, 1, 0]], np.float64)
+    assert sk.watershed(img, mk).tolist() == [[1, 1, 1, 1, 2, 2, 2]]
+    # mask stops the flood, markers outside the mask are dropped
+    msk = np.array([[1, 1, 0, 1, 1, 1, 0]], np.uint8)
+    assert sk.watershed(img, mk, msk).tolist() == [[1, 1, 0, 0, 0, 0, 0]]
+
+
+def test_literal_and_fast_dist_agree():
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import synth
+    t = synth.tile_dist(2, 3, H=120, W=130)
+    sp = opp.argmax_classes(opp.softmax(t["sem_logit"]))
+    a = opp.dist_postprocess(sp, t["dist_logit"], literal=True)[1]
+    b = opp.dist_postprocess(sp, t["dist_logit"], literal=False)[1]
+    assert np.array_equal(a, b) and a.max() > 3

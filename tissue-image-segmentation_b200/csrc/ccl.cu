@@ -1,0 +1,178 @@
+// K3 — connected-component labelling entry points (tiseg_label*, tiseg_re_instance) and the
+// non-template parts of the CCL toolbox declared in ccl.cuh.
+#include "ccl.cuh"
+
+namespace tiseg {
+
+__global__ void k_ccl_flatten(Geom g, int* par) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    int* tp = par + px.base;
+    int p = tp[px.idx];
+    if (p < 0) return;
+    int r = p;
+    for (int q = tp[r]; q != r; q = tp[r]) r = q;
+    if (r != p) tp[px.idx] = r;
+}
+
+__global__ void k_rank_scan(int bpt, int* blk, int* counts) {
+    __shared__ int s[256];
+    __shared__ int carry;
+    int* b = blk + (long long)blockIdx.x * bpt;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < bpt; base += 256) {
+        int i = base + threadIdx.x;
+        int v = i < bpt ? b[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            int t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int incl = s[threadIdx.x];
+        int c0 = carry;
+        if (i < bpt) b[i] = c0 + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c0 + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = carry;
+}
+
+__global__ void k_apply_rank(Geom g, const int* __restrict__ par,
+                                                              const int* __restrict__ rank, int32_t* __restrict__ out) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    int p = par[px.base + px.idx];
+    out[px.base + px.idx] = p >= 0 ? rank[px.base + p] : 0;
+}
+
+// area[root] += length of each in-segment run of pixels sharing the root (one atomic per run)
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* __restrict__ par, int* area) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    int p = px.ok ? par[px.base + px.idx] : -1;
+    int pl = __shfl_up_sync(0xffffffffu, p, 1);
+    bool cont = px.lane > 0 && p >= 0 && pl == p;
+    unsigned m = __ballot_sync(0xffffffffu, cont);
+    if (p >= 0 && !cont) {
+        int len = run_end_lane(m, px.lane) - px.lane + 1;
+        atomicAdd(&area[px.base + p], len);
+    }
+}
+
+int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
+    TISEG_LAUNCH(c, k_ccl_flatten, warp_grid(g), TISEG_THREADS, 0, g, par);
+    return TISEG_OK;
+}
+
+int rank_scan(tiseg_ctx* c, int N, int bpt, int* blk, int* counts) {
+    TISEG_LAUNCH(c, k_rank_scan, N, 256, 0, bpt, blk, counts);
+    return TISEG_OK;
+}
+
+int rank_roots(tiseg_ctx* c, const Geom& g, const int* par, int* rank, int* counts) {
+    return rank_generic(c, g, SelRoot{par}, rank, counts);
+}
+
+int apply_rank(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, int32_t* out) {
+    TISEG_LAUNCH(c, k_apply_rank, warp_grid(g), TISEG_THREADS, 0, g, par, rank, out);
+    return TISEG_OK;
+}
+
+int ccl_areas(tiseg_ctx* c, const Geom& g, const int* par, int* area) {
+    TISEG_TRY(zero(c, area, (size_t)g.N * g.P * sizeof(int)));
+    TISEG_LAUNCH(c, k_ccl_areas, warp_grid(g), TISEG_THREADS, 0, g, par, area);
+    return TISEG_OK;
+}
+
+// ---- re_instance: ranks of the distinct non-zero values (instance_semantic.py:5-15) -----------------
+// first[n, v] = 1 if value v occurs; rank over the value axis.  Values must be < vmax.
+__global__ void k_mark_values(Geom g, const int32_t* __restrict__ img, uint8_t* seen, int vmax, int* bad) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    int v = img[px.base + px.idx];
+    if (v == 0) return;
+    if (v < 0 || v >= vmax) { *bad = 1; return; }
+    seen[(long long)px.n * vmax + v] = 1;
+}
+__global__ void k_lookup_values(Geom g, const int32_t* __restrict__ img, const int* __restrict__ vr, int vmax,
+                                int32_t* __restrict__ out) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    int v = img[px.base + px.idx];
+    out[px.base + px.idx] = (v > 0 && v < vmax) ? vr[(long long)px.n * vmax + v] : 0;
+}
+
+}  // namespace tiseg
+
+using namespace tiseg;
+
+extern "C" {
+
+int tiseg_label(tiseg_ctx* c, const int32_t* img, int N, int H, int W, int32_t background, int connectivity,
+                int32_t* out, int32_t* count) {
+    if (!c || !img || !out || (connectivity != 1 && connectivity != 2)) { set_error("tiseg_label: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const int32_t* d_img = in(c, img, total);
+    int32_t* d_out = tiseg::out(c, out, total);
+    int32_t* d_cnt = count ? tiseg::out(c, count, (size_t)N) : nullptr;
+    if (!d_img || !d_out) return TISEG_ERR_CUDA;
+    TISEG_TRY(ccl_label(c, g, ImgEqI32{d_img, background}, connectivity, d_out, d_cnt));
+    return end_call(c);
+}
+
+int tiseg_label_u8(tiseg_ctx* c, const uint8_t* img, int N, int H, int W, int32_t background, int connectivity,
+                   int32_t* out, int32_t* count) {
+    if (!c || !img || !out || (connectivity != 1 && connectivity != 2)) { set_error("tiseg_label_u8: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const uint8_t* d_img = in(c, img, total);
+    int32_t* d_out = tiseg::out(c, out, total);
+    int32_t* d_cnt = count ? tiseg::out(c, count, (size_t)N) : nullptr;
+    if (!d_img || !d_out) return TISEG_ERR_CUDA;
+    TISEG_TRY(ccl_label(c, g, ImgEqU8{d_img, background}, connectivity, d_out, d_cnt));
+    return end_call(c);
+}
+
+int tiseg_re_instance(tiseg_ctx* c, const int32_t* img, int N, int H, int W, int32_t* out, int32_t* count) {
+    if (!c || !img || !out) { set_error("tiseg_re_instance: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const int32_t* d_img = in(c, img, total);
+    int32_t* d_out = tiseg::out(c, out, total);
+    int32_t* d_cnt = count ? tiseg::out(c, count, (size_t)N) : nullptr;
+    if (!d_img || !d_out) return TISEG_ERR_CUDA;
+    // value axis: ids are bounded by a generous multiple of the pixel count (instance ids never exceed it
+    // in the reference's datasets); larger ids are reported as an argument error rather than mis-ranked
+    int vmax = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;
+    uint8_t* seen = ws<uint8_t>(c, (size_t)N * vmax);
+    int* vr = ws<int>(c, (size_t)N * vmax);
+    int* bad = ws<int>(c, 1);
+    if (!seen || !vr || !bad) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, seen, (size_t)N * vmax));
+    TISEG_TRY(zero(c, bad, sizeof(int)));
+    TISEG_LAUNCH(c, k_mark_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, seen, vmax, bad);
+    // rank over the value axis: reuse the raster-rank machinery on a [N, 1, vmax] "image"
+    Geom gv = make_geom(N, 1, vmax);
+    TISEG_TRY(rank_generic(c, gv, SelFlagU8{seen}, vr, d_cnt));
+    TISEG_LAUNCH(c, k_lookup_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, vr, vmax, d_out);
+    int hbad = 0;
+    TISEG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TISEG_TRY(end_call(c));
+    TISEG_CHECK(cudaStreamSynchronize(c->stream));
+    if (hbad) { set_error("tiseg_re_instance: instance id out of the supported range"); return TISEG_ERR_LIMIT; }
+    return TISEG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// tiseg_b200 — shared device/host plumbing for the sm_100a kernels of the test-time instance pipeline.
+//
+// Layout convention (every kernel): a BATCH of tiles [N, H, W], C-contiguous, row pitch = W elements.
+// Class maps / masks are uint8, label maps int32, float maps fp32 / fp64.  One warp owns a 32-pixel
+// horizontal segment of one row (coalesced 128-byte int32 or 32-byte uint8 requests); the warp-level
+// run primitives (ballot / clz) below are what the CCL, histogram and area kernels build on.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tiseg_b200.h"
+
+#define TISEG_WARPS_PER_BLOCK 8
+#define TISEG_THREADS (32 * TISEG_WARPS_PER_BLOCK)
+
+struct tiseg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // device arena: list of blocks, bump-allocated per call, coalesced between calls
+    struct Block { char* p; size_t cap; };
+    std::vector<Block> blocks;
+    size_t cur_block = 0, cur_off = 0, call_total = 0;
+    // pending device->host copies of the current call
+    struct Pending { void* host; const void* dev; size_t bytes; };
+    std::vector<Pending> pending;
+    long long launches = 0;
+    int sm_count = 148;
+};
+
+namespace tiseg {
+
+void set_error(const std::string& msg);
+int fail(const char* where, cudaError_t e);
+
+// ---- call-scoped workspace -------------------------------------------------------------------
+void begin_call(tiseg_ctx* c);
+int end_call(tiseg_ctx* c);                       // flush pending D2H, sync if any host output
+void* ws_alloc(tiseg_ctx* c, size_t bytes);       // 256-byte aligned device scratch, valid until end_call
+bool is_device_ptr(const void* p);
+// input: device pointer returned as is; host pointer staged to the arena with an async H2D
+const void* in_ptr(tiseg_ctx* c, const void* p, size_t bytes);
+// output: device pointer returned as is; host pointer gets arena scratch + a pending D2H
+void* out_ptr(tiseg_ctx* c, void* p, size_t bytes);
+// in/out (mutated in place by the reference): staged in, copied back
+void* inout_ptr(tiseg_ctx* c, void* p, size_t bytes);
+
+template <class T> inline T* ws(tiseg_ctx* c, size_t n) { return (T*)ws_alloc(c, n * sizeof(T)); }
+template <class T> inline const T* in(tiseg_ctx* c, const T* p, size_t n) { return (const T*)in_ptr(c, p, n * sizeof(T)); }
+template <class T> inline T* out(tiseg_ctx* c, T* p, size_t n) { return p ? (T*)out_ptr(c, p, n * sizeof(T)) : nullptr; }
+
+int zero(tiseg_ctx* c, void* p, size_t bytes);
+
+#define TISEG_CHECK(expr)                                                \
+    do {                                                                 \
+        cudaError_t _e = (expr);                                         \
+        if (_e != cudaSuccess) return ::tiseg::fail(#expr, _e);          \
+    } while (0)
+
+#define TISEG_TRY(expr)                 \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != TISEG_OK) return _s;  \
+    } while (0)
+
+// launch + count + error check.  Usage: TISEG_LAUNCH(c, kernel, grid, block, smem, args...)
+#define TISEG_LAUNCH(c, kern, grid, block, smem, ...)                                 \
+    do {                                                                              \
+        kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                  \
+        (c)->launches++;                                                              \
+        cudaError_t _e = cudaGetLastError();                                          \
+        if (_e != cudaSuccess) return ::tiseg::fail(#kern, _e);                       \
+    } while (0)
+
+// ---- geometry: one warp per 32-pixel row segment, blocks never straddle two tiles ----------------
+struct Geom {
+    int N, H, W, SEG;          // SEG = ceil(W / 32)
+    int P;                     // H * W  (< 2^31: tile-local flat indices are int)
+    int wpt;                   // warps per tile = H * SEG
+    int bpt;                   // blocks per tile = ceil(wpt / 8)
+};
+inline Geom make_geom(int N, int H, int W) {
+    Geom g; g.N = N; g.H = H; g.W = W; g.SEG = (W + 31) / 32; g.P = H * W;
+    g.wpt = H * g.SEG; g.bpt = (g.wpt + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK; return g;
+}
+inline dim3 warp_grid(const Geom& g) { return dim3((unsigned)g.bpt, (unsigned)g.N, 1); }
+inline unsigned flat_grid(long long n, int per_block = TISEG_THREADS) { return (unsigned)((n + per_block - 1) / per_block); }
+inline int check_geom(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0 || N > 65535 || (long long)H * W >= (1ll << 30)) {
+        set_error("bad tile geometry (need 1 <= N <= 65535, H*W < 2^30)");
+        return TISEG_ERR_ARG;
+    }
+    return TISEG_OK;
+}
+
+#ifdef __CUDACC__
+struct Pix {
+    int n, y, x;               // tile, row, column (x may be >= W on the ragged last segment)
+    long long base;            // n * P
+    int idx;                   // y * W + x  (tile-local flat index)
+    int lane;
+    bool ok;                   // x < W
+};
+// returns false if this warp has no work (uniform across the warp)
+__device__ __forceinline__ bool warp_pixel(const Geom& g, Pix& p) {
+    int w = blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    p.lane = threadIdx.x & 31;
+    if (w >= g.wpt) return false;
+    p.n = blockIdx.y;
+    p.y = w / g.SEG;
+    p.x = (w - p.y * g.SEG) * 32 + p.lane;
+    p.ok = p.x < g.W;
+    p.base = (long long)p.n * g.P;
+    p.idx = p.y * g.W + p.x;
+    return true;
+}
+
+// Given the ballot of "this lane continues the run of the lane to its left" (bit 0 of the segment may be
+// set when the run continues from the previous segment), the lane at which my run starts inside the segment.
+__device__ __forceinline__ int run_start_lane(unsigned cont, int lane) {
+    unsigned brk = ~cont & (0xffffffffu >> (31 - lane));   // lanes <= me that start a run
+    return brk ? 31 - __clz(brk) : 0;
+}
+// number of lanes in my run from its start (inside the segment) to its end, valid at any lane of the run
+__device__ __forceinline__ int run_end_lane(unsigned cont, int lane) {
+    unsigned brk = ~cont & ~(0xffffffffu >> (31 - lane));  // lanes > me that start a run
+    return brk ? (__ffs(brk) - 1) - 1 : 31;
+}
+
+// (no __restrict__/const: parents are updated concurrently, loads must stay coherent)
+__device__ __forceinline__ int uf_find(int* par, int x) {
+    int p = par[x];
+    while (p != x) { x = p; p = par[x]; }
+    return x;
+}
+// union by minimum index: the root of a component is its lowest flat index (= first pixel in raster order)
+__device__ __forceinline__ void uf_union(int* par, int a, int b) {
+    for (;;) {
+        a = uf_find(par, a);
+        b = uf_find(par, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }      // a > b: hang a under b
+        int old = atomicMin(&par[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+#endif
+
+}  // namespace tiseg

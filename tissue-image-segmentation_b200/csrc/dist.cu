@@ -1,0 +1,189 @@
+// A8 — DIST postprocess: tiseg/models/segmentors/dist.py:275-284 -> dynamic_watershed_alias (:114-129)
+// with prepare_prob (:31-40), H_reconstruction_erosion (:43-57; lambda = 0.0 => identity), find_maxima
+// (:60-71), arrange_label (:101-111) and generate_wsl (:83-98).
+//
+//   d  = int32(clip(dist, 0, 255))             (truncation)             k_dist_prep
+//   I  = 255 - uint8(d);  b = d > 0.5  <=>  I < 255
+//   markers = label(recon_by_erosion(min(255, I+1), I) - I, masked by b)
+//           = 8-connected regional-minimum plateaus of I with value < 255, raster ids
+//                                                                       plateau CCL + k_plateau_lower + rank
+//   ws = watershed(I, markers, mask=b)                                   K6 (bucket flood)
+//   arranged = label(ws, background = most frequent value of ws)         k_ws_hist + k_pick_bg + CCL
+//   arranged[3x3 window holds >= 2 different non-zero labels] = 0        k_wsl_remove
+#include "ccl.cuh"
+#include "watershed.cuh"
+
+namespace tiseg {
+
+__global__ void k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    float d = dist[px.base + px.idx];
+    if (d > 255.f) d = 255.f;          // dist.py:277-278 (comparisons are false for NaN, like numpy)
+    if (d < 0.f) d = 0.f;
+    int t = (int)d;                    // astype('int32'): truncation
+    I[px.base + px.idx] = (uint8_t)(255 - (t & 255));
+}
+
+// low[root] = 1 if any pixel of the plateau has a strictly lower 8-neighbour
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_plateau_lower(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ par, uint8_t* low) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const uint8_t* t = I + px.base;
+    int v = t[px.idx];
+    bool lower = false;
+    for (int dy = -1; dy <= 1; ++dy) {
+        int yy = px.y + dy;
+        if (yy < 0 || yy >= g.H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int xx = px.x + dx;
+            if (xx < 0 || xx >= g.W) continue;
+            lower |= t[yy * g.W + xx] < v;
+        }
+    }
+    if (lower) {
+        int r = par[px.base + px.idx];
+        if (!low[px.base + r]) low[px.base + r] = 1;
+    }
+}
+
+struct SelMinimumRoot {         // roots of regional-minimum plateaus with value < 255
+    const int* par; const uint8_t* I; const uint8_t* low;
+    __device__ __forceinline__ bool operator()(long long gi, int idx) const {
+        return par[gi] == idx && I[gi] < 255 && !low[gi];
+    }
+};
+
+__global__ void k_markers_from_plateaus(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ par,
+                                        const uint8_t* __restrict__ low, const int* __restrict__ rank,
+                                        int32_t* __restrict__ markers) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    long long i = px.base + px.idx;
+    long long r = px.base + par[i];
+    markers[i] = (I[i] < 255 && !low[r]) ? rank[r] : 0;
+}
+
+// histogram of the flood labels (values 0..K), one atomic per in-segment run
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int KS) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    int v = px.ok ? ws[px.base + px.idx] : -1;
+    int vl = __shfl_up_sync(0xffffffffu, v, 1);
+    bool cont = px.lane > 0 && v == vl;
+    unsigned m = __ballot_sync(0xffffffffu, cont);
+    if (v >= 0 && !cont) atomicAdd(&hist[(long long)px.n * KS + v], run_end_lane(m, px.lane) - px.lane + 1);
+}
+
+__global__ void k_zero_prefix_i32(int* a, int KS, const int* __restrict__ counts) {
+    int n = blockIdx.y;
+    int k = counts[n];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= k; i += gridDim.x * blockDim.x) a[(long long)n * KS + i] = 0;
+}
+
+// arrange_label's background: np.unique(return_counts) + argmax => the most frequent value, smallest value on ties
+__global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int* bg) {
+    __shared__ unsigned long long s[256];
+    int n = blockIdx.x;
+    int k = counts[n];
+    // key = (count << 32) | (0xffffffff - value): max key = largest count, then smallest value
+    unsigned long long best = 0;
+    for (int v = threadIdx.x; v <= k; v += blockDim.x) {
+        unsigned long long key = ((unsigned long long)(unsigned)hist[(long long)n * KS + v] << 32) | (0xffffffffu - (unsigned)v);
+        if (key > best) best = key;
+    }
+    s[threadIdx.x] = best;
+    __syncthreads();
+    for (int d = 128; d; d >>= 1) {
+        if (threadIdx.x < d && s[threadIdx.x + d] > s[threadIdx.x]) s[threadIdx.x] = s[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bg[n] = (int)(0xffffffffu - (unsigned)(s[0] & 0xffffffffu));
+}
+
+// generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_wsl_remove(Geom g, const int32_t* __restrict__ lab, int32_t* __restrict__ out) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const int32_t* t = lab + px.base;
+    int v = t[px.idx];
+    bool line = false;
+    if (v != 0) {
+        for (int dy = -1; dy <= 1; ++dy) {
+            int yy = px.y + dy;
+            if (yy < 0 || yy >= g.H) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                int xx = px.x + dx;
+                if (xx < 0 || xx >= g.W) continue;
+                int u = t[yy * g.W + xx];
+                line |= (u != 0 && u != v);
+            }
+        }
+    }
+    out[px.base + px.idx] = line ? 0 : v;
+}
+
+int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* inst, int32_t* markers_out,
+                      int32_t* ws_out) {
+    int N = g.N, KS = g.P + 1;
+    size_t total = (size_t)N * g.P;
+    uint8_t* I = ws<uint8_t>(c, total);
+    uint8_t* low = ws<uint8_t>(c, total);
+    int* par = ws<int>(c, total);
+    int* rank = ws<int>(c, total);
+    int* bpar = ws<int>(c, total);
+    int* brank = ws<int>(c, total);
+    int32_t* markers = markers_out ? markers_out : ws<int32_t>(c, total);
+    int32_t* wsl = ws_out ? ws_out : ws<int32_t>(c, total);
+    int32_t* arranged = ws<int32_t>(c, total);
+    int* nmark = ws<int>(c, (size_t)N);
+    int* bg = ws<int>(c, (size_t)N);
+    int* hist = ws<int>(c, (size_t)N * KS);
+    if (!I || !low || !par || !rank || !bpar || !brank || !markers || !wsl || !arranged || !nmark || !bg || !hist) return TISEG_ERR_CUDA;
+
+    TISEG_LAUNCH(c, k_dist_prep, warp_grid(g), TISEG_THREADS, 0, g, dist, I);
+    // markers: regional-minimum plateaus (8-connected, equal value) of I below 255
+    TISEG_TRY(ccl_build(c, g, ImgEqU8{I, -1}, 2, par));
+    TISEG_TRY(zero(c, low, total));
+    TISEG_LAUNCH(c, k_plateau_lower, warp_grid(g), TISEG_THREADS, 0, g, I, par, low);
+    TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, I, low}, rank, nmark));
+    TISEG_LAUNCH(c, k_markers_from_plateaus, warp_grid(g), TISEG_THREADS, 0, g, I, par, low, rank, markers);
+    // flood inside b = (I < 255), blob by blob
+    BlobInfo b;
+    TISEG_TRY(blobs_build(c, g, ImgBelowU8{I, 255}, bpar, brank, b, false));
+    TISEG_TRY(ws_seed(c, g, markers, bpar, wsl));
+    TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
+    // arrange_label
+    TISEG_LAUNCH(c, k_zero_prefix_i32, dim3(8, N), 256, 0, hist, KS, nmark);
+    TISEG_LAUNCH(c, k_ws_hist, warp_grid(g), TISEG_THREADS, 0, g, wsl, hist, KS);
+    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, bg);
+    TISEG_TRY(ccl_build(c, g, ImgEqI32TileBg{wsl, bg}, 2, par));
+    TISEG_TRY(rank_roots(c, g, par, rank, nullptr));
+    TISEG_TRY(apply_rank(c, g, par, rank, arranged));
+    // watershed lines
+    TISEG_LAUNCH(c, k_wsl_remove, warp_grid(g), TISEG_THREADS, 0, g, arranged, inst);
+    return TISEG_OK;
+}
+
+}  // namespace tiseg
+
+using namespace tiseg;
+
+extern "C" int tiseg_postproc_dist(tiseg_ctx* c, const float* dist, int N, int H, int W, int32_t* inst_out,
+                                   int32_t* markers_out, int32_t* ws_out) {
+    if (!c || !dist || !inst_out) { set_error("tiseg_postproc_dist: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const float* d_dist = in(c, dist, total);
+    int32_t* d_inst = tiseg::out(c, inst_out, total);
+    int32_t* d_mk = markers_out ? tiseg::out(c, markers_out, total) : nullptr;
+    int32_t* d_ws = ws_out ? tiseg::out(c, ws_out, total) : nullptr;
+    if (!d_dist || !d_inst) return TISEG_ERR_CUDA;
+    TISEG_TRY(postproc_dist_dev(c, g, d_dist, d_inst, d_mk, d_ws));
+    return end_call(c);
+}

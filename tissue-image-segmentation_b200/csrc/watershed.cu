@@ -1,0 +1,358 @@
+// K6 — ordered marker-controlled watershed: blob bookkeeping, the uint8 bucket flood, the fp64 heap flood
+// and the tiseg_watershed_* entry points.  See watershed.cuh for the algorithm statement.
+#include "watershed.cuh"
+
+namespace tiseg {
+
+#define FULL 0xffffffffu
+
+__global__ void k_blob_init(BlobInfo b, int W) {
+    int n = blockIdx.y;
+    long long o = (long long)n * b.KS;
+    int k = b.count[n];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= k; i += gridDim.x * blockDim.x) {
+        b.root[o + i] = 0; b.ymax[o + i] = -1; b.xmin[o + i] = W; b.xmax[o + i] = -1; b.area[o + i] = 0;
+    }
+}
+
+__global__ void k_blob_roots(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    if (par[px.base + px.idx] == px.idx) b.root[(long long)px.n * b.KS + rank[px.base + px.idx]] = px.idx;
+}
+
+// bounding box + area per blob, one set of atomics per in-segment run
+__global__ void k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    int p = px.ok ? par[px.base + px.idx] : -1;
+    int pl = __shfl_up_sync(FULL, p, 1);
+    bool cont = px.lane > 0 && p >= 0 && pl == p;
+    unsigned m = __ballot_sync(FULL, cont);
+    if (p >= 0 && !cont) {
+        int end = run_end_lane(m, px.lane);
+        long long o = (long long)px.n * b.KS + rank[px.base + p];
+        atomicMax(&b.ymax[o], px.y);
+        atomicMin(&b.xmin[o], px.x);
+        atomicMax(&b.xmax[o], px.x + (end - px.lane));
+        atomicAdd(&b.area[o], end - px.lane + 1);
+    }
+}
+
+// off[1..B] = exclusive prefix sum of area[1..B]
+__global__ void k_blob_offsets(BlobInfo b) {
+    __shared__ int s[256];
+    __shared__ int carry;
+    int n = blockIdx.x;
+    long long o = (long long)n * b.KS;
+    int k = b.count[n];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 1; base <= k; base += 256) {
+        int i = base + threadIdx.x;
+        int v = i <= k ? b.area[o + i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            int t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int incl = s[threadIdx.x];
+        int c0 = carry;
+        if (i <= k) b.off[o + i] = c0 + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c0 + incl;
+        __syncthreads();
+    }
+}
+
+// out = markers * mask (skimage: markers outside the mask are dropped)
+__global__ void k_ws_seed(Geom g, const int32_t* __restrict__ markers, const int* __restrict__ par, int32_t* __restrict__ out) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    long long i = px.base + px.idx;
+    out[i] = par[i] >= 0 ? markers[i] : 0;
+}
+
+// ---- uint8 levels: 256 FIFO buckets --------------------------------------------------------------------
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, int* queue,
+              int* next, int32_t* out) {
+    __shared__ int s_head[TISEG_WARPS_PER_BLOCK][256];
+    __shared__ int s_tail[TISEG_WARPS_PER_BLOCK][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int B = b.count[n];
+    const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+    const uint8_t* I = image + base;
+    const int* tp = par + base;
+    int32_t* o = out + base;
+    int* nx = next + base;
+    int* head = s_head[warp];
+    int* tail = s_tail[warp];
+    const int W = g.W, H = g.H;
+    for (;;) {
+        int bid = 0;
+        if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
+        bid = __shfl_sync(FULL, bid, 0);
+        if (bid > B) break;
+        for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
+        __syncwarp();
+        const int root = b.root[ko + bid];
+        const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+        int cur = 256;
+        // seeds in raster order: all have age 0, ties inside a level resolved by flat index
+        for (int y = y0; y <= y1; ++y) {
+            for (int xb = x0; xb <= x1; xb += 32) {
+                int x = xb + lane;
+                bool seed = false;
+                int lv = 0;
+                if (x <= x1) {
+                    int idx = y * W + x;
+                    if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
+                }
+                unsigned m = __ballot_sync(FULL, seed);
+                while (m) {
+                    int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    int slv = __shfl_sync(FULL, lv, src);
+                    if (lane == 0) {
+                        int pix = y * W + xb + src;
+                        nx[pix] = -1;
+                        int t = tail[slv];
+                        if (t < 0) head[slv] = pix; else nx[t] = pix;
+                        tail[slv] = pix;
+                        if (slv < cur) cur = slv;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            for (;;) {
+                while (cur < 256 && head[cur] < 0) ++cur;
+                if (cur >= 256) break;
+                const int pix = head[cur];
+                const int nxt = nx[pix];
+                head[cur] = nxt;
+                if (nxt < 0) tail[cur] = -1;
+                const int lab = o[pix];
+                const int y = pix / W, x = pix - y * W;
+                const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};          // up, left, right, down
+                const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
+                int pv[4], ov[4], lv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pv[k] = -1; ov[k] = 1; lv[k] = 0;
+                    if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (pv[k] >= 0 && ov[k] == 0) {
+                        o[nb[k]] = lab;                                           // labelled at push time
+                        nx[nb[k]] = -1;
+                        int t = tail[lv[k]];
+                        if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
+                        tail[lv[k]] = nb[k];
+                        if (lv[k] < cur) cur = lv[k];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- fp64 values: binary heap keyed (value, age, index) -------------------------------------------------
+struct __align__(16) HeapItem { double v; unsigned age; int idx; };
+
+__device__ __forceinline__ bool heap_less(const HeapItem& a, const HeapItem& b) {
+    if (a.v != b.v) return a.v < b.v;
+    if (a.age != b.age) return a.age < b.age;
+    return a.idx < b.idx;
+}
+__device__ __forceinline__ void heap_push(HeapItem* h, int& sz, HeapItem it) {
+    int i = sz++;
+    while (i > 0) {
+        int p = (i - 1) >> 1;
+        HeapItem hp = h[p];
+        if (!heap_less(it, hp)) break;
+        h[i] = hp;
+        i = p;
+    }
+    h[i] = it;
+}
+__device__ __forceinline__ HeapItem heap_pop(HeapItem* h, int& sz) {
+    HeapItem top = h[0];
+    HeapItem last = h[--sz];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1;
+        if (l >= sz) break;
+        HeapItem c = h[l];
+        if (l + 1 < sz) {
+            HeapItem r = h[l + 1];
+            if (heap_less(r, c)) { c = r; l = l + 1; }
+        }
+        if (!heap_less(c, last)) break;
+        h[i] = c;
+        i = l;
+    }
+    if (sz > 0) h[i] = last;
+    return top;
+}
+
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ws_flood_f64(Geom g, const double* __restrict__ image, const int* __restrict__ par, BlobInfo b, int* queue,
+               HeapItem* heap, int32_t* out) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int B = b.count[n];
+    const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+    const double* I = image + base;
+    const int* tp = par + base;
+    int32_t* o = out + base;
+    const int W = g.W, H = g.H;
+    for (;;) {
+        int bid = 0;
+        if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
+        bid = __shfl_sync(FULL, bid, 0);
+        if (bid > B) break;
+        const int root = b.root[ko + bid];
+        const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+        HeapItem* h = heap + base + b.off[ko + bid];
+        int sz = 0;
+        for (int y = y0; y <= y1; ++y) {
+            for (int xb = x0; xb <= x1; xb += 32) {
+                int x = xb + lane;
+                bool seed = false;
+                double v = 0.0;
+                if (x <= x1) {
+                    int idx = y * W + x;
+                    if (tp[idx] == root && o[idx] != 0) { seed = true; v = I[idx]; }
+                }
+                unsigned m = __ballot_sync(FULL, seed);
+                while (m) {
+                    int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    double sv = __shfl_sync(FULL, v, src);
+                    if (lane == 0) { HeapItem it; it.v = sv; it.age = 0u; it.idx = y * W + xb + src; heap_push(h, sz, it); }
+                }
+            }
+        }
+        if (lane == 0) {
+            unsigned age = 0;
+            while (sz > 0) {
+                HeapItem e = heap_pop(h, sz);
+                const int pix = e.idx;
+                const int lab = o[pix];
+                const int y = pix / W, x = pix - y * W;
+                const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};
+                const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
+                int pv[4], ov[4];
+                double vv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pv[k] = -1; ov[k] = 1; vv[k] = 0.0;
+                    if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; vv[k] = I[nb[k]]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (pv[k] >= 0 && ov[k] == 0) {
+                        o[nb[k]] = lab;
+                        HeapItem it; it.v = vv[k]; it.age = ++age; it.idx = nb[k];
+                        heap_push(h, sz, it);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int ws_seed(tiseg_ctx* c, const Geom& g, const int32_t* markers, const int* par, int32_t* out) {
+    TISEG_LAUNCH(c, k_ws_seed, warp_grid(g), TISEG_THREADS, 0, g, markers, par, out);
+    return TISEG_OK;
+}
+
+int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, BlobInfo& b, bool want_offsets) {
+    TISEG_LAUNCH(c, k_blob_init, dim3(8, g.N), 256, 0, b, g.W);
+    TISEG_LAUNCH(c, k_blob_roots, warp_grid(g), TISEG_THREADS, 0, g, par, rank, b);
+    TISEG_LAUNCH(c, k_blob_bbox, warp_grid(g), TISEG_THREADS, 0, g, par, rank, b);
+    if (want_offsets) TISEG_LAUNCH(c, k_blob_offsets, g.N, 256, 0, b);
+    return TISEG_OK;
+}
+
+static inline int flood_blocks(tiseg_ctx* c, int N) {
+    // persistent-style grid: enough warps to fill the chip several times over, split evenly over tiles
+    int per_tile = (c->sm_count * 8 * 4 + N - 1) / N;
+    if (per_tile < 1) per_tile = 1;
+    if (per_tile > 512) per_tile = 512;
+    return per_tile;
+}
+
+int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
+                     const BlobInfo& b, int32_t* out) {
+    (void)rank;
+    int* queue = ws<int>(c, (size_t)g.N);
+    int* next = ws<int>(c, (size_t)g.N * g.P);
+    if (!queue || !next) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, queue, (size_t)g.N * sizeof(int)));
+    TISEG_LAUNCH(c, k_ws_flood_u8, dim3(flood_blocks(c, g.N), g.N), TISEG_THREADS, 0, g, image, par, b, queue, next, out);
+    return TISEG_OK;
+}
+
+int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,
+                      const BlobInfo& b, int32_t* out) {
+    (void)rank;
+    int* queue = ws<int>(c, (size_t)g.N);
+    HeapItem* heap = ws<HeapItem>(c, (size_t)g.N * g.P);
+    if (!queue || !heap || !b.off) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, queue, (size_t)g.N * sizeof(int)));
+    TISEG_LAUNCH(c, k_ws_flood_f64, dim3(flood_blocks(c, g.N), g.N), TISEG_THREADS, 0, g, image, par, b, queue, heap, out);
+    return TISEG_OK;
+}
+
+template <class T>
+static int watershed_entry(tiseg_ctx* c, const T* image, const int32_t* markers, const uint8_t* mask, int N, int H,
+                           int W, int32_t* out) {
+    if (!c || !image || !markers || !out) { set_error("tiseg_watershed: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const T* d_img = in(c, image, total);
+    const int32_t* d_mk = in(c, markers, total);
+    const uint8_t* d_mask = mask ? in(c, mask, total) : nullptr;
+    int32_t* d_out = tiseg::out(c, out, total);
+    int* par = ws<int>(c, total);
+    int* rank = ws<int>(c, total);
+    if (!d_img || !d_mk || !d_out || !par || !rank) return TISEG_ERR_CUDA;
+    BlobInfo b;
+    constexpr bool F64 = sizeof(T) == 8;
+    if (d_mask) TISEG_TRY(blobs_build(c, g, ImgMaskU8{d_mask}, par, rank, b, F64));
+    else        TISEG_TRY(blobs_build(c, g, ImgAll{}, par, rank, b, F64));
+    TISEG_TRY(ws_seed(c, g, d_mk, par, d_out));
+    if constexpr (F64) TISEG_TRY(watershed_f64_dev(c, g, (const double*)d_img, par, rank, b, d_out));
+    else               TISEG_TRY(watershed_u8_dev(c, g, (const uint8_t*)d_img, par, rank, b, d_out));
+    return end_call(c);
+}
+
+}  // namespace tiseg
+
+using namespace tiseg;
+
+extern "C" {
+
+int tiseg_watershed_u8(tiseg_ctx* c, const uint8_t* image, const int32_t* markers, const uint8_t* mask, int N, int H,
+                       int W, int32_t* out) {
+    return watershed_entry<uint8_t>(c, image, markers, mask, N, H, W, out);
+}
+
+int tiseg_watershed_f64(tiseg_ctx* c, const double* image, const int32_t* markers, const uint8_t* mask, int N, int H,
+                        int W, int32_t* out) {
+    return watershed_entry<double>(c, image, markers, mask, N, H, W, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""Array-level operators over the C-ABI CUDA library.
+
+Every function takes numpy arrays (host buffers; the library stages them) or CUDA tensors
+(zero-copy, stream-ordered) shaped ``[H, W]`` or batched ``[N, H, W]`` and returns arrays of the same
+kind.  Names follow the scipy / scikit-image calls the reference makes.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import as_input, batched, empty_like_kind, get_ctx, ptr
+
+
+def _dev(a):
+    return a.device.index if (_lib.is_torch(a) and a.is_cuda) else None
+
+
+def _unbatch(out, was2d):
+    return out[0] if was2d else out
+
+
+def softmax_argmax(logits, want_prob=False):
+    """A1.  logits ``[T, C, H, W]`` / ``[N, T, C, H, W]`` fp32 (T = TTA variants) ->
+    class map uint8 (and the TTA-mean probabilities ``[.., C, H, W]`` when ``want_prob``)."""
+    x = as_input(logits, np.float32)
+    single = x.ndim == 4
+    if single:
+        x = x[None]
+    N, T, C, H, W = x.shape
+    cls = empty_like_kind(x, (N, H, W), np.uint8)
+    prob = empty_like_kind(x, (N, C, H, W), np.float32) if want_prob else None
+    get_ctx(_dev(x)).call("tiseg_softmax_argmax", ptr(x), N, T, C, H, W, ptr(prob), ptr(cls))
+    if single:
+        cls, prob = cls[0], (prob[0] if want_prob else None)
+    return (cls, prob) if want_prob else cls
+
+
+def label(img, background=0, connectivity=None, return_num=False):
+    """skimage.measure.label (A5) / scipy.ndimage.label with the cross structure (connectivity=1)."""
+    conn = 2 if connectivity is None else int(connectivity)
+    if getattr(img, "dtype", None) in (np.uint8, np.bool_) or str(getattr(img, "dtype", "")) in ("torch.uint8", "torch.bool"):
+        x, fn = as_input(img, np.uint8), "tiseg_label_u8"
+    else:
+        x, fn = as_input(img, np.int32), "tiseg_label"
+    x, was2d = batched(x)
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.int32)
+    cnt = empty_like_kind(x, (N,), np.int32)
+    get_ctx(_dev(x)).call(fn, ptr(x), N, H, W, int(background), conn, ptr(out), ptr(cnt))
+    out = _unbatch(out, was2d)
+    if return_num:
+        return out, (int(cnt[0]) if was2d else cnt)
+    return out
+
+
+def re_instance(inst):
+    """datasets/utils/instance_semantic.py:5-15."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.int32)
+    get_ctx(_dev(x)).call("tiseg_re_instance", ptr(x), N, H, W, ptr(out), ptr(None))
+    return _unbatch(out, was2d)
+
+
+def binary_fill_holes(mask):
+    x, was2d = batched(as_input(mask, np.uint8))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.uint8)
+    get_ctx(_dev(x)).call("tiseg_fill_holes", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def remove_small_objects(ar, min_size=64, connectivity=1):
+    """skimage.morphology.remove_small_objects: bool / uint8 input -> component analysis;
+    integer label input -> the labels are the components."""
+    dt = str(getattr(ar, "dtype", ""))
+    if dt in ("bool", "uint8", "torch.bool", "torch.uint8"):
+        x, was2d = batched(as_input(ar, np.uint8))
+        N, H, W = x.shape
+        out = empty_like_kind(x, (N, H, W), np.uint8)
+        get_ctx(_dev(x)).call("tiseg_remove_small_objects", ptr(x), N, H, W, int(min_size), int(connectivity), ptr(out))
+    else:
+        x, was2d = batched(as_input(ar, np.int32))
+        N, H, W = x.shape
+        out = empty_like_kind(x, (N, H, W), np.int32)
+        get_ctx(_dev(x)).call("tiseg_remove_small_labels", ptr(x), N, H, W, int(min_size), ptr(out))
+    return _unbatch(out, was2d)
+
+
+def _morph(fn, lab, footprint, radius):
+    x, was2d = batched(as_input(lab, np.int32))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.int32)
+    get_ctx(_dev(x)).call(fn, ptr(x), N, H, W, {"disk": 0, "square": 1}[footprint], int(radius), ptr(out))
+    return _unbatch(out, was2d)
+
+
+def dilation(lab, footprint="disk", radius=1):
+    """skimage.morphology.dilation(lab, disk(radius)) / square(2*radius+1) on a label image."""
+    return _morph("tiseg_dilate_labels", lab, footprint, radius)
+
+
+def erosion(lab, footprint="disk", radius=1):
+    return _morph("tiseg_erode_labels", lab, footprint, radius)
+
+
+def postproc_unet(cls, max_class, radius=1, edge_id=None, kill=None):
+    """A2.  Returns (sem_pred uint8, inst_pred int32).  ``cls`` (uint8) is modified in place when
+    ``edge_id`` / ``kill`` are given, like the reference."""
+    x, was2d = batched(cls)
+    N, H, W = x.shape
+    k = None
+    if kill is not None:
+        k, _ = batched(as_input(kill, np.uint8))
+    sem = empty_like_kind(x, (N, H, W), np.uint8)
+    inst = empty_like_kind(x, (N, H, W), np.int32)
+    get_ctx(_dev(x)).call("tiseg_postproc_unet", ptr(x), N, H, W, int(max_class), int(radius),
+                          -1 if edge_id is None else int(edge_id), ptr(k), ptr(sem), ptr(inst))
+    return _unbatch(sem, was2d), _unbatch(inst, was2d)
+
+
+def watershed(image, markers, mask=None):
+    """skimage.segmentation.watershed(image, markers, mask=mask) (connectivity 1, no lines)."""
+    dt = str(getattr(image, "dtype", ""))
+    if dt in ("uint8", "torch.uint8"):
+        im, fn = as_input(image, np.uint8), "tiseg_watershed_u8"
+    else:
+        im, fn = as_input(image, np.float64), "tiseg_watershed_f64"
+    im, was2d = batched(im)
+    mk, _ = batched(as_input(markers, np.int32))
+    ms = None
+    if mask is not None:
+        ms, _ = batched(as_input(mask, np.uint8))
+    N, H, W = im.shape
+    out = empty_like_kind(im, (N, H, W), np.int32)
+    get_ctx(_dev(im)).call(fn, ptr(im), ptr(mk), ptr(ms), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def postproc_dist(dist, debug=False):
+    """A8.  dist fp32 -> inst int32 (and, with ``debug``, the marker and raw-flood maps)."""
+    x, was2d = batched(as_input(dist, np.float32))
+    N, H, W = x.shape
+    inst = empty_like_kind(x, (N, H, W), np.int32)
+    mk = empty_like_kind(x, (N, H, W), np.int32) if debug else None
+    ws = empty_like_kind(x, (N, H, W), np.int32) if debug else None
+    get_ctx(_dev(x)).call("tiseg_postproc_dist", ptr(x), N, H, W, ptr(inst), ptr(mk), ptr(ws))
+    if debug:
+        return _unbatch(inst, was2d), _unbatch(mk, was2d), _unbatch(ws, was2d)
+    return _unbatch(inst, was2d)
+
+
+def pair_metrics_bin(inst_pred, inst_gt):
+    """A16 + A17 in one pass.  -> (aji [N,2] fp64 = (inter, union), pq [N,4] fp64 = (tp, fp, fn, iou))."""
+    p, was2d = batched(as_input(inst_pred, np.int32))
+    g, _ = batched(as_input(inst_gt, np.int32))
+    if tuple(p.shape) != tuple(g.shape):
+        raise ValueError("prediction / ground-truth shape mismatch: %r vs %r" % (tuple(p.shape), tuple(g.shape)))
+    N, H, W = p.shape
+    aji = empty_like_kind(p, (N, 2), np.float64)
+    pq = empty_like_kind(p, (N, 4), np.float64)
+    get_ctx(_dev(p)).call("tiseg_pair_metrics_bin", ptr(p), ptr(g), N, H, W, ptr(aji), ptr(pq))
+    return (aji[0], pq[0]) if was2d else (aji, pq)
+
+
+def sem_counts(pred, gt, num_classes, ignore_index=255):
+    """A19.  -> (counts [N,5,C] int64 = TP, FP, FN, Pred, GT; valid [N] int64)."""
+    p, was2d = batched(as_input(pred, np.uint8))
+    g, _ = batched(as_input(gt, np.uint8))
+    N, H, W = p.shape
+    counts = empty_like_kind(p, (N, 5, num_classes), np.int64)
+    valid = empty_like_kind(p, (N,), np.int64)
+    get_ctx(_dev(p)).call("tiseg_sem_counts", ptr(p), ptr(g), N, H, W, int(num_classes), int(ignore_index),
+                          ptr(counts), ptr(valid))
+    return (counts[0], valid[0]) if was2d else (counts, valid)
