@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — post-process + evaluation throughput of the tiseg test-time instance pipeline on B200.
+
+Workload (BASELINE.json configs[1], the 1000x1000 configuration the metric is quoted on):
+  "dist_monuseg_1000": DIST (distance regression) MoNuSeg-like 1000x1000 tiles — softmax/argmax of the
+  2-class semantic head, distance-map marker extraction + ordered watershed (dist.py:275-284), then the
+  evaluation of custom.py:252-283: semantic counts, binary AJI and binary PQ on the GT x pred pair matrix.
+A "step" is one pass of that path over one batch of `--batch` synthetic tiles per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).  value = tiles/s with inputs resident in HBM; e2e = tiles/s through the same
+calls fed from pinned HOST buffers (H2D of every input + D2H of the metric records inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 1000
+WORKLOAD = "dist_monuseg_1000"
+METRIC = "postproc+eval tiles/s @1000x1000 (DIST MoNuSeg config)"
+# algorithmic bytes per pixel of one tile through the whole path:
+# sem logits 2x4 + dist 4 + sem_pred 1 + inst_pred 4 + inst_gt 4 + sem_gt 1
+PIPE_BYTES_PER_PX = 22
+# compulsory bytes per pixel of each kernel's own inputs + outputs, touched once
+KERNEL_BYTES_PER_PX = {
+    "k_ws_flood_u8": 1 + 4 + 4 + 4,          # level image, blob forest, seeds in, labels out
+    "k_softmax_argmax<4>": 8 + 1, "k_dist_prep": 4 + 1,
+    "k_ccl_init<Img>": 1 + 4, "(k_ccl_merge<Img, 1>)": 1 + 4 + 4, "(k_ccl_merge<Img, 2>)": 1 + 4 + 4,
+    "k_ccl_flatten": 4 + 4, "k_rank_count<Sel>": 4, "k_rank_place<Sel>": 4 + 4, "k_apply_rank": 4 + 4 + 4,
+    "k_pair_accumulate": 4 * 4, "k_plateau_lower": 1 + 4, "k_markers_from_plateaus": 1 + 4 + 4,
+    "k_blob_roots": 4, "k_blob_bbox": 4, "k_ws_seed": 4 + 4 + 4, "k_ws_hist": 4, "k_wsl_remove": 4 + 4,
+    "k_sem_counts": 2, "memset": 4,
+}
+
+
+def make_tiles(n_distinct, seed0):
+    """n_distinct seeded synthetic DIST tiles (tiseg_b200.synth, SURVEY.md §8d generator)."""
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import synth
+    return [synth.tile_dist(2, seed0 + j, H=H, W=W) for j in range(n_distinct)]
+
+
+def stack_batch(tiles, batch):
+    """Fill a batch from the distinct tiles, cycling through the 8 dihedral variants so no two are equal."""
+    def var(a, k):
+        a = np.rot90(a, k % 4, axes=(-2, -1))
+        return np.ascontiguousarray(a[..., ::-1] if k >= 4 else a)
+    out = dict(sem_logit=[], dist_logit=[], gt_inst=[], gt_sem=[])
+    for b in range(batch):
+        t = tiles[b % len(tiles)]
+        k = (b // len(tiles)) % 8
+        for key in out:
+            out[key].append(var(t[key], k))
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["sem_logit"] = res["sem_logit"][:, None]            # [B, T=1, C, H, W]
+    return res
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def _cpu_tile(args):
+    """The reference's path for one tile, literal cost profile (np.vectorize h-reconstruction, per-instance
+    masks in AJI/PQ): oracle port of dist.py:262-284 + custom.py:252-283."""
+    seed, = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import synth
+    from oracle import metrics as om
+    from oracle import postprocess as opp
+    t = synth.tile_dist(2, seed, H=H, W=W)
+    t0 = time.perf_counter()
+    sem = opp.argmax_classes(opp.softmax(t["sem_logit"]))
+    _, inst = opp.dist_postprocess(sem, t["dist_logit"], literal=True)
+    semres = om.pre_eval_all_semantic_metric(sem, t["gt_sem"], 2)
+    ip, ig = om.re_instance(inst), om.re_instance(t["gt_inst"])
+    aji = om.pre_eval_bin_aji(ip, ig, literal=True)
+    pq = om.pre_eval_bin_pq(ip, ig, literal=True)
+    return time.perf_counter() - t0, float(aji[0]), float(aji[1]), float(semres[0][0])
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    per_step = workers                                     # one tile per worker per step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        seed = 0
+        for _ in range(a.warmup):
+            pool.map(_cpu_tile, [(seed + i,) for i in range(per_step)]); seed += per_step
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            pool.map(_cpu_tile, [(seed + i,) for i in range(per_step)]); seed += per_step
+        dt = time.perf_counter() - t0
+    value = per_step * a.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 labels, fp32 softmax, fp64 IoU", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tile": [H, W], "tiles_per_step": per_step, "instances_per_tile": 900},
+        "cpu_baseline": {"value": value, "unit": "tiles/s", "cores": workers, "kind": "port",
+                         "sample": "%d tiles per step, one process per tile (oracle port of the reference path; "
+                                   "/root/reference is Python and not importable: mmcv/skimage absent)" % per_step},
+        "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- this repo (CUDA)
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import _lib, ops
+
+    B = a.batch
+    tiles = make_tiles(a.distinct, seed0=1000 * rank)
+    host = stack_batch(tiles, B)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    devt = {k: v.to(dev) for k, v in pinned.items()}
+    pinned_np = {k: v.numpy() for k, v in pinned.items()}
+    ctx = _lib.get_ctx(local)
+
+    acc = torch.zeros(16, dtype=torch.float64, device=dev)
+
+    def step(src):
+        cls = ops.softmax_argmax(src["sem_logit"])
+        inst = ops.postproc_dist(src["dist_logit"])
+        aji, pq = ops.pair_metrics_bin(inst, src["gt_inst"])
+        counts, valid = ops.sem_counts(cls, src["gt_sem"], 2)
+        acc[0:2] += aji.sum(0); acc[2:6] += pq.sum(0); acc[6:16] += counts.sum(0).reshape(-1).double()
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, steps, with_d2h):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record()
+        for _ in range(steps):
+            with _lib.device_outputs():
+                r = step(src)
+            if with_d2h:
+                r.cpu()                                    # the step's metric record comes back to the host
+        if world > 1:
+            dist.all_reduce(acc)                           # the only collective: metric accumulators
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launch_count() - l0
+
+    for _ in range(max(a.warmup, 3)):
+        with _lib.device_outputs():
+            step(devt)
+    sampler = ClockSampler(local) if rank == 0 else None
+    acc.zero_()
+    ms, launches = timed(devt, a.steps, with_d2h=False)
+    clocks = sampler.stop() if sampler else None
+    value = world * B * a.steps / (ms / 1e3)
+
+    # e2e: same calls, inputs are pinned host buffers (the library stages them), result record read back
+    for _ in range(2):
+        with _lib.device_outputs():
+            step(pinned_np)
+    acc.zero_()
+    ms_e2e, _ = timed(pinned_np, a.steps, with_d2h=True)
+    e2e = world * B * a.steps / (ms_e2e / 1e3)
+    h2d = int(sum(v.nbytes for v in pinned_np.values()))
+    d2h = int(acc.numel() * 8)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline leg: per-kernel CUDA-event durations over two more steps on the launching stream
+    ctx.timing(True)
+    for _ in range(2):
+        with _lib.device_outputs():
+            step(devt)
+    rep = ctx.timing_report()
+    ctx.timing(False)
+    total_ms = sum(v[1] for v in rep.values())
+    top = max(rep.items(), key=lambda kv: kv[1][1])
+    name, (cnt, kms) = top
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bpp = KERNEL_BYTES_PER_PX.get(name, 8)
+    alg_bytes = bpp * H * W * B                             # per launch: the kernel sees the whole batch
+    achieved = alg_bytes / (kms / cnt / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+            "kernel_share_of_step": kms / total_ms, "alg_bytes_per_launch": alg_bytes,
+            "pipeline_frac": (PIPE_BYTES_PER_PX * H * W * value / world) / 1e9 / peak,
+            "per_kernel_ms_per_step": {k: round(v[1] / 2, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        ts = [_cpu_tile((900000 + j,))[0] for j in range(a.cpu_tiles)]
+        cpu = {"value": len(ts) / sum(ts), "unit": "tiles/s", "cores": 1, "kind": "port",
+               "sample": "%d tiles of the same workload, one core, literal oracle port of the reference path" % len(ts)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 labels, fp32 softmax, fp64 IoU", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tile": [H, W], "tiles_per_step_per_gpu": B, "instances_per_tile": 900,
+                   "distinct_tiles": a.distinct, "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (h2d / 1e6),
+                   "parallelism": "tiles sharded per GPU, one all-reduce of metric accumulators"},
+        "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "check": {"aji": float(acc[0] / acc[1]) if float(acc[1]) else None},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="tiles per step per GPU")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic tiles generated per rank")
+    ap.add_argument("--cpu-tiles", type=int, default=2, help="tiles timed for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

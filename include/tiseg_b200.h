@@ -41,6 +41,10 @@ const char* tiseg_last_error(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long long tiseg_launch_count(tiseg_ctx* ctx);
 int tiseg_version(void);
+/* optional per-kernel CUDA-event timing (bench.py's roofline leg): enable, run, then read one
+ * "kernel_name launches total_ms" line per kernel (aggregated and reset). */
+int tiseg_timing_enable(tiseg_ctx* ctx, int on);
+int tiseg_timing_report(tiseg_ctx* ctx, char* buf, int cap);
 
 /* ---- A1: softmax / TTA mean / argmax ---------------------------------------------------------
  * tiseg/models/segmentors/base.py:321-339 (F.softmax per TTA variant, sum/len, resize == identity

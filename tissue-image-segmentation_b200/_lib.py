@@ -23,6 +23,8 @@ SIGNATURES = {
     "tiseg_last_error": [],
     "tiseg_launch_count": [_vp],
     "tiseg_version": [],
+    "tiseg_timing_enable": [_vp, _i],
+    "tiseg_timing_report": [_vp, ctypes.c_char_p, _i],
     "tiseg_softmax_argmax": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_label": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_label_u8": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
@@ -97,6 +99,19 @@ class Context:
     def launch_count(self):
         return int(self.lib.tiseg_launch_count(self.handle))
 
+    def timing(self, on):
+        check(self.lib.tiseg_timing_enable(self.handle, 1 if on else 0), "tiseg_timing_enable")
+
+    def timing_report(self):
+        """-> {kernel_name: (launches, total_ms)} since timing was enabled / last report."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(self.lib.tiseg_timing_report(self.handle, buf, len(buf)), "tiseg_timing_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
     def call(self, name, *args):
         check(getattr(self.lib, name)(self.handle, *args), name)
 
@@ -162,11 +177,30 @@ def as_input(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+_device_out = threading.local()
+
+
+class device_outputs:
+    """``with device_outputs():`` — operators return CUDA tensors even for host (numpy) inputs, so a chain
+    of calls keeps its intermediates in HBM and only the inputs cross PCIe."""
+
+    def __enter__(self):
+        self.prev = getattr(_device_out, "on", False)
+        _device_out.on = True
+        return self
+
+    def __exit__(self, *exc):
+        _device_out.on = self.prev
+        return False
+
+
 def empty_like_kind(ref, shape, dtype):
     """Output buffer of the same kind (numpy / CUDA tensor) as ``ref``."""
+    import torch
     if is_torch(ref) and ref.is_cuda:
-        import torch
         return torch.empty(tuple(shape), dtype=_torch_dtype(dtype), device=ref.device)
+    if getattr(_device_out, "on", False):
+        return torch.empty(tuple(shape), dtype=_torch_dtype(dtype), device="cuda")
     return np.empty(tuple(shape), dtype=dtype)
 
 

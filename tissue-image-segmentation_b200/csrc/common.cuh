@@ -28,6 +28,11 @@ struct tiseg_ctx {
     std::vector<Pending> pending;
     long long launches = 0;
     int sm_count = 148;
+    // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
+    bool timing = false;
+    struct Timed { const char* name; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 namespace tiseg {
@@ -52,6 +57,8 @@ template <class T> inline const T* in(tiseg_ctx* c, const T* p, size_t n) { retu
 template <class T> inline T* out(tiseg_ctx* c, T* p, size_t n) { return p ? (T*)out_ptr(c, p, n * sizeof(T)) : nullptr; }
 
 int zero(tiseg_ctx* c, void* p, size_t bytes);
+// records the 'before' event of a timed launch and returns the 'after' event to record
+cudaEvent_t timing_before(tiseg_ctx* c, const char* name);
 
 #define TISEG_CHECK(expr)                                                \
     do {                                                                 \
@@ -68,7 +75,9 @@ int zero(tiseg_ctx* c, void* p, size_t bytes);
 // launch + count + error check.  Usage: TISEG_LAUNCH(c, kernel, grid, block, smem, args...)
 #define TISEG_LAUNCH(c, kern, grid, block, smem, ...)                                 \
     do {                                                                              \
+        cudaEvent_t _tb = (c)->timing ? ::tiseg::timing_before((c), #kern) : nullptr; \
         kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                  \
+        if (_tb) cudaEventRecord(_tb, (c)->stream);                                   \
         (c)->launches++;                                                              \
         cudaError_t _e = cudaGetLastError();                                          \
         if (_e != cudaSuccess) return ::tiseg::fail(#kern, _e);                       \

@@ -112,8 +112,25 @@ int end_call(tiseg_ctx* c) {
 }
 
 int zero(tiseg_ctx* c, void* p, size_t bytes) {
+    cudaEvent_t tb = c->timing ? timing_before(c, "memset") : nullptr;
     TISEG_CHECK(cudaMemsetAsync(p, 0, bytes, c->stream));
+    if (tb) cudaEventRecord(tb, c->stream);
     return TISEG_OK;
+}
+
+static cudaEvent_t get_event(tiseg_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+cudaEvent_t timing_before(tiseg_ctx* c, const char* name) {
+    tiseg_ctx::Timed t;
+    t.name = name; t.a = get_event(c); t.b = get_event(c);
+    cudaEventRecord(t.a, c->stream);
+    c->timed.push_back(t);
+    return t.b;
 }
 
 }  // namespace tiseg
@@ -165,6 +182,36 @@ int tiseg_set_stream(tiseg_ctx* c, void* s) {
 int tiseg_synchronize(tiseg_ctx* c) {
     if (!c) { tiseg::set_error("null ctx"); return TISEG_ERR_ARG; }
     TISEG_CHECK(cudaStreamSynchronize(c->stream));
+    return TISEG_OK;
+}
+
+int tiseg_timing_enable(tiseg_ctx* c, int on) {
+    if (!c) { tiseg::set_error("null ctx"); return TISEG_ERR_ARG; }
+    c->timing = on != 0;
+    return TISEG_OK;
+}
+
+// "name count total_ms\n" per kernel, aggregated over everything launched since timing was enabled
+int tiseg_timing_report(tiseg_ctx* c, char* buf, int cap) {
+    if (!c || !buf || cap <= 0) { tiseg::set_error("tiseg_timing_report: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_CHECK(cudaStreamSynchronize(c->stream));
+    struct Agg { const char* name; long long n; double ms; };
+    std::vector<Agg> agg;
+    for (auto& t : c->timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        size_t i = 0;
+        for (; i < agg.size(); ++i) if (!strcmp(agg[i].name, t.name)) break;
+        if (i == agg.size()) agg.push_back({t.name, 0, 0.0});
+        agg[i].n++; agg[i].ms += ms;
+        c->event_pool.push_back(t.a); c->event_pool.push_back(t.b);
+    }
+    c->timed.clear();
+    std::string out;
+    char line[256];
+    for (auto& a : agg) { snprintf(line, sizeof line, "%s %lld %.6f\n", a.name, a.n, a.ms); out += line; }
+    if ((int)out.size() + 1 > cap) { tiseg::set_error("tiseg_timing_report: buffer too small"); return TISEG_ERR_ARG; }
+    memcpy(buf, out.c_str(), out.size() + 1);
     return TISEG_OK;
 }
 

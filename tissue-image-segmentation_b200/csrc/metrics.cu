@@ -183,25 +183,40 @@ __global__ void k_aji_pred(InstState s, unsigned long long* IU) {
 
 // numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum): what
 // `paired_iou.sum()` (inst_metrics.py:227) evaluates, reproduced so iou_sum is bit-identical.
-__device__ double np_pairwise_sum(const double* a, int n) {
+__device__ __forceinline__ double np_pairwise_leaf(const double* a, int n) {   // n <= 128
     if (n < 8) {
         double r = 0.0;
         for (int i = 0; i < n; ++i) r += a[i];
         return r;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i];
-        return res;
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+// the recursion "n2 = n/2 - (n/2)%8; sum(a, n2) + sum(a+n2, n-n2)" unrolled onto an explicit stack (device
+// recursion would need a run-time stack size)
+__device__ double np_pairwise_sum(const double* a, int n) {
+    struct Frame { int off, n, state; double left; };
+    Frame st[32];
+    int sp = 0;
+    double ret = 0.0;
+    st[sp++] = Frame{0, n, 0, 0.0};
+    while (sp) {
+        Frame& f = st[sp - 1];
+        if (f.n <= 128) { ret = np_pairwise_leaf(a + f.off, f.n); --sp; continue; }
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.state == 0) { f.state = 1; st[sp++] = Frame{f.off, n2, 0, 0.0}; continue; }
+        if (f.state == 1) { f.left = ret; f.state = 2; st[sp++] = Frame{f.off + n2, f.n - n2, 0, 0.0}; continue; }
+        ret = f.left + ret;
+        --sp;
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+    return ret;
 }
 
 // one warp per tile: compact the PQ match IoUs in gt-id order (== row-major order of np.nonzero), sum them
