@@ -115,6 +115,38 @@ int tiseg_watershed_f64(tiseg_ctx* ctx, const double* image, const int32_t* mark
 int tiseg_postproc_dist(tiseg_ctx* ctx, const float* dist, int N, int H, int W, int32_t* inst_out,
                         int32_t* markers_out, int32_t* ws_out);
 
+/* ---- A11: HoVer-Net post-process (hovernet.py:283-365, hover_post_proc; fx = 1) ------------------------------
+ * fore_map [N,H,W] fp32 (softmax channel 1 of the foreground head), hv_map [N,H,W,2] fp32 HWC (horizontal,
+ * vertical) as the reference passes them after permute(0,2,3,1).  scale_factor must be 1 (the MoNuSeg / CoNSeP
+ * configs; the resize path of the CoNIC config is not implemented).  inst_out [N,H,W] int32.  Optional debug
+ * outputs (NULL to skip): blb uint8, dist fp64 (the flooded image), marker int32. */
+int tiseg_postproc_hover(tiseg_ctx* ctx, const float* fore_map, const float* hv_map, int N, int H, int W,
+                         int scale_factor, int32_t* inst_out, uint8_t* blb_out, double* dist_out, int32_t* marker_out);
+
+/* ---- A12: CDNet direction-guided refinement ----------------------------------------------------------------
+ * generate_direction_differential_map(dir_map, 9) (tiseg/models/utils/direct_diff_map.py:95-167):
+ * dir_map [N,H,W] uint8 (0 = background, 1..8 directions) -> dd [N,H,W] fp32 in {0, 0.5, 1}. */
+int tiseg_ddm(tiseg_ctx* ctx, const uint8_t* dir_map, int N, int H, int W, float* dd);
+/* The tail of CDNet.inference after the CNN (cdnet.py:183-217) including _ddm_enhencement (:354-367):
+ * sem_logits [N,T,C,H,W], dir_logits [N,T,D=9,H,W], point_logits [N,T,1,H,W] raw fp32 head outputs of the T
+ * TTA variants.  Outputs (any may be NULL): sem_prob_out [N,C,H,W] refined probabilities, cls_out [N,H,W]
+ * their argmax, dir_map_out [N,H,W] direction map of variant 0, dd_out [N,H,W] mean DDM. */
+int tiseg_cdnet_refine(tiseg_ctx* ctx, const float* sem_logits, const float* dir_logits, const float* point_logits,
+                       int N, int T, int C, int D, int H, int W, int if_ddm, float* sem_prob_out, uint8_t* cls_out,
+                       uint8_t* dir_map_out, float* dd_out);
+
+/* ---- A13: align_foreground (tiseg/models/utils/postprocess.py:123-155) -----------------------------------
+ * Ordered multi-source BFS growing the labels of `pred` into `foreground` (8-neighbourhood, first claimant
+ * wins, at most time-1 rounds).  pred [N,H,W] int32 is modified in place; foreground uint8. */
+int tiseg_align_foreground(tiseg_ctx* ctx, int32_t* pred, const uint8_t* foreground, int N, int H, int W, int time);
+
+/* Multi-task postprocess (multi_task_unet.py:84-106, multi_task_cunet.py:86-108, multi_task_cdnet.py:222-243):
+ * sem canvas = per class remove_small_objects(5) then binary_fill_holes; instances = measure.label(inner,
+ * connectivity=1) with the edge class (edge_id, < 0 = none) zeroed, grown by align_foreground(., canvas>0, time).
+ * inner / sem uint8; canvas_out uint8; inst_out int32. */
+int tiseg_postproc_multitask(tiseg_ctx* ctx, const uint8_t* inner, const uint8_t* sem, int N, int H, int W,
+                             int max_class, int edge_id, int time, uint8_t* canvas_out, int32_t* inst_out);
+
 /* ---- A16 / A17: pre_eval_bin_aji + pre_eval_bin_pq (inst_metrics.py:10-92, 138-229) ---------------
  * pred / gt [N,H,W] int32 instance maps with arbitrary ids (the relabelling the reference does with
  * re_instance + measure.label is done inside).  aji [N,2] fp64 = (overall_inter, overall_union);
@@ -122,6 +154,16 @@ int tiseg_postproc_dist(tiseg_ctx* ctx, const float* dist, int N, int H, int W, 
  * reference default 0.5 (the Hungarian branch is unreachable with it). */
 int tiseg_pair_metrics_bin(tiseg_ctx* ctx, const int32_t* pred, const int32_t* gt, int N, int H, int W,
                            double* aji, double* pq);
+
+/* ---- A18: CoNIC multi-class evaluation (conic.py:165-188) -----------------------------------------------
+ * assign_sem_class_to_insts (datasets/utils/instance_semantic.py:68-93) on both sides, then pre_eval_aji /
+ * pre_eval_pq (inst_metrics.py:95-135, 232-280), and optionally the binary records, from ONE pair table.
+ * *_inst int32 (ids < max(H*W+1, 65536)), *_sem uint8, C = number of classes incl. background.
+ * aji [N,C,2], pq [N,C,4] fp64 with slot 0 = the reference's class-0 slot (dropped by reduce_zero_label);
+ * bin_aji [N,2], bin_pq [N,4] as tiseg_pair_metrics_bin.  Any output may be NULL. */
+int tiseg_pair_metrics_multiclass(tiseg_ctx* ctx, const int32_t* pred_inst, const uint8_t* pred_sem,
+                                  const int32_t* gt_inst, const uint8_t* gt_sem, int N, int H, int W, int C,
+                                  double* aji, double* pq, double* bin_aji, double* bin_pq);
 
 /* ---- A19: pre_eval_all_semantic_metric (sem_metrics.py:16-53) --------------------------------------
  * pred / gt [N,H,W] uint8; counts [N, 5, C] int64 = TP, FP, FN, Pred, GT per class (TN derived on the

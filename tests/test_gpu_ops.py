@@ -268,3 +268,104 @@ def test_sem_counts_golden():
     tp, fp, fn, pr, gt = (counts[k].astype(np.float32) for k in range(5))
     res = np.stack([tp, np.float32(valid) - (tp + fp + fn), fp, fn, pr, gt])[:, 1:]
     assert np.array_equal(res, mref["ign_sem"])
+
+
+# --------------------------------------------------------------------------- A18
+def test_multiclass_metrics_golden_and_oracle():
+    mref = np.load(os.path.join(G, "metrics_ref.npz"))
+    C = 4
+    for i in range(int(mref["n_cases"])):
+        n = "c%d" % i
+        p, g, ps, gs = mref[n + "_pred"], mref[n + "_gt"], mref[n + "_pred_sem"], mref[n + "_gt_sem"]
+        r = ops.pair_metrics_multiclass(p, ps, g, gs, C)
+        aji = r["aji"].astype(np.float32).T[:, 1:]            # [2, C-1]
+        pq = r["pq"].astype(np.float32).T[:, 1:]              # [4, C-1]
+        assert np.array_equal(aji, mref[n + "_aji"]), (n, aji, mref[n + "_aji"])
+        assert np.array_equal(pq, mref[n + "_pq"]), (n, pq, mref[n + "_pq"])
+        assert tuple(r["bin_aji"]) == tuple(mref[n + "_bin_aji"]), n
+        assert tuple(r["bin_pq"]) == tuple(mref[n + "_bin_pq"]), n
+        # slot 0 (dropped by reduce_zero_label) against the oracle
+        rp, rg = om.re_instance(p), om.re_instance(g)
+        dp, dg = om.assign_sem_class_to_insts(rp, ps, C), om.assign_sem_class_to_insts(rg, gs, C)
+        wa = np.stack(om.pre_eval_aji(rp, rg, dp, dg, C, reduce_zero_label=False, literal=False))
+        wp = np.stack(om.pre_eval_pq(rp, rg, dp, dg, C, reduce_zero_label=False, literal=False))
+        assert np.array_equal(r["aji"].astype(np.float32).T, wa), n
+        assert np.array_equal(r["pq"].astype(np.float32).T, wp), n
+
+
+def test_multiclass_metrics_batched_conic_like():
+    C = 7
+    tiles = [synth.gt_and_pred(7000 + j, 256, 256, num_classes=C) for j in range(6)]
+    st = lambda k: np.stack([t[k] for t in tiles])
+    r = ops.pair_metrics_multiclass(st("pred_inst"), st("pred_sem"), st("gt_inst"), st("gt_sem"), C)
+    for j, t in enumerate(tiles):
+        rp, rg = om.re_instance(t["pred_inst"]), om.re_instance(t["gt_inst"])
+        dp = om.assign_sem_class_to_insts(rp, t["pred_sem"], C)
+        dg = om.assign_sem_class_to_insts(rg, t["gt_sem"], C)
+        wa = np.stack(om.pre_eval_aji(rp, rg, dp, dg, C, literal=False))
+        wp = np.stack(om.pre_eval_pq(rp, rg, dp, dg, C, literal=False))
+        assert np.array_equal(r["aji"][j].astype(np.float32).T[:, 1:], wa), j
+        assert np.array_equal(r["pq"][j].astype(np.float32).T[:, 1:], wp), j
+
+
+# --------------------------------------------------------------------------- A12
+def test_ddm_golden_and_cdnet_tail():
+    o = np.load(os.path.join(G, "ordered_ref.npz"))
+    for j in range(3):
+        _diff(ops.ddm(o["dd%d_dir" % j].astype(np.uint8)), o["dd%d_out" % j], "ddm golden %d" % j)
+    _diff(ops.ddm(np.zeros((16, 16), np.uint8)), o["dd_zero_out"], "ddm of an all-background map")
+    for T, (H, W) in [(1, (64, 80)), (3, (96, 70))]:
+        rng = np.random.default_rng(80 + T)
+        t = synth.gt_and_pred(8000 + T, H, W)
+        tc = synth.three_class_map(t["pred_inst"])
+        sem = [synth.sem_logits(rng, tc, 3) for _ in range(T)]
+        dirs, pts = zip(*[synth.direction_logits(rng, t["pred_inst"]) for _ in range(T)])
+        for if_ddm in (True, False):
+            want_sem, want_dir, want_dd = opp.cdnet_inference_tail(sem, list(dirs), list(pts), if_ddm=if_ddm)
+            r = ops.cdnet_refine(np.stack(sem), np.stack(dirs), np.stack(pts), if_ddm=if_ddm)
+            _diff(r["dir_map"], want_dir, "cdnet dir map T=%d" % T)
+            _diff(r["dd"], want_dd, "cdnet dd map T=%d" % T)
+            np.testing.assert_allclose(r["sem_prob"], want_sem, rtol=1e-5, atol=1e-7)
+            want_cls = np.argmax(want_sem, 0)
+            top2 = np.sort(want_sem, axis=0)[-2:]
+            clear = (top2[1] - top2[0]) > 1e-6
+            assert np.array_equal(r["cls"][clear], want_cls[clear])
+
+
+# --------------------------------------------------------------------------- A13
+def test_align_foreground_golden_and_multitask():
+    o = np.load(os.path.join(G, "ordered_ref.npz"))
+    for j in range(3):
+        for key, tm in (("out", 20), ("out5", 5)):
+            got = ops.align_foreground(o["af%d_seed" % j].astype(np.int32), o["af%d_fg" % j], tm)
+            _diff(got, o["af%d_%s" % (j, key)], "align_foreground golden %d time %d" % (j, tm))
+    for j, variant in enumerate(("unet", "cunet", "cdnet")):
+        t = synth.gt_and_pred(8100 + j, 128, 150, num_classes=4)
+        inner = synth.three_class_map(t["pred_inst"]) if variant != "unet" else (t["pred_inst"] > 0).astype(np.uint8)
+        want_sem, want_inst = opp.multitask_postprocess(inner.astype(np.int64), t["pred_sem"].astype(np.int64), variant)
+        canvas, inst = ops.postproc_multitask(inner, t["pred_sem"], 3, None if variant == "unet" else 2)
+        _diff(inst, want_inst, "multitask inst (%s)" % variant)
+        if variant != "cdnet":
+            _diff(canvas, want_sem, "multitask sem canvas (%s)" % variant)
+
+
+# --------------------------------------------------------------------------- A11
+@pytest.mark.parametrize("H,W,idx", [(64, 100, 1), (256, 256, 0), (250, 131, 2), (500, 517, 3)])
+def test_postproc_hover(H, W, idx):
+    import cv2  # noqa: F401  (the oracle calls OpenCV exactly as the reference does)
+    t = synth.tile_hover(3, idx, H=H, W=W)
+    want, dbg = opp.hover_post_proc(t["fore_map"], t["hv_map"])
+    got, blb, dist, mk = ops.postproc_hover(t["fore_map"], t["hv_map"], debug=True)
+    _diff(blb, dbg["blb"], "hover blb")
+    _diff(mk, dbg["marker"], "hover markers")
+    _diff(dist, dbg["dist"], "hover flooded image (fp64, bit-exact)")
+    _diff(got, want, "hover inst")
+    assert got.max() > 3
+
+
+def test_postproc_hover_full_tile_batched():
+    tiles = [synth.tile_hover(3, j) for j in range(2)]
+    got = ops.postproc_hover(np.stack([t["fore_map"] for t in tiles]), np.stack([t["hv_map"] for t in tiles]))
+    for j, t in enumerate(tiles):
+        want, _ = opp.hover_post_proc(t["fore_map"], t["hv_map"])
+        _diff(got[j], want, "hover inst 1000^2 tile %d" % j)

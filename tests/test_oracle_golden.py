@@ -11,6 +11,8 @@ from oracle import postprocess as opp
 from oracle import skimage_port as sk
 
 G = os.path.join(os.path.dirname(__file__), "golden")
+import sys
+sys.path.insert(0, os.path.dirname(__file__))
 
 
 @pytest.fixture(scope="module")
@@ -159,3 +161,29 @@ def test_literal_and_fast_dist_agree():
     a = opp.dist_postprocess(sp, t["dist_logit"], literal=True)[1]
     b = opp.dist_postprocess(sp, t["dist_logit"], literal=False)[1]
     assert np.array_equal(a, b) and a.max() > 3
+
+
+def test_opencv_recipes_are_bit_exact():
+    """The arithmetic order the HoVer kernels implement (tests/cv_recipes.py) reproduces cv2 bit for bit
+    (normalize on fp32 input, Sobel ksize 21 -> CV_64F, GaussianBlur 3x3 on fp64, 5x5 ellipse)."""
+    cv2 = pytest.importorskip("cv2")
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import synth
+    import cv_recipes as R
+    assert np.array_equal(cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5)), R.ELLIPSE5)
+    d, sm = R.deriv_kernels_21()
+    kd, ks = cv2.getDerivKernels(1, 0, 21)
+    assert np.array_equal(kd.ravel(), d) and np.array_equal(ks.ravel(), sm)
+    for seed, (H, W) in enumerate([(48, 48), (64, 100), (250, 131)]):
+        t = synth.tile_hover(3, 50 + seed, H=H, W=W)
+        for ch in range(2):
+            x = np.ascontiguousarray(t["hv_map"][:, :, ch])
+            n = cv2.normalize(x, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+            assert np.array_equal(R.normalize_minmax_f32(x), n)
+            s = cv2.Sobel(n, cv2.CV_64F, 1 - ch, ch, ksize=21)
+            assert np.array_equal(R.sobel21(n, 1 - ch, ch), s)
+            assert np.array_equal(R.gaussian_blur3(s), cv2.GaussianBlur(s, (3, 3), 0))
+            # fp64 -> fp32 normalize contracts x*a+b into one FMA inside OpenCV; without FMA at most a few
+            # pixels next to the minimum differ in the last bit
+            sn = cv2.normalize(s, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+            assert (R.normalize_minmax_f32(s) != sn).sum() <= 4

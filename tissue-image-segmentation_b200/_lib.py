@@ -38,7 +38,13 @@ SIGNATURES = {
     "tiseg_watershed_u8": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tiseg_watershed_f64": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tiseg_postproc_dist": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "tiseg_postproc_hover": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "tiseg_ddm": [_vp, _vp, _i, _i, _i, _vp],
+    "tiseg_cdnet_refine": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "tiseg_align_foreground": [_vp, _vp, _vp, _i, _i, _i, _i],
+    "tiseg_postproc_multitask": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_pair_metrics_bin": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tiseg_pair_metrics_multiclass": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tiseg_sem_counts": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
 }
 _RESTYPE = {"tiseg_last_error": ctypes.c_char_p, "tiseg_launch_count": _ll}

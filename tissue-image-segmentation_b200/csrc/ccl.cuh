@@ -49,6 +49,14 @@ struct ImgBelowU8 {             // binary: uint8 value < thr
     const uint8_t* p; int thr;
     __device__ __forceinline__ bool operator()(int, long long gi, int& v) const { v = 1; return p[gi] < thr; }
 };
+struct ImgOrI32U8 {             // binary: labelled pixel OR foreground pixel (align_foreground's reachable set)
+    const int32_t* lab; const uint8_t* fg;
+    __device__ __forceinline__ bool operator()(int, long long gi, int& v) const { v = 1; return lab[gi] != 0 || fg[gi] != 0; }
+};
+struct ImgEqU8Drop {            // equal-value components of a uint8 image, values 0 and `drop` are background
+    const uint8_t* p; int drop;
+    __device__ __forceinline__ bool operator()(int, long long gi, int& v) const { v = p[gi]; return v != 0 && v != drop; }
+};
 struct ImgNonZeroI32 {          // binary: non-zero int32
     const int32_t* p;
     __device__ __forceinline__ bool operator()(int n, long long gi, int& v) const { v = 1; return p[gi] != 0; }

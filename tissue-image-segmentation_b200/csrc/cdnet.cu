@@ -1,0 +1,233 @@
+// K9 — CDNet direction-guided refinement.
+//   tiseg_ddm           generate_direction_differential_map (tiseg/models/utils/direct_diff_map.py:95-167), 9 classes
+//   tiseg_cdnet_refine  the tail of CDNet.inference after the CNN (tiseg/models/segmentors/cdnet.py:183-217):
+//                       softmax + TTA mean of the semantic head, TTA mean of the point head, per variant
+//                       dir[:,0] *= sem[:,0] -> argmax -> DDM, mean DDM, _ddm_enhencement (cdnet.py:354-367), argmax.
+// The reference does this with ~60 ATen launches per TTA variant (8 torch.roll temporaries); here the DDM is one
+// wrap-around 3x3 stencil on the uint8 direction map plus a per-tile max/min reduction.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace tiseg {
+
+int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, int C, float* d_prob, uint8_t* d_cls);
+
+// label -> (vertical, horizontal) unit-step vector, direct_diff_map.py:7
+__constant__ float c_dir9[9][2] = {{0, 0}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}, {1, -1}};
+
+// level = 1 - round(min over the 8 circularly shifted neighbours of cos(anchor, neighbour)), background -> 0.
+// Same fp32 expression as the reference so the rounding sees the same value.
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ddm_levels(Geom g, const uint8_t* __restrict__ dir, uint8_t* __restrict__ lv, int* mm) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    int level = -1;
+    if (px.ok) {
+        const uint8_t* t = dir + px.base;
+        int d = t[px.idx];
+        if (d > 8) d = 0;
+        float a0 = c_dir9[d][0], a1 = c_dir9[d][1];
+        float na = sqrtf(a0 * a0 + a1 * a1);
+        // torch.roll(shifts=(sv, sh)): feature[y, x] = anchor[y - sv, x - sh] (wrap-around); the 8 shifts of
+        // direct_diff_map.py:116-131 cover all 8 neighbours, so the min does not depend on their order
+        float best = FLT_MAX;
+        for (int sv = -1; sv <= 1; ++sv) {
+            int yy = px.y - sv; yy = yy < 0 ? yy + g.H : (yy >= g.H ? yy - g.H : yy);
+            for (int sh = -1; sh <= 1; ++sh) {
+                if (sv == 0 && sh == 0) continue;
+                int xx = px.x - sh; xx = xx < 0 ? xx + g.W : (xx >= g.W ? xx - g.W : xx);
+                int e = t[yy * g.W + xx];
+                if (e > 8) e = 0;
+                float f0 = c_dir9[e][0], f1 = c_dir9[e][1];
+                float num = a0 * f0 + a1 * f1;
+                float den = na * sqrtf(f0 * f0 + f1 * f1) + 0.000001f;
+                best = fminf(best, num / den);
+            }
+        }
+        if (d == 0) best = 1.f;
+        level = (int)(1.f - rintf(best));                    // torch.round: half to even
+        lv[px.base + px.idx] = (uint8_t)level;
+    }
+    int hi = level, lo = level < 0 ? 255 : level;
+    for (int s = 16; s; s >>= 1) { hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s)); lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s)); }
+    if (px.lane == 0) {
+        if (hi > mm[2 * px.n]) atomicMax(&mm[2 * px.n], hi);
+        if (lo < mm[2 * px.n + 1]) atomicMin(&mm[2 * px.n + 1], lo);
+    }
+}
+
+__global__ void k_ddm_mm_init(int* mm, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mm[2 * i] = 0; mm[2 * i + 1] = 255; }
+}
+
+__device__ __forceinline__ float ddm_normalise(int level, int mx, int mn) {
+    float v = (float)level;
+    if (mx == 0) return v;                                    // all-zero map is returned as is (:162-163)
+    return (v - (float)mn) / ((float)mx - (float)mn);
+}
+
+// dd[n] = (sum over the T variants of the normalised DDM) / T   (cdnet.py:201-212), T = 1 for tiseg_ddm
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ddm_mean(Geom g, const uint8_t* __restrict__ lv, const int* __restrict__ mm, int T, float* __restrict__ dd) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {
+        long long tile = (long long)px.n * T + t;
+        float v = ddm_normalise(lv[tile * g.P + px.idx], mm[2 * tile], mm[2 * tile + 1]);
+        acc = t == 0 ? v : acc + v;
+    }
+    dd[px.base + px.idx] = acc / (float)T;
+}
+
+// per variant: softmax over the D direction channels, channel 0 scaled by the mean background probability,
+// argmax (first maximum)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_dir_map(Geom g, const float* __restrict__ dir_logits, const float* __restrict__ sem_prob, int T, int D, int C,
+          uint8_t* __restrict__ dir_map) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const long long P = g.P;
+    float s0 = sem_prob[((long long)px.n * C) * P + px.idx];
+    for (int t = 0; t < T; ++t) {
+        const float* src = dir_logits + ((long long)px.n * T + t) * D * P + px.idx;
+        float m = -INFINITY;
+        for (int d = 0; d < D; ++d) m = fmaxf(m, src[d * P]);
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = s + expf(src[d * P] - m);
+        int best = 0;
+        float bv = -INFINITY;
+        for (int d = 0; d < D; ++d) {
+            float p = expf(src[d * P] - m) / s;
+            if (d == 0) p = p * s0;
+            if (p > bv) { bv = p; best = d; }
+        }
+        dir_map[((long long)px.n * T + t) * P + px.idx] = (uint8_t)best;
+    }
+}
+
+__device__ __forceinline__ int float_order_key(float f) {   // monotone float -> int map for atomicMax
+    int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float float_from_key(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void k_key_init(int* k, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k[i] = float_order_key(-INFINITY);
+}
+
+// point = sum_t point_t / T and its per-tile maximum
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_point_mean(Geom g, const float* __restrict__ point_logits, int T, float* __restrict__ pmean, int* pmax_key) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    float acc = -INFINITY;
+    if (px.ok) {
+        for (int t = 0; t < T; ++t) {
+            float v = point_logits[((long long)px.n * T + t) * g.P + px.idx];
+            acc = t == 0 ? v : acc + v;
+        }
+        acc = acc / (float)T;
+        pmean[px.base + px.idx] = acc;
+    }
+    int k = float_order_key(acc);
+    for (int s = 16; s; s >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, s));
+    if (px.lane == 0 && k > pmax_key[px.n]) atomicMax(&pmax_key[px.n], k);
+}
+
+// _ddm_enhencement + argmax: the last semantic channel becomes (p + dd') * (1 + dd'), dd' = dd - dd * point_map
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ddm_enhance(Geom g, float* __restrict__ sem_prob, int C, const float* __restrict__ dd, const float* __restrict__ pmean,
+              const int* __restrict__ pmax_key, int if_ddm, uint8_t* __restrict__ cls) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const long long P = g.P;
+    float* sp = sem_prob + (long long)px.n * C * P + px.idx;
+    if (if_ddm) {
+        float pm = float_from_key(pmax_key[px.n]);
+        float pmap = (pmean[px.base + px.idx] / pm) > 0.2f ? 1.f : 0.f;
+        float d = dd[px.base + px.idx];
+        float d2 = d - d * pmap;
+        float e = (sp[(C - 1) * P] + d2) * (1.f + d2);
+        sp[(C - 1) * P] = e;
+    }
+    if (cls) {
+        int best = 0;
+        float bv = -INFINITY;
+        for (int ch = 0; ch < C; ++ch) { float p = sp[ch * P]; if (p > bv) { bv = p; best = ch; } }
+        cls[px.base + px.idx] = (uint8_t)best;
+    }
+}
+
+int ddm_dev(tiseg_ctx* c, const Geom& g, const uint8_t* dir_map, int T, float* dd) {
+    // dir_map: [N*T, H, W]; dd: [N, H, W]
+    Geom gt = make_geom(g.N * T, g.H, g.W);
+    uint8_t* lv = ws<uint8_t>(c, (size_t)gt.N * gt.P);
+    int* mm = ws<int>(c, 2 * (size_t)gt.N);
+    if (!lv || !mm) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_ddm_mm_init, (gt.N + 255) / 256, 256, 0, mm, gt.N);
+    TISEG_LAUNCH(c, k_ddm_levels, warp_grid(gt), TISEG_THREADS, 0, gt, dir_map, lv, mm);
+    TISEG_LAUNCH(c, k_ddm_mean, warp_grid(g), TISEG_THREADS, 0, g, lv, mm, T, dd);
+    return TISEG_OK;
+}
+
+}  // namespace tiseg
+
+using namespace tiseg;
+
+extern "C" {
+
+int tiseg_ddm(tiseg_ctx* c, const uint8_t* dir_map, int N, int H, int W, float* dd) {
+    if (!c || !dir_map || !dd) { set_error("tiseg_ddm: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const uint8_t* d_dir = in(c, dir_map, total);
+    float* d_dd = tiseg::out(c, dd, total);
+    if (!d_dir || !d_dd) return TISEG_ERR_CUDA;
+    TISEG_TRY(ddm_dev(c, g, d_dir, 1, d_dd));
+    return end_call(c);
+}
+
+int tiseg_cdnet_refine(tiseg_ctx* c, const float* sem_logits, const float* dir_logits, const float* point_logits,
+                       int N, int T, int C, int D, int H, int W, int if_ddm, float* sem_prob_out, uint8_t* cls_out,
+                       uint8_t* dir_map_out, float* dd_out) {
+    if (!c || !sem_logits || !dir_logits || !point_logits || T <= 0 || C < 2 || C > 16 || D != 9) {
+        set_error("tiseg_cdnet_refine: bad argument (2 <= C <= 16, D == 9)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N * T, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const float* d_sem = in(c, sem_logits, total * T * C);
+    const float* d_dir = in(c, dir_logits, total * T * D);
+    const float* d_pt = in(c, point_logits, total * T);
+    float* d_prob = sem_prob_out ? tiseg::out(c, sem_prob_out, total * C) : ws<float>(c, total * C);
+    uint8_t* d_cls = cls_out ? tiseg::out(c, cls_out, total) : nullptr;
+    float* d_dd = dd_out ? tiseg::out(c, dd_out, total) : ws<float>(c, total);
+    uint8_t* dir_all = ws<uint8_t>(c, total * T);
+    float* pmean = ws<float>(c, total);
+    int* pmax = ws<int>(c, (size_t)N);
+    if (!d_sem || !d_dir || !d_pt || !d_prob || !d_dd || !dir_all || !pmean || !pmax) return TISEG_ERR_CUDA;
+    // softmax + TTA mean of the semantic head: the K1 kernel
+    TISEG_TRY(softmax_argmax_dev(c, g, d_sem, T, C, d_prob, nullptr));
+    TISEG_LAUNCH(c, k_dir_map, warp_grid(g), TISEG_THREADS, 0, g, d_dir, d_prob, T, D, C, dir_all);
+    TISEG_TRY(ddm_dev(c, g, dir_all, T, d_dd));
+    TISEG_LAUNCH(c, k_key_init, (N + 255) / 256, 256, 0, pmax, N);
+    TISEG_LAUNCH(c, k_point_mean, warp_grid(g), TISEG_THREADS, 0, g, d_pt, T, pmean, pmax);
+    TISEG_LAUNCH(c, k_ddm_enhance, warp_grid(g), TISEG_THREADS, 0, g, d_prob, C, d_dd, pmean, pmax, if_ddm, d_cls);
+    if (dir_map_out) {
+        // dir_map_list[0] of every tile (cdnet.py:217)
+        uint8_t* d_dm = tiseg::out(c, dir_map_out, total);
+        if (!d_dm) return TISEG_ERR_CUDA;
+        TISEG_CHECK(cudaMemcpy2DAsync(d_dm, g.P, dir_all, (size_t)T * g.P, g.P, N, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return end_call(c);
+}
+
+}  // extern "C"

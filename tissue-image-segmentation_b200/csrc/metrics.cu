@@ -61,19 +61,26 @@ struct InstState {
     int* bestp;                        // [N, KS] lowest pred id reaching `best`
     uint8_t* used;                     // [N, KS] pred id chosen by some gt
     double* pqiou;                     // [N, KS] IoU of the (unique) PQ match of a gt id, 0 = none
-    const int* ng; const int* np;      // [N]
+    const int* ng; const int* np;      // [N] number of components (ids 1..K)
     int KS;
+    // class of every component (NULL = binary evaluation: every component is class 1), C class slots
+    const uint8_t* cls_g; const uint8_t* cls_p;
+    int C;
+    __device__ __forceinline__ int class_g(long long o, unsigned id) const { return cls_g ? cls_g[o + id] : 1; }
+    __device__ __forceinline__ int class_p(long long o, unsigned id) const { return cls_p ? cls_p[o + id] : 1; }
 };
 
-__global__ void k_inst_init(InstState s) {
+__global__ void k_inst_init(InstState s, int areas) {
     int n = blockIdx.y;
     long long o = (long long)n * s.KS;
     int ng = s.ng[n], np = s.np[n];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= ng; i += gridDim.x * blockDim.x) {
-        s.area_g[o + i] = 0; s.best[o + i] = 0ull; s.bestp[o + i] = 0x7fffffff; s.pqiou[o + i] = 0.0;
+        if (areas) s.area_g[o + i] = 0;
+        s.best[o + i] = 0ull; s.bestp[o + i] = 0x7fffffff; s.pqiou[o + i] = 0.0;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= np; i += gridDim.x * blockDim.x) {
-        s.area_p[o + i] = 0; s.used[o + i] = 0;
+        if (areas) s.area_p[o + i] = 0;
+        s.used[o + i] = 0;
     }
 }
 
@@ -111,12 +118,14 @@ __global__ void k_pair_best(PairTab t, InstState s, int* tp) {
     if (!k) return;
     unsigned gid = (unsigned)(k >> 32), pid = (unsigned)k;
     long long o = (long long)n * s.KS;
+    int cg = s.class_g(o, gid);
+    if (cg == 0 || cg != s.class_p(o, pid)) return;         // only pairs inside one class meet (inst_metrics.py:112-122)
     double inter = (double)t.cnt[(long long)n * t.cap + slot];
     double tot = (double)s.area_g[o + gid] + (double)s.area_p[o + pid];
     double iou_aji = inter / ((tot - inter) + 1.0e-6);      // inst_metrics.py:69
     atomicMax(&s.best[o + gid], (unsigned long long)__double_as_longlong(iou_aji));
     double iou_pq = inter / (tot - inter);                  // inst_metrics.py:194
-    if (iou_pq > 0.5) { s.pqiou[o + gid] = iou_pq; atomicAdd(&tp[n], 1); }
+    if (iou_pq > 0.5) { s.pqiou[o + gid] = iou_pq; atomicAdd(&tp[n * s.C + cg], 1); }
 }
 
 // pass B: np.argmax tie rule — the lowest pred id among those reaching the best IoU (inst_metrics.py:74)
@@ -128,45 +137,62 @@ __global__ void k_pair_argbest(PairTab t, InstState s) {
     if (!k) return;
     unsigned gid = (unsigned)(k >> 32), pid = (unsigned)k;
     long long o = (long long)n * s.KS;
+    int cg = s.class_g(o, gid);
+    if (cg == 0 || cg != s.class_p(o, pid)) return;
     double inter = (double)t.cnt[(long long)n * t.cap + slot];
     double tot = (double)s.area_g[o + gid] + (double)s.area_p[o + pid];
     double iou_aji = inter / ((tot - inter) + 1.0e-6);
     if ((unsigned long long)__double_as_longlong(iou_aji) == s.best[o + gid]) atomicMin(&s.bestp[o + gid], (int)pid);
 }
 
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v) {
-    __shared__ unsigned long long sh[32];
-    for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0ull;
-    if (w == 0) for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-    return v;   // valid in thread 0
+// add (I, U) of one instance to its class slot; warps whose lanes all share one class (always, in the binary
+// evaluation) combine by shuffle first so the slot sees one atomic per warp
+__device__ __forceinline__ void add_iu(unsigned long long* IU, int n, int C, int cls, unsigned long long I,
+                                       unsigned long long U, bool active) {
+    int key = active ? cls : -1;
+    int kmax = key;
+    for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    bool uniform = __all_sync(0xffffffffu, key == kmax || key == -1);
+    if (uniform) {
+        if (kmax < 0) return;
+        for (int d = 16; d; d >>= 1) { I += __shfl_down_sync(0xffffffffu, I, d); U += __shfl_down_sync(0xffffffffu, U, d); }
+        if ((threadIdx.x & 31) == 0) {
+            if (I) atomicAdd(&IU[((long long)n * C + kmax) * 2], I);
+            if (U) atomicAdd(&IU[((long long)n * C + kmax) * 2 + 1], U);
+        }
+    } else if (active) {
+        if (I) atomicAdd(&IU[((long long)n * C + cls) * 2], I);
+        if (U) atomicAdd(&IU[((long long)n * C + cls) * 2 + 1], U);
+    }
 }
 
-// pass C: per gt — paired inter / union, or its own area when nothing overlaps (inst_metrics.py:76-87)
+// pass C: per gt — paired inter / union, or its own area when nothing overlaps (inst_metrics.py:76-87);
+// class-0 instances only contribute their area to union[0] (inst_metrics.py:105-110)
 __global__ void k_aji_gt(PairTab t, InstState s, unsigned long long* IU) {
     int n = blockIdx.y;
     long long o = (long long)n * s.KS;
     int ng = s.ng[n];
-    unsigned long long I = 0, U = 0;
-    for (int gid = 1 + blockIdx.x * blockDim.x + threadIdx.x; gid <= ng; gid += gridDim.x * blockDim.x) {
-        int ag = s.area_g[o + gid];
-        if (s.best[o + gid] != 0ull) {
-            int pid = s.bestp[o + gid];
-            int inter = pair_lookup(t, n, gid, pid);
-            I += inter;
-            U += (unsigned long long)(ag + s.area_p[o + pid] - inter);
-            s.used[o + pid] = 1;
-        } else {
-            U += ag;
+    int span = gridDim.x * blockDim.x;
+    for (int g0 = 1 + blockIdx.x * blockDim.x; g0 <= ng; g0 += span) {     // warp-uniform trip count
+        int gid = g0 + threadIdx.x;
+        bool act = gid <= ng;
+        unsigned long long I = 0, U = 0;
+        int cls = 0;
+        if (act) {
+            cls = s.class_g(o, gid);
+            int ag = s.area_g[o + gid];
+            if (cls != 0 && s.best[o + gid] != 0ull) {
+                int pid = s.bestp[o + gid];
+                int inter = pair_lookup(t, n, gid, pid);
+                I = inter;
+                U = (unsigned long long)(ag + s.area_p[o + pid] - inter);
+                s.used[o + pid] = 1;
+            } else {
+                U = ag;
+            }
         }
+        add_iu(IU, n, s.C, cls, I, U, act);
     }
-    I = block_sum_u64(I);
-    U = block_sum_u64(U);
-    if (threadIdx.x == 0) { if (I) atomicAdd(&IU[2 * n], I); if (U) atomicAdd(&IU[2 * n + 1], U); }
 }
 
 // pass D: preds never chosen by any gt add their area to the union (inst_metrics.py:88-90)
@@ -174,11 +200,18 @@ __global__ void k_aji_pred(InstState s, unsigned long long* IU) {
     int n = blockIdx.y;
     long long o = (long long)n * s.KS;
     int np = s.np[n];
-    unsigned long long U = 0;
-    for (int pid = 1 + blockIdx.x * blockDim.x + threadIdx.x; pid <= np; pid += gridDim.x * blockDim.x)
-        if (!s.used[o + pid]) U += s.area_p[o + pid];
-    U = block_sum_u64(U);
-    if (threadIdx.x == 0 && U) atomicAdd(&IU[2 * n + 1], U);
+    int span = gridDim.x * blockDim.x;
+    for (int p0 = 1 + blockIdx.x * blockDim.x; p0 <= np; p0 += span) {
+        int pid = p0 + threadIdx.x;
+        bool act = pid <= np;
+        unsigned long long U = 0;
+        int cls = 0;
+        if (act) {
+            cls = s.class_p(o, pid);
+            if (cls == 0 || !s.used[o + pid]) U = s.area_p[o + pid];
+        }
+        add_iu(IU, n, s.C, cls, 0ull, U, act);
+    }
 }
 
 // numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum): what
@@ -219,35 +252,57 @@ __device__ double np_pairwise_sum(const double* a, int n) {
     return ret;
 }
 
-// one warp per tile: compact the PQ match IoUs in gt-id order (== row-major order of np.nonzero), sum them
-// the numpy way, and write the two result records
-__global__ void k_metrics_final(InstState s, const unsigned long long* IU, const int* tp, double* scratch,
-                                double* aji, double* pq) {
-    int n = blockIdx.x;
+// per-class bookkeeping of the multi-class evaluation (all NULL in the binary one)
+struct ClassInfo {
+    const int* ncomp_g; const int* ncomp_p;   // [N, C] components per class
+    const int* ninst_g; const int* ninst_p;   // [N, C] instances (ids) per class; slot 0 includes id 0
+};
+
+// one warp per (tile, class): compact the PQ match IoUs of the class in gt-id order (== row-major order of
+// np.nonzero), sum them the numpy way, and write the result records.
+//   binary (ci.ncomp_g == NULL): class slot c0 = 1, records [N, 1]
+//   multi-class: slots 0..C-1, records [N, C] with the branch rules of inst_metrics.py:103-131, 247-273
+__global__ void k_metrics_final(InstState s, ClassInfo ci, const unsigned long long* IU, const int* tp,
+                                double* scratch, int c0, int Cout, double* aji, double* pq) {
+    int n = blockIdx.x, j = blockIdx.y, cls = c0 + j;
     int lane = threadIdx.x;
     long long o = (long long)n * s.KS;
     int ng = s.ng[n], np = s.np[n];
-    double* buf = scratch + o;
+    bool multi = ci.ncomp_g != nullptr;
+    // compaction slice: classes before this one own the first sum(ncomp_g[< cls]) entries
+    int off = 0;
+    if (multi) for (int t = 0; t < cls; ++t) off += ci.ncomp_g[n * s.C + t];
+    double* buf = scratch + o + off;
     int m = 0;
     for (int base = 1; base <= ng; base += 32) {
         int gid = base + lane;
-        double v = gid <= ng ? s.pqiou[o + gid] : 0.0;
+        double v = (gid <= ng && s.class_g(o, gid) == cls) ? s.pqiou[o + gid] : 0.0;
         unsigned b = __ballot_sync(0xffffffffu, v != 0.0);
         if (v != 0.0) buf[m + __popc(b & ((1u << lane) - 1))] = v;
         m += __popc(b);
     }
     __syncwarp();
-    if (lane == 0) {
-        if (aji) {
-            bool empty = ng == 0 || np == 0;                 // inst_metrics.py:72-73: (0., 0.) and nothing else
-            aji[2 * n] = empty ? 0.0 : (double)IU[2 * n];
-            aji[2 * n + 1] = empty ? 0.0 : (double)IU[2 * n + 1];
-        }
-        if (pq) {
-            int t = tp[n];
-            pq[4 * n] = t; pq[4 * n + 1] = np - t; pq[4 * n + 2] = ng - t;
-            pq[4 * n + 3] = np_pairwise_sum(buf, m);
-        }
+    if (lane != 0) return;
+    long long r = (long long)n * Cout + j;
+    double I = (double)IU[((long long)n * s.C + cls) * 2], U = (double)IU[((long long)n * s.C + cls) * 2 + 1];
+    int t = tp[n * s.C + cls];
+    double iou = np_pairwise_sum(buf, m);
+    if (!multi) {
+        bool empty = ng == 0 || np == 0;                     // inst_metrics.py:72-73: (0., 0.) and nothing else
+        if (aji) { aji[2 * r] = empty ? 0.0 : I; aji[2 * r + 1] = empty ? 0.0 : U; }
+        if (pq) { pq[4 * r] = t; pq[4 * r + 1] = np - t; pq[4 * r + 2] = ng - t; pq[4 * r + 3] = iou; }
+        return;
+    }
+    int ig = ci.ninst_g[n * s.C + cls], ip = ci.ninst_p[n * s.C + cls];
+    int kg = ci.ncomp_g[n * s.C + cls], kp = ci.ncomp_p[n * s.C + cls];
+    if (aji) { aji[2 * r] = I; aji[2 * r + 1] = U; }         // one-sided classes: all areas unpaired => same sums
+    if (pq) {
+        double vtp = 0, vfp = 0, vfn = 0, viou = 0;
+        if (cls == 0) { vfp = ip; vfn = ig; }                                   // :249-252 (id 0 counted)
+        else if (ip > 0 && ig > 0) { vtp = t; vfp = kp - t; vfn = kg - t; viou = iou; }   // :254-266
+        else if (ip > 0) vfp = ip;                                              // :267-269 counts ids
+        else if (ig > 0) vfn = ig;                                              // :270-272
+        pq[4 * r] = vtp; pq[4 * r + 1] = vfp; pq[4 * r + 2] = vfn; pq[4 * r + 3] = viou;
     }
 }
 
@@ -287,54 +342,152 @@ k_sem_counts(Geom g, const uint8_t* __restrict__ pred, const uint8_t* __restrict
 
 static int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-// pair metrics on already-flattened forests + ranks (shared with the multi-class path)
-int pair_metrics_core(tiseg_ctx* c, const Geom& g, const int* par_g, const int* rank_g, const int* ng,
-                      const int* par_p, const int* rank_p, const int* np, double* d_aji, double* d_pq) {
-    int N = g.N, KS = g.P + 1;
-    size_t ks = (size_t)N * KS;
+// ---- instance -> class assignment (assign_sem_class_to_insts, datasets/utils/instance_semantic.py:68-93) ----
+// hist[n, v, 0..C] = pixels of instance value v per semantic class (slot C collects out-of-range classes so
+// that the instance still exists); one atomic per in-segment run of equal (instance, class)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_inst_class_hist(Geom g, const int32_t* __restrict__ inst, const uint8_t* __restrict__ sem, int C, int VM,
+                  int* hist, int* bad) {
+    Pix px;
+    if (!warp_pixel(g, px)) return;
+    int v = 0, c = 0;
+    if (px.ok) { v = inst[px.base + px.idx]; c = sem[px.base + px.idx]; if (c >= C) c = C; }
+    int key = v * (C + 1) + c;
+    int kl = __shfl_up_sync(0xffffffffu, key, 1);
+    bool cont = px.lane > 0 && key == kl;
+    unsigned m = __ballot_sync(0xffffffffu, cont);
+    if (px.ok && v != 0 && !cont) {
+        if (v < 0 || v >= VM) { *bad = 1; return; }
+        atomicAdd(&hist[((long long)px.n * VM + v) * (C + 1) + c], run_end_lane(m, px.lane) - px.lane + 1);
+    }
+}
+
+__global__ void k_inst_class_pick(const int* __restrict__ hist, int C, int VM, uint8_t* cls_inst, int* ninst) {
+    int n = blockIdx.y;
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= VM) return;
+    int cls = -1;
+    if (v == 0) cls = 0;                                     // id 0 is always listed under class 0
+    else {
+        const int* h = hist + ((long long)n * VM + v) * (C + 1);
+        int tot = 0, best = 0, bc = 0, fg = 0;
+        for (int c = 0; c <= C; ++c) tot += h[c];
+        if (tot > 0) {
+            for (int c = 1; c < C; ++c) { fg += h[c]; if (h[c] > best) { best = h[c]; bc = c; } }   // first max
+            cls = fg > 0 ? bc : 0;
+        }
+    }
+    if (cls >= 0) { cls_inst[(long long)n * VM + v] = (uint8_t)cls; atomicAdd(&ninst[n * C + cls], 1); }
+}
+
+// class of every connected component = class of the instance value at its root pixel
+__global__ void k_comp_class(Geom g, const int32_t* __restrict__ inst, const int* __restrict__ par,
+                             const int* __restrict__ rank, const uint8_t* __restrict__ cls_inst, int VM, int C,
+                             uint8_t* cls_comp, int KS, int* ncomp) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    long long i = px.base + px.idx;
+    if (par[i] != px.idx) return;
+    int v = inst[i];
+    int cls = (v > 0 && v < VM) ? cls_inst[(long long)px.n * VM + v] : 0;
+    cls_comp[(long long)px.n * KS + rank[i]] = (uint8_t)cls;
+    atomicAdd(&ncomp[px.n * C + cls], 1);
+}
+
+struct PairWork {              // everything one evaluation shares: forests, ids, areas, the pair table
     InstState s;
+    PairTab t;
+    double* scratch;
+};
+
+// CCL of both maps + areas + pair table (retry at the always-sufficient size on overflow)
+static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, const int32_t* d_gt, PairWork& w,
+                            int** par_g_out, int** rank_g_out, int** par_p_out, int** rank_p_out) {
+    int N = g.N, KS = g.P + 1;
+    size_t total = (size_t)N * g.P, ks = (size_t)N * KS;
+    int* par_g = ws<int>(c, total); int* rank_g = ws<int>(c, total);
+    int* par_p = ws<int>(c, total); int* rank_p = ws<int>(c, total);
+    int* ng = ws<int>(c, (size_t)N); int* np = ws<int>(c, (size_t)N);
+    InstState& s = w.s;
     s.area_g = ws<int>(c, ks); s.area_p = ws<int>(c, ks);
     s.best = ws<unsigned long long>(c, ks); s.bestp = ws<int>(c, ks);
     s.used = ws<uint8_t>(c, ks); s.pqiou = ws<double>(c, ks);
-    double* scratch = ws<double>(c, ks);
-    s.ng = ng; s.np = np; s.KS = KS;
-    unsigned long long* IU = ws<unsigned long long>(c, 2 * (size_t)N);
-    int* tp = ws<int>(c, (size_t)N);
+    w.scratch = ws<double>(c, ks);
     int* overflow = ws<int>(c, 1);
-    if (!s.area_g || !s.area_p || !s.best || !s.bestp || !s.used || !s.pqiou || !scratch || !IU || !tp || !overflow)
-        return TISEG_ERR_CUDA;
+    if (!par_g || !rank_g || !par_p || !rank_p || !ng || !np || !s.area_g || !s.area_p || !s.best || !s.bestp ||
+        !s.used || !s.pqiou || !w.scratch || !overflow) return TISEG_ERR_CUDA;
+    s.ng = ng; s.np = np; s.KS = KS; s.cls_g = nullptr; s.cls_p = nullptr; s.C = 2;
+    // measure.label(inst.copy()) on both maps (inst_metrics.py:12-13): equal-value, 8-connected, background 0
+    TISEG_TRY(ccl_build(c, g, ImgEqI32{d_gt, 0}, 2, par_g));
+    TISEG_TRY(rank_roots(c, g, par_g, rank_g, ng));
+    TISEG_TRY(ccl_build(c, g, ImgEqI32{d_pred, 0}, 2, par_p));
+    TISEG_TRY(rank_roots(c, g, par_p, rank_p, np));
     // the table starts small (instances are compact: O(K) pairs) and is retried at the always-sufficient
     // size 2P if a pathological input overflows it
     int cap = next_pow2(g.P / 16 < 1024 ? 1024 : g.P / 16);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        PairTab t;
+    for (int attempt = 0;; ++attempt) {
+        PairTab& t = w.t;
         t.cap = cap;
         t.key = ws<unsigned long long>(c, (size_t)N * cap);
         t.cnt = ws<int>(c, (size_t)N * cap);
         if (!t.key || !t.cnt) return TISEG_ERR_CUDA;
         TISEG_TRY(zero(c, t.key, (size_t)N * cap * sizeof(unsigned long long)));
         TISEG_TRY(zero(c, t.cnt, (size_t)N * cap * sizeof(int)));
-        TISEG_TRY(zero(c, IU, 2 * (size_t)N * sizeof(unsigned long long)));
-        TISEG_TRY(zero(c, tp, (size_t)N * sizeof(int)));
         TISEG_TRY(zero(c, overflow, sizeof(int)));
-        TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s);
+        TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 1);
         TISEG_LAUNCH(c, k_pair_accumulate, warp_grid(g), TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t, overflow);
         int hov = 0;
         TISEG_CHECK(cudaMemcpyAsync(&hov, overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TISEG_CHECK(cudaStreamSynchronize(c->stream));
-        if (hov) {
-            if (attempt == 1) { set_error("pair table overflow"); return TISEG_ERR_LIMIT; }
-            cap = next_pow2(2ll * g.P);
-            continue;
-        }
-        dim3 tg((cap + 255) / 256, N);
-        TISEG_LAUNCH(c, k_pair_best, tg, 256, 0, t, s, tp);
-        TISEG_LAUNCH(c, k_pair_argbest, tg, 256, 0, t, s);
-        TISEG_LAUNCH(c, k_aji_gt, dim3(8, N), 256, 0, t, s, IU);
-        TISEG_LAUNCH(c, k_aji_pred, dim3(8, N), 256, 0, s, IU);
-        TISEG_LAUNCH(c, k_metrics_final, N, 32, 0, s, IU, tp, scratch, d_aji, d_pq);
-        break;
+        if (!hov) break;
+        if (attempt == 1) { set_error("pair table overflow"); return TISEG_ERR_LIMIT; }
+        cap = next_pow2(2ll * g.P);
     }
+    if (par_g_out) { *par_g_out = par_g; *rank_g_out = rank_g; *par_p_out = par_p; *rank_p_out = rank_p; }
+    return TISEG_OK;
+}
+
+// AJI / PQ records from a built table; cls_* NULL = binary
+static int pair_eval(tiseg_ctx* c, const Geom& g, PairWork& w, const uint8_t* cls_g, const uint8_t* cls_p, int C,
+                     const ClassInfo& ci, bool first_eval, double* d_aji, double* d_pq) {
+    int N = g.N;
+    InstState s = w.s;
+    s.cls_g = cls_g; s.cls_p = cls_p; s.C = C;
+    unsigned long long* IU = ws<unsigned long long>(c, 2 * (size_t)N * C);
+    int* tp = ws<int>(c, (size_t)N * C);
+    if (!IU || !tp) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, IU, 2 * (size_t)N * C * sizeof(unsigned long long)));
+    TISEG_TRY(zero(c, tp, (size_t)N * C * sizeof(int)));
+    if (!first_eval) TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 0);
+    dim3 tg((w.t.cap + 255) / 256, N);
+    TISEG_LAUNCH(c, k_pair_best, tg, 256, 0, w.t, s, tp);
+    TISEG_LAUNCH(c, k_pair_argbest, tg, 256, 0, w.t, s);
+    TISEG_LAUNCH(c, k_aji_gt, dim3(8, N), 256, 0, w.t, s, IU);
+    TISEG_LAUNCH(c, k_aji_pred, dim3(8, N), 256, 0, s, IU);
+    bool multi = cls_g != nullptr;
+    TISEG_LAUNCH(c, k_metrics_final, dim3(N, multi ? C : 1), 32, 0, s, ci, IU, tp, w.scratch, multi ? 0 : 1,
+                 multi ? C : 1, d_aji, d_pq);
+    return TISEG_OK;
+}
+
+// class of every component of one side (pred or gt)
+static int side_classes(tiseg_ctx* c, const Geom& g, const int32_t* inst, const uint8_t* sem, const int* par,
+                        const int* rank, int C, int VM, uint8_t** cls_comp_out, int** ncomp_out, int** ninst_out,
+                        int* bad) {
+    int N = g.N, KS = g.P + 1;
+    int* hist = ws<int>(c, (size_t)N * VM * (C + 1));
+    uint8_t* cls_inst = ws<uint8_t>(c, (size_t)N * VM);
+    uint8_t* cls_comp = ws<uint8_t>(c, (size_t)N * KS);
+    int* ncomp = ws<int>(c, (size_t)N * C);
+    int* ninst = ws<int>(c, (size_t)N * C);
+    if (!hist || !cls_inst || !cls_comp || !ncomp || !ninst) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, hist, (size_t)N * VM * (C + 1) * sizeof(int)));
+    TISEG_TRY(zero(c, ncomp, (size_t)N * C * sizeof(int)));
+    TISEG_TRY(zero(c, ninst, (size_t)N * C * sizeof(int)));
+    TISEG_LAUNCH(c, k_inst_class_hist, warp_grid(g), TISEG_THREADS, 0, g, inst, sem, C, VM, hist, bad);
+    TISEG_LAUNCH(c, k_inst_class_pick, dim3((VM + 255) / 256, N), 256, 0, hist, C, VM, cls_inst, ninst);
+    TISEG_LAUNCH(c, k_comp_class, warp_grid(g), TISEG_THREADS, 0, g, inst, par, rank, cls_inst, VM, C, cls_comp, KS, ncomp);
+    *cls_comp_out = cls_comp; *ncomp_out = ncomp; *ninst_out = ninst;
     return TISEG_OK;
 }
 
@@ -355,16 +508,58 @@ int tiseg_pair_metrics_bin(tiseg_ctx* c, const int32_t* pred, const int32_t* gt,
     const int32_t* d_gt = in(c, gt, total);
     double* d_aji = aji ? tiseg::out(c, aji, 2 * (size_t)N) : nullptr;
     double* d_pq = pq ? tiseg::out(c, pq, 4 * (size_t)N) : nullptr;
-    int* par_g = ws<int>(c, total); int* rank_g = ws<int>(c, total);
-    int* par_p = ws<int>(c, total); int* rank_p = ws<int>(c, total);
-    int* ng = ws<int>(c, (size_t)N); int* np = ws<int>(c, (size_t)N);
-    if (!d_pred || !d_gt || !par_g || !rank_g || !par_p || !rank_p || !ng || !np) return TISEG_ERR_CUDA;
-    // measure.label(inst.copy()) on both maps (inst_metrics.py:12-13): equal-value, 8-connected, background 0
-    TISEG_TRY(ccl_build(c, g, ImgEqI32{d_gt, 0}, 2, par_g));
-    TISEG_TRY(rank_roots(c, g, par_g, rank_g, ng));
-    TISEG_TRY(ccl_build(c, g, ImgEqI32{d_pred, 0}, 2, par_p));
-    TISEG_TRY(rank_roots(c, g, par_p, rank_p, np));
-    TISEG_TRY(pair_metrics_core(c, g, par_g, rank_g, ng, par_p, rank_p, np, d_aji, d_pq));
+    if (!d_pred || !d_gt) return TISEG_ERR_CUDA;
+    PairWork w;
+    TISEG_TRY(pair_table_build(c, g, d_pred, d_gt, w, nullptr, nullptr, nullptr, nullptr));
+    ClassInfo ci = {nullptr, nullptr, nullptr, nullptr};
+    TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, ci, true, d_aji, d_pq));
+    return end_call(c);
+}
+
+int tiseg_pair_metrics_multiclass(tiseg_ctx* c, const int32_t* pred_inst, const uint8_t* pred_sem,
+                                  const int32_t* gt_inst, const uint8_t* gt_sem, int N, int H, int W, int C,
+                                  double* aji, double* pq, double* bin_aji, double* bin_pq) {
+    if (!c || !pred_inst || !pred_sem || !gt_inst || !gt_sem || C < 2 || C > 64) {
+        set_error("tiseg_pair_metrics_multiclass: bad argument (2 <= C <= 64)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const int32_t* d_pi = in(c, pred_inst, total);
+    const uint8_t* d_ps = in(c, pred_sem, total);
+    const int32_t* d_gi = in(c, gt_inst, total);
+    const uint8_t* d_gs = in(c, gt_sem, total);
+    double* d_aji = aji ? tiseg::out(c, aji, 2 * (size_t)N * C) : nullptr;
+    double* d_pq = pq ? tiseg::out(c, pq, 4 * (size_t)N * C) : nullptr;
+    double* d_baji = bin_aji ? tiseg::out(c, bin_aji, 2 * (size_t)N) : nullptr;
+    double* d_bpq = bin_pq ? tiseg::out(c, bin_pq, 4 * (size_t)N) : nullptr;
+    if (!d_pi || !d_ps || !d_gi || !d_gs) return TISEG_ERR_CUDA;
+    PairWork w;
+    int *par_g, *rank_g, *par_p, *rank_p;
+    TISEG_TRY(pair_table_build(c, g, d_pi, d_gi, w, &par_g, &rank_g, &par_p, &rank_p));
+    ClassInfo none = {nullptr, nullptr, nullptr, nullptr};
+    bool first = true;
+    if (d_baji || d_bpq) { TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, none, first, d_baji, d_bpq)); first = false; }
+    if (d_aji || d_pq) {
+        int VM = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;     // instance ids index the class tables directly
+        int* bad = ws<int>(c, 1);
+        if (!bad) return TISEG_ERR_CUDA;
+        TISEG_TRY(zero(c, bad, sizeof(int)));
+        uint8_t *cls_g, *cls_p;
+        ClassInfo ci;
+        int *a, *b;
+        TISEG_TRY(side_classes(c, g, d_gi, d_gs, par_g, rank_g, C, VM, &cls_g, &a, &b, bad));
+        ci.ncomp_g = a; ci.ninst_g = b;
+        TISEG_TRY(side_classes(c, g, d_pi, d_ps, par_p, rank_p, C, VM, &cls_p, &a, &b, bad));
+        ci.ncomp_p = a; ci.ninst_p = b;
+        TISEG_TRY(pair_eval(c, g, w, cls_g, cls_p, C, ci, first, d_aji, d_pq));
+        int hbad = 0;
+        TISEG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TISEG_CHECK(cudaStreamSynchronize(c->stream));
+        if (hbad) { set_error("tiseg_pair_metrics_multiclass: instance id out of range (need id < max(H*W+1, 65536))"); return TISEG_ERR_LIMIT; }
+    }
     return end_call(c);
 }
 

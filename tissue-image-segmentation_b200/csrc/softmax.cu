@@ -46,6 +46,13 @@ k_softmax_argmax(Geom g, const float* __restrict__ logits, int T, int C, float* 
     if (cls) cls[px.base + px.idx] = (uint8_t)best;
 }
 
+int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, int C, float* d_prob, uint8_t* d_cls) {
+    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax<4>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
+    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax<8>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
+    else TISEG_LAUNCH(c, k_softmax_argmax<16>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
+    return TISEG_OK;
+}
+
 }  // namespace tiseg
 
 using namespace tiseg;
@@ -64,8 +71,6 @@ extern "C" int tiseg_softmax_argmax(tiseg_ctx* c, const float* logits, int N, in
     float* d_prob = prob ? tiseg::out(c, prob, total * C) : nullptr;
     uint8_t* d_cls = cls ? tiseg::out(c, cls, total) : nullptr;
     if (!d_in) return TISEG_ERR_CUDA;
-    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax<4>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
-    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax<8>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
-    else TISEG_LAUNCH(c, k_softmax_argmax<16>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
+    TISEG_TRY(softmax_argmax_dev(c, g, d_in, T, C, d_prob, d_cls));
     return end_call(c);
 }

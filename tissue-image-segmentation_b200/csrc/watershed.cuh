@@ -31,7 +31,8 @@ struct BlobInfo {
 
 // mask functor -> flattened blob forest `par`, blob ids `rank` (at roots), BlobInfo
 template <class MaskImg>
-int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, BlobInfo& b, bool want_offsets);
+int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, BlobInfo& b, bool want_offsets,
+                int conn = 1);
 
 int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
                      const BlobInfo& b, int32_t* out);
@@ -46,7 +47,8 @@ int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank,
 #ifdef __CUDACC__
 
 template <class MaskImg>
-int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, BlobInfo& b, bool want_offsets) {
+int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, BlobInfo& b, bool want_offsets,
+                int conn) {
     int N = g.N, KS = g.P + 1;
     size_t ks = (size_t)N * KS;
     int* count = ws<int>(c, (size_t)N);
@@ -54,7 +56,7 @@ int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, 
     b.area = ws<int>(c, ks); b.off = want_offsets ? ws<int>(c, ks) : nullptr;
     b.KS = KS; b.count = count;
     if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || (want_offsets && !b.off)) return TISEG_ERR_CUDA;
-    TISEG_TRY(ccl_build(c, g, mask, 1, par));
+    TISEG_TRY(ccl_build(c, g, mask, conn, par));
     TISEG_TRY(rank_roots(c, g, par, rank, count));
     return blobs_describe(c, g, par, rank, b, want_offsets);
 }

@@ -172,3 +172,96 @@ def sem_counts(pred, gt, num_classes, ignore_index=255):
     get_ctx(_dev(p)).call("tiseg_sem_counts", ptr(p), ptr(g), N, H, W, int(num_classes), int(ignore_index),
                           ptr(counts), ptr(valid))
     return (counts[0], valid[0]) if was2d else (counts, valid)
+
+
+def pair_metrics_multiclass(inst_pred, sem_pred, inst_gt, sem_gt, num_classes, want_bin=True):
+    """A18 (+ A16/A17 from the same pair table).  -> dict(aji [N,C,2], pq [N,C,4], bin_aji [N,2], bin_pq [N,4])
+    fp64; slot 0 of the class axis is the reference's class-0 slot."""
+    p, was2d = batched(as_input(inst_pred, np.int32))
+    g, _ = batched(as_input(inst_gt, np.int32))
+    ps, _ = batched(as_input(sem_pred, np.uint8))
+    gs, _ = batched(as_input(sem_gt, np.uint8))
+    N, H, W = p.shape
+    C = int(num_classes)
+    aji = empty_like_kind(p, (N, C, 2), np.float64)
+    pq = empty_like_kind(p, (N, C, 4), np.float64)
+    baji = empty_like_kind(p, (N, 2), np.float64) if want_bin else None
+    bpq = empty_like_kind(p, (N, 4), np.float64) if want_bin else None
+    get_ctx(_dev(p)).call("tiseg_pair_metrics_multiclass", ptr(p), ptr(ps), ptr(g), ptr(gs), N, H, W, C,
+                          ptr(aji), ptr(pq), ptr(baji), ptr(bpq))
+    out = dict(aji=aji, pq=pq, bin_aji=baji, bin_pq=bpq)
+    if was2d:
+        out = {k: (v[0] if v is not None else None) for k, v in out.items()}
+    return out
+
+
+def ddm(dir_map):
+    """A12: generate_direction_differential_map(dir_map, 9) -> fp32 map in {0, 0.5, 1}."""
+    x, was2d = batched(as_input(dir_map, np.uint8))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.float32)
+    get_ctx(_dev(x)).call("tiseg_ddm", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def cdnet_refine(sem_logits, dir_logits, point_logits, if_ddm=True):
+    """A12: CDNet.inference tail.  sem_logits [N,T,C,H,W], dir_logits [N,T,9,H,W], point_logits [N,T,1,H,W]
+    (or without the leading N) -> dict(sem_prob [N,C,H,W], cls uint8, dir_map uint8, dd fp32)."""
+    s = as_input(sem_logits, np.float32)
+    d = as_input(dir_logits, np.float32)
+    p = as_input(point_logits, np.float32)
+    single = s.ndim == 4
+    if single:
+        s, d, p = s[None], d[None], p[None]
+    N, T, C, H, W = s.shape
+    D = d.shape[2]
+    prob = empty_like_kind(s, (N, C, H, W), np.float32)
+    cls = empty_like_kind(s, (N, H, W), np.uint8)
+    dm = empty_like_kind(s, (N, H, W), np.uint8)
+    dd = empty_like_kind(s, (N, H, W), np.float32)
+    get_ctx(_dev(s)).call("tiseg_cdnet_refine", ptr(s), ptr(d), ptr(p), N, T, C, D, H, W, 1 if if_ddm else 0,
+                          ptr(prob), ptr(cls), ptr(dm), ptr(dd))
+    out = dict(sem_prob=prob, cls=cls, dir_map=dm, dd=dd)
+    return {k: v[0] for k, v in out.items()} if single else out
+
+
+def align_foreground(pred, foreground, time=20):
+    """A13: grows the labels of ``pred`` (int32, modified in place and returned) into ``foreground``."""
+    x, was2d = batched(pred)
+    f, _ = batched(as_input(foreground, np.uint8))
+    N, H, W = x.shape
+    get_ctx(_dev(x)).call("tiseg_align_foreground", ptr(x), ptr(f), N, H, W, int(time))
+    return pred
+
+
+def postproc_multitask(inner, sem, max_class, edge_id=None, time=20):
+    """Multi-task postprocess -> (sem canvas uint8, inst int32)."""
+    a, was2d = batched(as_input(inner, np.uint8))
+    s, _ = batched(as_input(sem, np.uint8))
+    N, H, W = a.shape
+    canvas = empty_like_kind(a, (N, H, W), np.uint8)
+    inst = empty_like_kind(a, (N, H, W), np.int32)
+    get_ctx(_dev(a)).call("tiseg_postproc_multitask", ptr(a), ptr(s), N, H, W, int(max_class),
+                          -1 if edge_id is None else int(edge_id), int(time), ptr(canvas), ptr(inst))
+    return _unbatch(canvas, was2d), _unbatch(inst, was2d)
+
+
+def postproc_hover(fore_map, hv_map, scale_factor=1, debug=False):
+    """A11: hover_post_proc.  fore_map [N,H,W] fp32, hv_map [N,H,W,2] fp32 -> inst int32 (with ``debug`` also
+    the blb mask, the flooded fp64 image and the markers)."""
+    f, was2d = batched(as_input(fore_map, np.float32))
+    hv = as_input(hv_map, np.float32)
+    if hv.ndim == 3:
+        hv = hv[None]
+    N, H, W = f.shape
+    if tuple(hv.shape) != (N, H, W, 2):
+        raise ValueError("hv_map must be [N,H,W,2] (HWC), got %r" % (tuple(hv.shape),))
+    inst = empty_like_kind(f, (N, H, W), np.int32)
+    blb = empty_like_kind(f, (N, H, W), np.uint8) if debug else None
+    dist = empty_like_kind(f, (N, H, W), np.float64) if debug else None
+    mk = empty_like_kind(f, (N, H, W), np.int32) if debug else None
+    get_ctx(_dev(f)).call("tiseg_postproc_hover", ptr(f), ptr(hv), N, H, W, int(scale_factor), ptr(inst), ptr(blb),
+                          ptr(dist), ptr(mk))
+    if debug:
+        return tuple(_unbatch(x, was2d) for x in (inst, blb, dist, mk))
+    return _unbatch(inst, was2d)

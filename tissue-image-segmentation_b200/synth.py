@@ -218,3 +218,32 @@ def tile_dist(config_id, tile_index, H=1000, W=1000):
     inst = np.where(t["pred_sem"] > 0, t["pred_inst"], 0)
     t["dist_logit"] = dist_map(rng, inst)
     return t
+
+
+def tile_hover(config_id, tile_index, H=1000, W=1000):
+    """Config 3 (HoVer-Net): 3-class type logits, foreground probability, HV map [H,W,2] + GT."""
+    seed = 1000 * config_id + tile_index
+    t = gt_and_pred(seed, H, W, num_classes=3)
+    rng = np.random.default_rng(seed + 500000)
+    t["sem_logit"] = sem_logits(rng, t["pred_sem"], 3)
+    inst = np.where(t["pred_sem"] > 0, t["pred_inst"], 0)
+    fg = sem_logits(rng, (inst > 0).astype(np.uint8), 2)
+    e = np.exp(fg - fg.max(0, keepdims=True))
+    t["fore_map"] = np.ascontiguousarray((e / e.sum(0, keepdims=True))[1].astype(np.float32))
+    t["hv_map"] = ndi.gaussian_filter(hv_map(rng, inst), (1.0, 1.0, 0)).astype(np.float32)
+    return t
+
+
+def tile_cdnet(config_id, tile_index, H=1000, W=1000, T=1):
+    """Config 4 (CDNet): 3-class (bg / inside / edge) logits, 9-class direction logits, point map, per TTA
+    variant, + GT."""
+    seed = 1000 * config_id + tile_index
+    t = gt_and_pred(seed, H, W, num_classes=2)
+    rng = np.random.default_rng(seed + 500000)
+    inst = np.where(t["pred_sem"] > 0, t["pred_inst"], 0)
+    tc = three_class_map(inst)
+    t["sem_logit"] = np.stack([sem_logits(rng, tc, 3) for _ in range(T)])
+    dirs, pts = zip(*[direction_logits(rng, inst) for _ in range(T)])
+    t["dir_logit"] = np.stack(dirs)
+    t["point_logit"] = np.stack(pts)
+    return t
