@@ -1,0 +1,76 @@
+"""Host-side multi-rank logic on CPU (gloo, world_size 2): sharding, record packing, the gather that replaces
+collect_results_cpu, and evaluate() giving the same numbers as a single process."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import tiseg_b200  # noqa: E402,F401
+from tiseg_b200 import datasets, parallel, synth  # noqa: E402
+from refpipe import oracle_pre_eval, same_result  # noqa: E402
+
+
+def _make(n, C, multi):
+    tiles = [synth.gt_and_pred(4000 + i, 64, 72, num_classes=C) for i in range(n)]
+    res = [oracle_pre_eval(dict(sem_pred=t['pred_sem'], inst_pred=t['pred_inst']), t['gt_sem'], t['gt_inst'], C,
+                           multi=multi, name=None if multi else "img%d" % i) for i, t in enumerate(tiles)]
+    return res
+
+
+def test_pack_unpack_roundtrip():
+    for C, multi in ((2, False), (7, True)):
+        res = _make(3, C, multi)
+        back = parallel.unpack_results(parallel.pack_results(res, C), C, None if multi else [r['name'] for r in res])
+        for a, b in zip(res, back):
+            same_result(a, b)
+
+
+def test_shard_indices_interleave():
+    assert parallel.shard_indices(7, 0, 2) == [0, 2, 4, 6] and parallel.shard_indices(7, 1, 2) == [1, 3, 5]
+    assert sorted(sum((parallel.shard_indices(4981, r, 8) for r in range(8)), [])) == list(range(4981))
+
+
+def _worker(rank, world, port, C, multi, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = _make(n, C, multi)
+        mine = parallel.shard_indices(n, rank, world)
+        names = None if multi else [r['name'] for r in res]
+        full = parallel.gather_results([res[i] for i in mine], mine, n, C, names)
+        ints = parallel.all_reduce_sums([sum(r['bin_pq_pre_eval_res'][0] for r in (res[i] for i in mine)), len(mine)])
+        if rank == 0:
+            for a, b in zip(res, full):
+                same_result(a, b)
+            ds = (datasets.CoNICDataset if multi else datasets.CustomDataset)(inst_gts=[None] * n, sem_gts=[None] * n)
+            want, _ = ds.evaluate(res, logger="silent")
+            got, _ = ds.evaluate(full, logger="silent")
+            assert want == got and len(want) > 8
+            assert int(ints[0]) == sum(r['bin_pq_pre_eval_res'][0] for r in res) and int(ints[1]) == n
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("C,multi", [(2, False), (7, True)])
+def test_gather_results_gloo_world2(C, multi):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (1 if multi else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, C, multi, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(msg == "ok" for _, msg in out), out

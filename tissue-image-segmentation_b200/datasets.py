@@ -1,0 +1,269 @@
+"""Evaluation side of the reference's datasets: ``pre_eval`` (per-image metric pre-results) and ``evaluate``
+(dataset-level reduction) with the reference's signatures, result-dict keys and ``eval_results`` key names
+(``tiseg/datasets/custom.py:219-435``, ``tiseg/datasets/conic.py:126-323``).
+
+Ground truth comes either from files laid out like the reference's converted datasets (``*_sem.png`` read with
+pillow, ``*_inst.npy``; ``custom.py:252-259``) or from arrays handed in at construction.  ``pre_eval`` batches
+all predictions of one call that share a shape into ONE pass over the CUDA library (the reference loops over
+images on the CPU); ``evaluate`` is host arithmetic on a handful of numbers per image.
+"""
+import os
+import os.path as osp
+from collections import OrderedDict
+
+import numpy as np
+
+from . import metrics as M
+from . import ops
+from ._lib import is_torch
+
+
+def _table(columns):
+    """Plain-text table from an ordered mapping name -> list of cells."""
+    cols = [[str(k)] + [("%.2f" % v if isinstance(v, (float, np.floating)) else str(v)) for v in vals]
+            for k, vals in columns.items()]
+    widths = [max(len(c) for c in col) for col in cols]
+    rows = zip(*cols)
+    return "\n".join(" | ".join(c.rjust(w) for c, w in zip(r, widths)) for r in rows)
+
+
+def _log(msg, logger=None):
+    if logger is None:
+        print(msg)
+    elif hasattr(logger, "info"):
+        logger.info(msg)
+
+
+def _host(a):
+    return a.cpu().numpy() if is_torch(a) else np.asarray(a)
+
+
+class CustomDataset:
+    """Nuclei dataset evaluation (binary instance metrics + semantic metrics): custom.py."""
+
+    CLASSES = ('background', 'nuclei')
+
+    def __init__(self, data_infos=None, sem_gts=None, inst_gts=None, names=None, classes=None,
+                 img_dir=None, ann_dir=None, img_suffix='.tif', sem_suffix='_sem.png', inst_suffix='_inst.npy',
+                 split=None):
+        if classes is not None:
+            self.CLASSES = tuple(classes)
+        self.sem_suffix, self.inst_suffix, self.img_suffix = sem_suffix, inst_suffix, img_suffix
+        self._sem_gts, self._inst_gts = sem_gts, inst_gts
+        if data_infos is None and ann_dir is not None:
+            data_infos = self.load_annotations(img_dir, img_suffix, ann_dir, sem_suffix, inst_suffix, split)
+        if data_infos is None:
+            n = len(inst_gts)
+            names = list(names) if names is not None else ["%d" % i for i in range(n)]
+            data_infos = [dict(file_name=nm + img_suffix, sem_file_name=nm + sem_suffix, inst_file_name=nm + inst_suffix)
+                          for nm in names]
+        self.data_infos = data_infos
+
+    def __len__(self):
+        return len(self.data_infos)
+
+    @staticmethod
+    def load_annotations(img_dir, img_suffix, ann_dir, sem_suffix, inst_suffix, split=None):
+        """File listing of custom.py:180-217: names from the split file or from the *_sem.png files."""
+        if split is not None:
+            names = [ln.strip() for ln in open(split) if ln.strip()]
+        else:
+            names = sorted(f[:-len(sem_suffix)] for f in os.listdir(ann_dir) if f.endswith(sem_suffix))
+        return [dict(file_name=osp.join(img_dir or "", nm + img_suffix), sem_file_name=osp.join(ann_dir, nm + sem_suffix),
+                     inst_file_name=osp.join(ann_dir, nm + inst_suffix)) for nm in names]
+
+    # ---- ground truth
+    def _load_gt(self, index):
+        if self._inst_gts is not None:
+            return self._sem_gts[index], self._inst_gts[index]
+        from PIL import Image
+        info = self.data_infos[index]
+        sem_gt = np.array(Image.open(info['sem_file_name']))          # mmcv.imread(flag='unchanged', backend='pillow')
+        inst_gt = np.load(info['inst_file_name'])
+        return sem_gt, inst_gt
+
+    def _gather(self, preds, indices):
+        if not isinstance(indices, list):
+            indices = [indices]
+        if not isinstance(preds, list):
+            preds = [preds]
+        sem_gt, inst_gt = zip(*[self._load_gt(i) for i in indices])
+        return preds, indices, sem_gt, inst_gt
+
+    @staticmethod
+    def _stack(arrs, dtype):
+        """Same-shaped per-image arrays -> one batch (CUDA tensors stay on the device)."""
+        if is_torch(arrs[0]):
+            import torch
+            return torch.stack([a for a in arrs])
+        return np.stack([np.asarray(a) for a in arrs]).astype(dtype, copy=False)
+
+    def _groups(self, preds):
+        by_shape = OrderedDict()
+        for k, p in enumerate(preds):
+            by_shape.setdefault(tuple(p['inst_pred'].shape), []).append(k)
+        return by_shape.values()
+
+    def pre_eval(self, preds, indices, show=False, show_folder=None):
+        """custom.py:219-305.  preds: list of {'sem_pred', 'inst_pred'}; returns one dict per image with
+        ``name``, ``bin_aji_pre_eval_res``, ``bin_pq_pre_eval_res``, ``sem_pre_eval_res``."""
+        if show:
+            raise NotImplementedError("drawing (show=True) is outside the rebuilt path")
+        preds, indices, sem_gts, inst_gts = self._gather(preds, indices)
+        out = [None] * len(preds)
+        C = len(self.CLASSES)
+        for ks in self._groups(preds):
+            sem_p = self._stack([preds[k]['sem_pred'] for k in ks], np.uint8)
+            inst_p = self._stack([preds[k]['inst_pred'] for k in ks], np.int32)
+            sem_g = np.stack([np.asarray(sem_gts[k]) for k in ks]).astype(np.uint8, copy=False)
+            inst_g = np.stack([np.asarray(inst_gts[k]) for k in ks]).astype(np.int32, copy=False)
+            sem_res = M.pre_eval_all_semantic_metric(sem_p, sem_g, C)
+            # re_instance + measure.label of both maps happen inside the pair kernel (custom.py:272-277)
+            aji, pq = ops.pair_metrics_bin(inst_p, inst_g)
+            aji, pq = _host(aji), _host(pq)
+            for j, k in enumerate(ks):
+                info = self.data_infos[indices[k]]
+                data_id = osp.basename(info['sem_file_name']).replace(self.sem_suffix, '')
+                out[k] = dict(
+                    name=data_id,
+                    bin_aji_pre_eval_res=(np.float64(aji[j, 0]), np.float64(aji[j, 1])),
+                    bin_pq_pre_eval_res=(int(pq[j, 0]), int(pq[j, 1]), int(pq[j, 2]), np.float64(pq[j, 3])),
+                    sem_pre_eval_res=sem_res[j])
+        return out
+
+    @staticmethod
+    def _columns(results):
+        cols = {}
+        for r in results:
+            for k, v in r.items():
+                cols.setdefault(k, []).append(v)
+        return cols
+
+    def evaluate(self, results, logger=None, **kwargs):
+        """custom.py:307-435 -> (eval_results, storage_results)."""
+        ret, img = self._columns(results), {}
+        names = ret.pop('name')
+        sem = ret.pop('sem_pre_eval_res')
+        ret.update(M.pre_eval_to_sem_metrics(sem, metrics=['Dice', 'Precision', 'Recall']))
+        img.update(M.pre_eval_to_imw_sem_metrics(sem, metrics=['Dice', 'Precision', 'Recall']))
+        baji = ret.pop('bin_aji_pre_eval_res')
+        ret.update(M.pre_eval_to_aji(baji))
+        ret.update({'b' + k: v for k, v in M.pre_eval_to_bin_aji(baji).items()})
+        img.update(M.pre_eval_to_imw_aji(baji))
+        bpq = ret.pop('bin_pq_pre_eval_res')
+        ret.update(M.pre_eval_to_pq(bpq))
+        ret.update({'b' + k: v for k, v in M.pre_eval_to_bin_pq(bpq).items()})
+        ret.update(M.pre_eval_to_inst_dice(bpq))
+        img.update(M.pre_eval_to_imw_pq(bpq))
+        img.update(M.pre_eval_to_imw_inst_dice(bpq))
+
+        names = list(names) + ['Average']
+        for key in img:
+            v = np.asarray(img[key])
+            if v.ndim == 2:
+                v = v[:, 0]
+            img[key] = np.append(v, np.nanmean(v))
+
+        vital = ['Dice', 'Precision', 'Recall', 'Aji', 'DQ', 'SQ', 'PQ', 'InstDice']
+        mean_metrics = OrderedDict(('imw' + k, img[k][-1]) for k in vital)
+        overall = OrderedDict(('m' + k, ret[k]) for k in vital)
+        for k in ['bAji', 'bDQ', 'bSQ', 'bPQ']:
+            overall[k] = ret[k]
+
+        sample = OrderedDict(name=names)
+        sample.update((k, np.round(np.asarray(v) * 100, 2)) for k, v in img.items())
+        _log('Per samples:\n' + _table(sample), logger)
+        mean_metrics = OrderedDict((k, np.round(np.mean(v) * 100, 2)) for k, v in mean_metrics.items())
+        overall = OrderedDict((k, np.round(np.mean(v) * 100, 2)) for k, v in overall.items())
+        _log('Mean Total:\n' + _table(OrderedDict((k, [v]) for k, v in mean_metrics.items())), logger)
+        _log('Overall Total:\n' + _table(OrderedDict((k, [v]) for k, v in overall.items())), logger)
+
+        storage_results = {'mean_metrics': mean_metrics, 'overall_metrics': overall}
+        eval_results = {}
+        eval_results.update(mean_metrics)
+        eval_results.update(overall)
+        return eval_results, storage_results
+
+
+class MoNuSegDataset(CustomDataset):
+    CLASSES = ('background', 'nuclei')
+
+
+class CPM17Dataset(CustomDataset):
+    CLASSES = ('background', 'nuclei')
+
+
+class CoNSePDataset(CustomDataset):
+    CLASSES = ('background', 'nuclei')
+
+
+class CoNICDataset(CustomDataset):
+    """Multi-class nuclei evaluation: conic.py."""
+
+    CLASSES = ('background', 'neutrophil', 'epithelial', 'lymphocyte', 'plasma', 'eosinophil', 'connective')
+
+    def pre_eval(self, preds, indices, show=False, show_folder='.nuclei_show'):
+        """conic.py:126-198: adds the per-class ``aji_pre_eval_res`` / ``pq_pre_eval_res``."""
+        if show:
+            raise NotImplementedError("drawing (show=True) is outside the rebuilt path")
+        preds, indices, sem_gts, inst_gts = self._gather(preds, indices)
+        out = [None] * len(preds)
+        C = len(self.CLASSES)
+        for ks in self._groups(preds):
+            sem_p = self._stack([preds[k]['sem_pred'] for k in ks], np.uint8)
+            inst_p = self._stack([preds[k]['inst_pred'] for k in ks], np.int32)
+            sem_g = np.stack([np.asarray(sem_gts[k]) for k in ks]).astype(np.uint8, copy=False)
+            inst_g = np.stack([np.asarray(inst_gts[k]) for k in ks]).astype(np.int32, copy=False)
+            sem_res = M.pre_eval_all_semantic_metric(sem_p, sem_g, C)
+            r = ops.pair_metrics_multiclass(inst_p, sem_p, inst_g, sem_g, C)
+            aji, pq = _host(r['aji']).astype(np.float32), _host(r['pq']).astype(np.float32)
+            baji, bpq = _host(r['bin_aji']), _host(r['bin_pq'])
+            for j, k in enumerate(ks):
+                out[k] = dict(
+                    bin_aji_pre_eval_res=(np.float64(baji[j, 0]), np.float64(baji[j, 1])),
+                    aji_pre_eval_res=(aji[j, 1:, 0], aji[j, 1:, 1]),
+                    bin_pq_pre_eval_res=(int(bpq[j, 0]), int(bpq[j, 1]), int(bpq[j, 2]), np.float64(bpq[j, 3])),
+                    pq_pre_eval_res=tuple(pq[j, 1:, q] for q in range(4)),
+                    sem_pre_eval_res=sem_res[j])
+        return out
+
+    def evaluate(self, results, logger=None, **kwargs):
+        """conic.py:200-323 -> (eval_results, storage_results) incl. the per-class ``Metric.class`` entries."""
+        ret, img = self._columns(results), {}
+        ret.pop('name', None)
+        sem = ret.pop('sem_pre_eval_res')
+        ret.update(M.pre_eval_to_sem_metrics(sem, metrics=['Dice', 'Precision', 'Recall']))
+        img.update(M.pre_eval_to_imw_sem_metrics(sem, metrics=['Dice', 'Precision', 'Recall']))
+        aji, baji = ret.pop('aji_pre_eval_res'), ret.pop('bin_aji_pre_eval_res')
+        ret.update(M.pre_eval_to_aji(aji))
+        ret.update({'b' + k: v for k, v in M.pre_eval_to_bin_aji(baji).items()})
+        img.update(M.pre_eval_to_imw_aji(baji))
+        pq, bpq = ret.pop('pq_pre_eval_res'), ret.pop('bin_pq_pre_eval_res')
+        ret.update(M.pre_eval_to_pq(pq))
+        ret.update({'b' + k: v for k, v in M.pre_eval_to_bin_pq(bpq).items()})
+        img.update(M.pre_eval_to_imw_pq(bpq))
+
+        vital = ['Dice', 'Precision', 'Recall', 'Aji', 'DQ', 'SQ', 'PQ']
+        mean_metrics, overall, per_class = OrderedDict(), OrderedDict(), OrderedDict()
+        for k in vital:
+            mean_metrics['imw' + k] = np.nanmean(img[k])
+            overall['m' + k] = np.nanmean(ret[k])
+            v = np.asarray(ret[k], dtype=np.float64).ravel()
+            per_class[k] = np.round(np.append(v, np.nanmean(v)) * 100, 2)
+        for k in ['bAji', 'bDQ', 'bSQ', 'bPQ']:
+            overall[k] = ret[k]
+        classes = list(self.CLASSES[1:]) + ['average']
+        tab = OrderedDict(classes=classes)
+        tab.update(per_class)
+        _log('Per classes:\n' + _table(tab), logger)
+        mean_metrics = OrderedDict((k, np.round(np.mean(v) * 100, 2)) for k, v in mean_metrics.items())
+        overall = OrderedDict((k, np.round(np.mean(v) * 100, 2)) for k, v in overall.items())
+        _log('Mean Total:\n' + _table(OrderedDict((k, [v]) for k, v in mean_metrics.items())), logger)
+        _log('Overall Total:\n' + _table(OrderedDict((k, [v]) for k, v in overall.items())), logger)
+        storage_results = {'mean_metrics': mean_metrics, 'overall_metrics': overall}
+        eval_results = {}
+        eval_results.update(overall)
+        eval_results.update(mean_metrics)
+        for key, value in per_class.items():
+            eval_results.update({key + '.' + str(name): f'{value[idx]:.3f}' for idx, name in enumerate(classes)})
+        return eval_results, storage_results

@@ -1,0 +1,153 @@
+"""Multi-GPU evaluation: one process per GPU, tiles sharded by index, and the ONLY communication is the exchange
+of metric records — replacing the reference's ``collect_results_cpu`` (``tiseg/apis/test.py:104``: a tmpdir name
+broadcast, one pickle file per rank on a shared filesystem, a barrier, and an unpickle + interleave on rank 0).
+
+* ``shard_indices``   — the interleaved split of ``DistributedSampler(shuffle=False)`` (``datasets/builder.py:74``).
+* ``all_reduce_sums`` — one all-reduce of the integer accumulators (int64, exact) and one of the fp64 IoU sums.
+* ``gather_results``  — all-gather of fixed-width per-image records so that ``Dataset.evaluate`` (which needs the
+                        image-wise metrics) sees exactly the list a single process would have produced, in index
+                        order.  ~100 bytes per image.
+
+Works with the ``nccl`` backend (records live on the rank's GPU, NVLink / NVSwitch) and with ``gloo`` (CPU tests).
+"""
+import numpy as np
+
+
+def shard_indices(n_items, rank, world_size):
+    return list(range(rank, n_items, world_size))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _device_for_backend():
+    import torch
+    dist = _dist()
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+# --------------------------------------------------------------------------- record packing
+_BIN_KEYS = ("bin_aji_pre_eval_res", "bin_pq_pre_eval_res")
+
+
+def pack_results(results, num_classes):
+    """list of pre_eval dicts -> float64 array [n, R].  Layout: bin aji (2), bin pq (4), sem (6 x (C-1)),
+    then, when present (CoNIC), aji (2 x (C-1)) and pq (4 x (C-1)).  All values are integers or fp64 sums, so
+    fp64 carries them exactly."""
+    c1 = num_classes - 1
+    multi = len(results) > 0 and "aji_pre_eval_res" in results[0]
+    width = 6 + 6 * c1 + (6 * c1 if multi else 0)
+    out = np.zeros((len(results), width), np.float64)
+    for i, r in enumerate(results):
+        row = [*r["bin_aji_pre_eval_res"], *r["bin_pq_pre_eval_res"]]
+        for t in r["sem_pre_eval_res"]:
+            row.extend(np.asarray(t, dtype=np.float64).ravel().tolist())
+        if multi:
+            for t in r["aji_pre_eval_res"]:
+                row.extend(np.asarray(t, dtype=np.float64).ravel().tolist())
+            for t in r["pq_pre_eval_res"]:
+                row.extend(np.asarray(t, dtype=np.float64).ravel().tolist())
+        out[i] = row
+    return out
+
+
+def unpack_results(records, num_classes, names=None):
+    """Inverse of ``pack_results`` (types as ``Dataset.pre_eval`` produces them)."""
+    import torch
+    c1 = num_classes - 1
+    multi = records.shape[1] == 6 + 12 * c1
+    out = []
+    for i, row in enumerate(records):
+        d = {}
+        if names is not None:
+            d["name"] = names[i]
+        d["bin_aji_pre_eval_res"] = (np.float64(row[0]), np.float64(row[1]))
+        d["bin_pq_pre_eval_res"] = (int(row[2]), int(row[3]), int(row[4]), np.float64(row[5]))
+        o = 6
+        d["sem_pre_eval_res"] = tuple(torch.from_numpy(row[o + k * c1:o + (k + 1) * c1].astype(np.float32)) for k in range(6))
+        o += 6 * c1
+        if multi:
+            d["aji_pre_eval_res"] = tuple(row[o + k * c1:o + (k + 1) * c1].astype(np.float32) for k in range(2))
+            o += 2 * c1
+            d["pq_pre_eval_res"] = tuple(row[o + k * c1:o + (k + 1) * c1].astype(np.float32) for k in range(4))
+        out.append(d)
+    return out
+
+
+# --------------------------------------------------------------------------- collectives
+def gather_results(results, indices, n_total, num_classes, names=None):
+    """Every rank passes the pre_eval dicts of ITS tiles and their dataset indices; every rank gets back the full
+    list in index order (what ``collect_results_cpu`` returns on rank 0), duplicates from sampler padding dropped."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    dev = _device_for_backend()
+    rec = pack_results(results, num_classes)
+    width = rec.shape[1] if len(results) else 0
+    meta = torch.tensor([len(results), width], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    counts = [int(m[0]) for m in metas]
+    width = max(int(m[1]) for m in metas)
+    cap = max(counts) if counts else 0
+    buf = torch.zeros((cap, width + 1), dtype=torch.float64, device=dev)
+    if len(results):
+        buf[:len(results), 0] = torch.as_tensor(np.asarray(indices, np.float64), device=dev)
+        buf[:len(results), 1:] = torch.as_tensor(rec, device=dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    full = np.zeros((n_total, width), np.float64)
+    seen = np.zeros(n_total, bool)
+    for r, b in enumerate(bufs):
+        b = b[:counts[r]].cpu().numpy()
+        for row in b:
+            i = int(row[0])
+            if 0 <= i < n_total and not seen[i]:
+                full[i] = row[1:]
+                seen[i] = True
+    if not seen.all():
+        raise RuntimeError("gather_results: %d tiles have no record" % int((~seen).sum()))
+    return unpack_results(full, num_classes, names)
+
+
+def all_reduce_sums(int_sums, float_sums=None):
+    """Sum integer accumulators (exact, int64) and optional fp64 accumulators over the ranks; returns numpy."""
+    import torch
+    dist = _dist()
+    dev = _device_for_backend()
+    a = torch.as_tensor(np.asarray(int_sums, np.int64), device=dev)
+    dist.all_reduce(a)
+    out = a.cpu().numpy()
+    if float_sums is None:
+        return out
+    f = torch.as_tensor(np.asarray(float_sums, np.float64), device=dev)
+    dist.all_reduce(f)
+    return out, f.cpu().numpy()
+
+
+def distributed_test(dataset, predict_fn, batch_size=32, num_classes=None):
+    """The reference's ``multi_gpu_test`` loop (``tiseg/apis/test.py:47-105``) for the rebuilt path:
+    rank r evaluates tiles r, r+W, ...; ``predict_fn(indices) -> list of {'sem_pred','inst_pred'}`` produces the
+    predictions (CNN + post-process); the records are exchanged once.  Returns the full result list on every rank."""
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = shard_indices(len(dataset), rank, world)
+    results = []
+    for s in range(0, len(mine), batch_size):
+        idx = mine[s:s + batch_size]
+        results.extend(dataset.pre_eval(predict_fn(idx), idx))
+    C = num_classes or len(dataset.CLASSES)
+    names = [r.get("name") for r in results] if results and "name" in results[0] else None
+    all_names = None
+    if names is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, list(zip(mine, names)))
+        all_names = [None] * len(dataset)
+        for part in gathered:
+            for i, nm in part:
+                all_names[i] = nm
+    return gather_results(results, mine, len(dataset), C, all_names)
