@@ -74,7 +74,9 @@ def test_config3_hovernet_consep(size):
         cls = opp.argmax_classes(opp.softmax(t['sem_logit']))
         i, _ = opp.hover_post_proc(t['fore_map'], t['hv_map'])
         want.append(dict(sem_pred=cls.astype(np.uint8), inst_pred=i))
-    _check(datasets.CoNSePDataset, C, tiles, preds, want)
+    class ThreeClass(datasets.CoNSePDataset):
+        CLASSES = ('background', 'type1', 'type2')
+    _check(ThreeClass, C, tiles, preds, want)
 
 
 @pytest.mark.parametrize("size,T", [(256, 2), (1000, 1)])
