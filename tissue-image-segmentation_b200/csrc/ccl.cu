@@ -4,15 +4,31 @@
 
 namespace tiseg {
 
-__global__ void k_ccl_flatten(Geom g, int* par) {
+// every foreground pixel points directly at its root; blk[n, block] = number of roots in the block
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, int* __restrict__ blk) {
+    __shared__ int s[TISEG_WARPS_PER_BLOCK];
     Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    int* tp = par + px.base;
-    int p = tp[px.idx];
-    if (p < 0) return;
-    int r = p;
-    for (int q = tp[r]; q != r; q = tp[r]) r = q;
-    if (r != p) tp[px.idx] = r;
+    bool act = warp_pixel(g, px) && px.ok;
+    bool root = false;
+    if (act) {
+        int* tp = par + px.base;
+        int p = tp[px.idx];
+        if (p >= 0) {
+            int r = p;
+            for (int q = tp[r]; q != r; q = tp[r]) r = q;
+            if (r != p) tp[px.idx] = r;
+            root = r == px.idx;
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, root);
+    if (px.lane == 0) s[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < TISEG_WARPS_PER_BLOCK; ++i) t += s[i];
+        blk[(long long)blockIdx.y * g.bpt + blockIdx.x] = t;
+    }
 }
 
 __global__ void k_rank_scan(int bpt, int* blk, int* counts) {
@@ -65,7 +81,11 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* 
 }
 
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
-    TISEG_LAUNCH(c, k_ccl_flatten, warp_grid(g), TISEG_THREADS, 0, g, par);
+    int* blk = ws<int>(c, (size_t)g.N * g.bpt);
+    if (!blk) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_ccl_flatten, warp_grid(g), TISEG_THREADS, 0, g, par, blk);
+    c->rootblk_par = par;             // rank_roots on this forest can skip its counting pass
+    c->rootblk = blk;
     return TISEG_OK;
 }
 
@@ -75,6 +95,14 @@ int rank_scan(tiseg_ctx* c, int N, int bpt, int* blk, int* counts) {
 }
 
 int rank_roots(tiseg_ctx* c, const Geom& g, const int* par, int* rank, int* counts) {
+    if (c->rootblk_par == par && c->rootblk) {
+        // the flatten pass already counted the roots per block: scan + place only
+        int* blk = c->rootblk;
+        c->rootblk_par = nullptr;
+        TISEG_TRY(rank_scan(c, g.N, g.bpt, blk, counts));
+        TISEG_LAUNCH(c, k_rank_place<SelRoot>, warp_grid(g), TISEG_THREADS, 0, g, SelRoot{par}, blk, rank);
+        return TISEG_OK;
+    }
     return rank_generic(c, g, SelRoot{par}, rank, counts);
 }
 

@@ -9,6 +9,8 @@
 // par[n*P + idx] = tile-local flat index of the parent (root = lowest index of the component = first pixel
 // in raster order, which is what makes skimage's numbering reproducible), -1 for background.
 #pragma once
+#include <climits>
+
 #include "common.cuh"
 
 namespace tiseg {
@@ -63,76 +65,130 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 };
 
 #ifdef __CUDACC__
-// ---- pass 1: row runs.  Every foreground pixel points at the start of its horizontal run inside its
-// 32-pixel segment (ballot + clz: no memory traffic for in-run merging).
-template <class Img>
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_init(Geom g, Img img, int* __restrict__ par) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int v = 0;
-    bool fg = px.ok && img(px.n, px.base + px.idx, v);
-    int vl = __shfl_up_sync(0xffffffffu, v, 1);
-    bool fgl = __shfl_up_sync(0xffffffffu, (int)fg, 1);
-    if (px.lane == 0) fgl = false;                       // cross-segment continuation is merged in pass 2
-    bool cont = fg && fgl && vl == v;
-    unsigned m = __ballot_sync(0xffffffffu, cont);
-    if (px.ok) par[px.base + px.idx] = fg ? px.idx - (px.lane - run_start_lane(m, px.lane)) : -1;
-}
+// =====================================================================================================
+// Three launches per labelling:
+//   k_ccl_local   one CTA per 64-row x 32-column tile: values staged in shared memory, union-find entirely in
+//                 shared memory (row runs by ballot/clz, merges with the row above by shared atomicMin), flattened
+//                 locally, then ONE coalesced global write per pixel: the tile-global index of its local root.
+//   k_ccl_border  only the pixels on tile borders (~8 %) merge across tiles with global atomicMin unions.
+//   k_ccl_flatten every pixel points at its global root (lowest flat index of the component = first pixel in
+//                 raster order); also counts the roots per block for the id ranking that usually follows.
+// =====================================================================================================
+#define CCL_TH 64                       // tile rows (8 warps x 8 rows); tile width is one warp = 32 columns
+#define CCL_BG INT_MIN                  // background marker inside the shared value tile
 
-// ---- pass 2: merge runs with the row above (and with the previous segment of the same row).
-// Redundant unions are skipped: a pixel whose left neighbour continues its run and whose upper-left
-// neighbour has the same value is already connected through them.
 template <class Img, int CONN>
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_merge(Geom g, Img img, int* par) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int v = 0;
-    bool fg = px.ok && img(px.n, px.base + px.idx, v);
-    // left neighbour (lane 0 reads the last pixel of the previous segment)
-    int vl = __shfl_up_sync(0xffffffffu, v, 1);
-    bool fgl = __shfl_up_sync(0xffffffffu, (int)fg, 1);
-    if (px.lane == 0) {
-        fgl = false;
-        if (px.x > 0) fgl = img(px.n, px.base + px.idx - 1, vl);
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
+    __shared__ int sval[CCL_TH * 32];
+    __shared__ int slab[CCL_TH * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ty = blockIdx.x / g.SEG, tx = blockIdx.x - ty * g.SEG;
+    const int n = blockIdx.y;
+    const int x = tx * 32 + lane;
+    const bool okx = x < g.W;
+    const long long base = (long long)n * g.P;
+    const int row0 = warp * 8, y0 = ty * CCL_TH + row0;
+    // phase A: coalesced loads (8 independent rows in flight per lane), row-run initialisation
+    int v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int y = y0 + r, vv = 0;
+        v[r] = CCL_BG;
+        if (okx && y < g.H && img(n, base + (long long)y * g.W + x, vv)) v[r] = vv;
     }
-    bool sameL = fg && fgl && vl == v;
-    // row above
-    int vu = 0; bool fgu = false;
-    if (px.y > 0 && px.ok) fgu = img(px.n, px.base + px.idx - g.W, vu);
-    int vul = __shfl_up_sync(0xffffffffu, vu, 1);
-    bool fgul = __shfl_up_sync(0xffffffffu, (int)fgu, 1);
-    int vur = __shfl_down_sync(0xffffffffu, vu, 1);
-    bool fgur = __shfl_down_sync(0xffffffffu, (int)fgu, 1);
-    if (px.lane == 0) {
-        fgul = false;
-        if (px.y > 0 && px.x > 0) fgul = img(px.n, px.base + px.idx - g.W - 1, vul);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
+        bool cont = lane > 0 && v[r] != CCL_BG && vl == v[r];
+        unsigned m = __ballot_sync(0xffffffffu, cont);
+        int li = (row0 + r) * 32 + lane;
+        sval[li] = v[r];
+        slab[li] = v[r] != CCL_BG ? (row0 + r) * 32 + run_start_lane(m, lane) : -1;
     }
-    if (px.lane == 31) {
-        fgur = false;
-        if (CONN == 2 && px.y > 0 && px.x + 1 < g.W) fgur = img(px.n, px.base + px.idx - g.W + 1, vur);
+    __syncthreads();
+    // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int row = row0 + r, li = row * 32 + lane;
+        if (row == 0 || v[r] == CCL_BG) continue;
+        int u = sval[li - 32];
+        int ul = lane > 0 ? sval[li - 33] : CCL_BG;
+        int ur = lane < 31 ? sval[li - 31] : CCL_BG;
+        bool sameL = lane > 0 && sval[li - 1] == v[r];
+        if (u == v[r]) {
+            if (!(sameL && ul == v[r])) uf_union(slab, li, li - 32);
+        } else if (CONN == 2) {
+            if (ul == v[r] && !sameL) uf_union(slab, li, li - 33);
+            if (ur == v[r]) uf_union(slab, li, li - 31);
+        }
     }
-    if (px.x + 1 >= g.W) fgur = false;
-    if (!fg) return;
-    int* tp = par + px.base;
-    bool sU = fgu && vu == v, sUL = fgul && vul == v, sUR = fgur && vur == v;
-    if (px.lane == 0 && sameL) uf_union(tp, px.idx, px.idx - 1);
-    if (sU) {
-        if (!(sameL && sUL)) uf_union(tp, px.idx, px.idx - g.W);
-    } else if (CONN == 2) {
-        if (sUL && !sameL) uf_union(tp, px.idx, px.idx - g.W - 1);
-        if (sUR) uf_union(tp, px.idx, px.idx - g.W + 1);
+    __syncthreads();
+    // phase C: local flatten, one global write per pixel
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int y = y0 + r;
+        if (!okx || y >= g.H) continue;
+        int out = -1;
+        if (v[r] != CCL_BG) {
+            int root = uf_find(slab, (row0 + r) * 32 + lane);
+            out = (ty * CCL_TH + (root >> 5)) * g.W + tx * 32 + (root & 31);
+        }
+        par[base + (long long)y * g.W + x] = out;
     }
 }
 
-// ---- pass 3: flatten (every foreground pixel points directly at its root); defined in ccl.cu
+// Cross-tile merges.  Candidates: A) pixels of a tile's top row (y = 64k, k >= 1) look up / up-left / up-right;
+// B) pixels of a tile's left column (x = 32k, k >= 1) look left / up-left; C) (8-connectivity) pixels of a tile's
+// right column (x = 32k - 1) look up-right.  A diagonal union is skipped when the vertical neighbour has the same
+// value (it is then connected through that neighbour's own row).
+template <class Img, int CONN>
+__global__ void __launch_bounds__(256) k_ccl_border(Geom g, Img img, int* par) {
+    const int n = blockIdx.y;
+    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
+    const int nA = (tilesY - 1) * g.W, nB = (g.SEG - 1) * g.H, nC = CONN == 2 ? nB : 0;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nA + nB + nC) return;
+    int y, x, kind;
+    if (t < nA) { kind = 0; y = (t / g.W + 1) * CCL_TH; x = t - (t / g.W) * g.W; }
+    else if (t < nA + nB) { t -= nA; kind = 1; x = (t / g.H + 1) * 32; y = t - (t / g.H) * g.H; }
+    else { t -= nA + nB; kind = 2; x = (t / g.H + 1) * 32 - 1; y = t - (t / g.H) * g.H; }
+    const long long base = (long long)n * g.P;
+    const int idx = y * g.W + x;
+    int v = 0;
+    if (!img(n, base + idx, v)) return;
+    int* tp = par + base;
+    int w = 0;
+    bool sU = y > 0 && img(n, base + idx - g.W, w) && w == v;
+    if (kind == 0) {
+        if (sU) uf_union(tp, idx, idx - g.W);
+        else if (CONN == 2) {
+            if (x > 0 && img(n, base + idx - g.W - 1, w) && w == v) uf_union(tp, idx, idx - g.W - 1);
+            if (x + 1 < g.W && img(n, base + idx - g.W + 1, w) && w == v) uf_union(tp, idx, idx - g.W + 1);
+        }
+    } else if (kind == 1) {
+        if (img(n, base + idx - 1, w) && w == v) uf_union(tp, idx, idx - 1);
+        else if (CONN == 2 && !sU && y > 0 && img(n, base + idx - g.W - 1, w) && w == v) uf_union(tp, idx, idx - g.W - 1);
+    } else {
+        if (!sU && y > 0 && x + 1 < g.W && img(n, base + idx - g.W + 1, w) && w == v) uf_union(tp, idx, idx - g.W + 1);
+    }
+}
+
+// flatten + per-block root counts (warp_grid geometry); defined in ccl.cu
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par);
 
 // build + flatten.  par: [N*P] int
 template <class Img>
 int ccl_build(tiseg_ctx* c, const Geom& g, Img img, int conn, int* par) {
-    TISEG_LAUNCH(c, k_ccl_init<Img>, warp_grid(g), TISEG_THREADS, 0, g, img, par);
-    if (conn == 1) TISEG_LAUNCH(c, (k_ccl_merge<Img, 1>), warp_grid(g), TISEG_THREADS, 0, g, img, par);
-    else           TISEG_LAUNCH(c, (k_ccl_merge<Img, 2>), warp_grid(g), TISEG_THREADS, 0, g, img, par);
+    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
+    dim3 lg((unsigned)(g.SEG * tilesY), (unsigned)g.N);
+    const int nb = (tilesY - 1) * g.W + (g.SEG - 1) * g.H * (conn == 2 ? 2 : 1);
+    if (conn == 1) {
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 1>), lg, TISEG_THREADS, 0, g, img, par);
+        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
+    } else {
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 2>), lg, TISEG_THREADS, 0, g, img, par);
+        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
+    }
     return ccl_flatten(c, g, par);
 }
 #endif

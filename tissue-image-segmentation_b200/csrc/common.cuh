@@ -28,6 +28,9 @@ struct tiseg_ctx {
     std::vector<Pending> pending;
     long long launches = 0;
     int sm_count = 148;
+    // root counts per block left behind by the last ccl_flatten (consumed by rank_roots on the same forest)
+    const int* rootblk_par = nullptr;
+    int* rootblk = nullptr;
     // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
     bool timing = false;
     struct Timed { const char* name; cudaEvent_t a, b; };

@@ -31,6 +31,8 @@ void begin_call(tiseg_ctx* c) {
     c->cur_block = 0;
     c->cur_off = 0;
     c->pending.clear();
+    c->rootblk_par = nullptr;
+    c->rootblk = nullptr;
 }
 
 void* ws_alloc(tiseg_ctx* c, size_t bytes) {
