@@ -4,42 +4,47 @@
 
 namespace tiseg {
 
-// every foreground pixel points directly at its root; blk[n, block] = number of roots in the block
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, int* __restrict__ blk) {
-    __shared__ int s[TISEG_WARPS_PER_BLOCK];
-    Pix px;
-    bool act = warp_pixel(g, px) && px.ok;
-    bool root = false;
-    if (act) {
-        int* tp = par + px.base;
-        int p = tp[px.idx];
-        if (p >= 0) {
-            int r = p;
-            for (int q = tp[r]; q != r; q = tp[r]) r = q;
-            if (r != p) tp[px.idx] = r;
-            root = r == px.idx;
-        }
-    }
-    unsigned m = __ballot_sync(0xffffffffu, root);
-    if (px.lane == 0) s[threadIdx.x >> 5] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
+// every foreground pixel points directly at its root; cnt[n, y, seg] = number of roots in the row segment
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, int* __restrict__ cnt) {
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    int* tp = par + s.base;
+    int p[STRIP_R];
 #pragma unroll
-        for (int i = 0; i < TISEG_WARPS_PER_BLOCK; ++i) t += s[i];
-        blk[(long long)blockIdx.y * g.bpt + blockIdx.x] = t;
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        p[r] = (s.okx && y < g.H) ? tp[y * g.W + s.x] : -1;
+    }
+    int q[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) q[r] = p[r] >= 0 ? tp[p[r]] : -1;      // second hop, also independent
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r, idx = y * g.W + s.x;
+        bool root = false;
+        if (p[r] >= 0) {
+            int a = p[r], b = q[r];
+            while (b != a) { a = b; b = tp[a]; }
+            if (a != p[r]) tp[idx] = a;
+            root = a == idx;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, root);
+        if (s.lane == 0 && y < g.H) cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] = __popc(m);
     }
 }
 
-__global__ void k_rank_scan(int bpt, int* blk, int* counts) {
+// one block per tile: thread = row.  Pass 1: row totals -> block scan with carry -> row offsets; pass 2: the
+// exclusive prefix inside each row.  cnt[n, y, seg] becomes the raster-order exclusive prefix.
+__global__ void k_rank_scan(Geom g, int* cnt, int* counts) {
     __shared__ int s[256];
     __shared__ int carry;
-    int* b = blk + (long long)blockIdx.x * bpt;
+    int* b = cnt + (long long)blockIdx.x * g.H * g.SEG;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < bpt; base += 256) {
-        int i = base + threadIdx.x;
-        int v = i < bpt ? b[i] : 0;
+    for (int base = 0; base < g.H; base += 256) {
+        int y = base + threadIdx.x;
+        int v = 0;
+        if (y < g.H) for (int k = 0; k < g.SEG; ++k) v += b[(long long)y * g.SEG + k];
         s[threadIdx.x] = v;
         __syncthreads();
         for (int d = 1; d < 256; d <<= 1) {
@@ -50,7 +55,10 @@ __global__ void k_rank_scan(int bpt, int* blk, int* counts) {
         }
         int incl = s[threadIdx.x];
         int c0 = carry;
-        if (i < bpt) b[i] = c0 + incl - v;
+        if (y < g.H) {
+            int run = c0 + incl - v;
+            for (int k = 0; k < g.SEG; ++k) { int t = b[(long long)y * g.SEG + k]; b[(long long)y * g.SEG + k] = run; run += t; }
+        }
         __syncthreads();
         if (threadIdx.x == 255) carry = c0 + incl;
         __syncthreads();
@@ -58,62 +66,72 @@ __global__ void k_rank_scan(int bpt, int* blk, int* counts) {
     if (threadIdx.x == 0 && counts) counts[blockIdx.x] = carry;
 }
 
-__global__ void k_apply_rank(Geom g, const int* __restrict__ par,
-                                                              const int* __restrict__ rank, int32_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    int p = par[px.base + px.idx];
-    out[px.base + px.idx] = p >= 0 ? rank[px.base + p] : 0;
+// out = par >= 0 ? rank[par] : 0, four pixels per thread
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_apply_rank(long long P, const int* __restrict__ par, const int* __restrict__ rank, int32_t* __restrict__ out, bool vec) {
+    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+    if (i >= P) return;
+    Pack4<int> p = ld4(par + base, i, P, vec), o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = (i + k < P && p.v[k] >= 0) ? rank[base + p.v[k]] : 0;
+    st4(out + base, i, P, vec, o);
 }
 
 // area[root] += length of each in-segment run of pixels sharing the root (one atomic per run)
 __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* __restrict__ par, int* area) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int p = px.ok ? par[px.base + px.idx] : -1;
-    int pl = __shfl_up_sync(0xffffffffu, p, 1);
-    bool cont = px.lane > 0 && p >= 0 && pl == p;
-    unsigned m = __ballot_sync(0xffffffffu, cont);
-    if (p >= 0 && !cont) {
-        int len = run_end_lane(m, px.lane) - px.lane + 1;
-        atomicAdd(&area[px.base + p], len);
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    int p[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        p[r] = (s.okx && y < g.H) ? par[s.base + (long long)y * g.W + s.x] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int pl = __shfl_up_sync(0xffffffffu, p[r], 1);
+        bool cont = s.lane > 0 && p[r] >= 0 && pl == p[r];
+        unsigned m = __ballot_sync(0xffffffffu, cont);
+        if (p[r] >= 0 && !cont) atomicAdd(&area[s.base + p[r]], run_end_lane(m, s.lane) - s.lane + 1);
     }
 }
 
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
-    int* blk = ws<int>(c, (size_t)g.N * g.bpt);
-    if (!blk) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH(c, k_ccl_flatten, warp_grid(g), TISEG_THREADS, 0, g, par, blk);
+    int* cnt = ws<int>(c, (size_t)g.N * g.H * g.SEG);
+    if (!cnt) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_ccl_flatten, strip_grid(g), TISEG_THREADS, 0, g, par, cnt);
     c->rootblk_par = par;             // rank_roots on this forest can skip its counting pass
-    c->rootblk = blk;
+    c->rootblk = cnt;
     return TISEG_OK;
 }
 
-int rank_scan(tiseg_ctx* c, int N, int bpt, int* blk, int* counts) {
-    TISEG_LAUNCH(c, k_rank_scan, N, 256, 0, bpt, blk, counts);
+int rank_scan(tiseg_ctx* c, const Geom& g, int* cnt, int* counts) {
+    TISEG_LAUNCH(c, k_rank_scan, g.N, 256, 0, g, cnt, counts);
     return TISEG_OK;
 }
 
 int rank_roots(tiseg_ctx* c, const Geom& g, const int* par, int* rank, int* counts) {
     if (c->rootblk_par == par && c->rootblk) {
-        // the flatten pass already counted the roots per block: scan + place only
-        int* blk = c->rootblk;
+        // the flatten pass already counted the roots per row segment: scan + place only
+        int* cnt = c->rootblk;
         c->rootblk_par = nullptr;
-        TISEG_TRY(rank_scan(c, g.N, g.bpt, blk, counts));
-        TISEG_LAUNCH(c, k_rank_place<SelRoot>, warp_grid(g), TISEG_THREADS, 0, g, SelRoot{par}, blk, rank);
+        TISEG_TRY(rank_scan(c, g, cnt, counts));
+        TISEG_LAUNCH(c, k_rank_place<SelRoot>, strip_grid(g), TISEG_THREADS, 0, g, SelRoot{par}, cnt, rank);
         return TISEG_OK;
     }
     return rank_generic(c, g, SelRoot{par}, rank, counts);
 }
 
 int apply_rank(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, int32_t* out) {
-    TISEG_LAUNCH(c, k_apply_rank, warp_grid(g), TISEG_THREADS, 0, g, par, rank, out);
+    const long long P = g.P;
+    const bool vec = (P % 4 == 0) && aligned16(par, out);
+    TISEG_LAUNCH(c, k_apply_rank, dim3(flat4_grid(P), g.N), TISEG_THREADS, 0, P, par, rank, out, vec);
     return TISEG_OK;
 }
 
 int ccl_areas(tiseg_ctx* c, const Geom& g, const int* par, int* area) {
     TISEG_TRY(zero(c, area, (size_t)g.N * g.P * sizeof(int)));
-    TISEG_LAUNCH(c, k_ccl_areas, warp_grid(g), TISEG_THREADS, 0, g, par, area);
+    TISEG_LAUNCH(c, k_ccl_areas, strip_grid(g), TISEG_THREADS, 0, g, par, area);
     return TISEG_OK;
 }
 

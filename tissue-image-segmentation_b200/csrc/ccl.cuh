@@ -72,7 +72,7 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 //                 locally, then ONE coalesced global write per pixel: the tile-global index of its local root.
 //   k_ccl_border  only the pixels on tile borders (~8 %) merge across tiles with global atomicMin unions.
 //   k_ccl_flatten every pixel points at its global root (lowest flat index of the component = first pixel in
-//                 raster order); also counts the roots per block for the id ranking that usually follows.
+//                 raster order); also counts the roots per row segment for the id ranking that usually follows.
 // =====================================================================================================
 #define CCL_TH 64                       // tile rows (8 warps x 8 rows); tile width is one warp = 32 columns
 #define CCL_BG INT_MIN                  // background marker inside the shared value tile
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_ccl_border(Geom g, Img img, int* par) {
     }
 }
 
-// flatten + per-block root counts (warp_grid geometry); defined in ccl.cu
+// flatten + per-row-segment root counts; defined in ccl.cu
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par);
 
 // build + flatten.  par: [N*P] int
@@ -208,50 +208,56 @@ struct SelFlagU8 {
 };
 
 #ifdef __CUDACC__
+// cnt[n, y, seg] = selected pixels in that 32-pixel row segment
 template <class Sel>
-__global__ void __launch_bounds__(TISEG_THREADS) k_rank_count(Geom g, Sel sel, int* __restrict__ blk) {
-    __shared__ int s[TISEG_WARPS_PER_BLOCK];
-    Pix px;
-    bool act = warp_pixel(g, px);
-    bool f = act && px.ok && sel(px.base + px.idx, px.idx);
-    unsigned m = __ballot_sync(0xffffffffu, f);
-    if (px.lane == 0) s[threadIdx.x >> 5] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
+__global__ void __launch_bounds__(TISEG_THREADS) k_rank_count(Geom g, Sel sel, int* __restrict__ cnt) {
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    bool f[STRIP_R];
 #pragma unroll
-        for (int i = 0; i < TISEG_WARPS_PER_BLOCK; ++i) t += s[i];
-        blk[(long long)blockIdx.y * g.bpt + blockIdx.x] = t;
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        f[r] = s.okx && y < g.H && sel(s.base + (long long)y * g.W + s.x, y * g.W + s.x);
+    }
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        unsigned m = __ballot_sync(0xffffffffu, f[r]);
+        int y = s.y0 + r;
+        if (s.lane == 0 && y < g.H) cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] = __popc(m);
     }
 }
 
+// cnt holds, after rank_scan, the number of selected pixels before each row segment (raster order)
 template <class Sel>
-__global__ void __launch_bounds__(TISEG_THREADS) k_rank_place(Geom g, Sel sel, const int* __restrict__ blk,
+__global__ void __launch_bounds__(TISEG_THREADS) k_rank_place(Geom g, Sel sel, const int* __restrict__ cnt,
                                                               int* __restrict__ rank) {
-    __shared__ int s[TISEG_WARPS_PER_BLOCK];
-    Pix px;
-    bool act = warp_pixel(g, px);
-    bool f = act && px.ok && sel(px.base + px.idx, px.idx);
-    unsigned m = __ballot_sync(0xffffffffu, f);
-    int w = threadIdx.x >> 5;
-    if (px.lane == 0) s[w] = __popc(m);
-    __syncthreads();
-    if (!f) return;
-    int off = blk[(long long)blockIdx.y * g.bpt + blockIdx.x];
-    for (int i = 0; i < w; ++i) off += s[i];
-    rank[px.base + px.idx] = off + __popc(m & ((1u << px.lane) - 1)) + 1;
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    bool f[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        f[r] = s.okx && y < g.H && sel(s.base + (long long)y * g.W + s.x, y * g.W + s.x);
+    }
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        unsigned m = __ballot_sync(0xffffffffu, f[r]);
+        int y = s.y0 + r;
+        if (f[r]) rank[s.base + (long long)y * g.W + s.x] =
+            cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] + __popc(m & ((1u << s.lane) - 1)) + 1;
+    }
 }
 
-// in-place exclusive scan of blk[n, 0..bpt) per tile; counts[n] = total (defined in ccl.cu)
-int rank_scan(tiseg_ctx* c, int N, int bpt, int* blk, int* counts);
+// in-place exclusive raster-order scan of cnt[n, 0..H, 0..SEG) per tile; counts[n] = total (defined in ccl.cu)
+int rank_scan(tiseg_ctx* c, const Geom& g, int* cnt, int* counts);
 
 template <class Sel>
 int rank_generic(tiseg_ctx* c, const Geom& g, Sel sel, int* rank, int* counts) {
-    int* blk = ws<int>(c, (size_t)g.N * g.bpt);
-    if (!blk) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH(c, k_rank_count<Sel>, warp_grid(g), TISEG_THREADS, 0, g, sel, blk);
-    TISEG_TRY(rank_scan(c, g.N, g.bpt, blk, counts));
-    TISEG_LAUNCH(c, k_rank_place<Sel>, warp_grid(g), TISEG_THREADS, 0, g, sel, blk, rank);
+    int* cnt = ws<int>(c, (size_t)g.N * g.H * g.SEG);
+    if (!cnt) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_rank_count<Sel>, strip_grid(g), TISEG_THREADS, 0, g, sel, cnt);
+    TISEG_TRY(rank_scan(c, g, cnt, counts));
+    TISEG_LAUNCH(c, k_rank_place<Sel>, strip_grid(g), TISEG_THREADS, 0, g, sel, cnt, rank);
     return TISEG_OK;
 }
 #endif

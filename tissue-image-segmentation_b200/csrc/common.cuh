@@ -99,6 +99,10 @@ inline Geom make_geom(int N, int H, int W) {
 }
 inline dim3 warp_grid(const Geom& g) { return dim3((unsigned)g.bpt, (unsigned)g.N, 1); }
 inline unsigned flat_grid(long long n, int per_block = TISEG_THREADS) { return (unsigned)((n + per_block - 1) / per_block); }
+inline unsigned flat4_grid(long long n) { return (unsigned)((n + 4 * TISEG_THREADS - 1) / (4 * TISEG_THREADS)); }
+inline bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr, const void* e = nullptr) {
+    return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d) | ((uintptr_t)e)) & 15) == 0;
+}
 inline int check_geom(int N, int H, int W) {
     if (N <= 0 || H <= 0 || W <= 0 || N > 65535 || (long long)H * W >= (1ll << 30)) {
         set_error("bad tile geometry (need 1 <= N <= 65535, H*W < 2^30)");
@@ -128,6 +132,86 @@ __device__ __forceinline__ bool warp_pixel(const Geom& g, Pix& p) {
     p.idx = p.y * g.W + p.x;
     return true;
 }
+
+// ---- strip iteration: one warp = STRIP_R consecutive rows of one 32-column segment -----------------------
+// Loads of the STRIP_R rows are issued before any of them is consumed (independent requests in flight), and
+// 3x3 stencils reuse the rows they share.  Consecutive warps take consecutive segments of the same row chunk.
+#define STRIP_R 4
+struct Strip {
+    int n, x, y0, seg, lane;   // tile, column of this lane, first row, segment index
+    bool okx;                  // x < W
+    long long base;            // n * P
+};
+inline dim3 strip_grid(const Geom& g) {
+    long long warps = (long long)g.SEG * ((g.H + STRIP_R - 1) / STRIP_R);
+    return dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)g.N, 1);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ bool warp_strip(const Geom& g, Strip& s) {
+    int w = blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    s.lane = threadIdx.x & 31;
+    int chunks = (g.H + STRIP_R - 1) / STRIP_R;
+    if (w >= g.SEG * chunks) return false;
+    int ch = w / g.SEG;
+    s.seg = w - ch * g.SEG;
+    s.y0 = ch * STRIP_R;
+    s.n = blockIdx.y;
+    s.x = s.seg * 32 + s.lane;
+    s.okx = s.x < g.W;
+    s.base = (long long)s.n * g.P;
+    return true;
+}
+// centre / left / right columns of rows y0-1 .. y0+STRIP_R for a 3x3 stencil; out-of-image taps read `oob`
+template <class T>
+__device__ __forceinline__ void strip_load3(const Geom& g, const Strip& s, const T* __restrict__ tile, T oob,
+                                            T (&c)[STRIP_R + 2], T (&l)[STRIP_R + 2], T (&r)[STRIP_R + 2]) {
+#pragma unroll
+    for (int j = 0; j < STRIP_R + 2; ++j) {
+        int y = s.y0 - 1 + j;
+        bool oky = y >= 0 && y < g.H;
+        c[j] = (oky && s.okx) ? tile[y * g.W + s.x] : oob;
+        T el = oob, er = oob;
+        if (s.lane == 0 && oky && s.x > 0 && s.x - 1 < g.W) el = tile[y * g.W + s.x - 1];
+        if (s.lane == 31 && oky && s.x + 1 < g.W) er = tile[y * g.W + s.x + 1];
+        l[j] = el; r[j] = er;
+    }
+#pragma unroll
+    for (int j = 0; j < STRIP_R + 2; ++j) {
+        T a = __shfl_up_sync(0xffffffffu, c[j], 1), b = __shfl_down_sync(0xffffffffu, c[j], 1);
+        if (s.lane != 0) l[j] = a;
+        if (s.lane != 31) r[j] = b;
+    }
+}
+#endif
+
+// ---- flat elementwise iteration: one thread = 4 consecutive elements (128-bit fp32/int32, 32-bit uint8) ----
+// `vec` (uniform) says every pointer of the launch is 16-byte aligned; otherwise, and on the ragged tail, the
+// accessors fall back to scalar loads.  Four elements per thread keeps 16 B per request in flight, which is what
+// a pure streaming pass needs to approach HBM bandwidth (one 4-byte load per thread cannot cover the latency).
+template <class T> struct Pack4 { T v[4]; };
+template <> struct __align__(16) Pack4<float> { float v[4]; };
+template <> struct __align__(16) Pack4<int> { int v[4]; };
+template <> struct __align__(4) Pack4<uint8_t> { uint8_t v[4]; };
+
+template <class T>
+__device__ __forceinline__ Pack4<T> ld4(const T* __restrict__ p, long long i, long long total, bool vec) {
+    Pack4<T> r;
+    if (vec && i + 3 < total) r = *reinterpret_cast<const Pack4<T>*>(p + i);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.v[k] = i + k < total ? p[i + k] : T(0);
+    }
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st4(T* __restrict__ p, long long i, long long total, bool vec, const Pack4<T>& r) {
+    if (vec && i + 3 < total) *reinterpret_cast<Pack4<T>*>(p + i) = r;
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i + k < total) p[i + k] = r.v[k];
+    }
+}
+__device__ __forceinline__ long long flat4_index() { return ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; }
 
 // Given the ballot of "this lane continues the run of the lane to its left" (bit 0 of the segment may be
 // set when the run continues from the previous segment), the lane at which my run starts inside the segment.

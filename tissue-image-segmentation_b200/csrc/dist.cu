@@ -15,36 +15,41 @@
 
 namespace tiseg {
 
-__global__ void k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    float d = dist[px.base + px.idx];
-    if (d > 255.f) d = 255.f;          // dist.py:277-278 (comparisons are false for NaN, like numpy)
-    if (d < 0.f) d = 0.f;
-    int t = (int)d;                    // astype('int32'): truncation
-    I[px.base + px.idx] = (uint8_t)(255 - (t & 255));
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_dist_prep(long long total, const float* __restrict__ dist, uint8_t* __restrict__ I, bool vec) {
+    const long long i = flat4_index();
+    if (i >= total) return;
+    Pack4<float> d = ld4(dist, i, total, vec);
+    Pack4<uint8_t> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v = d.v[k];
+        if (v > 255.f) v = 255.f;      // dist.py:277-278 (comparisons are false for NaN, like numpy)
+        if (v < 0.f) v = 0.f;
+        int t = (int)v;                // astype('int32'): truncation
+        o.v[k] = (uint8_t)(255 - (t & 255));
+    }
+    st4(I, i, total, vec, o);
 }
 
 // low[root] = 1 if any pixel of the plateau has a strictly lower 8-neighbour
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_plateau_lower(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ par, uint8_t* low) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    const uint8_t* t = I + px.base;
-    int v = t[px.idx];
-    bool lower = false;
-    for (int dy = -1; dy <= 1; ++dy) {
-        int yy = px.y + dy;
-        if (yy < 0 || yy >= g.H) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-            int xx = px.x + dx;
-            if (xx < 0 || xx >= g.W) continue;
-            lower |= t[yy * g.W + xx] < v;
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    uint8_t c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
+    strip_load3<uint8_t>(g, s, I + s.base, (uint8_t)255, c, l, r);      // out-of-image taps can never be lower
+#pragma unroll
+    for (int j = 1; j <= STRIP_R; ++j) {
+        int y = s.y0 + j - 1;
+        if (!s.okx || y >= g.H) continue;
+        int v = c[j];
+        int mn = min(min(min((int)l[j - 1], (int)c[j - 1]), min((int)r[j - 1], (int)l[j])),
+                     min(min((int)r[j], (int)l[j + 1]), min((int)c[j + 1], (int)r[j + 1])));
+        if (mn < v) {
+            int root = par[s.base + (long long)y * g.W + s.x];
+            if (!low[s.base + root]) low[s.base + root] = 1;
         }
-    }
-    if (lower) {
-        int r = par[px.base + px.idx];
-        if (!low[px.base + r]) low[px.base + r] = 1;
     }
 }
 
@@ -55,26 +60,40 @@ struct SelMinimumRoot {         // roots of regional-minimum plateaus with value
     }
 };
 
-__global__ void k_markers_from_plateaus(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ par,
-                                        const uint8_t* __restrict__ low, const int* __restrict__ rank,
-                                        int32_t* __restrict__ markers) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    long long i = px.base + px.idx;
-    long long r = px.base + par[i];
-    markers[i] = (I[i] < 255 && !low[r]) ? rank[r] : 0;
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_markers_from_plateaus(long long P, const uint8_t* __restrict__ I, const int* __restrict__ par,
+                        const uint8_t* __restrict__ low, const int* __restrict__ rank, int32_t* __restrict__ markers,
+                        bool vec) {
+    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+    if (i >= P) return;
+    Pack4<uint8_t> v = ld4(I + base, i, P, vec);
+    Pack4<int> p = ld4(par + base, i, P, vec), o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o.v[k] = 0;
+        if (i + k < P && v.v[k] < 255) { long long r = base + p.v[k]; if (!low[r]) o.v[k] = rank[r]; }
+    }
+    st4(markers + base, i, P, vec, o);
 }
 
 // histogram of the flood labels (values 0..K), one atomic per in-segment run
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int KS) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int v = px.ok ? ws[px.base + px.idx] : -1;
-    int vl = __shfl_up_sync(0xffffffffu, v, 1);
-    bool cont = px.lane > 0 && v == vl;
-    unsigned m = __ballot_sync(0xffffffffu, cont);
-    if (v >= 0 && !cont) atomicAdd(&hist[(long long)px.n * KS + v], run_end_lane(m, px.lane) - px.lane + 1);
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    int v[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        v[r] = (s.okx && y < g.H) ? ws[s.base + (long long)y * g.W + s.x] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
+        bool cont = s.lane > 0 && v[r] == vl;
+        unsigned m = __ballot_sync(0xffffffffu, cont);
+        if (v[r] >= 0 && !cont) atomicAdd(&hist[(long long)s.n * KS + v[r]], run_end_lane(m, s.lane) - s.lane + 1);
+    }
 }
 
 __global__ void k_zero_prefix_i32(int* a, int KS, const int* __restrict__ counts) {
@@ -106,24 +125,23 @@ __global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __res
 // generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_wsl_remove(Geom g, const int32_t* __restrict__ lab, int32_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    const int32_t* t = lab + px.base;
-    int v = t[px.idx];
-    bool line = false;
-    if (v != 0) {
-        for (int dy = -1; dy <= 1; ++dy) {
-            int yy = px.y + dy;
-            if (yy < 0 || yy >= g.H) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
-                int xx = px.x + dx;
-                if (xx < 0 || xx >= g.W) continue;
-                int u = t[yy * g.W + xx];
-                line |= (u != 0 && u != v);
-            }
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    int c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
+    strip_load3<int>(g, s, lab + s.base, 0, c, l, r);
+#pragma unroll
+    for (int j = 1; j <= STRIP_R; ++j) {
+        int y = s.y0 + j - 1;
+        if (!s.okx || y >= g.H) continue;
+        int v = c[j];
+        bool line = false;
+        if (v != 0) {
+            const int nb[8] = {l[j - 1], c[j - 1], r[j - 1], l[j], r[j], l[j + 1], c[j + 1], r[j + 1]};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) line |= (nb[k] != 0 && nb[k] != v);
         }
+        out[s.base + (long long)y * g.W + s.x] = line ? 0 : v;
     }
-    out[px.base + px.idx] = line ? 0 : v;
 }
 
 int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* inst, int32_t* markers_out,
@@ -144,13 +162,14 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     int* hist = ws<int>(c, (size_t)N * KS);
     if (!I || !low || !par || !rank || !bpar || !brank || !markers || !wsl || !arranged || !nmark || !bg || !hist) return TISEG_ERR_CUDA;
 
-    TISEG_LAUNCH(c, k_dist_prep, warp_grid(g), TISEG_THREADS, 0, g, dist, I);
+    TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I, aligned16(dist) && (((uintptr_t)I) & 3) == 0);
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255
     TISEG_TRY(ccl_build(c, g, ImgEqU8{I, -1}, 2, par));
     TISEG_TRY(zero(c, low, total));
-    TISEG_LAUNCH(c, k_plateau_lower, warp_grid(g), TISEG_THREADS, 0, g, I, par, low);
+    TISEG_LAUNCH(c, k_plateau_lower, strip_grid(g), TISEG_THREADS, 0, g, I, par, low);
     TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, I, low}, rank, nmark));
-    TISEG_LAUNCH(c, k_markers_from_plateaus, warp_grid(g), TISEG_THREADS, 0, g, I, par, low, rank, markers);
+    TISEG_LAUNCH(c, k_markers_from_plateaus, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, I, par, low, rank, markers,
+                 (g.P % 4 == 0) && aligned16(par, markers) && (((uintptr_t)I) & 3) == 0);
     // flood inside b = (I < 255), blob by blob
     BlobInfo b;
     TISEG_TRY(blobs_build(c, g, ImgBelowU8{I, 255}, bpar, brank, b, false));
@@ -158,13 +177,13 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
     // arrange_label
     TISEG_LAUNCH(c, k_zero_prefix_i32, dim3(8, N), 256, 0, hist, KS, nmark);
-    TISEG_LAUNCH(c, k_ws_hist, warp_grid(g), TISEG_THREADS, 0, g, wsl, hist, KS);
+    TISEG_LAUNCH(c, k_ws_hist, strip_grid(g), TISEG_THREADS, 0, g, wsl, hist, KS);
     TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, bg);
     TISEG_TRY(ccl_build(c, g, ImgEqI32TileBg{wsl, bg}, 2, par));
     TISEG_TRY(rank_roots(c, g, par, rank, nullptr));
     TISEG_TRY(apply_rank(c, g, par, rank, arranged));
     // watershed lines
-    TISEG_LAUNCH(c, k_wsl_remove, warp_grid(g), TISEG_THREADS, 0, g, arranged, inst);
+    TISEG_LAUNCH(c, k_wsl_remove, strip_grid(g), TISEG_THREADS, 0, g, arranged, inst);
     return TISEG_OK;
 }
 

@@ -88,24 +88,36 @@ __global__ void k_inst_init(InstState s, int areas) {
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_pair_accumulate(Geom g, const int* __restrict__ par_g, const int* __restrict__ rank_g,
                   const int* __restrict__ par_p, const int* __restrict__ rank_p, InstState s, PairTab t, int* overflow) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int gid = 0, pid = 0;
-    if (px.ok) {
-        int a = par_g[px.base + px.idx], b = par_p[px.base + px.idx];
-        if (a >= 0) gid = rank_g[px.base + a];
-        if (b >= 0) pid = rank_p[px.base + b];
+    Strip st;
+    if (!warp_strip(g, st)) return;
+    int a[STRIP_R], b[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = st.y0 + r;
+        bool ok = st.okx && y < g.H;
+        a[r] = ok ? par_g[st.base + (long long)y * g.W + st.x] : -1;
+        b[r] = ok ? par_p[st.base + (long long)y * g.W + st.x] : -1;
     }
-    int gl = __shfl_up_sync(0xffffffffu, gid, 1), pl = __shfl_up_sync(0xffffffffu, pid, 1);
-    bool first = px.lane == 0;
-    bool cg = !first && gid == gl, cp = !first && pid == pl;
-    unsigned mg = __ballot_sync(0xffffffffu, cg);
-    unsigned mp = __ballot_sync(0xffffffffu, cp);
-    unsigned mb = mg & mp;                                  // both continue => the pair continues
-    long long o = (long long)px.n * s.KS;
-    if (gid && !cg) atomicAdd(&s.area_g[o + gid], run_end_lane(mg, px.lane) - px.lane + 1);
-    if (pid && !cp) atomicAdd(&s.area_p[o + pid], run_end_lane(mp, px.lane) - px.lane + 1);
-    if (gid && pid && !(cg && cp)) pair_add(t, px.n, gid, pid, run_end_lane(mb, px.lane) - px.lane + 1, overflow);
+    int gid[STRIP_R], pid[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        gid[r] = a[r] >= 0 ? rank_g[st.base + a[r]] : 0;
+        pid[r] = b[r] >= 0 ? rank_p[st.base + b[r]] : 0;
+    }
+    const long long o = (long long)st.n * s.KS;
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int gl = __shfl_up_sync(0xffffffffu, gid[r], 1), pl = __shfl_up_sync(0xffffffffu, pid[r], 1);
+        bool first = st.lane == 0;
+        bool cg = !first && gid[r] == gl, cp = !first && pid[r] == pl;
+        unsigned mg = __ballot_sync(0xffffffffu, cg);
+        unsigned mp = __ballot_sync(0xffffffffu, cp);
+        unsigned mb = mg & mp;                              // both continue => the pair continues
+        if (gid[r] && !cg) atomicAdd(&s.area_g[o + gid[r]], run_end_lane(mg, st.lane) - st.lane + 1);
+        if (pid[r] && !cp) atomicAdd(&s.area_p[o + pid[r]], run_end_lane(mp, st.lane) - st.lane + 1);
+        if (gid[r] && pid[r] && !(cg && cp))
+            pair_add(t, st.n, gid[r], pid[r], run_end_lane(mb, st.lane) - st.lane + 1, overflow);
+    }
 }
 
 // pass A over the table: best AJI IoU per gt (atomicMax on fp64 bits: positive doubles order like integers),
@@ -311,20 +323,24 @@ __global__ void k_metrics_final(InstState s, ClassInfo ci, const unsigned long l
 // non-zero bin per block.  Classes outside [0, C) are not counted (torch.histc range semantics).
 #define SEM_MAXC 64
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_sem_counts(Geom g, const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, int C, int ignore,
-             unsigned long long* counts, unsigned long long* valid) {
+k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, int C, int ignore,
+             unsigned long long* counts, unsigned long long* valid, bool vec) {
     __shared__ unsigned h[5 * SEM_MAXC];
     __shared__ unsigned nvalid;
     for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) h[i] = 0;
     if (threadIdx.x == 0) nvalid = 0;
     __syncthreads();
-    Pix px;
-    bool act = warp_pixel(g, px) && px.ok;
-    bool v = false;
-    if (act) {
-        int p = pred[px.base + px.idx], t = gt[px.base + px.idx];
-        if (t != ignore) {
-            v = true;
+    const long long base = (long long)blockIdx.y * P;
+    int nv = 0;
+    // each thread walks several 4-pixel groups so that one block amortises its histogram flush
+    for (long long i = flat4_index(); i < P; i += (long long)gridDim.x * blockDim.x * 4) {
+        Pack4<uint8_t> pp = ld4(pred + base, i, P, vec), tt = ld4(gt + base, i, P, vec);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k >= P) continue;
+            int p = pp.v[k], t = tt.v[k];
+            if (t == ignore) continue;
+            ++nv;
             bool pin = p < C, tin = t < C;
             if (p == t) { if (tin) atomicAdd(&h[0 * C + t], 1u); }
             else { if (pin) atomicAdd(&h[1 * C + p], 1u); if (tin) atomicAdd(&h[2 * C + t], 1u); }
@@ -332,8 +348,8 @@ k_sem_counts(Geom g, const uint8_t* __restrict__ pred, const uint8_t* __restrict
             if (tin) atomicAdd(&h[4 * C + t], 1u);
         }
     }
-    unsigned b = __ballot_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&nvalid, __popc(b));
+    for (int d = 16; d; d >>= 1) nv += __shfl_down_sync(0xffffffffu, nv, d);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&nvalid, (unsigned)nv);
     __syncthreads();
     for (int i = threadIdx.x; i < 5 * C; i += blockDim.x)
         if (h[i]) atomicAdd(&counts[(long long)blockIdx.y * 5 * C + i], (unsigned long long)h[i]);
@@ -435,7 +451,7 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
         TISEG_TRY(zero(c, t.cnt, (size_t)N * cap * sizeof(int)));
         TISEG_TRY(zero(c, overflow, sizeof(int)));
         TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 1);
-        TISEG_LAUNCH(c, k_pair_accumulate, warp_grid(g), TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t, overflow);
+        TISEG_LAUNCH(c, k_pair_accumulate, strip_grid(g), TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t, overflow);
         int hov = 0;
         TISEG_CHECK(cudaMemcpyAsync(&hov, overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TISEG_CHECK(cudaStreamSynchronize(c->stream));
@@ -577,8 +593,11 @@ int tiseg_sem_counts(tiseg_ctx* c, const uint8_t* pred, const uint8_t* gt, int N
     if (!d_pred || !d_gt || !d_counts || !d_valid) return TISEG_ERR_CUDA;
     TISEG_TRY(zero(c, d_counts, (size_t)N * 5 * C * sizeof(int64_t)));
     TISEG_TRY(zero(c, d_valid, (size_t)N * sizeof(int64_t)));
-    TISEG_LAUNCH(c, k_sem_counts, warp_grid(g), TISEG_THREADS, 0, g, d_pred, d_gt, C, ignore_index,
-                 (unsigned long long*)d_counts, (unsigned long long*)d_valid);
+    unsigned gx = flat4_grid(g.P);
+    gx = gx > 64 ? (gx + 7) / 8 : gx;                         // ~8 groups per thread
+    bool vec = (g.P % 4 == 0) && ((((uintptr_t)d_pred) | ((uintptr_t)d_gt)) & 3) == 0;
+    TISEG_LAUNCH(c, k_sem_counts, dim3(gx, N), TISEG_THREADS, 0, (long long)g.P, d_pred, d_gt, C, ignore_index,
+                 (unsigned long long*)d_counts, (unsigned long long*)d_valid, vec);
     return end_call(c);
 }
 

@@ -10,46 +10,64 @@ namespace tiseg {
 
 template <int CMAX>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_softmax_argmax(Geom g, const float* __restrict__ logits, int T, int C, float* __restrict__ prob,
-                 uint8_t* __restrict__ cls) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    float acc[CMAX];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-    const long long P = g.P;
+k_softmax_argmax(long long P, const float* __restrict__ logits, int T, int C, float* __restrict__ prob,
+                 uint8_t* __restrict__ cls, bool vec) {
+    // one thread = 4 consecutive pixels of one tile (blockIdx.y): float4 per channel plane, uchar4 out
+    const int n = blockIdx.y;
+    const long long i = flat4_index();
+    if (i >= P) return;
+    float acc[CMAX][4];
     for (int t = 0; t < T; ++t) {
-        const float* src = logits + ((long long)px.n * T + t) * C * P + px.idx;
-        float x[CMAX];
-        float m = -INFINITY;
+        const float* src = logits + ((long long)n * T + t) * C * P;
+        Pack4<float> x[CMAX];
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-            if (c < C) { x[c] = src[c * P]; m = fmaxf(m, x[c]); }
-        float s = 0.f;
+            if (c < C) {
+                x[c] = ld4(src + c * P, i, P, vec);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], x[c].v[k]);
+            }
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-            if (c < C) { x[c] = expf(x[c] - m); s = s + x[c]; }
+            if (c < C) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { x[c].v[k] = expf(x[c].v[k] - m[k]); s[k] = s[k] + x[c].v[k]; }
+            }
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-            if (c < C) acc[c] = (t == 0) ? x[c] / s : acc[c] + x[c] / s;
+            if (c < C) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[c][k] = (t == 0) ? x[c].v[k] / s[k] : acc[c][k] + x[c].v[k] / s[k];
+            }
     }
-    float tf = (float)T;
-    int best = 0;
-    float bv = -INFINITY;
+    const float tf = (float)T;
+    Pack4<uint8_t> best;
+    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) best.v[k] = 0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
         if (c < C) {
-            float p = acc[c] / tf;
-            if (prob) prob[((long long)px.n * C + c) * P + px.idx] = p;
-            if (p > bv) { bv = p; best = c; }
+            Pack4<float> p;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                p.v[k] = acc[c][k] / tf;
+                if (p.v[k] > bv[k]) { bv[k] = p.v[k]; best.v[k] = (uint8_t)c; }
+            }
+            if (prob) st4(prob + ((long long)n * C + c) * P, i, P, vec, p);
         }
-    if (cls) cls[px.base + px.idx] = (uint8_t)best;
+    if (cls) st4(cls + (long long)n * P, i, P, vec, best);
 }
 
 int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, int C, float* d_prob, uint8_t* d_cls) {
-    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax<4>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
-    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax<8>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
-    else TISEG_LAUNCH(c, k_softmax_argmax<16>, warp_grid(g), TISEG_THREADS, 0, g, d_in, T, C, d_prob, d_cls);
+    const long long P = g.P;
+    const bool vec = (P % 4 == 0) && aligned16(d_in, d_prob) && (((uintptr_t)d_cls) & 3) == 0;
+    dim3 grid(flat4_grid(P), (unsigned)g.N);
+    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax<4>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);
+    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax<8>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);
+    else TISEG_LAUNCH(c, k_softmax_argmax<16>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);
     return TISEG_OK;
 }
 

@@ -15,27 +15,40 @@ __global__ void k_blob_init(BlobInfo b, int W) {
     }
 }
 
-__global__ void k_blob_roots(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    if (par[px.base + px.idx] == px.idx) b.root[(long long)px.n * b.KS + rank[px.base + px.idx]] = px.idx;
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_blob_roots(long long P, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b, bool vec) {
+    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+    if (i >= P) return;
+    Pack4<int> p = ld4(par + base, i, P, vec);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i + k < P && p.v[k] == (int)(i + k)) b.root[(long long)blockIdx.y * b.KS + rank[base + i + k]] = (int)(i + k);
 }
 
 // bounding box + area per blob, one set of atomics per in-segment run
-__global__ void k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int p = px.ok ? par[px.base + px.idx] : -1;
-    int pl = __shfl_up_sync(FULL, p, 1);
-    bool cont = px.lane > 0 && p >= 0 && pl == p;
-    unsigned m = __ballot_sync(FULL, cont);
-    if (p >= 0 && !cont) {
-        int end = run_end_lane(m, px.lane);
-        long long o = (long long)px.n * b.KS + rank[px.base + p];
-        atomicMax(&b.ymax[o], px.y);
-        atomicMin(&b.xmin[o], px.x);
-        atomicMax(&b.xmax[o], px.x + (end - px.lane));
-        atomicAdd(&b.area[o], end - px.lane + 1);
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    int p[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        p[r] = (s.okx && y < g.H) ? par[s.base + (long long)y * g.W + s.x] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int pl = __shfl_up_sync(FULL, p[r], 1);
+        bool cont = s.lane > 0 && p[r] >= 0 && pl == p[r];
+        unsigned m = __ballot_sync(FULL, cont);
+        if (p[r] >= 0 && !cont) {
+            int end = run_end_lane(m, s.lane);
+            long long o = (long long)s.n * b.KS + rank[s.base + p[r]];
+            atomicMax(&b.ymax[o], s.y0 + r);
+            atomicMin(&b.xmin[o], s.x);
+            atomicMax(&b.xmax[o], s.x + (end - s.lane));
+            atomicAdd(&b.area[o], end - s.lane + 1);
+        }
     }
 }
 
@@ -69,11 +82,14 @@ __global__ void k_blob_offsets(BlobInfo b) {
 }
 
 // out = markers * mask (skimage: markers outside the mask are dropped)
-__global__ void k_ws_seed(Geom g, const int32_t* __restrict__ markers, const int* __restrict__ par, int32_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    long long i = px.base + px.idx;
-    out[i] = par[i] >= 0 ? markers[i] : 0;
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __restrict__ par, int32_t* __restrict__ out, bool vec) {
+    const long long i = flat4_index();
+    if (i >= total) return;
+    Pack4<int> m = ld4(markers, i, total, vec), p = ld4(par, i, total, vec), o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = p.v[k] >= 0 ? m.v[k] : 0;
+    st4(out, i, total, vec, o);
 }
 
 // ---- uint8 levels: 256 FIFO buckets --------------------------------------------------------------------
@@ -272,14 +288,15 @@ k_ws_flood_f64(Geom g, const double* __restrict__ image, const int* __restrict__
 }
 
 int ws_seed(tiseg_ctx* c, const Geom& g, const int32_t* markers, const int* par, int32_t* out) {
-    TISEG_LAUNCH(c, k_ws_seed, warp_grid(g), TISEG_THREADS, 0, g, markers, par, out);
+    long long total = (long long)g.N * g.P;
+    TISEG_LAUNCH(c, k_ws_seed, flat4_grid(total), TISEG_THREADS, 0, total, markers, par, out, aligned16(markers, par, out));
     return TISEG_OK;
 }
 
 int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, BlobInfo& b, bool want_offsets) {
     TISEG_LAUNCH(c, k_blob_init, dim3(8, g.N), 256, 0, b, g.W);
-    TISEG_LAUNCH(c, k_blob_roots, warp_grid(g), TISEG_THREADS, 0, g, par, rank, b);
-    TISEG_LAUNCH(c, k_blob_bbox, warp_grid(g), TISEG_THREADS, 0, g, par, rank, b);
+    TISEG_LAUNCH(c, k_blob_roots, dim3(flat4_grid(g.P), g.N), TISEG_THREADS, 0, (long long)g.P, par, rank, b, (g.P % 4 == 0) && aligned16(par));
+    TISEG_LAUNCH(c, k_blob_bbox, strip_grid(g), TISEG_THREADS, 0, g, par, rank, b);
     if (want_offsets) TISEG_LAUNCH(c, k_blob_offsets, g.N, 256, 0, b);
     return TISEG_OK;
 }
