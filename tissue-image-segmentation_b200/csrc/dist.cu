@@ -92,7 +92,8 @@ k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int KS) {
         int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
         bool cont = s.lane > 0 && v[r] == vl;
         unsigned m = __ballot_sync(0xffffffffu, cont);
-        if (v[r] >= 0 && !cont) atomicAdd(&hist[(long long)s.n * KS + v[r]], run_end_lane(m, s.lane) - s.lane + 1);
+        // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
+        if (v[r] > 0 && !cont) atomicAdd(&hist[(long long)s.n * KS + v[r]], run_end_lane(m, s.lane) - s.lane + 1);
     }
 }
 
@@ -103,23 +104,35 @@ __global__ void k_zero_prefix_i32(int* a, int KS, const int* __restrict__ counts
 }
 
 // arrange_label's background: np.unique(return_counts) + argmax => the most frequent value, smallest value on ties
-__global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int* bg) {
+__global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int P, int* bg) {
     __shared__ unsigned long long s[256];
+    __shared__ long long tot[256];
     int n = blockIdx.x;
     int k = counts[n];
     // key = (count << 32) | (0xffffffff - value): max key = largest count, then smallest value
     unsigned long long best = 0;
-    for (int v = threadIdx.x; v <= k; v += blockDim.x) {
-        unsigned long long key = ((unsigned long long)(unsigned)hist[(long long)n * KS + v] << 32) | (0xffffffffu - (unsigned)v);
+    long long sum = 0;
+    for (int v = 1 + threadIdx.x; v <= k; v += blockDim.x) {
+        unsigned cnt = (unsigned)hist[(long long)n * KS + v];
+        sum += cnt;
+        unsigned long long key = ((unsigned long long)cnt << 32) | (0xffffffffu - (unsigned)v);
         if (key > best) best = key;
     }
     s[threadIdx.x] = best;
+    tot[threadIdx.x] = sum;
     __syncthreads();
     for (int d = 128; d; d >>= 1) {
-        if (threadIdx.x < d && s[threadIdx.x + d] > s[threadIdx.x]) s[threadIdx.x] = s[threadIdx.x + d];
+        if (threadIdx.x < d) {
+            if (s[threadIdx.x + d] > s[threadIdx.x]) s[threadIdx.x] = s[threadIdx.x + d];
+            tot[threadIdx.x] += tot[threadIdx.x + d];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) bg[n] = (int)(0xffffffffu - (unsigned)(s[0] & 0xffffffffu));
+    if (threadIdx.x == 0) {
+        unsigned long long zero_key = ((unsigned long long)(unsigned)(P - tot[0]) << 32) | 0xffffffffu;   // value 0
+        unsigned long long w = zero_key > s[0] ? zero_key : s[0];
+        bg[n] = (int)(0xffffffffu - (unsigned)(w & 0xffffffffu));
+    }
 }
 
 // generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
@@ -178,7 +191,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     // arrange_label
     TISEG_LAUNCH(c, k_zero_prefix_i32, dim3(8, N), 256, 0, hist, KS, nmark);
     TISEG_LAUNCH(c, k_ws_hist, strip_grid(g), TISEG_THREADS, 0, g, wsl, hist, KS);
-    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, bg);
+    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg);
     TISEG_TRY(ccl_build(c, g, ImgEqI32TileBg{wsl, bg}, 2, par));
     TISEG_TRY(rank_roots(c, g, par, rank, nullptr));
     TISEG_TRY(apply_rank(c, g, par, rank, arranged));

@@ -92,91 +92,187 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
     st4(out, i, total, vec, o);
 }
 
-// ---- uint8 levels: 256 FIFO buckets --------------------------------------------------------------------
-__global__ void __launch_bounds__(TISEG_THREADS)
+// ---- uint8 levels: 256 FIFO buckets -----------------------------------------------------------------------
+// A blob's flood is a chain of dependent accesses (pop -> look at 4 neighbours -> push), so its speed is the
+// latency of the memory it runs in.  Each warp therefore STAGES its blob into shared memory first: the bounding box
+// plus a one-pixel frame (so the flood needs no bounds checks), 5 bytes per cell — level (u8), FIFO link (u16) and
+// the local index of the seed pixel whose label the cell inherits (u16).  The flood then runs entirely in shared
+// memory (~30-cycle accesses instead of ~600), and the labels are written back with coalesced stores.  Blobs whose
+// framed bounding box exceeds WS_CAP cells take the same algorithm in global memory.
+// Persistent grid: one CTA per SM; every CTA walks all tiles (starting at a different one) and drains each
+// tile's blob queue with an atomic counter, so the load balances across tiles and blob sizes.
+#define WS_CAP 4096
+#define WS_NOTIN 0xFFFFu
+#define WS_UNLAB 0xFFFEu
+#define WS_END 0xFFFFu
+extern __shared__ __align__(16) unsigned char ws_smem[];
+
+__global__ void __launch_bounds__(TISEG_THREADS, 1)
 k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, int* queue,
               int* next, int32_t* out) {
     __shared__ int s_head[TISEG_WARPS_PER_BLOCK][256];
     __shared__ int s_tail[TISEG_WARPS_PER_BLOCK][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
-    const int B = b.count[n];
-    const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
-    const uint8_t* I = image + base;
-    const int* tp = par + base;
-    int32_t* o = out + base;
-    int* nx = next + base;
+    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem + (size_t)warp * WS_CAP * 5);
+    unsigned short* nxs = lab + WS_CAP;
+    unsigned char* lvl = reinterpret_cast<unsigned char*>(nxs + WS_CAP);
     int* head = s_head[warp];
     int* tail = s_tail[warp];
     const int W = g.W, H = g.H;
-    for (;;) {
-        int bid = 0;
-        if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
-        bid = __shfl_sync(FULL, bid, 0);
-        if (bid > B) break;
-        for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
-        __syncwarp();
-        const int root = b.root[ko + bid];
-        const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
-        int cur = 256;
-        // seeds in raster order: all have age 0, ties inside a level resolved by flat index
-        for (int y = y0; y <= y1; ++y) {
-            for (int xb = x0; xb <= x1; xb += 32) {
-                int x = xb + lane;
-                bool seed = false;
-                int lv = 0;
-                if (x <= x1) {
-                    int idx = y * W + x;
-                    if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
+    for (int tn = 0; tn < g.N; ++tn) {
+        const int n = (blockIdx.x + tn) % g.N;
+        const int B = b.count[n];
+        const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+        const uint8_t* I = image + base;
+        const int* tp = par + base;
+        int32_t* o = out + base;
+        int* nx = next + base;
+        for (;;) {
+            int bid = 0;
+            if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
+            bid = __shfl_sync(FULL, bid, 0);
+            if (bid > B) break;
+            for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
+            const int root = b.root[ko + bid];
+            const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+            const int w = x1 - x0 + 1, h = y1 - y0 + 1, wp = w + 2;
+            int cur = 256;
+            __syncwarp();
+            if (wp * (h + 2) <= WS_CAP) {
+                // ---- stage the framed bounding box; seeds enter their buckets in raster order
+                for (int ly = 0; ly < h + 2; ++ly) {
+                    for (int lxb = 0; lxb < wp; lxb += 32) {
+                        const int lx = lxb + lane, j = ly * wp + lx;
+                        bool seed = false;
+                        unsigned v = 0;
+                        if (lx < wp) {
+                            unsigned L = WS_NOTIN;
+                            if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
+                                const int gi = (y0 + ly - 1) * W + x0 + lx - 1;
+                                if (tp[gi] == root) { v = I[gi]; seed = o[gi] != 0; L = seed ? (unsigned)j : WS_UNLAB; }
+                            }
+                            lab[j] = (unsigned short)L;
+                            lvl[j] = (unsigned char)v;
+                        }
+                        unsigned m = __ballot_sync(FULL, seed);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int slv = __shfl_sync(FULL, (int)v, src);
+                            if (lane == 0) {
+                                const int pix = ly * wp + lxb + src;
+                                nxs[pix] = WS_END;
+                                const int t = tail[slv];
+                                if (t < 0) head[slv] = pix; else nxs[t] = (unsigned short)pix;
+                                tail[slv] = pix;
+                                if (slv < cur) cur = slv;
+                            }
+                        }
+                    }
                 }
-                unsigned m = __ballot_sync(FULL, seed);
-                while (m) {
-                    int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    int slv = __shfl_sync(FULL, lv, src);
-                    if (lane == 0) {
-                        int pix = y * W + xb + src;
-                        nx[pix] = -1;
-                        int t = tail[slv];
-                        if (t < 0) head[slv] = pix; else nx[t] = pix;
-                        tail[slv] = pix;
-                        if (slv < cur) cur = slv;
+                __syncwarp();
+                // ---- the ordered flood, in shared memory
+                if (lane == 0) {
+                    for (;;) {
+                        while (cur < 256 && head[cur] < 0) ++cur;
+                        if (cur >= 256) break;
+                        const int pix = head[cur];
+                        const unsigned nxt = nxs[pix];
+                        head[cur] = nxt == WS_END ? -1 : (int)nxt;
+                        if (nxt == WS_END) tail[cur] = -1;
+                        const unsigned short L = lab[pix];
+                        const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
+                        unsigned short ln[4];
+                        unsigned char vn[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (ln[k] == WS_UNLAB) {
+                                lab[nb[k]] = L;                                       // labelled at push time
+                                nxs[nb[k]] = WS_END;
+                                const int t = tail[vn[k]];
+                                if (t < 0) head[vn[k]] = nb[k]; else nxs[t] = (unsigned short)nb[k];
+                                tail[vn[k]] = nb[k];
+                                if (vn[k] < cur) cur = vn[k];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- write back: every flooded cell takes the marker label of its seed pixel
+                for (int ly = 1; ly <= h; ++ly) {
+                    for (int lx = 1 + lane; lx <= w; lx += 32) {
+                        const int j = ly * wp + lx;
+                        const unsigned L = lab[j];
+                        if (L < WS_UNLAB && L != (unsigned)j) {
+                            const int sy = L / wp, sx = L - sy * wp;
+                            o[(y0 + ly - 1) * W + x0 + lx - 1] = o[(y0 + sy - 1) * W + x0 + sx - 1];
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            // ---- fallback: the same flood in global memory (framed bounding box does not fit)
+            for (int y = y0; y <= y1; ++y) {
+                for (int xb = x0; xb <= x1; xb += 32) {
+                    int x = xb + lane;
+                    bool seed = false;
+                    int lv = 0;
+                    if (x <= x1) {
+                        int idx = y * W + x;
+                        if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
+                    }
+                    unsigned m = __ballot_sync(FULL, seed);
+                    while (m) {
+                        int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        int slv = __shfl_sync(FULL, lv, src);
+                        if (lane == 0) {
+                            int pix = y * W + xb + src;
+                            nx[pix] = -1;
+                            int t = tail[slv];
+                            if (t < 0) head[slv] = pix; else nx[t] = pix;
+                            tail[slv] = pix;
+                            if (slv < cur) cur = slv;
+                        }
                     }
                 }
             }
-        }
-        if (lane == 0) {
-            for (;;) {
-                while (cur < 256 && head[cur] < 0) ++cur;
-                if (cur >= 256) break;
-                const int pix = head[cur];
-                const int nxt = nx[pix];
-                head[cur] = nxt;
-                if (nxt < 0) tail[cur] = -1;
-                const int lab = o[pix];
-                const int y = pix / W, x = pix - y * W;
-                const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};          // up, left, right, down
-                const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
-                int pv[4], ov[4], lv[4];
+            if (lane == 0) {
+                for (;;) {
+                    while (cur < 256 && head[cur] < 0) ++cur;
+                    if (cur >= 256) break;
+                    const int pix = head[cur];
+                    const int nxt = nx[pix];
+                    head[cur] = nxt;
+                    if (nxt < 0) tail[cur] = -1;
+                    const int lab_g = o[pix];
+                    const int y = pix / W, x = pix - y * W;
+                    const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};
+                    const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
+                    int pv[4], ov[4], lv[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pv[k] = -1; ov[k] = 1; lv[k] = 0;
-                    if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
-                }
+                    for (int k = 0; k < 4; ++k) {
+                        pv[k] = -1; ov[k] = 1; lv[k] = 0;
+                        if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
+                    }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (pv[k] >= 0 && ov[k] == 0) {
-                        o[nb[k]] = lab;                                           // labelled at push time
-                        nx[nb[k]] = -1;
-                        int t = tail[lv[k]];
-                        if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
-                        tail[lv[k]] = nb[k];
-                        if (lv[k] < cur) cur = lv[k];
+                    for (int k = 0; k < 4; ++k) {
+                        if (pv[k] >= 0 && ov[k] == 0) {
+                            o[nb[k]] = lab_g;
+                            nx[nb[k]] = -1;
+                            int t = tail[lv[k]];
+                            if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
+                            tail[lv[k]] = nb[k];
+                            if (lv[k] < cur) cur = lv[k];
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -316,7 +412,13 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
     int* next = ws<int>(c, (size_t)g.N * g.P);
     if (!queue || !next) return TISEG_ERR_CUDA;
     TISEG_TRY(zero(c, queue, (size_t)g.N * sizeof(int)));
-    TISEG_LAUNCH(c, k_ws_flood_u8, dim3(flood_blocks(c, g.N), g.N), TISEG_THREADS, 0, g, image, par, b, queue, next, out);
+    const size_t smem = (size_t)TISEG_WARPS_PER_BLOCK * WS_CAP * 5;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    TISEG_LAUNCH(c, k_ws_flood_u8, c->sm_count, TISEG_THREADS, smem, g, image, par, b, queue, next, out);
     return TISEG_OK;
 }
 
