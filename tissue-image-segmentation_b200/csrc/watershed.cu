@@ -93,185 +93,260 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
 }
 
 // ---- uint8 levels: 256 FIFO buckets -----------------------------------------------------------------------
-// A blob's flood is a chain of dependent accesses (pop -> look at 4 neighbours -> push), so its speed is the
-// latency of the memory it runs in.  Each warp therefore STAGES its blob into shared memory first: the bounding box
-// plus a one-pixel frame (so the flood needs no bounds checks), 5 bytes per cell — level (u8), FIFO link (u16) and
-// the local index of the seed pixel whose label the cell inherits (u16).  The flood then runs entirely in shared
-// memory (~30-cycle accesses instead of ~600), and the labels are written back with coalesced stores.  Blobs whose
-// framed bounding box exceeds WS_CAP cells take the same algorithm in global memory.
-// Persistent grid: one CTA per SM; every CTA walks all tiles (starting at a different one) and drains each
-// tile's blob queue with an atomic counter, so the load balances across tiles and blob sizes.
-#define WS_CAP 4096
+// A blob's flood is a chain of dependent steps (pop -> look at 4 neighbours -> push), so its speed is the latency
+// of the memory it runs in and the number of floods in flight.  Each warp STAGES its blob into shared memory: the
+// bounding box plus a one-pixel frame (no bounds checks in the flood), 5 bytes per cell — level (u8), FIFO link
+// (u16) and the local index of the seed pixel whose label the cell inherits (u16) — floods it there, and writes
+// the labels back with four loads in flight per lane.
+// One persistent CTA per SM holds 22 "small" warps (framed box <= 1024 cells: ~94 % of nuclei blobs) and 4 "large"
+// warps (<= 4096 cells); blobs are pre-sorted into a small and a large list per tile; every CTA walks all tiles
+// (starting at a different one) and drains the lists through atomic cursors, so work balances across tiles and
+// blob sizes.  Boxes beyond 4096 cells are flooded by a large warp directly in global memory.
+#define WS_SMALL_WARPS 22
+#define WS_LARGE_WARPS 4
+#define WS_WARPS (WS_SMALL_WARPS + WS_LARGE_WARPS)
+#define WS_CAP_S 1024
+#define WS_CAP_L 4096
 #define WS_NOTIN 0xFFFFu
 #define WS_UNLAB 0xFFFEu
 #define WS_END 0xFFFFu
+#define WS_CELL_BYTES ((size_t)(WS_SMALL_WARPS * WS_CAP_S + WS_LARGE_WARPS * WS_CAP_L) * 5)
+#define WS_SMEM_BYTES (WS_CELL_BYTES + (size_t)WS_WARPS * 1024)
 extern __shared__ __align__(16) unsigned char ws_smem[];
 
-__global__ void __launch_bounds__(TISEG_THREADS, 1)
-k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, int* queue,
-              int* next, int32_t* out) {
-    __shared__ int s_head[TISEG_WARPS_PER_BLOCK][256];
-    __shared__ int s_tail[TISEG_WARPS_PER_BLOCK][256];
+struct FloodLists {
+    int* small; int* large;   // [N, KS] blob ids
+    int* ns; int* nl;         // [N] list lengths
+    int* qs; int* ql;         // [N] cursors
+};
+
+__global__ void k_blob_classify(BlobInfo b, int W, FloodLists L) {
+    int n = blockIdx.y;
+    long long ko = (long long)n * b.KS;
+    int B = b.count[n];
+    for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        int h = b.ymax[ko + bid] - b.root[ko + bid] / W + 1, w = b.xmax[ko + bid] - b.xmin[ko + bid] + 1;
+        if ((w + 2) * (h + 2) <= WS_CAP_S) L.small[ko + atomicAdd(&L.ns[n], 1)] = bid;
+        else L.large[ko + atomicAdd(&L.nl[n], 1)] = bid;
+    }
+}
+
+// One blob, staged in shared memory.  head/tail: 256 u16 each (0xFFFF = empty bucket).
+__device__ __forceinline__ void flood_blob_staged(int lane, int W, const uint8_t* __restrict__ I, const int* __restrict__ tp,
+                                                  int32_t* o, int root, int y0, int x0, int w, int h,
+                                                  unsigned short* lab, unsigned short* nxs, unsigned char* lvl,
+                                                  unsigned short* head, unsigned short* tail) {
+    const int wp = w + 2, cells = wp * (h + 2);
+    for (int i = lane; i < 256; i += 32) { head[i] = 0xFFFF; tail[i] = 0xFFFF; }
+    // stage: cells walked as a flat array (all lanes busy whatever the box width), four cells per lane loaded
+    // before any is used (12 loads in flight)
+    for (int j0 = 0; j0 < cells; j0 += 128) {
+        int jj[4], gi[4];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            jj[u] = j0 + 32 * u + lane;
+            const int ly = jj[u] / wp, lx = jj[u] - ly * wp;
+            in[u] = jj[u] < cells && ly >= 1 && ly <= h && lx >= 1 && lx <= w;
+            gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
+        }
+        int tpv[4], ov[4];
+        unsigned char iv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (jj[u] >= cells) continue;
+            unsigned L = WS_NOTIN;
+            if (in[u] && tpv[u] == root) L = ov[u] != 0 ? (unsigned)jj[u] : WS_UNLAB;
+            lab[jj[u]] = (unsigned short)L;
+            lvl[jj[u]] = iv[u];
+        }
+    }
+    __syncwarp();
+    // seeds (cells that point at themselves) enter their buckets in raster order
+    int cur = 256;
+    for (int j0 = 0; j0 < cells; j0 += 32) {
+        const int j = j0 + lane;
+        const bool seed = j < cells && lab[j] == (unsigned short)j;
+        const int v = j < cells ? lvl[j] : 0;
+        unsigned m = __ballot_sync(FULL, seed);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int slv = __shfl_sync(FULL, v, src);
+            if (lane == 0) {
+                const int pix = j0 + src;
+                nxs[pix] = WS_END;
+                const unsigned t = tail[slv];
+                if (t == 0xFFFFu) head[slv] = (unsigned short)pix; else nxs[t] = (unsigned short)pix;
+                tail[slv] = (unsigned short)pix;
+                if (slv < cur) cur = slv;
+            }
+        }
+    }
+    __syncwarp();
+    // the ordered flood
+    if (lane == 0) {
+        for (;;) {
+            while (cur < 256 && head[cur] == 0xFFFFu) ++cur;
+            if (cur >= 256) break;
+            const int pix = head[cur];
+            const unsigned nxt = nxs[pix];
+            head[cur] = (unsigned short)nxt;
+            if (nxt == WS_END) tail[cur] = 0xFFFF;
+            const unsigned short L = lab[pix];
+            const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
+            unsigned short ln[4];
+            unsigned char vn[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ln[k] == WS_UNLAB) {
+                    lab[nb[k]] = L;                                       // labelled at push time
+                    nxs[nb[k]] = WS_END;
+                    const unsigned t = tail[vn[k]];
+                    if (t == 0xFFFFu) head[vn[k]] = (unsigned short)nb[k]; else nxs[t] = (unsigned short)nb[k];
+                    tail[vn[k]] = (unsigned short)nb[k];
+                    if (vn[k] < cur) cur = vn[k];
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // write back: every flooded cell takes the marker label of its seed pixel
+    for (int j0 = 0; j0 < cells; j0 += 128) {
+        int dst[4], src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u + lane;
+            dst[u] = -1; src[u] = root;
+            if (j < cells) {
+                const unsigned L = lab[j];
+                if (L < WS_UNLAB && L != (unsigned)j) {
+                    const int ly = j / wp, lx = j - ly * wp, sy = L / wp, sx = L - sy * wp;
+                    dst[u] = (y0 + ly - 1) * W + x0 + lx - 1;
+                    src[u] = (y0 + sy - 1) * W + x0 + sx - 1;
+                }
+            }
+        }
+        int val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) val[u] = o[src[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (dst[u] >= 0) o[dst[u]] = val[u];
+    }
+    __syncwarp();
+}
+
+// The same flood in global memory (framed bounding box too large for shared memory); head/tail are int[256].
+__device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const uint8_t* __restrict__ I,
+                                                  const int* __restrict__ tp, int32_t* o, int* nx, int root, int y0,
+                                                  int y1, int x0, int x1, int* head, int* tail) {
+    for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
+    __syncwarp();
+    int cur = 256;
+    for (int y = y0; y <= y1; ++y) {
+        for (int xb = x0; xb <= x1; xb += 32) {
+            int x = xb + lane;
+            bool seed = false;
+            int lv = 0;
+            if (x <= x1) {
+                int idx = y * W + x;
+                if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
+            }
+            unsigned m = __ballot_sync(FULL, seed);
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                int slv = __shfl_sync(FULL, lv, src);
+                if (lane == 0) {
+                    int pix = y * W + xb + src;
+                    nx[pix] = -1;
+                    int t = tail[slv];
+                    if (t < 0) head[slv] = pix; else nx[t] = pix;
+                    tail[slv] = pix;
+                    if (slv < cur) cur = slv;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        for (;;) {
+            while (cur < 256 && head[cur] < 0) ++cur;
+            if (cur >= 256) break;
+            const int pix = head[cur];
+            const int nxt = nx[pix];
+            head[cur] = nxt;
+            if (nxt < 0) tail[cur] = -1;
+            const int lab_g = o[pix];
+            const int y = pix / W, x = pix - y * W;
+            const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};
+            const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
+            int pv[4], ov[4], lv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                pv[k] = -1; ov[k] = 1; lv[k] = 0;
+                if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (pv[k] >= 0 && ov[k] == 0) {
+                    o[nb[k]] = lab_g;
+                    nx[nb[k]] = -1;
+                    int t = tail[lv[k]];
+                    if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
+                    tail[lv[k]] = nb[k];
+                    if (lv[k] < cur) cur = lv[k];
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * WS_WARPS, 1)
+k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodLists L,
+              int* next, int* gheads, int32_t* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem + (size_t)warp * WS_CAP * 5);
-    unsigned short* nxs = lab + WS_CAP;
-    unsigned char* lvl = reinterpret_cast<unsigned char*>(nxs + WS_CAP);
-    int* head = s_head[warp];
-    int* tail = s_tail[warp];
+    const bool large = warp >= WS_SMALL_WARPS;
+    const size_t off = large ? ((size_t)WS_SMALL_WARPS * WS_CAP_S + (size_t)(warp - WS_SMALL_WARPS) * WS_CAP_L) * 5
+                             : (size_t)warp * WS_CAP_S * 5;
+    const int cap = large ? WS_CAP_L : WS_CAP_S;
+    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem + off);
+    unsigned short* nxs = lab + cap;
+    unsigned char* lvl = reinterpret_cast<unsigned char*>(nxs + cap);
+    unsigned short* head = reinterpret_cast<unsigned short*>(ws_smem + WS_CELL_BYTES + (size_t)warp * 1024);
+    unsigned short* tail = head + 256;
     const int W = g.W, H = g.H;
     for (int tn = 0; tn < g.N; ++tn) {
         const int n = (blockIdx.x + tn) % g.N;
-        const int B = b.count[n];
         const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
         const uint8_t* I = image + base;
         const int* tp = par + base;
         int32_t* o = out + base;
-        int* nx = next + base;
-        for (;;) {
-            int bid = 0;
-            if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
-            bid = __shfl_sync(FULL, bid, 0);
-            if (bid > B) break;
-            for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
-            const int root = b.root[ko + bid];
-            const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
-            const int w = x1 - x0 + 1, h = y1 - y0 + 1, wp = w + 2;
-            int cur = 256;
-            __syncwarp();
-            if (wp * (h + 2) <= WS_CAP) {
-                // ---- stage the framed bounding box; seeds enter their buckets in raster order
-                for (int ly = 0; ly < h + 2; ++ly) {
-                    for (int lxb = 0; lxb < wp; lxb += 32) {
-                        const int lx = lxb + lane, j = ly * wp + lx;
-                        bool seed = false;
-                        unsigned v = 0;
-                        if (lx < wp) {
-                            unsigned L = WS_NOTIN;
-                            if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
-                                const int gi = (y0 + ly - 1) * W + x0 + lx - 1;
-                                if (tp[gi] == root) { v = I[gi]; seed = o[gi] != 0; L = seed ? (unsigned)j : WS_UNLAB; }
-                            }
-                            lab[j] = (unsigned short)L;
-                            lvl[j] = (unsigned char)v;
-                        }
-                        unsigned m = __ballot_sync(FULL, seed);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const int slv = __shfl_sync(FULL, (int)v, src);
-                            if (lane == 0) {
-                                const int pix = ly * wp + lxb + src;
-                                nxs[pix] = WS_END;
-                                const int t = tail[slv];
-                                if (t < 0) head[slv] = pix; else nxs[t] = (unsigned short)pix;
-                                tail[slv] = pix;
-                                if (slv < cur) cur = slv;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- the ordered flood, in shared memory
-                if (lane == 0) {
-                    for (;;) {
-                        while (cur < 256 && head[cur] < 0) ++cur;
-                        if (cur >= 256) break;
-                        const int pix = head[cur];
-                        const unsigned nxt = nxs[pix];
-                        head[cur] = nxt == WS_END ? -1 : (int)nxt;
-                        if (nxt == WS_END) tail[cur] = -1;
-                        const unsigned short L = lab[pix];
-                        const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
-                        unsigned short ln[4];
-                        unsigned char vn[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (ln[k] == WS_UNLAB) {
-                                lab[nb[k]] = L;                                       // labelled at push time
-                                nxs[nb[k]] = WS_END;
-                                const int t = tail[vn[k]];
-                                if (t < 0) head[vn[k]] = nb[k]; else nxs[t] = (unsigned short)nb[k];
-                                tail[vn[k]] = nb[k];
-                                if (vn[k] < cur) cur = vn[k];
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- write back: every flooded cell takes the marker label of its seed pixel
-                for (int ly = 1; ly <= h; ++ly) {
-                    for (int lx = 1 + lane; lx <= w; lx += 32) {
-                        const int j = ly * wp + lx;
-                        const unsigned L = lab[j];
-                        if (L < WS_UNLAB && L != (unsigned)j) {
-                            const int sy = L / wp, sx = L - sy * wp;
-                            o[(y0 + ly - 1) * W + x0 + lx - 1] = o[(y0 + sy - 1) * W + x0 + sx - 1];
-                        }
-                    }
-                }
-                __syncwarp();
-                continue;
-            }
-            // ---- fallback: the same flood in global memory (framed bounding box does not fit)
-            for (int y = y0; y <= y1; ++y) {
-                for (int xb = x0; xb <= x1; xb += 32) {
-                    int x = xb + lane;
-                    bool seed = false;
-                    int lv = 0;
-                    if (x <= x1) {
-                        int idx = y * W + x;
-                        if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
-                    }
-                    unsigned m = __ballot_sync(FULL, seed);
-                    while (m) {
-                        int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        int slv = __shfl_sync(FULL, lv, src);
-                        if (lane == 0) {
-                            int pix = y * W + xb + src;
-                            nx[pix] = -1;
-                            int t = tail[slv];
-                            if (t < 0) head[slv] = pix; else nx[t] = pix;
-                            tail[slv] = pix;
-                            if (slv < cur) cur = slv;
-                        }
-                    }
+        for (int pass = large ? 0 : 1; pass < 2; ++pass) {
+            const int* list = (pass == 0 ? L.large : L.small) + ko;
+            int* cursor = (pass == 0 ? L.ql : L.qs) + n;
+            const int count = (pass == 0 ? L.nl : L.ns)[n];
+            for (;;) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(cursor, 1);
+                k = __shfl_sync(FULL, k, 0);
+                if (k >= count) break;
+                const int bid = list[k];
+                const int root = b.root[ko + bid];
+                const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+                const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+                if ((w + 2) * (h + 2) <= cap) {
+                    flood_blob_staged(lane, W, I, tp, o, root, y0, x0, w, h, lab, nxs, lvl, head, tail);
+                } else {
+                    // only reachable by large warps: 512 ints of bucket heads per warp in global scratch
+                    int* gh = gheads + ((size_t)blockIdx.x * WS_LARGE_WARPS + (warp - WS_SMALL_WARPS)) * 512;
+                    flood_blob_global(lane, W, H, I, tp, o, next + base, root, y0, y1, x0, x1, gh, gh + 256);
                 }
             }
-            if (lane == 0) {
-                for (;;) {
-                    while (cur < 256 && head[cur] < 0) ++cur;
-                    if (cur >= 256) break;
-                    const int pix = head[cur];
-                    const int nxt = nx[pix];
-                    head[cur] = nxt;
-                    if (nxt < 0) tail[cur] = -1;
-                    const int lab_g = o[pix];
-                    const int y = pix / W, x = pix - y * W;
-                    const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};
-                    const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
-                    int pv[4], ov[4], lv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        pv[k] = -1; ov[k] = 1; lv[k] = 0;
-                        if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (pv[k] >= 0 && ov[k] == 0) {
-                            o[nb[k]] = lab_g;
-                            nx[nb[k]] = -1;
-                            int t = tail[lv[k]];
-                            if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
-                            tail[lv[k]] = nb[k];
-                            if (lv[k] < cur) cur = lv[k];
-                        }
-                    }
-                }
-            }
-            __syncwarp();
         }
     }
 }
@@ -408,17 +483,23 @@ static inline int flood_blocks(tiseg_ctx* c, int N) {
 int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
                      const BlobInfo& b, int32_t* out) {
     (void)rank;
-    int* queue = ws<int>(c, (size_t)g.N);
-    int* next = ws<int>(c, (size_t)g.N * g.P);
-    if (!queue || !next) return TISEG_ERR_CUDA;
-    TISEG_TRY(zero(c, queue, (size_t)g.N * sizeof(int)));
-    const size_t smem = (size_t)TISEG_WARPS_PER_BLOCK * WS_CAP * 5;
+    const int N = g.N;
+    const size_t ks = (size_t)N * b.KS;
+    FloodLists L;
+    L.small = ws<int>(c, ks); L.large = ws<int>(c, ks);
+    int* counters = ws<int>(c, 4 * (size_t)N);
+    int* next = ws<int>(c, (size_t)N * g.P);
+    int* gheads = ws<int>(c, (size_t)c->sm_count * WS_LARGE_WARPS * 512);
+    if (!L.small || !L.large || !counters || !next || !gheads) return TISEG_ERR_CUDA;
+    L.ns = counters; L.nl = counters + N; L.qs = counters + 2 * N; L.ql = counters + 3 * N;
+    TISEG_TRY(zero(c, counters, 4 * (size_t)N * sizeof(int)));
+    TISEG_LAUNCH(c, k_blob_classify, dim3(8, N), 256, 0, b, g.W, L);
     static bool attr_set = false;
     if (!attr_set) {
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
         attr_set = true;
     }
-    TISEG_LAUNCH(c, k_ws_flood_u8, c->sm_count, TISEG_THREADS, smem, g, image, par, b, queue, next, out);
+    TISEG_LAUNCH(c, k_ws_flood_u8, c->sm_count, 32 * WS_WARPS, WS_SMEM_BYTES, g, image, par, b, L, next, gheads, out);
     return TISEG_OK;
 }
 
