@@ -172,7 +172,8 @@ def _random_ws_case(rng, H, W, levels, nmark):
 
 def test_watershed_u8():
     rng = np.random.default_rng(50)
-    for (H, W, levels, nmark) in [(1, 9, 3, 2), (20, 31, 4, 5), (64, 64, 8, 12), (100, 130, 256, 40), (128, 128, 2, 30)]:
+    for (H, W, levels, nmark) in [(1, 9, 3, 2), (20, 31, 4, 5), (64, 64, 8, 12), (100, 130, 256, 40), (128, 128, 2, 30),
+                                 (20, 31, 256, 5), (40, 40, 64, 6), (60, 70, 31, 9), (60, 70, 33, 9), (200, 300, 20, 50)]:
         img, mk, mask = _random_ws_case(rng, H, W, levels, nmark)
         _diff(ops.watershed(img, mk, mask), sk.watershed(img, mk, mask), "watershed u8 masked %dx%d" % (H, W))
         _diff(ops.watershed(img, mk), sk.watershed(img, mk), "watershed u8 unmasked %dx%d" % (H, W))

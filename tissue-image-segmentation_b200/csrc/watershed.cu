@@ -2,6 +2,9 @@
 // and the tiseg_watershed_* entry points.  See watershed.cuh for the algorithm statement.
 #include "watershed.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace tiseg {
 
 #define FULL 0xffffffffu
@@ -92,152 +95,316 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
     st4(out, i, total, vec, o);
 }
 
-// ---- uint8 levels: 256 FIFO buckets -----------------------------------------------------------------------
+// ---- uint8 levels: FIFO buckets ---------------------------------------------------------------------------
 // A blob's flood is a chain of dependent steps (pop -> look at 4 neighbours -> push), so its speed is the latency
-// of the memory it runs in and the number of floods in flight.  Each warp STAGES its blob into shared memory: the
-// bounding box plus a one-pixel frame (no bounds checks in the flood), 5 bytes per cell — level (u8), FIFO link
-// (u16) and the local index of the seed pixel whose label the cell inherits (u16) — floods it there, and writes
-// the labels back with four loads in flight per lane.
-// One persistent CTA per SM holds 22 "small" warps (framed box <= 1024 cells: ~94 % of nuclei blobs) and 4 "large"
-// warps (<= 4096 cells); blobs are pre-sorted into a small and a large list per tile; every CTA walks all tiles
-// (starting at a different one) and drains the lists through atomic cursors, so work balances across tiles and
-// blob sizes.  Boxes beyond 4096 cells are flooded by a large warp directly in global memory.
-#define WS_SMALL_WARPS 22
-#define WS_LARGE_WARPS 4
-#define WS_WARPS (WS_SMALL_WARPS + WS_LARGE_WARPS)
-#define WS_CAP_S 1024
-#define WS_CAP_L 4096
+// of the memory it runs in and the number of floods in flight.  Every blob is therefore STAGED into shared memory
+// first: the bounding box plus a one-pixel frame (no bounds checks in the flood), 5 bytes per cell — level (u8),
+// FIFO link (u16) and the local index of the seed pixel whose label the cell inherits (u16) — flooded there, and
+// written back with batched loads/stores.
+//
+// One persistent kernel (one CTA per SM), fed from work lists sorted by size class so that long floods start first:
+//  * multi-slot floods — the workhorse.  Every warp owns an arena of shared memory that is cut into 1..SLOTS equal
+//    slots according to the size class it is working on; the warp stages one blob per slot cooperatively, links the
+//    seeds into their buckets in raster order (match_any), then LANE s FLOODS SLOT s: up to SLOTS independent floods
+//    advance per warp instruction.  Buckets are indexed by (level mod 32): a blob qualifies if its levels span < 32
+//    values (a distance map inside a nucleus does); the head and tail of the current level live in registers.
+//    Default geometry: 8 warps x 5376-cell arenas x 16 slots (variants behind TISEG_FLOOD_VARIANT for experiments,
+//    including QUAD floods where four lanes probe the four neighbours of one flood).
+//  * general floods — framed boxes beyond the arena, or level spans >= 32: one blob per CTA at a time, staged by all
+//    warps into one 45056-cell slice with all 256 buckets.  The first sm_count/12 CTAs start with this list so the
+//    largest blobs begin at t = 0; every CTA helps with it after the multi-slot work.  Level-span overflows found
+//    while flooding go to a second list drained by a second (normally empty) launch.  Only boxes beyond 45056
+//    cells are flooded in global memory.
 #define WS_NOTIN 0xFFFFu
 #define WS_UNLAB 0xFFFEu
 #define WS_END 0xFFFFu
-#define WS_CELL_BYTES ((size_t)(WS_SMALL_WARPS * WS_CAP_S + WS_LARGE_WARPS * WS_CAP_L) * 5)
-#define WS_SMEM_BYTES (WS_CELL_BYTES + (size_t)WS_WARPS * 1024)
+
+#define WM_R 32                 // levels per multi-slot flood (buckets indexed by level mod WM_R)
+#define WS_MAXCLS 16            // most slots per warp arena (= number of size classes)
+#define WG_CAP 45056            // cells of the single-blob slice of the general path
+#define WG_SMEM_BYTES ((size_t)WG_CAP * 5 + 1024)
 extern __shared__ __align__(16) unsigned char ws_smem[];
 
-struct FloodLists {
-    int* small; int* large;   // [N, KS] blob ids
-    int* ns; int* nl;         // [N] list lengths
-    int* qs; int* ql;         // [N] cursors
+// Work lists of one batch.  An item is (tile << 32) | blob id.  Size class c = blobs whose framed box fits a slot of
+// arena / (c + 1) cells but no smaller one, so class 0 holds the largest blobs and is drained first.
+struct FloodWork {
+    long long* items;   // classes 0..slots-1, contiguous, class c at offset[c] .. offset[c] + count[c]
+    long long* gen;     // general list, filled by k_flood_scatter: boxes beyond the arena
+    long long* ovf;     // overflow list, filled by the flood kernel: level spans >= WM_R; drained by a second launch
+    int* count;         // [WS_MAXCLS]
+    int* offset;        // [WS_MAXCLS]
+    int* fill;          // [WS_MAXCLS] scatter cursors
+    int* cursor;        // [WS_MAXCLS] consumption cursors
+    int* ngen;          // [2] lengths of gen, ovf
+    int* gcursor;       // [2]
 };
+#define WK_INTS (4 * WS_MAXCLS + 4)
 
-__global__ void k_blob_classify(BlobInfo b, int W, FloodLists L) {
+__device__ __forceinline__ long long blob_cells(const BlobInfo& b, long long ko, int bid, int W) {
+    int h = b.ymax[ko + bid] - b.root[ko + bid] / W + 1, w = b.xmax[ko + bid] - b.xmin[ko + bid] + 1;
+    return (long long)(w + 2) * (h + 2);
+}
+__device__ __forceinline__ int blob_class(long long cells, int arena, int slots) {
+    if (cells > arena) return -1;
+    int cls = arena / (int)cells - 1;
+    return cls >= slots ? slots - 1 : cls;
+}
+
+__global__ void k_flood_count(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
     int n = blockIdx.y;
     long long ko = (long long)n * b.KS;
     int B = b.count[n];
     for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
-        int h = b.ymax[ko + bid] - b.root[ko + bid] / W + 1, w = b.xmax[ko + bid] - b.xmin[ko + bid] + 1;
-        if ((w + 2) * (h + 2) <= WS_CAP_S) L.small[ko + atomicAdd(&L.ns[n], 1)] = bid;
-        else L.large[ko + atomicAdd(&L.nl[n], 1)] = bid;
+        int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
+        if (cls >= 0) atomicAdd(&wk.count[cls], 1);
+    }
+}
+__global__ void k_flood_offsets(FloodWork wk) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < WS_MAXCLS; ++k) { wk.offset[k] = acc; acc += wk.count[k]; }
+    }
+}
+__global__ void k_flood_scatter(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
+    int n = blockIdx.y;
+    long long ko = (long long)n * b.KS;
+    int B = b.count[n];
+    for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
+        long long item = ((long long)n << 32) | (unsigned)bid;
+        if (cls >= 0) wk.items[wk.offset[cls] + atomicAdd(&wk.fill[cls], 1)] = item;
+        else wk.gen[atomicAdd(wk.ngen, 1)] = item;
     }
 }
 
-// One blob, staged in shared memory.  head/tail: 256 u16 each (0xFFFF = empty bucket).
-__device__ __forceinline__ void flood_blob_staged(int lane, int W, const uint8_t* __restrict__ I, const int* __restrict__ tp,
-                                                  int32_t* o, int root, int y0, int x0, int w, int h,
-                                                  unsigned short* lab, unsigned short* nxs, unsigned char* lvl,
-                                                  unsigned short* head, unsigned short* tail) {
+// floor(j / wp) for j * wp < 2^32 with magic = 0xFFFFFFFF / wp + 1
+__device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulhi((unsigned)j, magic); }
+
+// Copy the framed box of a blob into shared memory: lab = own index (seed), UNLAB (in the blob), NOTIN; lvl = level.
+// `tid`/`nthr`: the cooperating threads (a warp or a CTA); eight cells per thread are loaded before any is used.
+__device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const uint8_t* __restrict__ I,
+                                           const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
+                                           int y0, int x0, int w, int h, unsigned short* lab, unsigned char* lvl) {
     const int wp = w + 2, cells = wp * (h + 2);
-    for (int i = lane; i < 256; i += 32) { head[i] = 0xFFFF; tail[i] = 0xFFFF; }
-    // stage: cells walked as a flat array (all lanes busy whatever the box width), four cells per lane loaded
-    // before any is used (12 loads in flight)
-    for (int j0 = 0; j0 < cells; j0 += 128) {
-        int jj[4], gi[4];
-        bool in[4];
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
+    for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
+        int gi[8];
+        bool in[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            jj[u] = j0 + 32 * u + lane;
-            const int ly = jj[u] / wp, lx = jj[u] - ly * wp;
-            in[u] = jj[u] < cells && ly >= 1 && ly <= h && lx >= 1 && lx <= w;
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            const int ly = fdiv(j, magic), lx = j - ly * wp;
+            in[u] = j < cells && ly >= 1 && ly <= h && lx >= 1 && lx <= w;
             gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
         }
-        int tpv[4], ov[4];
-        unsigned char iv[4];
+        int tpv[8], ov[8];
+        unsigned char iv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+        for (int u = 0; u < 8; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (jj[u] >= cells) continue;
-            unsigned L = WS_NOTIN;
-            if (in[u] && tpv[u] == root) L = ov[u] != 0 ? (unsigned)jj[u] : WS_UNLAB;
-            lab[jj[u]] = (unsigned short)L;
-            lvl[jj[u]] = iv[u];
-        }
-    }
-    __syncwarp();
-    // seeds (cells that point at themselves) enter their buckets in raster order
-    int cur = 256;
-    for (int j0 = 0; j0 < cells; j0 += 32) {
-        const int j = j0 + lane;
-        const bool seed = j < cells && lab[j] == (unsigned short)j;
-        const int v = j < cells ? lvl[j] : 0;
-        unsigned m = __ballot_sync(FULL, seed);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int slv = __shfl_sync(FULL, v, src);
-            if (lane == 0) {
-                const int pix = j0 + src;
-                nxs[pix] = WS_END;
-                const unsigned t = tail[slv];
-                if (t == 0xFFFFu) head[slv] = (unsigned short)pix; else nxs[t] = (unsigned short)pix;
-                tail[slv] = (unsigned short)pix;
-                if (slv < cur) cur = slv;
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            if (j < cells) {
+                const bool inblob = in[u] && tpv[u] == root;
+                lab[j] = (unsigned short)(inblob ? (ov[u] != 0 ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
+                lvl[j] = iv[u];
             }
         }
     }
-    __syncwarp();
-    // the ordered flood
-    if (lane == 0) {
-        for (;;) {
-            while (cur < 256 && head[cur] == 0xFFFFu) ++cur;
-            if (cur >= 256) break;
-            const int pix = head[cur];
-            const unsigned nxt = nxs[pix];
-            head[cur] = (unsigned short)nxt;
-            if (nxt == WS_END) tail[cur] = 0xFFFF;
-            const unsigned short L = lab[pix];
-            const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
-            unsigned short ln[4];
-            unsigned char vn[4];
+}
+
+// One warp links the seeds of a staged blob into their buckets in raster order (32 cells per step, the seeds of one
+// level inside a step chained with match_any) and returns the level range of the blob and the lowest seed level.
+template <class Bucket>
+__device__ __forceinline__ void link_seeds(int lane, int cells, const unsigned short* lab, unsigned short* nxs,
+                                           const unsigned char* lvl, unsigned short* head, unsigned short* tail,
+                                           Bucket B, int& vmin, int& vmax, int& vsmin) {
+    vmin = 256; vmax = -1; vsmin = 256;
+    for (int j0 = 0; j0 < cells; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned L = WS_NOTIN;
+        int v = 0;
+        if (j < cells) { L = lab[j]; v = lvl[j]; }
+        const bool seed = L == (unsigned)j, inblob = L != WS_NOTIN;
+        if (inblob) { vmin = min(vmin, v); vmax = max(vmax, v); }
+        if (__ballot_sync(FULL, seed)) {
+            const unsigned peers = __match_any_sync(FULL, seed ? v : (0x100 | lane));
+            const unsigned below = peers & ((1u << lane) - 1u), above = lane == 31 ? 0u : (peers >> (lane + 1));
+            unsigned t = WS_END;
+            if (seed) {
+                vsmin = min(vsmin, v);
+                if (!below) t = tail[B(v)];
+            }
+            __syncwarp();
+            if (seed) {
+                nxs[j] = (unsigned short)(above ? (unsigned)(j + __ffs(above)) : WS_END);
+                if (!below) { if (t == WS_END) head[B(v)] = (unsigned short)j; else nxs[t] = (unsigned short)j; }
+                if (!above) tail[B(v)] = (unsigned short)j;
+            }
+            __syncwarp();
+        }
+    }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
+    for (int d = 16; d; d >>= 1) {
+        vmin = min(vmin, __shfl_xor_sync(FULL, vmin, d));
+        vmax = max(vmax, __shfl_xor_sync(FULL, vmax, d));
+        vsmin = min(vsmin, __shfl_xor_sync(FULL, vsmin, d));
+    }
+}
+
+// direction j of a quad lane: 0 up, 1 left, 2 right, 3 down (skimage's neighbour order)
+__device__ __forceinline__ int dir_off(int j, int wp) { return ((j == 0 || j == 3) ? wp : 1) * (j >= 2 ? 1 : -1); }
+
+// The ordered floods of the staged blobs of one warp: quad q (lanes 4q..4q+3) floods its own blob, lane k of the quad
+// probing neighbour k.  All quads run one warp-uniform loop (finished quads are predicated off), so the warp-level
+// primitives take the full mask.  cur / hcur / tcur (current level, head and tail of its bucket) are replicated in
+// the four lanes of a quad; lane k = 0 writes them back when the quad leaves a level.
+template <class Bucket>
+__device__ __forceinline__ void quad_flood(int lane, bool active, int wp, int smin, int lmax, unsigned short* lab,
+                                           unsigned short* nxs, const unsigned char* lvl, unsigned short* head,
+                                           unsigned short* tail, Bucket B) {
+    const int k = lane & 3;
+    const int off = dir_off(k, wp);
+    int cur = smin;
+    unsigned hcur = WS_END, tcur = WS_END;
+    if (active) { hcur = head[B(cur)]; tcur = tail[B(cur)]; }
+    for (;;) {
+        if (active && hcur == WS_END) {            // level exhausted: its bucket must read empty from now on
+            if (k == 0) { head[B(cur)] = (unsigned short)WS_END; tail[B(cur)] = (unsigned short)WS_END; }
+            do { ++cur; } while (cur <= lmax && (hcur = head[B(cur)]) == WS_END);
+            if (cur > lmax) active = false; else tcur = tail[B(cur)];
+        }
+        if (!__any_sync(FULL, active)) break;
+        __syncwarp();
+        const int pix = (int)hcur, nb = pix + off;
+        unsigned nxt = WS_END, L = 0, ln = WS_NOTIN;
+        int vn = 0;
+        if (active) { nxt = nxs[pix]; L = lab[pix]; ln = lab[nb]; vn = lvl[nb]; }
+        const bool push = ln == WS_UNLAB, same = push && vn == cur;
+        unsigned t = WS_END;
+        if (push && !same) t = tail[B(vn)];
+        // FIFO order of the pushes of this step inside the quad: who pushes to my level before / after me
+        const int key = push ? vn : (0x100 | k);
+        int below = -1, above = 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (ln[k] == WS_UNLAB) {
-                    lab[nb[k]] = L;                                       // labelled at push time
-                    nxs[nb[k]] = WS_END;
-                    const unsigned t = tail[vn[k]];
-                    if (t == 0xFFFFu) head[vn[k]] = (unsigned short)nb[k]; else nxs[t] = (unsigned short)nb[k];
-                    tail[vn[k]] = (unsigned short)nb[k];
-                    if (vn[k] < cur) cur = vn[k];
+        for (int x = 1; x < 4; ++x) {
+            const int kp = __shfl_xor_sync(FULL, key, x), p = k ^ x;
+            if (kp == key) { if (p < k) below = max(below, p); else above = min(above, p); }
+        }
+        const unsigned bs = (__ballot_sync(FULL, same) >> (lane & ~3)) & 0xFu;
+        const unsigned bl = __ballot_sync(FULL, push && vn < cur);
+        __syncwarp();                              // every probe of this step precedes every update
+        if (active) hcur = nxt;
+        if (push) {
+            lab[nb] = (unsigned short)L;           // labelled at push time
+            nxs[nb] = (unsigned short)(above < 4 ? (unsigned)(pix + dir_off(above, wp)) : WS_END);
+            if (below < 0) {
+                if (same) { if (hcur != WS_END) nxs[tcur] = (unsigned short)nb; }
+                else if (t == WS_END) head[B(vn)] = (unsigned short)nb;
+                else nxs[t] = (unsigned short)nb;
+            }
+            if (above == 4 && !same) tail[B(vn)] = (unsigned short)nb;
+        }
+        if (bs) {
+            if (hcur == WS_END) hcur = (unsigned)(pix + dir_off(__ffs(bs) - 1, wp));
+            tcur = (unsigned)(pix + dir_off(31 - __clz(bs), wp));
+        }
+        if (bl) {                                  // (uniform) a lower level appeared somewhere in the warp
+            int pv = push ? vn : 256;
+            pv = min(pv, __shfl_xor_sync(FULL, pv, 1));
+            pv = min(pv, __shfl_xor_sync(FULL, pv, 2));
+            const bool descend = active && pv < cur;
+            if (descend && k == 0) {               // park the current bucket
+                head[B(cur)] = (unsigned short)hcur;
+                tail[B(cur)] = (unsigned short)(hcur == WS_END ? WS_END : tcur);
+            }
+            __syncwarp();
+            if (descend) { cur = pv; hcur = head[B(cur)]; tcur = tail[B(cur)]; }
+        }
+    }
+}
+
+// The ordered flood of one staged blob by ONE lane (the lanes of a warp flood different slots side by side).  The
+// head and tail of the current level's bucket live in registers; the four neighbours' probes and the tails of the
+// buckets they will be pushed to are loaded before any update.
+template <class Bucket>
+__device__ __forceinline__ int lane_flood(int wp, int smin, int lmax, unsigned short* lab, unsigned short* nxs,
+                                          const unsigned char* lvl, unsigned short* head, unsigned short* tail, Bucket B) {
+    int cur = smin, pops = 0;
+    unsigned hcur = head[B(cur)], tcur = tail[B(cur)];
+    for (;;) {
+        if (hcur == WS_END) {
+            head[B(cur)] = (unsigned short)WS_END; tail[B(cur)] = (unsigned short)WS_END;
+            do { ++cur; } while (cur <= lmax && (hcur = head[B(cur)]) == WS_END);
+            if (cur > lmax) break;
+            tcur = tail[B(cur)];
+        }
+        ++pops;
+        const int pix = (int)hcur;
+        const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
+        unsigned ln[4], tl[4];
+        int vn[4];
+        hcur = nxs[pix];
+        const unsigned short L = lab[pix];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tl[k] = (ln[k] == WS_UNLAB && vn[k] != cur) ? tail[B(vn[k])] : WS_END;
+        int newcur = cur;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ln[k] == WS_UNLAB) {
+                lab[nb[k]] = L;                                       // labelled at push time
+                nxs[nb[k]] = (unsigned short)WS_END;
+                if (vn[k] == cur) {
+                    if (hcur == WS_END) hcur = (unsigned)nb[k]; else nxs[tcur] = (unsigned short)nb[k];
+                    tcur = (unsigned)nb[k];
+                } else {
+                    unsigned t = tl[k];
+#pragma unroll
+                    for (int q = 0; q < k; ++q) if (ln[q] == WS_UNLAB && vn[q] == vn[k]) t = (unsigned)nb[q];
+                    if (t == WS_END) head[B(vn[k])] = (unsigned short)nb[k]; else nxs[t] = (unsigned short)nb[k];
+                    tail[B(vn[k])] = (unsigned short)nb[k];
+                    newcur = min(newcur, vn[k]);
                 }
             }
         }
+        if (newcur < cur) {           // a lower level appeared: park the current bucket and descend
+            head[B(cur)] = (unsigned short)hcur;
+            tail[B(cur)] = (unsigned short)(hcur == WS_END ? WS_END : tcur);
+            cur = newcur;
+            hcur = head[B(cur)]; tcur = tail[B(cur)];
+        }
     }
-    __syncwarp();
-    // write back: every flooded cell takes the marker label of its seed pixel
-    for (int j0 = 0; j0 < cells; j0 += 128) {
-        int dst[4], src[4];
+    return pops;
+}
+
+// Every flooded cell takes the marker label of its seed pixel (eight gathers in flight per thread).
+__device__ __forceinline__ void stage_writeback(int tid, int nthr, int W, int32_t* o, int y0, int x0, int w, int h,
+                                                const unsigned short* lab) {
+    const int wp = w + 2, cells = wp * (h + 2), anchor = y0 * W + x0;
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
+    for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
+        int dst[8], src[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 32 * u + lane;
-            dst[u] = -1; src[u] = root;
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            dst[u] = -1; src[u] = anchor;
             if (j < cells) {
                 const unsigned L = lab[j];
                 if (L < WS_UNLAB && L != (unsigned)j) {
-                    const int ly = j / wp, lx = j - ly * wp, sy = L / wp, sx = L - sy * wp;
+                    const int ly = fdiv(j, magic), lx = j - ly * wp, sy = fdiv((int)L, magic), sx = (int)L - sy * wp;
                     dst[u] = (y0 + ly - 1) * W + x0 + lx - 1;
                     src[u] = (y0 + sy - 1) * W + x0 + sx - 1;
                 }
             }
         }
-        int val[4];
+        int val[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) val[u] = o[src[u]];
+        for (int u = 0; u < 8; ++u) val[u] = o[src[u]];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (dst[u] >= 0) o[dst[u]] = val[u];
+        for (int u = 0; u < 8; ++u) if (dst[u] >= 0) o[dst[u]] = val[u];
     }
-    __syncwarp();
 }
 
 // The same flood in global memory (framed bounding box too large for shared memory); head/tail are int[256].
@@ -306,49 +473,167 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * WS_WARPS, 1)
-k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodLists L,
-              int* next, int* gheads, int32_t* out) {
+struct BucketAll { __device__ __forceinline__ int operator()(int v) const { return v; } };
+template <int SLOTS> struct BucketSlot {    // heads of one level are contiguous over the slots of the warp
+    int s;
+    __device__ __forceinline__ int operator()(int v) const { return ((v & (WM_R - 1)) * SLOTS) + s; }
+};
+
+// General path: one blob per CTA at a time, staged by all warps into one WG_CAP-cell slice with all 256 buckets.
+template <bool QUAD>
+__device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __restrict__ image, const int* __restrict__ par,
+                                              const BlobInfo& b, const long long* list, int count, int* cursor, int* next,
+                                              int* gheads, int32_t* out) {
+    __shared__ int s_item;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool large = warp >= WS_SMALL_WARPS;
-    const size_t off = large ? ((size_t)WS_SMALL_WARPS * WS_CAP_S + (size_t)(warp - WS_SMALL_WARPS) * WS_CAP_L) * 5
-                             : (size_t)warp * WS_CAP_S * 5;
-    const int cap = large ? WS_CAP_L : WS_CAP_S;
-    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem + off);
-    unsigned short* nxs = lab + cap;
-    unsigned char* lvl = reinterpret_cast<unsigned char*>(nxs + cap);
-    unsigned short* head = reinterpret_cast<unsigned short*>(ws_smem + WS_CELL_BYTES + (size_t)warp * 1024);
+    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem);
+    unsigned short* nxs = lab + WG_CAP;
+    unsigned short* head = nxs + WG_CAP;
     unsigned short* tail = head + 256;
+    unsigned char* lvl = reinterpret_cast<unsigned char*>(tail + 256);
     const int W = g.W, H = g.H;
-    for (int tn = 0; tn < g.N; ++tn) {
-        const int n = (blockIdx.x + tn) % g.N;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int k = s_item;
+        if (k >= count) break;
+        const long long item = list[k];
+        const int n = (int)(item >> 32), bid = (int)(item & 0xffffffffll);
         const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
         const uint8_t* I = image + base;
         const int* tp = par + base;
         int32_t* o = out + base;
-        for (int pass = large ? 0 : 1; pass < 2; ++pass) {
-            const int* list = (pass == 0 ? L.large : L.small) + ko;
-            int* cursor = (pass == 0 ? L.ql : L.qs) + n;
-            const int count = (pass == 0 ? L.nl : L.ns)[n];
+        const int root = b.root[ko + bid];
+        const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+        const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+        const long long cells = (long long)(w + 2) * (h + 2);
+        if (cells > WG_CAP) {         // does not fit: the same flood in global memory, by one lane
+            if (warp == 0) flood_blob_global(lane, W, H, I, tp, o, next + base, root, y0, y1, x0, x1,
+                                             gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+            continue;
+        }
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
+        stage_copy(threadIdx.x, blockDim.x, W, I, tp, o, root, y0, x0, w, h, lab, lvl);
+        __syncthreads();
+        if (warp == 0) {
+            int vmin, vmax, vsmin;
+            link_seeds(lane, (int)cells, lab, nxs, lvl, head, tail, BucketAll{}, vmin, vmax, vsmin);
+            __syncwarp();
+            if (QUAD) quad_flood(lane, lane < 4 && vsmin <= vmax, w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketAll{});
+            else if (lane == 0 && vsmin <= vmax) lane_flood(w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketAll{});
+        }
+        __syncthreads();
+        stage_writeback(threadIdx.x, blockDim.x, W, o, y0, x0, w, h, lab);
+    }
+}
+
+// The flood kernel.  CTAs below `gen_first` start with the general list (the few largest blobs begin at t = 0), every
+// CTA then drains the multi-slot classes from the largest to the smallest (`do_multi`), and finally helps with what
+// is left of the general list.
+template <int WARPS, int ARENA, int SLOTS, bool QUAD, bool PROF>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodWork wk,
+              int* next, int* gheads, int32_t* out, int gen_first, int do_multi, long long* prof) {
+    constexpr size_t WARP_BYTES = (size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4;
+    if (!do_multi) {       // second launch: what the first one found too wide in levels
+        general_drain<QUAD>(g, image, par, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
+        return;
+    }
+    const int ngen = wk.ngen[0];
+    if ((int)blockIdx.x < gen_first && ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    {
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        long long t_stage = 0, t_flood = 0, t_wb = 0, t0 = 0, t_all = PROF ? clock64() : 0, iters = 0;
+        unsigned char* wbase = ws_smem + (size_t)warp * WARP_BYTES;
+        unsigned short* lab = reinterpret_cast<unsigned short*>(wbase);
+        unsigned short* nxs = lab + ARENA;
+        unsigned short* head = nxs + ARENA;
+        unsigned short* tail = head + WM_R * SLOTS;
+        unsigned char* lvl = reinterpret_cast<unsigned char*>(tail + WM_R * SLOTS);
+        const int W = g.W;
+        for (int cls = 0; cls < SLOTS; ++cls) {
+            const int cap = ARENA / (cls + 1), slots = cls + 1;
+            const int cnt = wk.count[cls];
+            const long long* list = wk.items + wk.offset[cls];
             for (;;) {
-                int k = 0;
-                if (lane == 0) k = atomicAdd(cursor, 1);
-                k = __shfl_sync(FULL, k, 0);
-                if (k >= count) break;
-                const int bid = list[k];
-                const int root = b.root[ko + bid];
-                const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
-                const int w = x1 - x0 + 1, h = y1 - y0 + 1;
-                if ((w + 2) * (h + 2) <= cap) {
-                    flood_blob_staged(lane, W, I, tp, o, root, y0, x0, w, h, lab, nxs, lvl, head, tail);
-                } else {
-                    // only reachable by large warps: 512 ints of bucket heads per warp in global scratch
-                    int* gh = gheads + ((size_t)blockIdx.x * WS_LARGE_WARPS + (warp - WS_SMALL_WARPS)) * 512;
-                    flood_blob_global(lane, W, H, I, tp, o, next + base, root, y0, y1, x0, x1, gh, gh + 256);
+                int k0 = 0;
+                if (lane == 0) k0 = atomicAdd(&wk.cursor[cls], slots);
+                k0 = __shfl_sync(FULL, k0, 0);
+                if (k0 >= cnt) break;
+                const int m = min(slots, cnt - k0);
+                // lane s < m holds the description of the blob in slot s
+                int mn = 0, mroot = 0, my0 = 0, mx0 = 0, mw = 0, mh = 0;
+                if (lane < m) {
+                    const long long item = list[k0 + lane];
+                    mn = (int)(item >> 32);
+                    const int bid = (int)(item & 0xffffffffll);
+                    const long long ko = (long long)mn * b.KS;
+                    mroot = b.root[ko + bid];
+                    my0 = mroot / W; mx0 = b.xmin[ko + bid];
+                    mw = b.xmax[ko + bid] - mx0 + 1; mh = b.ymax[ko + bid] - my0 + 1;
                 }
+                for (int i = lane; i < WM_R * SLOTS; i += 32) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
+                if (PROF) t0 = clock64();
+                for (int s = 0; s < m; ++s) {
+                    const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s);
+                    const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    const long long base = (long long)n * g.P;
+                    stage_copy(lane, 32, W, image + base, par + base, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
+                }
+                __syncwarp();
+                int lmin = 256, lmax = -1, smin = 256;        // of slot `lane`
+                for (int s = 0; s < m; ++s) {
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    int vmin, vmax, vsmin;
+                    link_seeds(lane, (w + 2) * (h + 2), lab + s * cap, nxs + s * cap, lvl + s * cap, head, tail,
+                               BucketSlot<SLOTS>{s}, vmin, vmax, vsmin);
+                    if (lane == s) { lmin = vmin; lmax = vmax; smin = vsmin; }
+                }
+                __syncwarp();
+                if (PROF) { long long t = clock64(); t_stage += t - t0; t0 = t; }
+                // ---- the floods: quad q / lane s floods slot q / s
+                const bool overflow = lane < m && lmax - lmin >= WM_R;
+                if (overflow) wk.ovf[atomicAdd(wk.ngen + 1, 1)] = list[k0 + lane];
+                const unsigned ovf = __ballot_sync(FULL, overflow);
+                if (QUAD) {
+                    const int q = lane >> 2;
+                    const int qw = __shfl_sync(FULL, mw, q), qsmin = __shfl_sync(FULL, smin, q), qlmax = __shfl_sync(FULL, lmax, q);
+                    quad_flood(lane, q < m && !((ovf >> q) & 1u) && qsmin <= qlmax, qw + 2, qsmin, qlmax, lab + q * cap,
+                               nxs + q * cap, lvl + q * cap, head, tail, BucketSlot<SLOTS>{q});
+                } else {
+                    int pops = 0;
+                    if (lane < m && !overflow && smin <= lmax)
+                        pops = lane_flood(mw + 2, smin, lmax, lab + lane * cap, nxs + lane * cap, lvl + lane * cap, head, tail,
+                                          BucketSlot<SLOTS>{lane});
+                    if (PROF) {
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) pops = max(pops, __shfl_xor_sync(FULL, pops, d));
+                        iters += pops;
+                    }
+                }
+                __syncwarp();
+                if (PROF) { long long t = clock64(); t_flood += t - t0; t0 = t; }
+                // ---- write back
+                for (int s = 0; s < m; ++s) {
+                    if ((ovf >> s) & 1u) continue;
+                    const int n = __shfl_sync(FULL, mn, s);
+                    const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    stage_writeback(lane, 32, W, out + (long long)n * g.P, y0, x0, w, h, lab + s * cap);
+                }
+                __syncwarp();
+                if (PROF) t_wb += clock64() - t0;
             }
         }
+        if (PROF && lane == 0) {
+            long long* p = prof + ((size_t)blockIdx.x * WARPS + warp) * 5;
+            p[0] = t_stage; p[1] = t_flood; p[2] = t_wb; p[3] = clock64() - t_all; p[4] = iters;
+        }
     }
+    if (ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
 }
 
 // ---- fp64 values: binary heap keyed (value, age, index) -------------------------------------------------
@@ -480,27 +765,78 @@ static inline int flood_blocks(tiseg_ctx* c, int N) {
     return per_tile;
 }
 
+template <int WARPS, int ARENA, int SLOTS, bool QUAD>
+static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const BlobInfo& b,
+                        FloodWork wk, int* next, int* gheads, int32_t* out, int* ints, bool debug) {
+    static_assert(SLOTS <= WS_MAXCLS && (!QUAD || SLOTS <= 8), "slots");
+    constexpr size_t MULTI = (size_t)WARPS * ((size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4);
+    constexpr size_t SMEM = MULTI > WG_SMEM_BYTES ? MULTI : WG_SMEM_BYTES;
+    static_assert(SMEM + 64 <= 232448, "shared memory");
+    TISEG_LAUNCH(c, k_flood_count, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
+    TISEG_LAUNCH(c, k_flood_offsets, 1, 32, 0, wk);
+    TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_set = true;
+    }
+    const int gen_first = c->sm_count >= 64 ? c->sm_count / 12 : 1;
+    long long* prof = nullptr;
+    if (debug) {
+        prof = ws<long long>(c, (size_t)c->sm_count * WARPS * 5);
+        if (!prof) return TISEG_ERR_CUDA;
+        TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
+                     gheads, out, gen_first, 1, prof);
+    } else {
+        TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
+                     gheads, out, gen_first, 1, prof);
+    }
+    // blobs found too wide in levels after the other CTAs had left the general list; exits at once if there are none
+    TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
+                 gheads, out, 0, 0, nullptr);
+    if (debug) {                                  // work-list census on stderr (synchronises; diagnostics only)
+        int h[WK_INTS];
+        TISEG_CHECK(cudaMemcpyAsync(h, ints, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        TISEG_CHECK(cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[tiseg flood] warps %d arena %d slots %d quad %d | N=%d classes:", WARPS, ARENA, SLOTS, (int)QUAD, g.N);
+        for (int k = 0; k < SLOTS; ++k) fprintf(stderr, " %d", h[k]);
+        fprintf(stderr, " | general: %d, level-span overflow: %d\n", h[4 * WS_MAXCLS], h[4 * WS_MAXCLS + 1]);
+        std::vector<long long> hp((size_t)c->sm_count * WARPS * 5);
+        TISEG_CHECK(cudaMemcpy(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long sum[5] = {0, 0, 0, 0, 0}, mx[5] = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i < hp.size(); ++i) { sum[i % 5] += hp[i]; if (hp[i] > mx[i % 5]) mx[i % 5] = hp[i]; }
+        const double nw = (double)c->sm_count * WARPS;
+        fprintf(stderr, "[tiseg flood] per-warp cycles mean (max): stage %.0f (%lld) flood %.0f (%lld) writeback %.0f (%lld) total %.0f (%lld); flood steps %.0f (%lld)\n",
+                sum[0] / nw, mx[0], sum[1] / nw, mx[1], sum[2] / nw, mx[2], sum[3] / nw, mx[3], sum[4] / nw, mx[4]);
+    }
+    return TISEG_OK;
+}
+
 int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
                      const BlobInfo& b, int32_t* out) {
     (void)rank;
     const int N = g.N;
-    const size_t ks = (size_t)N * b.KS;
-    FloodLists L;
-    L.small = ws<int>(c, ks); L.large = ws<int>(c, ks);
-    int* counters = ws<int>(c, 4 * (size_t)N);
+    const size_t max_blobs = (size_t)N * ((size_t)g.P / 2 + 1);      // a checkerboard is the worst case
+    FloodWork wk;
+    wk.items = ws<long long>(c, max_blobs);
+    wk.gen = ws<long long>(c, max_blobs);
+    wk.ovf = ws<long long>(c, max_blobs);
+    int* ints = ws<int>(c, WK_INTS);
     int* next = ws<int>(c, (size_t)N * g.P);
-    int* gheads = ws<int>(c, (size_t)c->sm_count * WS_LARGE_WARPS * 512);
-    if (!L.small || !L.large || !counters || !next || !gheads) return TISEG_ERR_CUDA;
-    L.ns = counters; L.nl = counters + N; L.qs = counters + 2 * N; L.ql = counters + 3 * N;
-    TISEG_TRY(zero(c, counters, 4 * (size_t)N * sizeof(int)));
-    TISEG_LAUNCH(c, k_blob_classify, dim3(8, N), 256, 0, b, g.W, L);
-    static bool attr_set = false;
-    if (!attr_set) {
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
-        attr_set = true;
+    int* gheads = ws<int>(c, (size_t)c->sm_count * 512);
+    if (!wk.items || !wk.gen || !wk.ovf || !ints || !next || !gheads) return TISEG_ERR_CUDA;
+    wk.count = ints; wk.offset = ints + WS_MAXCLS; wk.fill = ints + 2 * WS_MAXCLS; wk.cursor = ints + 3 * WS_MAXCLS;
+    wk.ngen = ints + 4 * WS_MAXCLS; wk.gcursor = wk.ngen + 2;
+    TISEG_TRY(zero(c, ints, WK_INTS * sizeof(int)));
+    static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
+    static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
+    switch (variant) {
+        case 1: return flood_launch<12, 3584, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 2: return flood_launch<16, 2688, 8, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 3: return flood_launch<8, 5376, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        default: return flood_launch<8, 5376, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
     }
-    TISEG_LAUNCH(c, k_ws_flood_u8, c->sm_count, 32 * WS_WARPS, WS_SMEM_BYTES, g, image, par, b, L, next, gheads, out);
-    return TISEG_OK;
 }
 
 int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,
