@@ -4,10 +4,13 @@
 
 namespace tiseg {
 
-// every foreground pixel points directly at its root; cnt[n, y, seg] = number of roots in the row segment
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, int* __restrict__ cnt) {
+// every foreground pixel points directly at its root; bits[n, y, seg] = ballot of the roots of the row segment
+template <bool LISTED>
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, unsigned* __restrict__ bits) {
     Strip s;
     if (!warp_strip(g, s)) return;
+    FOR_TILES(LISTED, g, n) {
+    strip_set_tile(g, s, n);
     int* tp = par + s.base;
     int p[STRIP_R];
 #pragma unroll
@@ -29,22 +32,26 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par,
             root = a == idx;
         }
         unsigned m = __ballot_sync(0xffffffffu, root);
-        if (s.lane == 0 && y < g.H) cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] = __popc(m);
+        if (s.lane == 0 && y < g.H) bits[((long long)s.n * g.H + y) * g.SEG + s.seg] = m;
+    }
     }
 }
 
-// one block per tile: thread = row.  Pass 1: row totals -> block scan with carry -> row offsets; pass 2: the
-// exclusive prefix inside each row.  cnt[n, y, seg] becomes the raster-order exclusive prefix.
-__global__ void k_rank_scan(Geom g, int* cnt, int* counts) {
+// one block per tile, thread = row: selected pixels per row (popcount of the row's words), block scan with carry.
+// rowpre[n, y] = selected pixels in the rows above y; counts[n] = total.
+template <bool LISTED>
+__global__ void k_rank_rowscan(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rowpre, int* counts) {
     __shared__ int s[256];
     __shared__ int carry;
-    int* b = cnt + (long long)blockIdx.x * g.H * g.SEG;
+    FOR_TILES_OF(LISTED, g, (int)blockIdx.x, n) {
+    const unsigned* b = bits + (long long)n * g.H * g.SEG;
+    __syncthreads();
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < g.H; base += 256) {
         int y = base + threadIdx.x;
         int v = 0;
-        if (y < g.H) for (int k = 0; k < g.SEG; ++k) v += b[(long long)y * g.SEG + k];
+        if (y < g.H) for (int k = 0; k < g.SEG; ++k) v += __popc(b[(long long)y * g.SEG + k]);
         s[threadIdx.x] = v;
         __syncthreads();
         for (int d = 1; d < 256; d <<= 1) {
@@ -55,26 +62,57 @@ __global__ void k_rank_scan(Geom g, int* cnt, int* counts) {
         }
         int incl = s[threadIdx.x];
         int c0 = carry;
-        if (y < g.H) {
-            int run = c0 + incl - v;
-            for (int k = 0; k < g.SEG; ++k) { int t = b[(long long)y * g.SEG + k]; b[(long long)y * g.SEG + k] = run; run += t; }
-        }
+        if (y < g.H) rowpre[(long long)n * g.H + y] = c0 + incl - v;
         __syncthreads();
         if (threadIdx.x == 255) carry = c0 + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = carry;
+    if (threadIdx.x == 0 && counts) counts[n] = carry;
+    }
+}
+
+// one warp per row, lane = row segment: warp scan of the popcounts, then one store per selected pixel
+template <bool LISTED>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_rank_place_bits(Geom g, const unsigned* __restrict__ bits, const int* __restrict__ rowpre, int* __restrict__ rank) {
+    const int y = blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (y >= g.H) return;
+    FOR_TILES(LISTED, g, n) {
+    int run = rowpre[(long long)n * g.H + y];
+    int* out = rank + (long long)n * g.P + (long long)y * g.W;
+    for (int c0 = 0; c0 < g.SEG; c0 += 32) {
+        const int seg = c0 + lane;
+        unsigned m = seg < g.SEG ? bits[((long long)n * g.H + y) * g.SEG + seg] : 0u;
+        int incl = __popc(m);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int k = run + incl - __popc(m);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            out[seg * 32 + bit] = ++k;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    }
 }
 
 // out = par >= 0 ? rank[par] : 0, four pixels per thread
+template <bool LISTED>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_apply_rank(long long P, const int* __restrict__ par, const int* __restrict__ rank, int32_t* __restrict__ out, bool vec) {
-    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+k_apply_rank(Geom g, const int* __restrict__ par, const int* __restrict__ rank, int32_t* __restrict__ out, bool vec) {
+    const long long P = g.P, i = flat4_index();
     if (i >= P) return;
-    Pack4<int> p = ld4(par + base, i, P, vec), o;
+    FOR_TILES(LISTED, g, n) {
+        const long long base = (long long)n * P;
+        Pack4<int> p = ld4(par + base, i, P, vec), o;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) o.v[k] = (i + k < P && p.v[k] >= 0) ? rank[base + p.v[k]] : 0;
-    st4(out + base, i, P, vec, o);
+        for (int k = 0; k < 4; ++k) o.v[k] = (i + k < P && p.v[k] >= 0) ? rank[base + p.v[k]] : 0;
+        st4(out + base, i, P, vec, o);
+    }
 }
 
 // area[root] += length of each in-segment run of pixels sharing the root (one atomic per run)
@@ -97,27 +135,29 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* 
 }
 
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
-    int* cnt = ws<int>(c, (size_t)g.N * g.H * g.SEG);
-    if (!cnt) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH(c, k_ccl_flatten, strip_grid(g), TISEG_THREADS, 0, g, par, cnt);
-    c->rootblk_par = par;             // rank_roots on this forest can skip its counting pass
-    c->rootblk = cnt;
+    unsigned* bits = ws<unsigned>(c, (size_t)g.N * g.H * g.SEG);
+    if (!bits) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH_TILES(c, k_ccl_flatten, g, strip_grid(g), TISEG_THREADS, 0, g, par, bits);
+    c->rootblk_par = par;             // rank_roots on this forest can skip its bitmap pass
+    c->rootblk = (int*)bits;
     return TISEG_OK;
 }
 
-int rank_scan(tiseg_ctx* c, const Geom& g, int* cnt, int* counts) {
-    TISEG_LAUNCH(c, k_rank_scan, g.N, 256, 0, g, cnt, counts);
+int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts) {
+    int* rowpre = ws<int>(c, (size_t)g.N * g.H);
+    if (!rowpre) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH_TILES(c, k_rank_rowscan, g, grid_tiles(g), 256, 0, g, bits, rowpre, counts);
+    TISEG_LAUNCH_TILES(c, k_rank_place_bits, g, dim3((g.H + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK, grid_tiles(g)), TISEG_THREADS, 0,
+                 g, bits, rowpre, rank);
     return TISEG_OK;
 }
 
 int rank_roots(tiseg_ctx* c, const Geom& g, const int* par, int* rank, int* counts) {
     if (c->rootblk_par == par && c->rootblk) {
-        // the flatten pass already counted the roots per row segment: scan + place only
-        int* cnt = c->rootblk;
+        // the flatten pass already left the bitmap of the roots
+        const unsigned* bits = (const unsigned*)c->rootblk;
         c->rootblk_par = nullptr;
-        TISEG_TRY(rank_scan(c, g, cnt, counts));
-        TISEG_LAUNCH(c, k_rank_place<SelRoot>, strip_grid(g), TISEG_THREADS, 0, g, SelRoot{par}, cnt, rank);
-        return TISEG_OK;
+        return rank_from_bits(c, g, bits, rank, counts);
     }
     return rank_generic(c, g, SelRoot{par}, rank, counts);
 }
@@ -125,7 +165,7 @@ int rank_roots(tiseg_ctx* c, const Geom& g, const int* par, int* rank, int* coun
 int apply_rank(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, int32_t* out) {
     const long long P = g.P;
     const bool vec = (P % 4 == 0) && aligned16(par, out);
-    TISEG_LAUNCH(c, k_apply_rank, dim3(flat4_grid(P), g.N), TISEG_THREADS, 0, P, par, rank, out, vec);
+    TISEG_LAUNCH_TILES(c, k_apply_rank, g, dim3(flat4_grid(P), grid_tiles(g)), TISEG_THREADS, 0, g, par, rank, out, vec);
     return TISEG_OK;
 }
 
@@ -202,6 +242,7 @@ int tiseg_re_instance(tiseg_ctx* c, const int32_t* img, int N, int H, int W, int
     // value axis: ids are bounded by a generous multiple of the pixel count (instance ids never exceed it
     // in the reference's datasets); larger ids are reported as an argument error rather than mis-ranked
     int vmax = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;
+    vmax = (vmax + 1023) / 1024 * 1024;          // the value axis is ranked as a [vmax / 1024, 1024] raster
     uint8_t* seen = ws<uint8_t>(c, (size_t)N * vmax);
     int* vr = ws<int>(c, (size_t)N * vmax);
     int* bad = ws<int>(c, 1);
@@ -209,8 +250,8 @@ int tiseg_re_instance(tiseg_ctx* c, const int32_t* img, int N, int H, int W, int
     TISEG_TRY(zero(c, seen, (size_t)N * vmax));
     TISEG_TRY(zero(c, bad, sizeof(int)));
     TISEG_LAUNCH(c, k_mark_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, seen, vmax, bad);
-    // rank over the value axis: reuse the raster-rank machinery on a [N, 1, vmax] "image"
-    Geom gv = make_geom(N, 1, vmax);
+    // rank over the value axis: reuse the raster-rank machinery on a [N, vmax / 1024, 1024] "image"
+    Geom gv = make_geom(N, vmax / 1024, 1024);
     TISEG_TRY(rank_generic(c, gv, SelFlagU8{seen}, vr, d_cnt));
     TISEG_LAUNCH(c, k_lookup_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, vr, vmax, d_out);
     int hbad = 0;

@@ -72,22 +72,22 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 //                 locally, then ONE coalesced global write per pixel: the tile-global index of its local root.
 //   k_ccl_border  only the pixels on tile borders (~8 %) merge across tiles with global atomicMin unions.
 //   k_ccl_flatten every pixel points at its global root (lowest flat index of the component = first pixel in
-//                 raster order); also counts the roots per row segment for the id ranking that usually follows.
+//                 raster order); also leaves the bitmap of the roots for the id ranking that usually follows.
 // =====================================================================================================
 #define CCL_TH 64                       // tile rows (8 warps x 8 rows); tile width is one warp = 32 columns
 #define CCL_BG INT_MIN                  // background marker inside the shared value tile
 
-template <class Img, int CONN>
+template <class Img, int CONN, bool LISTED>
 __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
     __shared__ int sval[CCL_TH * 32];
     __shared__ int slab[CCL_TH * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ty = blockIdx.x / g.SEG, tx = blockIdx.x - ty * g.SEG;
-    const int n = blockIdx.y;
     const int x = tx * 32 + lane;
     const bool okx = x < g.W;
-    const long long base = (long long)n * g.P;
     const int row0 = warp * 8, y0 = ty * CCL_TH + row0;
+    FOR_TILES(LISTED, g, n) {
+    const long long base = (long long)n * g.P;
     // phase A: coalesced loads (8 independent rows in flight per lane), row-run initialisation
     int v[8];
 #pragma unroll
@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, in
         }
         par[base + (long long)y * g.W + x] = out;
     }
+    if (LISTED) __syncthreads();        // the shared tile is reused by the next listed tile
+    }
 }
 
 // Cross-tile merges.  Candidates: A) pixels of a tile's top row (y = 64k, k >= 1) look up / up-left / up-right;
@@ -142,11 +144,9 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, in
 // right column (x = 32k - 1) look up-right.  A diagonal union is skipped when the vertical neighbour has the same
 // value (it is then connected through that neighbour's own row).
 template <class Img, int CONN>
-__global__ void __launch_bounds__(256) k_ccl_border(Geom g, Img img, int* par) {
-    const int n = blockIdx.y;
+__device__ __forceinline__ void ccl_border_one(const Geom& g, const Img& img, int* par, int n, int t) {
     const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
     const int nA = (tilesY - 1) * g.W, nB = (g.SEG - 1) * g.H, nC = CONN == 2 ? nB : 0;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nA + nB + nC) return;
     int y, x, kind;
     if (t < nA) { kind = 0; y = (t / g.W + 1) * CCL_TH; x = t - (t / g.W) * g.W; }
@@ -172,22 +172,34 @@ __global__ void __launch_bounds__(256) k_ccl_border(Geom g, Img img, int* par) {
         if (!sU && y > 0 && x + 1 < g.W && img(n, base + idx - g.W + 1, w) && w == v) uf_union(tp, idx, idx - g.W + 1);
     }
 }
+template <class Img, int CONN, bool LISTED>
+__global__ void __launch_bounds__(256) k_ccl_border(Geom g, Img img, int* par) {
+    FOR_TILES(LISTED, g, n) ccl_border_one<Img, CONN>(g, img, par, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
-// flatten + per-row-segment root counts; defined in ccl.cu
+// flatten + bitmap of the roots; defined in ccl.cu
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par);
 
 // build + flatten.  par: [N*P] int
 template <class Img>
 int ccl_build(tiseg_ctx* c, const Geom& g, Img img, int conn, int* par) {
     const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
-    dim3 lg((unsigned)(g.SEG * tilesY), (unsigned)g.N);
+    dim3 lg((unsigned)(g.SEG * tilesY), grid_tiles(g));
     const int nb = (tilesY - 1) * g.W + (g.SEG - 1) * g.H * (conn == 2 ? 2 : 1);
-    if (conn == 1) {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 1>), lg, TISEG_THREADS, 0, g, img, par);
-        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
+    if (g.tl) {
+        if (conn == 1) {
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 1, true>), lg, TISEG_THREADS, 0, g, img, par);
+            if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
+        } else {
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 2, true>), lg, TISEG_THREADS, 0, g, img, par);
+            if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
+        }
+    } else if (conn == 1) {
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 1, false>), lg, TISEG_THREADS, 0, g, img, par);
+        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     } else {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 2>), lg, TISEG_THREADS, 0, g, img, par);
-        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 2, false>), lg, TISEG_THREADS, 0, g, img, par);
+        if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     }
     return ccl_flatten(c, g, par);
 }
@@ -196,8 +208,10 @@ int ccl_build(tiseg_ctx* c, const Geom& g, Img img, int conn, int* par) {
 // ---- raster-order ranks ------------------------------------------------------------------------
 // Selection is a functor  __device__ bool operator()(long long gi, int idx) const  (e.g. "is a root").
 // rank[gi] = 1-based raster rank among the selected pixels of its tile (written only where selected);
-// counts[n] = number selected (may be null).  Three launches: per-block counts, per-tile scan of the
-// block counts, ballot/popc placement.
+// counts[n] = number selected (may be null).
+// The selection is first reduced to a BITMAP, one 32-bit ballot word per row segment (bits[n, y, seg]); ranking then
+// touches P/32 words instead of P pixels: k_rank_rowscan (one CTA per tile: popcount per row, exclusive scan over
+// the rows) and k_rank_place_bits (one warp per row: warp scan over the row's words, one store per selected pixel).
 struct SelRoot {                // roots of a flattened forest
     const int* par;
     __device__ __forceinline__ bool operator()(long long gi, int idx) const { return par[gi] == idx; }
@@ -208,9 +222,9 @@ struct SelFlagU8 {
 };
 
 #ifdef __CUDACC__
-// cnt[n, y, seg] = selected pixels in that 32-pixel row segment
+// bits[n, y, seg] = ballot of the selected pixels of that 32-pixel row segment
 template <class Sel>
-__global__ void __launch_bounds__(TISEG_THREADS) k_rank_count(Geom g, Sel sel, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(TISEG_THREADS) k_rank_bits(Geom g, Sel sel, unsigned* __restrict__ bits) {
     Strip s;
     if (!warp_strip(g, s)) return;
     bool f[STRIP_R];
@@ -223,42 +237,19 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_rank_count(Geom g, Sel sel, i
     for (int r = 0; r < STRIP_R; ++r) {
         unsigned m = __ballot_sync(0xffffffffu, f[r]);
         int y = s.y0 + r;
-        if (s.lane == 0 && y < g.H) cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] = __popc(m);
+        if (s.lane == 0 && y < g.H) bits[((long long)s.n * g.H + y) * g.SEG + s.seg] = m;
     }
 }
 
-// cnt holds, after rank_scan, the number of selected pixels before each row segment (raster order)
-template <class Sel>
-__global__ void __launch_bounds__(TISEG_THREADS) k_rank_place(Geom g, Sel sel, const int* __restrict__ cnt,
-                                                              int* __restrict__ rank) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    bool f[STRIP_R];
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        f[r] = s.okx && y < g.H && sel(s.base + (long long)y * g.W + s.x, y * g.W + s.x);
-    }
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        unsigned m = __ballot_sync(0xffffffffu, f[r]);
-        int y = s.y0 + r;
-        if (f[r]) rank[s.base + (long long)y * g.W + s.x] =
-            cnt[((long long)s.n * g.H + y) * g.SEG + s.seg] + __popc(m & ((1u << s.lane) - 1)) + 1;
-    }
-}
-
-// in-place exclusive raster-order scan of cnt[n, 0..H, 0..SEG) per tile; counts[n] = total (defined in ccl.cu)
-int rank_scan(tiseg_ctx* c, const Geom& g, int* cnt, int* counts);
+// bitmap -> ranks (defined in ccl.cu)
+int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts);
 
 template <class Sel>
 int rank_generic(tiseg_ctx* c, const Geom& g, Sel sel, int* rank, int* counts) {
-    int* cnt = ws<int>(c, (size_t)g.N * g.H * g.SEG);
-    if (!cnt) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH(c, k_rank_count<Sel>, strip_grid(g), TISEG_THREADS, 0, g, sel, cnt);
-    TISEG_TRY(rank_scan(c, g, cnt, counts));
-    TISEG_LAUNCH(c, k_rank_place<Sel>, strip_grid(g), TISEG_THREADS, 0, g, sel, cnt, rank);
-    return TISEG_OK;
+    unsigned* bits = ws<unsigned>(c, (size_t)g.N * g.H * g.SEG);
+    if (!bits) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_rank_bits<Sel>, strip_grid(g), TISEG_THREADS, 0, g, sel, bits);
+    return rank_from_bits(c, g, bits, rank, counts);
 }
 #endif
 

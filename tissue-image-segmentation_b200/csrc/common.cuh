@@ -92,12 +92,20 @@ struct Geom {
     int P;                     // H * W  (< 2^31: tile-local flat indices are int)
     int wpt;                   // warps per tile = H * SEG
     int bpt;                   // blocks per tile = ceil(wpt / 8)
+    // "listed" mode (kernels written with FOR_TILES): the launch has ONE tile slot (gridDim.y = 1) and every block
+    // loops over the device-side list tl[0 .. *tn) — normally empty, so a rarely needed general path costs a few
+    // microseconds of empty blocks instead of a host round trip to decide whether to launch it.
+    const int* tl;
+    const int* tn;
 };
 inline Geom make_geom(int N, int H, int W) {
     Geom g; g.N = N; g.H = H; g.W = W; g.SEG = (W + 31) / 32; g.P = H * W;
-    g.wpt = H * g.SEG; g.bpt = (g.wpt + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK; return g;
+    g.wpt = H * g.SEG; g.bpt = (g.wpt + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK;
+    g.tl = nullptr; g.tn = nullptr; return g;
 }
-inline dim3 warp_grid(const Geom& g) { return dim3((unsigned)g.bpt, (unsigned)g.N, 1); }
+inline Geom listed_geom(Geom g, const int* list, const int* count) { g.tl = list; g.tn = count; return g; }
+inline unsigned grid_tiles(const Geom& g) { return g.tl ? 1u : (unsigned)g.N; }
+inline dim3 warp_grid(const Geom& g) { return dim3((unsigned)g.bpt, grid_tiles(g), 1); }
 inline unsigned flat_grid(long long n, int per_block = TISEG_THREADS) { return (unsigned)((n + per_block - 1) / per_block); }
 inline unsigned flat4_grid(long long n) { return (unsigned)((n + 4 * TISEG_THREADS - 1) / (4 * TISEG_THREADS)); }
 inline bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr, const void* e = nullptr) {
@@ -144,9 +152,22 @@ struct Strip {
 };
 inline dim3 strip_grid(const Geom& g) {
     long long warps = (long long)g.SEG * ((g.H + STRIP_R - 1) / STRIP_R);
-    return dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)g.N, 1);
+    return dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), grid_tiles(g), 1);
 }
 #ifdef __CUDACC__
+// tile handled in iteration t of a FOR_TILES loop: the block's own tile (once), or entry t of the tile list.
+// LISTED is a compile-time flag of the kernel, so the ordinary instantiation keeps its single straight-line pass
+__device__ __forceinline__ int tile_listed(const Geom& g, int t) { return t < *g.tn ? g.tl[t] : -1; }
+#define FOR_TILES_OF(LISTED, g, own, n) \
+    for (int _t = 0, n = (LISTED) ? ::tiseg::tile_listed(g, 0) : (own); n >= 0; n = (LISTED) ? ::tiseg::tile_listed(g, ++_t) : -1)
+#define FOR_TILES(LISTED, g, n) FOR_TILES_OF(LISTED, g, (int)blockIdx.y, n)
+// launch kern<false> on every tile, or kern<true> on the tile list of g
+#define TISEG_LAUNCH_TILES(c, kern, g, grid, block, smem, ...)                                          \
+    do {                                                                                                \
+        if ((g).tl) TISEG_LAUNCH(c, kern<true>, grid, block, smem, __VA_ARGS__);                        \
+        else TISEG_LAUNCH(c, kern<false>, grid, block, smem, __VA_ARGS__);                              \
+    } while (0)
+__device__ __forceinline__ void strip_set_tile(const Geom& g, Strip& s, int n) { s.n = n; s.base = (long long)n * g.P; }
 __device__ __forceinline__ bool warp_strip(const Geom& g, Strip& s) {
     int w = blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     s.lane = threadIdx.x & 31;

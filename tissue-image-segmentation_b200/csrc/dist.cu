@@ -46,7 +46,7 @@ k_plateau_lower(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ p
         int v = c[j];
         int mn = min(min(min((int)l[j - 1], (int)c[j - 1]), min((int)r[j - 1], (int)l[j])),
                      min(min((int)r[j], (int)l[j + 1]), min((int)c[j + 1], (int)r[j + 1])));
-        if (mn < v) {
+        if (mn < v && v < 255) {          // the 255 plateau (background) is not built: its pixels have no parent
             int root = par[s.base + (long long)y * g.W + s.x];
             if (!low[s.base + root]) low[s.base + root] = 1;
         }
@@ -76,9 +76,10 @@ k_markers_from_plateaus(long long P, const uint8_t* __restrict__ I, const int* _
     st4(markers + base, i, P, vec, o);
 }
 
-// histogram of the flood labels (values 0..K), one atomic per in-segment run
+// histogram of the flood labels (values 0..K) and the first raster pixel of each label, one pair of atomics per
+// in-segment run
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int KS) {
+k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int* first, int KS) {
     Strip s;
     if (!warp_strip(g, s)) return;
     int v[STRIP_R];
@@ -93,18 +94,28 @@ k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int KS) {
         bool cont = s.lane > 0 && v[r] == vl;
         unsigned m = __ballot_sync(0xffffffffu, cont);
         // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
-        if (v[r] > 0 && !cont) atomicAdd(&hist[(long long)s.n * KS + v[r]], run_end_lane(m, s.lane) - s.lane + 1);
+        if (v[r] > 0 && !cont) {
+            const long long o = (long long)s.n * KS + v[r];
+            atomicAdd(&hist[o], run_end_lane(m, s.lane) - s.lane + 1);
+            atomicMin(&first[o], (s.y0 + r) * g.W + s.x);
+        }
     }
 }
 
-__global__ void k_zero_prefix_i32(int* a, int KS, const int* __restrict__ counts) {
+__global__ void k_init_label_tables(int* hist, int* first, int KS, const int* __restrict__ counts) {
     int n = blockIdx.y;
     int k = counts[n];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= k; i += gridDim.x * blockDim.x) a[(long long)n * KS + i] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= k; i += gridDim.x * blockDim.x) {
+        hist[(long long)n * KS + i] = 0;
+        first[(long long)n * KS + i] = INT_MAX;
+    }
 }
 
-// arrange_label's background: np.unique(return_counts) + argmax => the most frequent value, smallest value on ties
-__global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int P, int* bg) {
+// arrange_label's background: np.unique(return_counts) + argmax => the most frequent value, smallest value on ties.
+// Tiles whose background is NOT 0 (one flood region larger than everything unlabelled) go on the list of the
+// general relabelling path.
+__global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int P, int* bg,
+                          int* flagged, int* nflagged) {
     __shared__ unsigned long long s[256];
     __shared__ long long tot[256];
     int n = blockIdx.x;
@@ -131,15 +142,44 @@ __global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __res
     if (threadIdx.x == 0) {
         unsigned long long zero_key = ((unsigned long long)(unsigned)(P - tot[0]) << 32) | 0xffffffffu;   // value 0
         unsigned long long w = zero_key > s[0] ? zero_key : s[0];
-        bg[n] = (int)(0xffffffffu - (unsigned)(w & 0xffffffffu));
+        int b = (int)(0xffffffffu - (unsigned)(w & 0xffffffffu));
+        bg[n] = b;
+        if (b != 0) flagged[atomicAdd(nflagged, 1)] = n;
+    }
+}
+
+// Fast relabelling when the background is 0.  Every flood region is one 8-connected component (its marker plateau is
+// 8-connected and the flood grows it by 4-neighbours), so label(ws) only renumbers the regions by their first
+// raster pixel: set the bit of each region's first pixel, rank the bitmap, look the ids up.
+__global__ void k_first_bits(Geom g, const int* __restrict__ first, int KS, const int* __restrict__ counts, unsigned* bits) {
+    int n = blockIdx.y;
+    int k = counts[n];
+    for (int l = 1 + blockIdx.x * blockDim.x + threadIdx.x; l <= k; l += gridDim.x * blockDim.x) {
+        int idx = first[(long long)n * KS + l];
+        if (idx == INT_MAX) continue;
+        int y = idx / g.W, x = idx - y * g.W;
+        atomicOr(&bits[((long long)n * g.H + y) * g.SEG + (x >> 5)], 1u << (x & 31));
+    }
+}
+__global__ void k_arrange_lut(Geom g, const int* __restrict__ first, const int* __restrict__ rank, int KS,
+                              const int* __restrict__ counts, int* __restrict__ lut) {
+    int n = blockIdx.y;
+    int k = counts[n];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= k; l += gridDim.x * blockDim.x) {
+        int idx = l ? first[(long long)n * KS + l] : INT_MAX;
+        lut[(long long)n * KS + l] = idx == INT_MAX ? 0 : rank[(long long)n * g.P + idx];
     }
 }
 
 // generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
+// `lut` (may be null): the id of each label value, applied to the pixels that survive
+template <bool LISTED>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_wsl_remove(Geom g, const int32_t* __restrict__ lab, int32_t* __restrict__ out) {
+k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lut, int KS, int32_t* __restrict__ out) {
     Strip s;
     if (!warp_strip(g, s)) return;
+    FOR_TILES(LISTED, g, n) {
+    strip_set_tile(g, s, n);
     int c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
     strip_load3<int>(g, s, lab + s.base, 0, c, l, r);
 #pragma unroll
@@ -153,7 +193,9 @@ k_wsl_remove(Geom g, const int32_t* __restrict__ lab, int32_t* __restrict__ out)
 #pragma unroll
             for (int k = 0; k < 8; ++k) line |= (nb[k] != 0 && nb[k] != v);
         }
+        if (lut && v != 0 && !line) v = lut[(long long)s.n * KS + v];
         out[s.base + (long long)y * g.W + s.x] = line ? 0 : v;
+    }
     }
 }
 
@@ -172,12 +214,18 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     int32_t* arranged = ws<int32_t>(c, total);
     int* nmark = ws<int>(c, (size_t)N);
     int* bg = ws<int>(c, (size_t)N);
+    int* flagged = ws<int>(c, (size_t)N + 1);
     int* hist = ws<int>(c, (size_t)N * KS);
-    if (!I || !low || !par || !rank || !bpar || !brank || !markers || !wsl || !arranged || !nmark || !bg || !hist) return TISEG_ERR_CUDA;
+    int* first = ws<int>(c, (size_t)N * KS);
+    int* lut = ws<int>(c, (size_t)N * KS);
+    unsigned* fbits = ws<unsigned>(c, (size_t)N * g.H * g.SEG);
+    if (!I || !low || !par || !rank || !bpar || !brank || !markers || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
+        !first || !lut || !fbits) return TISEG_ERR_CUDA;
+    int* nflagged = flagged + N;
 
     TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I, aligned16(dist) && (((uintptr_t)I) & 3) == 0);
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255
-    TISEG_TRY(ccl_build(c, g, ImgEqU8{I, -1}, 2, par));
+    TISEG_TRY(ccl_build(c, g, ImgEqU8{I, 255}, 2, par));
     TISEG_TRY(zero(c, low, total));
     TISEG_LAUNCH(c, k_plateau_lower, strip_grid(g), TISEG_THREADS, 0, g, I, par, low);
     TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, I, low}, rank, nmark));
@@ -189,14 +237,23 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     TISEG_TRY(ws_seed(c, g, markers, bpar, wsl));
     TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
     // arrange_label
-    TISEG_LAUNCH(c, k_zero_prefix_i32, dim3(8, N), 256, 0, hist, KS, nmark);
-    TISEG_LAUNCH(c, k_ws_hist, strip_grid(g), TISEG_THREADS, 0, g, wsl, hist, KS);
-    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg);
-    TISEG_TRY(ccl_build(c, g, ImgEqI32TileBg{wsl, bg}, 2, par));
-    TISEG_TRY(rank_roots(c, g, par, rank, nullptr));
-    TISEG_TRY(apply_rank(c, g, par, rank, arranged));
-    // watershed lines
-    TISEG_LAUNCH(c, k_wsl_remove, strip_grid(g), TISEG_THREADS, 0, g, arranged, inst);
+    TISEG_TRY(zero(c, nflagged, sizeof(int)));
+    TISEG_TRY(zero(c, fbits, (size_t)N * g.H * g.SEG * sizeof(unsigned)));
+    TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);
+    TISEG_LAUNCH(c, k_ws_hist, strip_grid(g), TISEG_THREADS, 0, g, wsl, hist, first, KS);
+    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged);
+    //   background 0 (every tile but degenerate ones): ids = rank of each region's first pixel; watershed lines
+    //   are found on the flood labels themselves (the renumbering is a bijection)
+    TISEG_LAUNCH(c, k_first_bits, dim3(8, N), 256, 0, g, first, KS, nmark, fbits);
+    TISEG_TRY(rank_from_bits(c, g, fbits, rank, nullptr));
+    TISEG_LAUNCH(c, k_arrange_lut, dim3(8, N), 256, 0, g, first, rank, KS, nmark, lut);
+    TISEG_LAUNCH(c, k_wsl_remove<false>, strip_grid(g), TISEG_THREADS, 0, g, wsl, lut, KS, inst);
+    //   any other background: the general relabelling, on the listed tiles only (no blocks do anything otherwise)
+    Geom gl = listed_geom(g, flagged, nflagged);
+    TISEG_TRY(ccl_build(c, gl, ImgEqI32TileBg{wsl, bg}, 2, par));
+    TISEG_TRY(rank_roots(c, gl, par, rank, nullptr));
+    TISEG_TRY(apply_rank(c, gl, par, rank, arranged));
+    TISEG_LAUNCH(c, k_wsl_remove<true>, strip_grid(gl), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst);
     return TISEG_OK;
 }
 
