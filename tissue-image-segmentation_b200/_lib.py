@@ -122,9 +122,14 @@ class Context:
         check(getattr(self.lib, name)(self.handle, *args), name)
 
 
+_slot = threading.local()
+
+
 def get_ctx(device=None):
     """Context for ``device`` (default: torch's current CUDA device), bound to torch's current
-    stream so that zero-copy calls on CUDA tensors are ordered with the producer kernels."""
+    stream so that zero-copy calls on CUDA tensors are ordered with the producer kernels.
+    Inside ``with lane(k):`` the context of lane k is returned instead: every lane owns its own
+    workspace arena, so calls issued on different streams never share scratch memory."""
     import torch
     if not torch.cuda.is_available():
         # still go through tiseg_create so the error is the library's own
@@ -132,13 +137,41 @@ def get_ctx(device=None):
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     device = int(device)
-    ctx = _ctxs.get(device)
+    key = (device, getattr(_slot, "k", 0))
+    ctx = _ctxs.get(key)
     if ctx is None:
         ctx = Context(device)
-        _ctxs[device] = ctx
+        _ctxs[key] = ctx
     if torch.cuda.is_available():
-        ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        s = torch.cuda.current_stream(device).cuda_stream
+        if getattr(ctx, "_bound", None) != s:
+            ctx.set_stream(s)
+            ctx._bound = s
     return ctx
+
+
+class lane:
+    """``with lane(k, stream):`` — operator calls inside use the k-th context of the device (own arena) and,
+    if given, run on ``stream`` (a ``torch.cuda.Stream``).  Lanes are how a caller overlaps the host-to-device
+    staging of one chunk of tiles with the kernels of the previous one (see ``parallel.HostFeed``)."""
+
+    def __init__(self, k, stream=None):
+        self.k, self.stream, self._sc = int(k), stream, None
+
+    def __enter__(self):
+        import torch
+        self.prev = getattr(_slot, "k", 0)
+        _slot.k = self.k
+        if self.stream is not None:
+            self._sc = torch.cuda.stream(self.stream)
+            self._sc.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._sc is not None:
+            self._sc.__exit__(*exc)
+        _slot.k = self.prev
+        return False
 
 
 # --------------------------------------------------------------------------- array plumbing

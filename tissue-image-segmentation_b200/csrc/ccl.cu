@@ -245,21 +245,15 @@ int tiseg_re_instance(tiseg_ctx* c, const int32_t* img, int N, int H, int W, int
     vmax = (vmax + 1023) / 1024 * 1024;          // the value axis is ranked as a [vmax / 1024, 1024] raster
     uint8_t* seen = ws<uint8_t>(c, (size_t)N * vmax);
     int* vr = ws<int>(c, (size_t)N * vmax);
-    int* bad = ws<int>(c, 1);
-    if (!seen || !vr || !bad) return TISEG_ERR_CUDA;
+    int* bad = c->d_err;                 // deferred: reported by this call if it synchronises, else by the next that does
+    if (!seen || !vr) return TISEG_ERR_CUDA;
     TISEG_TRY(zero(c, seen, (size_t)N * vmax));
-    TISEG_TRY(zero(c, bad, sizeof(int)));
     TISEG_LAUNCH(c, k_mark_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, seen, vmax, bad);
     // rank over the value axis: reuse the raster-rank machinery on a [N, vmax / 1024, 1024] "image"
     Geom gv = make_geom(N, vmax / 1024, 1024);
     TISEG_TRY(rank_generic(c, gv, SelFlagU8{seen}, vr, d_cnt));
     TISEG_LAUNCH(c, k_lookup_values, warp_grid(g), TISEG_THREADS, 0, g, d_img, vr, vmax, d_out);
-    int hbad = 0;
-    TISEG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    TISEG_TRY(end_call(c));
-    TISEG_CHECK(cudaStreamSynchronize(c->stream));
-    if (hbad) { set_error("tiseg_re_instance: instance id out of the supported range"); return TISEG_ERR_LIMIT; }
-    return TISEG_OK;
+    return end_call(c);
 }
 
 }  // extern "C"

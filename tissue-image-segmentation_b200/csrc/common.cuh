@@ -28,6 +28,11 @@ struct tiseg_ctx {
     std::vector<Pending> pending;
     long long launches = 0;
     int sm_count = 148;
+    // data-dependent errors raised by kernels (word 0: instance id out of range, word 1: internal table loss).  A
+    // call that synchronises anyway (host outputs) reports them itself; stream-ordered calls with device outputs
+    // return before execution and leave them to the next call that synchronises (tiseg_synchronize included).
+    int* d_err = nullptr;      // [2] device
+    int* h_err = nullptr;      // [2] pinned host mirror
     // root counts per block left behind by the last ccl_flatten (consumed by rank_roots on the same forest)
     const int* rootblk_par = nullptr;
     int* rootblk = nullptr;
@@ -46,6 +51,7 @@ int fail(const char* where, cudaError_t e);
 // ---- call-scoped workspace -------------------------------------------------------------------
 void begin_call(tiseg_ctx* c);
 int end_call(tiseg_ctx* c);                       // flush pending D2H, sync if any host output
+int check_deferred(tiseg_ctx* c);                 // after a stream sync: report + clear kernel-raised errors
 void* ws_alloc(tiseg_ctx* c, size_t bytes);       // 256-byte aligned device scratch, valid until end_call
 bool is_device_ptr(const void* p);
 // input: device pointer returned as is; host pointer staged to the arena with an async H2D

@@ -105,12 +105,23 @@ void* inout_ptr(tiseg_ctx* c, void* p, size_t bytes) {
 }
 
 int end_call(tiseg_ctx* c) {
-    if (c->pending.empty()) return TISEG_OK;
+    if (c->pending.empty()) return TISEG_OK;          // device outputs: stream-ordered, nothing to wait for
     for (auto& q : c->pending)
         TISEG_CHECK(cudaMemcpyAsync(q.host, q.dev, q.bytes, cudaMemcpyDeviceToHost, c->stream));
     c->pending.clear();
+    TISEG_CHECK(cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TISEG_CHECK(cudaStreamSynchronize(c->stream));
-    return TISEG_OK;
+    return check_deferred(c);
+}
+
+int check_deferred(tiseg_ctx* c) {
+    if (!c->h_err[0] && !c->h_err[1]) return TISEG_OK;
+    const bool range = c->h_err[0] != 0;
+    c->h_err[0] = c->h_err[1] = 0;
+    cudaMemsetAsync(c->d_err, 0, 2 * sizeof(int), c->stream);
+    set_error(range ? "instance id out of the supported range (need 0 <= id < max(H*W+1, 65536))"
+                    : "internal pair table lost an entry");
+    return TISEG_ERR_LIMIT;
 }
 
 int zero(tiseg_ctx* c, void* p, size_t bytes) {
@@ -155,6 +166,13 @@ int tiseg_create(tiseg_ctx** out, int device) {
     if (e != cudaSuccess) { delete c; return tiseg::fail("cudaStreamCreate", e); }
     c->own_stream = true;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMalloc(&c->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, 2 * sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc(&c->h_err, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        cudaError_t e2 = cudaGetLastError();
+        tiseg_destroy(c);
+        return tiseg::fail("tiseg_create", e2);
+    }
+    c->h_err[0] = c->h_err[1] = 0;
     *out = c;
     return TISEG_OK;
 }
@@ -164,6 +182,8 @@ int tiseg_destroy(tiseg_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->blocks) cudaFree(b.p);
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return TISEG_OK;
@@ -183,8 +203,9 @@ int tiseg_set_stream(tiseg_ctx* c, void* s) {
 
 int tiseg_synchronize(tiseg_ctx* c) {
     if (!c) { tiseg::set_error("null ctx"); return TISEG_ERR_ARG; }
+    TISEG_CHECK(cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TISEG_CHECK(cudaStreamSynchronize(c->stream));
-    return TISEG_OK;
+    return tiseg::check_deferred(c);
 }
 
 int tiseg_timing_enable(tiseg_ctx* c, int on) {

@@ -13,10 +13,18 @@
 
 namespace tiseg {
 
-struct PairTab {
+// Two tables: a small one (instances are compact: O(K) pairs) that every batch tries first, and an
+// always-sufficient one (2P slots per tile: a pair needs a pixel) that is zeroed and filled ON THE DEVICE only if the
+// small one overflowed — no host round trip decides.  `view()` gives the table in force.
+struct PairTabView {
     unsigned long long* key;   // [N, cap]  (g << 32 | p), 0 = empty
     int* cnt;                  // [N, cap]
     int cap;                   // power of two
+};
+struct PairTab {
+    PairTabView small, big;
+    int* overflow;             // [1] set by the first accumulation pass
+    __device__ __forceinline__ PairTabView view() const { return *overflow ? big : small; }
 };
 
 __device__ __forceinline__ unsigned pair_hash(unsigned g, unsigned p) {
@@ -25,7 +33,7 @@ __device__ __forceinline__ unsigned pair_hash(unsigned g, unsigned p) {
     return h;
 }
 
-__device__ __forceinline__ void pair_add(const PairTab& t, int n, unsigned g, unsigned p, int len, int* overflow) {
+__device__ __forceinline__ void pair_add(const PairTabView& t, int n, unsigned g, unsigned p, int len, int* overflow) {
     unsigned long long k = ((unsigned long long)g << 32) | p;
     unsigned long long* keys = t.key + (long long)n * t.cap;
     unsigned s = pair_hash(g, p) & (t.cap - 1);
@@ -41,7 +49,7 @@ __device__ __forceinline__ void pair_add(const PairTab& t, int n, unsigned g, un
     *overflow = 1;
 }
 
-__device__ __forceinline__ int pair_lookup(const PairTab& t, int n, unsigned g, unsigned p) {
+__device__ __forceinline__ int pair_lookup(const PairTabView& t, int n, unsigned g, unsigned p) {
     unsigned long long k = ((unsigned long long)g << 32) | p;
     const unsigned long long* keys = t.key + (long long)n * t.cap;
     unsigned s = pair_hash(g, p) & (t.cap - 1);
@@ -84,12 +92,13 @@ __global__ void k_inst_init(InstState s, int areas) {
     }
 }
 
-// one pass over the two relabelled maps: areas by id + pair table
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_pair_accumulate(Geom g, const int* __restrict__ par_g, const int* __restrict__ rank_g,
-                  const int* __restrict__ par_p, const int* __restrict__ rank_p, InstState s, PairTab t, int* overflow) {
-    Strip st;
-    if (!warp_strip(g, st)) return;
+// one pass over the two relabelled maps: areas by id + pair table.  AREAS = false, BIG = true is the redo into the
+// always-sufficient table: a persistent grid that does nothing unless the first pass overflowed.
+template <bool BIG>
+__device__ __forceinline__ void pair_accumulate_strip(const Geom& g, const Strip& st, const int* __restrict__ par_g,
+                                                      const int* __restrict__ rank_g, const int* __restrict__ par_p,
+                                                      const int* __restrict__ rank_p, const InstState& s,
+                                                      const PairTabView& t, int* overflow) {
     int a[STRIP_R], b[STRIP_R];
 #pragma unroll
     for (int r = 0; r < STRIP_R; ++r) {
@@ -113,48 +122,85 @@ k_pair_accumulate(Geom g, const int* __restrict__ par_g, const int* __restrict__
         unsigned mg = __ballot_sync(0xffffffffu, cg);
         unsigned mp = __ballot_sync(0xffffffffu, cp);
         unsigned mb = mg & mp;                              // both continue => the pair continues
-        if (gid[r] && !cg) atomicAdd(&s.area_g[o + gid[r]], run_end_lane(mg, st.lane) - st.lane + 1);
-        if (pid[r] && !cp) atomicAdd(&s.area_p[o + pid[r]], run_end_lane(mp, st.lane) - st.lane + 1);
+        if (!BIG) {
+            if (gid[r] && !cg) atomicAdd(&s.area_g[o + gid[r]], run_end_lane(mg, st.lane) - st.lane + 1);
+            if (pid[r] && !cp) atomicAdd(&s.area_p[o + pid[r]], run_end_lane(mp, st.lane) - st.lane + 1);
+        }
         if (gid[r] && pid[r] && !(cg && cp))
             pair_add(t, st.n, gid[r], pid[r], run_end_lane(mb, st.lane) - st.lane + 1, overflow);
     }
 }
 
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_pair_accumulate(Geom g, const int* __restrict__ par_g, const int* __restrict__ rank_g,
+                  const int* __restrict__ par_p, const int* __restrict__ rank_p, InstState s, PairTab t) {
+    Strip st;
+    if (!warp_strip(g, st)) return;
+    pair_accumulate_strip<false>(g, st, par_g, rank_g, par_p, rank_p, s, t.small, t.overflow);
+}
+
+// the redo (persistent grid; exits at once unless the small table overflowed)
+__global__ void __launch_bounds__(TISEG_THREADS) k_pair_zero_big(PairTab t, int N) {
+    if (!*t.overflow) return;
+    const long long total = (long long)N * t.big.cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        t.big.key[i] = 0ull; t.big.cnt[i] = 0;
+    }
+}
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_pair_accumulate_big(Geom g, const int* __restrict__ par_g, const int* __restrict__ rank_g,
+                      const int* __restrict__ par_p, const int* __restrict__ rank_p, InstState s, PairTab t, int* lost) {
+    if (!*t.overflow) return;
+    const int chunks = (g.H + STRIP_R - 1) / STRIP_R;
+    const long long wpt = (long long)g.SEG * chunks, total = wpt * g.N;
+    const int lane = threadIdx.x & 31;
+    for (long long w = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5); w < total;
+         w += (long long)gridDim.x * TISEG_WARPS_PER_BLOCK) {
+        Strip st;
+        const int n = (int)(w / wpt), wl = (int)(w - (long long)n * wpt), ch = wl / g.SEG;
+        st.lane = lane; st.seg = wl - ch * g.SEG; st.y0 = ch * STRIP_R; st.n = n;
+        st.x = st.seg * 32 + lane; st.okx = st.x < g.W; st.base = (long long)n * g.P;
+        pair_accumulate_strip<true>(g, st, par_g, rank_g, par_p, rank_p, s, t.big, lost);
+    }
+}
+
 // pass A over the table: best AJI IoU per gt (atomicMax on fp64 bits: positive doubles order like integers),
 // and the PQ matches (IoU > 0.5 is unique per gt and per pred)
-__global__ void k_pair_best(PairTab t, InstState s, int* tp) {
+__global__ void k_pair_best(PairTab tt, InstState s, int* tp) {
+    const PairTabView t = tt.view();
     int n = blockIdx.y;
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= t.cap) return;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < t.cap; slot += gridDim.x * blockDim.x) {
     unsigned long long k = t.key[(long long)n * t.cap + slot];
-    if (!k) return;
+    if (!k) continue;
     unsigned gid = (unsigned)(k >> 32), pid = (unsigned)k;
     long long o = (long long)n * s.KS;
     int cg = s.class_g(o, gid);
-    if (cg == 0 || cg != s.class_p(o, pid)) return;         // only pairs inside one class meet (inst_metrics.py:112-122)
+    if (cg == 0 || cg != s.class_p(o, pid)) continue;       // only pairs inside one class meet (inst_metrics.py:112-122)
     double inter = (double)t.cnt[(long long)n * t.cap + slot];
     double tot = (double)s.area_g[o + gid] + (double)s.area_p[o + pid];
     double iou_aji = inter / ((tot - inter) + 1.0e-6);      // inst_metrics.py:69
     atomicMax(&s.best[o + gid], (unsigned long long)__double_as_longlong(iou_aji));
     double iou_pq = inter / (tot - inter);                  // inst_metrics.py:194
     if (iou_pq > 0.5) { s.pqiou[o + gid] = iou_pq; atomicAdd(&tp[n * s.C + cg], 1); }
+    }
 }
 
 // pass B: np.argmax tie rule — the lowest pred id among those reaching the best IoU (inst_metrics.py:74)
-__global__ void k_pair_argbest(PairTab t, InstState s) {
+__global__ void k_pair_argbest(PairTab tt, InstState s) {
+    const PairTabView t = tt.view();
     int n = blockIdx.y;
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= t.cap) return;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < t.cap; slot += gridDim.x * blockDim.x) {
     unsigned long long k = t.key[(long long)n * t.cap + slot];
-    if (!k) return;
+    if (!k) continue;
     unsigned gid = (unsigned)(k >> 32), pid = (unsigned)k;
     long long o = (long long)n * s.KS;
     int cg = s.class_g(o, gid);
-    if (cg == 0 || cg != s.class_p(o, pid)) return;
+    if (cg == 0 || cg != s.class_p(o, pid)) continue;
     double inter = (double)t.cnt[(long long)n * t.cap + slot];
     double tot = (double)s.area_g[o + gid] + (double)s.area_p[o + pid];
     double iou_aji = inter / ((tot - inter) + 1.0e-6);
     if ((unsigned long long)__double_as_longlong(iou_aji) == s.best[o + gid]) atomicMin(&s.bestp[o + gid], (int)pid);
+    }
 }
 
 // add (I, U) of one instance to its class slot; warps whose lanes all share one class (always, in the binary
@@ -180,7 +226,8 @@ __device__ __forceinline__ void add_iu(unsigned long long* IU, int n, int C, int
 
 // pass C: per gt — paired inter / union, or its own area when nothing overlaps (inst_metrics.py:76-87);
 // class-0 instances only contribute their area to union[0] (inst_metrics.py:105-110)
-__global__ void k_aji_gt(PairTab t, InstState s, unsigned long long* IU) {
+__global__ void k_aji_gt(PairTab tt, InstState s, unsigned long long* IU) {
+    const PairTabView t = tt.view();
     int n = blockIdx.y;
     long long o = (long long)n * s.KS;
     int ng = s.ng[n];
@@ -438,27 +485,24 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
     TISEG_TRY(rank_roots(c, g, par_g, rank_g, ng));
     TISEG_TRY(ccl_build(c, g, ImgEqI32{d_pred, 0}, 2, par_p));
     TISEG_TRY(rank_roots(c, g, par_p, rank_p, np));
-    // the table starts small (instances are compact: O(K) pairs) and is retried at the always-sufficient
-    // size 2P if a pathological input overflows it
-    int cap = next_pow2(g.P / 16 < 1024 ? 1024 : g.P / 16);
-    for (int attempt = 0;; ++attempt) {
-        PairTab& t = w.t;
-        t.cap = cap;
-        t.key = ws<unsigned long long>(c, (size_t)N * cap);
-        t.cnt = ws<int>(c, (size_t)N * cap);
-        if (!t.key || !t.cnt) return TISEG_ERR_CUDA;
-        TISEG_TRY(zero(c, t.key, (size_t)N * cap * sizeof(unsigned long long)));
-        TISEG_TRY(zero(c, t.cnt, (size_t)N * cap * sizeof(int)));
-        TISEG_TRY(zero(c, overflow, sizeof(int)));
-        TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 1);
-        TISEG_LAUNCH(c, k_pair_accumulate, strip_grid(g), TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t, overflow);
-        int hov = 0;
-        TISEG_CHECK(cudaMemcpyAsync(&hov, overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        TISEG_CHECK(cudaStreamSynchronize(c->stream));
-        if (!hov) break;
-        if (attempt == 1) { set_error("pair table overflow"); return TISEG_ERR_LIMIT; }
-        cap = next_pow2(2ll * g.P);
-    }
+    // the small table first; the always-sufficient one is zeroed and filled by a persistent grid that exits at once
+    // unless the first pass raised the overflow flag (a pathological input)
+    PairTab& t = w.t;
+    t.small.cap = next_pow2(g.P / 16 < 1024 ? 1024 : g.P / 16);
+    t.big.cap = next_pow2(2ll * g.P);
+    t.small.key = ws<unsigned long long>(c, (size_t)N * t.small.cap);
+    t.small.cnt = ws<int>(c, (size_t)N * t.small.cap);
+    t.big.key = ws<unsigned long long>(c, (size_t)N * t.big.cap);
+    t.big.cnt = ws<int>(c, (size_t)N * t.big.cap);
+    t.overflow = overflow;
+    if (!t.small.key || !t.small.cnt || !t.big.key || !t.big.cnt) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, t.small.key, (size_t)N * t.small.cap * sizeof(unsigned long long)));
+    TISEG_TRY(zero(c, t.small.cnt, (size_t)N * t.small.cap * sizeof(int)));
+    TISEG_TRY(zero(c, overflow, sizeof(int)));
+    TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 1);
+    TISEG_LAUNCH(c, k_pair_accumulate, strip_grid(g), TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t);
+    TISEG_LAUNCH(c, k_pair_zero_big, c->sm_count * 8, TISEG_THREADS, 0, t, N);
+    TISEG_LAUNCH(c, k_pair_accumulate_big, c->sm_count * 8, TISEG_THREADS, 0, g, par_g, rank_g, par_p, rank_p, s, t, c->d_err + 1);
     if (par_g_out) { *par_g_out = par_g; *rank_g_out = rank_g; *par_p_out = par_p; *rank_p_out = rank_p; }
     return TISEG_OK;
 }
@@ -475,7 +519,7 @@ static int pair_eval(tiseg_ctx* c, const Geom& g, PairWork& w, const uint8_t* cl
     TISEG_TRY(zero(c, IU, 2 * (size_t)N * C * sizeof(unsigned long long)));
     TISEG_TRY(zero(c, tp, (size_t)N * C * sizeof(int)));
     if (!first_eval) TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 0);
-    dim3 tg((w.t.cap + 255) / 256, N);
+    dim3 tg((w.t.small.cap + 255) / 256, N);                 // the kernels stride over the table in force
     TISEG_LAUNCH(c, k_pair_best, tg, 256, 0, w.t, s, tp);
     TISEG_LAUNCH(c, k_pair_argbest, tg, 256, 0, w.t, s);
     TISEG_LAUNCH(c, k_aji_gt, dim3(8, N), 256, 0, w.t, s, IU);
@@ -560,9 +604,7 @@ int tiseg_pair_metrics_multiclass(tiseg_ctx* c, const int32_t* pred_inst, const 
     if (d_baji || d_bpq) { TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, none, first, d_baji, d_bpq)); first = false; }
     if (d_aji || d_pq) {
         int VM = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;     // instance ids index the class tables directly
-        int* bad = ws<int>(c, 1);
-        if (!bad) return TISEG_ERR_CUDA;
-        TISEG_TRY(zero(c, bad, sizeof(int)));
+        int* bad = c->d_err;                                    // deferred: reported by the next synchronising call
         uint8_t *cls_g, *cls_p;
         ClassInfo ci;
         int *a, *b;
@@ -571,10 +613,6 @@ int tiseg_pair_metrics_multiclass(tiseg_ctx* c, const int32_t* pred_inst, const 
         TISEG_TRY(side_classes(c, g, d_pi, d_ps, par_p, rank_p, C, VM, &cls_p, &a, &b, bad));
         ci.ncomp_p = a; ci.ninst_p = b;
         TISEG_TRY(pair_eval(c, g, w, cls_g, cls_p, C, ci, first, d_aji, d_pq));
-        int hbad = 0;
-        TISEG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        TISEG_CHECK(cudaStreamSynchronize(c->stream));
-        if (hbad) { set_error("tiseg_pair_metrics_multiclass: instance id out of range (need id < max(H*W+1, 65536))"); return TISEG_ERR_LIMIT; }
     }
     return end_call(c);
 }

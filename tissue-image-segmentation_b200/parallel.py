@@ -8,9 +8,47 @@ broadcast, one pickle file per rank on a shared filesystem, a barrier, and an un
                         image-wise metrics) sees exactly the list a single process would have produced, in index
                         order.  ~100 bytes per image.
 
+* ``HostFeed``        — the caller loop of ``tiseg/apis/test.py:29-38`` for host-resident inputs: the batch is cut into
+                        chunks that alternate between lanes (own stream + own workspace), so the PCIe transfer of
+                        one chunk overlaps the kernels of the previous one.
+
 Works with the ``nccl`` backend (records live on the rank's GPU, NVLink / NVSwitch) and with ``gloo`` (CPU tests).
 """
 import numpy as np
+
+
+class HostFeed:
+    """Chunked, double-buffered execution of ``fn(chunk_dict, lane_index) -> None`` over a dict of host arrays
+    (numpy, ideally pinned) whose first axis is the tile axis.
+
+        feed = HostFeed(device, lanes=2, chunk=4)
+        feed.run(arrays, fn)      # enqueues everything, returns after all lanes have been joined to the
+                                  # caller's current stream (no host synchronisation)
+
+    ``fn`` is called inside ``_lib.lane(k, stream_k)`` and ``_lib.device_outputs()``: the operators stage the chunk
+    with asynchronous copies on stream k and keep their results on the device.  Per-lane accumulators are the
+    caller's business (index them with ``lane_index``)."""
+
+    def __init__(self, device=None, lanes=2, chunk=4):
+        import torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(int(lanes))]
+        self.chunk = int(chunk)
+
+    def run(self, arrays, fn):
+        import torch
+        from . import _lib
+        n = len(next(iter(arrays.values())))
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for k, lo in enumerate(range(0, n, self.chunk)):
+            ln = k % len(self.streams)
+            part = {key: a[lo:lo + self.chunk] for key, a in arrays.items()}
+            with _lib.lane(1 + ln, self.streams[ln]), _lib.device_outputs():
+                fn(part, ln)
+        for s in self.streams:
+            cur.wait_stream(s)
 
 
 def shard_indices(n_items, rank, world_size):
