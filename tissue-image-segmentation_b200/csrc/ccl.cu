@@ -37,37 +37,62 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par,
     }
 }
 
-// one block per tile, thread = row: selected pixels per row (popcount of the row's words), block scan with carry.
+// one block (32 warps) per tile.  Phase 1: a warp per row sums the popcounts of the row's words (one coalesced
+// request per 32 segments).  Phase 2: exclusive block scan over the rows.
 // rowpre[n, y] = selected pixels in the rows above y; counts[n] = total.
 template <bool LISTED>
-__global__ void k_rank_rowscan(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rowpre, int* counts) {
-    __shared__ int s[256];
+__global__ void __launch_bounds__(1024) k_rank_rowscan(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rowpre, int* counts) {
+    __shared__ int wsum[32];
     __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FOR_TILES_OF(LISTED, g, (int)blockIdx.x, n) {
     const unsigned* b = bits + (long long)n * g.H * g.SEG;
-    __syncthreads();
+    int* rp = rowpre + (long long)n * g.H;
+    for (int y0 = warp * 8; y0 < g.H; y0 += 32 * 8) {       // eight rows per warp step: eight requests in flight
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = 0;
+            if (y0 + j < g.H) for (int k = lane; k < g.SEG; k += 32) v[j] += __popc(b[(long long)(y0 + j) * g.SEG + k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], d);
+            if (lane == 0 && y0 + j < g.H) rp[y0 + j] = v[j];
+        }
+    }
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < g.H; base += 256) {
-        int y = base + threadIdx.x;
-        int v = 0;
-        if (y < g.H) for (int k = 0; k < g.SEG; ++k) v += __popc(b[(long long)y * g.SEG + k]);
-        s[threadIdx.x] = v;
-        __syncthreads();
-        for (int d = 1; d < 256; d <<= 1) {
-            int t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
-            __syncthreads();
-            s[threadIdx.x] += t;
-            __syncthreads();
+    for (int base = 0; base < g.H; base += 1024) {
+        const int y = base + threadIdx.x;
+        const int v = y < g.H ? rp[y] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-        int incl = s[threadIdx.x];
-        int c0 = carry;
-        if (y < g.H) rowpre[(long long)n * g.H + y] = c0 + incl - v;
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        if (threadIdx.x == 255) carry = c0 + incl;
+        if (warp == 0) {
+            int w = wsum[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += t;
+            }
+            wsum[lane] = wi - w;                       // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int c0 = carry;
+        if (y < g.H) rp[y] = c0 + wsum[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c0 + wsum[31] + incl;
         __syncthreads();
     }
     if (threadIdx.x == 0 && counts) counts[n] = carry;
+    __syncthreads();
     }
 }
 
@@ -146,7 +171,7 @@ int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
 int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts) {
     int* rowpre = ws<int>(c, (size_t)g.N * g.H);
     if (!rowpre) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH_TILES(c, k_rank_rowscan, g, grid_tiles(g), 256, 0, g, bits, rowpre, counts);
+    TISEG_LAUNCH_TILES(c, k_rank_rowscan, g, grid_tiles(g), 1024, 0, g, bits, rowpre, counts);
     TISEG_LAUNCH_TILES(c, k_rank_place_bits, g, dim3((g.H + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK, grid_tiles(g)), TISEG_THREADS, 0,
                  g, bits, rowpre, rank);
     return TISEG_OK;

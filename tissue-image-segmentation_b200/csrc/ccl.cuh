@@ -24,6 +24,10 @@ struct ImgEqU8 {                // equal-value components of a uint8 image, bg <
     const uint8_t* p; int bg;
     __device__ __forceinline__ bool operator()(int n, long long gi, int& v) const { v = p[gi]; return v != bg; }
 };
+struct ImgEqU8Where {           // equal-value components of a uint8 image restricted to the pixels flagged in `on`
+    const uint8_t* p; const uint8_t* on;
+    __device__ __forceinline__ bool operator()(int n, long long gi, int& v) const { v = p[gi]; return on[gi] != 0; }
+};
 struct ImgMaskU8 {              // binary: non-zero is foreground
     const uint8_t* p;
     __device__ __forceinline__ bool operator()(int n, long long gi, int& v) const { v = 1; return p[gi] != 0; }
@@ -78,7 +82,7 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 #define CCL_BG INT_MIN                  // background marker inside the shared value tile
 
 template <class Img, int CONN, bool LISTED>
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
+__global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
     __shared__ int sval[CCL_TH * 32];
     __shared__ int slab[CCL_TH * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -96,20 +100,24 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_local(Geom g, Img img, in
         v[r] = CCL_BG;
         if (okx && y < g.H && img(n, base + (long long)y * g.W + x, vv)) v[r] = vv;
     }
+    unsigned fg = 0;                    // bit r: row r of this warp has a foreground pixel (uniform over the warp)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
         bool cont = lane > 0 && v[r] != CCL_BG && vl == v[r];
         unsigned m = __ballot_sync(0xffffffffu, cont);
+        if (__ballot_sync(0xffffffffu, v[r] != CCL_BG)) fg |= 1u << r;
         int li = (row0 + r) * 32 + lane;
         sval[li] = v[r];
         slab[li] = v[r] != CCL_BG ? (row0 + r) * 32 + run_start_lane(m, lane) : -1;
     }
     __syncthreads();
-    // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border)
+    // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border); rows without a
+    // foreground pixel are skipped by the whole warp
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         int row = row0 + r, li = row * 32 + lane;
+        if (!((fg >> r) & 1u)) continue;
         if (row == 0 || v[r] == CCL_BG) continue;
         int u = sval[li - 32];
         int ul = lane > 0 ? sval[li - 33] : CCL_BG;

@@ -188,15 +188,24 @@ __device__ __forceinline__ bool warp_strip(const Geom& g, Strip& s) {
     s.base = (long long)s.n * g.P;
     return true;
 }
-// centre / left / right columns of rows y0-1 .. y0+STRIP_R for a 3x3 stencil; out-of-image taps read `oob`
+// centre / left / right columns of rows y0-1 .. y0+STRIP_R for a 3x3 stencil; out-of-image taps read `oob`.
+// Split in two so a kernel can look at the centre rows first and skip the halo work of an empty strip.
 template <class T>
-__device__ __forceinline__ void strip_load3(const Geom& g, const Strip& s, const T* __restrict__ tile, T oob,
-                                            T (&c)[STRIP_R + 2], T (&l)[STRIP_R + 2], T (&r)[STRIP_R + 2]) {
+__device__ __forceinline__ void strip_load_c(const Geom& g, const Strip& s, const T* __restrict__ tile, T oob,
+                                             T (&c)[STRIP_R + 2]) {
+#pragma unroll
+    for (int j = 0; j < STRIP_R + 2; ++j) {
+        int y = s.y0 - 1 + j;
+        c[j] = (y >= 0 && y < g.H && s.okx) ? tile[y * g.W + s.x] : oob;
+    }
+}
+template <class T>
+__device__ __forceinline__ void strip_fill_lr(const Geom& g, const Strip& s, const T* __restrict__ tile, T oob,
+                                              const T (&c)[STRIP_R + 2], T (&l)[STRIP_R + 2], T (&r)[STRIP_R + 2]) {
 #pragma unroll
     for (int j = 0; j < STRIP_R + 2; ++j) {
         int y = s.y0 - 1 + j;
         bool oky = y >= 0 && y < g.H;
-        c[j] = (oky && s.okx) ? tile[y * g.W + s.x] : oob;
         T el = oob, er = oob;
         if (s.lane == 0 && oky && s.x > 0 && s.x - 1 < g.W) el = tile[y * g.W + s.x - 1];
         if (s.lane == 31 && oky && s.x + 1 < g.W) er = tile[y * g.W + s.x + 1];
@@ -208,6 +217,12 @@ __device__ __forceinline__ void strip_load3(const Geom& g, const Strip& s, const
         if (s.lane != 0) l[j] = a;
         if (s.lane != 31) r[j] = b;
     }
+}
+template <class T>
+__device__ __forceinline__ void strip_load3(const Geom& g, const Strip& s, const T* __restrict__ tile, T oob,
+                                            T (&c)[STRIP_R + 2], T (&l)[STRIP_R + 2], T (&r)[STRIP_R + 2]) {
+    strip_load_c<T>(g, s, tile, oob, c);
+    strip_fill_lr<T>(g, s, tile, oob, c, l, r);
 }
 #endif
 

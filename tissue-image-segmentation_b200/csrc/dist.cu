@@ -32,13 +32,32 @@ k_dist_prep(long long total, const float* __restrict__ dist, uint8_t* __restrict
     st4(I, i, total, vec, o);
 }
 
-// low[root] = 1 if any pixel of the plateau has a strictly lower 8-neighbour
+// Regional-minimum plateaus without labelling every plateau of the image.  A pixel is a CANDIDATE if its value is
+// below 255 and no 8-neighbour is strictly lower.  A plateau P (maximal 8-connected set of equal values) is a regional
+// minimum iff all its pixels are candidates.  Label the candidates only (equal value, 8-connected): if P is a
+// minimum it comes out as one component, none of whose pixels has an equal-valued non-candidate neighbour; if P is
+// not, every candidate component C inside it is a proper subset of the connected P, so some pixel of C touches an
+// equal-valued pixel outside C — which must be a non-candidate (a candidate would have joined C).  Hence:
+// minimum plateaus = candidate components without an "equal-valued non-candidate neighbour" flag.  On a distance map
+// the candidates are the few pixels around each nucleus centre, so the labelling pass skips almost every row.
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_plateau_lower(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ par, uint8_t* low) {
+k_min_candidates(Geom g, const uint8_t* __restrict__ I, uint8_t* __restrict__ cand) {
     Strip s;
     if (!warp_strip(g, s)) return;
     uint8_t c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
-    strip_load3<uint8_t>(g, s, I + s.base, (uint8_t)255, c, l, r);      // out-of-image taps can never be lower
+    strip_load_c<uint8_t>(g, s, I + s.base, (uint8_t)255, c);          // out-of-image taps can never be lower
+    bool any = false;
+#pragma unroll
+    for (int j = 1; j <= STRIP_R; ++j) any |= c[j] < 255;
+    if (!__ballot_sync(0xffffffffu, any)) {                            // (uniform) a strip of background
+#pragma unroll
+        for (int j = 1; j <= STRIP_R; ++j) {
+            int y = s.y0 + j - 1;
+            if (s.okx && y < g.H) cand[s.base + (long long)y * g.W + s.x] = 0;
+        }
+        return;
+    }
+    strip_fill_lr<uint8_t>(g, s, I + s.base, (uint8_t)255, c, l, r);
 #pragma unroll
     for (int j = 1; j <= STRIP_R; ++j) {
         int y = s.y0 + j - 1;
@@ -46,34 +65,68 @@ k_plateau_lower(Geom g, const uint8_t* __restrict__ I, const int* __restrict__ p
         int v = c[j];
         int mn = min(min(min((int)l[j - 1], (int)c[j - 1]), min((int)r[j - 1], (int)l[j])),
                      min(min((int)r[j], (int)l[j + 1]), min((int)c[j + 1], (int)r[j + 1])));
-        if (mn < v && v < 255) {          // the 255 plateau (background) is not built: its pixels have no parent
-            int root = par[s.base + (long long)y * g.W + s.x];
+        cand[s.base + (long long)y * g.W + s.x] = (uint8_t)(v < 255 && mn >= v);
+    }
+}
+
+// low[root] = 1 if a pixel of the candidate component has an equal-valued neighbour that is not a candidate.
+// Candidates are rare, so only their lanes probe the eight neighbours (straight from L1/L2).
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_cand_invalid(Geom g, const uint8_t* __restrict__ I, const uint8_t* __restrict__ cand, const int* __restrict__ par,
+               uint8_t* low) {
+    Strip s;
+    if (!warp_strip(g, s)) return;
+    uint8_t kc[STRIP_R];
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        int y = s.y0 + r;
+        kc[r] = (s.okx && y < g.H) ? cand[s.base + (long long)y * g.W + s.x] : (uint8_t)0;
+    }
+    const uint8_t* It = I + s.base;
+    const uint8_t* Ct = cand + s.base;
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) {
+        if (!kc[r]) continue;
+        const int y = s.y0 + r, x = s.x, idx = y * g.W + x;
+        const int v = It[idx];
+        bool bad = false;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dy == 0 && dx == 0) continue;
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
+                const int q = yy * g.W + xx;
+                bad |= It[q] == v && !Ct[q];
+            }
+        }
+        if (bad) {
+            int root = par[s.base + idx];
             if (!low[s.base + root]) low[s.base + root] = 1;
         }
     }
 }
 
-struct SelMinimumRoot {         // roots of regional-minimum plateaus with value < 255
-    const int* par; const uint8_t* I; const uint8_t* low;
-    __device__ __forceinline__ bool operator()(long long gi, int idx) const {
-        return par[gi] == idx && I[gi] < 255 && !low[gi];
-    }
+struct SelMinimumRoot {         // roots of the candidate components that are regional-minimum plateaus
+    const int* par; const uint8_t* low;
+    __device__ __forceinline__ bool operator()(long long gi, int idx) const { return par[gi] == idx && !low[gi]; }
 };
 
+// markers = raster id of the minimum plateau a pixel belongs to, else 0; written to one or two maps
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_markers_from_plateaus(long long P, const uint8_t* __restrict__ I, const int* __restrict__ par,
-                        const uint8_t* __restrict__ low, const int* __restrict__ rank, int32_t* __restrict__ markers,
-                        bool vec) {
+k_markers_from_plateaus(long long P, const int* __restrict__ par, const uint8_t* __restrict__ low,
+                        const int* __restrict__ rank, int32_t* __restrict__ markers, int32_t* __restrict__ copy, bool vec) {
     const long long base = (long long)blockIdx.y * P, i = flat4_index();
     if (i >= P) return;
-    Pack4<uint8_t> v = ld4(I + base, i, P, vec);
     Pack4<int> p = ld4(par + base, i, P, vec), o;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         o.v[k] = 0;
-        if (i + k < P && v.v[k] < 255) { long long r = base + p.v[k]; if (!low[r]) o.v[k] = rank[r]; }
+        if (i + k < P && p.v[k] >= 0) { long long r = base + p.v[k]; if (!low[r]) o.v[k] = rank[r]; }
     }
     st4(markers + base, i, P, vec, o);
+    if (copy) st4(copy + base, i, P, vec, o);
 }
 
 // histogram of the flood labels (values 0..K) and the first raster pixel of each label, one pair of atomics per
@@ -90,6 +143,7 @@ k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int* first, int KS)
     }
 #pragma unroll
     for (int r = 0; r < STRIP_R; ++r) {
+        if (!__ballot_sync(0xffffffffu, v[r] > 0)) continue;       // (uniform) nothing but background here
         int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
         bool cont = s.lane > 0 && v[r] == vl;
         unsigned m = __ballot_sync(0xffffffffu, cont);
@@ -181,7 +235,19 @@ k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lu
     FOR_TILES(LISTED, g, n) {
     strip_set_tile(g, s, n);
     int c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
-    strip_load3<int>(g, s, lab + s.base, 0, c, l, r);
+    strip_load_c<int>(g, s, lab + s.base, 0, c);
+    bool any = false;
+#pragma unroll
+    for (int j = 1; j <= STRIP_R; ++j) any |= c[j] != 0;
+    if (!__ballot_sync(0xffffffffu, any)) {                        // (uniform) a strip of background: zeros out
+#pragma unroll
+        for (int j = 1; j <= STRIP_R; ++j) {
+            int y = s.y0 + j - 1;
+            if (s.okx && y < g.H) out[s.base + (long long)y * g.W + s.x] = 0;
+        }
+        continue;
+    }
+    strip_fill_lr<int>(g, s, lab + s.base, 0, c, l, r);
 #pragma unroll
     for (int j = 1; j <= STRIP_R; ++j) {
         int y = s.y0 + j - 1;
@@ -209,7 +275,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     int* rank = ws<int>(c, total);
     int* bpar = ws<int>(c, total);
     int* brank = ws<int>(c, total);
-    int32_t* markers = markers_out ? markers_out : ws<int32_t>(c, total);
+    uint8_t* cand = ws<uint8_t>(c, total);
     int32_t* wsl = ws_out ? ws_out : ws<int32_t>(c, total);
     int32_t* arranged = ws<int32_t>(c, total);
     int* nmark = ws<int>(c, (size_t)N);
@@ -219,22 +285,23 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     int* first = ws<int>(c, (size_t)N * KS);
     int* lut = ws<int>(c, (size_t)N * KS);
     unsigned* fbits = ws<unsigned>(c, (size_t)N * g.H * g.SEG);
-    if (!I || !low || !par || !rank || !bpar || !brank || !markers || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
+    if (!I || !low || !par || !rank || !bpar || !brank || !cand || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
         !first || !lut || !fbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
 
     TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I, aligned16(dist) && (((uintptr_t)I) & 3) == 0);
-    // markers: regional-minimum plateaus (8-connected, equal value) of I below 255
-    TISEG_TRY(ccl_build(c, g, ImgEqU8{I, 255}, 2, par));
+    // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
+    TISEG_LAUNCH(c, k_min_candidates, strip_grid(g), TISEG_THREADS, 0, g, I, cand);
+    TISEG_TRY(ccl_build(c, g, ImgEqU8Where{I, cand}, 2, par));
     TISEG_TRY(zero(c, low, total));
-    TISEG_LAUNCH(c, k_plateau_lower, strip_grid(g), TISEG_THREADS, 0, g, I, par, low);
-    TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, I, low}, rank, nmark));
-    TISEG_LAUNCH(c, k_markers_from_plateaus, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, I, par, low, rank, markers,
-                 (g.P % 4 == 0) && aligned16(par, markers) && (((uintptr_t)I) & 3) == 0);
-    // flood inside b = (I < 255), blob by blob
+    TISEG_LAUNCH(c, k_cand_invalid, strip_grid(g), TISEG_THREADS, 0, g, I, cand, par, low);
+    TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, low}, rank, nmark));
+    // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
+    TISEG_LAUNCH(c, k_markers_from_plateaus, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, par, low, rank, wsl,
+                 markers_out, (g.P % 4 == 0) && aligned16(par, wsl, markers_out));
+    // flood inside b, blob by blob
     BlobInfo b;
     TISEG_TRY(blobs_build(c, g, ImgBelowU8{I, 255}, bpar, brank, b, false));
-    TISEG_TRY(ws_seed(c, g, markers, bpar, wsl));
     TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
     // arrange_label
     TISEG_TRY(zero(c, nflagged, sizeof(int)));

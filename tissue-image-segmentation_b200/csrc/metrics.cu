@@ -107,6 +107,10 @@ __device__ __forceinline__ void pair_accumulate_strip(const Geom& g, const Strip
         a[r] = ok ? par_g[st.base + (long long)y * g.W + st.x] : -1;
         b[r] = ok ? par_p[st.base + (long long)y * g.W + st.x] : -1;
     }
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < STRIP_R; ++r) any |= a[r] >= 0 || b[r] >= 0;
+    if (!__ballot_sync(0xffffffffu, any)) return;            // (uniform) a strip of background on both sides
     int gid[STRIP_R], pid[STRIP_R];
 #pragma unroll
     for (int r = 0; r < STRIP_R; ++r) {
@@ -366,41 +370,53 @@ __global__ void k_metrics_final(InstState s, ClassInfo ci, const unsigned long l
 }
 
 // ---- K13 semantic counts ---------------------------------------------------------------------------
-// counts[n, k, c], k = TP, FP, FN, Pred, GT.  Shared-memory histogram per block, one global atomic per
-// non-zero bin per block.  Classes outside [0, C) are not counted (torch.histc range semantics).
+// counts[n, k, c], k = TP, FP, FN, Pred, GT.  Each block keeps the (C+1) x (C+1) confusion matrix (gt, pred) of its
+// pixels in shared memory — index C collects classes outside [0, C), which torch.histc does not count — with ONE
+// shared atomic per group of lanes holding the same (gt, pred) pair (match_any), then derives the five vectors
+// and flushes one global atomic per non-zero entry.
 #define SEM_MAXC 64
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, int C, int ignore,
              unsigned long long* counts, unsigned long long* valid, bool vec) {
-    __shared__ unsigned h[5 * SEM_MAXC];
-    __shared__ unsigned nvalid;
-    for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) h[i] = 0;
-    if (threadIdx.x == 0) nvalid = 0;
+    __shared__ unsigned h[(SEM_MAXC + 1) * (SEM_MAXC + 1)];
+    const int C1 = C + 1, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < C1 * C1; i += blockDim.x) h[i] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.y * P;
-    int nv = 0;
-    // each thread walks several 4-pixel groups so that one block amortises its histogram flush
-    for (long long i = flat4_index(); i < P; i += (long long)gridDim.x * blockDim.x * 4) {
-        Pack4<uint8_t> pp = ld4(pred + base, i, P, vec), tt = ld4(gt + base, i, P, vec);
+    // each thread walks several 4-pixel groups so that one block amortises its flush; the trip count is uniform
+    const long long step = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x * 4; i0 < P; i0 += step) {
+        const long long i = i0 + (long long)threadIdx.x * 4;
+        Pack4<uint8_t> pp, tt;
+        if (i < P) { pp = ld4(pred + base, i, P, vec); tt = ld4(gt + base, i, P, vec); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (i + k >= P) continue;
-            int p = pp.v[k], t = tt.v[k];
-            if (t == ignore) continue;
-            ++nv;
-            bool pin = p < C, tin = t < C;
-            if (p == t) { if (tin) atomicAdd(&h[0 * C + t], 1u); }
-            else { if (pin) atomicAdd(&h[1 * C + p], 1u); if (tin) atomicAdd(&h[2 * C + t], 1u); }
-            if (pin) atomicAdd(&h[3 * C + p], 1u);
-            if (tin) atomicAdd(&h[4 * C + t], 1u);
+            int key = -1;
+            if (i + k < P) {
+                const int p = pp.v[k], t = tt.v[k];
+                if (t != ignore) key = min(t, C) * C1 + min(p, C);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&h[key], (unsigned)__popc(peers));
         }
     }
-    for (int d = 16; d; d >>= 1) nv += __shfl_down_sync(0xffffffffu, nv, d);
-    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&nvalid, (unsigned)nv);
     __syncthreads();
-    for (int i = threadIdx.x; i < 5 * C; i += blockDim.x)
-        if (h[i]) atomicAdd(&counts[(long long)blockIdx.y * 5 * C + i], (unsigned long long)h[i]);
-    if (threadIdx.x == 0 && nvalid) atomicAdd(&valid[blockIdx.y], (unsigned long long)nvalid);
+    for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) {
+        const int k = i / C, c = i - k * C;
+        unsigned v = 0;
+        if (k == 0) v = h[c * C1 + c];
+        else if (k == 1) { for (int t = 0; t <= C; ++t) if (t != c) v += h[t * C1 + c]; }
+        else if (k == 2) { for (int q = 0; q <= C; ++q) if (q != c) v += h[c * C1 + q]; }
+        else if (k == 3) { for (int t = 0; t <= C; ++t) v += h[t * C1 + c]; }
+        else { for (int q = 0; q <= C; ++q) v += h[c * C1 + q]; }
+        if (v) atomicAdd(&counts[(long long)blockIdx.y * 5 * C + i], (unsigned long long)v);
+    }
+    if (threadIdx.x < 32) {
+        unsigned nv = 0;
+        for (int i = lane; i < C1 * C1; i += 32) nv += h[i];
+        for (int d = 16; d; d >>= 1) nv += __shfl_down_sync(0xffffffffu, nv, d);
+        if (lane == 0 && nv) atomicAdd(&valid[blockIdx.y], (unsigned long long)nv);
+    }
 }
 
 static int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }

@@ -61,10 +61,42 @@ k_softmax_argmax(long long P, const float* __restrict__ logits, int T, int C, fl
     if (cls) st4(cls + (long long)n * P, i, P, vec, best);
 }
 
+// One variant and only the class map wanted: softmax is strictly increasing in the logit, so the class is the first
+// maximum of the logits themselves (it can differ from the reference's argmax-of-probabilities only where two
+// probabilities round to the same fp32 value, the tie band the parity test already excludes).  Pure streaming.
+template <int CMAX>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_argmax_logits(long long P, const float* __restrict__ logits, int C, uint8_t* __restrict__ cls, bool vec) {
+    const int n = blockIdx.y;
+    const long long i = flat4_index();
+    if (i >= P) return;
+    const float* src = logits + (long long)n * C * P;
+    Pack4<float> x[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) if (c < C) x[c] = ld4(src + c * P, i, P, vec);
+    Pack4<uint8_t> best;
+    float bv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best.v[k] = 0; bv[k] = x[0].v[k]; }
+#pragma unroll
+    for (int c = 1; c < CMAX; ++c)
+        if (c < C) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x[c].v[k] > bv[k]) { bv[k] = x[c].v[k]; best.v[k] = (uint8_t)c; }
+        }
+    st4(cls + (long long)n * P, i, P, vec, best);
+}
+
 int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, int C, float* d_prob, uint8_t* d_cls) {
     const long long P = g.P;
     const bool vec = (P % 4 == 0) && aligned16(d_in, d_prob) && (((uintptr_t)d_cls) & 3) == 0;
     dim3 grid(flat4_grid(P), (unsigned)g.N);
+    if (T == 1 && !d_prob) {
+        if (C <= 4) TISEG_LAUNCH(c, k_argmax_logits<4>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
+        else if (C <= 8) TISEG_LAUNCH(c, k_argmax_logits<8>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
+        else TISEG_LAUNCH(c, k_argmax_logits<16>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
+        return TISEG_OK;
+    }
     if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax<4>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);
     else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax<8>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);
     else TISEG_LAUNCH(c, k_softmax_argmax<16>, grid, TISEG_THREADS, 0, P, d_in, T, C, d_prob, d_cls, vec);

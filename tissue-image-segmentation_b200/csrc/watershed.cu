@@ -41,6 +41,7 @@ k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, B
     }
 #pragma unroll
     for (int r = 0; r < STRIP_R; ++r) {
+        if (!__ballot_sync(FULL, p[r] >= 0)) continue;           // (uniform) nothing but background here
         int pl = __shfl_up_sync(FULL, p[r], 1);
         bool cont = s.lane > 0 && p[r] >= 0 && pl == p[r];
         unsigned m = __ballot_sync(FULL, cont);
