@@ -33,16 +33,25 @@ METRIC = "postproc+eval tiles/s @1000x1000 (DIST MoNuSeg config)"
 # algorithmic bytes per pixel of one tile through the whole path:
 # sem logits 2x4 + dist 4 + sem_pred 1 + inst_pred 4 + inst_gt 4 + sem_gt 1
 PIPE_BYTES_PER_PX = 22
-# compulsory bytes per pixel of each kernel's own inputs + outputs, touched once
-KERNEL_BYTES_PER_PX = {
-    "k_ws_flood_u8": 1 + 4 + 4 + 4,          # level image, blob forest, seeds in, labels out
-    "k_softmax_argmax<4>": 8 + 1, "k_dist_prep": 4 + 1,
-    "k_ccl_init<Img>": 1 + 4, "(k_ccl_merge<Img, 1>)": 1 + 4 + 4, "(k_ccl_merge<Img, 2>)": 1 + 4 + 4,
-    "k_ccl_flatten": 4 + 4, "k_rank_count<Sel>": 4, "k_rank_place<Sel>": 4 + 4, "k_apply_rank": 4 + 4 + 4,
-    "k_pair_accumulate": 4 * 4, "k_plateau_lower": 1 + 4, "k_markers_from_plateaus": 1 + 4 + 4,
-    "k_blob_roots": 4, "k_blob_bbox": 4, "k_ws_seed": 4 + 4 + 4, "k_ws_hist": 4, "k_wsl_remove": 4 + 4,
-    "k_sem_counts": 2, "memset": 4,
-}
+# compulsory bytes per pixel of each kernel's own inputs + outputs, touched once; matched by prefix of the
+# kernel name reported by the library's per-launch CUDA-event timing
+KERNEL_BYTES_PER_PX = [
+    ("k_ws_flood_u8", 1 + 4 + 4 + 4),            # level image, blob forest, seeds in, labels out
+    ("(k_ccl_local<Img, 2", 4 + 4), ("(k_ccl_local<Img, 1", 1 + 4),     # values in (int32 label map / uint8), forest out
+    ("(k_ccl_border", 4), ("k_ccl_flatten", 4 + 4),
+    ("k_argmax_logits", 8 + 1), ("k_softmax_argmax", 8 + 1), ("k_dist_prep", 4 + 1),
+    ("k_min_candidates", 1 + 1), ("k_cand_invalid", 1 + 1), ("k_markers_from_plateaus", 4 + 4),
+    ("k_rank_bits", 4), ("k_rank_rowscan", 1.0 / 8), ("k_rank_place_bits", 1.0 / 8),
+    ("k_blob_roots", 4), ("k_blob_bbox", 4), ("k_ws_hist", 4), ("k_wsl_remove", 4 + 4),
+    ("k_pair_accumulate", 4 * 4), ("k_sem_counts", 2), ("memset", 1),
+]
+
+
+def kernel_bytes_per_px(name):
+    for prefix, b in KERNEL_BYTES_PER_PX:
+        if name.startswith(prefix):
+            return b
+    return 8
 
 
 def make_tiles(n_distinct, seed0):
@@ -282,14 +291,25 @@ def run_b200(a):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    bpp = KERNEL_BYTES_PER_PX.get(name, 8)
+    bpp = kernel_bytes_per_px(name)
     alg_bytes = bpp * H * W * B                             # per launch: the kernel sees the whole batch
     achieved = alg_bytes / (kms / cnt / 1e3) / 1e9
+    # DRAM traffic of that kernel per launch from the committed ncu capture of this workload, if one is recorded
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        if prof.get("kernel") == name and prof.get("batch") == B:
+            traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
             "kernel_share_of_step": kms / total_ms, "alg_bytes_per_launch": alg_bytes,
+            "launches_of_kernel_per_step": cnt / 2,
             "pipeline_frac": (PIPE_BYTES_PER_PX * H * W * value / world) / 1e9 / peak,
-            "per_kernel_ms_per_step": {k: round(v[1] / 2, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}}
+            "per_kernel_ms_per_step": {k: round(v[1] / 2, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
+            "per_kernel_frac": {k: round(kernel_bytes_per_px(k) * H * W * B / (v[1] / v[0] / 1e3) / 1e9 / peak, 4)
+                                for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if v[1] / 2 > 0.02}}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:

@@ -82,15 +82,16 @@ cudaEvent_t timing_before(tiseg_ctx* c, const char* name);
     } while (0)
 
 // launch + count + error check.  Usage: TISEG_LAUNCH(c, kernel, grid, block, smem, args...)
-#define TISEG_LAUNCH(c, kern, grid, block, smem, ...)                                 \
+#define TISEG_LAUNCH_AS(c, name, kern, grid, block, smem, ...)                        \
     do {                                                                              \
-        cudaEvent_t _tb = (c)->timing ? ::tiseg::timing_before((c), #kern) : nullptr; \
+        cudaEvent_t _tb = (c)->timing ? ::tiseg::timing_before((c), name) : nullptr;  \
         kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);                  \
         if (_tb) cudaEventRecord(_tb, (c)->stream);                                   \
         (c)->launches++;                                                              \
         cudaError_t _e = cudaGetLastError();                                          \
-        if (_e != cudaSuccess) return ::tiseg::fail(#kern, _e);                       \
+        if (_e != cudaSuccess) return ::tiseg::fail(name, _e);                        \
     } while (0)
+#define TISEG_LAUNCH(c, kern, grid, block, smem, ...) TISEG_LAUNCH_AS(c, #kern, kern, grid, block, smem, __VA_ARGS__)
 
 // ---- geometry: one warp per 32-pixel row segment, blocks never straddle two tiles ----------------
 struct Geom {

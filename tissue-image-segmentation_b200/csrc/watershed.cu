@@ -787,15 +787,15 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     if (debug) {
         prof = ws<long long>(c, (size_t)c->sm_count * WARPS * 5);
         if (!prof) return TISEG_ERR_CUDA;
-        TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
-                     gheads, out, gen_first, 1, prof);
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>), c->sm_count, 32 * WARPS, SMEM, g,
+                        image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     } else {
-        TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
-                     gheads, out, gen_first, 1, prof);
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g,
+                        image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     }
     // blobs found too wide in levels after the other CTAs had left the general list; exits at once if there are none
-    TISEG_LAUNCH(c, (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g, image, par, b, wk, next,
-                 gheads, out, 0, 0, nullptr);
+    TISEG_LAUNCH_AS(c, "k_ws_flood_u8(level-span overflow)", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count,
+                    32 * WARPS, SMEM, g, image, par, b, wk, next, gheads, out, 0, 0, nullptr);
     if (debug) {                                  // work-list census on stderr (synchronises; diagnostics only)
         int h[WK_INTS];
         TISEG_CHECK(cudaMemcpyAsync(h, ints, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
