@@ -117,9 +117,10 @@ int tiseg_postproc_dist(tiseg_ctx* ctx, const float* dist, int N, int H, int W, 
 
 /* ---- A11: HoVer-Net post-process (hovernet.py:283-365, hover_post_proc; fx = 1) ------------------------------
  * fore_map [N,H,W] fp32 (softmax channel 1 of the foreground head), hv_map [N,H,W,2] fp32 HWC (horizontal,
- * vertical) as the reference passes them after permute(0,2,3,1).  scale_factor must be 1 (the MoNuSeg / CoNSeP
- * configs; the resize path of the CoNIC config is not implemented).  inst_out [N,H,W] int32.  Optional debug
- * outputs (NULL to skip): blb uint8, dist fp64 (the flooded image), marker int32. */
+ * vertical) as the reference passes them after permute(0,2,3,1).  scale_factor: 1 (the MoNuSeg / CoNSeP configs)
+ * or 2 (the CoNIC config: cv2.resize x2 bilinear in, the whole chain at 2H x 2W, INTER_NEAREST back).
+ * inst_out [N,H,W] int32.  Optional debug outputs (NULL to skip), at the SCALED size [N, sH, sW]: blb uint8,
+ * dist fp64 (the flooded image), marker int32. */
 int tiseg_postproc_hover(tiseg_ctx* ctx, const float* fore_map, const float* hv_map, int N, int H, int W,
                          int scale_factor, int32_t* inst_out, uint8_t* blb_out, double* dist_out, int32_t* marker_out);
 
@@ -170,6 +171,14 @@ int tiseg_pair_metrics_multiclass(tiseg_ctx* ctx, const int32_t* pred_inst, cons
  * host as N_valid - (TP+FP+FN)); valid [N] int64 = pixels with gt != ignore_index. */
 int tiseg_sem_counts(tiseg_ctx* ctx, const uint8_t* pred, const uint8_t* gt, int N, int H, int W, int C,
                      int ignore_index, int64_t* counts, int64_t* valid);
+
+/* ---- A14: distance transforms (label generation: datasets/ops/distance_map.py:93, direction_map.py:167,179,
+ * unet_map.py:72, utils/direction_calculation.py:164; losses/surface_loss.py:7) -------------------------------
+ * mask [N,H,W] uint8 (non-zero = object).  edt: fp64 Euclidean distance to the nearest zero pixel
+ * (scipy.ndimage.distance_transform_edt, bit-identical: sqrt of the exact integer squared distance);
+ * cdt: int32 chessboard distance (scipy.ndimage.distance_transform_cdt, default metric; -1 when a tile has no zero). */
+int tiseg_distance_transform_edt(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, double* out);
+int tiseg_distance_transform_cdt(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, int32_t* out);
 
 #ifdef __cplusplus
 }

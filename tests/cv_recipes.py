@@ -64,3 +64,38 @@ def gaussian_blur3(d64):
 
 
 ELLIPSE5 = np.array([[0, 0, 1, 0, 0], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [0, 0, 1, 0, 0]], np.uint8)
+
+
+def resize_up2_linear(x):
+    """cv2.resize(x, (0, 0), fx=2, fy=2) for fp32 HW or HWC input (OpenCV 4.13 of this image): sample positions
+    (d + 0.5) / 2 - 0.5 (weights 0.75 / 0.25, clamped at the borders), horizontal pass then vertical.  One-channel
+    images with both sides >= 2 take OpenCV's 2x fast path and interpolate as fma(a, x1 - x0, x0); everything
+    else as x0 * (1 - a) + x1 * a with separately rounded products."""
+    f32 = np.float32
+
+    def coords(n):
+        d = np.arange(2 * n)
+        f = (d + 0.5) * 0.5 - 0.5
+        s = np.floor(f).astype(int)
+        a = (f - s).astype(f32)
+        lo = s < 0; s[lo] = 0; a[lo] = 0
+        hi = s >= n - 1; a[hi] = 0; s[hi] = n - 1
+        return s, np.minimum(s + 1, n - 1), a
+
+    def lerp(x0, x1, a):
+        return (a.astype(np.float64) * (x1 - x0).astype(f32).astype(np.float64) + x0.astype(np.float64)).astype(f32)
+
+    def mma(x0, x1, a):
+        return (x0 * (f32(1) - a)).astype(f32) + (x1 * a).astype(f32)
+
+    def one(S, mix):
+        H, W = S.shape
+        x0, x1, ax = coords(W)
+        y0, y1, ay = coords(H)
+        h = mix(S[:, x0], S[:, x1], np.broadcast_to(ax[None, :], (H, 2 * W)))
+        return mix(h[y0, :], h[y1, :], np.broadcast_to(ay[:, None], (2 * H, 2 * W)))
+
+    x = np.asarray(x, f32)
+    if x.ndim == 2:
+        return one(x, lerp if min(x.shape) >= 2 else mma)
+    return np.stack([one(x[..., c], mma) for c in range(x.shape[2])], -1)

@@ -364,9 +364,44 @@ def test_postproc_hover(H, W, idx):
     assert got.max() > 3
 
 
+@pytest.mark.parametrize("H,W,idx", [(64, 100, 1), (256, 256, 0), (125, 131, 2), (1, 40, 4), (33, 1, 5)])
+def test_postproc_hover_scale2(H, W, idx):
+    """The CoNIC configuration: cv2.resize x2 in, the chain at 2H x 2W, INTER_NEAREST back (hovernet.py:286-287, 363)."""
+    t = synth.tile_hover(3, idx, H=max(H, 40), W=max(W, 40))
+    fore, hv = np.ascontiguousarray(t["fore_map"][:H, :W]), np.ascontiguousarray(t["hv_map"][:H, :W])
+    want, dbg = opp.hover_post_proc(fore, hv, scale_factor=2)
+    got, blb, dist, mk = ops.postproc_hover(fore, hv, scale_factor=2, debug=True)
+    assert blb.shape == (2 * H, 2 * W)
+    _diff(blb, dbg["blb"], "hover x2 blb")
+    _diff(mk, dbg["marker"], "hover x2 markers")
+    _diff(dist, dbg["dist"], "hover x2 flooded image (fp64, bit-exact)")
+    _diff(got, want, "hover x2 inst")
+
+
 def test_postproc_hover_full_tile_batched():
     tiles = [synth.tile_hover(3, j) for j in range(2)]
     got = ops.postproc_hover(np.stack([t["fore_map"] for t in tiles]), np.stack([t["hv_map"] for t in tiles]))
     for j, t in enumerate(tiles):
         want, _ = opp.hover_post_proc(t["fore_map"], t["hv_map"])
         _diff(got[j], want, "hover inst 1000^2 tile %d" % j)
+
+
+# --------------------------------------------------------------------------- A14
+def test_distance_transforms_vs_scipy():
+    rng = np.random.default_rng(140)
+    cases = [np.ones((4, 5), np.uint8), np.zeros((3, 7), np.uint8)]
+    for (H, W) in [(1, 1), (1, 40), (37, 1), (64, 64), (50, 97), (130, 257)]:
+        cases.append((rng.random((H, W)) < 0.9).astype(np.uint8))
+        m = ndi.binary_dilation(rng.random((H, W)) < 0.02, iterations=3).astype(np.uint8)
+        cases.append(m)
+    t = synth.tile_dist(2, 5, H=300, W=400)
+    cases.append((t["gt_inst"] > 0).astype(np.uint8))
+    for m in cases:
+        want_e = ndi.distance_transform_edt(m)
+        got_e = ops.distance_transform_edt(m)
+        assert got_e.dtype == np.float64 and np.array_equal(got_e, want_e), "edt differs for shape %r" % (m.shape,)
+        _diff(ops.distance_transform_cdt(m), ndi.distance_transform_cdt(m, metric="chessboard"), "cdt %r" % (m.shape,))
+    big = np.stack([(synth.tile_dist(2, j)["gt_inst"] > 0).astype(np.uint8) for j in range(2)])
+    got = ops.distance_transform_edt(big)
+    for j in range(2):
+        assert np.array_equal(got[j], ndi.distance_transform_edt(big[j]))

@@ -187,3 +187,18 @@ def test_opencv_recipes_are_bit_exact():
             # pixels next to the minimum differ in the last bit
             sn = cv2.normalize(s, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
             assert (R.normalize_minmax_f32(s) != sn).sum() <= 4
+
+
+def test_opencv_resize_x2_recipe_is_bit_exact():
+    """cv2.resize(x, (0, 0), fx=2, fy=2) of hover_post_proc with scale_factor = 2 (the CoNIC config), and the
+    INTER_NEAREST way back: the arithmetic the k_resize_up2 / k_resize_down2_nearest kernels implement."""
+    cv2 = pytest.importorskip("cv2")
+    import cv_recipes as R
+    rng = np.random.default_rng(77)
+    for (H, W) in [(1, 1), (1, 5), (3, 1), (2, 2), (7, 9), (64, 64), (100, 131), (256, 256)]:
+        x = (rng.standard_normal((H, W)) * 3).astype(np.float32)
+        assert np.array_equal(R.resize_up2_linear(x), cv2.resize(x, (0, 0), fx=2, fy=2)), (H, W)
+        hv = (rng.random((H, W, 2)) * 2 - 1).astype(np.float32)
+        assert np.array_equal(R.resize_up2_linear(hv), cv2.resize(hv, (0, 0), fx=2, fy=2)), (H, W)
+        lab = rng.integers(0, 1000, (2 * H, 2 * W)).astype(np.int32)
+        assert np.array_equal(cv2.resize(lab, (W, H), interpolation=cv2.INTER_NEAREST), lab[::2, ::2])

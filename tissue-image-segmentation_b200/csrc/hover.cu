@@ -240,6 +240,49 @@ int postproc_hover_dev(tiseg_ctx* c, const Geom& g, const float* fore, const flo
     return TISEG_OK;
 }
 
+// ---- scale_factor = 2 (the CoNIC config, hovernet_adam-lr1e-4_bs8_256x256_100e_conic.py:47) -----------------------
+// cv2.resize(src, (0, 0), fx=2, fy=2) = bilinear with sample positions (d + 0.5) / 2 - 0.5: weights 0.75 / 0.25,
+// clamped at the borders; horizontal pass, then vertical.  Arithmetic of the OpenCV 4.13 build the oracle runs
+// (pinned in tests/cv_recipes.py): one-channel images with both sides >= 2 take OpenCV's 2x fast path, which
+// interpolates as fma(a, x1 - x0, x0); everything else (two channels, degenerate sides) as x0 * (1 - a) + x1 * a.
+__device__ __forceinline__ void up2_coord(int d, int n, int& s0, int& s1, float& a) {
+    // f = (d + 0.5) * 0.5 - 0.5 = d / 2 - 0.25
+    int s = (d & 1) ? (d >> 1) : (d >> 1) - 1;
+    a = (d & 1) ? 0.25f : 0.75f;
+    if (s < 0) { s = 0; a = 0.f; }
+    if (s >= n - 1) { s = n - 1; a = 0.f; }
+    s0 = s; s1 = min(s + 1, n - 1);
+}
+template <bool LERP>
+__device__ __forceinline__ float up2_mix(float x0, float x1, float a) {
+    if (LERP) return fmaf(a, __fsub_rn(x1, x0), x0);
+    return __fadd_rn(__fmul_rn(x0, __fsub_rn(1.f, a)), __fmul_rn(x1, a));
+}
+template <int CN, bool LERP>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_resize_up2(Geom gd, int H, int W, const float* __restrict__ src, float* __restrict__ dst) {
+    Pix px;
+    if (!warp_pixel(gd, px) || !px.ok) return;
+    int y0, y1, x0, x1;
+    float ay, ax;
+    up2_coord(px.y, H, y0, y1, ay);
+    up2_coord(px.x, W, x0, x1, ax);
+    const float* t = src + (long long)px.n * H * W * CN;
+#pragma unroll
+    for (int ch = 0; ch < CN; ++ch) {
+        const float h0 = up2_mix<LERP>(t[((long long)y0 * W + x0) * CN + ch], t[((long long)y0 * W + x1) * CN + ch], ax);
+        const float h1 = up2_mix<LERP>(t[((long long)y1 * W + x0) * CN + ch], t[((long long)y1 * W + x1) * CN + ch], ax);
+        dst[(px.base + px.idx) * CN + ch] = up2_mix<LERP>(h0, h1, ay);
+    }
+}
+// cv2.resize(labels, (W, H), interpolation=INTER_NEAREST) from (2H, 2W): source pixel (2y, 2x)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_resize_down2_nearest(Geom g, const int32_t* __restrict__ src, int32_t* __restrict__ dst) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    dst[px.base + px.idx] = src[(long long)px.n * g.P * 4 + (long long)(2 * px.y) * (2 * g.W) + 2 * px.x];
+}
+
 }  // namespace tiseg
 
 using namespace tiseg;
@@ -248,18 +291,34 @@ extern "C" int tiseg_postproc_hover(tiseg_ctx* c, const float* fore_map, const f
                                     int scale_factor, int32_t* inst_out, uint8_t* blb_out, double* dist_out,
                                     int32_t* marker_out) {
     if (!c || !fore_map || !hv_map || !inst_out) { set_error("tiseg_postproc_hover: bad argument"); return TISEG_ERR_ARG; }
-    if (scale_factor != 1) { set_error("tiseg_postproc_hover: only scale_factor = 1 is implemented"); return TISEG_ERR_ARG; }
-    TISEG_TRY(check_geom(N, H, W));
+    if (scale_factor != 1 && scale_factor != 2) {
+        set_error("tiseg_postproc_hover: scale_factor must be 1 or 2 (the values of the reference configs)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N, H * scale_factor, W * scale_factor));
     begin_call(c);
     Geom g = make_geom(N, H, W);
-    size_t total = (size_t)N * g.P;
+    Geom gs = make_geom(N, H * scale_factor, W * scale_factor);          // the resolution the pipeline runs at
+    size_t total = (size_t)N * g.P, stotal = (size_t)N * gs.P;
     const float* d_fore = in(c, fore_map, total);
     const float* d_hv = in(c, hv_map, total * 2);
     int32_t* d_inst = tiseg::out(c, inst_out, total);
-    uint8_t* d_blb = blb_out ? tiseg::out(c, blb_out, total) : nullptr;
-    double* d_dist = dist_out ? tiseg::out(c, dist_out, total) : nullptr;
-    int32_t* d_mk = marker_out ? tiseg::out(c, marker_out, total) : nullptr;
+    uint8_t* d_blb = blb_out ? tiseg::out(c, blb_out, stotal) : nullptr;
+    double* d_dist = dist_out ? tiseg::out(c, dist_out, stotal) : nullptr;
+    int32_t* d_mk = marker_out ? tiseg::out(c, marker_out, stotal) : nullptr;
     if (!d_fore || !d_hv || !d_inst) return TISEG_ERR_CUDA;
-    TISEG_TRY(postproc_hover_dev(c, g, d_fore, d_hv, 10, d_inst, d_blb, d_dist, d_mk));
+    if (scale_factor == 1) {
+        TISEG_TRY(postproc_hover_dev(c, g, d_fore, d_hv, 10, d_inst, d_blb, d_dist, d_mk));
+        return end_call(c);
+    }
+    float* fore2 = ws<float>(c, stotal);
+    float* hv2 = ws<float>(c, stotal * 2);
+    int32_t* inst2 = ws<int32_t>(c, stotal);
+    if (!fore2 || !hv2 || !inst2) return TISEG_ERR_CUDA;
+    if (H >= 2 && W >= 2) TISEG_LAUNCH(c, (k_resize_up2<1, true>), warp_grid(gs), TISEG_THREADS, 0, gs, H, W, d_fore, fore2);
+    else                  TISEG_LAUNCH(c, (k_resize_up2<1, false>), warp_grid(gs), TISEG_THREADS, 0, gs, H, W, d_fore, fore2);
+    TISEG_LAUNCH(c, (k_resize_up2<2, false>), warp_grid(gs), TISEG_THREADS, 0, gs, H, W, d_hv, hv2);
+    TISEG_TRY(postproc_hover_dev(c, gs, fore2, hv2, 10, inst2, d_blb, d_dist, d_mk));
+    TISEG_LAUNCH(c, k_resize_down2_nearest, warp_grid(g), TISEG_THREADS, 0, g, inst2, d_inst);
     return end_call(c);
 }

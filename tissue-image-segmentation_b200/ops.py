@@ -8,6 +8,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import as_input, batched, empty_like_kind, get_ctx, ptr
+from ._lib import is_torch as _lib_is_torch
 
 
 def _dev(a):
@@ -257,11 +258,32 @@ def postproc_hover(fore_map, hv_map, scale_factor=1, debug=False):
     if tuple(hv.shape) != (N, H, W, 2):
         raise ValueError("hv_map must be [N,H,W,2] (HWC), got %r" % (tuple(hv.shape),))
     inst = empty_like_kind(f, (N, H, W), np.int32)
-    blb = empty_like_kind(f, (N, H, W), np.uint8) if debug else None
-    dist = empty_like_kind(f, (N, H, W), np.float64) if debug else None
-    mk = empty_like_kind(f, (N, H, W), np.int32) if debug else None
+    sf = int(scale_factor)                      # the debug maps live at the resolution the chain runs at
+    blb = empty_like_kind(f, (N, H * sf, W * sf), np.uint8) if debug else None
+    dist = empty_like_kind(f, (N, H * sf, W * sf), np.float64) if debug else None
+    mk = empty_like_kind(f, (N, H * sf, W * sf), np.int32) if debug else None
     get_ctx(_dev(f)).call("tiseg_postproc_hover", ptr(f), ptr(hv), N, H, W, int(scale_factor), ptr(inst), ptr(blb),
                           ptr(dist), ptr(mk))
     if debug:
         return tuple(_unbatch(x, was2d) for x in (inst, blb, dist, mk))
     return _unbatch(inst, was2d)
+
+
+def distance_transform_edt(mask):
+    """A14.  scipy.ndimage.distance_transform_edt of a binary mask -> fp64 (bit-identical)."""
+    x, was2d = batched(as_input(np.asarray(mask) != 0 if not _lib_is_torch(mask) else mask != 0, np.uint8))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.float64)
+    get_ctx(_dev(x)).call("tiseg_distance_transform_edt", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def distance_transform_cdt(mask, metric="chessboard"):
+    """A14.  scipy.ndimage.distance_transform_cdt (chessboard) of a binary mask -> int32."""
+    if metric != "chessboard":
+        raise ValueError("only the chessboard metric (the one the reference uses) is implemented")
+    x, was2d = batched(as_input(np.asarray(mask) != 0 if not _lib_is_torch(mask) else mask != 0, np.uint8))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.int32)
+    get_ctx(_dev(x)).call("tiseg_distance_transform_cdt", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
