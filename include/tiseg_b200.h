@@ -114,6 +114,16 @@ int tiseg_watershed_f64(tiseg_ctx* ctx, const double* image, const int32_t* mark
  * with the same values).  Optional debug outputs (NULL to skip): markers int32, ws int32 (raw flood). */
 int tiseg_postproc_dist(tiseg_ctx* ctx, const float* dist, int N, int H, int W, int32_t* inst_out,
                         int32_t* markers_out, int32_t* ws_out);
+/* The same with the paper's p1 ("lamb" of dynamic_watershed_alias, dist.py:114; the reference's test path passes 0.0,
+ * dist.py:281): markers and flood levels come from Hrecons = reconstruction_by_erosion(min(255, I + lamb), I).
+ * lamb > 0 runs an iterative reconstruction that synchronises with the host between sweeps. */
+int tiseg_postproc_dist_lambda(tiseg_ctx* ctx, const float* dist, int N, int H, int W, int lamb, int32_t* inst_out,
+                               int32_t* markers_out, int32_t* ws_out);
+
+/* ---- A9: skimage.morphology.reconstruction(seed, mask, method='erosion') on uint8 images, 3x3 footprint
+ * (dist.py:56).  seed is clamped from below by mask.  Synchronises with the host between sweeps. */
+int tiseg_reconstruction_erosion_u8(tiseg_ctx* ctx, const uint8_t* seed, const uint8_t* mask, int N, int H, int W,
+                                    uint8_t* out);
 
 /* ---- A11: HoVer-Net post-process (hovernet.py:283-365, hover_post_proc; fx = 1) ------------------------------
  * fore_map [N,H,W] fp32 (softmax channel 1 of the foreground head), hv_map [N,H,W,2] fp32 HWC (horizontal,

@@ -405,3 +405,22 @@ def test_distance_transforms_vs_scipy():
     got = ops.distance_transform_edt(big)
     for j in range(2):
         assert np.array_equal(got[j], ndi.distance_transform_edt(big[j]))
+
+
+# --------------------------------------------------------------------------- A9
+def test_reconstruction_erosion_vs_oracle():
+    rng = np.random.default_rng(90)
+    for (H, W, h) in [(1, 1, 3), (1, 40, 5), (37, 1, 2), (30, 33, 7), (64, 64, 1), (130, 257, 20), (200, 300, 60)]:
+        x = ndi.uniform_filter(rng.integers(0, 256, (H, W)).astype(np.float64), 3).astype(np.uint8)
+        seed = np.minimum(255, x.astype(np.int32) + h).astype(np.uint8)
+        want = sk.reconstruction_erosion(seed.astype(np.float64), x.astype(np.float64)).astype(np.uint8)
+        _diff(ops.reconstruction(seed, x), want, "reconstruction %dx%d h=%d" % (H, W, h))
+
+
+@pytest.mark.parametrize("lamb", [1, 2, 5])
+def test_postproc_dist_lambda(lamb):
+    """dynamic_watershed_alias with lamb > 0 (H-minima reconstruction before the markers and the flood)."""
+    t = synth.tile_dist(2, 7, H=200, W=230)
+    d = np.clip(t["dist_logit"], 0, 255).astype("int32")
+    want = opp.dist_dynamic_watershed(d, float(lamb), 0.5, literal=False)
+    _diff(ops.postproc_dist(t["dist_logit"], lamb=lamb), want, "dist inst lambda=%d" % lamb)

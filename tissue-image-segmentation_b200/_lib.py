@@ -38,6 +38,8 @@ SIGNATURES = {
     "tiseg_watershed_u8": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tiseg_watershed_f64": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tiseg_postproc_dist": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "tiseg_postproc_dist_lambda": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "tiseg_reconstruction_erosion_u8": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "tiseg_postproc_hover": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tiseg_ddm": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_cdnet_refine": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

@@ -265,11 +265,14 @@ k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lu
     }
 }
 
-int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* inst, int32_t* markers_out,
+int h_reconstruction_erosion_dev(tiseg_ctx* c, const Geom& g, const uint8_t* img, int h, uint8_t* out);   // recon.cu
+
+int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, int32_t* inst, int32_t* markers_out,
                       int32_t* ws_out) {
     int N = g.N, KS = g.P + 1;
     size_t total = (size_t)N * g.P;
-    uint8_t* I = ws<uint8_t>(c, total);
+    uint8_t* I0 = ws<uint8_t>(c, total);
+    uint8_t* I = I0;
     uint8_t* low = ws<uint8_t>(c, total);
     int* par = ws<int>(c, total);
     int* rank = ws<int>(c, total);
@@ -285,11 +288,18 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
     int* first = ws<int>(c, (size_t)N * KS);
     int* lut = ws<int>(c, (size_t)N * KS);
     unsigned* fbits = ws<unsigned>(c, (size_t)N * g.H * g.SEG);
-    if (!I || !low || !par || !rank || !bpar || !brank || !cand || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
+    if (!I0 || !low || !par || !rank || !bpar || !brank || !cand || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
         !first || !lut || !fbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
 
-    TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I, aligned16(dist) && (((uintptr_t)I) & 3) == 0);
+    TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I0, aligned16(dist) && (((uintptr_t)I0) & 3) == 0);
+    // Hrecons (dist.py:120): the identity for the lambda = 0.0 the reference hard-codes (dist.py:281); a real
+    // H-minima reconstruction otherwise.  Markers and flood levels come from it, the mask b from the image itself.
+    if (lamb > 0) {
+        I = ws<uint8_t>(c, total);
+        if (!I) return TISEG_ERR_CUDA;
+        TISEG_TRY(h_reconstruction_erosion_dev(c, g, I0, lamb, I));
+    }
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
     TISEG_LAUNCH(c, k_min_candidates, strip_grid(g), TISEG_THREADS, 0, g, I, cand);
     TISEG_TRY(ccl_build(c, g, ImgEqU8Where{I, cand}, 2, par));
@@ -301,7 +311,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
                  markers_out, (g.P % 4 == 0) && aligned16(par, wsl, markers_out));
     // flood inside b, blob by blob
     BlobInfo b;
-    TISEG_TRY(blobs_build(c, g, ImgBelowU8{I, 255}, bpar, brank, b, false));
+    TISEG_TRY(blobs_build(c, g, ImgBelowU8{I0, 255}, bpar, brank, b, false));
     TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
     // arrange_label
     TISEG_TRY(zero(c, nflagged, sizeof(int)));
@@ -328,9 +338,17 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int32_t* i
 
 using namespace tiseg;
 
+extern "C" int tiseg_postproc_dist_lambda(tiseg_ctx* c, const float* dist, int N, int H, int W, int lamb,
+                                          int32_t* inst_out, int32_t* markers_out, int32_t* ws_out);
+
 extern "C" int tiseg_postproc_dist(tiseg_ctx* c, const float* dist, int N, int H, int W, int32_t* inst_out,
                                    int32_t* markers_out, int32_t* ws_out) {
-    if (!c || !dist || !inst_out) { set_error("tiseg_postproc_dist: bad argument"); return TISEG_ERR_ARG; }
+    return tiseg_postproc_dist_lambda(c, dist, N, H, W, 0, inst_out, markers_out, ws_out);
+}
+
+extern "C" int tiseg_postproc_dist_lambda(tiseg_ctx* c, const float* dist, int N, int H, int W, int lamb,
+                                          int32_t* inst_out, int32_t* markers_out, int32_t* ws_out) {
+    if (!c || !dist || !inst_out || lamb < 0 || lamb > 255) { set_error("tiseg_postproc_dist: bad argument (0 <= lambda <= 255)"); return TISEG_ERR_ARG; }
     TISEG_TRY(check_geom(N, H, W));
     begin_call(c);
     Geom g = make_geom(N, H, W);
@@ -340,6 +358,6 @@ extern "C" int tiseg_postproc_dist(tiseg_ctx* c, const float* dist, int N, int H
     int32_t* d_mk = markers_out ? tiseg::out(c, markers_out, total) : nullptr;
     int32_t* d_ws = ws_out ? tiseg::out(c, ws_out, total) : nullptr;
     if (!d_dist || !d_inst) return TISEG_ERR_CUDA;
-    TISEG_TRY(postproc_dist_dev(c, g, d_dist, d_inst, d_mk, d_ws));
+    TISEG_TRY(postproc_dist_dev(c, g, d_dist, lamb, d_inst, d_mk, d_ws));
     return end_call(c);
 }

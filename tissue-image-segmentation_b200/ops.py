@@ -137,14 +137,17 @@ def watershed(image, markers, mask=None):
     return _unbatch(out, was2d)
 
 
-def postproc_dist(dist, debug=False):
-    """A8.  dist fp32 -> inst int32 (and, with ``debug``, the marker and raw-flood maps)."""
+def postproc_dist(dist, debug=False, lamb=0):
+    """A8.  dist fp32 -> inst int32 (and, with ``debug``, the marker and raw-flood maps).  ``lamb`` is the first
+    argument of ``dynamic_watershed_alias`` (dist.py:114); the reference's test path passes 0.0 (dist.py:281)."""
     x, was2d = batched(as_input(dist, np.float32))
     N, H, W = x.shape
+    if int(lamb) != lamb:
+        raise ValueError("lamb must be an integer number of grey levels")
     inst = empty_like_kind(x, (N, H, W), np.int32)
     mk = empty_like_kind(x, (N, H, W), np.int32) if debug else None
     ws = empty_like_kind(x, (N, H, W), np.int32) if debug else None
-    get_ctx(_dev(x)).call("tiseg_postproc_dist", ptr(x), N, H, W, ptr(inst), ptr(mk), ptr(ws))
+    get_ctx(_dev(x)).call("tiseg_postproc_dist_lambda", ptr(x), N, H, W, int(lamb), ptr(inst), ptr(mk), ptr(ws))
     if debug:
         return _unbatch(inst, was2d), _unbatch(mk, was2d), _unbatch(ws, was2d)
     return _unbatch(inst, was2d)
@@ -286,4 +289,16 @@ def distance_transform_cdt(mask, metric="chessboard"):
     N, H, W = x.shape
     out = empty_like_kind(x, (N, H, W), np.int32)
     get_ctx(_dev(x)).call("tiseg_distance_transform_cdt", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def reconstruction(seed, mask, method="erosion"):
+    """A9.  skimage.morphology.reconstruction(seed, mask, method='erosion') for uint8 images (3x3 footprint)."""
+    if method != "erosion":
+        raise ValueError("only method='erosion' (the one the reference uses, dist.py:56) is implemented")
+    sd, was2d = batched(as_input(seed, np.uint8))
+    mk, _ = batched(as_input(mask, np.uint8))
+    N, H, W = sd.shape
+    out = empty_like_kind(sd, (N, H, W), np.uint8)
+    get_ctx(_dev(sd)).call("tiseg_reconstruction_erosion_u8", ptr(sd), ptr(mk), N, H, W, ptr(out))
     return _unbatch(out, was2d)
