@@ -54,6 +54,18 @@ int tiseg_timing_report(tiseg_ctx* ctx, char* buf, int cap);
 int tiseg_softmax_argmax(tiseg_ctx* ctx, const float* logits, int N, int T, int C, int H, int W,
                          float* prob, uint8_t* cls);
 
+/* ---- the step before A1, fused: window stitch + TTA reverse + softmax + mean + argmax -------------------------
+ * Replaces split_inference's canvas (base.py:255-295), reverse_tta_transform (base.py:365-381) and the softmax /
+ * mean / argmax of A1 with ONE pass that reads each logit once from the tensors the network produced.
+ * logits: per tile, the T variants back to back; variant t was computed on tta_transform(img, rotate_degrees[t],
+ * flips[t]) (flips: 0 none, 1 horizontal, 2 vertical, 3 diagonal) and is either the whole [C, Ht, Wt] output
+ * (window = 0; (Ht, Wt) = (W, H) for 90/270 degrees) or its windows [My*Mx, C, window, window] in the row-major
+ * order split_inference visits them.  tiseg_tta_input_elems gives the elements per tile.  H, W: the original image. */
+long long tiseg_tta_input_elems(int T, int C, int H, int W, const int* rotate_degrees, int window, int overlap);
+int tiseg_softmax_argmax_tta(tiseg_ctx* ctx, const float* logits, int N, int T, int C, int H, int W,
+                             const int* rotate_degrees, const int* flips, int window, int overlap,
+                             float* prob, uint8_t* cls);
+
 /* ---- A5 / A6 / A15: connected-component labelling ---------------------------------------------
  * skimage.measure.label(img, background=bg, connectivity=conn) (unet.py:85, dist.py:107,123,
  * multi_task_unet.py:101, inst_metrics.py:12-13,142-143) and scipy.ndimage.label (hovernet.py:296,358;

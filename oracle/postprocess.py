@@ -83,6 +83,40 @@ def softmax_tta_mean(logit_list):
     return (acc / np.float32(len(logit_list))).astype(np.float32)
 
 
+def split_stitch(patches, H, W, window, overlap):
+    """base.py:255-295 ``split_inference`` with the network replaced by its outputs: ``patches`` [M, C, window,
+    window] in the order the double loop visits the windows.  -> [C, H, W]."""
+    st = window - overlap
+    pad_h = st - (H - window) % st if H - window > 0 else window - H
+    pad_w = st - (W - window) % st if W - window > 0 else window - W
+    H1, W1 = pad_h + H, pad_w + W
+    C = patches.shape[1]
+    canvas = np.zeros((C, H1, W1), patches.dtype)
+    k = 0
+    for i in range(0, H1 - overlap, st):
+        r_s = i + overlap // 2 if i > 0 else 0
+        r_e = i + window - overlap // 2 if i + window < H1 else H1
+        for j in range(0, W1 - overlap, st):
+            c_s = j + overlap // 2 if j > 0 else 0
+            c_e = j + window - overlap // 2 if j + window < W1 else W1
+            canvas[:, r_s:r_e, c_s:c_e] = patches[k][:, r_s - i:r_e - i, c_s - j:c_e - j]
+            k += 1
+    assert k == len(patches), (k, len(patches))
+    return canvas[:, (H1 - H) // 2:(H1 - H) // 2 + H, (W1 - W) // 2:(W1 - W) // 2 + W]
+
+
+def reverse_tta_transform(x, rotate_degree, flip_direction):
+    """base.py:365-381 on a [C, H, W] array (numpy's rot90 / flip are torch's)."""
+    k = 4 - (rotate_degree // 90) % 4
+    if flip_direction == "horizontal":
+        x = np.flip(x, axis=-1)
+    if flip_direction == "vertical":
+        x = np.flip(x, axis=-2)
+    if flip_direction == "diagonal":
+        x = np.flip(x, axis=(-2, -1))
+    return np.ascontiguousarray(np.rot90(x, k=k, axes=(-2, -1)))
+
+
 def argmax_classes(prob):
     """``sem_logit.argmax(dim=1)``: first maximum wins."""
     return np.argmax(prob, axis=0).astype(np.int64)

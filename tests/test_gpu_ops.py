@@ -424,3 +424,41 @@ def test_postproc_dist_lambda(lamb):
     d = np.clip(t["dist_logit"], 0, 255).astype("int32")
     want = opp.dist_dynamic_watershed(d, float(lamb), 0.5, literal=False)
     _diff(ops.postproc_dist(t["dist_logit"], lamb=lamb), want, "dist inst lambda=%d" % lamb)
+
+
+# --------------------------------------------------------------------------- window stitch + TTA reverse fused into K1
+@pytest.mark.parametrize("H,W,window,overlap", [(40, 52, 0, 0), (100, 131, 0, 0), (100, 131, 40, 16), (64, 64, 64, 20),
+                                                (30, 45, 40, 10), (131, 100, 48, 17)])
+def test_softmax_argmax_tta_windows(H, W, window, overlap):
+    rng = np.random.default_rng(H * 1000 + W + window)
+    rots, flips = [0, 0, 0, 0, 90, 90, 90, 90], ["none", "horizontal", "vertical", "diagonal"] * 2   # shipped TTA: 8 variants
+    C, N = 3, 2
+    variants, want = [], []
+    for n in range(N):
+        rev = []
+        for t, (r, f) in enumerate(zip(rots, flips)):
+            Ht, Wt = (W, H) if (r // 90) % 2 else (H, W)
+            if window == 0:
+                x = rng.standard_normal((C, Ht, Wt)).astype(np.float32) * 3
+                full = x
+            else:
+                st = window - overlap
+                pad_h = st - (Ht - window) % st if Ht - window > 0 else window - Ht
+                pad_w = st - (Wt - window) % st if Wt - window > 0 else window - Wt
+                M = ((Ht + pad_h - window) // st + 1) * ((Wt + pad_w - window) // st + 1)
+                x = rng.standard_normal((M, C, window, window)).astype(np.float32) * 3
+                full = opp.split_stitch(x, Ht, Wt, window, overlap)
+            if n == 0:
+                variants.append([x])
+            else:
+                variants[t].append(x)
+            rev.append(opp.reverse_tta_transform(full, r, f))
+        want.append(opp.softmax_tta_mean(rev))
+    variants = [np.stack(v) for v in variants]
+    cls, prob = ops.softmax_argmax_tta(variants, rots, flips, (H, W), window, overlap, want_prob=True)
+    want = np.stack(want)
+    assert prob.shape == want.shape
+    np.testing.assert_allclose(prob, want, rtol=1e-5, atol=1e-7)
+    top2 = np.sort(want, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+    assert np.array_equal(cls[clear], want.argmax(1).astype(np.uint8)[clear])

@@ -26,6 +26,8 @@ SIGNATURES = {
     "tiseg_timing_enable": [_vp, _i],
     "tiseg_timing_report": [_vp, ctypes.c_char_p, _i],
     "tiseg_softmax_argmax": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "tiseg_tta_input_elems": [_i, _i, _i, _i, _vp, _i, _i],
+    "tiseg_softmax_argmax_tta": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "tiseg_label": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_label_u8": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_re_instance": [_vp, _vp, _i, _i, _i, _vp, _vp],
@@ -51,7 +53,7 @@ SIGNATURES = {
     "tiseg_distance_transform_edt": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_distance_transform_cdt": [_vp, _vp, _i, _i, _i, _vp],
 }
-_RESTYPE = {"tiseg_last_error": ctypes.c_char_p, "tiseg_launch_count": _ll}
+_RESTYPE = {"tiseg_last_error": ctypes.c_char_p, "tiseg_launch_count": _ll, "tiseg_tta_input_elems": _ll}
 
 _lib = None
 _lock = threading.Lock()

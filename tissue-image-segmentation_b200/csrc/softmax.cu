@@ -103,9 +103,144 @@ int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, in
     return TISEG_OK;
 }
 
+// ---- the step before K1, fused into its load indexing ------------------------------------------
+// The reference stitches the half-overlap window outputs of every TTA variant into a canvas (base.py:255-295), undoes
+// the variant's rotation / flip (base.py:365-381), applies softmax and averages (base.py:321-336).  Those are pure
+// re-indexings, so this kernel reads every logit ONCE, straight from the window tensors:
+//   original pixel (y, x)  ->  pixel of the variant's (transformed) image, by the inverse of reverse_tta_transform
+//                          ->  window (my, mx) whose kept centre region holds it, and the position inside the window.
+// window == 0 means "whole" inference: the variant tensor is the full transformed image.
+struct TtaPlan {
+    int T;
+    int rot[16];                // rotate_degree // 90 of the forward transform (0..3)
+    int flip[16];               // 0 none, 1 horizontal, 2 vertical, 3 diagonal
+    long long off[16];          // element offset of variant t inside one tile's block of the input
+    long long tile_stride;      // elements per tile
+    int window, overlap;
+};
+
+__device__ __forceinline__ void tta_source(const TtaPlan& p, int t, int H, int W, int y, int x, int& sy, int& sx, int& Ht,
+                                           int& Wt) {
+    // Y = rot90(flip(X), k), k = (4 - rot) % 4, with torch.rot90 counter-clockwise: rot90(Z, 1)[i, j] = Z[j, Wz - 1 - i]
+    const int k = (4 - p.rot[t]) & 3;
+    Ht = (k & 1) ? W : H; Wt = (k & 1) ? H : W;       // shape of Z (and of X)
+    int a, b;
+    if (k == 0) { a = y; b = x; }
+    else if (k == 1) { a = x; b = Wt - 1 - y; }
+    else if (k == 2) { a = Ht - 1 - y; b = Wt - 1 - x; }
+    else { a = Ht - 1 - x; b = y; }
+    const int f = p.flip[t];
+    sy = (f & 2) ? Ht - 1 - a : a;
+    sx = (f & 1) ? Wt - 1 - b : b;
+}
+
+// element index (without the channel term) of pixel (sy, sx) of a variant image of shape (Ht, Wt): whole tensor or windows
+__device__ __forceinline__ long long window_source(const TtaPlan& p, int C, int Ht, int Wt, int sy, int sx, long long& cstride) {
+    if (p.window == 0) { cstride = (long long)Ht * Wt; return (long long)sy * Wt + sx; }
+    const int win = p.window, ov = p.overlap, st = win - ov;
+    const int pad_h = Ht - win > 0 ? st - (Ht - win) % st : win - Ht;          // base.py:264-273
+    const int pad_w = Wt - win > 0 ? st - (Wt - win) % st : win - Wt;
+    const int H1 = Ht + pad_h, W1 = Wt + pad_w;
+    const int My = (H1 - win) / st + 1, Mx = (W1 - win) / st + 1;
+    const int Y = sy + (H1 - Ht) / 2, X = sx + (W1 - Wt) / 2;                    // crop of base.py:294
+    int my = (Y - ov / 2) / st; my = my < 0 ? 0 : (my > My - 1 ? My - 1 : my);
+    int mx = (X - ov / 2) / st; mx = mx < 0 ? 0 : (mx > Mx - 1 ? Mx - 1 : mx);
+    if (Y < ov / 2) my = 0;
+    if (X < ov / 2) mx = 0;
+    cstride = (long long)win * win;
+    return ((long long)(my * Mx + mx) * C) * win * win + (long long)(Y - my * st) * win + (X - mx * st);
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_softmax_argmax_tta(Geom g, const float* __restrict__ in, TtaPlan plan, int C, float* __restrict__ prob,
+                     uint8_t* __restrict__ cls) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    float acc[CMAX];
+    for (int t = 0; t < plan.T; ++t) {
+        int sy, sx, Ht, Wt;
+        tta_source(plan, t, g.H, g.W, px.y, px.x, sy, sx, Ht, Wt);
+        long long cs;
+        const float* src = in + (long long)px.n * plan.tile_stride + plan.off[t] + window_source(plan, C, Ht, Wt, sy, sx, cs);
+        float xv[CMAX], m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) if (c < C) { xv[c] = src[c * cs]; m = fmaxf(m, xv[c]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) if (c < C) { xv[c] = expf(xv[c] - m); sum = sum + xv[c]; }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) if (c < C) acc[c] = (t == 0) ? xv[c] / sum : acc[c] + xv[c] / sum;
+    }
+    const float tf = (float)plan.T;
+    int best = 0;
+    float bv = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+            const float pv = acc[c] / tf;
+            if (pv > bv) { bv = pv; best = c; }
+            if (prob) prob[((long long)px.n * C + c) * g.P + px.idx] = pv;
+        }
+    if (cls) cls[px.base + px.idx] = (uint8_t)best;
+}
+
 }  // namespace tiseg
 
 using namespace tiseg;
+
+// elements of one variant: the whole transformed image, or all its windows
+static long long tta_variant_elems(int C, int Ht, int Wt, int window, int overlap) {
+    if (window == 0) return (long long)C * Ht * Wt;
+    const int st = window - overlap;
+    const int pad_h = Ht - window > 0 ? st - (Ht - window) % st : window - Ht;
+    const int pad_w = Wt - window > 0 ? st - (Wt - window) % st : window - Wt;
+    const int My = (Ht + pad_h - window) / st + 1, Mx = (Wt + pad_w - window) / st + 1;
+    return (long long)My * Mx * C * window * window;
+}
+
+extern "C" long long tiseg_tta_input_elems(int T, int C, int H, int W, const int* rotate_degrees, int window, int overlap) {
+    long long n = 0;
+    for (int t = 0; t < T; ++t) {
+        const bool odd = ((rotate_degrees[t] / 90) & 1) != 0;
+        n += tta_variant_elems(C, odd ? W : H, odd ? H : W, window, overlap);
+    }
+    return n;
+}
+
+extern "C" int tiseg_softmax_argmax_tta(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W,
+                                        const int* rotate_degrees, const int* flips, int window, int overlap,
+                                        float* prob, uint8_t* cls) {
+    if (!c || !logits || !rotate_degrees || !flips || T <= 0 || T > 16 || C <= 0 || C > 16 || (!prob && !cls) ||
+        window < 0 || (window > 0 && (overlap < 0 || overlap >= window))) {
+        set_error("tiseg_softmax_argmax_tta: bad argument (1 <= T, C <= 16, 0 <= overlap < window)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N, H, W));
+    TtaPlan plan;
+    plan.T = T; plan.window = window; plan.overlap = overlap;
+    long long off = 0;
+    for (int t = 0; t < T; ++t) {
+        if (rotate_degrees[t] % 90 != 0 || flips[t] < 0 || flips[t] > 3) { set_error("tiseg_softmax_argmax_tta: bad transform"); return TISEG_ERR_ARG; }
+        plan.rot[t] = ((rotate_degrees[t] / 90) % 4 + 4) % 4;
+        plan.flip[t] = flips[t];
+        plan.off[t] = off;
+        const bool odd = (plan.rot[t] & 1) != 0;
+        off += tta_variant_elems(C, odd ? W : H, odd ? H : W, window, overlap);
+    }
+    plan.tile_stride = off;
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const float* d_in = in(c, logits, (size_t)N * (size_t)off);
+    float* d_prob = prob ? tiseg::out(c, prob, total * C) : nullptr;
+    uint8_t* d_cls = cls ? tiseg::out(c, cls, total) : nullptr;
+    if (!d_in) return TISEG_ERR_CUDA;
+    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax_tta<4>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax_tta<8>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    else TISEG_LAUNCH(c, k_softmax_argmax_tta<16>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    return end_call(c);
+}
 
 extern "C" int tiseg_softmax_argmax(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W,
                                     float* prob, uint8_t* cls) {

@@ -302,3 +302,39 @@ def reconstruction(seed, mask, method="erosion"):
     out = empty_like_kind(sd, (N, H, W), np.uint8)
     get_ctx(_dev(sd)).call("tiseg_reconstruction_erosion_u8", ptr(sd), ptr(mk), N, H, W, ptr(out))
     return _unbatch(out, was2d)
+
+
+_FLIPS = {"none": 0, None: 0, "horizontal": 1, "vertical": 2, "diagonal": 3}
+
+
+def softmax_argmax_tta(variants, rotate_degrees, flip_directions, ori_hw, window=0, overlap=0, want_prob=False):
+    """Window stitch + TTA reverse + softmax + mean + argmax in one pass (base.py:255-295, 321-339, 365-381).
+
+    ``variants``: one array per TTA variant, in the reference's loop order (rotate_degrees outer, flip_directions
+    inner; pass the flattened lists), each the raw network output on the TRANSFORMED image: [N, C, Ht, Wt] for whole
+    inference (``window = 0``) or [N, M, C, window, window] for split inference.  ``ori_hw`` = (H, W) of the image.
+    Returns the class map [N, H, W] uint8 (and the mean probabilities [N, C, H, W] with ``want_prob``)."""
+    import ctypes
+    from . import _lib
+    T = len(variants)
+    if not (T == len(rotate_degrees) == len(flip_directions)):
+        raise ValueError("one rotate_degree and one flip_direction per variant")
+    H, W = int(ori_hw[0]), int(ori_hw[1])
+    vs = [as_input(v, np.float32) for v in variants]
+    N = int(vs[0].shape[0])
+    C = int(vs[0].shape[1] if window == 0 else vs[0].shape[2])
+    rots = (ctypes.c_int * T)(*[int(r) for r in rotate_degrees])
+    flips = (ctypes.c_int * T)(*[_FLIPS[f] for f in flip_directions])
+    per_tile = int(_lib.load().tiseg_tta_input_elems(T, C, H, W, rots, int(window), int(overlap)))
+    if sum(int(np.prod(v.shape[1:])) for v in vs) != per_tile:
+        raise ValueError("variant shapes do not match the transforms / window geometry")
+    if _lib_is_torch(vs[0]):
+        import torch
+        packed = torch.cat([v.reshape(N, -1) for v in vs], dim=1).contiguous()
+    else:
+        packed = np.ascontiguousarray(np.concatenate([v.reshape(N, -1) for v in vs], axis=1))
+    cls = empty_like_kind(packed, (N, H, W), np.uint8)
+    prob = empty_like_kind(packed, (N, C, H, W), np.float32) if want_prob else None
+    get_ctx(_dev(packed)).call("tiseg_softmax_argmax_tta", ptr(packed), N, T, C, H, W, rots, flips, int(window),
+                               int(overlap), ptr(prob), ptr(cls))
+    return (cls, prob) if want_prob else cls
