@@ -181,6 +181,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"           # the version banner goes to stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=dev)
     import tiseg_b200  # noqa: F401
     from tiseg_b200 import _lib, ops
