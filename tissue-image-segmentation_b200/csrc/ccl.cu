@@ -37,31 +37,31 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par,
     }
 }
 
-// one block (32 warps) per tile.  Phase 1: a warp per row sums the popcounts of the row's words (one coalesced
-// request per 32 segments).  Phase 2: exclusive block scan over the rows.
+// selected pixels per row: one warp per row sums the popcounts of the row's words (one coalesced request per 32 segments)
+template <bool LISTED>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_rank_rowtot(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rowpre) {
+    const int y = blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (y >= g.H) return;
+    FOR_TILES(LISTED, g, n) {
+        const unsigned* b = bits + ((long long)n * g.H + y) * g.SEG;
+        int v = 0;
+        for (int k = lane; k < g.SEG; k += 32) v += __popc(b[k]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) rowpre[(long long)n * g.H + y] = v;
+    }
+}
+
+// one block per tile: exclusive scan of the row totals in place.
 // rowpre[n, y] = selected pixels in the rows above y; counts[n] = total.
 template <bool LISTED>
-__global__ void __launch_bounds__(1024) k_rank_rowscan(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rowpre, int* counts) {
+__global__ void __launch_bounds__(1024) k_rank_rowscan(Geom g, int* __restrict__ rowpre, int* counts) {
     __shared__ int wsum[32];
     __shared__ int carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FOR_TILES_OF(LISTED, g, (int)blockIdx.x, n) {
-    const unsigned* b = bits + (long long)n * g.H * g.SEG;
     int* rp = rowpre + (long long)n * g.H;
-    for (int y0 = warp * 8; y0 < g.H; y0 += 32 * 8) {       // eight rows per warp step: eight requests in flight
-        int v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = 0;
-            if (y0 + j < g.H) for (int k = lane; k < g.SEG; k += 32) v[j] += __popc(b[(long long)(y0 + j) * g.SEG + k]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-#pragma unroll
-            for (int d = 16; d; d >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], d);
-            if (lane == 0 && y0 + j < g.H) rp[y0 + j] = v[j];
-        }
-    }
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < g.H; base += 1024) {
@@ -171,7 +171,9 @@ int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
 int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts) {
     int* rowpre = ws<int>(c, (size_t)g.N * g.H);
     if (!rowpre) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH_TILES(c, k_rank_rowscan, g, grid_tiles(g), 1024, 0, g, bits, rowpre, counts);
+    TISEG_LAUNCH_TILES(c, k_rank_rowtot, g, dim3((g.H + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK, grid_tiles(g)), TISEG_THREADS, 0,
+                       g, bits, rowpre);
+    TISEG_LAUNCH_TILES(c, k_rank_rowscan, g, grid_tiles(g), 1024, 0, g, rowpre, counts);
     TISEG_LAUNCH_TILES(c, k_rank_place_bits, g, dim3((g.H + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK, grid_tiles(g)), TISEG_THREADS, 0,
                  g, bits, rowpre, rank);
     return TISEG_OK;

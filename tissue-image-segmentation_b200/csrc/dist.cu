@@ -40,72 +40,128 @@ k_dist_prep(long long total, const float* __restrict__ dist, uint8_t* __restrict
 // equal-valued pixel outside C — which must be a non-candidate (a candidate would have joined C).  Hence:
 // minimum plateaus = candidate components without an "equal-valued non-candidate neighbour" flag.  On a distance map
 // the candidates are the few pixels around each nucleus centre, so the labelling pass skips almost every row.
+// One thread = four horizontally adjacent pixels (one 32-bit load per row); threads whose four pixels are all
+// background (the common case) stop after that single load.
+__device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ row, int x, int W, unsigned oob, bool vec) {
+    if (vec) return *reinterpret_cast<const unsigned*>(row + x);
+    unsigned r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r |= (x + k < W ? (unsigned)row[x + k] : oob) << (8 * k);
+    return r;
+}
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_min_candidates(Geom g, const uint8_t* __restrict__ I, uint8_t* __restrict__ cand) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    uint8_t c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
-    strip_load_c<uint8_t>(g, s, I + s.base, (uint8_t)255, c);          // out-of-image taps can never be lower
-    bool any = false;
+k_min_candidates(Geom g, const uint8_t* __restrict__ I, uint8_t* __restrict__ cand, bool vec) {
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
+    const uint8_t* It = I + (long long)n * g.P;
+    uint8_t* out = cand + (long long)n * g.P + (long long)y * g.W + x;
+    const unsigned c = ld_u8x4(It + (long long)y * g.W, x, g.W, 255u, vec);
+    unsigned res = 0;
+    if (c != 0xffffffffu) {
+        // rows y-1, y, y+1, columns x-1 .. x+4; out-of-image taps can never be lower
+        unsigned rows[3]; int lft[3], rgt[3];
 #pragma unroll
-    for (int j = 1; j <= STRIP_R; ++j) any |= c[j] < 255;
-    if (!__ballot_sync(0xffffffffu, any)) {                            // (uniform) a strip of background
-#pragma unroll
-        for (int j = 1; j <= STRIP_R; ++j) {
-            int y = s.y0 + j - 1;
-            if (s.okx && y < g.H) cand[s.base + (long long)y * g.W + s.x] = 0;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            const bool ok = yy >= 0 && yy < g.H;
+            const uint8_t* rp = It + (long long)yy * g.W;
+            rows[dy + 1] = dy == 0 ? c : (ok ? ld_u8x4(rp, x, g.W, 255u, vec) : 0xffffffffu);
+            lft[dy + 1] = (ok && x > 0) ? rp[x - 1] : 255;
+            rgt[dy + 1] = (ok && x + 4 < g.W) ? rp[x + 4] : 255;
         }
-        return;
-    }
-    strip_fill_lr<uint8_t>(g, s, I + s.base, (uint8_t)255, c, l, r);
 #pragma unroll
-    for (int j = 1; j <= STRIP_R; ++j) {
-        int y = s.y0 + j - 1;
-        if (!s.okx || y >= g.H) continue;
-        int v = c[j];
-        int mn = min(min(min((int)l[j - 1], (int)c[j - 1]), min((int)r[j - 1], (int)l[j])),
-                     min(min((int)r[j], (int)l[j + 1]), min((int)c[j + 1], (int)r[j + 1])));
-        cand[s.base + (long long)y * g.W + s.x] = (uint8_t)(v < 255 && mn >= v);
+        for (int k = 0; k < 4; ++k) {
+            const int v = (c >> (8 * k)) & 255;
+            int mn = 255;
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3) {
+                const int a = k == 0 ? lft[r3] : (int)((rows[r3] >> (8 * (k - 1))) & 255);
+                const int m = (int)((rows[r3] >> (8 * k)) & 255);
+                const int z = k == 3 ? rgt[r3] : (int)((rows[r3] >> (8 * (k + 1))) & 255);
+                mn = min(mn, min(a, min(m, z)));
+            }
+            if (v < 255 && mn >= v) res |= 1u << (8 * k);
+        }
+    }
+    if (vec) *reinterpret_cast<unsigned*>(out) = res;
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (x + k < g.W) out[k] = (uint8_t)((res >> (8 * k)) & 255);
     }
 }
 
 // low[root] = 1 if a pixel of the candidate component has an equal-valued neighbour that is not a candidate.
-// Candidates are rare, so only their lanes probe the eight neighbours (straight from L1/L2).
+// Candidates are rare: one 32-bit load tells a thread that its four pixels hold none; only candidate pixels probe
+// their eight neighbours (straight from L1/L2).
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_cand_invalid(Geom g, const uint8_t* __restrict__ I, const uint8_t* __restrict__ cand, const int* __restrict__ par,
-               uint8_t* low) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    uint8_t kc[STRIP_R];
+               uint8_t* low, bool vec) {
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
+    const long long base = (long long)n * g.P;
+    const uint8_t* It = I + base;
+    const uint8_t* Ct = cand + base;
+    const unsigned c = ld_u8x4(Ct + (long long)y * g.W, x, g.W, 0u, vec);
+    if (!c) return;
+    // rows y-1, y, y+1, columns x-1 .. x+4 of the level image and of the candidate mask (out-of-image: level 255,
+    // which never equals a candidate's level)
+    unsigned iv[3], cv[3];
+    int il[3], ir[3], cl[3], cr[3];
 #pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        kc[r] = (s.okx && y < g.H) ? cand[s.base + (long long)y * g.W + s.x] : (uint8_t)0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        const bool ok = yy >= 0 && yy < g.H;
+        const long long ro = (long long)yy * g.W;
+        iv[dy + 1] = ok ? ld_u8x4(It + ro, x, g.W, 255u, vec) : 0xffffffffu;
+        cv[dy + 1] = dy == 0 ? c : (ok ? ld_u8x4(Ct + ro, x, g.W, 1u, vec) : 0x01010101u);
+        il[dy + 1] = (ok && x > 0) ? It[ro + x - 1] : 255;
+        ir[dy + 1] = (ok && x + 4 < g.W) ? It[ro + x + 4] : 255;
+        cl[dy + 1] = (ok && x > 0) ? Ct[ro + x - 1] : 1;
+        cr[dy + 1] = (ok && x + 4 < g.W) ? Ct[ro + x + 4] : 1;
     }
-    const uint8_t* It = I + s.base;
-    const uint8_t* Ct = cand + s.base;
 #pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        if (!kc[r]) continue;
-        const int y = s.y0 + r, x = s.x, idx = y * g.W + x;
-        const int v = It[idx];
+    for (int k = 0; k < 4; ++k) {
+        if (!((c >> (8 * k)) & 255)) continue;
+        const int v = (iv[1] >> (8 * k)) & 255;
         bool bad = false;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dy == 0 && dx == 0) continue;
-                const int yy = y + dy, xx = x + dx;
-                if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
-                const int q = yy * g.W + xx;
-                bad |= It[q] == v && !Ct[q];
-            }
+        for (int r3 = 0; r3 < 3; ++r3) {
+            const int ia = k == 0 ? il[r3] : (int)((iv[r3] >> (8 * (k - 1))) & 255);
+            const int ca = k == 0 ? cl[r3] : (int)((cv[r3] >> (8 * (k - 1))) & 255);
+            const int im = (int)((iv[r3] >> (8 * k)) & 255), cm = (int)((cv[r3] >> (8 * k)) & 255);
+            const int iz = k == 3 ? ir[r3] : (int)((iv[r3] >> (8 * (k + 1))) & 255);
+            const int cz = k == 3 ? cr[r3] : (int)((cv[r3] >> (8 * (k + 1))) & 255);
+            bad |= (ia == v && !ca) || (iz == v && !cz);
+            if (r3 != 1) bad |= im == v && !cm;
         }
         if (bad) {
-            int root = par[s.base + idx];
-            if (!low[s.base + root]) low[s.base + root] = 1;
+            int root = par[base + (long long)y * g.W + x + k];
+            if (!low[base + root]) low[base + root] = 1;
         }
     }
+}
+
+// clear, in the bitmap of the roots that ccl_flatten left, the roots whose component is not a minimum plateau
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_filter_root_bits(Geom g, const uint8_t* __restrict__ low, unsigned* bits) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    unsigned m = bits[(long long)n * words + t];
+    if (!m) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    unsigned keep = m;
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        if (low[(long long)n * g.P + (long long)y * g.W + seg * 32 + b]) keep &= ~(1u << b);
+    }
+    bits[(long long)n * words + t] = keep;
 }
 
 struct SelMinimumRoot {         // roots of the candidate components that are regional-minimum plateaus
@@ -301,11 +357,17 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         TISEG_TRY(h_reconstruction_erosion_dev(c, g, I0, lamb, I));
     }
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
-    TISEG_LAUNCH(c, k_min_candidates, strip_grid(g), TISEG_THREADS, 0, g, I, cand);
+    const bool vec4 = (g.W % 4 == 0) && ((((uintptr_t)I) | ((uintptr_t)cand)) & 3) == 0;
+    const dim3 quad_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_min_candidates, quad_grid, TISEG_THREADS, 0, g, I, cand, vec4);
     TISEG_TRY(ccl_build(c, g, ImgEqU8Where{I, cand}, 2, par));
+    unsigned* rbits = (unsigned*)c->rootblk;          // bitmap of the candidate components' roots (left by the flatten)
+    c->rootblk_par = nullptr;
     TISEG_TRY(zero(c, low, total));
-    TISEG_LAUNCH(c, k_cand_invalid, strip_grid(g), TISEG_THREADS, 0, g, I, cand, par, low);
-    TISEG_TRY(rank_generic(c, g, SelMinimumRoot{par, low}, rank, nmark));
+    TISEG_LAUNCH(c, k_cand_invalid, quad_grid, TISEG_THREADS, 0, g, I, cand, par, low, vec4);
+    TISEG_LAUNCH(c, k_filter_root_bits, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N),
+                 TISEG_THREADS, 0, g, low, rbits);
+    TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
     // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
     TISEG_LAUNCH(c, k_markers_from_plateaus, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, par, low, rank, wsl,
                  markers_out, (g.P % 4 == 0) && aligned16(par, wsl, markers_out));

@@ -18,14 +18,22 @@ __global__ void k_blob_init(BlobInfo b, int W) {
     }
 }
 
+// root[id] = flat index of the blob's first pixel, from the bitmap of the roots (P/32 words instead of the forest)
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_blob_roots(long long P, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b, bool vec) {
-    const long long base = (long long)blockIdx.y * P, i = flat4_index();
-    if (i >= P) return;
-    Pack4<int> p = ld4(par + base, i, P, vec);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (i + k < P && p.v[k] == (int)(i + k)) b.root[(long long)blockIdx.y * b.KS + rank[base + i + k]] = (int)(i + k);
+k_blob_roots(Geom g, const unsigned* __restrict__ bits, const int* __restrict__ rank, BlobInfo b) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    unsigned m = bits[(long long)n * words + t];
+    if (!m) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int idx = y * g.W + seg * 32 + bit;
+        b.root[(long long)n * b.KS + rank[(long long)n * g.P + idx]] = idx;
+    }
 }
 
 // bounding box + area per blob, one set of atomics per in-segment run
@@ -750,9 +758,11 @@ int ws_seed(tiseg_ctx* c, const Geom& g, const int32_t* markers, const int* par,
     return TISEG_OK;
 }
 
-int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, BlobInfo& b, bool want_offsets) {
+int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, const unsigned* root_bits, BlobInfo& b,
+                   bool want_offsets) {
     TISEG_LAUNCH(c, k_blob_init, dim3(8, g.N), 256, 0, b, g.W);
-    TISEG_LAUNCH(c, k_blob_roots, dim3(flat4_grid(g.P), g.N), TISEG_THREADS, 0, (long long)g.P, par, rank, b, (g.P % 4 == 0) && aligned16(par));
+    TISEG_LAUNCH(c, k_blob_roots, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), g.N), TISEG_THREADS, 0,
+                 g, root_bits, rank, b);
     TISEG_LAUNCH(c, k_blob_bbox, strip_grid(g), TISEG_THREADS, 0, g, par, rank, b);
     if (want_offsets) TISEG_LAUNCH(c, k_blob_offsets, g.N, 256, 0, b);
     return TISEG_OK;

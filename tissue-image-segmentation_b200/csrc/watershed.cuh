@@ -42,7 +42,8 @@ int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const in
 // out = markers where the mask forest has a pixel, else 0 (skimage drops markers outside the mask)
 int ws_seed(tiseg_ctx* c, const Geom& g, const int32_t* markers, const int* par, int32_t* out);
 // root / bbox / area (/ offsets) of every blob of a flattened + ranked forest
-int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, BlobInfo& b, bool want_offsets);
+int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, const unsigned* root_bits, BlobInfo& b,
+                   bool want_offsets);
 
 #ifdef __CUDACC__
 
@@ -57,8 +58,9 @@ int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, 
     b.KS = KS; b.count = count;
     if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || (want_offsets && !b.off)) return TISEG_ERR_CUDA;
     TISEG_TRY(ccl_build(c, g, mask, conn, par));
+    const unsigned* root_bits = (const unsigned*)c->rootblk;      // left by the flatten; rank_roots consumes the same bitmap
     TISEG_TRY(rank_roots(c, g, par, rank, count));
-    return blobs_describe(c, g, par, rank, b, want_offsets);
+    return blobs_describe(c, g, par, rank, root_bits, b, want_offsets);
 }
 #endif
 
