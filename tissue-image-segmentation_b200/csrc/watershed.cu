@@ -117,7 +117,7 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
 //    seeds into their buckets in raster order (match_any), then LANE s FLOODS SLOT s: up to SLOTS independent floods
 //    advance per warp instruction.  Buckets are indexed by (level mod 32): a blob qualifies if its levels span < 32
 //    values (a distance map inside a nucleus does); the head and tail of the current level live in registers.
-//    Default geometry: 8 warps x 5376-cell arenas x 16 slots (variants behind TISEG_FLOOD_VARIANT for experiments,
+//    Default geometry: 10 warps x 4096-cell arenas x 16 slots (variants behind TISEG_FLOOD_VARIANT for experiments,
 //    including QUAD floods where four lanes probe the four neighbours of one flood).
 //  * general floods — framed boxes beyond the arena, or level spans >= 32: one blob per CTA at a time, staged by all
 //    warps into one 45056-cell slice with all 256 buckets.  The first sm_count/12 CTAs start with this list so the
@@ -334,13 +334,17 @@ __device__ __forceinline__ void quad_flood(int lane, bool active, int wp, int sm
 }
 
 // The ordered flood of one staged blob by ONE lane (the lanes of a warp flood different slots side by side).  The
-// head and tail of the current level's bucket live in registers; the four neighbours' probes and the tails of the
-// buckets they will be pushed to are loaded before any update.
+// head and tail of the current level's bucket live in registers.  A pop probes the four neighbours' labels; only the
+// unlabelled ones (about one per pop on average) run the push body — a loop over the set bits rather than four
+// predicated copies, which is what keeps the dependent instruction chain of a step short.
 template <class Bucket>
 __device__ __forceinline__ int lane_flood(int wp, int smin, int lmax, unsigned short* lab, unsigned short* nxs,
                                           const unsigned char* lvl, unsigned short* head, unsigned short* tail, Bucket B) {
     int cur = smin, pops = 0;
     unsigned hcur = head[B(cur)], tcur = tail[B(cur)];
+    // neighbour offsets up, left, right, down as four signed 16-bit fields
+    const unsigned long long offs = ((unsigned long long)(unsigned short)(-wp)) | ((unsigned long long)(unsigned short)(-1) << 16) |
+                                    (1ull << 32) | ((unsigned long long)(unsigned short)wp << 48);
     for (;;) {
         if (hcur == WS_END) {
             head[B(cur)] = (unsigned short)WS_END; tail[B(cur)] = (unsigned short)WS_END;
@@ -350,32 +354,26 @@ __device__ __forceinline__ int lane_flood(int wp, int smin, int lmax, unsigned s
         }
         ++pops;
         const int pix = (int)hcur;
-        const int nb[4] = {pix - wp, pix - 1, pix + 1, pix + wp};      // up, left, right, down
-        unsigned ln[4], tl[4];
-        int vn[4];
-        hcur = nxs[pix];
+        const unsigned l0 = lab[pix - wp], l1 = lab[pix - 1], l2 = lab[pix + 1], l3 = lab[pix + wp];
         const unsigned short L = lab[pix];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { ln[k] = lab[nb[k]]; vn[k] = lvl[nb[k]]; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tl[k] = (ln[k] == WS_UNLAB && vn[k] != cur) ? tail[B(vn[k])] : WS_END;
+        hcur = nxs[pix];
+        unsigned m = (l0 == WS_UNLAB ? 1u : 0u) | (l1 == WS_UNLAB ? 2u : 0u) | (l2 == WS_UNLAB ? 4u : 0u) | (l3 == WS_UNLAB ? 8u : 0u);
         int newcur = cur;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (ln[k] == WS_UNLAB) {
-                lab[nb[k]] = L;                                       // labelled at push time
-                nxs[nb[k]] = (unsigned short)WS_END;
-                if (vn[k] == cur) {
-                    if (hcur == WS_END) hcur = (unsigned)nb[k]; else nxs[tcur] = (unsigned short)nb[k];
-                    tcur = (unsigned)nb[k];
-                } else {
-                    unsigned t = tl[k];
-#pragma unroll
-                    for (int q = 0; q < k; ++q) if (ln[q] == WS_UNLAB && vn[q] == vn[k]) t = (unsigned)nb[q];
-                    if (t == WS_END) head[B(vn[k])] = (unsigned short)nb[k]; else nxs[t] = (unsigned short)nb[k];
-                    tail[B(vn[k])] = (unsigned short)nb[k];
-                    newcur = min(newcur, vn[k]);
-                }
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int nb = pix + (int)(short)(offs >> (16 * k));
+            const int v = lvl[nb];
+            lab[nb] = L;                                          // labelled at push time
+            nxs[nb] = (unsigned short)WS_END;
+            if (v == cur) {
+                if (hcur == WS_END) hcur = (unsigned)nb; else nxs[tcur] = (unsigned short)nb;
+                tcur = (unsigned)nb;
+            } else {
+                const unsigned t = tail[B(v)];                    // (sees the push of an earlier neighbour to the same level)
+                if (t == WS_END) head[B(v)] = (unsigned short)nb; else nxs[t] = (unsigned short)nb;
+                tail[B(v)] = (unsigned short)nb;
+                newcur = min(newcur, v);
             }
         }
         if (newcur < cur) {           // a lower level appeared: park the current bucket and descend
@@ -550,7 +548,7 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
         return;
     }
     const int ngen = wk.ngen[0];
-    if ((int)blockIdx.x < gen_first && ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    if ((int)blockIdx.x < min(gen_first, ngen) && ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
     {
         __syncthreads();
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -792,7 +790,7 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
         TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
-    const int gen_first = c->sm_count >= 64 ? c->sm_count / 12 : 1;
+    const int gen_first = c->sm_count >= 8 ? c->sm_count / 4 : 1;     // at most this many CTAs, one per listed blob
     long long* prof = nullptr;
     if (debug) {
         prof = ws<long long>(c, (size_t)c->sm_count * WARPS * 5);
@@ -846,7 +844,10 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
         case 1: return flood_launch<12, 3584, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
         case 2: return flood_launch<16, 2688, 8, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
         case 3: return flood_launch<8, 5376, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        default: return flood_launch<8, 5376, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 5: return flood_launch<12, 3584, 8, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 6: return flood_launch<9, 4608, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 7: return flood_launch<8, 5376, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        default: return flood_launch<10, 4096, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
     }
 }
 
