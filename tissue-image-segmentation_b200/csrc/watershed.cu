@@ -191,9 +191,10 @@ __device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulh
 
 // Copy the framed box of a blob into shared memory: lab = own index (seed), UNLAB (in the blob), NOTIN; lvl = level.
 // `tid`/`nthr`: the cooperating threads (a warp or a CTA); eight cells per thread are loaded before any is used.
-__device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const uint8_t* __restrict__ I,
+template <class LT>
+__device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const LT* __restrict__ I,
                                            const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
-                                           int y0, int x0, int w, int h, unsigned short* lab, unsigned char* lvl) {
+                                           int y0, int x0, int w, int h, unsigned short* lab, LT* lvl) {
     const int wp = w + 2, cells = wp * (h + 2);
     const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
     for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
@@ -207,7 +208,7 @@ __device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const uint8
             gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
         }
         int tpv[8], ov[8];
-        unsigned char iv[8];
+        LT iv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
 #pragma unroll
@@ -224,11 +225,12 @@ __device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const uint8
 
 // One warp links the seeds of a staged blob into their buckets in raster order (32 cells per step, the seeds of one
 // level inside a step chained with match_any) and returns the level range of the blob and the lowest seed level.
-template <class Bucket>
+#define WS_LVL_NONE 0x10000        // above every level (uint8 or ranked uint16)
+template <class LT, class Bucket>
 __device__ __forceinline__ void link_seeds(int lane, int cells, const unsigned short* lab, unsigned short* nxs,
-                                           const unsigned char* lvl, unsigned short* head, unsigned short* tail,
+                                           const LT* lvl, unsigned short* head, unsigned short* tail,
                                            Bucket B, int& vmin, int& vmax, int& vsmin) {
-    vmin = 256; vmax = -1; vsmin = 256;
+    vmin = WS_LVL_NONE; vmax = -1; vsmin = WS_LVL_NONE;
     for (int j0 = 0; j0 < cells; j0 += 32) {
         const int j = j0 + lane;
         unsigned L = WS_NOTIN;
@@ -237,7 +239,7 @@ __device__ __forceinline__ void link_seeds(int lane, int cells, const unsigned s
         const bool seed = L == (unsigned)j, inblob = L != WS_NOTIN;
         if (inblob) { vmin = min(vmin, v); vmax = max(vmax, v); }
         if (__ballot_sync(FULL, seed)) {
-            const unsigned peers = __match_any_sync(FULL, seed ? v : (0x100 | lane));
+            const unsigned peers = __match_any_sync(FULL, seed ? v : (WS_LVL_NONE | lane));
             const unsigned below = peers & ((1u << lane) - 1u), above = lane == 31 ? 0u : (peers >> (lane + 1));
             unsigned t = WS_END;
             if (seed) {
@@ -337,9 +339,9 @@ __device__ __forceinline__ void quad_flood(int lane, bool active, int wp, int sm
 // head and tail of the current level's bucket live in registers.  A pop probes the four neighbours' labels; only the
 // unlabelled ones (about one per pop on average) run the push body — a loop over the set bits rather than four
 // predicated copies, which is what keeps the dependent instruction chain of a step short.
-template <class Bucket>
+template <class LT, class Bucket>
 __device__ __forceinline__ int lane_flood(int wp, int smin, int lmax, unsigned short* lab, unsigned short* nxs,
-                                          const unsigned char* lvl, unsigned short* head, unsigned short* tail, Bucket B) {
+                                          const LT* lvl, unsigned short* head, unsigned short* tail, Bucket B) {
     int cur = smin, pops = 0;
     unsigned hcur = head[B(cur)], tcur = tail[B(cur)];
     // neighbour offsets up, left, right, down as four signed 16-bit fields
@@ -591,7 +593,7 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
                     stage_copy(lane, 32, W, image + base, par + base, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
                 }
                 __syncwarp();
-                int lmin = 256, lmax = -1, smin = 256;        // of slot `lane`
+                int lmin = WS_LVL_NONE, lmax = -1, smin = WS_LVL_NONE;        // of slot `lane`
                 for (int s = 0; s < m; ++s) {
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     int vmin, vmax, vsmin;
@@ -643,6 +645,260 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
     if (ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
 }
 
+// ---- fp64 values, fast path: per-blob dense ranks + the same bucket flood ---------------------------------------------
+// The (value, age) order of the flood only compares values INSIDE one blob, so the fp64 image can be replaced, blob
+// by blob, by the dense rank of each pixel's value among the blob's distinct values (equal doubles -> equal rank):
+// the flood then runs on small integers with FIFO buckets in shared memory exactly like the uint8 case, instead of
+// a binary heap in global memory.  Ranking = one bitonic sort of the blob's values in shared memory (k_rank_blobs),
+// a flag-and-scan for the distinct values, and a binary search per pixel.  Blobs whose framed box exceeds WR_GEN_CAP
+// cells or whose area exceeds WR_SORT_MAX keep the heap flood (k_ws_flood_f64).
+#define WR_SORT_SMALL 1024        // values sorted by a 128-thread CTA
+#define WR_SORT_MAX 16384         // values sorted by a 1024-thread CTA
+#define WR_GEN_CAP 22528          // cells of the single-blob slice of the ranked general path (10 B per cell)
+
+__device__ __forceinline__ bool blob_is_huge(const BlobInfo& b, long long ko, int bid, int W) {
+    return blob_cells(b, ko, bid, W) > WR_GEN_CAP || b.area[ko + bid] > WR_SORT_MAX;
+}
+
+// blob index -> (tile, id): prefix[n] = blobs in the tiles before n (prefix[N] = total)
+__global__ void k_blob_prefix(const int* __restrict__ count, int N, int* prefix) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int n = 0; n < N; ++n) { prefix[n] = acc; acc += count[n]; }
+        prefix[N] = acc;
+    }
+}
+
+// One CTA per blob (persistent over all blobs of the batch); LARGE = false takes areas <= WR_SORT_SMALL, true the rest
+// up to WR_SORT_MAX.  level[pixel] = dense rank of image[pixel] among the blob's values.
+template <bool LARGE>
+__global__ void __launch_bounds__(LARGE ? 1024 : 128)
+k_rank_blobs(Geom g, const double* __restrict__ image, const int* __restrict__ par, BlobInfo b, const int* __restrict__ prefix,
+             unsigned short* __restrict__ level) {
+    extern __shared__ __align__(16) unsigned char rk_smem[];
+    constexpr int CAP = LARGE ? WR_SORT_MAX : WR_SORT_SMALL;
+    double* val = reinterpret_cast<double*>(rk_smem);                    // [CAP] sorted values
+    unsigned short* rnk = reinterpret_cast<unsigned short*>(val + CAP);  // [CAP] dense rank of sorted position
+    __shared__ int s_cnt, s_carry;
+    const int N = g.N, W = g.W, total = prefix[N];
+    for (int bi = blockIdx.x; bi < total; bi += gridDim.x) {
+        int n = 0;                                         // tile of blob bi (N is small: linear search)
+        while (n + 1 < N && prefix[n + 1] <= bi) ++n;
+        const int bid = bi - prefix[n] + 1;
+        const long long ko = (long long)n * b.KS, base = (long long)n * g.P;
+        const int area = b.area[ko + bid];
+        if (LARGE ? (area <= WR_SORT_SMALL || blob_is_huge(b, ko, bid, W)) : (area > WR_SORT_SMALL)) continue;   // uniform
+        const int root = b.root[ko + bid];
+        const int y0 = root / W, x0 = b.xmin[ko + bid], w = b.xmax[ko + bid] - x0 + 1, h = b.ymax[ko + bid] - y0 + 1;
+        const int box = w * h;
+        const unsigned magic = 0xFFFFFFFFu / (unsigned)w + 1u;
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        // gather the blob's values (order irrelevant)
+        for (int j = threadIdx.x; j < box; j += blockDim.x) {
+            const int ly = fdiv(j, magic), lx = j - ly * w;
+            const int gi = (y0 + ly) * W + x0 + lx;
+            if (par[base + gi] == root) val[atomicAdd(&s_cnt, 1)] = image[base + gi];
+        }
+        __syncthreads();
+        const int cnt = s_cnt;                             // == area
+        int n2 = 1;
+        while (n2 < cnt) n2 <<= 1;
+        for (int j = cnt + threadIdx.x; j < n2; j += blockDim.x) val[j] = INFINITY;
+        __syncthreads();
+        // bitonic sort, ascending
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int d = k >> 1; d > 0; d >>= 1) {
+                for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                    const int ixj = i ^ d;
+                    if (ixj > i) {
+                        const double a = val[i], c = val[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > c) == up) { val[i] = c; val[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // dense ranks of the sorted positions: inclusive scan of "differs from the previous value", chunk by chunk
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int c0 = 0; c0 < cnt; c0 += blockDim.x) {
+            const int i = c0 + threadIdx.x;
+            const int f = (i < cnt && i > 0 && val[i] != val[i - 1]) ? 1 : 0;
+            // block inclusive scan of f (warp scans + warp totals in rnk scratch beyond cnt is unsafe: use shuffles + smem)
+            int incl = f;
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { int t = __shfl_up_sync(FULL, incl, dd); if (lane >= dd) incl += t; }
+            __shared__ int wtot[32];
+            if (lane == 31) wtot[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                int wv = lane < (int)(blockDim.x >> 5) ? wtot[lane] : 0, wi = wv;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { int t = __shfl_up_sync(FULL, wi, dd); if (lane >= dd) wi += t; }
+                wtot[lane] = wi - wv;
+            }
+            __syncthreads();
+            const int r = s_carry + wtot[wid] + incl;
+            if (i < cnt) rnk[i] = (unsigned short)r;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) s_carry = r;
+            __syncthreads();
+        }
+        // every pixel: first sorted position holding its value -> rank
+        for (int j = threadIdx.x; j < box; j += blockDim.x) {
+            const int ly = fdiv(j, magic), lx = j - ly * w;
+            const int gi = (y0 + ly) * W + x0 + lx;
+            if (par[base + gi] != root) continue;
+            const double v = image[base + gi];
+            int lo = 0, hi = cnt - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (val[mid] < v) lo = mid + 1; else hi = mid; }
+            level[base + gi] = rnk[lo];
+        }
+    }
+}
+
+struct BucketDirect {           // ranked levels index their bucket directly inside the slot's range
+    int base;
+    __device__ __forceinline__ int operator()(int v) const { return base + v; }
+};
+
+// work lists for the ranked flood: like k_flood_count / k_flood_scatter, but huge blobs go to the heap list (ovf)
+__global__ void k_flood_count_ranked(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
+    int n = blockIdx.y;
+    long long ko = (long long)n * b.KS;
+    int B = b.count[n];
+    for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        if (blob_is_huge(b, ko, bid, W)) continue;
+        int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
+        if (cls >= 0) atomicAdd(&wk.count[cls], 1);
+    }
+}
+__global__ void k_flood_scatter_ranked(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
+    int n = blockIdx.y;
+    long long ko = (long long)n * b.KS;
+    int B = b.count[n];
+    for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        long long item = ((long long)n << 32) | (unsigned)bid;
+        if (blob_is_huge(b, ko, bid, W)) { wk.ovf[atomicAdd(wk.ngen + 1, 1)] = item; continue; }
+        int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
+        if (cls >= 0) wk.items[wk.offset[cls] + atomicAdd(&wk.fill[cls], 1)] = item;
+        else wk.gen[atomicAdd(wk.ngen, 1)] = item;
+    }
+}
+
+// one blob per CTA at a time, ranked levels, all arrays sized by the blob (levels < cells)
+__device__ __forceinline__ void general_drain_ranked(const Geom& g, const unsigned short* __restrict__ level,
+                                                     const int* __restrict__ par, const BlobInfo& b, const long long* list,
+                                                     int count, int* cursor, int32_t* out) {
+    __shared__ int s_item;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem);
+    unsigned short* nxs = lab + WR_GEN_CAP;
+    unsigned short* lvl = nxs + WR_GEN_CAP;
+    unsigned short* head = lvl + WR_GEN_CAP;
+    unsigned short* tail = head + WR_GEN_CAP;
+    const int W = g.W;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int k = s_item;
+        if (k >= count) break;
+        const long long item = list[k];
+        const int n = (int)(item >> 32), bid = (int)(item & 0xffffffffll);
+        const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+        const int root = b.root[ko + bid];
+        const int y0 = root / W, x0 = b.xmin[ko + bid];
+        const int w = b.xmax[ko + bid] - x0 + 1, h = b.ymax[ko + bid] - y0 + 1;
+        const int cells = (w + 2) * (h + 2);
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
+        stage_copy(threadIdx.x, blockDim.x, W, level + base, par + base, out + base, root, y0, x0, w, h, lab, lvl);
+        __syncthreads();
+        if (warp == 0) {
+            int vmin, vmax, vsmin;
+            link_seeds(lane, cells, lab, nxs, lvl, head, tail, BucketDirect{0}, vmin, vmax, vsmin);
+            __syncwarp();
+            if (lane == 0 && vsmin <= vmax) lane_flood(w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketDirect{0});
+        }
+        __syncthreads();
+        stage_writeback(threadIdx.x, blockDim.x, W, out + base, y0, x0, w, h, lab);
+    }
+}
+
+template <int WARPS, int ARENA, int SLOTS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+k_ws_flood_ranked(Geom g, const unsigned short* __restrict__ level, const int* __restrict__ par, BlobInfo b, FloodWork wk,
+                  int32_t* out, int gen_first) {
+    const int ngen = wk.ngen[0];
+    if ((int)blockIdx.x < min(gen_first, ngen)) general_drain_ranked(g, level, par, b, wk.gen, ngen, wk.gcursor, out);
+    __syncthreads();
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem) + (size_t)warp * ARENA * 5;
+        unsigned short* nxs = lab + ARENA;
+        unsigned short* lvl = nxs + ARENA;
+        unsigned short* head = lvl + ARENA;
+        unsigned short* tail = head + ARENA;
+        const int W = g.W;
+        for (int cls = 0; cls < SLOTS; ++cls) {
+            const int cap = ARENA / (cls + 1), slots = cls + 1;
+            const int cnt = wk.count[cls];
+            const long long* list = wk.items + wk.offset[cls];
+            for (;;) {
+                int k0 = 0;
+                if (lane == 0) k0 = atomicAdd(&wk.cursor[cls], slots);
+                k0 = __shfl_sync(FULL, k0, 0);
+                if (k0 >= cnt) break;
+                const int m = min(slots, cnt - k0);
+                int mn = 0, mroot = 0, my0 = 0, mx0 = 0, mw = 0, mh = 0;
+                if (lane < m) {
+                    const long long item = list[k0 + lane];
+                    mn = (int)(item >> 32);
+                    const int bid = (int)(item & 0xffffffffll);
+                    const long long ko = (long long)mn * b.KS;
+                    mroot = b.root[ko + bid];
+                    my0 = mroot / W; mx0 = b.xmin[ko + bid];
+                    mw = b.xmax[ko + bid] - mx0 + 1; mh = b.ymax[ko + bid] - my0 + 1;
+                }
+                for (int i = lane; i < m * cap; i += 32) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
+                for (int s = 0; s < m; ++s) {
+                    const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s);
+                    const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    const long long base = (long long)n * g.P;
+                    stage_copy(lane, 32, W, level + base, par + base, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
+                }
+                __syncwarp();
+                int lmax = -1, smin = WS_LVL_NONE;              // of slot `lane`
+                for (int s = 0; s < m; ++s) {
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    int vmin, vmax, vsmin;
+                    link_seeds(lane, (w + 2) * (h + 2), lab + s * cap, nxs + s * cap, lvl + s * cap, head, tail,
+                               BucketDirect{s * cap}, vmin, vmax, vsmin);
+                    if (lane == s) { lmax = vmax; smin = vsmin; }
+                }
+                __syncwarp();
+                if (lane < m && smin <= lmax)
+                    lane_flood(mw + 2, smin, lmax, lab + lane * cap, nxs + lane * cap, lvl + lane * cap, head, tail,
+                               BucketDirect{lane * cap});
+                __syncwarp();
+                for (int s = 0; s < m; ++s) {
+                    const int n = __shfl_sync(FULL, mn, s);
+                    const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
+                    const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
+                    stage_writeback(lane, 32, W, out + (long long)n * g.P, y0, x0, w, h, lab + s * cap);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (ngen > 0) general_drain_ranked(g, level, par, b, wk.gen, ngen, wk.gcursor, out);
+}
+
 // ---- fp64 values: binary heap keyed (value, age, index) -------------------------------------------------
 struct __align__(16) HeapItem { double v; unsigned age; int idx; };
 
@@ -682,22 +938,29 @@ __device__ __forceinline__ HeapItem heap_pop(HeapItem* h, int& sz) {
     return top;
 }
 
+// `list` == NULL: every blob of tile blockIdx.y (queue[n] is the cursor); else the listed blobs only (persistent grid)
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ws_flood_f64(Geom g, const double* __restrict__ image, const int* __restrict__ par, BlobInfo b, int* queue,
-               HeapItem* heap, int32_t* out) {
+               const long long* __restrict__ list, const int* __restrict__ nlist, HeapItem* heap, int32_t* out) {
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
-    const int B = b.count[n];
-    const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
-    const double* I = image + base;
-    const int* tp = par + base;
-    int32_t* o = out + base;
     const int W = g.W, H = g.H;
     for (;;) {
-        int bid = 0;
-        if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
-        bid = __shfl_sync(FULL, bid, 0);
-        if (bid > B) break;
+        int n = blockIdx.y, bid = 0;
+        if (list) {
+            int k = 0;
+            if (lane == 0) k = atomicAdd(queue, 1);
+            k = __shfl_sync(FULL, k, 0);
+            if (k >= *nlist) break;
+            n = (int)(list[k] >> 32); bid = (int)(list[k] & 0xffffffffll);
+        } else {
+            if (lane == 0) bid = atomicAdd(&queue[n], 1) + 1;
+            bid = __shfl_sync(FULL, bid, 0);
+            if (bid > b.count[n]) break;
+        }
+        const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+        const double* I = image + base;
+        const int* tp = par + base;
+        int32_t* o = out + base;
         const int root = b.root[ko + bid];
         const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
         HeapItem* h = heap + base + b.off[ko + bid];
@@ -854,11 +1117,53 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
 int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,
                       const BlobInfo& b, int32_t* out) {
     (void)rank;
-    int* queue = ws<int>(c, (size_t)g.N);
-    HeapItem* heap = ws<HeapItem>(c, (size_t)g.N * g.P);
-    if (!queue || !heap || !b.off) return TISEG_ERR_CUDA;
-    TISEG_TRY(zero(c, queue, (size_t)g.N * sizeof(int)));
-    TISEG_LAUNCH(c, k_ws_flood_f64, dim3(flood_blocks(c, g.N), g.N), TISEG_THREADS, 0, g, image, par, b, queue, heap, out);
+    const int N = g.N;
+    static const bool heap_only = getenv("TISEG_F64_HEAP") != nullptr;       // the global-memory heap flood for everything
+    HeapItem* heap = ws<HeapItem>(c, (size_t)N * g.P);
+    if (!heap || !b.off) return TISEG_ERR_CUDA;
+    if (heap_only) {
+        int* queue = ws<int>(c, (size_t)N);
+        if (!queue) return TISEG_ERR_CUDA;
+        TISEG_TRY(zero(c, queue, (size_t)N * sizeof(int)));
+        TISEG_LAUNCH(c, k_ws_flood_f64, dim3(flood_blocks(c, N), N), TISEG_THREADS, 0, g, image, par, b, queue,
+                     (const long long*)nullptr, (const int*)nullptr, heap, out);
+        return TISEG_OK;
+    }
+    // ranked levels per blob, then the bucket flood in shared memory
+    constexpr int WARPS = 7, ARENA = 3072, SLOTS = 16;
+    constexpr size_t MULTI = (size_t)WARPS * ARENA * 10, GEN = (size_t)WR_GEN_CAP * 10;
+    constexpr size_t SMEM = MULTI > GEN ? MULTI : GEN;
+    static_assert(SMEM + 64 <= 232448, "shared memory");
+    const size_t max_blobs = (size_t)N * ((size_t)g.P / 2 + 1);
+    unsigned short* level = ws<unsigned short>(c, (size_t)N * g.P);
+    int* prefix = ws<int>(c, (size_t)N + 1);
+    FloodWork wk;
+    wk.items = ws<long long>(c, max_blobs);
+    wk.gen = ws<long long>(c, max_blobs);
+    wk.ovf = ws<long long>(c, max_blobs);
+    int* ints = ws<int>(c, WK_INTS);
+    if (!level || !prefix || !wk.items || !wk.gen || !wk.ovf || !ints) return TISEG_ERR_CUDA;
+    wk.count = ints; wk.offset = ints + WS_MAXCLS; wk.fill = ints + 2 * WS_MAXCLS; wk.cursor = ints + 3 * WS_MAXCLS;
+    wk.ngen = ints + 4 * WS_MAXCLS; wk.gcursor = wk.ngen + 2;
+    TISEG_TRY(zero(c, ints, WK_INTS * sizeof(int)));
+    static bool attr_set = false;
+    constexpr size_t RK_SMALL = (size_t)WR_SORT_SMALL * 10, RK_LARGE = (size_t)WR_SORT_MAX * 10;
+    if (!attr_set) {
+        TISEG_CHECK(cudaFuncSetAttribute(k_rank_blobs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_LARGE));
+        TISEG_CHECK(cudaFuncSetAttribute((k_ws_flood_ranked<WARPS, ARENA, SLOTS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_set = true;
+    }
+    TISEG_LAUNCH(c, k_blob_prefix, 1, 32, 0, b.count, N, prefix);
+    TISEG_LAUNCH(c, k_rank_blobs<false>, c->sm_count * 16, 128, RK_SMALL, g, image, par, b, prefix, level);
+    TISEG_LAUNCH(c, k_rank_blobs<true>, c->sm_count, 1024, RK_LARGE, g, image, par, b, prefix, level);
+    TISEG_LAUNCH(c, k_flood_count_ranked, dim3(8, N), 256, 0, b, g.W, wk, ARENA, SLOTS);
+    TISEG_LAUNCH(c, k_flood_offsets, 1, 32, 0, wk);
+    TISEG_LAUNCH(c, k_flood_scatter_ranked, dim3(8, N), 256, 0, b, g.W, wk, ARENA, SLOTS);
+    const int gen_first = c->sm_count >= 8 ? c->sm_count / 4 : 1;
+    TISEG_LAUNCH(c, (k_ws_flood_ranked<WARPS, ARENA, SLOTS>), c->sm_count, 32 * WARPS, SMEM, g, level, par, b, wk, out, gen_first);
+    // blobs too large to rank / stage: the heap flood in global memory (persistent grid; exits at once if there are none)
+    TISEG_LAUNCH(c, k_ws_flood_f64, dim3(c->sm_count, 1), TISEG_THREADS, 0, g, image, par, b, wk.gcursor + 1,
+                 (const long long*)wk.ovf, (const int*)(wk.ngen + 1), heap, out);
     return TISEG_OK;
 }
 
