@@ -181,7 +181,7 @@ def test_watershed_u8():
 
 def test_watershed_f64():
     rng = np.random.default_rng(51)
-    for (H, W, nmark) in [(1, 9, 2), (20, 31, 5), (64, 64, 12), (100, 130, 40)]:
+    for (H, W, nmark) in [(1, 9, 2), (20, 31, 5), (64, 64, 12), (100, 130, 40), (200, 300, 60)]:
         img, mk, mask = _random_ws_case(rng, H, W, 16, nmark)
         f = -ndi.gaussian_filter(img.astype(np.float64), 1.0)
         f[::3] = np.round(f[::3], 1)          # plateaus of equal doubles
