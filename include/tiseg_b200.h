@@ -12,6 +12,12 @@
  *
  * Each function names the reference code (file:line under the reference repository) it replaces.
  * All return TISEG_OK (0) or an error code; tiseg_last_error() gives the message (thread-local).
+ *
+ * Errors that only a kernel can detect (an instance id outside [0, max(H*W+1, 65536))) are raised on the device.
+ * A call with a host output synchronises anyway and reports them itself; a call with device outputs only returns
+ * before execution, and the error is reported by the next call on the context that synchronises (any call with a
+ * host output, or tiseg_synchronize).  No call decides anything on the host in the middle of its kernels, except
+ * tiseg_reconstruction_erosion_u8 / tiseg_postproc_dist_lambda with lamb > 0 (iteration to a fixed point).
  */
 #ifndef TISEG_B200_H
 #define TISEG_B200_H
@@ -26,7 +32,7 @@ extern "C" {
 #define TISEG_ERR_CUDA 1   /* a CUDA runtime call or kernel launch failed                     */
 #define TISEG_ERR_ARG 2    /* bad argument (null pointer, non-positive size, unknown option)  */
 #define TISEG_ERR_NOGPU 3  /* no CUDA device: there is no CPU fallback                        */
-#define TISEG_ERR_LIMIT 4  /* an internal capacity (pair table, queue) was exceeded           */
+#define TISEG_ERR_LIMIT 4  /* a data-dependent limit was exceeded (instance id out of range)  */
 
 typedef struct tiseg_ctx tiseg_ctx;
 
