@@ -95,7 +95,8 @@ class CustomDataset:
         """Same-shaped per-image arrays -> one batch (CUDA tensors stay on the device)."""
         if is_torch(arrs[0]):
             import torch
-            return torch.stack([a for a in arrs])
+            tdt = {np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+            return torch.stack([a for a in arrs]).to(tdt)
         return np.stack([np.asarray(a) for a in arrs]).astype(dtype, copy=False)
 
     def _groups(self, preds):
@@ -115,8 +116,8 @@ class CustomDataset:
         for ks in self._groups(preds):
             sem_p = self._stack([preds[k]['sem_pred'] for k in ks], np.uint8)
             inst_p = self._stack([preds[k]['inst_pred'] for k in ks], np.int32)
-            sem_g = np.stack([np.asarray(sem_gts[k]) for k in ks]).astype(np.uint8, copy=False)
-            inst_g = np.stack([np.asarray(inst_gts[k]) for k in ks]).astype(np.int32, copy=False)
+            sem_g = self._stack([sem_gts[k] for k in ks], np.uint8)        # CUDA-resident ground truth stays resident
+            inst_g = self._stack([inst_gts[k] for k in ks], np.int32)
             sem_res = M.pre_eval_all_semantic_metric(sem_p, sem_g, C)
             # re_instance + measure.label of both maps happen inside the pair kernel (custom.py:272-277)
             aji, pq = ops.pair_metrics_bin(inst_p, inst_g)
@@ -212,8 +213,8 @@ class CoNICDataset(CustomDataset):
         for ks in self._groups(preds):
             sem_p = self._stack([preds[k]['sem_pred'] for k in ks], np.uint8)
             inst_p = self._stack([preds[k]['inst_pred'] for k in ks], np.int32)
-            sem_g = np.stack([np.asarray(sem_gts[k]) for k in ks]).astype(np.uint8, copy=False)
-            inst_g = np.stack([np.asarray(inst_gts[k]) for k in ks]).astype(np.int32, copy=False)
+            sem_g = self._stack([sem_gts[k] for k in ks], np.uint8)        # CUDA-resident ground truth stays resident
+            inst_g = self._stack([inst_gts[k] for k in ks], np.int32)
             sem_res = M.pre_eval_all_semantic_metric(sem_p, sem_g, C)
             r = ops.pair_metrics_multiclass(inst_p, sem_p, inst_g, sem_g, C)
             aji, pq = _host(r['aji']).astype(np.float32), _host(r['pq']).astype(np.float32)

@@ -72,15 +72,15 @@ def pre_eval_all_semantic_metric(pred_label, target_label, num_classes, ignore_i
     counts, valid = ops.sem_counts(pred_label, target_label, num_classes, ignore_index)
     counts, valid = _host(counts), _host(valid)
 
-    def one(cn):
-        tp, fp, fn, pr, gt = (torch.from_numpy(cn[k].astype(np.float32)) for k in range(5))
-        tn = pr.sum() - (tp + fp + fn)
-        pack = (tp, tn, fp, fn, pr, gt)
-        return tuple(x[1:] for x in pack) if reduce_zero_label else pack
-
-    if counts.ndim == 3:
-        return [one(c) for c in counts]
-    return one(counts)
+    batch = counts.ndim == 3
+    t = torch.from_numpy(np.ascontiguousarray(counts if batch else counts[None]).astype(np.float32))      # [N, 5, C]
+    tp, fp, fn, pr, gt = (t[:, k] for k in range(5))
+    tn = pr.sum(1, keepdim=True) - (tp + fp + fn)       # sem_metrics.py:43: total = histc(pred).sum() over every class
+    pack = (tp, tn, fp, fn, pr, gt)
+    if reduce_zero_label:
+        pack = tuple(x[:, 1:] for x in pack)
+    out = [tuple(x[j] for x in pack) for j in range(t.shape[0])]
+    return out if batch else out[0]
 
 
 # --------------------------------------------------------------------------- convenience scores
