@@ -17,9 +17,22 @@ int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, in
 __constant__ float c_dir9[9][2] = {{0, 0}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}, {1, -1}};
 
 // level = 1 - round(min over the 8 circularly shifted neighbours of cos(anchor, neighbour)), background -> 0.
-// Same fp32 expression as the reference so the rounding sees the same value.
+// The cosine only depends on the two direction labels, so every block first evaluates the reference's fp32
+// expression for the 81 label pairs (same operations, same rounding) into a shared table of LEVELS
+// (1 - rint(cos); rint is monotone, so 1 - rint(min cos) = max of the pair levels); a pixel is then eight byte loads,
+// eight table lookups and a max.
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ddm_levels(Geom g, const uint8_t* __restrict__ dir, uint8_t* __restrict__ lv, int* mm) {
+    __shared__ int s_lvl[81];
+    if (threadIdx.x < 81) {
+        const int d = threadIdx.x / 9, e = threadIdx.x - d * 9;
+        const float a0 = c_dir9[d][0], a1 = c_dir9[d][1], f0 = c_dir9[e][0], f1 = c_dir9[e][1];
+        const float na = sqrtf(a0 * a0 + a1 * a1);
+        const float num = a0 * f0 + a1 * f1;
+        const float den = na * sqrtf(f0 * f0 + f1 * f1) + 0.000001f;
+        s_lvl[threadIdx.x] = d == 0 ? 0 : (int)(1.f - rintf(num / den));      // torch.round: half to even; background -> 1 -> level 0
+    }
+    __syncthreads();
     Pix px;
     if (!warp_pixel(g, px)) return;
     int level = -1;
@@ -27,26 +40,24 @@ k_ddm_levels(Geom g, const uint8_t* __restrict__ dir, uint8_t* __restrict__ lv, 
         const uint8_t* t = dir + px.base;
         int d = t[px.idx];
         if (d > 8) d = 0;
-        float a0 = c_dir9[d][0], a1 = c_dir9[d][1];
-        float na = sqrtf(a0 * a0 + a1 * a1);
         // torch.roll(shifts=(sv, sh)): feature[y, x] = anchor[y - sv, x - sh] (wrap-around); the 8 shifts of
-        // direct_diff_map.py:116-131 cover all 8 neighbours, so the min does not depend on their order
-        float best = FLT_MAX;
-        for (int sv = -1; sv <= 1; ++sv) {
-            int yy = px.y - sv; yy = yy < 0 ? yy + g.H : (yy >= g.H ? yy - g.H : yy);
-            for (int sh = -1; sh <= 1; ++sh) {
-                if (sv == 0 && sh == 0) continue;
-                int xx = px.x - sh; xx = xx < 0 ? xx + g.W : (xx >= g.W ? xx - g.W : xx);
-                int e = t[yy * g.W + xx];
-                if (e > 8) e = 0;
-                float f0 = c_dir9[e][0], f1 = c_dir9[e][1];
-                float num = a0 * f0 + a1 * f1;
-                float den = na * sqrtf(f0 * f0 + f1 * f1) + 0.000001f;
-                best = fminf(best, num / den);
+        // direct_diff_map.py:116-131 cover all 8 neighbours, so the extremum does not depend on their order
+        level = 0;
+        if (d != 0) {
+            level = -8;
+#pragma unroll
+            for (int sv = -1; sv <= 1; ++sv) {
+                int yy = px.y - sv; yy = yy < 0 ? yy + g.H : (yy >= g.H ? yy - g.H : yy);
+#pragma unroll
+                for (int sh = -1; sh <= 1; ++sh) {
+                    if (sv == 0 && sh == 0) continue;
+                    int xx = px.x - sh; xx = xx < 0 ? xx + g.W : (xx >= g.W ? xx - g.W : xx);
+                    int e = t[yy * g.W + xx];
+                    if (e > 8) e = 0;
+                    level = max(level, s_lvl[d * 9 + e]);
+                }
             }
         }
-        if (d == 0) best = 1.f;
-        level = (int)(1.f - rintf(best));                    // torch.round: half to even
         lv[px.base + px.idx] = (uint8_t)level;
     }
     int hi = level, lo = level < 0 ? 255 : level;
@@ -83,28 +94,48 @@ k_ddm_mean(Geom g, const uint8_t* __restrict__ lv, const int* __restrict__ mm, i
 }
 
 // per variant: softmax over the D direction channels, channel 0 scaled by the mean background probability,
-// argmax (first maximum)
+// argmax (first maximum).  Four pixels per thread, every logit read once (128-bit loads), exp evaluated once.
+template <int DMAX>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_dir_map(Geom g, const float* __restrict__ dir_logits, const float* __restrict__ sem_prob, int T, int D, int C,
-          uint8_t* __restrict__ dir_map) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    const long long P = g.P;
-    float s0 = sem_prob[((long long)px.n * C) * P + px.idx];
+k_dir_map(long long P, const float* __restrict__ dir_logits, const float* __restrict__ sem_prob, int T, int D, int C,
+          uint8_t* __restrict__ dir_map, bool vec) {
+    const int n = blockIdx.y;
+    const long long i = flat4_index();
+    if (i >= P) return;
+    const Pack4<float> s0 = ld4(sem_prob + ((long long)n * C) * P, i, P, vec);
     for (int t = 0; t < T; ++t) {
-        const float* src = dir_logits + ((long long)px.n * T + t) * D * P + px.idx;
-        float m = -INFINITY;
-        for (int d = 0; d < D; ++d) m = fmaxf(m, src[d * P]);
-        float s = 0.f;
-        for (int d = 0; d < D; ++d) s = s + expf(src[d * P] - m);
-        int best = 0;
-        float bv = -INFINITY;
-        for (int d = 0; d < D; ++d) {
-            float p = expf(src[d * P] - m) / s;
-            if (d == 0) p = p * s0;
-            if (p > bv) { bv = p; best = d; }
-        }
-        dir_map[((long long)px.n * T + t) * P + px.idx] = (uint8_t)best;
+        const float* src = dir_logits + ((long long)n * T + t) * D * P;
+        Pack4<float> x[DMAX];
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d)
+            if (d < D) {
+                x[d] = ld4(src + d * P, i, P, vec);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], x[d].v[k]);
+            }
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d)
+            if (d < D) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { x[d].v[k] = expf(x[d].v[k] - m[k]); s[k] = s[k] + x[d].v[k]; }
+            }
+        Pack4<uint8_t> best;
+        float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) best.v[k] = 0;
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d)
+            if (d < D) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float p = x[d].v[k] / s[k];
+                    if (d == 0) p = p * s0.v[k];
+                    if (p > bv[k]) { bv[k] = p; best.v[k] = (uint8_t)d; }
+                }
+            }
+        st4(dir_map + ((long long)n * T + t) * P, i, P, vec, best);
     }
 }
 
@@ -216,7 +247,11 @@ int tiseg_cdnet_refine(tiseg_ctx* c, const float* sem_logits, const float* dir_l
     if (!d_sem || !d_dir || !d_pt || !d_prob || !d_dd || !dir_all || !pmean || !pmax) return TISEG_ERR_CUDA;
     // softmax + TTA mean of the semantic head: the K1 kernel
     TISEG_TRY(softmax_argmax_dev(c, g, d_sem, T, C, d_prob, nullptr));
-    TISEG_LAUNCH(c, k_dir_map, warp_grid(g), TISEG_THREADS, 0, g, d_dir, d_prob, T, D, C, dir_all);
+    {
+        const bool v4 = (g.P % 4 == 0) && aligned16(d_dir, d_prob) && (((uintptr_t)dir_all) & 3) == 0;
+        const dim3 fg(flat4_grid(g.P), (unsigned)N);
+        TISEG_LAUNCH(c, k_dir_map<9>, fg, TISEG_THREADS, 0, (long long)g.P, d_dir, d_prob, T, D, C, dir_all, v4);     // D == 9 is checked above
+    }
     TISEG_TRY(ddm_dev(c, g, dir_all, T, d_dd));
     TISEG_LAUNCH(c, k_key_init, (N + 255) / 256, 256, 0, pmax, N);
     TISEG_LAUNCH(c, k_point_mean, warp_grid(g), TISEG_THREADS, 0, g, d_pt, T, pmean, pmax);

@@ -24,12 +24,16 @@ __global__ void k_border_touch(Geom g, const int* __restrict__ par, uint8_t* tou
     if (p >= 0) touch[base + p] = 1;
 }
 
-__global__ void k_fill_from_forest(Geom g, const int* __restrict__ par, const uint8_t* __restrict__ touch,
-                                   uint8_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    int p = par[px.base + px.idx];
-    out[px.base + px.idx] = (p < 0) || !touch[px.base + p];
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_fill_from_forest(long long P, const int* __restrict__ par, const uint8_t* __restrict__ touch, uint8_t* __restrict__ out,
+                   bool vec) {
+    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+    if (i >= P) return;
+    Pack4<int> p = ld4(par + base, i, P, vec);
+    Pack4<uint8_t> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = (uint8_t)((p.v[k] < 0) || (i + k < P && !touch[base + p.v[k]]));
+    st4(out + base, i, P, vec, o);
 }
 
 int fill_from_complement_forest(tiseg_ctx* c, const Geom& g, const int* par, uint8_t* out) {
@@ -39,17 +43,22 @@ int fill_from_complement_forest(tiseg_ctx* c, const Geom& g, const int* par, uin
     TISEG_TRY(zero(c, touch, total));
     int per = 2 * g.W + 2 * g.H;
     TISEG_LAUNCH(c, k_border_touch, dim3((per + 255) / 256, g.N), 256, 0, g, par, touch);
-    TISEG_LAUNCH(c, k_fill_from_forest, warp_grid(g), TISEG_THREADS, 0, g, par, touch, out);
+    TISEG_LAUNCH(c, k_fill_from_forest, dim3(flat4_grid(g.P), g.N), TISEG_THREADS, 0, (long long)g.P, par, touch, out,
+                 (g.P % 4 == 0) && aligned16(par) && (((uintptr_t)out) & 3) == 0);
     return TISEG_OK;
 }
 
 // ---- remove small objects ---------------------------------------------------------------------------
-__global__ void k_keep_large(Geom g, const int* __restrict__ par, const int* __restrict__ area, int min_size,
-                             uint8_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    int p = par[px.base + px.idx];
-    out[px.base + px.idx] = p >= 0 && area[px.base + p] >= min_size;
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_keep_large(long long P, const int* __restrict__ par, const int* __restrict__ area, int min_size, uint8_t* __restrict__ out,
+             bool vec) {
+    const long long base = (long long)blockIdx.y * P, i = flat4_index();
+    if (i >= P) return;
+    Pack4<int> p = ld4(par + base, i, P, vec);
+    Pack4<uint8_t> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = (uint8_t)(i + k < P && p.v[k] >= 0 && area[base + p.v[k]] >= min_size);
+    st4(out + base, i, P, vec, o);
 }
 
 int remove_small_mask(tiseg_ctx* c, const Geom& g, const uint8_t* mask, int min_size, int conn, uint8_t* out) {
@@ -59,7 +68,8 @@ int remove_small_mask(tiseg_ctx* c, const Geom& g, const uint8_t* mask, int min_
     if (!par || !area) return TISEG_ERR_CUDA;
     TISEG_TRY(ccl_build(c, g, ImgMaskU8{mask}, conn, par));
     TISEG_TRY(ccl_areas(c, g, par, area));
-    TISEG_LAUNCH(c, k_keep_large, warp_grid(g), TISEG_THREADS, 0, g, par, area, min_size, out);
+    TISEG_LAUNCH(c, k_keep_large, dim3(flat4_grid(g.P), g.N), TISEG_THREADS, 0, (long long)g.P, par, area, min_size, out,
+                 (g.P % 4 == 0) && aligned16(par) && (((uintptr_t)out) & 3) == 0);
     return TISEG_OK;
 }
 
@@ -134,49 +144,72 @@ __global__ void k_zero_class(Geom g, uint8_t* cls, int edge_id, const uint8_t* _
     if ((edge_id >= 0 && cls[i] == edge_id) || (kill && kill[i] > 0)) cls[i] = 0;
 }
 
-__global__ void k_class_presence(Geom g, const uint8_t* __restrict__ cls, unsigned long long* present) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_class_presence(long long P, const uint8_t* __restrict__ cls, unsigned long long* present, bool vec) {
+    const long long base = (long long)blockIdx.y * P;
     unsigned lo = 0, hi = 0;
-    if (px.ok) {
-        int v = cls[px.base + px.idx];
-        if (v < 32) lo = 1u << v; else if (v < 64) hi = 1u << (v - 32);
+    for (long long i = flat4_index(); i < P; i += (long long)gridDim.x * blockDim.x * 4) {
+        Pack4<uint8_t> v = ld4(cls + base, i, P, vec);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k < P) { if (v.v[k] < 32) lo |= 1u << v.v[k]; else if (v.v[k] < 64) hi |= 1u << (v.v[k] - 32); }
     }
     lo = __reduce_or_sync(0xffffffffu, lo);
     hi = __reduce_or_sync(0xffffffffu, hi);
-    if (px.lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
         unsigned long long m = ((unsigned long long)hi << 32) | lo;
-        if ((present[px.n] & m) != m) atomicOr(&present[px.n], m);
+        if ((present[blockIdx.y] & m) != m) atomicOr(&present[blockIdx.y], m);
     }
 }
 
-// dilation(disk(r)) of the class's label image fused with the overwrite into inst / sem (unet.py:86-91)
+// dilation(disk(r)) of the class's label image fused with the overwrite into inst / sem (unet.py:86-91).
+// One thread = four adjacent pixels: every row of the footprint is read once (four centre values + r on each side)
+// instead of once per tap, and threads whose whole window is background — most of them — write nothing.
+template <int R>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_unet_compose(Geom g, const int32_t* __restrict__ lab, int r, int cls_id, const int* __restrict__ cur,
-               uint8_t* seen, int KS, int* haszero, uint8_t* __restrict__ sem, int32_t* __restrict__ inst) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int v = 0;
-    if (px.ok) {
-        const int32_t* t = lab + px.base;
-        int r2 = r * r;
-        for (int dy = -r; dy <= r; ++dy) {
-            int yy = px.y + dy;
+k_unet_compose(Geom g, const int32_t* __restrict__ lab, int cls_id, const int* __restrict__ cur, uint8_t* seen, int KS,
+               int* haszero, uint8_t* __restrict__ sem, int32_t* __restrict__ inst, bool vec) {
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < (long long)W4 * g.H;
+    const int n = blockIdx.y;
+    int v[4] = {0, 0, 0, 0};
+    int y = 0, x = 0;
+    if (live) {
+        y = (int)(t / W4); x = (int)(t - (long long)y * W4) * 4;
+        const int32_t* tl = lab + (long long)n * g.P;
+#pragma unroll
+        for (int dy = -R; dy <= R; ++dy) {
+            const int yy = y + dy;
             if (yy < 0 || yy >= g.H) continue;
-            for (int dx = -r; dx <= r; ++dx) {
-                int xx = px.x + dx;
-                if (xx < 0 || xx >= g.W || dx * dx + dy * dy > r2) continue;
-                v = max(v, t[yy * g.W + xx]);
+            const int32_t* row = tl + (long long)yy * g.W;
+            int w[4 + 2 * R];                                   // columns x-R .. x+3+R
+            if (vec) { const Pack4<int> c4 = *reinterpret_cast<const Pack4<int>*>(row + x); w[R] = c4.v[0]; w[R + 1] = c4.v[1]; w[R + 2] = c4.v[2]; w[R + 3] = c4.v[3]; }
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[R + k] = x + k < g.W ? row[x + k] : 0;
             }
+#pragma unroll
+            for (int k = 1; k <= R; ++k) { w[R - k] = x - k >= 0 ? row[x - k] : 0; w[R + 3 + k] = x + 3 + k < g.W ? row[x + 3 + k] : 0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int dx = -R; dx <= R; ++dx)
+                    if (dx * dx + dy * dy <= R * R) v[k] = max(v[k], w[R + k + dx]);
         }
-        if (v > 0) {
-            inst[px.base + px.idx] = v + cur[px.n];
-            sem[px.base + px.idx] = (uint8_t)cls_id;
-            seen[(long long)px.n * KS + v] = 1;
-        }
+        const long long o = (long long)n * g.P + (long long)y * g.W + x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x + k < g.W && v[k] > 0) {
+                inst[o + k] = v[k] + cur[n];
+                sem[o + k] = (uint8_t)cls_id;
+                seen[(long long)n * KS + v[k]] = 1;
+            }
     }
-    bool z = px.ok && v == 0;
-    if (__any_sync(0xffffffffu, z) && px.lane == 0 && !haszero[px.n]) haszero[px.n] = 1;
+    bool z = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z |= live && x + k < g.W && v[k] == 0;
+    if (__any_sync(0xffffffffu, z) && (threadIdx.x & 31) == 0 && !haszero[n]) haszero[n] = 1;
 }
 
 __global__ void k_zero_prefix_u8(uint8_t* a, int KS, const int* __restrict__ counts) {
@@ -225,7 +258,12 @@ int postproc_unet_dev(tiseg_ctx* c, const Geom& g, uint8_t* cls, int max_class, 
     TISEG_TRY(zero(c, haszero, (size_t)N * sizeof(int)));
     TISEG_TRY(zero(c, sem, total));
     TISEG_TRY(zero(c, inst, total * sizeof(int32_t)));
-    TISEG_LAUNCH(c, k_class_presence, warp_grid(g), TISEG_THREADS, 0, g, cls, present);
+    {
+        unsigned gx = flat4_grid(g.P);
+        gx = gx > 32 ? (gx + 15) / 16 : gx;                   // ~16 groups per thread
+        TISEG_LAUNCH(c, k_class_presence, dim3(gx, N), TISEG_THREADS, 0, (long long)g.P, cls, present,
+                     (g.P % 4 == 0) && (((uintptr_t)cls) & 3) == 0);
+    }
     for (int id = 1; id <= max_class; ++id) {
         if (id == edge_id) continue;
         // binary_fill_holes(pred == id)
@@ -234,14 +272,24 @@ int postproc_unet_dev(tiseg_ctx* c, const Geom& g, uint8_t* cls, int max_class, 
         // remove_small_objects(., 5): bool input -> 4-connected components
         TISEG_TRY(ccl_build(c, g, ImgMaskU8{m1}, 1, par));
         TISEG_TRY(ccl_areas(c, g, par, aux));
-        TISEG_LAUNCH(c, k_keep_large, warp_grid(g), TISEG_THREADS, 0, g, par, aux, 5, m2);
+        TISEG_LAUNCH(c, k_keep_large, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, par, aux, 5, m2,
+                     (g.P % 4 == 0) && aligned16(par) && (((uintptr_t)m2) & 3) == 0);
         // measure.label (8-connected, raster ids)
         TISEG_TRY(ccl_build(c, g, ImgMaskU8{m2}, 2, par));
         TISEG_TRY(rank_roots(c, g, par, aux, counts));
         TISEG_TRY(apply_rank(c, g, par, aux, lab));
         // dilation(disk(radius)) + overwrite + cur bookkeeping
         TISEG_LAUNCH(c, k_zero_prefix_u8, dim3(8, N), 256, 0, seen, KS, counts);
-        TISEG_LAUNCH(c, k_unet_compose, warp_grid(g), TISEG_THREADS, 0, g, lab, radius, id, cur, seen, KS, haszero, sem, inst);
+        {
+            const dim3 qg((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+            const bool v4 = (g.W % 4 == 0) && aligned16(lab);
+            switch (radius) {
+                case 0: TISEG_LAUNCH(c, k_unet_compose<0>, qg, TISEG_THREADS, 0, g, lab, id, cur, seen, KS, haszero, sem, inst, v4); break;
+                case 1: TISEG_LAUNCH(c, k_unet_compose<1>, qg, TISEG_THREADS, 0, g, lab, id, cur, seen, KS, haszero, sem, inst, v4); break;
+                case 2: TISEG_LAUNCH(c, k_unet_compose<2>, qg, TISEG_THREADS, 0, g, lab, id, cur, seen, KS, haszero, sem, inst, v4); break;
+                default: TISEG_LAUNCH(c, k_unet_compose<3>, qg, TISEG_THREADS, 0, g, lab, id, cur, seen, KS, haszero, sem, inst, v4); break;
+            }
+        }
         TISEG_LAUNCH(c, k_unet_advance, N, 256, 0, seen, KS, counts, haszero, present, id, cur);
     }
     return TISEG_OK;
