@@ -74,3 +74,27 @@ def test_gather_results_gloo_world2(C, multi):
     for p in procs:
         p.join(60)
     assert all(msg == "ok" for _, msg in out), out
+
+
+def test_gt_prefetch_reads_the_reference_file_layout(tmp_path):
+    """custom.py:252-259: *_sem.png through pillow, *_inst.npy through np.load; the prefetcher must hand pre_eval
+    exactly what a synchronous read gives, in any order of use."""
+    from PIL import Image
+    from tiseg_b200 import datasets
+    rng = np.random.default_rng(9)
+    names = ["img%02d" % i for i in range(7)]
+    want = {}
+    for nm in names:
+        sem = rng.integers(0, 2, (20, 31)).astype(np.uint8)
+        inst = rng.integers(0, 50, (20, 31)).astype(np.int32)
+        Image.fromarray(sem).save(str(tmp_path / (nm + "_sem.png")))
+        np.save(str(tmp_path / (nm + "_inst.npy")), inst)
+        want[nm] = (sem, inst)
+    ds = datasets.CustomDataset(img_dir=str(tmp_path), ann_dir=str(tmp_path))
+    assert len(ds) == 7
+    ds.prefetch([5, 1, 3], workers=2)
+    for i in (3, 0, 5, 1, 6):                      # prefetched and not, out of order
+        sem, inst = ds._load_gt(i)
+        nm = os.path.basename(ds.data_infos[i]['sem_file_name'])[:-len('_sem.png')]
+        assert np.array_equal(sem, want[nm][0]) and np.array_equal(inst, want[nm][1])
+    assert not ds._pending

@@ -73,9 +73,35 @@ class CustomDataset:
                      inst_file_name=osp.join(ann_dir, nm + inst_suffix)) for nm in names]
 
     # ---- ground truth
+    def prefetch(self, indices, workers=8):
+        """Start reading the ground truth of ``indices`` in the background (``custom.py:252-259`` reads it
+        synchronously inside ``pre_eval``, one image at a time, between two GPU calls).  A pool of threads decodes
+        the ``*_sem.png`` / loads the ``*_inst.npy`` files — PNG inflate and ``np.load`` release the GIL — so that
+        by the time ``pre_eval`` asks for an index its arrays are in memory.  Call it for batch k+1 before running
+        the model on batch k."""
+        if self._inst_gts is not None:
+            return
+        import concurrent.futures
+        if getattr(self, "_pool", None) is None:
+            self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=int(workers))
+            self._pending = {}
+        for i in indices:
+            if i not in self._pending:
+                self._pending[i] = self._pool.submit(self._read_gt, i)
+
+    def _read_gt(self, index):
+        from PIL import Image
+        info = self.data_infos[index]
+        sem_gt = np.array(Image.open(info['sem_file_name']))          # mmcv.imread(flag='unchanged', backend='pillow')
+        inst_gt = np.load(info['inst_file_name'])
+        return sem_gt, inst_gt
+
     def _load_gt(self, index):
         if self._inst_gts is not None:
             return self._sem_gts[index], self._inst_gts[index]
+        pending = getattr(self, "_pending", None)
+        if pending and index in pending:
+            return pending.pop(index).result()
         from PIL import Image
         info = self.data_infos[index]
         sem_gt = np.array(Image.open(info['sem_file_name']))          # mmcv.imread(flag='unchanged', backend='pillow')
