@@ -48,14 +48,26 @@ __global__ void k_mm_init(long long* mm, int n) {
     if (i < n) { mm[2 * i] = 0x7fffffffffffffffll; mm[2 * i + 1] = (long long)0x8000000000000000ull; }
 }
 
-// min / max of the two HWC channels of the HV map
+// min / max of the two HWC channels of the HV map (eight pixels per thread before the warp reduction)
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_hv_minmax(Geom g, const float2* __restrict__ hv, long long* mm /* [N, 2 channels, 2] */) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    float2 v = px.ok ? hv[px.base + px.idx] : make_float2(0.f, 0.f);
-    warp_minmax_commit(v.x, v.x, px.ok, mm + (long long)px.n * 4);
-    warp_minmax_commit(v.y, v.y, px.ok, mm + (long long)px.n * 4 + 2);
+    const int n = blockIdx.y;
+    const float2* t = hv + (long long)n * g.P;
+    float lx = INFINITY, hx = -INFINITY, ly = INFINITY, hy = -INFINITY;
+    bool any = false;
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long i = i0 + k * stride;
+        if (i < g.P) {
+            const float2 v = t[i];
+            lx = fminf(lx, v.x); hx = fmaxf(hx, v.x); ly = fminf(ly, v.y); hy = fmaxf(hy, v.y);
+            any = true;
+        }
+    }
+    warp_minmax_commit(lx, hx, any, mm + (long long)n * 4);
+    warp_minmax_commit(ly, hy, any, mm + (long long)n * 4 + 2);
 }
 
 struct NormCoef { double a, b; };
@@ -85,40 +97,73 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// row pass: fp32 source -> fp64, 21 sequential taps along x
+// row pass: fp32 source -> fp64, 21 sequential taps along x.  One thread = four adjacent outputs: the 24 source values
+// they share are read once (reflected only at the image sides); every output keeps OpenCV's tap order.
 template <bool DERIV>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_sobel_row(Geom g, const float* __restrict__ src, double* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    const float* row = src + px.base + (long long)px.y * g.W;
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
+    const float* row = src + (long long)n * g.P + (long long)y * g.W;
+    double* orow = out + (long long)n * g.P + (long long)y * g.W;
     const double* k = DERIV ? c_deriv21 : c_smooth21;
-    double s = k[0] * (double)row[reflect101(px.x - 10, g.W)];
+    double v[24];
+    if (x >= 10 && x + 13 < g.W) {
 #pragma unroll
-    for (int t = 1; t < 21; ++t) s = s + k[t] * (double)row[reflect101(px.x + t - 10, g.W)];
-    out[px.base + px.idx] = s;
+        for (int j = 0; j < 24; ++j) v[j] = (double)row[x - 10 + j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 24; ++j) v[j] = (double)row[reflect101(x - 10 + j, g.W)];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (x + q >= g.W) break;
+        double s = k[0] * v[q];
+#pragma unroll
+        for (int tt = 1; tt < 21; ++tt) s = s + k[tt] * v[q + tt];
+        orow[x + q] = s;
+    }
 }
 
-// column pass (symmetric pairing, separate multiply and add) + min / max of the result
+// column pass (symmetric pairing, separate multiply and add) + min / max of the result.  One thread = four
+// vertically adjacent outputs of one column (24 row values read once, each read coalesced over the warp).
 template <bool DERIV>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_sobel_col(Geom g, const double* __restrict__ rowbuf, double* __restrict__ out, long long* mm /* [N, 2] */) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    double acc = 0.0;
-    if (px.ok) {
-        const double* t = rowbuf + px.base + px.x;
+    const int H4 = (g.H + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < (long long)H4 * g.W;
+    const int n = blockIdx.y;
+    double lo = 0.0, hi = 0.0;
+    if (live) {
+        const int y = (int)(t / g.W) * 4, x = (int)(t - (long long)(y >> 2) * g.W);
+        const double* col = rowbuf + (long long)n * g.P + x;
         const double* k = DERIV ? c_deriv21 : c_smooth21;
-        acc = DERIV ? 0.0 : __dmul_rn(k[10], t[(long long)px.y * g.W]);
+        double v[24];
+        if (y >= 10 && y + 13 < g.H) {
 #pragma unroll
-        for (int d = 1; d <= 10; ++d) {
-            double hi = t[(long long)reflect101(px.y + d, g.H) * g.W], lo = t[(long long)reflect101(px.y - d, g.H) * g.W];
-            double pair = DERIV ? __dsub_rn(hi, lo) : __dadd_rn(hi, lo);
-            acc = __dadd_rn(acc, __dmul_rn(k[10 + d], pair));
+            for (int j = 0; j < 24; ++j) v[j] = col[(long long)(y - 10 + j) * g.W];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) v[j] = col[(long long)reflect101(y - 10 + j, g.H) * g.W];
         }
-        out[px.base + px.idx] = acc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (y + q >= g.H) break;
+            double acc = DERIV ? 0.0 : __dmul_rn(k[10], v[q + 10]);
+#pragma unroll
+            for (int d = 1; d <= 10; ++d) {
+                const double pair = DERIV ? __dsub_rn(v[q + 10 + d], v[q + 10 - d]) : __dadd_rn(v[q + 10 + d], v[q + 10 - d]);
+                acc = __dadd_rn(acc, __dmul_rn(k[10 + d], pair));
+            }
+            out[(long long)n * g.P + (long long)(y + q) * g.W + x] = acc;
+            lo = q == 0 ? acc : fmin(lo, acc);
+            hi = q == 0 ? acc : fmax(hi, acc);
+        }
     }
-    warp_minmax_commit(acc, acc, px.ok, mm + (long long)px.n * 2);
+    warp_minmax_commit(lo, hi, live, mm + (long long)n * 2);
 }
 
 __global__ void k_threshold_ge(Geom g, const float* __restrict__ x, float thr, uint8_t* __restrict__ out) {
@@ -170,22 +215,55 @@ k_gauss3_col_neg(Geom g, const double* __restrict__ src, double* __restrict__ ou
 // Erosion sees the outside of the image as foreground, dilation as background (morphologyDefaultBorderValue).
 template <bool ERODE>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_ellipse5(Geom g, const uint8_t* __restrict__ src, uint8_t* __restrict__ out) {
-    Pix px;
-    if (!warp_pixel(g, px) || !px.ok) return;
-    const uint8_t* t = src + px.base;
-    bool r = ERODE;
+k_ellipse5(Geom g, const uint8_t* __restrict__ src, uint8_t* __restrict__ out, bool vec) {
+    // one thread = four adjacent pixels; every row of the 5x5 ellipse (00100 / 11111 / 11111 / 11111 / 00100) is read as
+    // one 32-bit word plus the two bytes on each side.  Outside the image counts as set for the erosion, clear for the
+    // dilation (cv::morphologyEx default border).
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
+    const uint8_t* tile = src + (long long)n * g.P;
+    const unsigned OOB = ERODE ? 1u : 0u;
+    bool r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = ERODE;
+#pragma unroll
     for (int dy = -2; dy <= 2; ++dy) {
-        int yy = px.y + dy;
-        int half = (dy == -2 || dy == 2) ? 0 : 2;
-        for (int dx = -half; dx <= half; ++dx) {
-            int xx = px.x + dx;
-            bool inb = yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
-            bool v = inb ? t[yy * g.W + xx] != 0 : ERODE;
-            r = ERODE ? (r && v) : (r || v);
+        const int yy = y + dy;
+        const bool oky = yy >= 0 && yy < g.H;
+        const uint8_t* row = tile + (long long)yy * g.W;
+        unsigned b[8];                                           // columns x-2 .. x+5
+        if (oky && vec) {
+            const unsigned w = *reinterpret_cast<const unsigned*>(row + x);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b[2 + k] = ((w >> (8 * k)) & 255u) != 0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b[2 + k] = (oky && x + k < g.W) ? (unsigned)(row[x + k] != 0) : OOB;
+        }
+        if (dy == -2 || dy == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = ERODE ? (r[k] && b[2 + k]) : (r[k] || b[2 + k]);
+            continue;
+        }
+        b[0] = (oky && x - 2 >= 0) ? (unsigned)(row[x - 2] != 0) : OOB;
+        b[1] = (oky && x - 1 >= 0) ? (unsigned)(row[x - 1] != 0) : OOB;
+        b[6] = (oky && x + 4 < g.W) ? (unsigned)(row[x + 4] != 0) : OOB;
+        b[7] = (oky && x + 5 < g.W) ? (unsigned)(row[x + 5] != 0) : OOB;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool all5 = b[k] && b[k + 1] && b[k + 2] && b[k + 3] && b[k + 4];
+            const bool any5 = b[k] || b[k + 1] || b[k + 2] || b[k + 3] || b[k + 4];
+            r[k] = ERODE ? (r[k] && all5) : (r[k] || any5);
         }
     }
-    out[px.base + px.idx] = r;
+    uint8_t* o = out + (long long)n * g.P + (long long)y * g.W + x;
+    if (vec) *reinterpret_cast<unsigned*>(o) = (unsigned)r[0] | ((unsigned)r[1] << 8) | ((unsigned)r[2] << 16) | ((unsigned)r[3] << 24);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (x + k < g.W) o[k] = r[k];
+    }
 }
 
 int postproc_hover_dev(tiseg_ctx* c, const Geom& g, const float* fore, const float* hv, int obj_size, int32_t* inst,
@@ -214,13 +292,15 @@ int postproc_hover_dev(tiseg_ctx* c, const Geom& g, const float* fore, const flo
     TISEG_TRY(remove_small_mask(c, g, m0, 10, 1, blb));
     // normalised H / V maps
     TISEG_LAUNCH(c, k_mm_init, (4 * N + 255) / 256, 256, 0, mm, 4 * N);
-    TISEG_LAUNCH(c, k_hv_minmax, warp_grid(g), TISEG_THREADS, 0, g, hv2, mm_hv);
+    TISEG_LAUNCH(c, k_hv_minmax, dim3((unsigned)((g.P + 8 * TISEG_THREADS - 1) / (8 * TISEG_THREADS)), (unsigned)N), TISEG_THREADS, 0, g, hv2, mm_hv);
     TISEG_LAUNCH(c, k_hv_normalize, warp_grid(g), TISEG_THREADS, 0, g, hv2, mm_hv, hdir, vdir);
     // Sobel(h_dir, dx=1): derivative along x, smoothing along y;  Sobel(v_dir, dy=1): the transpose
-    TISEG_LAUNCH(c, k_sobel_row<true>, warp_grid(g), TISEG_THREADS, 0, g, hdir, rowb);
-    TISEG_LAUNCH(c, k_sobel_col<false>, warp_grid(g), TISEG_THREADS, 0, g, rowb, sobh, mm_sh);
-    TISEG_LAUNCH(c, k_sobel_row<false>, warp_grid(g), TISEG_THREADS, 0, g, vdir, rowb);
-    TISEG_LAUNCH(c, k_sobel_col<true>, warp_grid(g), TISEG_THREADS, 0, g, rowb, sobv, mm_sv);
+    const dim3 rg((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    const dim3 cg((unsigned)(((long long)((g.H + 3) / 4) * g.W + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_sobel_row<true>, rg, TISEG_THREADS, 0, g, hdir, rowb);
+    TISEG_LAUNCH(c, k_sobel_col<false>, cg, TISEG_THREADS, 0, g, rowb, sobh, mm_sh);
+    TISEG_LAUNCH(c, k_sobel_row<false>, rg, TISEG_THREADS, 0, g, vdir, rowb);
+    TISEG_LAUNCH(c, k_sobel_col<true>, cg, TISEG_THREADS, 0, g, rowb, sobv, mm_sv);
     // energy, thresholds, blurred distance
     TISEG_LAUNCH(c, k_hover_energy, warp_grid(g), TISEG_THREADS, 0, g, sobh, sobv, mm_sh, mm_sv, blb, dpre, mk0);
     TISEG_LAUNCH(c, k_gauss3_row, warp_grid(g), TISEG_THREADS, 0, g, dpre, rowb);
@@ -228,8 +308,9 @@ int postproc_hover_dev(tiseg_ctx* c, const Geom& g, const float* fore, const flo
     // markers: fill holes -> 5x5 elliptical opening -> 4-connected labels -> drop < obj_size (ids kept)
     TISEG_TRY(ccl_build(c, g, ImgNotMaskU8{mk0}, 1, par));
     TISEG_TRY(fill_from_complement_forest(c, g, par, mk1));
-    TISEG_LAUNCH(c, k_ellipse5<true>, warp_grid(g), TISEG_THREADS, 0, g, mk1, mk0);
-    TISEG_LAUNCH(c, k_ellipse5<false>, warp_grid(g), TISEG_THREADS, 0, g, mk0, mk1);
+    const bool ev = (g.W % 4 == 0) && ((((uintptr_t)mk0) | ((uintptr_t)mk1)) & 3) == 0;
+    TISEG_LAUNCH(c, k_ellipse5<true>, rg, TISEG_THREADS, 0, g, mk1, mk0, ev);
+    TISEG_LAUNCH(c, k_ellipse5<false>, rg, TISEG_THREADS, 0, g, mk0, mk1, ev);
     TISEG_TRY(ccl_label(c, g, ImgMaskU8{mk1}, 1, lab, nullptr));
     TISEG_TRY(remove_small_labels(c, g, lab, obj_size, markers));
     // watershed(dist, markers, mask = blb)
