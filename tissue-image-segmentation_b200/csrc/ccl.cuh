@@ -89,14 +89,16 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
     const int ty = blockIdx.x / g.SEG, tx = blockIdx.x - ty * g.SEG;
     const int x = tx * 32 + lane;
     const bool okx = x < g.W;
-    const int row0 = warp * 8, y0 = ty * CCL_TH + row0;
+    // rows are dealt to the warps round-robin (warp w owns rows w, w + 8, ...): a nucleus spreads over all eight warps, so
+    // they reach the barriers together instead of one warp doing a blob's unions while seven wait
+    const int yt = ty * CCL_TH;
     FOR_TILES(LISTED, g, n) {
     const long long base = (long long)n * g.P;
     // phase A: coalesced loads (8 independent rows in flight per lane), row-run initialisation
     int v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int y = y0 + r, vv = 0;
+        int y = yt + r * 8 + warp, vv = 0;
         v[r] = CCL_BG;
         if (okx && y < g.H && img(n, base + (long long)y * g.W + x, vv)) v[r] = vv;
     }
@@ -107,16 +109,16 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
         bool cont = lane > 0 && v[r] != CCL_BG && vl == v[r];
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (__ballot_sync(0xffffffffu, v[r] != CCL_BG)) fg |= 1u << r;
-        int li = (row0 + r) * 32 + lane;
+        int li = (r * 8 + warp) * 32 + lane;
         sval[li] = v[r];
-        slab[li] = v[r] != CCL_BG ? (row0 + r) * 32 + run_start_lane(m, lane) : -1;
+        slab[li] = v[r] != CCL_BG ? (r * 8 + warp) * 32 + run_start_lane(m, lane) : -1;
     }
     __syncthreads();
     // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border); rows without a
     // foreground pixel are skipped by the whole warp
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int row = row0 + r, li = row * 32 + lane;
+        int row = r * 8 + warp, li = row * 32 + lane;
         if (!((fg >> r) & 1u)) continue;
         if (row == 0 || v[r] == CCL_BG) continue;
         int u = sval[li - 32];
@@ -134,11 +136,11 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
     // phase C: local flatten, one global write per pixel
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int y = y0 + r;
+        int y = yt + r * 8 + warp;
         if (!okx || y >= g.H) continue;
         int out = -1;
         if (v[r] != CCL_BG) {
-            int root = uf_find(slab, (row0 + r) * 32 + lane);
+            int root = uf_find(slab, (r * 8 + warp) * 32 + lane);
             out = (ty * CCL_TH + (root >> 5)) * g.W + tx * 32 + (root & 31);
         }
         par[base + (long long)y * g.W + x] = out;
