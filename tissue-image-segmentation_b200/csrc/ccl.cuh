@@ -78,18 +78,19 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 //   k_ccl_flatten every pixel points at its global root (lowest flat index of the component = first pixel in
 //                 raster order); also leaves the bitmap of the roots for the id ranking that usually follows.
 // =====================================================================================================
-#define CCL_TH 64                       // tile rows (8 warps x 8 rows); tile width is one warp = 32 columns
+#define CCL_WARPS 8                     // warps per tile CTA
+#define CCL_TH (8 * CCL_WARPS)           // tile rows (each warp owns 8 of them); tile width is one warp = 32 columns
 #define CCL_BG INT_MIN                  // background marker inside the shared value tile
 
 template <class Img, int CONN, bool LISTED>
-__global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
+__global__ void __launch_bounds__(32 * CCL_WARPS, LISTED ? 1 : 2048 / (32 * CCL_WARPS)) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
     __shared__ int sval[CCL_TH * 32];
     __shared__ int slab[CCL_TH * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ty = blockIdx.x / g.SEG, tx = blockIdx.x - ty * g.SEG;
     const int x = tx * 32 + lane;
     const bool okx = x < g.W;
-    // rows are dealt to the warps round-robin (warp w owns rows w, w + 8, ...): a nucleus spreads over all eight warps, so
+    // rows are dealt to the warps round-robin (warp w owns rows w, w + CCL_WARPS, ...): a nucleus spreads over all eight warps, so
     // they reach the barriers together instead of one warp doing a blob's unions while seven wait
     const int yt = ty * CCL_TH;
     FOR_TILES(LISTED, g, n) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
     int v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int y = yt + r * 8 + warp, vv = 0;
+        int y = yt + r * CCL_WARPS + warp, vv = 0;
         v[r] = CCL_BG;
         if (okx && y < g.H && img(n, base + (long long)y * g.W + x, vv)) v[r] = vv;
     }
@@ -109,16 +110,16 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
         bool cont = lane > 0 && v[r] != CCL_BG && vl == v[r];
         unsigned m = __ballot_sync(0xffffffffu, cont);
         if (__ballot_sync(0xffffffffu, v[r] != CCL_BG)) fg |= 1u << r;
-        int li = (r * 8 + warp) * 32 + lane;
+        int li = (r * CCL_WARPS + warp) * 32 + lane;
         sval[li] = v[r];
-        slab[li] = v[r] != CCL_BG ? (r * 8 + warp) * 32 + run_start_lane(m, lane) : -1;
+        slab[li] = v[r] != CCL_BG ? (r * CCL_WARPS + warp) * 32 + run_start_lane(m, lane) : -1;
     }
     __syncthreads();
     // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border); rows without a
     // foreground pixel are skipped by the whole warp
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int row = r * 8 + warp, li = row * 32 + lane;
+        int row = r * CCL_WARPS + warp, li = row * 32 + lane;
         if (!((fg >> r) & 1u)) continue;
         if (row == 0 || v[r] == CCL_BG) continue;
         int u = sval[li - 32];
@@ -136,11 +137,11 @@ __global__ void __launch_bounds__(TISEG_THREADS, LISTED ? 1 : 8) k_ccl_local(Geo
     // phase C: local flatten, one global write per pixel
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        int y = yt + r * 8 + warp;
+        int y = yt + r * CCL_WARPS + warp;
         if (!okx || y >= g.H) continue;
         int out = -1;
         if (v[r] != CCL_BG) {
-            int root = uf_find(slab, (r * 8 + warp) * 32 + lane);
+            int root = uf_find(slab, (r * CCL_WARPS + warp) * 32 + lane);
             out = (ty * CCL_TH + (root >> 5)) * g.W + tx * 32 + (root & 31);
         }
         par[base + (long long)y * g.W + x] = out;
@@ -198,17 +199,17 @@ int ccl_build(tiseg_ctx* c, const Geom& g, Img img, int conn, int* par) {
     const int nb = (tilesY - 1) * g.W + (g.SEG - 1) * g.H * (conn == 2 ? 2 : 1);
     if (g.tl) {
         if (conn == 1) {
-            TISEG_LAUNCH(c, (k_ccl_local<Img, 1, true>), lg, TISEG_THREADS, 0, g, img, par);
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 1, true>), lg, 32 * CCL_WARPS, 0, g, img, par);
             if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
         } else {
-            TISEG_LAUNCH(c, (k_ccl_local<Img, 2, true>), lg, TISEG_THREADS, 0, g, img, par);
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 2, true>), lg, 32 * CCL_WARPS, 0, g, img, par);
             if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
         }
     } else if (conn == 1) {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 1, false>), lg, TISEG_THREADS, 0, g, img, par);
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 1, false>), lg, 32 * CCL_WARPS, 0, g, img, par);
         if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     } else {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 2, false>), lg, TISEG_THREADS, 0, g, img, par);
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 2, false>), lg, 32 * CCL_WARPS, 0, g, img, par);
         if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     }
     return ccl_flatten(c, g, par);
