@@ -140,7 +140,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -230,6 +230,9 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx.launch_count() - l0
 
+    # clocks and throttle reasons are sampled from the warm-up to the end of the end-to-end measurement (the timed
+    # regions themselves last tens of milliseconds, less than one nvidia-smi sampling period)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         with _lib.device_outputs():
             step(devt)
@@ -255,12 +258,10 @@ def run_b200(a):
             return plain_step(src)
         for _ in range(2):
             step(devt)
-    sampler = ClockSampler(local) if rank == 0 else None
     acc.zero_()
     ms, launches = timed(devt, a.steps, with_d2h=False)
     if launches_per_step is not None:
         launches = launches_per_step * a.steps             # replayed launches are not seen by the library's counter
-    clocks = sampler.stop() if sampler else None
     value = world * B * a.steps / (ms / 1e3)
 
     # e2e: same calls, inputs are pinned host buffers (the library stages them), result record read back.
@@ -293,6 +294,13 @@ def run_b200(a):
     ms_e2e, _ = timed(pinned_np, a.steps, with_d2h=True)
     step = step_resident
     e2e = world * B * a.steps / (ms_e2e / 1e3)
+    if sampler and len(open(sampler.f.name).read().splitlines()) < 5:
+        # a very short run: keep the same step going until a few samples exist
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            step(devt)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     h2d = int(sum(v.nbytes for v in pinned_np.values()))
     d2h = int(acc.numel() * 8)
 
