@@ -191,10 +191,14 @@ __device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulh
 
 // Copy the framed box of a blob into shared memory: lab = own index (seed), UNLAB (in the blob), NOTIN; lvl = level.
 // `tid`/`nthr`: the cooperating threads (a warp or a CTA); eight cells per thread are loaded before any is used.
+// Per-thread by-products (the caller reduces them if it wants them): the range [lmn, lmx] of the seed labels seen and
+// the lowest seed cell — a blob whose seeds all carry ONE label needs no ordered flood at all.
+struct SeedStats { int lmn, lmx, jseed; };
 template <class LT>
-__device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const LT* __restrict__ I,
-                                           const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
-                                           int y0, int x0, int w, int h, unsigned short* lab, LT* lvl) {
+__device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const LT* __restrict__ I,
+                                                const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
+                                                int y0, int x0, int w, int h, unsigned short* lab, LT* lvl) {
+    SeedStats st; st.lmn = 0x7fffffff; st.lmx = 0; st.jseed = 0x7fffffff;
     const int wp = w + 2, cells = wp * (h + 2);
     const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
     for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
@@ -218,9 +222,26 @@ __device__ __forceinline__ void stage_copy(int tid, int nthr, int W, const LT* _
                 const bool inblob = in[u] && tpv[u] == root;
                 lab[j] = (unsigned short)(inblob ? (ov[u] != 0 ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
                 lvl[j] = iv[u];
+                if (inblob && ov[u] != 0) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
             }
         }
     }
+    return st;
+}
+
+// warp-level: true if the staged blob has seeds and they all carry one label; then every in-blob cell is pointed at the
+// lowest seed cell (the write-back copies that seed's label) and the flood is skipped.  A 4-connected blob is flooded
+// completely from any seed, so with a single label there is nothing for the (value, age) order to decide.
+__device__ __forceinline__ bool fill_if_single_marker(int lane, SeedStats st, int cells, unsigned short* lab) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        st.lmn = min(st.lmn, __shfl_xor_sync(FULL, st.lmn, d));
+        st.lmx = max(st.lmx, __shfl_xor_sync(FULL, st.lmx, d));
+        st.jseed = min(st.jseed, __shfl_xor_sync(FULL, st.jseed, d));
+    }
+    if (st.lmx == 0 || st.lmn != st.lmx) return false;
+    for (int j = lane; j < cells; j += 32) if (lab[j] == WS_UNLAB) lab[j] = (unsigned short)st.jseed;
+    return true;
 }
 
 // One warp links the seeds of a staged blob into their buckets in raster order (32 cells per step, the seeds of one
@@ -585,16 +606,21 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
                 }
                 for (int i = lane; i < WM_R * SLOTS; i += 32) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
                 if (PROF) t0 = clock64();
+                unsigned single = 0;                                           // slots whose blob has one marker label
                 for (int s = 0; s < m; ++s) {
                     const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s);
                     const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     const long long base = (long long)n * g.P;
-                    stage_copy(lane, 32, W, image + base, par + base, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
+                    const SeedStats st = stage_copy(lane, 32, W, image + base, par + base, out + base, root, y0, x0, w, h,
+                                                    lab + s * cap, lvl + s * cap);
+                    __syncwarp();
+                    if (fill_if_single_marker(lane, st, (w + 2) * (h + 2), lab + s * cap)) single |= 1u << s;
                 }
                 __syncwarp();
                 int lmin = WS_LVL_NONE, lmax = -1, smin = WS_LVL_NONE;        // of slot `lane`
                 for (int s = 0; s < m; ++s) {
+                    if ((single >> s) & 1u) continue;                          // nothing to flood in this slot
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     int vmin, vmax, vsmin;
                     link_seeds(lane, (w + 2) * (h + 2), lab + s * cap, nxs + s * cap, lvl + s * cap, head, tail,
@@ -865,16 +891,21 @@ k_ws_flood_ranked(Geom g, const unsigned short* __restrict__ level, const int* _
                     mw = b.xmax[ko + bid] - mx0 + 1; mh = b.ymax[ko + bid] - my0 + 1;
                 }
                 for (int i = lane; i < m * cap; i += 32) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
+                unsigned single = 0;
                 for (int s = 0; s < m; ++s) {
                     const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s);
                     const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     const long long base = (long long)n * g.P;
-                    stage_copy(lane, 32, W, level + base, par + base, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
+                    const SeedStats st = stage_copy(lane, 32, W, level + base, par + base, out + base, root, y0, x0, w, h,
+                                                    lab + s * cap, lvl + s * cap);
+                    __syncwarp();
+                    if (fill_if_single_marker(lane, st, (w + 2) * (h + 2), lab + s * cap)) single |= 1u << s;
                 }
                 __syncwarp();
                 int lmax = -1, smin = WS_LVL_NONE;              // of slot `lane`
                 for (int s = 0; s < m; ++s) {
+                    if ((single >> s) & 1u) continue;
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     int vmin, vmax, vsmin;
                     link_seeds(lane, (w + 2) * (h + 2), lab + s * cap, nxs + s * cap, lvl + s * cap, head, tail,
