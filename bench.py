@@ -229,16 +229,20 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(src, steps, with_d2h):
+    def timed(src, steps, with_d2h, fork=None, join=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count()
         e0.record()
+        if src is devt and join is not None:
+            fork()                                         # the value lanes start after the start event
         for _ in range(steps):
             with _lib.device_outputs():
                 r = step(src)
             if with_d2h:
                 r.cpu()                                    # the step's metric record comes back to the host
+        if src is devt and join is not None:
+            join()                                         # the value lanes rejoin the timing stream
         if world > 1:
             dist.all_reduce(acc)                           # the only collective: metric accumulators
         e1.record()
@@ -260,25 +264,73 @@ def run_b200(a):
     # addresses).  --no-graph times the plain launches instead.
     launches_per_step = None
     if not a.no_graph:
+        # one graph per value lane (own stream, own workspace, own accumulator): successive steps alternate between the
+        # lanes, so the latency-bound kernels of one step (the ordered flood keeps ~10 warps per SM busy) share the
+        # SMs with the streaming kernels of the next.  Every step is still one full pass over one batch.
+        VL = max(1, a.value_lanes)
+        vstreams = [torch.cuda.Stream(dev) for _ in range(VL)]
+        vacc = [torch.zeros(16, dtype=torch.float64, device=dev) for _ in range(VL)]
+        graphs = []
+
+        def lane_step(k):
+            cls = ops.softmax_argmax(devt["sem_logit"])
+            inst = ops.postproc_dist(devt["dist_logit"])
+            aji, pq = ops.pair_metrics_bin(inst, devt["gt_inst"])
+            counts, valid = ops.sem_counts(cls, devt["gt_sem"], 2)
+            va = vacc[k]
+            va[0:2] += aji.sum(0); va[2:6] += pq.sum(0); va[6:16] += counts.sum(0).reshape(-1).double()
+
         torch.cuda.synchronize()
-        l0 = ctx.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            with _lib.device_outputs():
-                step(devt)
-        _lib.get_ctx(local)                                # re-bind the context to the ordinary stream
-        launches_per_step = ctx.launch_count() - l0
+        for k in range(VL):
+            with _lib.lane(10 + k, vstreams[k]), _lib.device_outputs():
+                for _ in range(3):
+                    lane_step(k)                                   # grow this lane's workspace before the capture
+            torch.cuda.synchronize()
+            lctx = None
+            with _lib.lane(10 + k):
+                lctx = _lib.get_ctx(local)
+            l0 = lctx.launch_count()
+            gk = torch.cuda.CUDAGraph()
+            with _lib.lane(10 + k), _lib.device_outputs():
+                with torch.cuda.graph(gk, stream=vstreams[k]):
+                    lane_step(k)
+            launches_per_step = lctx.launch_count() - l0
+            graphs.append(gk)
+        _lib.get_ctx(local)                                # re-bind the default context to the ordinary stream
         plain_step = step
+        turn = [0]
 
         def step(src):                                     # noqa: F811  (timed() looks the name up at call time)
-            if src is devt:
-                graph.replay()
-                return acc
-            return plain_step(src)
-        for _ in range(2):
+            if src is not devt:
+                return plain_step(src)
+            k = turn[0] % VL
+            turn[0] += 1
+            with torch.cuda.stream(vstreams[k]):
+                graphs[k].replay()
+            return acc
+
+        def fork_value_lanes():
+            cur = torch.cuda.current_stream(dev)
+            for k in range(VL):
+                vstreams[k].wait_stream(cur)
+
+        def join_value_lanes():
+            cur = torch.cuda.current_stream(dev)
+            for k in range(VL):
+                cur.wait_stream(vstreams[k])
+            acc.add_(torch.stack(vacc).sum(0))
+            for v in vacc:
+                v.zero_()
+        for v in vacc:
+            v.zero_()
+        fork_value_lanes()
+        for _ in range(2 * VL):
             step(devt)
+        join_value_lanes()
+        turn[0] = 0
     acc.zero_()
-    ms, launches = timed(devt, a.steps, with_d2h=False)
+    ms, launches = timed(devt, a.steps, with_d2h=False, fork=None if a.no_graph else fork_value_lanes,
+                         join=None if a.no_graph else join_value_lanes)
     if launches_per_step is not None:
         launches = launches_per_step * a.steps             # replayed launches are not seen by the library's counter
     value = world * B * a.steps / (ms / 1e3)
@@ -316,8 +368,12 @@ def run_b200(a):
     if sampler and len(open(sampler.f.name).read().splitlines()) < 5:
         # a very short run: keep the same step going until a few samples exist
         t_end = time.perf_counter() + 0.4
+        if not a.no_graph:
+            fork_value_lanes()
         while time.perf_counter() < t_end:
             step(devt)
+        if not a.no_graph:
+            join_value_lanes()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     h2d = int(sum(v.nbytes for v in pinned_np.values()))
@@ -377,7 +433,8 @@ def run_b200(a):
         "config": {"workload": WORKLOAD, "tile": [H, W], "tiles_per_step_per_gpu": B, "instances_per_tile": 900,
                    "distinct_tiles": a.distinct, "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (h2d / 1e6),
                    "parallelism": "tiles sharded per GPU, one all-reduce of metric accumulators",
-                   "launch": "plain stream launches" if a.no_graph else "CUDA graph replay of the step (value); plain launches on 4 lanes (e2e)"},
+                   "launch": "plain stream launches" if a.no_graph else
+                   "CUDA graph replay of the step, steps alternating over %d streams (value); plain launches on %d lanes (e2e)" % (a.value_lanes, a.lanes)},
         "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -401,6 +458,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=2, help="tiles timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a CUDA-graph replay of the step")
+    ap.add_argument("--value-lanes", type=int, default=2, help="resident-input steps alternate between this many streams")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
