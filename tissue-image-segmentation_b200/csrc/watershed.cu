@@ -117,8 +117,8 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
 //    seeds into their buckets in raster order (match_any), then LANE s FLOODS SLOT s: up to SLOTS independent floods
 //    advance per warp instruction.  Buckets are indexed by (level mod 32): a blob qualifies if its levels span < 32
 //    values (a distance map inside a nucleus does); the head and tail of the current level live in registers.
-//    Default geometry: 10 warps x 4096-cell arenas x 16 slots (variants behind TISEG_FLOOD_VARIANT for experiments,
-//    including QUAD floods where four lanes probe the four neighbours of one flood).
+//    Default geometry: 10 warps x 4096-cell arenas x 16 slots (other geometries behind TISEG_FLOOD_VARIANT).  A blob
+//    whose seeds all carry one label is simply filled (a 4-connected blob is flooded completely from any seed).
 //  * general floods — framed boxes beyond the arena, or level spans >= 32: one blob per CTA at a time, staged by all
 //    warps into one 45056-cell slice with all 256 buckets.  The first sm_count/12 CTAs start with this list so the
 //    largest blobs begin at t = 0; every CTA helps with it after the multi-slot work.  Level-span overflows found
@@ -284,78 +284,6 @@ __device__ __forceinline__ void link_seeds(int lane, int cells, const unsigned s
     }
 }
 
-// direction j of a quad lane: 0 up, 1 left, 2 right, 3 down (skimage's neighbour order)
-__device__ __forceinline__ int dir_off(int j, int wp) { return ((j == 0 || j == 3) ? wp : 1) * (j >= 2 ? 1 : -1); }
-
-// The ordered floods of the staged blobs of one warp: quad q (lanes 4q..4q+3) floods its own blob, lane k of the quad
-// probing neighbour k.  All quads run one warp-uniform loop (finished quads are predicated off), so the warp-level
-// primitives take the full mask.  cur / hcur / tcur (current level, head and tail of its bucket) are replicated in
-// the four lanes of a quad; lane k = 0 writes them back when the quad leaves a level.
-template <class Bucket>
-__device__ __forceinline__ void quad_flood(int lane, bool active, int wp, int smin, int lmax, unsigned short* lab,
-                                           unsigned short* nxs, const unsigned char* lvl, unsigned short* head,
-                                           unsigned short* tail, Bucket B) {
-    const int k = lane & 3;
-    const int off = dir_off(k, wp);
-    int cur = smin;
-    unsigned hcur = WS_END, tcur = WS_END;
-    if (active) { hcur = head[B(cur)]; tcur = tail[B(cur)]; }
-    for (;;) {
-        if (active && hcur == WS_END) {            // level exhausted: its bucket must read empty from now on
-            if (k == 0) { head[B(cur)] = (unsigned short)WS_END; tail[B(cur)] = (unsigned short)WS_END; }
-            do { ++cur; } while (cur <= lmax && (hcur = head[B(cur)]) == WS_END);
-            if (cur > lmax) active = false; else tcur = tail[B(cur)];
-        }
-        if (!__any_sync(FULL, active)) break;
-        __syncwarp();
-        const int pix = (int)hcur, nb = pix + off;
-        unsigned nxt = WS_END, L = 0, ln = WS_NOTIN;
-        int vn = 0;
-        if (active) { nxt = nxs[pix]; L = lab[pix]; ln = lab[nb]; vn = lvl[nb]; }
-        const bool push = ln == WS_UNLAB, same = push && vn == cur;
-        unsigned t = WS_END;
-        if (push && !same) t = tail[B(vn)];
-        // FIFO order of the pushes of this step inside the quad: who pushes to my level before / after me
-        const int key = push ? vn : (0x100 | k);
-        int below = -1, above = 4;
-#pragma unroll
-        for (int x = 1; x < 4; ++x) {
-            const int kp = __shfl_xor_sync(FULL, key, x), p = k ^ x;
-            if (kp == key) { if (p < k) below = max(below, p); else above = min(above, p); }
-        }
-        const unsigned bs = (__ballot_sync(FULL, same) >> (lane & ~3)) & 0xFu;
-        const unsigned bl = __ballot_sync(FULL, push && vn < cur);
-        __syncwarp();                              // every probe of this step precedes every update
-        if (active) hcur = nxt;
-        if (push) {
-            lab[nb] = (unsigned short)L;           // labelled at push time
-            nxs[nb] = (unsigned short)(above < 4 ? (unsigned)(pix + dir_off(above, wp)) : WS_END);
-            if (below < 0) {
-                if (same) { if (hcur != WS_END) nxs[tcur] = (unsigned short)nb; }
-                else if (t == WS_END) head[B(vn)] = (unsigned short)nb;
-                else nxs[t] = (unsigned short)nb;
-            }
-            if (above == 4 && !same) tail[B(vn)] = (unsigned short)nb;
-        }
-        if (bs) {
-            if (hcur == WS_END) hcur = (unsigned)(pix + dir_off(__ffs(bs) - 1, wp));
-            tcur = (unsigned)(pix + dir_off(31 - __clz(bs), wp));
-        }
-        if (bl) {                                  // (uniform) a lower level appeared somewhere in the warp
-            int pv = push ? vn : 256;
-            pv = min(pv, __shfl_xor_sync(FULL, pv, 1));
-            pv = min(pv, __shfl_xor_sync(FULL, pv, 2));
-            const bool descend = active && pv < cur;
-            if (descend && k == 0) {               // park the current bucket
-                head[B(cur)] = (unsigned short)hcur;
-                tail[B(cur)] = (unsigned short)(hcur == WS_END ? WS_END : tcur);
-            }
-            __syncwarp();
-            if (descend) { cur = pv; hcur = head[B(cur)]; tcur = tail[B(cur)]; }
-        }
-    }
-}
-
 // The ordered flood of one staged blob by ONE lane (the lanes of a warp flood different slots side by side).  The
 // head and tail of the current level's bucket live in registers.  A pop probes the four neighbours' labels; only the
 // unlabelled ones (about one per pop on average) run the push body — a loop over the set bits rather than four
@@ -510,7 +438,6 @@ template <int SLOTS> struct BucketSlot {    // heads of one level are contiguous
 };
 
 // General path: one blob per CTA at a time, staged by all warps into one WG_CAP-cell slice with all 256 buckets.
-template <bool QUAD>
 __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __restrict__ image, const int* __restrict__ par,
                                               const BlobInfo& b, const long long* list, int count, int* cursor, int* next,
                                               int* gheads, int32_t* out) {
@@ -550,8 +477,7 @@ __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __re
             int vmin, vmax, vsmin;
             link_seeds(lane, (int)cells, lab, nxs, lvl, head, tail, BucketAll{}, vmin, vmax, vsmin);
             __syncwarp();
-            if (QUAD) quad_flood(lane, lane < 4 && vsmin <= vmax, w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketAll{});
-            else if (lane == 0 && vsmin <= vmax) lane_flood(w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketAll{});
+            if (lane == 0 && vsmin <= vmax) lane_flood(w + 2, vsmin, vmax, lab, nxs, lvl, head, tail, BucketAll{});
         }
         __syncthreads();
         stage_writeback(threadIdx.x, blockDim.x, W, o, y0, x0, w, h, lab);
@@ -561,17 +487,17 @@ __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __re
 // The flood kernel.  CTAs below `gen_first` start with the general list (the few largest blobs begin at t = 0), every
 // CTA then drains the multi-slot classes from the largest to the smallest (`do_multi`), and finally helps with what
 // is left of the general list.
-template <int WARPS, int ARENA, int SLOTS, bool QUAD, bool PROF>
+template <int WARPS, int ARENA, int SLOTS, bool PROF>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodWork wk,
               int* next, int* gheads, int32_t* out, int gen_first, int do_multi, long long* prof) {
     constexpr size_t WARP_BYTES = (size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4;
     if (!do_multi) {       // second launch: what the first one found too wide in levels
-        general_drain<QUAD>(g, image, par, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
+        general_drain(g, image, par, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
         return;
     }
     const int ngen = wk.ngen[0];
-    if ((int)blockIdx.x < min(gen_first, ngen) && ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    if ((int)blockIdx.x < min(gen_first, ngen) && ngen > 0) general_drain(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
     {
         __syncthreads();
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -629,16 +555,11 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
                 }
                 __syncwarp();
                 if (PROF) { long long t = clock64(); t_stage += t - t0; t0 = t; }
-                // ---- the floods: quad q / lane s floods slot q / s
+                // ---- the floods: lane s floods slot s
                 const bool overflow = lane < m && lmax - lmin >= WM_R;
                 if (overflow) wk.ovf[atomicAdd(wk.ngen + 1, 1)] = list[k0 + lane];
                 const unsigned ovf = __ballot_sync(FULL, overflow);
-                if (QUAD) {
-                    const int q = lane >> 2;
-                    const int qw = __shfl_sync(FULL, mw, q), qsmin = __shfl_sync(FULL, smin, q), qlmax = __shfl_sync(FULL, lmax, q);
-                    quad_flood(lane, q < m && !((ovf >> q) & 1u) && qsmin <= qlmax, qw + 2, qsmin, qlmax, lab + q * cap,
-                               nxs + q * cap, lvl + q * cap, head, tail, BucketSlot<SLOTS>{q});
-                } else {
+                {
                     int pops = 0;
                     if (lane < m && !overflow && smin <= lmax)
                         pops = lane_flood(mw + 2, smin, lmax, lab + lane * cap, nxs + lane * cap, lvl + lane * cap, head, tail,
@@ -668,7 +589,7 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
             p[0] = t_stage; p[1] = t_flood; p[2] = t_wb; p[3] = clock64() - t_all; p[4] = iters;
         }
     }
-    if (ngen > 0) general_drain<QUAD>(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    if (ngen > 0) general_drain(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
 }
 
 // ---- fp64 values, fast path: per-blob dense ranks + the same bucket flood ---------------------------------------------
@@ -1068,10 +989,10 @@ static inline int flood_blocks(tiseg_ctx* c, int N) {
     return per_tile;
 }
 
-template <int WARPS, int ARENA, int SLOTS, bool QUAD>
+template <int WARPS, int ARENA, int SLOTS>
 static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const BlobInfo& b,
                         FloodWork wk, int* next, int* gheads, int32_t* out, int* ints, bool debug) {
-    static_assert(SLOTS <= WS_MAXCLS && (!QUAD || SLOTS <= 8), "slots");
+    static_assert(SLOTS <= WS_MAXCLS, "slots");
     constexpr size_t MULTI = (size_t)WARPS * ((size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4);
     constexpr size_t SMEM = MULTI > WG_SMEM_BYTES ? MULTI : WG_SMEM_BYTES;
     static_assert(SMEM + 64 <= 232448, "shared memory");
@@ -1080,8 +1001,8 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
     static bool attr_set = false;
     if (!attr_set) {
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     const int gen_first = c->sm_count >= 8 ? c->sm_count / 4 : 1;     // at most this many CTAs, one per listed blob
@@ -1089,20 +1010,20 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     if (debug) {
         prof = ws<long long>(c, (size_t)c->sm_count * WARPS * 5);
         if (!prof) return TISEG_ERR_CUDA;
-        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, true>), c->sm_count, 32 * WARPS, SMEM, g,
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, true>), c->sm_count, 32 * WARPS, SMEM, g,
                         image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     } else {
-        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count, 32 * WARPS, SMEM, g,
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false>), c->sm_count, 32 * WARPS, SMEM, g,
                         image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     }
     // blobs found too wide in levels after the other CTAs had left the general list; exits at once if there are none
-    TISEG_LAUNCH_AS(c, "k_ws_flood_u8(level-span overflow)", (k_ws_flood_u8<WARPS, ARENA, SLOTS, QUAD, false>), c->sm_count,
+    TISEG_LAUNCH_AS(c, "k_ws_flood_u8(level-span overflow)", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false>), c->sm_count,
                     32 * WARPS, SMEM, g, image, par, b, wk, next, gheads, out, 0, 0, nullptr);
     if (debug) {                                  // work-list census on stderr (synchronises; diagnostics only)
         int h[WK_INTS];
         TISEG_CHECK(cudaMemcpyAsync(h, ints, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         TISEG_CHECK(cudaStreamSynchronize(c->stream));
-        fprintf(stderr, "[tiseg flood] warps %d arena %d slots %d quad %d | N=%d classes:", WARPS, ARENA, SLOTS, (int)QUAD, g.N);
+        fprintf(stderr, "[tiseg flood] warps %d arena %d slots %d | N=%d classes:", WARPS, ARENA, SLOTS, g.N);
         for (int k = 0; k < SLOTS; ++k) fprintf(stderr, " %d", h[k]);
         fprintf(stderr, " | general: %d, level-span overflow: %d\n", h[4 * WS_MAXCLS], h[4 * WS_MAXCLS + 1]);
         std::vector<long long> hp((size_t)c->sm_count * WARPS * 5);
@@ -1134,14 +1055,11 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
     TISEG_TRY(zero(c, ints, WK_INTS * sizeof(int)));
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
-    switch (variant) {
-        case 1: return flood_launch<12, 3584, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 2: return flood_launch<16, 2688, 8, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 3: return flood_launch<8, 5376, 8, true>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 5: return flood_launch<12, 3584, 8, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 6: return flood_launch<9, 4608, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 7: return flood_launch<8, 5376, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        default: return flood_launch<10, 4096, 16, false>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+    switch (variant) {            // arena geometries kept for tuning on other blob-size distributions
+        case 1: return flood_launch<8, 5376, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 2: return flood_launch<16, 2688, 8>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 3: return flood_launch<12, 3584, 8>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        default: return flood_launch<10, 4096, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
     }
 }
 
