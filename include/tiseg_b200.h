@@ -200,6 +200,13 @@ int tiseg_pair_metrics_multiclass(tiseg_ctx* ctx, const int32_t* pred_inst, cons
 int tiseg_sem_counts(tiseg_ctx* ctx, const uint8_t* pred, const uint8_t* gt, int N, int H, int W, int C,
                      int ignore_index, int64_t* counts, int64_t* valid);
 
+/* ---- mudslide_watershed(seg, dir_graph, fore) (models/utils/postprocess.py:158-181 with get_graph_degree :12-28 and
+ * prepare :31-120; exported by the reference, enabled by no shipped config).  seg / fore [N,H,W] uint8 masks,
+ * dir_graph [N,H,W] uint8 direction labels 0..8, MODIFIED IN PLACE as the reference does (small direction regions
+ * cleared, directions filled in by the ordered pass).  pred_out, boundary_out uint8 masks. */
+int tiseg_mudslide_watershed(tiseg_ctx* ctx, const uint8_t* seg, uint8_t* dir_graph, const uint8_t* fore, int N, int H,
+                             int W, uint8_t* pred_out, uint8_t* boundary_out);
+
 /* ---- A14: distance transforms (label generation: datasets/ops/distance_map.py:93, direction_map.py:167,179,
  * unet_map.py:72, utils/direction_calculation.py:164; losses/surface_loss.py:7) -------------------------------
  * mask [N,H,W] uint8 (non-zero = object).  edt: fp64 Euclidean distance to the nearest zero pixel

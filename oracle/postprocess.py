@@ -345,3 +345,98 @@ def multitask_postprocess(inner_pred, sem_pred, variant="unet"):
 
 
 warnings.filterwarnings("ignore", category=DeprecationWarning, module="scipy")
+
+
+# --------------------------------------------------------------------------- mudslide_watershed
+_DIRX = [0, 0, -1, -1, -1, 0, 1, 1, 1]          # postprocess.py:37-38: (row, col) offset of direction k = 1..8
+_DIRY = [0, -1, -1, 0, 1, 1, 1, 0, -1]
+
+
+def graph_degree(graph):
+    """postprocess.py:12-28 ``get_graph_degree``: every pixel with a direction k adds one to the pixel BEHIND it
+    (position minus the direction vector)."""
+    n, m = graph.shape
+    degree = np.zeros((n, m), np.int16)
+    for i in range(n):
+        for j in range(m):
+            k = int(graph[i, j])
+            if k > 0:
+                nx, ny = i - _DIRX[k], j - _DIRY[k]
+                if 0 <= nx < n and 0 <= ny < m:
+                    degree[nx, ny] += 1
+    return degree
+
+
+def mudslide_prepare(seg, dir_graph, contour, degree):
+    """postprocess.py:31-120 ``prepare`` (plain-Python restatement of the numba kernel, same visiting order).
+    Mutates ``seg`` and ``dir_graph``; returns ``level``."""
+    h, w = seg.shape
+    vis = np.zeros((h, w), np.int16)
+    level = np.ones((h, w), np.int16)
+    hfa = np.zeros((h, w), np.int16)
+    seg[degree > 0] = 0                                              # :50-53
+    Q = []
+    for i in range(h):                                               # :55-78
+        for j in range(w):
+            ok1 = 0
+            if seg[i, j] == 1:
+                for k in range(1, 9):
+                    nx, ny = i + _DIRX[k], j + _DIRY[k]
+                    if nx < 0 or nx >= h or ny < 0 or ny >= w or seg[nx, ny] != 1:
+                        ok1 = 1
+            if ok1 == 1:                                             # ok2 can never become 1 (:66-67)
+                Q.append((i, j)); vis[i, j] = 1
+            if contour[i, j] > 0 and vis[i, j] == 0:
+                Q.append((i, j)); vis[i, j] = 1
+            k = int(dir_graph[i, j])
+            if k > 0:
+                nx, ny = i + _DIRX[k], j + _DIRY[k]
+                if 0 <= nx < h and 0 <= ny < w:
+                    hfa[nx, ny] = 1
+    it = 1
+    while Q:                                                         # :80-119
+        NQ = []
+        it += 1
+        for (x, y) in Q:
+            k = int(dir_graph[x, y])
+            if k != 0:
+                nx, ny = x + _DIRX[k], y + _DIRY[k]
+                if 0 <= nx < h and 0 <= ny < w and seg[nx, ny] > 0:
+                    if vis[nx, ny] == 0:
+                        NQ.append((nx, ny)); vis[nx, ny] = it
+                    if vis[nx, ny] == it:
+                        level[nx, ny] = min(level[nx, ny], level[x, y] - 1)
+                        if dir_graph[nx, ny] == 0:
+                            dir_graph[nx, ny] = dir_graph[x, y]
+        for (x, y) in Q:
+            for k in range(1, 9):
+                nx, ny = x + _DIRX[k], y + _DIRY[k]
+                if 0 <= nx < h and 0 <= ny < w and seg[nx, ny] > 0 and vis[nx, ny] == 0 and hfa[nx, ny] == 0:
+                    NQ.append((nx, ny)); vis[nx, ny] = it
+                    if dir_graph[nx, ny] == 0:
+                        dir_graph[nx, ny] = k
+                        level[nx, ny] = min(level[nx, ny], level[x, y] - 1)
+                    if level[x, y] <= -1:
+                        level[nx, ny] = min(level[nx, ny], level[x, y])
+        Q = NQ
+    return level
+
+
+def mudslide_watershed(seg, dir_graph, fore):
+    """postprocess.py:158-181.  ``dir_graph`` is modified in place like the reference does.  -> (pred, boundary)."""
+    seg = ndi.binary_fill_holes(seg)
+    fore = ndi.binary_fill_holes(fore)
+    fore = remove_small_objects(fore, 20)
+    seg[fore == 0] = 0
+    contour = (fore > 0) ^ (seg > 0)
+    dir_graph_pos = remove_small_objects(dir_graph > 0, 20)
+    dir_graph[dir_graph_pos == 0] = 0
+    small_area = remove_small_objects(seg, 60) ^ seg
+    du = graph_degree(dir_graph) > 1
+    du = remove_small_objects(du, 3)
+    level = mudslide_prepare(seg, dir_graph, contour, du)
+    pred = level <= 0
+    boundary = level > 0
+    pred = remove_small_objects(pred, 15, connectivity=1)
+    pred = pred ^ small_area
+    return pred, boundary

@@ -60,7 +60,8 @@ def load_reference():
     _stub("mmcv")
     sk = _stub("skimage")
     sk.measure = _stub("skimage.measure", label=scipy_label)
-    sk.morphology = _stub("skimage.morphology", remove_small_objects=None)
+    from oracle import postprocess as _opp          # scikit-image is absent: mudslide_watershed's remove_small_objects
+    sk.morphology = _stub("skimage.morphology", remove_small_objects=_opp.remove_small_objects)
     pkg = types.ModuleType("refutils")
     pkg.__path__ = [os.path.join(REF, "tiseg", "utils")]
     sys.modules["refutils"] = pkg
@@ -177,6 +178,26 @@ def main():
     zero = np.zeros((16, 16), np.int64)
     out["dd_zero_out"] = ddm.generate_direction_differential_map(torch.from_numpy(zero)[None], 9)[0].numpy()
     np.savez_compressed(os.path.join(HERE, "ordered_ref.npz"), **out)
+
+    # ---- mudslide_watershed (numba get_graph_degree / prepare run by the reference's own file)
+    mud = {}
+    specs = [(9700, 96, 110, 14, 2, 1, 0.0), (9701, 64, 64, 8, 1, 2, 0.05), (9702, 128, 100, 20, 3, 0, 0.1),
+             (9703, 40, 52, 5, 1, 1, 0.3), (9704, 150, 160, 40, 2, 1, 0.02)]
+    for j, (seed, H, W, n, ero, dil, noise) in enumerate(specs):
+        t = synth.gt_and_pred(seed, H, W, n=n)
+        inst = t["pred_inst"]
+        r2 = np.random.default_rng(seed)
+        fore = ndi.binary_dilation(inst > 0, iterations=dil) if dil else inst > 0
+        seg = ndi.binary_erosion(inst > 0, iterations=ero)
+        dl, _ = synth.direction_logits(r2, inst)
+        dirg = np.argmax(dl, 0).astype(np.int64)
+        dirg[r2.random((H, W)) < noise] = r2.integers(0, 9)
+        dirg[~fore] = 0
+        mud["m%d_seg" % j], mud["m%d_dir" % j], mud["m%d_fore" % j] = seg.copy(), dirg.copy(), fore.copy()
+        d_io = dirg.copy()
+        pred, boundary = pp.mudslide_watershed(seg.copy(), d_io, fore.copy())
+        mud["m%d_pred" % j], mud["m%d_boundary" % j], mud["m%d_dir_after" % j] = pred, boundary, d_io
+    np.savez_compressed(os.path.join(HERE, "mudslide_ref.npz"), **mud)
     print("golden vectors written to", HERE)
 
 

@@ -462,3 +462,35 @@ def test_softmax_argmax_tta_windows(H, W, window, overlap):
     top2 = np.sort(want, axis=1)[:, -2:]
     clear = (top2[:, 1] - top2[:, 0]) > 1e-6
     assert np.array_equal(cls[clear], want.argmax(1).astype(np.uint8)[clear])
+
+
+# --------------------------------------------------------------------------- mudslide_watershed (§8f rank 3)
+def test_mudslide_watershed_golden_and_oracle():
+    m = np.load(os.path.join(G, "mudslide_ref.npz"))
+    for j in range(5):
+        d = m["m%d_dir" % j].copy()
+        pred, boundary = ops.mudslide_watershed(m["m%d_seg" % j], d, m["m%d_fore" % j])
+        _diff(pred, m["m%d_pred" % j], "mudslide pred (golden %d)" % j)
+        _diff(boundary, m["m%d_boundary" % j], "mudslide boundary (golden %d)" % j)
+        _diff(d, m["m%d_dir_after" % j], "mudslide dir_graph after (golden %d)" % j)
+    # a batch of full-size tiles against the oracle
+    rng = np.random.default_rng(31)
+    segs, dirs, fores = [], [], []
+    for j in range(2):
+        t = synth.gt_and_pred(9800 + j, 256, 256, n=60)
+        inst = t["pred_inst"]
+        fore = ndi.binary_dilation(inst > 0, iterations=1)
+        seg = ndi.binary_erosion(inst > 0, iterations=2)
+        dl, _ = synth.direction_logits(rng, inst)
+        dg = np.argmax(dl, 0).astype(np.uint8)
+        dg[rng.random(dg.shape) < 0.05] = 3
+        dg[~fore] = 0
+        segs.append(seg); dirs.append(dg); fores.append(fore)
+    dbatch = np.stack(dirs)
+    pred, boundary = ops.mudslide_watershed(np.stack(segs), dbatch, np.stack(fores))
+    for j in range(2):
+        dj = dirs[j].astype(np.int64)
+        wp, wb = opp.mudslide_watershed(segs[j].copy(), dj, fores[j].copy())
+        _diff(pred[j], wp, "mudslide pred tile %d" % j)
+        _diff(boundary[j], wb, "mudslide boundary tile %d" % j)
+        _diff(dbatch[j], dj, "mudslide dir_graph tile %d" % j)

@@ -202,3 +202,14 @@ def test_opencv_resize_x2_recipe_is_bit_exact():
         assert np.array_equal(R.resize_up2_linear(hv), cv2.resize(hv, (0, 0), fx=2, fy=2)), (H, W)
         lab = rng.integers(0, 1000, (2 * H, 2 * W)).astype(np.int32)
         assert np.array_equal(cv2.resize(lab, (W, H), interpolation=cv2.INTER_NEAREST), lab[::2, ::2])
+
+
+def test_mudslide_watershed_matches_numba_reference():
+    """oracle mudslide_watershed == the reference's numba get_graph_degree / prepare / mudslide_watershed
+    (tests/golden/mudslide_ref.npz, made by tests/golden/make_golden.py from the reference's own file)."""
+    m = np.load(os.path.join(G, "mudslide_ref.npz"))
+    for j in range(5):
+        d = m["m%d_dir" % j].copy()
+        pred, boundary = opp.mudslide_watershed(m["m%d_seg" % j].copy(), d, m["m%d_fore" % j].copy())
+        assert np.array_equal(pred, m["m%d_pred" % j]) and np.array_equal(boundary, m["m%d_boundary" % j])
+        assert np.array_equal(d, m["m%d_dir_after" % j])

@@ -338,3 +338,27 @@ def softmax_argmax_tta(variants, rotate_degrees, flip_directions, ori_hw, window
     get_ctx(_dev(packed)).call("tiseg_softmax_argmax_tta", ptr(packed), N, T, C, H, W, rots, flips, int(window),
                                int(overlap), ptr(prob), ptr(cls))
     return (cls, prob) if want_prob else cls
+
+
+def mudslide_watershed(seg, dir_graph, fore):
+    """models/utils/postprocess.py:158-181.  seg / fore: masks, dir_graph: direction labels 0..8 (modified in place when
+    it is a uint8 array or tensor; otherwise the updated copy is written back into the caller's array).
+    -> (pred, boundary) boolean masks."""
+    s, was2d = batched(as_input(np.asarray(seg) != 0 if not _lib_is_torch(seg) else seg != 0, np.uint8))
+    f, _ = batched(as_input(np.asarray(fore) != 0 if not _lib_is_torch(fore) else fore != 0, np.uint8))
+    d_in = dir_graph
+    d, _ = batched(as_input(d_in, np.uint8))
+    if not d.flags.writeable if not _lib_is_torch(d) else False:
+        d = d.copy()
+    N, H, W = s.shape
+    pred = empty_like_kind(s, (N, H, W), np.uint8)
+    bnd = empty_like_kind(s, (N, H, W), np.uint8)
+    get_ctx(_dev(s)).call("tiseg_mudslide_watershed", ptr(s), ptr(d), ptr(f), N, H, W, ptr(pred), ptr(bnd))
+    dv = _unbatch(d, was2d)
+    if dv is not d_in and not (_lib_is_torch(d_in) and d_in.data_ptr() == d.data_ptr()):
+        if _lib_is_torch(d_in):
+            d_in.copy_(dv.to(d_in.dtype))
+        elif isinstance(d_in, np.ndarray) and not np.shares_memory(d_in, d):
+            d_in[...] = np.asarray(dv).astype(d_in.dtype)
+    to_bool = (lambda a: a.bool()) if _lib_is_torch(pred) else (lambda a: a.astype(bool))
+    return to_bool(_unbatch(pred, was2d)), to_bool(_unbatch(bnd, was2d))
