@@ -194,6 +194,12 @@ int tiseg_pair_metrics_multiclass(tiseg_ctx* ctx, const int32_t* pred_inst, cons
                                   const int32_t* gt_inst, const uint8_t* gt_sem, int N, int H, int W, int C,
                                   double* aji, double* pq, double* bin_aji, double* bin_pq);
 
+/* assign_sem_class_to_insts (datasets/utils/instance_semantic.py:68-93) as a table: table_out [N, VM] uint8 with
+ * VM = max(H*W + 1, 65536); entry v = class of instance id v (first argmax over the classes >= 1 of its pixel counts,
+ * 0 if it has no non-background pixel; id 0 is class 0), 255 = the id does not occur. */
+int tiseg_assign_sem_class(tiseg_ctx* ctx, const int32_t* inst, const uint8_t* sem, int N, int H, int W, int C,
+                           uint8_t* table_out);
+
 /* ---- A19: pre_eval_all_semantic_metric (sem_metrics.py:16-53) --------------------------------------
  * pred / gt [N,H,W] uint8; counts [N, 5, C] int64 = TP, FP, FN, Pred, GT per class (TN derived on the
  * host as N_valid - (TP+FP+FN)); valid [N] int64 = pixels with gt != ignore_index. */

@@ -494,3 +494,43 @@ def test_mudslide_watershed_golden_and_oracle():
         _diff(pred[j], wp, "mudslide pred tile %d" % j)
         _diff(boundary[j], wb, "mudslide boundary tile %d" % j)
         _diff(dbatch[j], dj, "mudslide dir_graph tile %d" % j)
+
+
+def test_assign_sem_class_to_insts_matches_reference():
+    """datasets/utils/instance_semantic.py:68-93 against the (class, id) pairs the reference's own function produced
+    (tests/golden/metrics_ref.npz), dict order included."""
+    from tiseg_b200 import metrics as M
+    m = np.load(os.path.join(G, "metrics_ref.npz"))
+    names = sorted(k[:-len("_cls_pred")] for k in m.files if k.endswith("_cls_pred"))
+    assert names
+    for n in names:
+        for side in ("pred", "gt"):
+            got = M.assign_sem_class_to_insts(M.re_instance(m[n + "_" + side]), m[n + "_" + side + "_sem"], 4)
+            flat = np.array([(c, i) for c, ids in got.items() for i in ids], np.int64).reshape(-1, 2)
+            assert np.array_equal(flat, m[n + "_cls_" + side]), (n, side)
+    assert np.array_equal(M.re_instance(m[names[0] + "_pred"]), m[names[0] + "_re_pred"])
+
+
+def test_debug_dataset_adds_bound_metrics():
+    """monuseg_debug.py:85,133-135: the three-class maps give BoundDice / BoundPrecision / BoundRecall (last class)."""
+    import torch
+    from tiseg_b200 import datasets, metrics as M
+    tiles = [synth.tile_unet(1, 60 + j, 128, 128, 2) for j in range(3)]
+    preds = []
+    for t in tiles:
+        cls = opp.argmax_classes(opp.softmax(t["sem_logit"]))
+        sem, inst = opp.unet_family_postprocess(cls, radius=1)
+        tc_pred = synth.three_class_map(inst).astype(np.uint8)
+        tc_gt = synth.three_class_map(t["gt_inst"]).astype(np.uint8)
+        preds.append(dict(sem_pred=sem.astype(np.uint8), inst_pred=inst.astype(np.int32), tc_pred=tc_pred, tc_gt=tc_gt))
+    ds = datasets.MoNuSegDatasetDebug(sem_gts=[t["gt_sem"] for t in tiles], inst_gts=[t["gt_inst"] for t in tiles])
+    res = ds.pre_eval(preds, [0, 1, 2])
+    assert all("bound_sem_pre_eval_res" in r for r in res)
+    ev, _ = ds.evaluate(res, logger="silent")
+    want = [tuple(torch.from_numpy(x) for x in om.pre_eval_all_semantic_metric(p["tc_pred"], p["tc_gt"], 3)) for p in preds]
+    bm = M.pre_eval_to_sem_metrics(want, metrics=["Dice", "Precision", "Recall"])
+    for k in ("Dice", "Precision", "Recall"):
+        assert ev["Bound" + k] == np.round(np.mean(bm[k][-1]) * 100, 2)
+    plain, _ = datasets.MoNuSegDataset(sem_gts=[t["gt_sem"] for t in tiles], inst_gts=[t["gt_inst"] for t in tiles]).evaluate(
+        [{k: v for k, v in r.items() if k != "bound_sem_pre_eval_res"} for r in res], logger="silent")
+    assert all(ev[k] == v for k, v in plain.items())

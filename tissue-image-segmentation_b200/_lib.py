@@ -50,6 +50,7 @@ SIGNATURES = {
     "tiseg_pair_metrics_bin": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tiseg_pair_metrics_multiclass": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tiseg_sem_counts": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "tiseg_assign_sem_class": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tiseg_mudslide_watershed": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tiseg_distance_transform_edt": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_distance_transform_cdt": [_vp, _vp, _i, _i, _i, _vp],

@@ -571,7 +571,44 @@ static int side_classes(tiseg_ctx* c, const Geom& g, const int32_t* inst, const 
 
 using namespace tiseg;
 
+// cls_out[n, v] = semantic class of instance id v (first argmax over classes >= 1, 0 without a non-background pixel), 255 = no such id
+__global__ void k_inst_class_table(const int* __restrict__ hist, int C, int VM, uint8_t* __restrict__ table) {
+    int n = blockIdx.y;
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= VM) return;
+    int cls = 255;
+    if (v == 0) cls = 0;
+    else {
+        const int* h = hist + ((long long)n * VM + v) * (C + 1);
+        int tot = 0, best = 0, bc = 0, fg = 0;
+        for (int c = 0; c <= C; ++c) tot += h[c];
+        if (tot > 0) {
+            for (int c = 1; c < C; ++c) { fg += h[c]; if (h[c] > best) { best = h[c]; bc = c; } }
+            cls = fg > 0 ? bc : 0;
+        }
+    }
+    table[(long long)n * VM + v] = (uint8_t)cls;
+}
+
 extern "C" {
+
+int tiseg_assign_sem_class(tiseg_ctx* c, const int32_t* inst, const uint8_t* sem, int N, int H, int W, int C, uint8_t* table_out) {
+    if (!c || !inst || !sem || !table_out || C < 2 || C > 64) { set_error("tiseg_assign_sem_class: bad argument (2 <= C <= 64)"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    size_t total = (size_t)N * g.P;
+    const int VM = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;
+    const int32_t* d_inst = in(c, inst, total);
+    const uint8_t* d_sem = in(c, sem, total);
+    uint8_t* d_tab = tiseg::out(c, table_out, (size_t)N * VM);
+    int* hist = ws<int>(c, (size_t)N * VM * (C + 1));
+    if (!d_inst || !d_sem || !d_tab || !hist) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, hist, (size_t)N * VM * (C + 1) * sizeof(int)));
+    TISEG_LAUNCH(c, k_inst_class_hist, warp_grid(g), TISEG_THREADS, 0, g, d_inst, d_sem, C, VM, hist, c->d_err);
+    TISEG_LAUNCH(c, k_inst_class_table, dim3((VM + 255) / 256, N), 256, 0, hist, C, VM, d_tab);
+    return end_call(c);
+}
 
 int tiseg_pair_metrics_bin(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, int N, int H, int W,
                            double* aji, double* pq) {

@@ -216,6 +216,43 @@ class MoNuSegDataset(CustomDataset):
     CLASSES = ('background', 'nuclei')
 
 
+class GlasDataset(CustomDataset):       # glas.py: '.png' images
+    CLASSES = ('background', 'nuclei')
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault('img_suffix', '.png')
+        super().__init__(*args, **kwargs)
+
+
+class MoNuSegDatasetDebug(CustomDataset):
+    """monuseg_debug.py: the predictions also carry the three-class maps ``tc_pred`` / ``tc_gt`` and the evaluation
+    adds the boundary class's Dice / Precision / Recall (``BoundDice`` ...)."""
+    CLASSES = ('background', 'nuclei')
+
+    def pre_eval(self, preds, indices, show=False, show_folder=None):
+        out = super().pre_eval(preds, indices, show, show_folder)
+        if not isinstance(preds, list):
+            preds = [preds]
+        C = len(self.CLASSES) + 1
+        for ks in self._groups(preds):
+            tc_p = self._stack([preds[k]['tc_pred'] for k in ks], np.uint8)
+            tc_g = self._stack([preds[k]['tc_gt'] for k in ks], np.uint8)
+            res = M.pre_eval_all_semantic_metric(tc_p, tc_g, C)            # monuseg_debug.py:85
+            for j, k in enumerate(ks):
+                out[k]['bound_sem_pre_eval_res'] = res[j]
+        return out
+
+    def evaluate(self, results, logger=None, **kwargs):
+        bound = [r['bound_sem_pre_eval_res'] for r in results]
+        rest = [{k: v for k, v in r.items() if k != 'bound_sem_pre_eval_res'} for r in results]
+        eval_results, storage = super().evaluate(rest, logger=logger, **kwargs)
+        bm = M.pre_eval_to_sem_metrics(bound, metrics=['Dice', 'Precision', 'Recall'])      # :133-135: the last class
+        extra = OrderedDict(('Bound' + k, np.round(np.mean(v[-1]) * 100, 2)) for k, v in bm.items())
+        storage['overall_metrics'].update(extra)
+        eval_results.update(extra)
+        return eval_results, storage
+
+
 class CPM17Dataset(CustomDataset):
     CLASSES = ('background', 'nuclei')
 

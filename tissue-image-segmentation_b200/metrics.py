@@ -237,3 +237,19 @@ def precision_recall(pred_label, target_label, num_classes, nan_to_num=None):
     res = pre_eval_all_semantic_metric(pred_label, target_label, num_classes, reduce_zero_label=False)
     r = pre_eval_to_sem_metrics([res], ['Precision', 'Recall'], nan_to_num)
     return r['Precision'], r['Recall']
+
+
+# --------------------------------------------------------------------------- tiseg/datasets/utils exports
+def re_instance(instance_map):
+    """datasets/utils/instance_semantic.py:5-15: sorted unique non-zero ids -> 1..K (int32)."""
+    return ops.re_instance(instance_map)
+
+
+def assign_sem_class_to_insts(inst_seg, sem_seg, num_classes):
+    """datasets/utils/instance_semantic.py:68-93 -> {class: [instance ids]} (id 0 always listed under class 0, ids in
+    ascending order inside a class, classes in order of first appearance over the ascending ids)."""
+    table = _host(ops.assign_sem_class(inst_seg, sem_seg, num_classes))
+    out = {}
+    for v in np.flatnonzero(table != 255):
+        out.setdefault(int(table[v]), []).append(int(v))
+    return out

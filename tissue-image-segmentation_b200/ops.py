@@ -362,3 +362,14 @@ def mudslide_watershed(seg, dir_graph, fore):
             d_in[...] = np.asarray(dv).astype(d_in.dtype)
     to_bool = (lambda a: a.bool()) if _lib_is_torch(pred) else (lambda a: a.astype(bool))
     return to_bool(_unbatch(pred, was2d)), to_bool(_unbatch(bnd, was2d))
+
+
+def assign_sem_class(inst, sem, num_classes):
+    """Class of every instance id as a table [N, VM] uint8 (255 = id absent); see ``metrics.assign_sem_class_to_insts``."""
+    x, was2d = batched(as_input(inst, np.int32))
+    sm, _ = batched(as_input(sem, np.uint8))
+    N, H, W = x.shape
+    VM = max(H * W + 1, 1 << 16)
+    table = empty_like_kind(x, (N, VM), np.uint8)
+    get_ctx(_dev(x)).call("tiseg_assign_sem_class", ptr(x), ptr(sm), N, H, W, int(num_classes), ptr(table))
+    return table[0] if was2d else table
