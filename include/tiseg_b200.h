@@ -221,6 +221,23 @@ int tiseg_mudslide_watershed(tiseg_ctx* ctx, const uint8_t* seg, uint8_t* dir_gr
 int tiseg_distance_transform_edt(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, double* out);
 int tiseg_distance_transform_cdt(tiseg_ctx* ctx, const uint8_t* mask, int N, int H, int W, int32_t* out);
 
+/* ---- train-time label generation -----------------------------------------------------------
+ * gen_instance_hv_map (datasets/ops/hv_map.py:18-97): inst [N,H,W] int32 -> hv_out [N,H,W,2] fp32 (x map, y map).
+ * The per-instance chessboard distance of DistanceLabelMake.__call__ (datasets/ops/distance_map.py:59-110), on an
+ * instance map already passed through its _fix_inst: dist_out [N,H,W] fp32, divided by the instance maximum when
+ * inst_norm != 0.  Instance ids must be < max(H*W+1, 65536) (deferred error otherwise). */
+int tiseg_gen_hv_map(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, float* hv_out);
+int tiseg_instance_distance_map(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, int inst_norm, float* dist_out);
+/* _fix_inst, the first step of every label maker (distance_map.py:41-57, bound_map.py:18-33, unet_map.py:36-51,
+ * direction_map.py:17-32): per id drop the 4-connected pieces under 5 px, split into 8-connected pieces, renumber
+ * 1..K in (id, raster order of the piece) order. */
+int tiseg_fix_inst(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, int32_t* out);
+/* BoundLabelMake.__call__ after _fix_inst (bound_map.py:62-88): sem_out = sem with unlabelled pixels zeroed (may be
+ * NULL), sem_w_bound_out = sem_out with edge_id on dilation(diamond(radius_dilate)) & ~erosion(diamond(radius_erode))
+ * of every instance. */
+int tiseg_bound_label(tiseg_ctx* ctx, const uint8_t* sem, const int32_t* inst, int N, int H, int W, int edge_id,
+                      int radius_dilate, int radius_erode, uint8_t* sem_out, uint8_t* sem_w_bound_out);
+
 #ifdef __cplusplus
 }
 #endif

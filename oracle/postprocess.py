@@ -440,3 +440,112 @@ def mudslide_watershed(seg, dir_graph, fore):
     pred = remove_small_objects(pred, 15, connectivity=1)
     pred = pred ^ small_area
     return pred, boundary
+
+
+# --------------------------------------------------------------------------- label generation
+def _bounding_box(img):
+    """hv_map.py:5-15 / distance_map.py:11-20."""
+    rows, cols = np.any(img, axis=1), np.any(img, axis=0)
+    rmin, rmax = np.where(rows)[0][[0, -1]]
+    cmin, cmax = np.where(cols)[0][[0, -1]]
+    return [rmin, rmax + 1, cmin, cmax + 1]
+
+
+def _expanded_box(inst_map, h, w):
+    box = _bounding_box(inst_map)
+    box[0] -= 2; box[2] -= 2; box[1] += 2; box[3] += 2
+    box[0] = max(box[0], 0); box[2] = max(box[2], 0); box[1] = min(box[1], h); box[3] = min(box[3], w)
+    return box
+
+
+def gen_instance_hv_map(inst_gt):
+    """hv_map.py:18-97."""
+    x_map = np.zeros(inst_gt.shape[:2], np.float32)
+    y_map = np.zeros(inst_gt.shape[:2], np.float32)
+    h, w = inst_gt.shape[:2]
+    for inst_id in np.unique(inst_gt):
+        if inst_id == 0:
+            continue
+        inst_map = np.array(inst_gt == inst_id, np.uint8)
+        box = _expanded_box(inst_map, h, w)
+        inst_map = inst_map[box[0]:box[1], box[2]:box[3]]
+        if inst_map.shape[0] < 2 or inst_map.shape[1] < 2:
+            continue
+        com = list(ndi.center_of_mass(inst_map))
+        com[0] = int(com[0] + 0.5); com[1] = int(com[1] + 0.5)
+        xr = np.arange(1, inst_map.shape[1] + 1) - com[1]
+        yr = np.arange(1, inst_map.shape[0] + 1) - com[0]
+        ix, iy = np.meshgrid(xr, yr)
+        ix[inst_map == 0] = 0; iy[inst_map == 0] = 0
+        ix = ix.astype("float32"); iy = iy.astype("float32")
+        if np.min(ix) < 0:
+            ix[ix < 0] /= -np.amin(ix[ix < 0])
+        if np.min(iy) < 0:
+            iy[iy < 0] /= -np.amin(iy[iy < 0])
+        if np.max(ix) > 0:
+            ix[ix > 0] /= np.amax(ix[ix > 0])
+        if np.max(iy) > 0:
+            iy[iy > 0] /= np.amax(iy[iy > 0])
+        x_map[box[0]:box[1], box[2]:box[3]][inst_map > 0] = ix[inst_map > 0]
+        y_map[box[0]:box[1], box[2]:box[3]][inst_map > 0] = iy[inst_map > 0]
+    return np.dstack([x_map, y_map])
+
+
+def fix_inst(inst_gt):
+    """distance_map.py:41-57 ``_fix_inst``: per id drop the 4-connected pieces below 5 px, split into 8-connected
+    components, renumber consecutively in (id, raster) order."""
+    cur = 0
+    new = np.zeros_like(inst_gt)
+    for inst_id in np.unique(inst_gt):
+        if inst_id == 0:
+            continue
+        m = remove_small_objects(inst_gt == inst_id, 5)
+        rem = sk_label(np.array(m, np.uint8))
+        rem[rem > 0] += cur
+        new[rem > 0] = rem[rem > 0]
+        cur += len(np.unique(rem[rem > 0]))
+    return new
+
+
+def instance_distance_map(inst_gt, inst_norm=True):
+    """distance_map.py:67-106 (after ``_fix_inst``): per-instance scipy chessboard distance on the expanded crop."""
+    dist = np.zeros(inst_gt.shape, np.float32)
+    h, w = inst_gt.shape[:2]
+    for inst_id in np.unique(inst_gt):
+        if inst_id == 0:
+            continue
+        inst_map = (inst_gt == inst_id).astype(np.uint8)
+        box = _expanded_box(inst_map, h, w)
+        inst_map = inst_map[box[0]:box[1], box[2]:box[3]]
+        if inst_map.shape[0] < 2 or inst_map.shape[1] < 2:
+            continue
+        d = ndi.distance_transform_cdt(inst_map).astype("float32")
+        if inst_norm:
+            mx = np.amax(d)
+            if mx <= 0:
+                continue
+            d = d / np.amax(d)
+        dist[box[0]:box[1], box[2]:box[3]][inst_map > 0] = d[inst_map > 0]
+    return dist
+
+
+def diamond(radius):
+    """skimage.morphology.diamond: {(x, y): |x| + |y| <= r} as uint8."""
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return (np.abs(X) + np.abs(Y) <= radius).astype(np.uint8)
+
+
+def bound_label(sem_gt, inst_gt, edge_id=2, radius=(3, 3)):
+    """bound_map.py:62-88 (after ``_fix_inst``) -> (sem_gt, sem_gt_w_bound)."""
+    sem_gt = sem_gt.copy()
+    sem_gt[inst_gt == 0] = 0
+    out = np.zeros_like(sem_gt)
+    out += sem_gt
+    for inst_id in np.unique(inst_gt):
+        if inst_id == 0:
+            continue
+        m = inst_gt == inst_id
+        bound = dilation(m, diamond(radius[0])) & (~erosion(m, diamond(radius[1])))
+        out[bound > 0] = edge_id
+    return sem_gt, out

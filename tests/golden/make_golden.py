@@ -56,6 +56,11 @@ def _stub(name, **attrs):
     return m
 
 
+def _opp_mod():
+    from oracle import postprocess as _opp
+    return _opp
+
+
 def load_reference():
     _stub("mmcv")
     sk = _stub("skimage")
@@ -198,6 +203,47 @@ def main():
         pred, boundary = pp.mudslide_watershed(seg.copy(), d_io, fore.copy())
         mud["m%d_pred" % j], mud["m%d_boundary" % j], mud["m%d_dir_after" % j] = pred, boundary, d_io
     np.savez_compressed(os.path.join(HERE, "mudslide_ref.npz"), **mud)
+
+    # ---- train-time label generation: gen_instance_hv_map / DistanceLabelMake run from the reference's own files
+    def load(modname, path):
+        spec = importlib.util.spec_from_file_location(modname, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    hv = load("ref_hv_map", os.path.join(REF, "tiseg/datasets/ops/hv_map.py"))
+    dmap = load("ref_distance_map", os.path.join(REF, "tiseg/datasets/ops/distance_map.py"))
+    lab = {}
+    for j, (seed, H, W, n) in enumerate([(9900, 64, 80, 10), (9901, 128, 100, 30), (9902, 256, 256, 60),
+                                         (9903, 40, 33, 3), (9904, 96, 96, 1)]):
+        t = synth.gt_and_pred(seed, H, W, n=n)
+        inst = t["gt_inst"].astype(np.int32)
+        if j == 4:                                   # one instance covering the whole tile, one thin line
+            inst[:] = 1
+        if j == 3:
+            inst[5, 2:30] = 77
+        lab["l%d_inst" % j] = inst
+        lab["l%d_hv" % j] = hv.gen_instance_hv_map(inst)
+        for norm in (0, 1):
+            data = dict(sem_gt=(inst > 0).astype(np.uint8), inst_gt=inst.copy(), seg_fields=[])
+            lab["l%d_dist%d" % (j, norm)] = dmap.DistanceLabelMake(inst_norm=bool(norm))(data)["dist_gt"]
+    # BoundLabelMake: skimage 0.18's dilation / erosion are ndi.grey_dilation / grey_erosion(footprint=selem)
+    sk = sys.modules["skimage"]
+    sk.morphology.dilation = lambda image, selem=None: ndi.grey_dilation(image, footprint=selem[::-1, ::-1])
+    sk.morphology.erosion = lambda image, selem=None: ndi.grey_erosion(image, footprint=selem)
+    sk.morphology.selem = _stub("skimage.morphology.selem", diamond=_opp_mod().diamond)
+    bmap = load("ref_bound_map", os.path.join(REF, "tiseg/datasets/ops/bound_map.py"))
+    for j in range(5):
+        inst = lab["l%d_inst" % j]
+        sem = ((inst % 3) + 1).astype(np.uint8) * (inst > 0)
+        lab["l%d_sem" % j] = sem
+        for radius in (1, 3, (2, 1)):
+            data = dict(sem_gt=sem.copy(), inst_gt=inst.copy(), seg_fields=[])
+            out = bmap.BoundLabelMake(edge_id=4, selem_radius=radius)(data)
+            tag = "l%d_r%s" % (j, "".join(str(r) for r in (radius if isinstance(radius, tuple) else (radius,))))
+            lab[tag + "_sem"], lab[tag + "_bound"] = out["sem_gt"], out["sem_gt_w_bound"]
+        lab["l%d_fixed" % j] = bmap.BoundLabelMake()._fix_inst(inst)
+    np.savez_compressed(os.path.join(HERE, "labelgen_ref.npz"), **lab)
     print("golden vectors written to", HERE)
 
 

@@ -534,3 +534,73 @@ def test_debug_dataset_adds_bound_metrics():
     plain, _ = datasets.MoNuSegDataset(sem_gts=[t["gt_sem"] for t in tiles], inst_gts=[t["gt_inst"] for t in tiles]).evaluate(
         [{k: v for k, v in r.items() if k != "bound_sem_pre_eval_res"} for r in res], logger="silent")
     assert all(ev[k] == v for k, v in plain.items())
+
+
+# --------------------------------------------------------------------------- label generation (§8f rank 4)
+def test_label_generation_golden_and_oracle():
+    m = np.load(os.path.join(G, "labelgen_ref.npz"))
+    for j in range(5):
+        inst = m["l%d_inst" % j]
+        hv = ops.gen_instance_hv_map(inst)
+        assert hv.shape == m["l%d_hv" % j].shape and hv.dtype == np.float32
+        _diff(hv, m["l%d_hv" % j], "hv map (golden %d)" % j)
+        fixed = opp.fix_inst(inst)
+        for norm in (0, 1):
+            _diff(ops.instance_distance_map(fixed, bool(norm)), m["l%d_dist%d" % (j, norm)],
+                  "distance map norm=%d (golden %d)" % (norm, j))
+    # a batch of larger tiles against the oracle, touching instances included
+    insts = np.stack([synth.gt_and_pred(9950 + j, 500, 500, n=250)["gt_inst"].astype(np.int32) for j in range(3)])
+    hv = ops.gen_instance_hv_map(insts)
+    d1 = ops.instance_distance_map(insts, True)
+    d0 = ops.instance_distance_map(insts, False)
+    for j in range(3):
+        _diff(hv[j], opp.gen_instance_hv_map(insts[j]), "hv map tile %d" % j)
+        _diff(d1[j], opp.instance_distance_map(insts[j], True), "distance map (norm) tile %d" % j)
+        _diff(d0[j], opp.instance_distance_map(insts[j], False), "distance map tile %d" % j)
+
+
+def test_fix_inst_and_bound_label_golden_and_oracle():
+    m = np.load(os.path.join(G, "labelgen_ref.npz"))
+    for j in range(5):
+        inst = m["l%d_inst" % j]
+        fixed = ops.fix_inst(inst)
+        _diff(fixed, m["l%d_fixed" % j], "fix_inst (golden %d)" % j)
+        for tag, radius in (("1", 1), ("3", 3), ("21", (2, 1))):
+            sem, bound = ops.bound_label(m["l%d_sem" % j], fixed, 4, radius)
+            _diff(sem, m["l%d_r%s_sem" % (j, tag)], "bound sem r=%s (golden %d)" % (tag, j))
+            _diff(bound, m["l%d_r%s_bound" % (j, tag)], "bound map r=%s (golden %d)" % (tag, j))
+    # ids with several pieces, pieces under 5 px, diagonal contacts, ids out of raster order
+    rng = np.random.default_rng(77)
+    insts = []
+    for j in range(3):
+        t = synth.gt_and_pred(9960 + j, 300, 340, n=120)["gt_inst"].astype(np.int32)
+        perm = rng.permutation(int(t.max()) + 1)
+        perm[perm == 0], perm[0] = perm[0], 0
+        a = perm[t] // 2 * 3                                     # merges pairs of ids -> multi-piece ids, gaps in the ids
+        a[rng.random(a.shape) < 0.02] = 0
+        a[rng.random(a.shape) < 0.01] = 5
+        insts.append(a.astype(np.int32))
+    insts = np.stack(insts)
+    fixed = ops.fix_inst(insts)
+    for j in range(3):
+        want = opp.fix_inst(insts[j])
+        _diff(fixed[j], want, "fix_inst tile %d" % j)
+        sem = ((want % 2) + 1).astype(np.uint8)
+        s2, b2 = ops.bound_label(sem, want, 3, 2)
+        ws_, wb = opp.bound_label(sem, want, 3, (2, 2))
+        _diff(s2, ws_, "bound sem tile %d" % j)
+        _diff(b2, wb, "bound map tile %d" % j)
+
+
+def test_label_maker_classes_follow_the_reference_protocol():
+    from tiseg_b200 import label_makers as lm
+    m = np.load(os.path.join(G, "labelgen_ref.npz"))
+    inst, sem = m["l1_inst"], m["l1_sem"]
+    d = lm.DistanceLabelMake(inst_norm=True)(dict(sem_gt=sem.copy(), inst_gt=inst.copy(), seg_fields=[]))
+    _diff(d["dist_gt"], m["l1_dist1"], "DistanceLabelMake dist_gt")
+    assert d["seg_fields"] == ["dist_gt"]
+    b = lm.BoundLabelMake(edge_id=4, selem_radius=(2, 1))(dict(sem_gt=sem.copy(), inst_gt=inst.copy(), seg_fields=[]))
+    _diff(b["sem_gt_w_bound"], m["l1_r21_bound"], "BoundLabelMake sem_gt_w_bound")
+    _diff(b["sem_gt"], m["l1_r21_sem"], "BoundLabelMake sem_gt")
+    h = lm.HVLabelMake()(dict(inst_gt=inst.copy(), seg_fields=[]))
+    _diff(h["hv_gt"], m["l1_hv"].transpose(2, 0, 1), "HVLabelMake hv_gt")

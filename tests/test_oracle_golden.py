@@ -213,3 +213,20 @@ def test_mudslide_watershed_matches_numba_reference():
         pred, boundary = opp.mudslide_watershed(m["m%d_seg" % j].copy(), d, m["m%d_fore" % j].copy())
         assert np.array_equal(pred, m["m%d_pred" % j]) and np.array_equal(boundary, m["m%d_boundary" % j])
         assert np.array_equal(d, m["m%d_dir_after" % j])
+
+
+def test_label_generation_matches_reference():
+    """oracle gen_instance_hv_map / fix_inst + instance_distance_map == datasets/ops/hv_map.py and
+    datasets/ops/distance_map.py (DistanceLabelMake) run from the reference's own files (labelgen_ref.npz)."""
+    m = np.load(os.path.join(G, "labelgen_ref.npz"))
+    for j in range(5):
+        inst = m["l%d_inst" % j]
+        assert np.array_equal(opp.gen_instance_hv_map(inst), m["l%d_hv" % j])
+        fixed = opp.fix_inst(inst)
+        for norm in (0, 1):
+            assert np.array_equal(opp.instance_distance_map(fixed, bool(norm)), m["l%d_dist%d" % (j, norm)])
+        assert np.array_equal(fixed, m["l%d_fixed" % j])
+        for tag, radius in (("1", (1, 1)), ("3", (3, 3)), ("21", (2, 1))):
+            sem, bound = opp.bound_label(m["l%d_sem" % j], fixed, 4, radius)
+            assert np.array_equal(sem, m["l%d_r%s_sem" % (j, tag)])
+            assert np.array_equal(bound, m["l%d_r%s_bound" % (j, tag)])

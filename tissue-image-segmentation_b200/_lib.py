@@ -52,6 +52,10 @@ SIGNATURES = {
     "tiseg_sem_counts": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_assign_sem_class": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tiseg_mudslide_watershed": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tiseg_gen_hv_map": [_vp, _vp, _i, _i, _i, _vp],
+    "tiseg_instance_distance_map": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "tiseg_fix_inst": [_vp, _vp, _i, _i, _i, _vp],
+    "tiseg_bound_label": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_distance_transform_edt": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_distance_transform_cdt": [_vp, _vp, _i, _i, _i, _vp],
 }

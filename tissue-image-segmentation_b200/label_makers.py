@@ -1,0 +1,48 @@
+"""Train-time label makers of ``tiseg/datasets/ops`` on the GPU.
+
+Same class names, constructor arguments and ``data`` dict protocol as the reference (``DistanceLabelMake``:
+datasets/ops/distance_map.py:23-142, ``HVLabelMake``: hv_map.py:100-114, ``BoundLabelMake``: bound_map.py:6-89).
+``DirectionLabelMake`` and ``UNetLabelMake`` (OpenCV Sobel-11 gradients, per-instance exact EDT stacks) are not built.
+"""
+import numpy as np
+
+from . import ops
+
+
+class HVLabelMake(object):
+    def __call__(self, data):
+        hv = ops.gen_instance_hv_map(data["inst_gt"])
+        data["hv_gt"] = hv.transpose(2, 0, 1)
+        data["seg_fields"].append("hv_gt")
+        return data
+
+
+class BoundLabelMake(object):
+    def __init__(self, edge_id=2, selem_radius=3):
+        self.edge_id = edge_id
+        if isinstance(selem_radius, int):
+            selem_radius = (selem_radius, selem_radius)
+        self.radius = selem_radius
+
+    def __call__(self, data):
+        inst_gt = ops.fix_inst(data["inst_gt"])
+        sem_gt, bound = ops.bound_label(data["sem_gt"], inst_gt, self.edge_id, self.radius)
+        assert np.array_equal(np.asarray(sem_gt) > 0, np.asarray(inst_gt) > 0)
+        data["sem_gt"] = sem_gt.astype(np.asarray(data["sem_gt"]).dtype, copy=False)
+        data["sem_gt_w_bound"] = bound.astype(data["sem_gt"].dtype, copy=False)
+        data["seg_fields"].append("sem_gt_w_bound")
+        return data
+
+
+class DistanceLabelMake(object):
+    def __init__(self, inst_norm=True):
+        self.inst_norm = inst_norm
+
+    def __call__(self, data):
+        sem_gt = np.asarray(data["sem_gt"])
+        inst_gt = ops.fix_inst(data["inst_gt"])
+        sem_gt = np.where(inst_gt == 0, 0, sem_gt).astype(sem_gt.dtype)
+        data["sem_gt"] = sem_gt
+        data["dist_gt"] = ops.instance_distance_map(inst_gt, self.inst_norm)
+        data["seg_fields"].append("dist_gt")
+        return data

@@ -373,3 +373,45 @@ def assign_sem_class(inst, sem, num_classes):
     table = empty_like_kind(x, (N, VM), np.uint8)
     get_ctx(_dev(x)).call("tiseg_assign_sem_class", ptr(x), ptr(sm), N, H, W, int(num_classes), ptr(table))
     return table[0] if was2d else table
+
+
+def gen_instance_hv_map(inst):
+    """datasets/ops/hv_map.py:18-97.  inst [H,W] / [N,H,W] int -> [.., H, W, 2] fp32 (x map, y map)."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W, 2), np.float32)
+    get_ctx(_dev(x)).call("tiseg_gen_hv_map", ptr(x), N, H, W, ptr(out))
+    return out[0] if was2d else out
+
+
+def instance_distance_map(inst, inst_norm=True):
+    """The distance target of DistanceLabelMake (datasets/ops/distance_map.py:59-110) for an instance map that
+    already went through its ``_fix_inst``: per-instance chessboard distance, optionally divided by its maximum."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.float32)
+    get_ctx(_dev(x)).call("tiseg_instance_distance_map", ptr(x), N, H, W, 1 if inst_norm else 0, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def fix_inst(inst):
+    """``_fix_inst`` of the label makers (datasets/ops/distance_map.py:41-57 and its copies)."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    out = empty_like_kind(x, (N, H, W), np.int32)
+    get_ctx(_dev(x)).call("tiseg_fix_inst", ptr(x), N, H, W, ptr(out))
+    return _unbatch(out, was2d)
+
+
+def bound_label(sem, inst, edge_id=2, selem_radius=3):
+    """BoundLabelMake.__call__ after ``_fix_inst`` (datasets/ops/bound_map.py:62-88) -> (sem_gt, sem_gt_w_bound)."""
+    if isinstance(selem_radius, int):
+        selem_radius = (selem_radius, selem_radius)
+    x, was2d = batched(as_input(inst, np.int32))
+    s, _ = batched(as_input(sem, np.uint8))
+    N, H, W = x.shape
+    sem_out = empty_like_kind(x, (N, H, W), np.uint8)
+    bound = empty_like_kind(x, (N, H, W), np.uint8)
+    get_ctx(_dev(x)).call("tiseg_bound_label", ptr(s), ptr(x), N, H, W, int(edge_id), int(selem_radius[0]),
+                          int(selem_radius[1]), ptr(sem_out), ptr(bound))
+    return _unbatch(sem_out, was2d), _unbatch(bound, was2d)
