@@ -40,7 +40,8 @@ KERNEL_BYTES_PER_PX = [
     ("(k_ccl_local<Img, 2", 4 + 4), ("(k_ccl_local<Img, 1", 1 + 4),     # values in (int32 label map / uint8), forest out
     ("(k_ccl_border", 4), ("k_ccl_flatten", 4 + 4),
     ("k_argmax_logits", 8 + 1), ("k_softmax_argmax", 8 + 1), ("k_dist_prep", 4 + 1),
-    ("k_min_candidates", 1 + 1), ("k_cand_invalid", 1 + 1), ("k_markers_from_plateaus", 4 + 4),
+    ("k_min_candidate_bits", 1 + 1.0 / 8), ("k_bitccl", 1.0 / 8), ("k_plateau_invalid", 1.0 / 8),
+    ("k_filter_root_bits", 1.0 / 8), ("k_markers_from_bits", 4 + 1.0 / 8),
     ("k_rank_bits", 4), ("k_rank_rowscan", 1.0 / 8), ("k_rank_place_bits", 1.0 / 8),
     ("k_blob_roots", 4), ("k_blob_bbox", 4), ("k_ws_hist", 4), ("k_wsl_remove", 4 + 4),
     ("k_pair_accumulate", 4 * 4), ("k_sem_counts", 2), ("memset", 1),

@@ -39,9 +39,7 @@ k_dist_prep(long long total, const float* __restrict__ dist, uint8_t* __restrict
 // not, every candidate component C inside it is a proper subset of the connected P, so some pixel of C touches an
 // equal-valued pixel outside C — which must be a non-candidate (a candidate would have joined C).  Hence:
 // minimum plateaus = candidate components without an "equal-valued non-candidate neighbour" flag.  On a distance map
-// the candidates are the few pixels around each nucleus centre, so the labelling pass skips almost every row.
-// One thread = four horizontally adjacent pixels (one 32-bit load per row); threads whose four pixels are all
-// background (the common case) stop after that single load.
+// the candidates are the few pixels around each nucleus centre.
 __device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ row, int x, int W, unsigned oob, bool vec) {
     if (vec) return *reinterpret_cast<const unsigned*>(row + x);
     unsigned r = 0;
@@ -49,99 +47,219 @@ __device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ row, int
     for (int k = 0; k < 4; ++k) r |= (x + k < W ? (unsigned)row[x + k] : oob) << (8 * k);
     return r;
 }
+// Candidates are a few percent of the pixels, so the plateau labelling works on one 32-bit word per 32-pixel row
+// segment (bits[n, y, seg]) and touches `par` / `low` only at the first pixel of each in-word run of candidates (the
+// nodes of the union-find).  Adjacent candidates always carry the same level (the higher one would have a lower
+// neighbour), so the labelling is binary.
+//   k_plateau_bits         candidate bitmap + bitmap of the candidates that touch an equal-valued non-candidate; nodes
+//   k_bitccl_link          one thread per non-empty word: unions with the word to the left and the three words above
+//   k_bitccl_flatten       nodes point at their root; bitmap of the roots; low[root] = 1 for plateaus with a bad pixel
+//   k_marker_scatter       the seed map (rank of the plateau's root on its pixels; zero elsewhere by memset)
+__device__ __forceinline__ int run_len_from(unsigned w, int a) {       // length of the run of ones starting at bit a
+    const unsigned x = w >> a;
+    return x == 0xffffffffu ? 32 : __ffs(~x) - 1;
+}
+__device__ __forceinline__ int run_start_of(unsigned w, int q) {       // first bit of the run of ones containing bit q
+    const unsigned below = ~w & ((1u << q) - 1u);
+    return below ? 32 - __clz(below) : 0;
+}
+
+// Candidate and "bad candidate" bitmaps in one sweep.  With J = I where a pixel is NOT a candidate and 255 where it
+// is, a candidate p touches an equal-valued non-candidate iff min3x3(J)(p) == I(p) (every neighbour of a candidate is
+// >= it).  So both maps are 3x3 minima.  A thread owns four pixels of a row as two u16x2 words (pixels 0,1 / 2,3) so
+// that a three-way minimum of two pixels is ONE instruction (VIMNMX3.U16x2, __vimin3_u16x2); a warp walks down
+// PB_ROWS rows of a 32-thread (128-pixel) wide column band keeping the last three row minima in registers, left / right
+// pixels come from the neighbouring lanes.  The outer four threads on each side are halo (the stencil of a stencil
+// needs two pixels), so a warp emits 24 x 4 pixels = three bitmap words per row.  Lane <-> column mapping: lanes
+// 0..23 = output columns, 24..27 = right halo, 28..31 = left halo (neighbours by lane rotation).
+#define PB_ROWS 32
+struct Px4 { unsigned lo, hi; };                      // (px0 | px1 << 16), (px2 | px3 << 16)
+__device__ __forceinline__ Px4 pb_hmin(Px4 v, int lane) {
+    const unsigned hl = __shfl_sync(0xffffffffu, v.hi, (lane + 31) & 31);      // pixels 2,3 of the thread to the left
+    const unsigned lr = __shfl_sync(0xffffffffu, v.lo, (lane + 1) & 31);       // pixels 0,1 of the thread to the right
+    const unsigned a = __byte_perm(hl, v.lo, 0x5432);                          // (px-1, px0)
+    const unsigned m = __byte_perm(v.lo, v.hi, 0x5432);                        // (px1, px2)
+    const unsigned z = __byte_perm(v.hi, lr, 0x5432);                          // (px3, px4)
+    Px4 r;
+    r.lo = __vimin3_u16x2(a, v.lo, m);
+    r.hi = __vimin3_u16x2(m, v.hi, z);
+    return r;
+}
+// per 16-bit lane (values <= 255): 1 where the lane is non-zero
+__device__ __forceinline__ unsigned pb_nonzero(unsigned x) { return ((x + 0x7fff7fffu) >> 15) & 0x00010001u; }
+// flags at bits 0 / 16 of (lo, hi) -> 4-bit nibble, bit k = pixel k
+__device__ __forceinline__ unsigned pb_nibble(unsigned lo, unsigned hi) {
+    const unsigned t = lo | (hi << 2);
+    return (t | (t >> 15)) & 15u;
+}
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_min_candidates(Geom g, const uint8_t* __restrict__ I, uint8_t* __restrict__ cand, bool vec) {
-    const int W4 = (g.W + 3) >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)W4 * g.H) return;
-    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
+k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbits, unsigned* __restrict__ badbits,
+               int* __restrict__ par, uint8_t* __restrict__ low, bool vec) {
+    const int lane = threadIdx.x & 31;
+    const int W4 = (g.W + 3) >> 2, S = (W4 + 23) / 24, bands = (g.H + PB_ROWS - 1) / PB_ROWS;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (wi >= (long long)S * bands) return;
+    const int band = (int)(wi / S), st = (int)(wi - (long long)band * S), n = blockIdx.y;
+    const int col = lane < 28 ? lane : lane - 32;
+    const int x = (st * 24 + col) * 4, y0 = band * PB_ROWS;
+    const bool inx = x >= 0 && x < g.W;
     const uint8_t* It = I + (long long)n * g.P;
-    uint8_t* out = cand + (long long)n * g.P + (long long)y * g.W + x;
-    const unsigned c = ld_u8x4(It + (long long)y * g.W, x, g.W, 255u, vec);
-    unsigned res = 0;
-    if (c != 0xffffffffu) {
-        // rows y-1, y, y+1, columns x-1 .. x+4; out-of-image taps can never be lower
-        unsigned rows[3]; int lft[3], rgt[3];
+    const int seg = st * 3 + (lane >> 3);
+    const bool writer = lane < 24 && (lane & 7) == 0 && seg < g.SEG;
+    const Px4 FF = {0x00ff00ffu, 0x00ff00ffu};
+    Px4 hI1 = FF, hI2 = FF;          // row minima of I, rows r-1 and r-2
+    Px4 hJ1 = FF, hJ2 = FF;          // row minima of J, rows r-2 and r-3
+    Px4 I1 = FF, I2 = FF;            // I of rows r-1, r-2
+    Px4 C2 = {0u, 0u};               // candidate flags (bits 0 / 16) of row r-2
+    const int yend = min(y0 + PB_ROWS, g.H);
+    for (int r0 = y0 - 2; r0 < yend + 2; r0 += 4) {
+        unsigned cw[4];
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            const bool ok = yy >= 0 && yy < g.H;
-            const uint8_t* rp = It + (long long)yy * g.W;
-            rows[dy + 1] = dy == 0 ? c : (ok ? ld_u8x4(rp, x, g.W, 255u, vec) : 0xffffffffu);
-            lft[dy + 1] = (ok && x > 0) ? rp[x - 1] : 255;
-            rgt[dy + 1] = (ok && x + 4 < g.W) ? rp[x + 4] : 255;
+        for (int k = 0; k < 4; ++k) {                    // four independent loads in flight
+            const int r = r0 + k;
+            cw[k] = (inx && r >= 0 && r < g.H) ? ld_u8x4(It + (long long)r * g.W, x, g.W, 255u, vec) : 0xffffffffu;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int v = (c >> (8 * k)) & 255;
-            int mn = 255;
-#pragma unroll
-            for (int r3 = 0; r3 < 3; ++r3) {
-                const int a = k == 0 ? lft[r3] : (int)((rows[r3] >> (8 * (k - 1))) & 255);
-                const int m = (int)((rows[r3] >> (8 * k)) & 255);
-                const int z = k == 3 ? rgt[r3] : (int)((rows[r3] >> (8 * (k + 1))) & 255);
-                mn = min(mn, min(a, min(m, z)));
+            const int r = r0 + k;
+            Px4 c;
+            c.lo = __byte_perm(cw[k], 0u, 0x4140);
+            c.hi = __byte_perm(cw[k], 0u, 0x4342);
+            const Px4 hI0 = pb_hmin(c, lane);
+            // candidates of row r-1: the 3x3 minimum (centre included) equals the pixel, and the pixel is below 255
+            Px4 C1, J;
+            {
+                const unsigned mlo = __vimin3_u16x2(hI0.lo, hI1.lo, hI2.lo), mhi = __vimin3_u16x2(hI0.hi, hI1.hi, hI2.hi);
+                const unsigned nlo = pb_nonzero(I1.lo - mlo) | (((I1.lo + 0x00010001u) >> 8) & 0x00010001u);
+                const unsigned nhi = pb_nonzero(I1.hi - mhi) | (((I1.hi + 0x00010001u) >> 8) & 0x00010001u);
+                C1.lo = nlo ^ 0x00010001u;
+                C1.hi = nhi ^ 0x00010001u;
+                J.lo = I1.lo | (C1.lo * 255u);
+                J.hi = I1.hi | (C1.hi * 255u);
             }
-            if (v < 255 && mn >= v) res |= 1u << (8 * k);
+            const Px4 hJ0 = pb_hmin(J, lane);
+            // bad candidates of row r-2
+            const unsigned jlo = __vimin3_u16x2(hJ0.lo, hJ1.lo, hJ2.lo), jhi = __vimin3_u16x2(hJ0.hi, hJ1.hi, hJ2.hi);
+            const unsigned Blo = C2.lo & ~pb_nonzero(jlo ^ I2.lo), Bhi = C2.hi & ~pb_nonzero(jhi ^ I2.hi);
+            const int y = r - 2;
+            if (y >= y0 && y < yend) {                   // (uniform)
+                unsigned w = (pb_nibble(C2.lo, C2.hi) | (pb_nibble(Blo, Bhi) << 16)) << (lane & 3) * 4;
+                // eight lanes x four pixels -> one 32-bit word of each map: lanes 0..3 of a group fill the low
+                // half-words, lanes 4..7 the high ones
+                w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                const unsigned o = __shfl_xor_sync(0xffffffffu, w, 4);
+                if (writer) {
+                    const unsigned cwd = (w & 0xffffu) | (o << 16), bwd = (w >> 16) | (o & 0xffff0000u);
+                    const long long wo = ((long long)n * g.H + y) * g.SEG + seg;
+                    cbits[wo] = cwd;
+                    badbits[wo] = bwd;
+                    unsigned starts = cwd & ~(cwd << 1);
+                    const long long po = (long long)n * g.P;
+                    const int idx0 = y * g.W + seg * 32;
+                    while (starts) {
+                        const int a = __ffs(starts) - 1;
+                        starts &= starts - 1;
+                        par[po + idx0 + a] = idx0 + a;
+                        low[po + idx0 + a] = 0;
+                    }
+                }
+            }
+            hI2 = hI1; hI1 = hI0; hJ2 = hJ1; hJ1 = hJ0; I2 = I1; I1 = c; C2 = C1;
         }
-    }
-    if (vec) *reinterpret_cast<unsigned*>(out) = res;
-    else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (x + k < g.W) out[k] = (uint8_t)((res >> (8 * k)) & 255);
     }
 }
 
-// low[root] = 1 if a pixel of the candidate component has an equal-valued neighbour that is not a candidate.
-// Candidates are rare: one 32-bit load tells a thread that its four pixels hold none; only candidate pixels probe
-// their eight neighbours (straight from L1/L2).
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_cand_invalid(Geom g, const uint8_t* __restrict__ I, const uint8_t* __restrict__ cand, const int* __restrict__ par,
-               uint8_t* low, bool vec) {
-    const int W4 = (g.W + 3) >> 2;
+k_bitccl_link(Geom g, const unsigned* __restrict__ bits, int* par) {
+    const long long words = (long long)g.H * g.SEG;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)W4 * g.H) return;
-    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, n = blockIdx.y;
-    const long long base = (long long)n * g.P;
-    const uint8_t* It = I + base;
-    const uint8_t* Ct = cand + base;
-    const unsigned c = ld_u8x4(Ct + (long long)y * g.W, x, g.W, 0u, vec);
-    if (!c) return;
-    // rows y-1, y, y+1, columns x-1 .. x+4 of the level image and of the candidate mask (out-of-image: level 255,
-    // which never equals a candidate's level)
-    unsigned iv[3], cv[3];
-    int il[3], ir[3], cl[3], cr[3];
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        const bool ok = yy >= 0 && yy < g.H;
-        const long long ro = (long long)yy * g.W;
-        iv[dy + 1] = ok ? ld_u8x4(It + ro, x, g.W, 255u, vec) : 0xffffffffu;
-        cv[dy + 1] = dy == 0 ? c : (ok ? ld_u8x4(Ct + ro, x, g.W, 1u, vec) : 0x01010101u);
-        il[dy + 1] = (ok && x > 0) ? It[ro + x - 1] : 255;
-        ir[dy + 1] = (ok && x + 4 < g.W) ? It[ro + x + 4] : 255;
-        cl[dy + 1] = (ok && x > 0) ? Ct[ro + x - 1] : 1;
-        cr[dy + 1] = (ok && x + 4 < g.W) ? Ct[ro + x + 4] : 1;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    const unsigned* B = bits + (long long)n * words;
+    const unsigned w = B[t];
+    if (!w) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    int* tp = par + (long long)n * g.P;
+    const int idx0 = y * g.W + seg * 32;
+    const unsigned lw = seg > 0 ? B[t - 1] : 0u;
+    unsigned up = 0, upl = 0, upr = 0;
+    if (y > 0) {
+        up = B[t - g.SEG];
+        if (seg > 0) upl = B[t - g.SEG - 1];
+        if (seg + 1 < g.SEG) upr = B[t - g.SEG + 1];
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!((c >> (8 * k)) & 255)) continue;
-        const int v = (iv[1] >> (8 * k)) & 255;
-        bool bad = false;
-#pragma unroll
-        for (int r3 = 0; r3 < 3; ++r3) {
-            const int ia = k == 0 ? il[r3] : (int)((iv[r3] >> (8 * (k - 1))) & 255);
-            const int ca = k == 0 ? cl[r3] : (int)((cv[r3] >> (8 * (k - 1))) & 255);
-            const int im = (int)((iv[r3] >> (8 * k)) & 255), cm = (int)((cv[r3] >> (8 * k)) & 255);
-            const int iz = k == 3 ? ir[r3] : (int)((iv[r3] >> (8 * (k + 1))) & 255);
-            const int cz = k == 3 ? cr[r3] : (int)((cv[r3] >> (8 * (k + 1))) & 255);
-            bad |= (ia == v && !ca) || (iz == v && !cz);
-            if (r3 != 1) bad |= im == v && !cm;
+    const int up0 = idx0 - g.W;
+    unsigned m = w;
+    while (m) {
+        const int a = __ffs(m) - 1, len = run_len_from(m, a), b = a + len - 1;
+        m = len == 32 ? 0u : m & ~(((1u << len) - 1u) << a);
+        const int node = idx0 + a;
+        if (a == 0 && (lw >> 31)) uf_union(tp, node, idx0 - 32 + run_start_of(lw, 31));
+        if (y == 0) continue;
+        if (a == 0 && (upl >> 31)) uf_union(tp, node, up0 - 32 + run_start_of(upl, 31));
+        if (b == 31 && (upr & 1u)) uf_union(tp, node, up0 + 32);
+        const int lo = a > 0 ? a - 1 : 0, hi = b < 31 ? b + 1 : 31;
+        const unsigned range = (hi - lo == 31) ? 0xffffffffu : (((1u << (hi - lo + 1)) - 1u) << lo);
+        unsigned um = up & range;
+        while (um) {
+            const int q = __ffs(um) - 1;
+            const int st = run_start_of(up, q), ul = run_len_from(up, st);
+            um = ul == 32 ? 0u : um & ~(((1u << ul) - 1u) << st);
+            uf_union(tp, node, up0 + st);
         }
-        if (bad) {
-            int root = par[base + (long long)y * g.W + x + k];
-            if (!low[base + root]) low[base + root] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_bitccl_flatten(Geom g, const unsigned* __restrict__ bits, const unsigned* __restrict__ badbits, int* par, uint8_t* low,
+                 unsigned* __restrict__ rootbits) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    const unsigned w = bits[(long long)n * words + t];
+    unsigned rb = 0;
+    if (w) {
+        const unsigned bad = badbits[(long long)n * words + t];
+        const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+        int* tp = par + (long long)n * g.P;
+        const int idx0 = y * g.W + seg * 32;
+        unsigned starts = w & ~(w << 1);
+        while (starts) {
+            const int a = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int r = uf_find(tp, idx0 + a);
+            if (r == idx0 + a) rb |= 1u << a; else tp[idx0 + a] = r;
+            const int len = run_len_from(w, a);
+            const unsigned runmask = len == 32 ? 0xffffffffu : (((1u << len) - 1u) << a);
+            // a plateau with a pixel that touches an equal-valued non-candidate is not a regional minimum
+            if ((bad & runmask) && !low[(long long)n * g.P + r]) low[(long long)n * g.P + r] = 1;
         }
+    }
+    rootbits[(long long)n * words + t] = rb;
+}
+
+// seeds: rank of the plateau's root on the pixels of every run of a minimum plateau (the map is zeroed beforehand)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_marker_scatter(Geom g, const unsigned* __restrict__ bits, const int* __restrict__ par, const uint8_t* __restrict__ low,
+                 const int* __restrict__ rank, int32_t* __restrict__ markers) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    unsigned w = bits[(long long)n * words + t];
+    if (!w) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    const long long base = (long long)n * g.P;
+    const int idx0 = y * g.W + seg * 32;
+    while (w) {
+        const int a = __ffs(w) - 1, len = run_len_from(w, a);
+        w = len == 32 ? 0u : w & ~(((1u << len) - 1u) << a);
+        const int root = par[base + idx0 + a];
+        if (low[base + root]) continue;
+        const int id = rank[base + root];
+        for (int k = 0; k < len; ++k) markers[base + idx0 + a + k] = id;
     }
 }
 
@@ -162,27 +280,6 @@ k_filter_root_bits(Geom g, const uint8_t* __restrict__ low, unsigned* bits) {
         if (low[(long long)n * g.P + (long long)y * g.W + seg * 32 + b]) keep &= ~(1u << b);
     }
     bits[(long long)n * words + t] = keep;
-}
-
-struct SelMinimumRoot {         // roots of the candidate components that are regional-minimum plateaus
-    const int* par; const uint8_t* low;
-    __device__ __forceinline__ bool operator()(long long gi, int idx) const { return par[gi] == idx && !low[gi]; }
-};
-
-// markers = raster id of the minimum plateau a pixel belongs to, else 0; written to one or two maps
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_markers_from_plateaus(long long P, const int* __restrict__ par, const uint8_t* __restrict__ low,
-                        const int* __restrict__ rank, int32_t* __restrict__ markers, int32_t* __restrict__ copy, bool vec) {
-    const long long base = (long long)blockIdx.y * P, i = flat4_index();
-    if (i >= P) return;
-    Pack4<int> p = ld4(par + base, i, P, vec), o;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        o.v[k] = 0;
-        if (i + k < P && p.v[k] >= 0) { long long r = base + p.v[k]; if (!low[r]) o.v[k] = rank[r]; }
-    }
-    st4(markers + base, i, P, vec, o);
-    if (copy) st4(copy + base, i, P, vec, o);
 }
 
 // histogram of the flood labels (values 0..K) and the first raster pixel of each label, one pair of atomics per
@@ -334,7 +431,6 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     int* rank = ws<int>(c, total);
     int* bpar = ws<int>(c, total);
     int* brank = ws<int>(c, total);
-    uint8_t* cand = ws<uint8_t>(c, total);
     int32_t* wsl = ws_out ? ws_out : ws<int32_t>(c, total);
     int32_t* arranged = ws<int32_t>(c, total);
     int* nmark = ws<int>(c, (size_t)N);
@@ -344,7 +440,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     int* first = ws<int>(c, (size_t)N * KS);
     int* lut = ws<int>(c, (size_t)N * KS);
     unsigned* fbits = ws<unsigned>(c, (size_t)N * g.H * g.SEG);
-    if (!I0 || !low || !par || !rank || !bpar || !brank || !cand || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
+    if (!I0 || !low || !par || !rank || !bpar || !brank || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
         !first || !lut || !fbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
 
@@ -357,20 +453,26 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         TISEG_TRY(h_reconstruction_erosion_dev(c, g, I0, lamb, I));
     }
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
-    const bool vec4 = (g.W % 4 == 0) && ((((uintptr_t)I) | ((uintptr_t)cand)) & 3) == 0;
-    const dim3 quad_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
-    TISEG_LAUNCH(c, k_min_candidates, quad_grid, TISEG_THREADS, 0, g, I, cand, vec4);
-    TISEG_TRY(ccl_build(c, g, ImgEqU8Where{I, cand}, 2, par));
-    unsigned* rbits = (unsigned*)c->rootblk;          // bitmap of the candidate components' roots (left by the flatten)
-    c->rootblk_par = nullptr;
-    TISEG_TRY(zero(c, low, total));
-    TISEG_LAUNCH(c, k_cand_invalid, quad_grid, TISEG_THREADS, 0, g, I, cand, par, low, vec4);
-    TISEG_LAUNCH(c, k_filter_root_bits, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N),
-                 TISEG_THREADS, 0, g, low, rbits);
+    const size_t nwords = (size_t)N * g.H * g.SEG;
+    const dim3 word_grid((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    unsigned* cbits = ws<unsigned>(c, nwords);
+    unsigned* rbits = ws<unsigned>(c, nwords);
+    if (!cbits || !rbits) return TISEG_ERR_CUDA;
+    unsigned* bbits = ws<unsigned>(c, nwords);
+    if (!bbits) return TISEG_ERR_CUDA;
+    {
+        const long long warps = (long long)(((g.W + 3) / 4 + 23) / 24) * ((g.H + PB_ROWS - 1) / PB_ROWS);
+        TISEG_LAUNCH(c, k_plateau_bits, dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N),
+                     TISEG_THREADS, 0, g, I, cbits, bbits, par, low, (g.W % 4 == 0) && (((uintptr_t)I) & 3) == 0);
+    }
+    TISEG_LAUNCH(c, k_bitccl_link, word_grid, TISEG_THREADS, 0, g, cbits, par);
+    TISEG_LAUNCH(c, k_bitccl_flatten, word_grid, TISEG_THREADS, 0, g, cbits, bbits, par, low, rbits);
+    TISEG_LAUNCH(c, k_filter_root_bits, word_grid, TISEG_THREADS, 0, g, low, rbits);
     TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
     // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
-    TISEG_LAUNCH(c, k_markers_from_plateaus, dim3(flat4_grid(g.P), N), TISEG_THREADS, 0, (long long)g.P, par, low, rank, wsl,
-                 markers_out, (g.P % 4 == 0) && aligned16(par, wsl, markers_out));
+    TISEG_TRY(zero(c, wsl, total * sizeof(int32_t)));
+    TISEG_LAUNCH(c, k_marker_scatter, word_grid, TISEG_THREADS, 0, g, cbits, par, low, rank, wsl);
+    if (markers_out) TISEG_CHECK(cudaMemcpyAsync(markers_out, wsl, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     // flood inside b, blob by blob
     BlobInfo b;
     TISEG_TRY(blobs_build(c, g, ImgBelowU8{I0, 255}, bpar, brank, b, false));

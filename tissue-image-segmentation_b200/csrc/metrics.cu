@@ -385,6 +385,37 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
     const long long base = (long long)blockIdx.y * P;
     // each thread walks several 4-pixel groups so that one block amortises its flush; the trip count is uniform
     const long long step = (long long)gridDim.x * blockDim.x * 4;
+    if (C1 * C1 <= 16) {
+        // few classes: every thread counts its own pixels in 16 packed 8-bit fields (flushed every 60 groups), the
+        // warp adds the fields up with redux and lane 0 posts them to the block histogram
+        unsigned long long a0 = 0ull, a1 = 0ull;
+        int groups = 0;
+        for (long long i0 = (long long)blockIdx.x * blockDim.x * 4; i0 < P; i0 += step) {
+            const long long i = i0 + (long long)threadIdx.x * 4;
+            Pack4<uint8_t> pp, tt;
+            if (i < P) { pp = ld4(pred + base, i, P, vec); tt = ld4(gt + base, i, P, vec); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i + k < P) {
+                    const int p = pp.v[k], t = tt.v[k];
+                    if (t != ignore) {
+                        const int key = min(t, C) * C1 + min(p, C);
+                        const unsigned long long one = 1ull << ((key & 7) * 8);
+                        if (key < 8) a0 += one; else a1 += one;
+                    }
+                }
+            }
+            if (++groups == 60 || i0 + step >= P) {
+#pragma unroll
+                for (int key = 0; key < 16; ++key) {
+                    const unsigned f = (unsigned)(((key < 8 ? a0 : a1) >> ((key & 7) * 8)) & 0xffull);
+                    const unsigned tot = __reduce_add_sync(0xffffffffu, f);
+                    if (lane == 0 && tot && key < C1 * C1) atomicAdd(&h[key], tot);
+                }
+                a0 = a1 = 0ull; groups = 0;
+            }
+        }
+    } else
     for (long long i0 = (long long)blockIdx.x * blockDim.x * 4; i0 < P; i0 += step) {
         const long long i = i0 + (long long)threadIdx.x * 4;
         Pack4<uint8_t> pp, tt;
