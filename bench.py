@@ -452,7 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="tiles per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="tiles per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic tiles generated per rank")
     ap.add_argument("--chunk", type=int, default=8, help="e2e: tiles per host-fed chunk")
     ap.add_argument("--lanes", type=int, default=4, help="e2e: lanes (stream + workspace) the chunks alternate between")

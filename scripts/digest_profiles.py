@@ -25,7 +25,7 @@ for r in rows:
     a = agg.setdefault(r["Kernel Name"], [0, 0.0])
     a[0] += 1; a[1] += us
 tot = sum(a[1] for a in agg.values())
-with open(os.path.join(PR, "%s_launches_dist1000_b32.csv" % R), "w") as f:
+with open(os.path.join(PR, "%s_launches_dist1000_b%d.csv" % (R, bench["config"]["tiles_per_step_per_gpu"])), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 1 (first 400 launches)\n")
     f.write("kernel,launches,total_us,share\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):

@@ -6,7 +6,7 @@ import bench
 import tiseg_b200
 from tiseg_b200 import _lib, ops
 tiles = bench.make_tiles(8, 0)
-host = bench.stack_batch(tiles, int(os.environ.get("BATCH", "32")))
+host = bench.stack_batch(tiles, int(os.environ.get("BATCH", "64")))
 d = {k: torch.from_numpy(v).cuda() for k, v in host.items()}
 with _lib.device_outputs():
     for _ in range(int(os.environ.get("REPS", "2"))):

@@ -11,6 +11,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python scripts/full_pass.py > /dev/null 2>&1 || exit 1
 REPS=2 ncu --set full --clock-control none --import-source on -k regex:k_ws_flood_u8 --launch-skip 2 -c 1 -f \
     -o gpurun_out/${R}_flood python scripts/full_pass.py > gpurun_out/ncu_flood_${R}.log 2>&1
-REPS=2 ncu --set full --clock-control none --import-source on -k regex:k_ccl_local --launch-skip 8 -c 1 -f \
+REPS=2 ncu --set full --clock-control none --import-source on -k regex:k_ccl_local --launch-skip 6 -c 1 -f \
     -o gpurun_out/${R}_ccl_local python scripts/full_pass.py > gpurun_out/ncu_ccl_${R}.log 2>&1
 tail -2 gpurun_out/ncu_ccl_${R}.log

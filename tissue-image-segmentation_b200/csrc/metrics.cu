@@ -386,18 +386,34 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
     // each thread walks several 4-pixel groups so that one block amortises its flush; the trip count is uniform
     const long long step = (long long)gridDim.x * blockDim.x * 4;
     if (C1 * C1 <= 16) {
-        // few classes: every thread counts its own pixels in 16 packed 8-bit fields (flushed every 60 groups), the
-        // warp adds the fields up with redux and lane 0 posts them to the block histogram
+        // few classes: every thread counts its own pixels (16 per trip, one 128-bit load per map) in 16 packed 8-bit
+        // fields, flushed every 15 trips; the warp adds the fields up with redux and lane 0 posts them to the block
+        // histogram
         unsigned long long a0 = 0ull, a1 = 0ull;
-        int groups = 0;
-        for (long long i0 = (long long)blockIdx.x * blockDim.x * 4; i0 < P; i0 += step) {
-            const long long i = i0 + (long long)threadIdx.x * 4;
-            Pack4<uint8_t> pp, tt;
-            if (i < P) { pp = ld4(pred + base, i, P, vec); tt = ld4(gt + base, i, P, vec); }
+        int trips = 0;
+        const bool vec16 = vec && (P % 16 == 0) && ((((uintptr_t)(pred + base)) | ((uintptr_t)(gt + base))) & 15) == 0;
+        const long long step16 = (long long)gridDim.x * blockDim.x * 16;
+        for (long long i0 = (long long)blockIdx.x * blockDim.x * 16; i0 < P; i0 += step16) {
+            const long long i = i0 + (long long)threadIdx.x * 16;
+            unsigned pw[4] = {0u, 0u, 0u, 0u}, tw[4] = {0u, 0u, 0u, 0u};
+            int npx = 0;
+            if (i < P) {
+                npx = (int)(P - i < 16 ? P - i : 16);
+                if (vec16) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(pred + base + i), b = *reinterpret_cast<const uint4*>(gt + base + i);
+                    pw[0] = a.x; pw[1] = a.y; pw[2] = a.z; pw[3] = a.w;
+                    tw[0] = b.x; tw[1] = b.y; tw[2] = b.z; tw[3] = b.w;
+                } else {
+                    for (int k = 0; k < npx; ++k) {
+                        pw[k >> 2] |= (unsigned)pred[base + i + k] << (8 * (k & 3));
+                        tw[k >> 2] |= (unsigned)gt[base + i + k] << (8 * (k & 3));
+                    }
+                }
+            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i + k < P) {
-                    const int p = pp.v[k], t = tt.v[k];
+            for (int k = 0; k < 16; ++k) {
+                if (k < npx) {
+                    const int p = (pw[k >> 2] >> (8 * (k & 3))) & 255, t = (tw[k >> 2] >> (8 * (k & 3))) & 255;
                     if (t != ignore) {
                         const int key = min(t, C) * C1 + min(p, C);
                         const unsigned long long one = 1ull << ((key & 7) * 8);
@@ -405,14 +421,14 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
                     }
                 }
             }
-            if (++groups == 60 || i0 + step >= P) {
+            if (++trips == 15 || i0 + step16 >= P) {
 #pragma unroll
                 for (int key = 0; key < 16; ++key) {
                     const unsigned f = (unsigned)(((key < 8 ? a0 : a1) >> ((key & 7) * 8)) & 0xffull);
                     const unsigned tot = __reduce_add_sync(0xffffffffu, f);
                     if (lane == 0 && tot && key < C1 * C1) atomicAdd(&h[key], tot);
                 }
-                a0 = a1 = 0ull; groups = 0;
+                a0 = a1 = 0ull; trips = 0;
             }
         }
     } else
@@ -717,6 +733,7 @@ int tiseg_sem_counts(tiseg_ctx* c, const uint8_t* pred, const uint8_t* gt, int N
     TISEG_TRY(zero(c, d_valid, (size_t)N * sizeof(int64_t)));
     unsigned gx = flat4_grid(g.P);
     gx = gx > 64 ? (gx + 7) / 8 : gx;                         // ~8 groups per thread
+    if ((C + 1) * (C + 1) <= 16 && gx > 16) gx = (gx + 1) / 2; // the 16-pixel path: ~4 trips per thread
     bool vec = (g.P % 4 == 0) && ((((uintptr_t)d_pred) | ((uintptr_t)d_gt)) & 3) == 0;
     TISEG_LAUNCH(c, k_sem_counts, dim3(gx, N), TISEG_THREADS, 0, (long long)g.P, d_pred, d_gt, C, ignore_index,
                  (unsigned long long*)d_counts, (unsigned long long*)d_valid, vec);
