@@ -238,6 +238,13 @@ int tiseg_fix_inst(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, int
 int tiseg_bound_label(tiseg_ctx* ctx, const uint8_t* sem, const int32_t* inst, int N, int H, int W, int edge_id,
                       int radius_dilate, int radius_erode, uint8_t* sem_out, uint8_t* sem_w_bound_out);
 
+/* UNetLabelMake after _fix_inst (unet_map.py:53-98, 111-119 with wc = None): inner_out = every instance eroded by
+ * diamond(1) (_remove_1px_boundary); wmap_out [N,H,W] fp64 = 1 + w0 * exp(-((d1 + d2) / sigma)^2 / 2) on the pixels
+ * outside the eroded instances, d1 / d2 = Euclidean distance to the nearest / second nearest eroded instance (1
+ * everywhere when fewer than two instances remain). */
+int tiseg_unet_weight_map(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, double w0, double sigma,
+                          int32_t* inner_out, double* wmap_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -549,3 +549,33 @@ def bound_label(sem_gt, inst_gt, edge_id=2, radius=(3, 3)):
         bound = dilation(m, diamond(radius[0])) & (~erosion(m, diamond(radius[1])))
         out[bound > 0] = edge_id
     return sem_gt, out
+
+
+def unet_weight_map(inst_gt, w0=10.0, sigma=5.0):
+    """unet_map.py:53-98 (after ``_fix_inst``; wc = None) -> (eroded instance map, weight map + 1)."""
+    inner = np.zeros(inst_gt.shape[:2], np.int32)
+    for inst_id in np.unique(inst_gt):
+        if inst_id == 0:
+            continue
+        m = erosion((inst_gt == inst_id).astype(np.uint8), diamond(1))
+        inner[m > 0] = inst_id
+    ids = [i for i in np.unique(inner) if i > 0]
+    if len(ids) <= 1:
+        return inner, np.zeros(inner.shape[:2]) + 1
+    stacked = np.zeros(inner.shape[:2] + (len(ids), ))
+    for k, inst_id in enumerate(ids):
+        stacked[..., k] = ndi.distance_transform_edt(np.array(inner != inst_id, np.uint8))
+    near1 = np.amin(stacked, axis=2)
+    near2 = stacked - np.expand_dims(near1, axis=2)
+    near2[near2 == 0] = np.inf
+    near2 = np.amin(near2, axis=2)
+    near2[inner > 0] = 0
+    near2 = near2 + near1
+    eve = (1.0 + stacked) / (1.0 + np.expand_dims(near1, axis=2))
+    eve[eve != 1] = 0
+    eve = np.sum(eve, axis=2)
+    near2[eve > 1] = near1[eve > 1]
+    pen = (near1 + near2) / sigma
+    pen = w0 * np.exp(-pen**2 / 2)
+    pen[inner > 0] = 0
+    return inner, pen + 1

@@ -243,6 +243,15 @@ def main():
             tag = "l%d_r%s" % (j, "".join(str(r) for r in (radius if isinstance(radius, tuple) else (radius,))))
             lab[tag + "_sem"], lab[tag + "_bound"] = out["sem_gt"], out["sem_gt_w_bound"]
         lab["l%d_fixed" % j] = bmap.BoundLabelMake()._fix_inst(inst)
+    # UNetLabelMake (np.PINF left numpy in 2.0: restored for the reference's own line, unet_map.py:77)
+    if not hasattr(np, "PINF"):
+        np.PINF = np.inf
+    umap = load("ref_unet_map", os.path.join(REF, "tiseg/datasets/ops/unet_map.py"))
+    for j in (0, 1, 3, 4):
+        inst = lab["l%d_inst" % j]
+        data = dict(sem_gt=lab["l%d_sem" % j].copy(), inst_gt=inst.copy(), seg_fields=[])
+        out = umap.UNetLabelMake(w0=10.0, sigma=5.0)(data)
+        lab["l%d_unet_w" % j], lab["l%d_unet_inner" % j] = out["loss_weight_map"], out["sem_gt_inner"]
     np.savez_compressed(os.path.join(HERE, "labelgen_ref.npz"), **lab)
     print("golden vectors written to", HERE)
 

@@ -190,7 +190,8 @@ def test_watershed_f64():
 
 
 # --------------------------------------------------------------------------- A8
-@pytest.mark.parametrize("H,W,idx", [(120, 130, 3), (256, 256, 0), (256, 256, 1), (300, 517, 2)])
+@pytest.mark.parametrize("H,W,idx", [(120, 130, 3), (256, 256, 0), (256, 256, 1), (300, 517, 2), (97, 101, 4), (33, 385, 5),
+                                     (65, 96, 6), (31, 29, 7)])
 def test_postproc_dist(H, W, idx):
     t = synth.tile_dist(2, idx, H=H, W=W)
     _, want = opp.dist_postprocess(None, t["dist_logit"], literal=False)
@@ -202,7 +203,7 @@ def test_postproc_dist(H, W, idx):
     _diff(mk, want_mk, "dist markers")
     _diff(ws, sk.watershed(inv, want_mk, mask=(d > 0.5) + 0), "dist raw flood")
     _diff(got, want, "dist inst")
-    assert got.max() > 3
+    assert got.max() > (3 if H * W > 10000 else 0)
 
 
 def test_postproc_dist_full_tile_and_batch():
@@ -604,3 +605,21 @@ def test_label_maker_classes_follow_the_reference_protocol():
     _diff(b["sem_gt"], m["l1_r21_sem"], "BoundLabelMake sem_gt")
     h = lm.HVLabelMake()(dict(inst_gt=inst.copy(), seg_fields=[]))
     _diff(h["hv_gt"], m["l1_hv"].transpose(2, 0, 1), "HVLabelMake hv_gt")
+
+
+def test_unet_weight_map_golden_and_oracle():
+    """UNetLabelMake: eroded instances bit-exact; the fp64 weight map within 1e-12 relative of the reference's (it ends
+    in an exp)."""
+    from tiseg_b200 import label_makers as lm
+    m = np.load(os.path.join(G, "labelgen_ref.npz"))
+    for j in (0, 1, 3, 4):
+        d = lm.UNetLabelMake()(dict(sem_gt=m["l%d_sem" % j].copy(), inst_gt=m["l%d_inst" % j].copy(), seg_fields=[]))
+        _diff(d["sem_gt_inner"], m["l%d_unet_inner" % j], "UNetLabelMake sem_gt_inner (golden %d)" % j)
+        assert d["loss_weight_map"].dtype == np.float64
+        np.testing.assert_allclose(d["loss_weight_map"], m["l%d_unet_w" % j], rtol=1e-12, atol=0)
+    insts = np.stack([opp.fix_inst(synth.gt_and_pred(9970 + j, 200, 260, n=60)["gt_inst"].astype(np.int32)) for j in range(2)])
+    inner, w = ops.unet_weight_map(insts, w0=7.5, sigma=3.0)
+    for j in range(2):
+        wi, ww = opp.unet_weight_map(insts[j], w0=7.5, sigma=3.0)
+        _diff(inner[j], wi, "unet inner tile %d" % j)
+        np.testing.assert_allclose(w[j], ww, rtol=1e-12, atol=0)

@@ -230,3 +230,8 @@ def test_label_generation_matches_reference():
             sem, bound = opp.bound_label(m["l%d_sem" % j], fixed, 4, radius)
             assert np.array_equal(sem, m["l%d_r%s_sem" % (j, tag)])
             assert np.array_equal(bound, m["l%d_r%s_bound" % (j, tag)])
+        if j != 2:
+            inner, w = opp.unet_weight_map(fixed)
+            sem = np.where(fixed == 0, 0, m["l%d_sem" % j])
+            assert np.array_equal(np.where(inner == 0, 0, sem), m["l%d_unet_inner" % j])
+            assert np.array_equal(w, m["l%d_unet_w" % j])

@@ -14,6 +14,8 @@
 
 namespace tiseg {
 
+#define LG_INF 0x3fffffff
+
 struct InstBox {
     int* ymin; int* ymax; int* xmin; int* xmax; int* cnt;       // [N, VM]
     unsigned long long* sy; unsigned long long* sx;             // [N, VM] coordinate sums
@@ -77,7 +79,6 @@ k_hv_map(Geom g, const int32_t* __restrict__ inst, InstBox b, float2* __restrict
 // distance_transform_cdt of one instance's crop = chessboard distance to the nearest pixel that is NOT of this
 // instance inside the crop; the crop keeps a two-pixel ring of such pixels wherever the image allows, so this is the
 // distance to the nearest differently-labelled pixel of the image (-1 for an instance that fills the image).
-#define LG_INF 0x3fffffff
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_idm_columns(Geom g, const int32_t* __restrict__ inst, int* __restrict__ col) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
@@ -243,6 +244,104 @@ k_bound_label(Geom g, const uint8_t* __restrict__ sem, const int32_t* __restrict
     bound_out[i] = edge ? (uint8_t)edge_id : s;
 }
 
+// ---- UNetLabelMake ------------------------------------------------------------------------------------------------
+// _remove_1px_boundary (unet_map.py:53-63): erosion of every instance by diamond(1) = a pixel keeps its id iff its
+// four in-image neighbours carry the same id.
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_unet_inner(Geom g, const int32_t* __restrict__ inst, int32_t* __restrict__ inner, uint8_t* seen, int VM, int* bad) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const long long i = px.base + px.idx;
+    const int v = inst[i];
+    int o = 0;
+    if (v != 0) {
+        bool keep = true;
+        if (px.x > 0) keep &= inst[i - 1] == v;
+        if (px.x + 1 < g.W) keep &= inst[i + 1] == v;
+        if (px.y > 0) keep &= inst[i - g.W] == v;
+        if (px.y + 1 < g.H) keep &= inst[i + g.W] == v;
+        if (keep) {
+            o = v;
+            if (v < 0 || v >= VM) *bad = 1; else if (!seen[(long long)px.n * VM + v]) seen[(long long)px.n * VM + v] = 1;
+        }
+    }
+    inner[i] = o;
+}
+__global__ void k_count_seen(const uint8_t* __restrict__ seen, int VM, int* count) {
+    int n = blockIdx.y, c = 0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < VM; v += gridDim.x * blockDim.x) c += seen[(long long)n * VM + v];
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&count[n], c);
+}
+// _get_weight_map (unet_map.py:65-98) needs, per pixel, the Euclidean distances to the nearest and to the second
+// nearest INSTANCE.  Per column only the two vertically nearest distinct ids can matter (a third one is farther than
+// both from every pixel of the row), so a column sweep leaves (distance, id) x 2 per pixel and a bounded row search
+// combines them — the exact squared distances scipy's EDT takes the square root of.
+struct Top2 { int g1, l1, g2, l2; };            // vertical distance / id of the nearest and the second nearest id
+__device__ __forceinline__ void top2_offer(long long d, int l, long long& d1, int& l1, long long& d2, int& l2) {
+    if (l == l1) { if (d < d1) d1 = d; return; }
+    if (d < d1) { d2 = d1; l2 = l1; d1 = d; l1 = l; return; }
+    if (l == l2) { if (d < d2) d2 = d; return; }
+    if (d < d2) { d2 = d; l2 = l; }
+}
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_unet_columns(Geom g, const int32_t* __restrict__ inner, int4* __restrict__ col) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (x >= g.W) return;
+    const int32_t* m = inner + (long long)n * g.P + x;
+    int4* c = col + (long long)n * g.P + x;
+    int la = 0, ya = 0, lb = 0, yb = 0;               // last id seen and the id seen before it (distinct), with their rows
+    for (int y = 0; y < g.H; ++y) {
+        const int v = m[(long long)y * g.W];
+        if (v != 0) { if (v != la) { lb = la; yb = ya; la = v; } ya = y; }
+        c[(long long)y * g.W] = make_int4(la ? y - ya : LG_INF, la, lb ? y - yb : LG_INF, lb);
+    }
+    la = lb = 0;
+    for (int y = g.H - 1; y >= 0; --y) {
+        const int v = m[(long long)y * g.W];
+        if (v != 0) { if (v != la) { lb = la; yb = ya; la = v; } ya = y; }
+        const int4 t = c[(long long)y * g.W];
+        long long d1 = t.y ? t.x : (long long)LG_INF, d2 = t.w ? t.z : (long long)LG_INF;
+        int l1 = t.y, l2 = t.w;
+        if (la) top2_offer(ya - y, la, d1, l1, d2, l2);
+        if (lb) top2_offer(yb - y, lb, d1, l1, d2, l2);
+        c[(long long)y * g.W] = make_int4((int)d1, l1, (int)d2, l2);
+    }
+}
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_unet_weight(Geom g, const int32_t* __restrict__ inner, const int4* __restrict__ col, const int* __restrict__ count,
+              double w0, double sigma, double* __restrict__ wmap) {
+    const int y = blockIdx.x, n = blockIdx.y;
+    const long long ro = (long long)n * g.P + (long long)y * g.W;
+    const bool several = count[n] > 1;
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        double pen = 0.0;
+        if (several && inner[ro + x] == 0) {
+            const long long INF2 = (long long)LG_INF * LG_INF;
+            long long d1 = INF2, d2 = INF2;
+            int l1 = 0, l2 = 0;
+            for (int dx = 0; dx < g.W && (long long)dx * dx < d2; ++dx) {
+#pragma unroll
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    if (sgn && dx == 0) continue;
+                    const int xx = sgn ? x - dx : x + dx;
+                    if (xx < 0 || xx >= g.W) continue;
+                    const int4 t = col[ro + xx];
+                    if (t.y) top2_offer((long long)dx * dx + (long long)t.x * t.x, t.y, d1, l1, d2, l2);
+                    if (t.w) top2_offer((long long)dx * dx + (long long)t.z * t.z, t.w, d1, l1, d2, l2);
+                }
+            }
+            const double n1 = sqrt((double)d1), s2 = sqrt((double)d2);
+            // the reference's order of operations: near2 = (d_k - near1 minimised) + near1; ties -> near1
+            double n2 = d2 == d1 ? n1 : (s2 - n1) + n1;
+            const double pix = n1 + n2;
+            const double p = pix / sigma;
+            pen = w0 * exp(-(p * p) / 2.0);
+        }
+        wmap[ro + x] = pen + 1.0;                        // wc is None: uniform class weight (unet_map.py:118-119)
+    }
+}
+
 static int inst_tables(tiseg_ctx* c, const Geom& g, const int32_t* d_inst, InstBox& b) {
     const int VM = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;
     const size_t n = (size_t)g.N * VM;
@@ -345,6 +444,30 @@ int tiseg_bound_label(tiseg_ctx* c, const uint8_t* sem, const int32_t* inst, int
     if (!d_sem || !d_inst || !d_bo || (sem_out && !d_so)) return TISEG_ERR_CUDA;
     TISEG_LAUNCH(c, k_bound_label, warp_grid(g), TISEG_THREADS, 0, g, d_sem, d_inst, edge_id, radius_dilate, radius_erode,
                  d_so, d_bo);
+    return end_call(c);
+}
+
+int tiseg_unet_weight_map(tiseg_ctx* c, const int32_t* inst, int N, int H, int W, double w0, double sigma,
+                          int32_t* inner_out, double* wmap_out) {
+    if (!c || !inst || !inner_out || !wmap_out || !(sigma > 0)) { set_error("tiseg_unet_weight_map: bad argument"); return TISEG_ERR_ARG; }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    const size_t total = (size_t)N * g.P;
+    const int VM = g.P + 1 < (1 << 16) ? (1 << 16) : g.P + 1;
+    const int32_t* d_inst = in(c, inst, total);
+    int32_t* d_inner = tiseg::out(c, inner_out, total);
+    double* d_w = tiseg::out(c, wmap_out, total);
+    uint8_t* seen = ws<uint8_t>(c, (size_t)N * VM);
+    int* count = ws<int>(c, N);
+    int4* col = ws<int4>(c, total);
+    if (!d_inst || !d_inner || !d_w || !seen || !count || !col) return TISEG_ERR_CUDA;
+    TISEG_TRY(zero(c, seen, (size_t)N * VM));
+    TISEG_TRY(zero(c, count, (size_t)N * sizeof(int)));
+    TISEG_LAUNCH(c, k_unet_inner, warp_grid(g), TISEG_THREADS, 0, g, d_inst, d_inner, seen, VM, c->d_err);
+    TISEG_LAUNCH(c, k_count_seen, dim3(32, N), 256, 0, seen, VM, count);
+    TISEG_LAUNCH(c, k_unet_columns, dim3((g.W + TISEG_THREADS - 1) / TISEG_THREADS, N), TISEG_THREADS, 0, g, d_inner, col);
+    TISEG_LAUNCH(c, k_unet_weight, dim3(g.H, N), TISEG_THREADS, 0, g, d_inner, col, count, w0, sigma, d_w);
     return end_call(c);
 }
 

@@ -2,7 +2,8 @@
 
 Same class names, constructor arguments and ``data`` dict protocol as the reference (``DistanceLabelMake``:
 datasets/ops/distance_map.py:23-142, ``HVLabelMake``: hv_map.py:100-114, ``BoundLabelMake``: bound_map.py:6-89).
-``DirectionLabelMake`` and ``UNetLabelMake`` (OpenCV Sobel-11 gradients, per-instance exact EDT stacks) are not built.
+``UNetLabelMake``: unet_map.py:7-127).  ``DirectionLabelMake`` (per-pixel binary-search centre points, OpenCV Sobel-11
+gradients) is not built.
 """
 import numpy as np
 
@@ -45,4 +46,24 @@ class DistanceLabelMake(object):
         data["sem_gt"] = sem_gt
         data["dist_gt"] = ops.instance_distance_map(inst_gt, self.inst_norm)
         data["seg_fields"].append("dist_gt")
+        return data
+
+
+class UNetLabelMake(object):
+    def __init__(self, wc=None, w0=10.0, sigma=5.0):
+        if wc is not None:
+            # unet_map.py:120-124 builds ``np.zeros_like(inst_gt.shape[:2])`` (a length-2 vector) and indexes it with an
+            # image-sized mask: the reference itself raises for any wc
+            raise NotImplementedError("UNetLabelMake(wc=...) fails in the reference (unet_map.py:121-123)")
+        self.wc, self.w0, self.sigma = wc, w0, sigma
+
+    def __call__(self, data):
+        sem_gt = np.asarray(data["sem_gt"])
+        inst_gt = ops.fix_inst(data["inst_gt"])
+        sem_gt = np.where(inst_gt == 0, 0, sem_gt).astype(sem_gt.dtype)
+        data["sem_gt"] = sem_gt
+        inner, wmap = ops.unet_weight_map(inst_gt, self.w0, self.sigma)
+        data["loss_weight_map"] = wmap
+        data["sem_gt_inner"] = np.where(inner == 0, 0, sem_gt).astype(sem_gt.dtype)
+        data["seg_fields"].append("sem_gt_inner")
         return data

@@ -415,3 +415,14 @@ def bound_label(sem, inst, edge_id=2, selem_radius=3):
     get_ctx(_dev(x)).call("tiseg_bound_label", ptr(s), ptr(x), N, H, W, int(edge_id), int(selem_radius[0]),
                           int(selem_radius[1]), ptr(sem_out), ptr(bound))
     return _unbatch(sem_out, was2d), _unbatch(bound, was2d)
+
+
+def unet_weight_map(inst, w0=10.0, sigma=5.0):
+    """UNetLabelMake after ``_fix_inst`` (datasets/ops/unet_map.py:53-98): -> (instances eroded by diamond(1), fp64 loss
+    weight map with the uniform class weight 1 added)."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    inner = empty_like_kind(x, (N, H, W), np.int32)
+    wmap = empty_like_kind(x, (N, H, W), np.float64)
+    get_ctx(_dev(x)).call("tiseg_unet_weight_map", ptr(x), N, H, W, float(w0), float(sigma), ptr(inner), ptr(wmap))
+    return _unbatch(inner, was2d), _unbatch(wmap, was2d)
