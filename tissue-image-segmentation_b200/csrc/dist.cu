@@ -72,7 +72,6 @@ __device__ __forceinline__ int run_start_of(unsigned w, int q) {       // first 
 // pixels come from the neighbouring lanes.  The outer four threads on each side are halo (the stencil of a stencil
 // needs two pixels), so a warp emits 24 x 4 pixels = three bitmap words per row.  Lane <-> column mapping: lanes
 // 0..23 = output columns, 24..27 = right halo, 28..31 = left halo (neighbours by lane rotation).
-#define PB_ROWS 32
 struct Px4 { unsigned lo, hi; };                      // (px0 | px1 << 16), (px2 | px3 << 16)
 __device__ __forceinline__ Px4 pb_hmin(Px4 v, int lane) {
     const unsigned hl = __shfl_sync(0xffffffffu, v.hi, (lane + 31) & 31);      // pixels 2,3 of the thread to the left
@@ -94,7 +93,7 @@ __device__ __forceinline__ unsigned pb_nibble(unsigned lo, unsigned hi) {
 }
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbits, unsigned* __restrict__ badbits,
-               int* __restrict__ par, uint8_t* __restrict__ low, bool vec) {
+               int* __restrict__ par, uint8_t* __restrict__ low, bool vec, int PB_ROWS) {
     const int lane = threadIdx.x & 31;
     const int W4 = (g.W + 3) >> 2, S = (W4 + 23) / 24, bands = (g.H + PB_ROWS - 1) / PB_ROWS;
     const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -461,9 +460,11 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     unsigned* bbits = ws<unsigned>(c, nwords);
     if (!bbits) return TISEG_ERR_CUDA;
     {
+        static int PB_ROWS = 0;                  // rows per warp band (multiple of 4); TISEG_PB_ROWS for experiments
+        if (!PB_ROWS) { const char* e = getenv("TISEG_PB_ROWS"); PB_ROWS = e ? atoi(e) : 32; if (PB_ROWS < 4 || PB_ROWS % 4) PB_ROWS = 32; }
         const long long warps = (long long)(((g.W + 3) / 4 + 23) / 24) * ((g.H + PB_ROWS - 1) / PB_ROWS);
         TISEG_LAUNCH(c, k_plateau_bits, dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N),
-                     TISEG_THREADS, 0, g, I, cbits, bbits, par, low, (g.W % 4 == 0) && (((uintptr_t)I) & 3) == 0);
+                     TISEG_THREADS, 0, g, I, cbits, bbits, par, low, (g.W % 4 == 0) && (((uintptr_t)I) & 3) == 0, PB_ROWS);
     }
     TISEG_LAUNCH(c, k_bitccl_link, word_grid, TISEG_THREADS, 0, g, cbits, par);
     TISEG_LAUNCH(c, k_bitccl_flatten, word_grid, TISEG_THREADS, 0, g, cbits, bbits, par, low, rbits);
