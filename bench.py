@@ -128,7 +128,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- this repo (CUDA)
@@ -201,8 +201,6 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     bind_to_gpu_numa_node(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"           # the version banner goes to stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=dev)
     import tiseg_b200  # noqa: F401
     from tiseg_b200 import _lib, ops
@@ -441,12 +439,34 @@ def run_b200(a):
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "check": {"aji": float(acc[0] / acc[1]) if float(acc[1]) else None},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints there (the NCCL version banner does) is sent to
+    stderr instead, and the line is written to the real stdout at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
