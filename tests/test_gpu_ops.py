@@ -222,6 +222,10 @@ def test_postproc_dist_edge_cases():
     _diff(ops.postproc_dist(full), opp.dist_postprocess(None, full, literal=False)[1], "all-foreground dist")
     big = np.full((30, 30), 300.0, np.float32); big[0, 0] = -5
     _diff(ops.postproc_dist(big), opp.dist_postprocess(None, big, literal=False)[1], "clipped dist")
+    rng = np.random.default_rng(5)
+    for (H, W) in [(1, 1), (1, 40), (37, 1), (2, 3), (4, 129)]:          # degenerate geometry, noisy levels
+        d = (rng.random((H, W)) * 6).astype(np.float32)
+        _diff(ops.postproc_dist(d), opp.dist_postprocess(None, d, literal=False)[1], "dist %dx%d" % (H, W))
 
 
 # --------------------------------------------------------------------------- A16 / A17 / A19
@@ -623,3 +627,23 @@ def test_unet_weight_map_golden_and_oracle():
         wi, ww = opp.unet_weight_map(insts[j], w0=7.5, sigma=3.0)
         _diff(inner[j], wi, "unet inner tile %d" % j)
         np.testing.assert_allclose(w[j], ww, rtol=1e-12, atol=0)
+
+
+def test_label_makers_degenerate_geometry():
+    rng = np.random.default_rng(9)
+    for (H, W) in [(1, 1), (1, 40), (37, 1), (2, 3), (6, 65)]:
+        inst = (rng.integers(0, 4, (H, W)) * rng.integers(0, 2, (H, W))).astype(np.int32)
+        if W >= 8:
+            inst[:, W // 4:W // 2], inst[:, W // 2:3 * W // 4] = 5, 6
+        if H >= 8:
+            inst[H // 4:H // 2], inst[H // 2:3 * H // 4] = 7, 8
+        fixed = opp.fix_inst(inst)
+        _diff(ops.fix_inst(inst), fixed, "fix_inst %dx%d" % (H, W))
+        _diff(ops.gen_instance_hv_map(inst), opp.gen_instance_hv_map(inst), "hv map %dx%d" % (H, W))
+        _diff(ops.instance_distance_map(fixed, True), opp.instance_distance_map(fixed, True), "distance map %dx%d" % (H, W))
+        sem = (fixed > 0).astype(np.uint8)
+        _diff(ops.bound_label(sem, fixed, 2, 3)[1], opp.bound_label(sem, fixed, 2, (3, 3))[1], "bound %dx%d" % (H, W))
+        inner, w = ops.unet_weight_map(fixed)
+        wi, ww = opp.unet_weight_map(fixed)
+        _diff(inner, wi, "unet inner %dx%d" % (H, W))
+        np.testing.assert_allclose(w, ww, rtol=1e-12, atol=0)

@@ -127,7 +127,9 @@ k_idm_finish(Geom g, const int32_t* __restrict__ inst, const int* __restrict__ d
     const long long i = px.base + px.idx;
     const int v = inst[i];
     float r = 0.f;
-    if (v > 0 && v < VM) {
+    // an instance whose expanded crop is thinner than two pixels is skipped (distance_map.py:85-86): with the
+    // two-pixel expansion that only happens when the image itself is
+    if (v > 0 && v < VM && g.H >= 2 && g.W >= 2) {
         const int mx = maxd[(long long)px.n * VM + v];
         if (!normalise) r = (float)dist[i];
         else if (mx > 0) r = __fdiv_rn((float)dist[i], (float)mx);         // max <= 0: the instance is skipped (:100-102)
