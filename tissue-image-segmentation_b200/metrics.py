@@ -223,7 +223,7 @@ def pre_eval_to_imw_sem_metrics(pre_eval_results, metrics=['IoU'], nan_to_num=No
     sums = [[torch.sum(x) for x in col] for col in cols]
     ret = {}
     for m in [k for k in _SEM_ALLOWED if k in metrics]:
-        ret[m] = np.array([np.array(_sem_formulas(*vals, [m])[m]) for vals in zip(*sums)])
+        ret[m] = np.array([_sem_formulas(*vals, [m])[m].numpy() for vals in zip(*sums)])
     order = [k for k in ('Accuracy', 'IoU', 'Dice', 'Recall', 'Precision') if k in ret]
     return _finish(OrderedDict((k, ret[k]) for k in order), nan_to_num)
 
