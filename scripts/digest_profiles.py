@@ -37,12 +37,13 @@ def raw(rep):
     rr = list(csv.reader(out.splitlines()))
     return dict(zip(rr[0], rr[-1])), out
 
-for tag in ("flood", "ccl_local"):
+for tag in ("flood", "ccl_local", "flatten", "plateau", "pair", "wsl_remove"):
     rep = os.path.join(GO, "%s_%s.ncu-rep" % (R, tag))
     if not os.path.exists(rep):
         continue
     d, out = raw(rep)
-    open(os.path.join(PR, "%s_%s_full_raw.csv" % (R, tag)), "w").write(out)
+    if tag in ("flood", "ccl_local"):          # the raw metric dump only for the two heaviest kernels
+        open(os.path.join(PR, "%s_%s_full_raw.csv" % (R, tag)), "w").write(out)
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     open(os.path.join(PR, "%s_%s_details.txt" % (R, tag)), "w").write(det)
     keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

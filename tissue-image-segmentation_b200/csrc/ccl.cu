@@ -4,35 +4,48 @@
 
 namespace tiseg {
 
-// every foreground pixel points directly at its root; bits[n, y, seg] = ballot of the roots of the row segment
+// every foreground pixel points directly at its root; bits[n, y, seg] (zeroed beforehand) gets the bit of every root.
+// Four pixels per thread (one 128-bit load / store; the pixels of a run share one chase): a pixel-per-lane version of
+// this pass was issue-bound at a quarter of the HBM rate (profiles/r1_flatten_*).
 template <bool LISTED>
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, unsigned* __restrict__ bits) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_flatten(Geom g, int* par, unsigned* bits, bool vec) {
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4, idx = y * g.W + x;
     FOR_TILES(LISTED, g, n) {
-    strip_set_tile(g, s, n);
-    int* tp = par + s.base;
-    int p[STRIP_R];
+    int* tp = par + (long long)n * g.P;
+    int p[4], a[4];
+    if (vec) {
+        const int4 v = *reinterpret_cast<const int4*>(tp + idx);
+        p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+    } else {
 #pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        p[r] = (s.okx && y < g.H) ? tp[y * g.W + s.x] : -1;
+        for (int k = 0; k < 4; ++k) p[k] = x + k < g.W ? tp[idx + k] : -1;
     }
-    int q[STRIP_R];
+    int q[4];
 #pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) q[r] = p[r] >= 0 ? tp[p[r]] : -1;      // second hop, also independent
+    for (int k = 0; k < 4; ++k) q[k] = p[k] >= 0 ? tp[p[k]] : -1;           // second hops, independent
+    bool changed = false;
 #pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r, idx = y * g.W + s.x;
-        bool root = false;
-        if (p[r] >= 0) {
-            int a = p[r], b = q[r];
-            while (b != a) { a = b; b = tp[a]; }
-            if (a != p[r]) tp[idx] = a;
-            root = a == idx;
+    for (int k = 0; k < 4; ++k) {
+        a[k] = p[k];
+        if (p[k] < 0) continue;
+        if (k > 0 && p[k] == p[k - 1]) a[k] = a[k - 1];
+        else {
+            int r = p[k], nx = q[k];
+            while (nx != r) { r = nx; nx = tp[r]; }
+            a[k] = r;
         }
-        unsigned m = __ballot_sync(0xffffffffu, root);
-        if (s.lane == 0 && y < g.H) bits[((long long)s.n * g.H + y) * g.SEG + s.seg] = m;
+        changed |= a[k] != p[k];
+        if (a[k] == idx + k) atomicOr(&bits[((long long)n * g.H + y) * g.SEG + ((x + k) >> 5)], 1u << ((x + k) & 31));
+    }
+    if (changed) {
+        if (vec) *reinterpret_cast<int4*>(tp + idx) = make_int4(a[0], a[1], a[2], a[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < g.W && a[k] != p[k]) tp[idx + k] = a[k];
+        }
     }
     }
 }
@@ -162,7 +175,9 @@ __global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* 
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
     unsigned* bits = ws<unsigned>(c, (size_t)g.N * g.H * g.SEG);
     if (!bits) return TISEG_ERR_CUDA;
-    TISEG_LAUNCH_TILES(c, k_ccl_flatten, g, strip_grid(g), TISEG_THREADS, 0, g, par, bits);
+    TISEG_TRY(zero(c, bits, (size_t)g.N * g.H * g.SEG * sizeof(unsigned)));
+    const dim3 qg((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), grid_tiles(g));
+    TISEG_LAUNCH_TILES(c, k_ccl_flatten, g, qg, TISEG_THREADS, 0, g, par, bits, (g.W % 4 == 0) && aligned16(par));
     c->rootblk_par = par;             // rank_roots on this forest can skip its bitmap pass
     c->rootblk = (int*)bits;
     return TISEG_OK;

@@ -378,41 +378,66 @@ __global__ void k_arrange_lut(Geom g, const int* __restrict__ first, const int* 
 }
 
 // generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
-// `lut` (may be null): the id of each label value, applied to the pixels that survive
+// `lut` (may be null): the id of each label value, applied to the pixels that survive.
+// Four pixels per thread: three 128-bit row loads + the two columns beside them, one 128-bit store (a pixel-per-lane
+// version was issue-bound at 29 % of the HBM rate, profiles/r1_wsl_remove_*).
 template <bool LISTED>
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lut, int KS, int32_t* __restrict__ out) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
+k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lut, int KS, int32_t* __restrict__ out, bool vec) {
+    const int W4 = (g.W + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W4 * g.H) return;
+    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4;
     FOR_TILES(LISTED, g, n) {
-    strip_set_tile(g, s, n);
-    int c[STRIP_R + 2], l[STRIP_R + 2], r[STRIP_R + 2];
-    strip_load_c<int>(g, s, lab + s.base, 0, c);
-    bool any = false;
+    const int32_t* tile = lab + (long long)n * g.P;
+    int32_t* dst = out + (long long)n * g.P + (long long)y * g.W + x;
+    int c[4];
+    {
+        const int32_t* rp = tile + (long long)y * g.W + x;
+        if (vec) { const int4 v = *reinterpret_cast<const int4*>(rp); c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; }
+        else {
 #pragma unroll
-    for (int j = 1; j <= STRIP_R; ++j) any |= c[j] != 0;
-    if (!__ballot_sync(0xffffffffu, any)) {                        // (uniform) a strip of background: zeros out
-#pragma unroll
-        for (int j = 1; j <= STRIP_R; ++j) {
-            int y = s.y0 + j - 1;
-            if (s.okx && y < g.H) out[s.base + (long long)y * g.W + s.x] = 0;
+            for (int k = 0; k < 4; ++k) c[k] = x + k < g.W ? rp[k] : 0;
         }
-        continue;
     }
-    strip_fill_lr<int>(g, s, lab + s.base, 0, c, l, r);
+    int o[4] = {0, 0, 0, 0};
+    if (c[0] | c[1] | c[2] | c[3]) {
+        int w[3][6];                                 // rows y-1 .. y+1, columns x-1 .. x+4 (0 outside the image)
 #pragma unroll
-    for (int j = 1; j <= STRIP_R; ++j) {
-        int y = s.y0 + j - 1;
-        if (!s.okx || y >= g.H) continue;
-        int v = c[j];
-        bool line = false;
-        if (v != 0) {
-            const int nb[8] = {l[j - 1], c[j - 1], r[j - 1], l[j], r[j], l[j + 1], c[j + 1], r[j + 1]};
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            const bool ok = yy >= 0 && yy < g.H;
+            const int32_t* rp = tile + (long long)yy * g.W + x;
+            if (dy == 0) { w[1][1] = c[0]; w[1][2] = c[1]; w[1][3] = c[2]; w[1][4] = c[3]; }
+            else if (ok && vec) {
+                const int4 v = *reinterpret_cast<const int4*>(rp);
+                w[dy + 1][1] = v.x; w[dy + 1][2] = v.y; w[dy + 1][3] = v.z; w[dy + 1][4] = v.w;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) line |= (nb[k] != 0 && nb[k] != v);
+                for (int k = 0; k < 4; ++k) w[dy + 1][k + 1] = (ok && x + k < g.W) ? rp[k] : 0;
+            }
+            w[dy + 1][0] = (ok && x > 0) ? rp[-1] : 0;
+            w[dy + 1][5] = (ok && x + 4 < g.W) ? rp[4] : 0;
         }
-        if (lut && v != 0 && !line) v = lut[(long long)s.n * KS + v];
-        out[s.base + (long long)y * g.W + s.x] = line ? 0 : v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = c[k];
+            if (v == 0) continue;
+            bool line = false;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int nb = w[dy][k + dx];
+                    line |= nb != 0 && nb != v;
+                }
+            o[k] = line ? 0 : (lut ? lut[(long long)n * KS + v] : v);
+        }
+    }
+    if (vec) *reinterpret_cast<int4*>(dst) = make_int4(o[0], o[1], o[2], o[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (x + k < g.W) dst[k] = o[k];
     }
     }
 }
@@ -489,13 +514,15 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     TISEG_LAUNCH(c, k_first_bits, dim3(8, N), 256, 0, g, first, KS, nmark, fbits);
     TISEG_TRY(rank_from_bits(c, g, fbits, rank, nullptr));
     TISEG_LAUNCH(c, k_arrange_lut, dim3(8, N), 256, 0, g, first, rank, KS, nmark, lut);
-    TISEG_LAUNCH(c, k_wsl_remove<false>, strip_grid(g), TISEG_THREADS, 0, g, wsl, lut, KS, inst);
+    const dim3 quad_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_wsl_remove<false>, quad_grid, TISEG_THREADS, 0, g, wsl, lut, KS, inst, (g.W % 4 == 0) && aligned16(wsl, inst));
     //   any other background: the general relabelling, on the listed tiles only (no blocks do anything otherwise)
     Geom gl = listed_geom(g, flagged, nflagged);
     TISEG_TRY(ccl_build(c, gl, ImgEqI32TileBg{wsl, bg}, 2, par));
     TISEG_TRY(rank_roots(c, gl, par, rank, nullptr));
     TISEG_TRY(apply_rank(c, gl, par, rank, arranged));
-    TISEG_LAUNCH(c, k_wsl_remove<true>, strip_grid(gl), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst);
+    TISEG_LAUNCH(c, k_wsl_remove<true>, dim3(quad_grid.x, 1), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst,
+                 (g.W % 4 == 0) && aligned16(arranged, inst));
     return TISEG_OK;
 }
 
