@@ -71,98 +71,154 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 #ifdef __CUDACC__
 // =====================================================================================================
 // Three launches per labelling:
-//   k_ccl_local   one CTA per 64-row x 32-column tile: values staged in shared memory, union-find entirely in
-//                 shared memory (row runs by ballot/clz, merges with the row above by shared atomicMin), flattened
-//                 locally, then ONE coalesced global write per pixel: the tile-global index of its local root.
-//   k_ccl_border  only the pixels on tile borders (~8 %) merge across tiles with global atomicMin unions.
+//   k_ccl_local   one CTA per 32-row x 128-column tile, FOUR PIXELS PER THREAD (a warp = 128 pixels of a row): values
+//                 staged in shared memory, union-find entirely in shared memory — row runs from in-thread compares
+//                 plus one ballot (which threads are one unbroken run), merges with the row above by shared
+//                 atomicMin — flattened locally, then one 128-bit global write per thread: the tile-global index
+//                 of each pixel's local root.  (A pixel-per-lane version of this kernel issued 132 instructions
+//                 per 32 pixels and ran issue-bound at 3.4 IPC, profiles/r1_ccl_local_*.)
+//   k_ccl_border  only the pixels on tile borders (~4 %) merge across tiles with global atomicMin unions.
 //   k_ccl_flatten every pixel points at its global root (lowest flat index of the component = first pixel in
 //                 raster order); also leaves the bitmap of the roots for the id ranking that usually follows.
 // =====================================================================================================
 #define CCL_WARPS 8                     // warps per tile CTA
-#define CCL_TH (8 * CCL_WARPS)           // tile rows (each warp owns 8 of them); tile width is one warp = 32 columns
+#define CCL_RPW 4                       // rows per warp
+#define CCL_TH (CCL_RPW * CCL_WARPS)    // tile rows
+#define CCL_TW 128                      // tile columns: one warp x four pixels
 #define CCL_BG INT_MIN                  // background marker inside the shared value tile
 
+static __device__ __noinline__ void uf_union_tile(int* lab, int a, int b) { uf_union(lab, a, b); }
+
 template <class Img, int CONN, bool LISTED>
-__global__ void __launch_bounds__(32 * CCL_WARPS, LISTED ? 1 : 2048 / (32 * CCL_WARPS)) k_ccl_local(Geom g, Img img, int* __restrict__ par) {
-    __shared__ int sval[CCL_TH * 32];
-    __shared__ int slab[CCL_TH * 32];
+__global__ void __launch_bounds__(32 * CCL_WARPS) k_ccl_local(Geom g, Img img, int* __restrict__ par, bool vec) {
+    __shared__ __align__(16) int sval[CCL_TH * CCL_TW];
+    __shared__ __align__(16) int slab[CCL_TH * CCL_TW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ty = blockIdx.x / g.SEG, tx = blockIdx.x - ty * g.SEG;
-    const int x = tx * 32 + lane;
-    const bool okx = x < g.W;
-    // rows are dealt to the warps round-robin (warp w owns rows w, w + CCL_WARPS, ...): a nucleus spreads over all eight warps, so
-    // they reach the barriers together instead of one warp doing a blob's unions while seven wait
-    const int yt = ty * CCL_TH;
+    const int tilesX = (g.W + CCL_TW - 1) / CCL_TW;
+    const int ty = blockIdx.x / tilesX, tx = blockIdx.x - ty * tilesX;
+    const int x0 = tx * CCL_TW + lane * 4, yt = ty * CCL_TH;
+    // rows are dealt to the warps round-robin (warp w owns rows w, w + CCL_WARPS, ...): a nucleus spreads over all the
+    // warps, so they reach the barriers together instead of one warp doing a blob's unions while the others wait
     FOR_TILES(LISTED, g, n) {
     const long long base = (long long)n * g.P;
-    // phase A: coalesced loads (8 independent rows in flight per lane), row-run initialisation
-    int v[8];
+    // phase A: loads (all rows of the thread in flight), in-thread runs, run starts across threads, staging
+    int v[CCL_RPW][4];
+    unsigned cm[CCL_RPW];               // bit k: pixel k continues the run of the pixel to its left
+    unsigned fgm[CCL_RPW];              // bit k: pixel k is foreground
+    int l0[CCL_RPW];                    // label (tile-local index of the run start) of the run pixel 0 belongs to
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        int y = yt + r * CCL_WARPS + warp, vv = 0;
-        v[r] = CCL_BG;
-        if (okx && y < g.H && img(n, base + (long long)y * g.W + x, vv)) v[r] = vv;
+    for (int r = 0; r < CCL_RPW; ++r) {
+        const int y = yt + r * CCL_WARPS + warp;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int vv = 0;
+            v[r][k] = CCL_BG;
+            if (y < g.H && x0 + k < g.W && img(n, base + (long long)y * g.W + x0 + k, vv)) v[r][k] = vv;
+        }
     }
-    unsigned fg = 0;                    // bit r: row r of this warp has a foreground pixel (uniform over the warp)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
-        bool cont = lane > 0 && v[r] != CCL_BG && vl == v[r];
-        unsigned m = __ballot_sync(0xffffffffu, cont);
-        if (__ballot_sync(0xffffffffu, v[r] != CCL_BG)) fg |= 1u << r;
-        int li = (r * CCL_WARPS + warp) * 32 + lane;
-        sval[li] = v[r];
-        slab[li] = v[r] != CCL_BG ? (r * CCL_WARPS + warp) * 32 + run_start_lane(m, lane) : -1;
+    for (int r = 0; r < CCL_RPW; ++r) {
+        const int row = r * CCL_WARPS + warp, li0 = row * CCL_TW + lane * 4;
+        int left = __shfl_up_sync(0xffffffffu, v[r][3], 1);
+        if (lane == 0) left = CCL_BG;
+        const unsigned f = (v[r][0] != CCL_BG ? 1u : 0u) | (v[r][1] != CCL_BG ? 2u : 0u) | (v[r][2] != CCL_BG ? 4u : 0u) |
+                           (v[r][3] != CCL_BG ? 8u : 0u);
+        const unsigned c = ((v[r][0] == left ? 1u : 0u) | (v[r][1] == v[r][0] ? 2u : 0u) | (v[r][2] == v[r][1] ? 4u : 0u) |
+                            (v[r][3] == v[r][2] ? 8u : 0u)) & f;
+        fgm[r] = f; cm[r] = c;
+        // threads that are one unbroken continuation of the run to their left; the run of my pixel 0 (if it
+        // continues) started in the nearest lower lane that is not one, at that lane's last in-thread start
+        const unsigned full = __ballot_sync(0xffffffffu, c == 15u);
+        const unsigned lower = ~full & ((1u << lane) - 1u);
+        const int src = lower ? 31 - __clz(lower) : 0;
+        const int s3 = 31 - __clz((~c & 15u) | 1u);                 // in-thread start of the run of pixel 3 (0 if unbroken)
+        const int inherited = __shfl_sync(0xffffffffu, li0 + s3, src);
+        l0[r] = (c & 1u) ? inherited : li0;
+        // label of pixel k = last break at or below k (the run start inside the thread), or the inherited one
+        const unsigned brk = ~c & 15u;
+        int4 lab;
+        lab.x = (f & 1u) ? l0[r] : -1;
+        lab.y = (f & 2u) ? ((brk & 2u) ? li0 + 1 : l0[r]) : -1;
+        lab.z = (f & 4u) ? ((brk & 4u) ? li0 + 2 : (brk & 2u) ? li0 + 1 : l0[r]) : -1;
+        lab.w = (f & 8u) ? ((brk & 14u) ? li0 + s3 : l0[r]) : -1;
+        *reinterpret_cast<int4*>(&sval[li0]) = make_int4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        *reinterpret_cast<int4*>(&slab[li0]) = lab;
     }
     __syncthreads();
-    // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border); rows without a
-    // foreground pixel are skipped by the whole warp
+    // phase B: merge with the row above (same redundancy rule as documented at k_ccl_border), decided for the four
+    // pixels at once as bit masks; the inside of a blob needs no union at all
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        int row = r * CCL_WARPS + warp, li = row * 32 + lane;
-        if (!((fg >> r) & 1u)) continue;
-        if (row == 0 || v[r] == CCL_BG) continue;
-        int u = sval[li - 32];
-        int ul = lane > 0 ? sval[li - 33] : CCL_BG;
-        int ur = lane < 31 ? sval[li - 31] : CCL_BG;
-        bool sameL = lane > 0 && sval[li - 1] == v[r];
-        if (u == v[r]) {
-            if (!(sameL && ul == v[r])) uf_union(slab, li, li - 32);
-        } else if (CONN == 2) {
-            if (ul == v[r] && !sameL) uf_union(slab, li, li - 33);
-            if (ur == v[r]) uf_union(slab, li, li - 31);
+    for (int r = 0; r < CCL_RPW; ++r) {
+        const int row = r * CCL_WARPS + warp, li0 = row * CCL_TW + lane * 4;
+        if (row == 0 || !fgm[r]) continue;
+        const int4 up = *reinterpret_cast<const int4*>(&sval[li0 - CCL_TW]);
+        const int ul = lane > 0 ? sval[li0 - CCL_TW - 1] : CCL_BG;
+        const int ur = lane < 31 ? sval[li0 - CCL_TW + 4] : CCL_BG;
+        const unsigned eU = ((up.x == v[r][0] ? 1u : 0u) | (up.y == v[r][1] ? 2u : 0u) | (up.z == v[r][2] ? 4u : 0u) |
+                             (up.w == v[r][3] ? 8u : 0u)) & fgm[r];
+        const unsigned eL = ((ul == v[r][0] ? 1u : 0u) | (up.x == v[r][1] ? 2u : 0u) | (up.y == v[r][2] ? 4u : 0u) |
+                             (up.z == v[r][3] ? 8u : 0u)) & fgm[r];
+        unsigned need_u = eU & ~(cm[r] & eL), need_l = 0, need_r = 0;
+        if (CONN == 2) {
+            const unsigned eR = ((up.y == v[r][0] ? 1u : 0u) | (up.z == v[r][1] ? 2u : 0u) | (up.w == v[r][2] ? 4u : 0u) |
+                                 (ur == v[r][3] ? 8u : 0u)) & fgm[r];
+            need_l = ~eU & eL & ~cm[r];
+            need_r = ~eU & eR;
+        }
+        unsigned todo = need_u | (need_l << 4) | (need_r << 8);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int k = b & 3, li = li0 + k;
+            uf_union_tile(slab, li, li - CCL_TW + (b >> 2 == 0 ? 0 : b >> 2 == 1 ? -1 : 1));
         }
     }
     __syncthreads();
-    // phase C: local flatten, one global write per pixel
+    // phase C: local flatten, one chase per in-thread run, one global write per thread
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        int y = yt + r * CCL_WARPS + warp;
-        if (!okx || y >= g.H) continue;
-        int out = -1;
-        if (v[r] != CCL_BG) {
-            int root = uf_find(slab, (r * CCL_WARPS + warp) * 32 + lane);
-            out = (ty * CCL_TH + (root >> 5)) * g.W + tx * 32 + (root & 31);
+    for (int r = 0; r < CCL_RPW; ++r) {
+        const int row = r * CCL_WARPS + warp, y = yt + row, li0 = row * CCL_TW + lane * 4;
+        if (y >= g.H || x0 >= g.W) continue;
+        int out[4] = {-1, -1, -1, -1};
+        // run starts inside the thread: foreground pixels that do not continue, plus pixel 0 if it does
+        unsigned starts = fgm[r] & (~cm[r] | 1u);
+        while (starts) {
+            const int k = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int root = uf_find(slab, (k == 0 && (cm[r] & 1u)) ? l0[r] : li0 + k);
+            const int o = (yt + (root >> 7)) * g.W + tx * CCL_TW + (root & (CCL_TW - 1));
+            // the run: pixel k and the continuing pixels right after it
+            const unsigned runlen = __ffs(~(cm[r] >> (k + 1)));            // pixels k .. k+runlen-1 (cm has four bits)
+            const unsigned mask = ((1u << runlen) - 1u) << k;
+            if (mask & 1u) out[0] = o;
+            if (mask & 2u) out[1] = o;
+            if (mask & 4u) out[2] = o;
+            if (mask & 8u) out[3] = o;
         }
-        par[base + (long long)y * g.W + x] = out;
+        int* dst = par + base + (long long)y * g.W + x0;
+        if (vec) *reinterpret_cast<int4*>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x0 + k < g.W) dst[k] = out[k];
+        }
     }
     if (LISTED) __syncthreads();        // the shared tile is reused by the next listed tile
     }
 }
 
-// Cross-tile merges.  Candidates: A) pixels of a tile's top row (y = 64k, k >= 1) look up / up-left / up-right;
-// B) pixels of a tile's left column (x = 32k, k >= 1) look left / up-left; C) (8-connectivity) pixels of a tile's
-// right column (x = 32k - 1) look up-right.  A diagonal union is skipped when the vertical neighbour has the same
+// Cross-tile merges.  Candidates: A) pixels of a tile's top row (y = 32k, k >= 1) look up / up-left / up-right;
+// B) pixels of a tile's left column (x = 128k, k >= 1) look left / up-left; C) (8-connectivity) pixels of a tile's
+// right column (x = 128k - 1) look up-right.  A diagonal union is skipped when the vertical neighbour has the same
 // value (it is then connected through that neighbour's own row).
 template <class Img, int CONN>
 __device__ __forceinline__ void ccl_border_one(const Geom& g, const Img& img, int* par, int n, int t) {
-    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
-    const int nA = (tilesY - 1) * g.W, nB = (g.SEG - 1) * g.H, nC = CONN == 2 ? nB : 0;
+    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH, tilesX = (g.W + CCL_TW - 1) / CCL_TW;
+    const int nA = (tilesY - 1) * g.W, nB = (tilesX - 1) * g.H, nC = CONN == 2 ? nB : 0;
     if (t >= nA + nB + nC) return;
     int y, x, kind;
     if (t < nA) { kind = 0; y = (t / g.W + 1) * CCL_TH; x = t - (t / g.W) * g.W; }
-    else if (t < nA + nB) { t -= nA; kind = 1; x = (t / g.H + 1) * 32; y = t - (t / g.H) * g.H; }
-    else { t -= nA + nB; kind = 2; x = (t / g.H + 1) * 32 - 1; y = t - (t / g.H) * g.H; }
+    else if (t < nA + nB) { t -= nA; kind = 1; x = (t / g.H + 1) * CCL_TW; y = t - (t / g.H) * g.H; }
+    else { t -= nA + nB; kind = 2; x = (t / g.H + 1) * CCL_TW - 1; y = t - (t / g.H) * g.H; }
     const long long base = (long long)n * g.P;
     const int idx = y * g.W + x;
     int v = 0;
@@ -194,22 +250,23 @@ int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par);
 // build + flatten.  par: [N*P] int
 template <class Img>
 int ccl_build(tiseg_ctx* c, const Geom& g, Img img, int conn, int* par) {
-    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH;
-    dim3 lg((unsigned)(g.SEG * tilesY), grid_tiles(g));
-    const int nb = (tilesY - 1) * g.W + (g.SEG - 1) * g.H * (conn == 2 ? 2 : 1);
+    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH, tilesX = (g.W + CCL_TW - 1) / CCL_TW;
+    dim3 lg((unsigned)(tilesX * tilesY), grid_tiles(g));
+    const int nb = (tilesY - 1) * g.W + (tilesX - 1) * g.H * (conn == 2 ? 2 : 1);
+    const bool vec = (g.W % 4 == 0) && aligned16(par);
     if (g.tl) {
         if (conn == 1) {
-            TISEG_LAUNCH(c, (k_ccl_local<Img, 1, true>), lg, 32 * CCL_WARPS, 0, g, img, par);
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 1, true>), lg, 32 * CCL_WARPS, 0, g, img, par, vec);
             if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
         } else {
-            TISEG_LAUNCH(c, (k_ccl_local<Img, 2, true>), lg, 32 * CCL_WARPS, 0, g, img, par);
+            TISEG_LAUNCH(c, (k_ccl_local<Img, 2, true>), lg, 32 * CCL_WARPS, 0, g, img, par, vec);
             if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, true>), dim3((nb + 255) / 256, 1), 256, 0, g, img, par);
         }
     } else if (conn == 1) {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 1, false>), lg, 32 * CCL_WARPS, 0, g, img, par);
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 1, false>), lg, 32 * CCL_WARPS, 0, g, img, par, vec);
         if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 1, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     } else {
-        TISEG_LAUNCH(c, (k_ccl_local<Img, 2, false>), lg, 32 * CCL_WARPS, 0, g, img, par);
+        TISEG_LAUNCH(c, (k_ccl_local<Img, 2, false>), lg, 32 * CCL_WARPS, 0, g, img, par, vec);
         if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<Img, 2, false>), dim3((nb + 255) / 256, g.N), 256, 0, g, img, par);
     }
     return ccl_flatten(c, g, par);
