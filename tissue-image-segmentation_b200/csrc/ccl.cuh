@@ -89,8 +89,48 @@ struct ImgNonZeroI32 {          // binary: non-zero int32
 
 static __device__ __noinline__ void uf_union_tile(int* lab, int a, int b) { uf_union(lab, a, b); }
 
+// four consecutive pixels gi .. gi+3 of one row: value, or CCL_BG on the background.  The generic form asks the functor
+// pixel by pixel; the functors of the hot paths read the four pixels with one 128-bit / 32-bit load when the address
+// is aligned.
+template <class Img>
+__device__ __forceinline__ void img_quad(const Img& img, int n, long long gi, int (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { int vv = 0; v[k] = img(n, gi + k, vv) ? vv : CCL_BG; }
+}
+__device__ __forceinline__ bool quad_u8(const uint8_t* q, int (&b)[4]) {
+    if (((uintptr_t)q) & 3) return false;
+    const unsigned w = *reinterpret_cast<const unsigned*>(q);
+    b[0] = w & 255u; b[1] = (w >> 8) & 255u; b[2] = (w >> 16) & 255u; b[3] = w >> 24;
+    return true;
+}
+__device__ __forceinline__ bool quad_i32(const int32_t* q, int (&b)[4]) {
+    if (((uintptr_t)q) & 15) return false;
+    const int4 w = *reinterpret_cast<const int4*>(q);
+    b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w;
+    return true;
+}
+#define TISEG_IMG_QUAD(Type, LOAD, PTR, FG, VAL)                                                                  \
+    __device__ __forceinline__ void img_quad(const Type& img, int n, long long gi, int (&v)[4]) {                 \
+        int b[4];                                                                                                 \
+        if (LOAD(PTR + gi, b)) {                                                                                  \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) v[k] = (FG) ? (VAL) : CCL_BG;                           \
+        } else {                                                                                                  \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) { int vv = 0; v[k] = img(n, gi + k, vv) ? vv : CCL_BG; } \
+        }                                                                                                         \
+    }
+TISEG_IMG_QUAD(ImgEqI32, quad_i32, img.p, b[k] != img.bg, b[k])
+TISEG_IMG_QUAD(ImgNonZeroI32, quad_i32, img.p, b[k] != 0, 1)
+TISEG_IMG_QUAD(ImgEqU8, quad_u8, img.p, b[k] != img.bg, b[k])
+TISEG_IMG_QUAD(ImgMaskU8, quad_u8, img.p, b[k] != 0, 1)
+TISEG_IMG_QUAD(ImgNotMaskU8, quad_u8, img.p, b[k] == 0, 1)
+TISEG_IMG_QUAD(ImgClassU8, quad_u8, img.p, b[k] == img.cls, 1)
+TISEG_IMG_QUAD(ImgNotClassU8, quad_u8, img.p, b[k] != img.cls, 1)
+TISEG_IMG_QUAD(ImgBelowU8, quad_u8, img.p, b[k] < img.thr, 1)
+TISEG_IMG_QUAD(ImgEqU8Drop, quad_u8, img.p, b[k] != 0 && b[k] != img.drop, b[k])
+#undef TISEG_IMG_QUAD
+
 template <class Img, int CONN, bool LISTED>
-__global__ void __launch_bounds__(32 * CCL_WARPS) k_ccl_local(Geom g, Img img, int* __restrict__ par, bool vec) {
+__global__ void __launch_bounds__(32 * CCL_WARPS, LISTED ? 1 : 5) k_ccl_local(Geom g, Img img, int* __restrict__ par, bool vec) {
     __shared__ __align__(16) int sval[CCL_TH * CCL_TW];
     __shared__ __align__(16) int slab[CCL_TH * CCL_TW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,11 +149,14 @@ __global__ void __launch_bounds__(32 * CCL_WARPS) k_ccl_local(Geom g, Img img, i
 #pragma unroll
     for (int r = 0; r < CCL_RPW; ++r) {
         const int y = yt + r * CCL_WARPS + warp;
+        if (y < g.H && x0 + 3 < g.W) img_quad(img, n, base + (long long)y * g.W + x0, v[r]);
+        else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int vv = 0;
-            v[r][k] = CCL_BG;
-            if (y < g.H && x0 + k < g.W && img(n, base + (long long)y * g.W + x0 + k, vv)) v[r][k] = vv;
+            for (int k = 0; k < 4; ++k) {
+                int vv = 0;
+                v[r][k] = CCL_BG;
+                if (y < g.H && x0 + k < g.W && img(n, base + (long long)y * g.W + x0 + k, vv)) v[r][k] = vv;
+            }
         }
     }
 #pragma unroll
