@@ -217,26 +217,34 @@ __global__ void __launch_bounds__(32 * CCL_WARPS, LISTED ? 1 : 5) k_ccl_local(Ge
         }
     }
     __syncthreads();
-    // phase C: local flatten, one chase per in-thread run, one global write per thread
+    // phase C1: the threads that hold a run START point it at its local root (the inside of a blob has nothing to do)
+#pragma unroll
+    for (int r = 0; r < CCL_RPW; ++r) {
+        const int li0 = (r * CCL_WARPS + warp) * CCL_TW + lane * 4;
+        unsigned starts = fgm[r] & ~cm[r];
+        while (starts) {
+            const int k = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int root = uf_find(slab, li0 + k);
+            if (root != li0 + k) slab[li0 + k] = root;
+        }
+    }
+    __syncthreads();
+    // phase C2: every pixel reads the root through its run start; one 128-bit global write per thread
 #pragma unroll
     for (int r = 0; r < CCL_RPW; ++r) {
         const int row = r * CCL_WARPS + warp, y = yt + row, li0 = row * CCL_TW + lane * 4;
         if (y >= g.H || x0 >= g.W) continue;
-        int out[4] = {-1, -1, -1, -1};
-        // run starts inside the thread: foreground pixels that do not continue, plus pixel 0 if it does
-        unsigned starts = fgm[r] & (~cm[r] | 1u);
-        while (starts) {
-            const int k = __ffs(starts) - 1;
-            starts &= starts - 1;
-            const int root = uf_find(slab, (k == 0 && (cm[r] & 1u)) ? l0[r] : li0 + k);
-            const int o = (yt + (root >> 7)) * g.W + tx * CCL_TW + (root & (CCL_TW - 1));
-            // the run: pixel k and the continuing pixels right after it
-            const unsigned runlen = __ffs(~(cm[r] >> (k + 1)));            // pixels k .. k+runlen-1 (cm has four bits)
-            const unsigned mask = ((1u << runlen) - 1u) << k;
-            if (mask & 1u) out[0] = o;
-            if (mask & 2u) out[1] = o;
-            if (mask & 4u) out[2] = o;
-            if (mask & 8u) out[3] = o;
+        int out[4];
+        int root = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool fg = (fgm[r] >> k) & 1u, cont = (cm[r] >> k) & 1u;
+            if (fg && !(k > 0 && cont)) {
+                const int q = slab[(k == 0 && cont) ? l0[r] : li0 + k];
+                root = (yt + (q >> 7)) * g.W + tx * CCL_TW + (q & (CCL_TW - 1));
+            }
+            out[k] = fg ? root : -1;
         }
         int* dst = par + base + (long long)y * g.W + x0;
         if (vec) *reinterpret_cast<int4*>(dst) = make_int4(out[0], out[1], out[2], out[3]);
