@@ -268,6 +268,59 @@ __device__ __forceinline__ int run_end_lane(unsigned cont, int lane) {
     return brk ? (__ffs(brk) - 1) - 1 : 31;
 }
 
+// ---- rows as quads: one warp = 128 pixels of a row, four per thread -------------------------------------------
+// The pixel-per-lane kernels of this library were issue-bound (ncu: 70-85 % issue slots at a quarter of the HBM
+// rate); the per-run kernels therefore read four pixels per thread and still post ONE set of atomics per run of
+// equal keys inside the warp's 128 pixels.
+struct Quad { int n, y, x, lane; long long base; };      // x = the first of the thread's four columns
+inline dim3 quad_grid(const Geom& g) {
+    long long warps = (long long)((g.W + 127) / 128) * g.H;
+    return dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), grid_tiles(g), 1);
+}
+__device__ __forceinline__ bool warp_quad(const Geom& g, Quad& q) {
+    const int segs = (g.W + 127) >> 7;
+    const long long w = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (w >= (long long)segs * g.H) return false;
+    q.lane = threadIdx.x & 31;
+    q.n = blockIdx.y;
+    q.y = (int)(w / segs);
+    q.x = (int)(w - (long long)q.y * segs) * 128 + q.lane * 4;
+    q.base = (long long)q.n * g.P;
+    return true;
+}
+__device__ __forceinline__ void quad_load_i32(const Geom& g, const Quad& q, const int32_t* __restrict__ tile, int oob, bool vec, int (&v)[4]) {
+    const int32_t* rp = tile + (long long)q.y * g.W + q.x;
+    if (vec && q.x + 3 < g.W) { const int4 t = *reinterpret_cast<const int4*>(rp); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = q.x + k < g.W ? rp[k] : oob;
+    }
+}
+// runs of equal keys along the warp's 128 pixels; `null` keys belong to no run
+struct QuadRuns {
+    unsigned fg, cont;      // bit k: pixel k has a key / continues the run of the pixel to its left
+    int ext;                // pixels beyond my pixel 3 that belong to its run
+};
+template <class K>
+__device__ __forceinline__ QuadRuns quad_runs(const K (&key)[4], K null, int lane) {
+    QuadRuns r;
+    const K left = __shfl_up_sync(0xffffffffu, key[3], 1);
+    r.fg = (key[0] != null ? 1u : 0u) | (key[1] != null ? 2u : 0u) | (key[2] != null ? 4u : 0u) | (key[3] != null ? 8u : 0u);
+    r.cont = (((lane > 0 && key[0] == left) ? 1u : 0u) | (key[1] == key[0] ? 2u : 0u) | (key[2] == key[1] ? 4u : 0u) |
+              (key[3] == key[2] ? 8u : 0u)) & r.fg;
+    const unsigned full = __ballot_sync(0xffffffffu, r.cont == 15u);
+    const unsigned rest = lane < 31 ? full >> (lane + 1) : 0u;
+    const int nfull = __ffs(~rest) - 1, next = lane + 1 + nfull;
+    const int lead = __ffs(~r.cont) - 1;                                   // my leading continuing pixels
+    const int nl = __shfl_sync(0xffffffffu, lead, next < 32 ? next : 31);
+    r.ext = 4 * nfull + (next < 32 ? nl : 0);
+    return r;
+}
+// iterate the runs that START in this thread: k = first pixel, len = length inside the warp's 128 pixels
+#define FOR_QUAD_RUNS(r, k, len)                                                                             \
+    for (unsigned _s = (r).fg & ~(r).cont, k = 0, len = 0;                                                   \
+         _s && (k = __ffs(_s) - 1, len = __ffs(~((r).cont >> (k + 1))), len += (k + len == 4 ? (r).ext : 0), true); _s &= _s - 1)
+
 // (no __restrict__/const: parents are updated concurrently, loads must stay coherent)
 __device__ __forceinline__ int uf_find(int* par, int x) {
     int p = par[x];

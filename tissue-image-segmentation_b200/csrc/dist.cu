@@ -284,27 +284,18 @@ k_filter_root_bits(Geom g, const uint8_t* __restrict__ low, unsigned* bits) {
 // histogram of the flood labels (values 0..K) and the first raster pixel of each label, one pair of atomics per
 // in-segment run
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int* first, int KS) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    int v[STRIP_R];
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        v[r] = (s.okx && y < g.H) ? ws[s.base + (long long)y * g.W + s.x] : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        if (!__ballot_sync(0xffffffffu, v[r] > 0)) continue;       // (uniform) nothing but background here
-        int vl = __shfl_up_sync(0xffffffffu, v[r], 1);
-        bool cont = s.lane > 0 && v[r] == vl;
-        unsigned m = __ballot_sync(0xffffffffu, cont);
-        // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
-        if (v[r] > 0 && !cont) {
-            const long long o = (long long)s.n * KS + v[r];
-            atomicAdd(&hist[o], run_end_lane(m, s.lane) - s.lane + 1);
-            atomicMin(&first[o], (s.y0 + r) * g.W + s.x);
-        }
+k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int* first, int KS, bool vec) {
+    Quad q;
+    if (!warp_quad(g, q)) return;
+    int v[4];
+    quad_load_i32(g, q, ws + q.base, 0, vec, v);
+    // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
+    if (!__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) return;
+    const QuadRuns r = quad_runs(v, 0, q.lane);
+    FOR_QUAD_RUNS(r, k, len) {
+        const long long o = (long long)q.n * KS + v[k];
+        atomicAdd(&hist[o], (int)len);
+        atomicMin(&first[o], q.y * g.W + q.x + (int)k);
     }
 }
 
@@ -507,21 +498,21 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     TISEG_TRY(zero(c, nflagged, sizeof(int)));
     TISEG_TRY(zero(c, fbits, (size_t)N * g.H * g.SEG * sizeof(unsigned)));
     TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);
-    TISEG_LAUNCH(c, k_ws_hist, strip_grid(g), TISEG_THREADS, 0, g, wsl, hist, first, KS);
+    TISEG_LAUNCH(c, k_ws_hist, quad_grid(g), TISEG_THREADS, 0, g, wsl, hist, first, KS, (g.W % 4 == 0) && aligned16(wsl));
     TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged);
     //   background 0 (every tile but degenerate ones): ids = rank of each region's first pixel; watershed lines
     //   are found on the flood labels themselves (the renumbering is a bijection)
     TISEG_LAUNCH(c, k_first_bits, dim3(8, N), 256, 0, g, first, KS, nmark, fbits);
     TISEG_TRY(rank_from_bits(c, g, fbits, rank, nullptr));
     TISEG_LAUNCH(c, k_arrange_lut, dim3(8, N), 256, 0, g, first, rank, KS, nmark, lut);
-    const dim3 quad_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
-    TISEG_LAUNCH(c, k_wsl_remove<false>, quad_grid, TISEG_THREADS, 0, g, wsl, lut, KS, inst, (g.W % 4 == 0) && aligned16(wsl, inst));
+    const dim3 px4_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_wsl_remove<false>, px4_grid, TISEG_THREADS, 0, g, wsl, lut, KS, inst, (g.W % 4 == 0) && aligned16(wsl, inst));
     //   any other background: the general relabelling, on the listed tiles only (no blocks do anything otherwise)
     Geom gl = listed_geom(g, flagged, nflagged);
     TISEG_TRY(ccl_build(c, gl, ImgEqI32TileBg{wsl, bg}, 2, par));
     TISEG_TRY(rank_roots(c, gl, par, rank, nullptr));
     TISEG_TRY(apply_rank(c, gl, par, rank, arranged));
-    TISEG_LAUNCH(c, k_wsl_remove<true>, dim3(quad_grid.x, 1), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst,
+    TISEG_LAUNCH(c, k_wsl_remove<true>, dim3(px4_grid.x, 1), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst,
                  (g.W % 4 == 0) && aligned16(arranged, inst));
     return TISEG_OK;
 }

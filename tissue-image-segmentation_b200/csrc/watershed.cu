@@ -38,29 +38,19 @@ k_blob_roots(Geom g, const unsigned* __restrict__ bits, const int* __restrict__ 
 
 // bounding box + area per blob, one set of atomics per in-segment run
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    int p[STRIP_R];
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        p[r] = (s.okx && y < g.H) ? par[s.base + (long long)y * g.W + s.x] : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        if (!__ballot_sync(FULL, p[r] >= 0)) continue;           // (uniform) nothing but background here
-        int pl = __shfl_up_sync(FULL, p[r], 1);
-        bool cont = s.lane > 0 && p[r] >= 0 && pl == p[r];
-        unsigned m = __ballot_sync(FULL, cont);
-        if (p[r] >= 0 && !cont) {
-            int end = run_end_lane(m, s.lane);
-            long long o = (long long)s.n * b.KS + rank[s.base + p[r]];
-            atomicMax(&b.ymax[o], s.y0 + r);
-            atomicMin(&b.xmin[o], s.x);
-            atomicMax(&b.xmax[o], s.x + (end - s.lane));
-            atomicAdd(&b.area[o], end - s.lane + 1);
-        }
+k_blob_bbox(Geom g, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b, bool vec) {
+    Quad q;
+    if (!warp_quad(g, q)) return;
+    int p[4];
+    quad_load_i32(g, q, par + q.base, -1, vec, p);
+    if (!__any_sync(FULL, p[0] >= 0 || p[1] >= 0 || p[2] >= 0 || p[3] >= 0)) return;           // (uniform) background only
+    const QuadRuns r = quad_runs(p, -1, q.lane);
+    FOR_QUAD_RUNS(r, k, len) {
+        const long long o = (long long)q.n * b.KS + rank[q.base + p[k]];
+        atomicMax(&b.ymax[o], q.y);
+        atomicMin(&b.xmin[o], q.x + (int)k);
+        atomicMax(&b.xmax[o], q.x + (int)k + (int)len - 1);
+        atomicAdd(&b.area[o], (int)len);
     }
 }
 
@@ -976,7 +966,7 @@ int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank,
     TISEG_LAUNCH(c, k_blob_init, dim3(8, g.N), 256, 0, b, g.W);
     TISEG_LAUNCH(c, k_blob_roots, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), g.N), TISEG_THREADS, 0,
                  g, root_bits, rank, b);
-    TISEG_LAUNCH(c, k_blob_bbox, strip_grid(g), TISEG_THREADS, 0, g, par, rank, b);
+    TISEG_LAUNCH(c, k_blob_bbox, quad_grid(g), TISEG_THREADS, 0, g, par, rank, b, (g.W % 4 == 0) && aligned16(par));
     if (want_offsets) TISEG_LAUNCH(c, k_blob_offsets, g.N, 256, 0, b);
     return TISEG_OK;
 }
