@@ -404,9 +404,12 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
                     pw[0] = a.x; pw[1] = a.y; pw[2] = a.z; pw[3] = a.w;
                     tw[0] = b.x; tw[1] = b.y; tw[2] = b.z; tw[3] = b.w;
                 } else {
-                    for (int k = 0; k < npx; ++k) {
-                        pw[k >> 2] |= (unsigned)pred[base + i + k] << (8 * (k & 3));
-                        tw[k >> 2] |= (unsigned)gt[base + i + k] << (8 * (k & 3));
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {               // (unrolled: pw / tw stay in registers)
+                        if (k < npx) {
+                            pw[k >> 2] |= (unsigned)pred[base + i + k] << (8 * (k & 3));
+                            tw[k >> 2] |= (unsigned)gt[base + i + k] << (8 * (k & 3));
+                        }
                     }
                 }
             }
@@ -733,7 +736,9 @@ int tiseg_sem_counts(tiseg_ctx* c, const uint8_t* pred, const uint8_t* gt, int N
     TISEG_TRY(zero(c, d_valid, (size_t)N * sizeof(int64_t)));
     unsigned gx = flat4_grid(g.P);
     gx = gx > 64 ? (gx + 7) / 8 : gx;                         // ~8 groups per thread
-    if ((C + 1) * (C + 1) <= 16 && gx > 16) gx = (gx + 1) / 2; // the 16-pixel path: ~4 trips per thread
+    // the 16-pixel path: few blocks per tile with many trips each — every block ends with 5C + 1 global atomics on the
+    // handful of cache lines that hold the counters, and those serialise in L2
+    if ((C + 1) * (C + 1) <= 16 && gx > 16) gx = 16;
     bool vec = (g.P % 4 == 0) && ((((uintptr_t)d_pred) | ((uintptr_t)d_gt)) & 3) == 0;
     TISEG_LAUNCH(c, k_sem_counts, dim3(gx, N), TISEG_THREADS, 0, (long long)g.P, d_pred, d_gt, C, ignore_index,
                  (unsigned long long*)d_counts, (unsigned long long*)d_valid, vec);
