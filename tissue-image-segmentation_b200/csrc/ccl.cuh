@@ -230,27 +230,26 @@ __global__ void __launch_bounds__(32 * CCL_WARPS, LISTED ? 1 : 5) k_ccl_local(Ge
         }
     }
     __syncthreads();
-    // phase C2: every pixel reads the root through its run start; one 128-bit global write per thread
+    // phase C2: every pixel reads the root through its run start (its own label); one 128-bit global write per thread
 #pragma unroll
     for (int r = 0; r < CCL_RPW; ++r) {
         const int row = r * CCL_WARPS + warp, y = yt + row, li0 = row * CCL_TW + lane * 4;
         if (y >= g.H || x0 >= g.W) continue;
-        int out[4];
-        int root = -1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool fg = (fgm[r] >> k) & 1u, cont = (cm[r] >> k) & 1u;
-            if (fg && !(k > 0 && cont)) {
-                const int q = slab[(k == 0 && cont) ? l0[r] : li0 + k];
-                root = (yt + (q >> 7)) * g.W + tx * CCL_TW + (q & (CCL_TW - 1));
-            }
-            out[k] = fg ? root : -1;
-        }
+        const int4 lab = *reinterpret_cast<const int4*>(&slab[li0]);
+        const int q0 = slab[max(lab.x, 0)], q1 = slab[max(lab.y, 0)], q2 = slab[max(lab.z, 0)], q3 = slab[max(lab.w, 0)];
+        const int off = yt * g.W + tx * CCL_TW;
+        int4 out;
+        out.x = lab.x >= 0 ? (q0 >> 7) * g.W + (q0 & (CCL_TW - 1)) + off : -1;
+        out.y = lab.y >= 0 ? (q1 >> 7) * g.W + (q1 & (CCL_TW - 1)) + off : -1;
+        out.z = lab.z >= 0 ? (q2 >> 7) * g.W + (q2 & (CCL_TW - 1)) + off : -1;
+        out.w = lab.w >= 0 ? (q3 >> 7) * g.W + (q3 & (CCL_TW - 1)) + off : -1;
         int* dst = par + base + (long long)y * g.W + x0;
-        if (vec) *reinterpret_cast<int4*>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+        if (vec) *reinterpret_cast<int4*>(dst) = out;
         else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (x0 + k < g.W) dst[k] = out[k];
+            if (x0 < g.W) dst[0] = out.x;
+            if (x0 + 1 < g.W) dst[1] = out.y;
+            if (x0 + 2 < g.W) dst[2] = out.z;
+            if (x0 + 3 < g.W) dst[3] = out.w;
         }
     }
     if (LISTED) __syncthreads();        // the shared tile is reused by the next listed tile
