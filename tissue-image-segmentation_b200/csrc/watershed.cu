@@ -97,9 +97,10 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
 // ---- uint8 levels: FIFO buckets ---------------------------------------------------------------------------
 // A blob's flood is a chain of dependent steps (pop -> look at 4 neighbours -> push), so its speed is the latency
 // of the memory it runs in and the number of floods in flight.  Every blob is therefore STAGED into shared memory
-// first: the bounding box plus a one-pixel frame (no bounds checks in the flood), 5 bytes per cell — level (u8),
-// FIFO link (u16) and the local index of the seed pixel whose label the cell inherits (u16) — flooded there, and
-// written back with batched loads/stores.
+// first: the bounding box plus a one-pixel frame (no bounds checks in the flood), 4 bytes per cell — one 16-bit field
+// that holds the level until the cell is labelled and its FIFO link afterwards (the level is dead by then), and the
+// local index of the seed pixel whose label the cell inherits (u16) — flooded there, and written back with batched
+// loads/stores.
 //
 // One persistent kernel (one CTA per SM), fed from work lists sorted by size class so that long floods start first:
 //  * multi-slot floods — the workhorse.  Every warp owns an arena of shared memory that is cut into 1..SLOTS equal
@@ -107,7 +108,7 @@ k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __res
 //    seeds into their buckets in raster order (match_any), then LANE s FLOODS SLOT s: up to SLOTS independent floods
 //    advance per warp instruction.  Buckets are indexed by (level mod 32): a blob qualifies if its levels span < 32
 //    values (a distance map inside a nucleus does); the head and tail of the current level live in registers.
-//    Default geometry: 10 warps x 4096-cell arenas x 16 slots (other geometries behind TISEG_FLOOD_VARIANT).  A blob
+//    Default geometry: 12 warps x 4224-cell arenas x 16 slots (other geometries behind TISEG_FLOOD_VARIANT).  A blob
 //    whose seeds all carry one label is simply filled (a 4-connected blob is flooded completely from any seed).
 //  * general floods — framed boxes beyond the arena, or level spans >= 32: one blob per CTA at a time, staged by all
 //    warps into one 45056-cell slice with all 256 buckets.  The first sm_count/12 CTAs start with this list so the
@@ -184,8 +185,8 @@ __device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulh
 // Per-thread by-products (the caller reduces them if it wants them): the range [lmn, lmx] of the seed labels seen and
 // the lowest seed cell — a blob whose seeds all carry ONE label needs no ordered flood at all.
 struct SeedStats { int lmn, lmx, jseed; };
-template <class LT>
-__device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const LT* __restrict__ I,
+template <class IT, class LT>
+__device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const IT* __restrict__ I,
                                                 const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
                                                 int y0, int x0, int w, int h, unsigned short* lab, LT* lvl) {
     SeedStats st; st.lmn = 0x7fffffff; st.lmx = 0; st.jseed = 0x7fffffff;
@@ -202,7 +203,7 @@ __device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const 
             gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
         }
         int tpv[8], ov[8];
-        LT iv[8];
+        IT iv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
 #pragma unroll
@@ -211,7 +212,7 @@ __device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const 
             if (j < cells) {
                 const bool inblob = in[u] && tpv[u] == root;
                 lab[j] = (unsigned short)(inblob ? (ov[u] != 0 ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
-                lvl[j] = iv[u];
+                lvl[j] = (LT)iv[u];
                 if (inblob && ov[u] != 0) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
             }
         }
@@ -481,7 +482,7 @@ template <int WARPS, int ARENA, int SLOTS, bool PROF>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodWork wk,
               int* next, int* gheads, int32_t* out, int gen_first, int do_multi, long long* prof) {
-    constexpr size_t WARP_BYTES = (size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4;
+    constexpr size_t WARP_BYTES = (size_t)ARENA * 4 + (size_t)WM_R * SLOTS * 4;
     if (!do_multi) {       // second launch: what the first one found too wide in levels
         general_drain(g, image, par, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
         return;
@@ -497,7 +498,9 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
         unsigned short* nxs = lab + ARENA;
         unsigned short* head = nxs + ARENA;
         unsigned short* tail = head + WM_R * SLOTS;
-        unsigned char* lvl = reinterpret_cast<unsigned char*>(tail + WM_R * SLOTS);
+        // 4 bytes per cell: the level of a cell is dead once the cell is labelled and its FIFO link only lives after
+        // that, so both sit in the same 16-bit field (every reader below takes the level before it writes the link)
+        unsigned short* lvl = nxs;
         const int W = g.W;
         for (int cls = 0; cls < SLOTS; ++cls) {
             const int cap = ARENA / (cls + 1), slots = cls + 1;
@@ -591,7 +594,7 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
 // cells or whose area exceeds WR_SORT_MAX keep the heap flood (k_ws_flood_f64).
 #define WR_SORT_SMALL 1024        // values sorted by a 128-thread CTA
 #define WR_SORT_MAX 16384         // values sorted by a 1024-thread CTA
-#define WR_GEN_CAP 22528          // cells of the single-blob slice of the ranked general path (10 B per cell)
+#define WR_GEN_CAP 28160          // cells of the single-blob slice of the ranked general path (8 B per cell)
 
 __device__ __forceinline__ bool blob_is_huge(const BlobInfo& b, long long ko, int bid, int W) {
     return blob_cells(b, ko, bid, W) > WR_GEN_CAP || b.area[ko + bid] > WR_SORT_MAX;
@@ -735,8 +738,8 @@ __device__ __forceinline__ void general_drain_ranked(const Geom& g, const unsign
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem);
     unsigned short* nxs = lab + WR_GEN_CAP;
-    unsigned short* lvl = nxs + WR_GEN_CAP;
-    unsigned short* head = lvl + WR_GEN_CAP;
+    unsigned short* lvl = nxs;                       // level and FIFO link share a field, as in k_ws_flood_u8
+    unsigned short* head = nxs + WR_GEN_CAP;
     unsigned short* tail = head + WR_GEN_CAP;
     const int W = g.W;
     for (;;) {
@@ -775,10 +778,10 @@ k_ws_flood_ranked(Geom g, const unsigned short* __restrict__ level, const int* _
     __syncthreads();
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem) + (size_t)warp * ARENA * 5;
+        unsigned short* lab = reinterpret_cast<unsigned short*>(ws_smem) + (size_t)warp * ARENA * 4;
         unsigned short* nxs = lab + ARENA;
-        unsigned short* lvl = nxs + ARENA;
-        unsigned short* head = lvl + ARENA;
+        unsigned short* lvl = nxs;
+        unsigned short* head = nxs + ARENA;
         unsigned short* tail = head + ARENA;
         const int W = g.W;
         for (int cls = 0; cls < SLOTS; ++cls) {
@@ -983,7 +986,7 @@ template <int WARPS, int ARENA, int SLOTS>
 static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const BlobInfo& b,
                         FloodWork wk, int* next, int* gheads, int32_t* out, int* ints, bool debug) {
     static_assert(SLOTS <= WS_MAXCLS, "slots");
-    constexpr size_t MULTI = (size_t)WARPS * ((size_t)ARENA * 5 + (size_t)WM_R * SLOTS * 4);
+    constexpr size_t MULTI = (size_t)WARPS * ((size_t)ARENA * 4 + (size_t)WM_R * SLOTS * 4);
     constexpr size_t SMEM = MULTI > WG_SMEM_BYTES ? MULTI : WG_SMEM_BYTES;
     static_assert(SMEM + 64 <= 232448, "shared memory");
     TISEG_LAUNCH(c, k_flood_count, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
@@ -1046,10 +1049,11 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
     switch (variant) {            // arena geometries kept for tuning on other blob-size distributions
-        case 1: return flood_launch<8, 5376, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 2: return flood_launch<16, 2688, 8>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 3: return flood_launch<12, 3584, 8>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        default: return flood_launch<10, 4096, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 1: return flood_launch<14, 3584, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 2: return flood_launch<16, 3072, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 3: return flood_launch<10, 5120, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 4: return flood_launch<11, 4608, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        default: return flood_launch<12, 4224, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
     }
 }
 
@@ -1069,8 +1073,8 @@ int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const in
         return TISEG_OK;
     }
     // ranked levels per blob, then the bucket flood in shared memory
-    constexpr int WARPS = 7, ARENA = 3072, SLOTS = 16;
-    constexpr size_t MULTI = (size_t)WARPS * ARENA * 10, GEN = (size_t)WR_GEN_CAP * 10;
+    constexpr int WARPS = 7, ARENA = 3840, SLOTS = 16;
+    constexpr size_t MULTI = (size_t)WARPS * ARENA * 8, GEN = (size_t)WR_GEN_CAP * 8;
     constexpr size_t SMEM = MULTI > GEN ? MULTI : GEN;
     static_assert(SMEM + 64 <= 232448, "shared memory");
     const size_t max_blobs = (size_t)N * ((size_t)g.P / 2 + 1);
