@@ -1049,10 +1049,10 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
     switch (variant) {            // arena geometries kept for tuning on other blob-size distributions
-        case 1: return flood_launch<14, 3584, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 2: return flood_launch<16, 3072, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 1: return flood_launch<13, 3840, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 2: return flood_launch<12, 4096, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
         case 3: return flood_launch<10, 5120, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 4: return flood_launch<11, 4608, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 4: return flood_launch<12, 4224, 12>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
         default: return flood_launch<12, 4224, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
     }
 }
