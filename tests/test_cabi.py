@@ -46,3 +46,16 @@ def test_no_cpu_fallback(lib):
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, f)).read().replace("CPU oracle", ""), f
+
+
+def test_label_maker_classes_mirror_the_reference_constructors():
+    """Host-side mirror of tiseg/datasets/ops: same class names and constructor arguments; the one configuration the
+    reference itself cannot run (UNetLabelMake with class weights, unet_map.py:120-124) is refused, not emulated."""
+    import inspect
+    from tiseg_b200 import label_makers as lm
+    assert list(inspect.signature(lm.BoundLabelMake.__init__).parameters)[1:] == ["edge_id", "selem_radius"]
+    assert list(inspect.signature(lm.DistanceLabelMake.__init__).parameters)[1:] == ["inst_norm"]
+    assert list(inspect.signature(lm.UNetLabelMake.__init__).parameters)[1:] == ["wc", "w0", "sigma"]
+    assert lm.BoundLabelMake(selem_radius=2).radius == (2, 2)
+    with pytest.raises(NotImplementedError):
+        lm.UNetLabelMake(wc={1: 2.0})
