@@ -153,23 +153,15 @@ k_apply_rank(Geom g, const int* __restrict__ par, const int* __restrict__ rank, 
     }
 }
 
-// area[root] += length of each in-segment run of pixels sharing the root (one atomic per run)
-__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* __restrict__ par, int* area) {
-    Strip s;
-    if (!warp_strip(g, s)) return;
-    int p[STRIP_R];
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int y = s.y0 + r;
-        p[r] = (s.okx && y < g.H) ? par[s.base + (long long)y * g.W + s.x] : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < STRIP_R; ++r) {
-        int pl = __shfl_up_sync(0xffffffffu, p[r], 1);
-        bool cont = s.lane > 0 && p[r] >= 0 && pl == p[r];
-        unsigned m = __ballot_sync(0xffffffffu, cont);
-        if (p[r] >= 0 && !cont) atomicAdd(&area[s.base + p[r]], run_end_lane(m, s.lane) - s.lane + 1);
-    }
+// area[root] += length of each run of pixels sharing the root (one atomic per run of the warp's 128 pixels)
+__global__ void __launch_bounds__(TISEG_THREADS) k_ccl_areas(Geom g, const int* __restrict__ par, int* area, bool vec) {
+    Quad q;
+    if (!warp_quad(g, q)) return;
+    int p[4];
+    quad_load_i32(g, q, par + q.base, -1, vec, p);
+    if (!__any_sync(0xffffffffu, p[0] >= 0 || p[1] >= 0 || p[2] >= 0 || p[3] >= 0)) return;      // (uniform)
+    const QuadRuns r = quad_runs(p, -1, q.lane);
+    FOR_QUAD_RUNS(r, k, len) atomicAdd(&area[q.base + p[k]], (int)len);
 }
 
 int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
@@ -213,7 +205,7 @@ int apply_rank(tiseg_ctx* c, const Geom& g, const int* par, const int* rank, int
 
 int ccl_areas(tiseg_ctx* c, const Geom& g, const int* par, int* area) {
     TISEG_TRY(zero(c, area, (size_t)g.N * g.P * sizeof(int)));
-    TISEG_LAUNCH(c, k_ccl_areas, strip_grid(g), TISEG_THREADS, 0, g, par, area);
+    TISEG_LAUNCH(c, k_ccl_areas, quad_grid(g), TISEG_THREADS, 0, g, par, area, (g.W % 4 == 0) && aligned16(par));
     return TISEG_OK;
 }
 

@@ -74,16 +74,17 @@ int remove_small_mask(tiseg_ctx* c, const Geom& g, const uint8_t* mask, int min_
 }
 
 // int input: the label values are the component ids (skimage: bincount of the labels themselves)
-__global__ void k_label_hist(Geom g, const int32_t* __restrict__ lab, int* hist, int KS, int* bad) {
-    Pix px;
-    if (!warp_pixel(g, px)) return;
-    int v = px.ok ? lab[px.base + px.idx] : 0;
-    int vl = __shfl_up_sync(0xffffffffu, v, 1);
-    bool cont = px.lane > 0 && v == vl;
-    unsigned m = __ballot_sync(0xffffffffu, cont);
-    if (v != 0 && !cont) {
-        if (v < 0 || v >= KS) { *bad = 1; return; }
-        atomicAdd(&hist[(long long)px.n * KS + v], run_end_lane(m, px.lane) - px.lane + 1);
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_label_hist(Geom g, const int32_t* __restrict__ lab, int* hist, int KS, int* bad, bool vec) {
+    Quad q;
+    if (!warp_quad(g, q)) return;
+    int v[4];
+    quad_load_i32(g, q, lab + q.base, 0, vec, v);
+    if (!__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) return;                      // (uniform)
+    const QuadRuns r = quad_runs(v, 0, q.lane);
+    FOR_QUAD_RUNS(r, k, len) {
+        if (v[k] < 0 || v[k] >= KS) { *bad = 1; continue; }
+        atomicAdd(&hist[(long long)q.n * KS + v[k]], (int)len);
     }
 }
 __global__ void k_drop_small_labels(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ hist, int KS,
@@ -102,7 +103,7 @@ int remove_small_labels(tiseg_ctx* c, const Geom& g, const int32_t* lab, int min
     if (!hist || !bad) return TISEG_ERR_CUDA;
     TISEG_TRY(zero(c, hist, (size_t)g.N * KS * sizeof(int)));
     TISEG_TRY(zero(c, bad, sizeof(int)));
-    TISEG_LAUNCH(c, k_label_hist, warp_grid(g), TISEG_THREADS, 0, g, lab, hist, KS, bad);
+    TISEG_LAUNCH(c, k_label_hist, quad_grid(g), TISEG_THREADS, 0, g, lab, hist, KS, bad, (g.W % 4 == 0) && aligned16(lab));
     TISEG_LAUNCH(c, k_drop_small_labels, warp_grid(g), TISEG_THREADS, 0, g, lab, hist, KS, min_size, out);
     return TISEG_OK;
 }
