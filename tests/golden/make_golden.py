@@ -253,6 +253,45 @@ def main():
         out = umap.UNetLabelMake(w0=10.0, sigma=5.0)(data)
         lab["l%d_unet_w" % j], lab["l%d_unet_inner" % j] = out["loss_weight_map"], out["sem_gt_inner"]
     np.savez_compressed(os.path.join(HERE, "labelgen_ref.npz"), **lab)
+
+    # ---- DIST post-process: the reference's OWN SOURCE TEXT (dist.py:31-131 helpers + DIST.postprocess :275-284),
+    # executed with scikit-image replaced by the oracle's port (scikit-image is absent here).  This pins the control
+    # flow of the restatement in oracle/postprocess.py, not scikit-image itself.
+    import ast, textwrap
+    from oracle import skimage_port as skp
+    dsrc = open(os.path.join(REF, "tiseg/models/segmentors/dist.py")).read()
+    tree = ast.parse(dsrc)
+    wanted = ("prepare_prob", "H_reconstruction_erosion", "find_maxima", "generate_wsl", "arrange_label",
+              "dynamic_watershed_alias")
+    chunks = [ast.get_source_segment(dsrc, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DIST"][0]
+    post = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "postprocess"][0]
+    chunks.append(textwrap.dedent(ast.get_source_segment(dsrc, post, padded=True)))
+    morph = types.SimpleNamespace(
+        reconstruction=lambda seed, mask, method="erosion": skp.reconstruction_erosion(seed, mask),
+        dilation=_opp_mod().dilation, erosion=_opp_mod().erosion, square=_opp_mod().square, disk=_opp_mod().disk,
+        watershed=lambda image, markers, mask=None: skp.watershed(image, markers, mask))
+    measure = types.SimpleNamespace(label=skp.label)
+    class _Numpy1Scalars:
+        """numpy as the reference's pinned numpy 1.x sees scalars: ``np.uint8(255) + 1`` inside the np.vectorize'd
+        ``making_top_mask`` (dist.py:48-52) promotes to a Python-int sum (256); numpy >= 2 would wrap it to 0."""
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def vectorize(f):
+            return np.vectorize(lambda x: f(int(x)))
+    ns = {"np": _Numpy1Scalars(), "morph": morph, "measure": measure}
+    exec(compile("\n\n".join(chunks), "dist.py (reference source)", "exec"), ns)
+    dref = {}
+    for j, (H, W) in enumerate([(48, 56), (64, 64), (80, 100), (33, 47)]):
+        t = synth.tile_dist(2, 40 + j, H=H, W=W)
+        d = t["dist_logit"]
+        if j == 3:
+            d = d * 0 + 7.3                     # one plateau: the background value of arrange_label is the label
+        dref["d%d_in" % j] = d
+        dref["d%d_out" % j] = ns["postprocess"](None, None, d)[1]
+    np.savez_compressed(os.path.join(HERE, "dist_ref.npz"), **dref)
     print("golden vectors written to", HERE)
 
 

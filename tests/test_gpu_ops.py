@@ -647,3 +647,10 @@ def test_label_makers_degenerate_geometry():
         wi, ww = opp.unet_weight_map(fixed)
         _diff(inner, wi, "unet inner %dx%d" % (H, W))
         np.testing.assert_allclose(w, ww, rtol=1e-12, atol=0)
+
+
+def test_postproc_dist_matches_reference_source_golden():
+    """tiseg_postproc_dist vs the outputs of the reference's own dist.py source text (tests/golden/dist_ref.npz)."""
+    m = np.load(os.path.join(G, "dist_ref.npz"))
+    for j in range(4):
+        _diff(ops.postproc_dist(m["d%d_in" % j]), m["d%d_out" % j], "dist inst (reference source golden %d)" % j)

@@ -235,3 +235,15 @@ def test_label_generation_matches_reference():
             sem = np.where(fixed == 0, 0, m["l%d_sem" % j])
             assert np.array_equal(np.where(inner == 0, 0, sem), m["l%d_unet_inner" % j])
             assert np.array_equal(w, m["l%d_unet_w" % j])
+
+
+def test_dist_postprocess_matches_reference_source():
+    """oracle dist_postprocess (literal and fast forms) == the reference's own dist.py helpers + DIST.postprocess
+    executed from its source text with scikit-image replaced by the port (tests/golden/dist_ref.npz): pins the control
+    flow of the restatement."""
+    m = np.load(os.path.join(G, "dist_ref.npz"))
+    for j in range(4):
+        want = m["d%d_out" % j]
+        for literal in (True, False):
+            got = opp.dist_postprocess(None, m["d%d_in" % j], literal=literal)[1]
+            assert np.array_equal(got, want), (j, literal)
