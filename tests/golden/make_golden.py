@@ -292,6 +292,62 @@ def main():
         dref["d%d_in" % j] = d
         dref["d%d_out" % j] = ns["postprocess"](None, None, d)[1]
     np.savez_compressed(os.path.join(HERE, "dist_ref.npz"), **dref)
+
+    # ---- the other segmentors' post-processes, same technique: the method's source text out of the reference file,
+    # executed with `self` = a namespace carrying the attributes it reads; scipy / OpenCV are the real libraries,
+    # scikit-image calls go to the port, align_foreground is the reference's own numba function (loaded above).
+    import math
+    import cv2
+    from scipy.ndimage import binary_fill_holes, measurements
+
+    def ref_method(relpath, cls_name, meth_name, extra):
+        src = open(os.path.join(REF, relpath)).read()
+        tr = ast.parse(src)
+        c = [n for n in tr.body if isinstance(n, ast.ClassDef) and n.name == cls_name][0]
+        f = [n for n in c.body if isinstance(n, ast.FunctionDef) and n.name == meth_name][0]
+        env = {"np": np, "math": math, "cv2": cv2, "binary_fill_holes": binary_fill_holes, "measurements": measurements,
+               "remove_small_objects": _opp_mod().remove_small_objects, "watershed": skp.watershed,
+               "measure": types.SimpleNamespace(label=skp.label),
+               "morphology": types.SimpleNamespace(dilation=lambda image, selem=None: _opp_mod().dilation(image, selem),
+                                                   disk=_opp_mod().disk),
+               "align_foreground": pp.align_foreground}
+        env.update(extra)
+        exec(compile(textwrap.dedent(ast.get_source_segment(src, f, padded=True)), relpath, "exec"), env)
+        return env[meth_name]
+
+    seg = {}
+    cfg = lambda radius: types.SimpleNamespace(test_cfg={"radius": radius}, num_classes=3)
+    unet_pp = ref_method("tiseg/models/segmentors/unet.py", "UNet", "postprocess", {})
+    cdnet_pp = ref_method("tiseg/models/segmentors/cdnet.py", "CDNet", "postprocess", {})
+    dcan_pp = ref_method("tiseg/models/segmentors/dcan.py", "DCAN", "postprocess", {})
+    mt_unet = ref_method("tiseg/models/segmentors/multi_task_unet.py", "MultiTaskUNet", "postprocess", {})
+    mt_cunet = ref_method("tiseg/models/segmentors/multi_task_cunet.py", "MultiTaskCUNet", "postprocess", {})
+    mt_cdnet = ref_method("tiseg/models/segmentors/multi_task_cdnet.py", "MultiTaskCDNet", "postprocess", {})
+    hover = ref_method("tiseg/models/segmentors/hovernet.py", "HoverNet", "hover_post_proc", {})
+    for j, (H, W, C) in enumerate([(96, 110, 4), (128, 128, 2), (70, 61, 7)]):
+        t = synth.gt_and_pred(9300 + j, H, W, n=max(4, H * W // 600), num_classes=C)
+        pred = (t["pred_sem"] if "pred_sem" in t else (t["pred_inst"] > 0)).astype(np.int64)
+        pred = np.where(t["pred_inst"] > 0, np.maximum(pred, 1), 0)
+        seg["u%d_pred" % j] = pred
+        seg["u%d_sem" % j], seg["u%d_inst" % j] = unet_pp(cfg(1), pred.copy())
+        tc = synth.three_class_map(t["pred_inst"]).astype(np.int64)             # 0 bg, 1 inside, 2 edge
+        edge3 = np.where(tc == 2, 3, pred * (tc == 1)).astype(np.int64)          # classes 1..2 inside, 3 = edge class
+        edge3 = np.minimum(edge3, 3)
+        seg["c%d_pred" % j] = edge3
+        seg["c%d_sem" % j], seg["c%d_inst" % j] = cdnet_pp(cfg(3), edge3.copy())
+        cell, cont = (t["pred_inst"] > 0).astype(np.int64), (tc == 2).astype(np.uint8)
+        seg["d%d_cell" % j], seg["d%d_cont" % j] = cell, cont
+        seg["d%d_sem" % j], seg["d%d_inst" % j] = dcan_pp(cfg(3), cell.copy(), cont)
+        inner = (tc == 1).astype(np.int64)
+        seg["m%d_inner" % j], seg["m%d_tc" % j], seg["m%d_sempred" % j] = inner, tc, pred
+        seg["m%d_unet_sem" % j], seg["m%d_unet_inst" % j] = mt_unet(None, inner.copy(), pred.copy())
+        seg["m%d_cunet_sem" % j], seg["m%d_cunet_inst" % j] = mt_cunet(None, tc.copy(), pred.copy())
+        seg["m%d_cdnet_sem" % j], seg["m%d_cdnet_inst" % j] = mt_cdnet(None, tc.copy(), pred.copy())
+    for j, (H, W, sf) in enumerate([(120, 140, 1), (96, 96, 2), (150, 131, 1)]):
+        t = synth.tile_hover(3, 20 + j, H=H, W=W)
+        seg["h%d_fore" % j], seg["h%d_hv" % j], seg["h%d_sf" % j] = t["fore_map"], t["hv_map"], np.array(sf)
+        seg["h%d_out" % j] = hover(None, t["fore_map"].copy(), t["hv_map"].copy(), fx=1, scale_factor=sf)
+    np.savez_compressed(os.path.join(HERE, "segmentors_ref.npz"), **seg)
     print("golden vectors written to", HERE)
 
 

@@ -654,3 +654,29 @@ def test_postproc_dist_matches_reference_source_golden():
     m = np.load(os.path.join(G, "dist_ref.npz"))
     for j in range(4):
         _diff(ops.postproc_dist(m["d%d_in" % j]), m["d%d_out" % j], "dist inst (reference source golden %d)" % j)
+
+
+def test_segmentor_postprocesses_match_reference_source_golden():
+    """The CUDA post-processes vs the outputs of the reference's own method source text (segmentors_ref.npz: unet.py,
+    cdnet.py, dcan.py, multi_task_*.py, hovernet.py)."""
+    m = np.load(os.path.join(G, "segmentors_ref.npz"))
+    for j in range(3):
+        pred = m["u%d_pred" % j].astype(np.uint8)
+        sem, inst = ops.postproc_unet(pred.copy(), int(pred.max()), 1, None)
+        _diff(sem, m["u%d_sem" % j], "unet sem (golden %d)" % j)
+        _diff(inst, m["u%d_inst" % j], "unet inst (golden %d)" % j)
+        pred = m["c%d_pred" % j].astype(np.uint8)
+        sem, inst = ops.postproc_unet(pred.copy(), 3, 3, 3)
+        _diff(sem, m["c%d_sem" % j], "cdnet sem (golden %d)" % j)
+        _diff(inst, m["c%d_inst" % j], "cdnet inst (golden %d)" % j)
+        sem, inst = ops.postproc_unet(m["d%d_cell" % j].astype(np.uint8), 1, 3, None, kill=m["d%d_cont" % j])
+        _diff(sem, m["d%d_sem" % j], "dcan sem (golden %d)" % j)
+        _diff(inst, m["d%d_inst" % j], "dcan inst (golden %d)" % j)
+        sempred = m["m%d_sempred" % j].astype(np.uint8)
+        for variant, first, edge in (("unet", "inner", None), ("cunet", "tc", 2), ("cdnet", "tc", 2)):
+            canvas, inst = ops.postproc_multitask(m["m%d_%s" % (j, first)].astype(np.uint8), sempred, int(sempred.max()), edge)
+            _diff(inst, m["m%d_%s_inst" % (j, variant)], "multitask inst %s (golden %d)" % (variant, j))
+            if variant != "cdnet":
+                _diff(canvas, m["m%d_%s_sem" % (j, variant)], "multitask canvas %s (golden %d)" % (variant, j))
+        out = ops.postproc_hover(m["h%d_fore" % j], m["h%d_hv" % j], scale_factor=int(m["h%d_sf" % j]))
+        _diff(out, m["h%d_out" % j], "hover inst (golden %d)" % j)

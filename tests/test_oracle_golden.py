@@ -247,3 +247,22 @@ def test_dist_postprocess_matches_reference_source():
         for literal in (True, False):
             got = opp.dist_postprocess(None, m["d%d_in" % j], literal=literal)[1]
             assert np.array_equal(got, want), (j, literal)
+
+
+def test_segmentor_postprocesses_match_reference_source():
+    """oracle restatements == the reference's own method source text (unet.py, cdnet.py, dcan.py, multi_task_*.py,
+    hovernet.py) executed with scipy / OpenCV real and scikit-image served by the port (segmentors_ref.npz)."""
+    m = np.load(os.path.join(G, "segmentors_ref.npz"))
+    for j in range(3):
+        sem, inst = opp.unet_family_postprocess(m["u%d_pred" % j].copy(), radius=1)
+        assert np.array_equal(sem, m["u%d_sem" % j]) and np.array_equal(inst, m["u%d_inst" % j])
+        sem, inst = opp.unet_family_postprocess(m["c%d_pred" % j].copy(), radius=3, edge_id=3)
+        assert np.array_equal(sem, m["c%d_sem" % j]) and np.array_equal(inst, m["c%d_inst" % j])
+        sem, inst = opp.dcan_postprocess(m["d%d_cell" % j].copy(), m["d%d_cont" % j], radius=3)
+        assert np.array_equal(sem, m["d%d_sem" % j]) and np.array_equal(inst, m["d%d_inst" % j])
+        for variant, first in (("unet", "inner"), ("cunet", "tc"), ("cdnet", "tc")):
+            sem, inst = opp.multitask_postprocess(m["m%d_%s" % (j, first)].copy(), m["m%d_sempred" % j].copy(), variant)
+            assert np.array_equal(sem, m["m%d_%s_sem" % (j, variant)]), (j, variant)
+            assert np.array_equal(inst, m["m%d_%s_inst" % (j, variant)]), (j, variant)
+        out = opp.hover_post_proc(m["h%d_fore" % j].copy(), m["h%d_hv" % j].copy(), fx=1, scale_factor=int(m["h%d_sf" % j]))[0]
+        assert np.array_equal(out, m["h%d_out" % j])
