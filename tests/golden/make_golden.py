@@ -94,6 +94,7 @@ def main():
     from tiseg_b200 import synth
 
     misc, inst, sem, isem, pp, ddm = load_reference()
+    inst_mod, sem_mod = inst, sem                       # (the names inst / sem are reused for arrays further down)
     import torch
 
     # ---- instance metrics (binary) on seeded synthetic pairs + hand-made edge cases
@@ -348,6 +349,83 @@ def main():
         seg["h%d_fore" % j], seg["h%d_hv" % j], seg["h%d_sf" % j] = t["fore_map"], t["hv_map"], np.array(sf)
         seg["h%d_out" % j] = hover(None, t["fore_map"].copy(), t["hv_map"].copy(), fx=1, scale_factor=sf)
     np.savez_compressed(os.path.join(HERE, "segmentors_ref.npz"), **seg)
+
+    # ---- CustomDataset.pre_eval / evaluate (custom.py:219-435) from their source text: ground truth written to a
+    # temporary directory in the converted-dataset layout, mmcv.imread served by pillow, the metric functions are the
+    # reference's own modules loaded above
+    import tempfile, warnings as _warnings, os.path as osp
+    from collections import OrderedDict
+    from PIL import Image
+
+    class _Table:
+        def add_column(self, *a, **k):
+            pass
+
+        def get_string(self):
+            return ""
+    dsenv = {"osp": osp, "os": os, "warnings": _warnings, "OrderedDict": OrderedDict, "PrettyTable": _Table,
+             "print_log": lambda *a, **k: None,
+             "mmcv": types.SimpleNamespace(imread=lambda f, flag=None, backend=None: np.array(Image.open(f))),
+             "re_instance": isem.re_instance}
+    for mod in (inst_mod, sem_mod):
+        dsenv.update({k: getattr(mod, k) for k in dir(mod) if k.startswith("pre_eval")})
+    ds_pre_eval = ref_method("tiseg/datasets/custom.py", "CustomDataset", "pre_eval", dsenv)
+    ds_evaluate = ref_method("tiseg/datasets/custom.py", "CustomDataset", "evaluate", dsenv)
+    dsr = {}
+    with tempfile.TemporaryDirectory() as td:
+        infos, preds = [], []
+        for j, (H, W) in enumerate([(96, 110), (128, 128), (70, 61), (64, 64)]):
+            t = synth.gt_and_pred(9400 + j, H, W, n=max(4, H * W // 600))
+            gs = (t["gt_inst"] > 0).astype(np.uint8)
+            gi = t["gt_inst"].astype(np.int32) * 3                     # non-contiguous ids: re_instance has work to do
+            if j == 3:
+                gi[:] = 0; gs[:] = 0                                   # an image without nuclei
+            Image.fromarray(gs).save(osp.join(td, "im%d_sem.png" % j))
+            np.save(osp.join(td, "im%d_inst.npy" % j), gi)
+            infos.append(dict(file_name=osp.join(td, "im%d.tif" % j), sem_file_name=osp.join(td, "im%d_sem.png" % j),
+                              inst_file_name=osp.join(td, "im%d_inst.npy" % j)))
+            sp, ip = (t["pred_inst"] > 0).astype(np.uint8), t["pred_inst"].astype(np.int32) * 2
+            preds.append(dict(sem_pred=sp, inst_pred=ip))
+            dsr["p%d_gt_sem" % j], dsr["p%d_gt_inst" % j], dsr["p%d_sem_pred" % j], dsr["p%d_inst_pred" % j] = gs, gi, sp, ip
+        me = types.SimpleNamespace(data_infos=infos, sem_suffix="_sem.png", CLASSES=("background", "nuclei"))
+        results = ds_pre_eval(me, [dict(p) for p in preds], list(range(4)))
+    for j, r in enumerate(results):
+        dsr["p%d_name" % j] = np.array(r["name"])
+        dsr["p%d_bin_aji" % j] = np.array(r["bin_aji_pre_eval_res"], np.float64)
+        dsr["p%d_bin_pq" % j] = np.array(r["bin_pq_pre_eval_res"], np.float64)
+        dsr["p%d_sem" % j] = np.stack([x.numpy() for x in r["sem_pre_eval_res"]])
+    ev, storage = ds_evaluate(me, results)
+    dsr["eval_keys"] = np.array(list(ev.keys()))
+    dsr["eval_values"] = np.array([float(v) for v in ev.values()], np.float64)
+    # CoNICDataset (conic.py:126-323): per-class AJI / PQ on top of the class assignment
+    dsenv["assign_sem_class_to_insts"] = isem.assign_sem_class_to_insts
+    cn_pre_eval = ref_method("tiseg/datasets/conic.py", "CoNICDataset", "pre_eval", dsenv)
+    cn_evaluate = ref_method("tiseg/datasets/conic.py", "CoNICDataset", "evaluate", dsenv)
+    CN = ("background", "neutrophil", "epithelial", "lymphocyte", "plasma", "eosinophil", "connective")
+    with tempfile.TemporaryDirectory() as td:
+        infos, preds = [], []
+        for j, (H, W) in enumerate([(96, 110), (128, 128), (70, 61)]):
+            t = synth.gt_and_pred(9450 + j, H, W, n=max(6, H * W // 500), num_classes=7)
+            gs, gi = t["gt_sem"].astype(np.uint8), t["gt_inst"].astype(np.int32)
+            Image.fromarray(gs).save(osp.join(td, "c%d_sem.png" % j))
+            np.save(osp.join(td, "c%d_inst.npy" % j), gi)
+            infos.append(dict(sem_file_name=osp.join(td, "c%d_sem.png" % j), inst_file_name=osp.join(td, "c%d_inst.npy" % j)))
+            sp, ip = t["pred_sem"].astype(np.uint8), t["pred_inst"].astype(np.int32)
+            preds.append(dict(sem_pred=sp, inst_pred=ip))
+            dsr["q%d_gt_sem" % j], dsr["q%d_gt_inst" % j], dsr["q%d_sem_pred" % j], dsr["q%d_inst_pred" % j] = gs, gi, sp, ip
+        me = types.SimpleNamespace(data_infos=infos, CLASSES=CN)
+        cres = cn_pre_eval(me, [dict(p) for p in preds], list(range(3)))
+    for j, r in enumerate(cres):
+        dsr["q%d_bin_aji" % j] = np.array(r["bin_aji_pre_eval_res"], np.float64)
+        dsr["q%d_bin_pq" % j] = np.array(r["bin_pq_pre_eval_res"], np.float64)
+        dsr["q%d_aji" % j] = np.stack([np.asarray(x) for x in r["aji_pre_eval_res"]])          # float32, as returned
+        dsr["q%d_pq" % j] = np.stack([np.asarray(x) for x in r["pq_pre_eval_res"]])
+        dsr["q%d_sem" % j] = np.stack([x.numpy() for x in r["sem_pre_eval_res"]])
+    cev, _ = cn_evaluate(me, cres)
+    dsr["conic_eval_keys"] = np.array(list(cev.keys()))
+    dsr["conic_eval_values"] = np.array([float(v) for v in cev.values()], np.float64)
+    dsr["conic_eval_isstr"] = np.array([isinstance(v, str) for v in cev.values()])
+    np.savez_compressed(os.path.join(HERE, "dataset_ref.npz"), **dsr)
     print("golden vectors written to", HERE)
 
 

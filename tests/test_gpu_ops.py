@@ -680,3 +680,43 @@ def test_segmentor_postprocesses_match_reference_source_golden():
                 _diff(canvas, m["m%d_%s_sem" % (j, variant)], "multitask canvas %s (golden %d)" % (variant, j))
         out = ops.postproc_hover(m["h%d_fore" % j], m["h%d_hv" % j], scale_factor=int(m["h%d_sf" % j]))
         _diff(out, m["h%d_out" % j], "hover inst (golden %d)" % j)
+
+
+def test_dataset_pre_eval_matches_reference_source_golden():
+    """CustomDataset.pre_eval (one batched CUDA pass per shape) vs the reference's own pre_eval source text run on the
+    same predictions and ground truth (dataset_ref.npz), then evaluate on top of it."""
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    ds = datasets.CustomDataset(sem_gts=[m["p%d_gt_sem" % j] for j in range(4)], inst_gts=[m["p%d_gt_inst" % j] for j in range(4)],
+                                names=["im%d" % j for j in range(4)])
+    preds = [dict(sem_pred=m["p%d_sem_pred" % j], inst_pred=m["p%d_inst_pred" % j]) for j in range(4)]
+    res = ds.pre_eval(preds, list(range(4)))
+    for j, r in enumerate(res):
+        assert r["name"] == str(m["p%d_name" % j])
+        _diff(np.array(r["bin_aji_pre_eval_res"], np.float64), m["p%d_bin_aji" % j], "pre_eval bin aji %d" % j)
+        _diff(np.array(r["bin_pq_pre_eval_res"], np.float64), m["p%d_bin_pq" % j], "pre_eval bin pq %d" % j)
+        _diff(np.stack([np.asarray(x) for x in r["sem_pre_eval_res"]]), m["p%d_sem" % j], "pre_eval sem %d" % j)
+    ev, _ = ds.evaluate(res, logger="silent")
+    assert list(ev.keys()) == m["eval_keys"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["eval_values"], rtol=0, atol=1e-9)
+
+
+def test_conic_dataset_pre_eval_matches_reference_source_golden():
+    """CoNICDataset.pre_eval vs conic.py:126-198 executed from source on the same inputs (dataset_ref.npz), values and
+    dtypes; then evaluate on top of it: all 67 entries."""
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    ds = datasets.CoNICDataset(sem_gts=[m["q%d_gt_sem" % j] for j in range(3)], inst_gts=[m["q%d_gt_inst" % j] for j in range(3)])
+    preds = [dict(sem_pred=m["q%d_sem_pred" % j], inst_pred=m["q%d_inst_pred" % j]) for j in range(3)]
+    res = ds.pre_eval(preds, list(range(3)))
+    for j, r in enumerate(res):
+        _diff(np.array(r["bin_aji_pre_eval_res"], np.float64), m["q%d_bin_aji" % j], "conic bin aji %d" % j)
+        _diff(np.array(r["bin_pq_pre_eval_res"], np.float64), m["q%d_bin_pq" % j], "conic bin pq %d" % j)
+        for key in ("aji", "pq"):
+            got = np.stack([np.asarray(x) for x in r[key + "_pre_eval_res"]])
+            assert got.dtype == m["q%d_%s" % (j, key)].dtype, (key, got.dtype)
+            _diff(got, m["q%d_%s" % (j, key)], "conic %s %d" % (key, j))
+        _diff(np.stack([np.asarray(x) for x in r["sem_pre_eval_res"]]), m["q%d_sem" % j], "conic sem %d" % j)
+    ev, _ = ds.evaluate(res, logger="silent")
+    assert list(ev.keys()) == m["conic_eval_keys"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["conic_eval_values"], rtol=0, atol=1e-9)

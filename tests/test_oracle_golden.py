@@ -266,3 +266,34 @@ def test_segmentor_postprocesses_match_reference_source():
             assert np.array_equal(inst, m["m%d_%s_inst" % (j, variant)]), (j, variant)
         out = opp.hover_post_proc(m["h%d_fore" % j].copy(), m["h%d_hv" % j].copy(), fx=1, scale_factor=int(m["h%d_sf" % j]))[0]
         assert np.array_equal(out, m["h%d_out" % j])
+
+
+def test_dataset_evaluate_matches_reference_source():
+    """tiseg_b200.datasets.CustomDataset.evaluate (host arithmetic) on the per-image results the reference's own
+    pre_eval produced == the reference's own evaluate (custom.py:307-435 executed from source, dataset_ref.npz)."""
+    import torch
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    results = [dict(name=str(m["p%d_name" % j]), bin_aji_pre_eval_res=tuple(m["p%d_bin_aji" % j]),
+                    bin_pq_pre_eval_res=tuple(m["p%d_bin_pq" % j]),
+                    sem_pre_eval_res=tuple(torch.from_numpy(x) for x in m["p%d_sem" % j])) for j in range(4)]
+    ds = datasets.CustomDataset(sem_gts=[None] * 4, inst_gts=[None] * 4, names=["im%d" % j for j in range(4)])
+    ev, _ = ds.evaluate(results, logger="silent")
+    assert list(ev.keys()) == m["eval_keys"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["eval_values"], rtol=0, atol=1e-9)
+
+
+def test_conic_dataset_evaluate_matches_reference_source():
+    """CoNICDataset.evaluate on the reference's own per-image results == conic.py:200-323 executed from source (all 67
+    entries, including the per-class strings)."""
+    import torch
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    results = [dict(bin_aji_pre_eval_res=tuple(m["q%d_bin_aji" % j]), aji_pre_eval_res=tuple(m["q%d_aji" % j]),
+                    bin_pq_pre_eval_res=tuple(m["q%d_bin_pq" % j]), pq_pre_eval_res=tuple(m["q%d_pq" % j]),
+                    sem_pre_eval_res=tuple(torch.from_numpy(x) for x in m["q%d_sem" % j])) for j in range(3)]
+    ds = datasets.CoNICDataset(sem_gts=[None] * 3, inst_gts=[None] * 3)
+    ev, _ = ds.evaluate(results, logger="silent")
+    assert list(ev.keys()) == m["conic_eval_keys"].tolist()
+    assert [isinstance(v, str) for v in ev.values()] == m["conic_eval_isstr"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["conic_eval_values"], rtol=0, atol=1e-9)

@@ -189,7 +189,10 @@ class CustomDataset:
             v = np.asarray(img[key])
             if v.ndim == 2:
                 v = v[:, 0]
-            img[key] = np.append(v, np.nanmean(v))
+            # custom.py:367-370: the list round trip turns the float32 semantic columns into float64
+            lst = v.tolist()
+            lst.append(np.nanmean(v))
+            img[key] = np.array(lst)
 
         vital = ['Dice', 'Precision', 'Recall', 'Aji', 'DQ', 'SQ', 'PQ', 'InstDice']
         mean_metrics = OrderedDict(('imw' + k, img[k][-1]) for k in vital)
