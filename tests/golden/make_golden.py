@@ -426,6 +426,61 @@ def main():
     dsr["conic_eval_values"] = np.array([float(v) for v in cev.values()], np.float64)
     dsr["conic_eval_isstr"] = np.array([isinstance(v, str) for v in cev.values()])
     np.savez_compressed(os.path.join(HERE, "dataset_ref.npz"), **dsr)
+
+    # ---- BaseSegmentor.inference (base.py:255-381): window canvas + TTA + reverse + softmax + mean, from source.
+    # `self.calculate` is a recorder that returns seeded logits for every window it is asked for; the recorded windows
+    # are what the fused kernel (tiseg_softmax_argmax_tta) is given.
+    import torch.nn.functional as F
+    benv = {"torch": torch, "F": F, "resize": None}
+    b_inference = ref_method("tiseg/models/segmentors/base.py", "BaseSegmentor", "inference", benv)
+    b_split = ref_method("tiseg/models/segmentors/base.py", "BaseSegmentor", "split_inference", benv)
+    b_whole = ref_method("tiseg/models/segmentors/base.py", "BaseSegmentor", "whole_inference", benv)
+
+    def _plain(meth):                                  # the two transforms are @classmethod in the reference
+        src = open(os.path.join(REF, "tiseg/models/segmentors/base.py")).read()
+        tr = ast.parse(src)
+        c = [n for n in tr.body if isinstance(n, ast.ClassDef) and n.name == "BaseSegmentor"][0]
+        f = [n for n in c.body if isinstance(n, ast.FunctionDef) and n.name == meth][0]
+        f.decorator_list = []
+        env = dict(benv)
+        exec(compile(ast.Module(body=[f], type_ignores=[]), "base.py", "exec"), env)
+        return env[meth]
+    b_tta, b_rev = _plain("tta_transform"), _plain("reverse_tta_transform")
+
+    class _Cfg(dict):
+        __getattr__ = dict.__getitem__
+    tta = {}
+    for j, (H, W, window, overlap, C, B, rots, flips) in enumerate([
+            (70, 90, 32, 8, 2, 1, [0, 90], ["none", "horizontal", "vertical", "diagonal"]),     # the shipped TTA set
+            (48, 56, 24, 8, 3, 2, [90, 180], ["horizontal", "vertical"]),
+            (50, 37, 0, 0, 3, 1, [0, 270], ["none", "diagonal"])]):
+        rng = np.random.default_rng(9600 + j)
+        calls = []
+
+        def calculate(patch):
+            out = torch.from_numpy((rng.integers(-12, 13, (patch.shape[0], C, patch.shape[2], patch.shape[3])) / 4.0)
+                                   .astype(np.float32))
+            calls.append(out.numpy())
+            return out
+        me = types.SimpleNamespace(num_classes=C, calculate=calculate)
+        me.test_cfg = _Cfg(mode="split" if window else "whole", crop_size=(window, window), overlap_size=(overlap, overlap),
+                           rotate_degrees=rots, flip_directions=flips)
+        me.tta_transform = lambda img, r, f: b_tta(me, img, r, f)
+        me.reverse_tta_transform = lambda img, r, f: b_rev(me, img, r, f)
+        me.split_inference = lambda img, meta, rescale: b_split(me, img, meta, rescale)
+        me.whole_inference = lambda img, meta, rescale: b_whole(me, img, meta, rescale)
+        prob = b_inference(me, torch.zeros(B, 3, H, W), None, False).numpy()
+        # the recorder saw the windows variant by variant (rotation outer, flip inner), row-major inside a variant
+        per = len(calls) // (len(rots) * len(flips))
+        for t in range(len(rots) * len(flips)):
+            w = np.stack(calls[t * per:(t + 1) * per])                   # [M, B, C, h, w]
+            w = np.ascontiguousarray(np.moveaxis(w, 1, 0)) if window else w[0]
+            tta["t%d_v%d" % (j, t)] = np.round(w * 4).astype(np.int8)    # the logits are quarter-integers: stored x4 as int8
+        tta["t%d_meta" % j] = np.array([H, W, window, overlap, C, B, len(rots) * len(flips)])
+        tta["t%d_rots" % j] = np.array([r for r in rots for _ in flips])
+        tta["t%d_flips" % j] = np.array([f for _ in rots for f in flips])
+        tta["t%d_prob" % j] = prob
+    np.savez_compressed(os.path.join(HERE, "tta_ref.npz"), **tta)
     print("golden vectors written to", HERE)
 
 

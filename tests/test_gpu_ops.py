@@ -720,3 +720,19 @@ def test_conic_dataset_pre_eval_matches_reference_source_golden():
     ev, _ = ds.evaluate(res, logger="silent")
     assert list(ev.keys()) == m["conic_eval_keys"].tolist()
     np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["conic_eval_values"], rtol=0, atol=1e-9)
+
+
+def test_softmax_argmax_tta_matches_reference_source_golden():
+    """The fused stitch + TTA reverse + softmax + mean kernel vs BaseSegmentor.inference executed from source on the same
+    recorded window logits (tta_ref.npz)."""
+    from test_oracle_golden import _tta_case
+    m = np.load(os.path.join(G, "tta_ref.npz"))
+    for j in range(3):
+        H, W, window, overlap, B, variants, rots, flips = _tta_case(m, j)
+        cls, prob = ops.softmax_argmax_tta(variants, rots, flips, (H, W), window, overlap, want_prob=True)
+        want = m["t%d_prob" % j]
+        assert prob.shape == want.shape
+        np.testing.assert_allclose(prob, want, rtol=1e-5, atol=1e-7)
+        top2 = np.sort(want, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert np.array_equal(cls[clear], want.argmax(1).astype(np.uint8)[clear])

@@ -297,3 +297,24 @@ def test_conic_dataset_evaluate_matches_reference_source():
     assert list(ev.keys()) == m["conic_eval_keys"].tolist()
     assert [isinstance(v, str) for v in ev.values()] == m["conic_eval_isstr"].tolist()
     np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["conic_eval_values"], rtol=0, atol=1e-9)
+
+
+def _tta_case(m, j):
+    H, W, window, overlap, C, B, T = (int(v) for v in m["t%d_meta" % j])
+    variants = [m["t%d_v%d" % (j, t)].astype(np.float32) / 4.0 for t in range(T)]
+    return H, W, window, overlap, B, variants, [int(r) for r in m["t%d_rots" % j]], [str(f) for f in m["t%d_flips" % j]]
+
+
+def test_tta_stitch_softmax_matches_reference_source():
+    """oracle split_stitch + reverse_tta_transform + softmax_tta_mean == BaseSegmentor.inference (base.py:255-381)
+    executed from source on recorded window logits (tta_ref.npz); fp32 softmax: 1e-6."""
+    m = np.load(os.path.join(G, "tta_ref.npz"))
+    for j in range(3):
+        H, W, window, overlap, B, variants, rots, flips = _tta_case(m, j)
+        for n in range(B):
+            rev = []
+            for v, r, f in zip(variants, rots, flips):
+                Ht, Wt = (W, H) if (r // 90) % 2 else (H, W)
+                full = opp.split_stitch(v[n], Ht, Wt, window, overlap) if window else v[n]
+                rev.append(opp.reverse_tta_transform(full, r, f))
+            np.testing.assert_allclose(opp.softmax_tta_mean(rev), m["t%d_prob" % j][n], rtol=1e-6, atol=1e-7)
