@@ -480,6 +480,36 @@ def main():
         tta["t%d_rots" % j] = np.array([r for r in rots for _ in flips])
         tta["t%d_flips" % j] = np.array([f for _ in rots for f in flips])
         tta["t%d_prob" % j] = prob
+    # CDNet.inference (cdnet.py:154-217) + _ddm_enhencement (:354-367) from source, whole-image mode, recorder network
+    cenv = dict(benv)
+    cenv["generate_direction_differential_map"] = ddm.generate_direction_differential_map
+    c_inference = ref_method("tiseg/models/segmentors/cdnet.py", "CDNet", "inference", cenv)
+    csrc = open(os.path.join(REF, "tiseg/models/segmentors/cdnet.py")).read()
+    cnode = [n for n in ast.parse(csrc).body if isinstance(n, ast.ClassDef) and n.name == "CDNet"][0]
+    enh = [n for n in cnode.body if isinstance(n, ast.FunctionDef) and n.name == "_ddm_enhencement"][0]
+    enh.decorator_list = []
+    exec(compile(ast.Module(body=[enh], type_ignores=[]), "cdnet.py", "exec"), cenv)
+    for j, (H, W, flips, if_ddm) in enumerate([(40, 44, ["none", "horizontal", "vertical"], True), (36, 36, ["none"], False)]):
+        rng = np.random.default_rng(9700 + j)
+        rec = []
+
+        def whole(img, meta, rescale):
+            outs = [torch.from_numpy((rng.standard_normal((1, c, img.shape[2], img.shape[3])) * 2).astype(np.float16)
+                                     .astype(np.float32)) for c in (3, 9, 1)]
+            outs[2] = outs[2].abs()
+            rec.append([o.numpy()[0].astype(np.float16) for o in outs])
+            return tuple(outs)
+        me = types.SimpleNamespace(num_classes=3, num_angles=8, whole_inference=whole)
+        me.test_cfg = _Cfg(mode="whole", rotate_degrees=[0], flip_directions=flips, if_ddm=if_ddm)
+        me.tta_transform = lambda img, r, f: b_tta(me, img, r, f)
+        me.reverse_tta_transform = lambda img, r, f: b_rev(me, img, r, f)
+        me._ddm_enhencement = lambda a, b, c: cenv["_ddm_enhencement"](me, a, b, c)
+        sem_out, dir_out = c_inference(me, torch.zeros(1, 3, H, W), None, False)
+        tta["c%d_flips" % j] = np.array(flips)
+        tta["c%d_if_ddm" % j] = np.array(if_ddm)
+        for t, (a, b, c) in enumerate(rec):
+            tta["c%d_sem%d" % (j, t)], tta["c%d_dir%d" % (j, t)], tta["c%d_pt%d" % (j, t)] = a, b, c
+        tta["c%d_sem_out" % j], tta["c%d_dir_out" % j] = sem_out.numpy()[0], dir_out.numpy()[0]
     np.savez_compressed(os.path.join(HERE, "tta_ref.npz"), **tta)
     print("golden vectors written to", HERE)
 

@@ -736,3 +736,13 @@ def test_softmax_argmax_tta_matches_reference_source_golden():
         top2 = np.sort(want, axis=1)[:, -2:]
         clear = (top2[:, 1] - top2[:, 0]) > 1e-6
         assert np.array_equal(cls[clear], want.argmax(1).astype(np.uint8)[clear])
+
+
+def test_cdnet_refine_matches_reference_source_golden():
+    from test_oracle_golden import _cdnet_case
+    m = np.load(os.path.join(G, "tta_ref.npz"))
+    for j in range(2):
+        sem, dirs, pts, if_ddm = _cdnet_case(m, j)
+        r = ops.cdnet_refine(np.stack(sem), np.stack(dirs), np.stack(pts), if_ddm=if_ddm)
+        _diff(r["dir_map"], m["c%d_dir_out" % j], "cdnet dir map (reference source golden %d)" % j)
+        np.testing.assert_allclose(r["sem_prob"], m["c%d_sem_out" % j], rtol=1e-5, atol=1e-7)

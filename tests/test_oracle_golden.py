@@ -318,3 +318,23 @@ def test_tta_stitch_softmax_matches_reference_source():
                 full = opp.split_stitch(v[n], Ht, Wt, window, overlap) if window else v[n]
                 rev.append(opp.reverse_tta_transform(full, r, f))
             np.testing.assert_allclose(opp.softmax_tta_mean(rev), m["t%d_prob" % j][n], rtol=1e-6, atol=1e-7)
+
+
+def _cdnet_case(m, j):
+    flips = [str(f) for f in m["c%d_flips" % j]]
+    sem, dirs, pts = [], [], []
+    for t, f in enumerate(flips):                      # the recorder saw the logits of the TRANSFORMED image
+        sem.append(opp.reverse_tta_transform(m["c%d_sem%d" % (j, t)].astype(np.float32), 0, f))
+        dirs.append(opp.reverse_tta_transform(m["c%d_dir%d" % (j, t)].astype(np.float32), 0, f))
+        pts.append(opp.reverse_tta_transform(m["c%d_pt%d" % (j, t)].astype(np.float32), 0, f))
+    return sem, dirs, pts, bool(m["c%d_if_ddm" % j])
+
+
+def test_cdnet_inference_tail_matches_reference_source():
+    """oracle cdnet_inference_tail == CDNet.inference + _ddm_enhencement executed from source (tta_ref.npz)."""
+    m = np.load(os.path.join(G, "tta_ref.npz"))
+    for j in range(2):
+        sem, dirs, pts, if_ddm = _cdnet_case(m, j)
+        got_sem, got_dir, _ = opp.cdnet_inference_tail(sem, dirs, pts, if_ddm=if_ddm)
+        assert np.array_equal(got_dir, m["c%d_dir_out" % j])
+        np.testing.assert_allclose(got_sem, m["c%d_sem_out" % j], rtol=1e-5, atol=1e-7)
