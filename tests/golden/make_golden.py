@@ -425,6 +425,34 @@ def main():
     dsr["conic_eval_keys"] = np.array(list(cev.keys()))
     dsr["conic_eval_values"] = np.array([float(v) for v in cev.values()], np.float64)
     dsr["conic_eval_isstr"] = np.array([isinstance(v, str) for v in cev.values()])
+    # MoNuSegDatasetDebug (monuseg_debug.py:34-...): the extra boundary-class semantic metrics
+    md_pre_eval = ref_method("tiseg/datasets/monuseg_debug.py", "MoNuSegDatasetDebug", "pre_eval", dsenv)
+    md_evaluate = ref_method("tiseg/datasets/monuseg_debug.py", "MoNuSegDatasetDebug", "evaluate", dsenv)
+    with tempfile.TemporaryDirectory() as td:
+        infos, preds = [], []
+        for j, (H, W) in enumerate([(96, 110), (80, 64)]):
+            t = synth.gt_and_pred(9480 + j, H, W, n=max(4, H * W // 600))
+            gs, gi = (t["gt_inst"] > 0).astype(np.uint8), t["gt_inst"].astype(np.int32)
+            Image.fromarray(gs).save(osp.join(td, "m%d_sem.png" % j))
+            np.save(osp.join(td, "m%d_inst.npy" % j), gi)
+            infos.append(dict(file_name=osp.join(td, "m%d.tif" % j), sem_file_name=osp.join(td, "m%d_sem.png" % j),
+                              inst_file_name=osp.join(td, "m%d_inst.npy" % j)))
+            sp, ip = (t["pred_inst"] > 0).astype(np.uint8), t["pred_inst"].astype(np.int32)
+            tcp, tcg = synth.three_class_map(t["pred_inst"]).astype(np.uint8), synth.three_class_map(t["gt_inst"]).astype(np.uint8)
+            preds.append(dict(sem_pred=sp, inst_pred=ip, tc_pred=tcp, tc_gt=tcg))
+            for key, val in (("gt_sem", gs), ("gt_inst", gi), ("sem_pred", sp), ("inst_pred", ip), ("tc_pred", tcp), ("tc_gt", tcg)):
+                dsr["d%d_%s" % (j, key)] = val
+        me = types.SimpleNamespace(data_infos=infos, sem_suffix="_sem.png", CLASSES=("background", "nuclei"))
+        mres = md_pre_eval(me, [dict(p) for p in preds], list(range(2)))
+    for j, r in enumerate(mres):
+        dsr["d%d_name" % j] = np.array(r["name"])
+        dsr["d%d_bin_aji" % j] = np.array(r["bin_aji_pre_eval_res"], np.float64)
+        dsr["d%d_bin_pq" % j] = np.array(r["bin_pq_pre_eval_res"], np.float64)
+        dsr["d%d_sem" % j] = np.stack([x.numpy() for x in r["sem_pre_eval_res"]])
+        dsr["d%d_bound" % j] = np.stack([x.numpy() for x in r["bound_sem_pre_eval_res"]])
+    mev, _ = md_evaluate(me, mres)
+    dsr["monuseg_eval_keys"] = np.array(list(mev.keys()))
+    dsr["monuseg_eval_values"] = np.array([float(v) for v in mev.values()], np.float64)
     np.savez_compressed(os.path.join(HERE, "dataset_ref.npz"), **dsr)
 
     # ---- BaseSegmentor.inference (base.py:255-381): window canvas + TTA + reverse + softmax + mean, from source.

@@ -746,3 +746,21 @@ def test_cdnet_refine_matches_reference_source_golden():
         r = ops.cdnet_refine(np.stack(sem), np.stack(dirs), np.stack(pts), if_ddm=if_ddm)
         _diff(r["dir_map"], m["c%d_dir_out" % j], "cdnet dir map (reference source golden %d)" % j)
         np.testing.assert_allclose(r["sem_prob"], m["c%d_sem_out" % j], rtol=1e-5, atol=1e-7)
+
+
+def test_monuseg_debug_pre_eval_matches_reference_source_golden():
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    ds = datasets.MoNuSegDatasetDebug(sem_gts=[m["d%d_gt_sem" % j] for j in range(2)], inst_gts=[m["d%d_gt_inst" % j] for j in range(2)],
+                                      names=["m0", "m1"])
+    preds = [dict(sem_pred=m["d%d_sem_pred" % j], inst_pred=m["d%d_inst_pred" % j], tc_pred=m["d%d_tc_pred" % j],
+                  tc_gt=m["d%d_tc_gt" % j]) for j in range(2)]
+    res = ds.pre_eval(preds, [0, 1])
+    for j, r in enumerate(res):
+        _diff(np.array(r["bin_aji_pre_eval_res"], np.float64), m["d%d_bin_aji" % j], "monuseg bin aji %d" % j)
+        _diff(np.array(r["bin_pq_pre_eval_res"], np.float64), m["d%d_bin_pq" % j], "monuseg bin pq %d" % j)
+        _diff(np.stack([np.asarray(x) for x in r["sem_pre_eval_res"]]), m["d%d_sem" % j], "monuseg sem %d" % j)
+        _diff(np.stack([np.asarray(x) for x in r["bound_sem_pre_eval_res"]]), m["d%d_bound" % j], "monuseg bound %d" % j)
+    ev, _ = ds.evaluate(res, logger="silent")
+    assert list(ev.keys()) == m["monuseg_eval_keys"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["monuseg_eval_values"], rtol=0, atol=1e-9)

@@ -338,3 +338,19 @@ def test_cdnet_inference_tail_matches_reference_source():
         got_sem, got_dir, _ = opp.cdnet_inference_tail(sem, dirs, pts, if_ddm=if_ddm)
         assert np.array_equal(got_dir, m["c%d_dir_out" % j])
         np.testing.assert_allclose(got_sem, m["c%d_sem_out" % j], rtol=1e-5, atol=1e-7)
+
+
+def test_monuseg_debug_evaluate_matches_reference_source():
+    """MoNuSegDatasetDebug.evaluate (boundary-class metrics on top of CustomDataset's) on the reference's own per-image
+    results == monuseg_debug.py executed from source."""
+    import torch
+    from tiseg_b200 import datasets
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    results = [dict(name=str(m["d%d_name" % j]), bin_aji_pre_eval_res=tuple(m["d%d_bin_aji" % j]),
+                    bin_pq_pre_eval_res=tuple(m["d%d_bin_pq" % j]),
+                    bound_sem_pre_eval_res=tuple(torch.from_numpy(x) for x in m["d%d_bound" % j]),
+                    sem_pre_eval_res=tuple(torch.from_numpy(x) for x in m["d%d_sem" % j])) for j in range(2)]
+    ds = datasets.MoNuSegDatasetDebug(sem_gts=[None] * 2, inst_gts=[None] * 2, names=["m0", "m1"])
+    ev, _ = ds.evaluate(results, logger="silent")
+    assert list(ev.keys()) == m["monuseg_eval_keys"].tolist()
+    np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["monuseg_eval_values"], rtol=0, atol=1e-9)
