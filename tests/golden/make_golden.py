@@ -8,8 +8,18 @@ Imports, by file path, the parts of /root/reference that load in this image:
   tiseg/datasets/utils/instance_semantic.py              (stub ``skimage.morphology``)
   tiseg/models/utils/postprocess.py                      (numba align_foreground)
   tiseg/models/utils/direct_diff_map.py                  (torch, CPU)
-and stores seeded inputs together with the reference outputs.  /root/reference does not exist
-on the GPU box, so the tests only read the committed .npz files.
+  tiseg/datasets/ops/{hv_map,distance_map,bound_map,unet_map}.py   (label makers; skimage morphology served by scipy)
+and stores seeded inputs together with the reference outputs.  Code that cannot be imported (it lives in modules that
+pull in mmcv / the model zoo) is executed FROM ITS SOURCE TEXT instead: the function or method is cut out of the
+reference file with ``ast`` and run in a namespace where scipy / OpenCV / torch are the real libraries, scikit-image
+calls are served by the oracle's port (``oracle/skimage_port``: this pins control flow, not scikit-image) and ``self``
+is a small namespace carrying the attributes the method reads:
+  tiseg/models/segmentors/dist.py        helpers :31-131 + DIST.postprocess                      -> dist_ref.npz
+  tiseg/models/segmentors/{unet,cdnet,dcan,multi_task_*,hovernet}.py   .postprocess / .hover_post_proc -> segmentors_ref.npz
+  tiseg/models/segmentors/base.py        BaseSegmentor.inference (+ split/whole, TTA transforms)  -> tta_ref.npz
+  tiseg/models/segmentors/cdnet.py       CDNet.inference tail + _ddm_enhencement                  -> tta_ref.npz
+  tiseg/datasets/{custom,monuseg_debug,conic}.py   pre_eval + evaluate (GT files in a temp dir)   -> dataset_ref.npz
+/root/reference does not exist on the GPU box, so the tests only read the committed .npz files.
 
     python tests/golden/make_golden.py
 """
