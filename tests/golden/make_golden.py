@@ -463,6 +463,19 @@ def main():
     mev, _ = md_evaluate(me, mres)
     dsr["monuseg_eval_keys"] = np.array(list(mev.keys()))
     dsr["monuseg_eval_values"] = np.array([float(v) for v in mev.values()], np.float64)
+    # the convenience scores of tiseg/utils/__init__.py that run in the reference (binary_aggregated_jaccard_index,
+    # aggregated_jaccard_index and panoptic_quality raise there: they hand semantic maps to pre_eval_aji / pre_eval_pq,
+    # which expect id lists — inst_metrics.py:292, 307, 353)
+    for j, (H, W) in enumerate([(96, 110), (64, 80)]):
+        t = synth.gt_and_pred(9490 + j, H, W, n=max(4, H * W // 600), num_classes=4)
+        ipd, igt = isem.re_instance(t["pred_inst"]), isem.re_instance(t["gt_inst"])
+        sp, sg = t["pred_sem"].astype(np.uint8), t["gt_sem"].astype(np.uint8)
+        dsr["s%d_inst_pred" % j], dsr["s%d_inst_gt" % j], dsr["s%d_sem_pred" % j], dsr["s%d_sem_gt" % j] = ipd, igt, sp, sg
+        dsr["s%d_bin_pq" % j] = np.array(inst_mod.binary_panoptic_quality(ipd, igt), np.float64)
+        dsr["s%d_inst_dice" % j] = np.float64(inst_mod.binary_inst_dice(ipd, igt))
+        dsr["s%d_dice" % j] = sem_mod.dice_similarity_coefficient(sp, sg, 4)
+        pr = sem_mod.precision_recall(sp, sg, 4)
+        dsr["s%d_precision" % j], dsr["s%d_recall" % j] = pr[0], pr[1]
     np.savez_compressed(os.path.join(HERE, "dataset_ref.npz"), **dsr)
 
     # ---- BaseSegmentor.inference (base.py:255-381): window canvas + TTA + reverse + softmax + mean, from source.

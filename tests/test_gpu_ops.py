@@ -764,3 +764,20 @@ def test_monuseg_debug_pre_eval_matches_reference_source_golden():
     ev, _ = ds.evaluate(res, logger="silent")
     assert list(ev.keys()) == m["monuseg_eval_keys"].tolist()
     np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["monuseg_eval_values"], rtol=0, atol=1e-9)
+
+
+def test_convenience_scores_match_reference():
+    """binary_panoptic_quality / binary_inst_dice / dice_similarity_coefficient / precision_recall (the convenience
+    scores of tiseg/utils that run in the reference) vs the reference's own functions (dataset_ref.npz)."""
+    from tiseg_b200 import metrics as M
+    m = np.load(os.path.join(G, "dataset_ref.npz"))
+    for j in range(2):
+        ip, ig, sp, sg = (m["s%d_%s" % (j, k)] for k in ("inst_pred", "inst_gt", "sem_pred", "sem_gt"))
+        np.testing.assert_allclose(np.array(M.binary_panoptic_quality(ip, ig), np.float64), m["s%d_bin_pq" % j], rtol=1e-12)
+        np.testing.assert_allclose(float(M.binary_inst_dice(ip, ig)), float(m["s%d_inst_dice" % j]), rtol=1e-12)
+        d = np.asarray(M.dice_similarity_coefficient(sp, sg, 4))
+        assert d.dtype == m["s%d_dice" % j].dtype
+        _diff(d, m["s%d_dice" % j], "dice_similarity_coefficient %d" % j)
+        p, r = M.precision_recall(sp, sg, 4)
+        _diff(np.asarray(p), m["s%d_precision" % j], "precision %d" % j)
+        _diff(np.asarray(r), m["s%d_recall" % j], "recall %d" % j)

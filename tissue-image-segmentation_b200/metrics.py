@@ -84,6 +84,10 @@ def pre_eval_all_semantic_metric(pred_label, target_label, num_classes, ignore_i
 
 
 # --------------------------------------------------------------------------- convenience scores
+# (binary_panoptic_quality, binary_inst_dice, dice_similarity_coefficient and precision_recall are compared with the
+# reference's own functions; binary_aggregated_jaccard_index, aggregated_jaccard_index and panoptic_quality RAISE in
+# the reference — inst_metrics.py:292, 307, 353 hand semantic maps to functions that expect per-class id lists — so
+# these three follow the formulas of the corresponding reducers instead.)
 def binary_aggregated_jaccard_index(inst_pred, inst_gt):
     i, u = pre_eval_bin_aji(inst_pred, inst_gt)
     return 0. if i == 0. or u == 0. else i / u
