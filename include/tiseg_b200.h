@@ -47,6 +47,9 @@ const char* tiseg_last_error(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long long tiseg_launch_count(tiseg_ctx* ctx);
 int tiseg_version(void);
+/* hash of the source tree (csrc/, this header, compiler flags) the library was built from; the Python loader compares it
+ * with the sources next to it and refuses a stale binary */
+const char* tiseg_build_hash(void);
 /* optional per-kernel CUDA-event timing (bench.py's roofline leg): enable, run, then read one
  * "kernel_name launches total_ms" line per kernel (aggregated and reset). */
 int tiseg_timing_enable(tiseg_ctx* ctx, int on);

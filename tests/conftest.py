@@ -14,6 +14,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked ``gpu`` are skipped (not failed) on a box without a CUDA device or without the built library."""
+    reason = None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            reason = "no CUDA device"
+    except Exception as e:                      # pragma: no cover
+        reason = "torch unavailable: %s" % e
+    so = os.path.join(ROOT, "tissue-image-segmentation_b200", "libtiseg_b200.so")
+    if reason is None and not os.path.exists(so):
+        reason = "libtiseg_b200.so is not built"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -23,6 +23,7 @@ SIGNATURES = {
     "tiseg_last_error": [],
     "tiseg_launch_count": [_vp],
     "tiseg_version": [],
+    "tiseg_build_hash": [],
     "tiseg_timing_enable": [_vp, _i],
     "tiseg_timing_report": [_vp, ctypes.c_char_p, _i],
     "tiseg_softmax_argmax": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
@@ -60,7 +61,7 @@ SIGNATURES = {
     "tiseg_distance_transform_edt": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_distance_transform_cdt": [_vp, _vp, _i, _i, _i, _vp],
 }
-_RESTYPE = {"tiseg_last_error": ctypes.c_char_p, "tiseg_launch_count": _ll, "tiseg_tta_input_elems": _ll}
+_RESTYPE = {"tiseg_last_error": ctypes.c_char_p, "tiseg_build_hash": ctypes.c_char_p, "tiseg_launch_count": _ll, "tiseg_tta_input_elems": _ll}
 
 _lib = None
 _lock = threading.Lock()
@@ -69,6 +70,20 @@ _ctxs = {}
 
 class TisegError(RuntimeError):
     pass
+
+
+def _check_fresh(lib):
+    """The .so is git-ignored but travels with repo snapshots: refuse one that was not built from the sources beside it."""
+    if not os.path.isdir(os.path.join(_HERE, "csrc")) or os.environ.get("TISEG_ALLOW_STALE"):
+        return
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_tiseg_build", os.path.join(_HERE, "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    have, want = (lib.tiseg_build_hash() or b"").decode(), b.source_hash()
+    if have != want:
+        raise TisegError("libtiseg_b200.so is stale (built from %s, sources are %s): run "
+                         "`python tissue-image-segmentation_b200/build.py`" % (have, want))
 
 
 def load():
@@ -85,6 +100,7 @@ def load():
                 fn = getattr(lib, name)           # AttributeError if a declared symbol is missing
                 fn.argtypes = argtypes
                 fn.restype = _RESTYPE.get(name, _i)
+            _check_fresh(lib)
             _lib = lib
     return _lib
 

@@ -19,6 +19,7 @@ struct tiseg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaEvent_t order_ev = nullptr;   // orders a newly bound stream after the work queued on the previous one
     // device arena: list of blocks, bump-allocated per call, coalesced between calls
     struct Block { char* p; size_t cap; };
     std::vector<Block> blocks;

@@ -184,6 +184,7 @@ int tiseg_destroy(tiseg_ctx* c) {
     for (auto& b : c->blocks) cudaFree(b.p);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->order_ev) cudaEventDestroy(c->order_ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return TISEG_OK;
@@ -192,12 +193,29 @@ int tiseg_destroy(tiseg_ctx* c) {
 int tiseg_set_stream(tiseg_ctx* c, void* s) {
     if (!c) { tiseg::set_error("null ctx"); return TISEG_ERR_ARG; }
     cudaSetDevice(c->device);
+    cudaStream_t ns = (cudaStream_t)s;   // NULL == the legacy default stream (what torch uses by default)
     if (c->own_stream) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
         c->own_stream = false;
+    } else if (ns != c->stream) {
+        // Work queued on the previous stream may still be using the arena that the next call on the new stream resets
+        // and overwrites: order the new stream after it (event, no host wait).  A stream under graph capture cannot
+        // wait on an event from outside the capture; callers that capture keep one context per stream (_lib.lane).
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ns, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+        if (cs == cudaStreamCaptureStatusNone) {
+            if (!c->order_ev && cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                c->order_ev = nullptr;
+            }
+            if (c->order_ev) {
+                if (cudaEventRecord(c->order_ev, c->stream) == cudaSuccess) cudaStreamWaitEvent(ns, c->order_ev, 0);
+                else { cudaGetLastError(); cudaStreamSynchronize(c->stream); cudaGetLastError(); }
+            }
+        }
     }
-    c->stream = (cudaStream_t)s;   // NULL == the legacy default stream (what torch uses by default)
+    c->stream = ns;
     return TISEG_OK;
 }
 
@@ -242,6 +260,11 @@ const char* tiseg_last_error(void) { return tiseg::g_err.c_str(); }
 
 long long tiseg_launch_count(tiseg_ctx* c) { return c ? c->launches : 0; }
 
-int tiseg_version(void) { return 100; }
+int tiseg_version(void) { return 200; }
+
+#ifndef TISEG_SRC_HASH
+#define TISEG_SRC_HASH "unknown"
+#endif
+const char* tiseg_build_hash(void) { return TISEG_SRC_HASH; }
 
 }  // extern "C"

@@ -61,9 +61,14 @@ k_softmax_argmax(long long P, const float* __restrict__ logits, int T, int C, fl
     if (cls) st4(cls + (long long)n * P, i, P, vec, best);
 }
 
-// One variant and only the class map wanted: softmax is strictly increasing in the logit, so the class is the first
-// maximum of the logits themselves (it can differ from the reference's argmax-of-probabilities only where two
-// probabilities round to the same fp32 value, the tie band the parity test already excludes).  Pure streaming.
+// One variant and only the class map wanted.  softmax is increasing in the logit, so away from ties the class is the
+// first maximum of the logits themselves (pure streaming, no exp).  It is NOT the same thing inside the tie band: the
+// reference takes the first maximum of the fp32 PROBABILITIES (base.py:332-336, unet.py:62), and exp(x_c - max) rounds
+// to exactly 1.0f for every logit within ~8e-8 of the maximum (and e / s can round to 1 / s a little further out), so
+// an EARLIER class whose logit is a hair below the maximum wins there.  Bound: with max - x_c > 1e-6, e_c <= 1 - 7e-7
+// under expf's 2-ulp error and two roundings of 6e-8 cannot close that gap, so the probabilities are strictly ordered
+// like the logits.  Pixels with a runner-up inside 1e-6 (or a NaN) are re-evaluated with the exact arithmetic of
+// k_softmax_argmax (same expf, same summation order, first maximum).
 template <int CMAX>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_argmax_logits(long long P, const float* __restrict__ logits, int C, uint8_t* __restrict__ cls, bool vec) {
@@ -84,6 +89,34 @@ k_argmax_logits(long long P, const float* __restrict__ logits, int C, uint8_t* _
 #pragma unroll
             for (int k = 0; k < 4; ++k) if (x[c].v[k] > bv[k]) { bv[k] = x[c].v[k]; best.v[k] = (uint8_t)c; }
         }
+    // runner-up inside the tie band (or NaN)?  count the logits not clearly below the maximum; the maximum itself is one
+    int near[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) near[k] += (bv[k] - x[c].v[k] > 1.0e-6f) ? 0 : 1;
+        }
+    if ((near[0] | near[1] | near[2] | near[3]) > 1) {            // rare: the exact arithmetic of k_softmax_argmax
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (near[k] <= 1) continue;
+            float m = -INFINITY, e[CMAX], sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < C) m = fmaxf(m, x[c].v[k]);
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < C) { e[c] = expf(x[c].v[k] - m); sum = sum + e[c]; }
+            int b = 0;
+            float pv = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+                if (c < C) {
+                    const float p = (e[c] / sum) / 1.f;          // T = 1: the TTA mean divides by 1
+                    if (p > pv) { pv = p; b = c; }
+                }
+            best.v[k] = (uint8_t)b;
+        }
+    }
     st4(cls + (long long)n * P, i, P, vec, best);
 }
 

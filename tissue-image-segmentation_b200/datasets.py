@@ -15,6 +15,7 @@ import numpy as np
 
 from . import metrics as M
 from . import ops
+from . import _lib
 from ._lib import is_torch
 
 
@@ -35,7 +36,13 @@ def _log(msg, logger=None):
 
 
 def _host(a):
-    return a.cpu().numpy() if is_torch(a) else np.asarray(a)
+    """Result array -> numpy.  For a CUDA tensor the library context is synchronised first: errors only a kernel can
+    detect (an instance id outside the supported range) are raised HERE instead of being read back as wrong numbers."""
+    if is_torch(a):
+        if a.is_cuda:
+            _lib.get_ctx(a.device.index).synchronize()
+        return a.cpu().numpy()
+    return np.asarray(a)
 
 
 class CustomDataset:

@@ -11,11 +11,18 @@ from collections import OrderedDict
 import numpy as np
 
 from . import ops
+from . import _lib
 from ._lib import is_torch
 
 
 def _host(a):
-    return a.cpu().numpy() if is_torch(a) else np.asarray(a)
+    """Result array -> numpy.  For a CUDA tensor the library context is synchronised first: errors only a kernel can
+    detect (an instance id outside the supported range) are raised HERE instead of being read back as wrong numbers."""
+    if is_torch(a):
+        if a.is_cuda:
+            _lib.get_ctx(a.device.index).synchronize()
+        return a.cpu().numpy()
+    return np.asarray(a)
 
 
 def _is_batch(a):

@@ -19,6 +19,19 @@ def _unbatch(out, was2d):
     return out[0] if was2d else out
 
 
+def _inplace_arg(a, dtype, what):
+    """Arguments the reference mutates in place are handed to the library as they are (no converted copy could carry
+    the mutation back), so they must already be C-contiguous arrays of the exact dtype."""
+    if _lib.is_torch(a):
+        ok = a.dtype == _lib._torch_dtype(dtype) and a.is_contiguous()
+    else:
+        ok = isinstance(a, np.ndarray) and a.dtype == np.dtype(dtype) and a.flags.c_contiguous and a.flags.writeable
+    if not ok:
+        raise TypeError("%s must be a writeable C-contiguous %s array (it is modified in place), got %s %s" % (
+            what, np.dtype(dtype).name, type(a).__name__, getattr(a, "dtype", None)))
+    return a
+
+
 def softmax_argmax(logits, want_prob=False):
     """A1.  logits ``[T, C, H, W]`` / ``[N, T, C, H, W]`` fp32 (T = TTA variants) ->
     class map uint8 (and the TTA-mean probabilities ``[.., C, H, W]`` when ``want_prob``)."""
@@ -107,7 +120,7 @@ def erosion(lab, footprint="disk", radius=1):
 def postproc_unet(cls, max_class, radius=1, edge_id=None, kill=None):
     """A2.  Returns (sem_pred uint8, inst_pred int32).  ``cls`` (uint8) is modified in place when
     ``edge_id`` / ``kill`` are given, like the reference."""
-    x, was2d = batched(cls)
+    x, was2d = batched(_inplace_arg(cls, np.uint8, "postproc_unet: cls"))
     N, H, W = x.shape
     k = None
     if kill is not None:
@@ -231,7 +244,7 @@ def cdnet_refine(sem_logits, dir_logits, point_logits, if_ddm=True):
 
 def align_foreground(pred, foreground, time=20):
     """A13: grows the labels of ``pred`` (int32, modified in place and returned) into ``foreground``."""
-    x, was2d = batched(pred)
+    x, was2d = batched(_inplace_arg(pred, np.int32, "align_foreground: pred"))
     f, _ = batched(as_input(foreground, np.uint8))
     N, H, W = x.shape
     get_ctx(_dev(x)).call("tiseg_align_foreground", ptr(x), ptr(f), N, H, W, int(time))
