@@ -1,0 +1,310 @@
+// Connected components on BIT PLANES: the per-pixel work of a labelling is reduced to one streaming pass that turns the
+// image into five bit planes (one 32-bit ballot word per 32-pixel row segment and plane); everything after that — the
+// union-find, the cross-tile merges, the root bitmaps, and the consumers that only need to know WHICH component a pixel
+// run belongs to (pair histogram, blob boxes, flood staging) — works on words and on the horizontal RUNS they describe,
+// never on pixels.  The pixel-level shared-memory union-find of ccl.cuh issues ~4.4 warp instructions per pixel and map
+// (profiles/r2_pair_local_*: 566 M warp instructions for two 64 x 1000^2 labellings, 45 % of them in single-lane
+// union / find loops); here the streaming pass costs ~0.7 and the rest is proportional to the number of runs.
+//
+// Planes (bit x of word [n, y, seg] = pixel 32 * seg + x of row y; bits beyond W are zero):
+//   F   pixel is foreground
+//   C   foreground and equal to its left neighbour            (same run)
+//   EU  foreground and equal to the pixel above
+//   EL  foreground and equal to the pixel above-left
+//   ER  foreground and equal to the pixel above-right
+// For a binary mask only F is stored and the other four are derived with shifts (BitPlanes::C == nullptr).
+//
+// Nodes of the union-find are the runs of a TILE ROW: a run is cut where it crosses a tile's left edge, so that every
+// node lies inside one tile of BT_TH rows x BT_TWW words and the tile kernel needs no neighbour.  A node's id is the
+// tile-local / tile-global flat index of its first pixel; `par` is a pixel-indexed int array that is only ever touched
+// at run starts (root = lowest index of the component = its first pixel in raster order, as everywhere in this library).
+//   k_bitccl_tile     one CTA per tile, one thread per word: unions inside the tile in shared memory, then
+//                     par[run start] = local root (global index) and the bitmap of the local roots
+//   k_bitccl_border   the unions that cross tile edges (top rows of tiles, first / last column of tiles)
+//   k_bitccl_resolve  local roots -> final roots; bitmap of the final roots (what the raster-order ranking consumes)
+#pragma once
+#include "common.cuh"
+
+namespace tiseg {
+
+#define BT_TH 32                 // tile rows
+#define BT_TWW 8                 // tile width in words (256 pixels)
+#define BT_TW (32 * BT_TWW)
+#define BT_THREADS (BT_TH * BT_TWW)
+
+struct BitPlanes {
+    const unsigned* F;
+    const unsigned* C;           // nullptr: binary mask, planes derived from F
+    const unsigned* EU;
+    const unsigned* EL;
+    const unsigned* ER;
+};
+struct BitPlanesW { unsigned *F, *C, *EU, *EL, *ER; };
+inline BitPlanes as_const(const BitPlanesW& w) { return BitPlanes{w.F, w.C, w.EU, w.EL, w.ER}; }
+
+// allocation of the five planes of `maps` tile batches in the call workspace
+inline int bitplanes_alloc(tiseg_ctx* c, const Geom& g, int maps, BitPlanesW& p) {
+    const size_t words = (size_t)maps * g.N * g.H * g.SEG;
+    p.F = ws<unsigned>(c, words); p.C = ws<unsigned>(c, words); p.EU = ws<unsigned>(c, words);
+    p.EL = ws<unsigned>(c, words); p.ER = ws<unsigned>(c, words);
+    return (p.F && p.C && p.EU && p.EL && p.ER) ? TISEG_OK : TISEG_ERR_CUDA;
+}
+
+#ifdef __CUDACC__
+struct Masks { unsigned f, c, eu, el, er; };
+
+// the five masks of word (y, seg) of tile-batch entry `n` (wo = n * H * SEG), as the image defines them (not cut at
+// tile edges)
+__device__ __forceinline__ Masks bit_masks(const BitPlanes& p, const Geom& g, long long wo, int y, int seg) {
+    Masks m;
+    const long long i = wo + (long long)y * g.SEG + seg;
+    m.f = p.F[i];
+    if (p.C) {
+        m.c = p.C[i]; m.eu = p.EU[i]; m.el = p.EL[i]; m.er = p.ER[i];
+        return m;
+    }
+    const unsigned fl = seg > 0 ? p.F[i - 1] : 0u;
+    m.c = m.f & ((m.f << 1) | (fl >> 31));
+    m.eu = m.el = m.er = 0u;
+    if (y > 0) {
+        const unsigned u = p.F[i - g.SEG];
+        const unsigned ul = seg > 0 ? p.F[i - g.SEG - 1] : 0u, ur = seg + 1 < g.SEG ? p.F[i - g.SEG + 1] : 0u;
+        m.eu = m.f & u;
+        m.el = m.f & ((u << 1) | (ul >> 31));
+        m.er = m.f & ((u >> 1) | (ur << 31));
+    }
+    return m;
+}
+
+// run starts of word (y, seg) with runs cut at the left edge of every tile
+__device__ __forceinline__ unsigned bit_starts(const BitPlanes& p, const Geom& g, long long wo, int y, int seg) {
+    const long long i = wo + (long long)y * g.SEG + seg;
+    const unsigned f = p.F[i];
+    unsigned c;
+    if (p.C) c = p.C[i];
+    else c = f & ((f << 1) | (seg > 0 ? p.F[i - 1] >> 31 : 0u));
+    if (seg % BT_TWW == 0) c &= ~1u;
+    return f & ~c;
+}
+
+// tile-global flat index of the first pixel of the tile-row run that contains foreground pixel (y, x)
+__device__ __forceinline__ int bit_node_of(const BitPlanes& p, const Geom& g, long long wo, int y, int x) {
+    int seg = x >> 5;
+    unsigned m = bit_starts(p, g, wo, y, seg) & (0xffffffffu >> (31 - (x & 31)));
+    while (!m) { --seg; m = bit_starts(p, g, wo, y, seg); }      // ends inside the tile row: its first pixel starts a run
+    return y * g.W + seg * 32 + 31 - __clz(m);
+}
+
+// ---- streaming pass: int32 label map -> planes (equal-value components, background 0) ---------------------------------
+// One warp = one 32-pixel column strip x EQ_BAND rows, walking down: the row above and its two shuffled copies stay in
+// registers, so every pixel is loaded once (plus the two strip-edge columns); five ballots per row, lane k stores plane k.
+#define EQ_BAND 32
+#define EQ_UNROLL 8
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_eqbits_i32(Geom g, const int32_t* __restrict__ img, BitPlanesW out) {
+    const int lane = threadIdx.x & 31;
+    const int bands = (g.H + EQ_BAND - 1) / EQ_BAND;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (wi >= (long long)g.SEG * bands) return;
+    const int band = (int)(wi / g.SEG), seg = (int)(wi - (long long)band * g.SEG), n = blockIdx.y;
+    const int x = seg * 32 + lane, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
+    const int32_t* t = img + (long long)n * g.P;
+    const bool okx = x < g.W;
+    // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
+    const int xe = lane == 0 ? x - 1 : x + 1;
+    const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
+    int prev = 0, prevL = 0, prevR = 0;
+    if (y0 > 0) {
+        const long long ro = (long long)(y0 - 1) * g.W;
+        prev = okx ? t[ro + x] : 0;
+        const int e = oke ? t[ro + xe] : 0;
+        prevL = __shfl_up_sync(0xffffffffu, prev, 1);
+        prevR = __shfl_down_sync(0xffffffffu, prev, 1);
+        if (lane == 0) prevL = e;
+        if (lane == 31) prevR = e;
+    }
+    unsigned* const plane = lane == 0 ? out.F : lane == 1 ? out.C : lane == 2 ? out.EU : lane == 3 ? out.EL : out.ER;
+    for (int yb = y0; yb < y1; yb += EQ_UNROLL) {
+        int cur[EQ_UNROLL], ext[EQ_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {
+            const int y = yb + u;
+            const long long ro = (long long)y * g.W;
+            cur[u] = (okx && y < y1) ? t[ro + x] : 0;
+            ext[u] = (oke && y < y1) ? t[ro + xe] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {
+            const int y = yb + u;
+            if (y >= y1) break;                                  // (uniform)
+            const int v = cur[u];
+            int vL = __shfl_up_sync(0xffffffffu, v, 1), vR = __shfl_down_sync(0xffffffffu, v, 1);
+            if (lane == 0) vL = ext[u];
+            if (lane == 31) vR = ext[u];
+            const bool f = v != 0;
+            const unsigned mF = __ballot_sync(0xffffffffu, f);
+            const unsigned mC = __ballot_sync(0xffffffffu, f && v == vL);
+            const unsigned mU = __ballot_sync(0xffffffffu, f && v == prev);
+            const unsigned mL = __ballot_sync(0xffffffffu, f && v == prevL);
+            const unsigned mR = __ballot_sync(0xffffffffu, f && v == prevR);
+            const unsigned mine = lane == 0 ? mF : lane == 1 ? mC : lane == 2 ? mU : lane == 3 ? mL : mR;
+            if (lane < 5) plane[((long long)n * g.H + y) * g.SEG + seg] = mine;
+            prev = v; prevL = vL; prevR = vR;
+        }
+    }
+}
+
+// ---- tile union-find on the planes -------------------------------------------------------------------------------------
+static __device__ __noinline__ void bt_union(int* par, int a, int b) { uf_union(par, a, b); }
+
+// tile-local node (row * BT_TW + column of the run start) of foreground pixel (row, x) from the tile's start masks
+__device__ __forceinline__ int bt_node_of(const unsigned (*sS)[BT_TWW], int row, int x) {
+    int w = x >> 5;
+    unsigned m = sS[row][w] & (0xffffffffu >> (31 - (x & 31)));
+    while (!m) { --w; m = sS[row][w]; }
+    return row * BT_TW + w * 32 + 31 - __clz(m);
+}
+
+// p: planes of `g.N` tile-batch entries; par [g.N, P]; lbits [g.N, H, SEG].  conn 1: 4-neighbourhood, 2: 8.
+template <int CONN>
+__global__ void __launch_bounds__(BT_THREADS)
+k_bitccl_tile(Geom g, BitPlanes p, int* __restrict__ par, unsigned* __restrict__ lbits) {
+    __shared__ int spar[BT_TH * BT_TW];
+    __shared__ unsigned sS[BT_TH][BT_TWW];
+    const int tilesX = (g.SEG + BT_TWW - 1) / BT_TWW;
+    const int ty = blockIdx.x / tilesX, tx = blockIdx.x - ty * tilesX, n = blockIdx.y;
+    const int r = threadIdx.x / BT_TWW, w = threadIdx.x - r * BT_TWW;
+    const int y = ty * BT_TH + r, seg = tx * BT_TWW + w;
+    const long long wo = (long long)n * g.H * g.SEG;
+    const bool live = y < g.H && seg < g.SEG;
+    Masks m = {0u, 0u, 0u, 0u, 0u};
+    if (live) m = bit_masks(p, g, wo, y, seg);
+    // connections that leave the tile belong to k_bitccl_border
+    if (w == 0) { m.c &= ~1u; m.el &= ~1u; }
+    if (w == BT_TWW - 1) m.er &= 0x7fffffffu;
+    if (r == 0) m.eu = m.el = m.er = 0u;
+    const unsigned S = m.f & ~m.c;
+    sS[r][w] = S;
+    const int node0 = r * BT_TW + w * 32;
+    for (unsigned s = S; s; s &= s - 1) { const int b = __ffs(s) - 1; spar[node0 + b] = node0 + b; }
+    __syncthreads();
+    // unions with the row above; a pixel that continues its run and whose left neighbour already sits under the same
+    // upper run needs none (rule of k_ccl_local)
+    unsigned need_u = m.eu & ~(m.c & m.el), need_l = 0u, need_r = 0u;
+    if (CONN == 2) { need_l = ~m.eu & m.el & ~m.c; need_r = ~m.eu & m.er; }
+    for (unsigned s = need_u; s; s &= s - 1) {
+        const int x = w * 32 + __ffs(s) - 1;
+        bt_union(spar, bt_node_of(sS, r, x), bt_node_of(sS, r - 1, x));
+    }
+    for (unsigned s = need_l; s; s &= s - 1) {
+        const int x = w * 32 + __ffs(s) - 1;
+        bt_union(spar, bt_node_of(sS, r, x), bt_node_of(sS, r - 1, x - 1));
+    }
+    for (unsigned s = need_r; s; s &= s - 1) {
+        const int x = w * 32 + __ffs(s) - 1;
+        bt_union(spar, bt_node_of(sS, r, x), bt_node_of(sS, r - 1, x + 1));
+    }
+    __syncthreads();
+    // every node: global par entry = global index of its local root; bitmap of the local roots
+    unsigned roots = 0u;
+    const int gy0 = ty * BT_TH, gx0 = tx * BT_TW;
+    int* tp = par + (long long)n * g.P;
+    for (unsigned s = S; s; s &= s - 1) {
+        const int b = __ffs(s) - 1, node = node0 + b;
+        const int root = uf_find(spar, node);
+        if (root == node) roots |= 1u << b;
+        tp[y * g.W + gx0 + w * 32 + b] = (gy0 + root / BT_TW) * g.W + gx0 + (root & (BT_TW - 1));
+    }
+    if (live) lbits[wo + (long long)y * g.SEG + seg] = roots;
+}
+
+// unions across tile edges.  Work items per tile-batch entry: (a) every word of every tile-top row (rows BT_TH * k,
+// k >= 1): the vertical / diagonal connections into the tile above, plus run continuations across tile columns;
+// (b) for every other row, each inner tile-column boundary: the continuation across it and the two diagonals the tile
+// kernel dropped there.
+template <int CONN>
+__global__ void __launch_bounds__(256)
+k_bitccl_border(Geom g, BitPlanes p, int* par) {
+    const int tilesX = (g.SEG + BT_TWW - 1) / BT_TWW, tilesY = (g.H + BT_TH - 1) / BT_TH;
+    const int nA = (tilesY - 1) * g.SEG, nB = g.H * (tilesX - 1);
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nA + nB) return;
+    const int n = blockIdx.y;
+    const long long wo = (long long)n * g.H * g.SEG;
+    int* tp = par + (long long)n * g.P;
+    if (t < nA) {
+        const int y = (t / g.SEG + 1) * BT_TH, seg = t - (t / g.SEG) * g.SEG;
+        const Masks m = bit_masks(p, g, wo, y, seg);
+        if (!m.f) return;
+        unsigned need_u = m.eu & ~(m.c & m.el), need_l = 0u, need_r = 0u;
+        if (CONN == 2) { need_l = ~m.eu & m.el & ~m.c; need_r = ~m.eu & m.er; }
+        for (unsigned s = need_u; s; s &= s - 1) {
+            const int x = seg * 32 + __ffs(s) - 1;
+            uf_union(tp, bit_node_of(p, g, wo, y, x), bit_node_of(p, g, wo, y - 1, x));
+        }
+        for (unsigned s = need_l; s; s &= s - 1) {
+            const int x = seg * 32 + __ffs(s) - 1;
+            uf_union(tp, bit_node_of(p, g, wo, y, x), bit_node_of(p, g, wo, y - 1, x - 1));
+        }
+        for (unsigned s = need_r; s; s &= s - 1) {
+            const int x = seg * 32 + __ffs(s) - 1;
+            uf_union(tp, bit_node_of(p, g, wo, y, x), bit_node_of(p, g, wo, y - 1, x + 1));
+        }
+        return;
+    }
+    t -= nA;
+    const int y = t / (tilesX - 1), j = t - y * (tilesX - 1) + 1;     // boundary between tile columns j-1 and j
+    const int segR = j * BT_TWW, xr = segR * 32;                      // first pixel of the right tile
+    if (xr >= g.W) return;
+    const bool top = y % BT_TH == 0;                                  // (the diagonals of tile-top rows are items (a))
+    const Masks mr = bit_masks(p, g, wo, y, segR);
+    if (mr.c & 1u) uf_union(tp, y * g.W + xr, bit_node_of(p, g, wo, y, xr - 1));
+    if (CONN == 2 && !top && y > 0) {
+        if (~mr.eu & mr.el & ~mr.c & 1u) uf_union(tp, y * g.W + xr, bit_node_of(p, g, wo, y - 1, xr - 1));
+        const Masks ml = bit_masks(p, g, wo, y, segR - 1);
+        if ((~ml.eu & ml.er) >> 31) uf_union(tp, bit_node_of(p, g, wo, y, xr - 1), bit_node_of(p, g, wo, y - 1, xr));
+    }
+}
+
+// local roots -> final roots (path compression on the way); fbits = bitmap of the final roots
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_bitccl_resolve(Geom g, int* par, const unsigned* __restrict__ lbits, unsigned* __restrict__ fbits) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    unsigned m = lbits[(long long)n * words + t], keep = m;
+    if (m) {
+        const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+        int* tp = par + (long long)n * g.P;
+        const int idx0 = y * g.W + seg * 32;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int r = idx0 + b, G = uf_find(tp, r);
+            if (G != r) { tp[r] = G; keep &= ~(1u << b); }
+        }
+    }
+    fbits[(long long)n * words + t] = keep;
+}
+
+// planes -> forest (par at run starts) + bitmap of the final roots.  lbits / fbits: [g.N, H, SEG] scratch / output.
+inline int bitccl_build(tiseg_ctx* c, const Geom& g, const BitPlanes& p, int conn, int* par, unsigned* lbits, unsigned* fbits) {
+    const int tilesX = (g.SEG + BT_TWW - 1) / BT_TWW, tilesY = (g.H + BT_TH - 1) / BT_TH;
+    const dim3 tg((unsigned)(tilesX * tilesY), (unsigned)g.N);
+    const int nb = (tilesY - 1) * g.SEG + g.H * (tilesX - 1);
+    const dim3 bg((unsigned)((nb + 255) / 256), (unsigned)g.N);
+    if (conn == 2) {
+        TISEG_LAUNCH(c, k_bitccl_tile<2>, tg, BT_THREADS, 0, g, p, par, lbits);
+        if (nb > 0) TISEG_LAUNCH(c, k_bitccl_border<2>, bg, 256, 0, g, p, par);
+    } else {
+        TISEG_LAUNCH(c, k_bitccl_tile<1>, tg, BT_THREADS, 0, g, p, par, lbits);
+        if (nb > 0) TISEG_LAUNCH(c, k_bitccl_border<1>, bg, 256, 0, g, p, par);
+    }
+    const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
+    TISEG_LAUNCH(c, k_bitccl_resolve, wg, TISEG_THREADS, 0, g, par, lbits, fbits);
+    return TISEG_OK;
+}
+#endif
+
+}  // namespace tiseg

@@ -9,6 +9,7 @@
 // by (gt id, pred id) — one atomic per horizontal RUN of equal pairs (warp ballot), not per pixel — and
 // everything downstream works on the O(K) non-zero pairs.  Counts are exact integers; the only floating
 // point is the fp64 IoU used for argmax / thresholding, evaluated with the reference's expressions.
+#include "bitccl.cuh"
 #include "ccl.cuh"
 
 namespace tiseg {
@@ -171,319 +172,59 @@ k_pair_accumulate_big(Geom g, const int* __restrict__ par_g, const int* __restri
 
 
 // =====================================================================================================================
-// Fused labelling + pair table (the default path of tiseg_pair_metrics_*).
+// Pair table from bit planes (the default path of tiseg_pair_metrics_*; bitccl.cuh).
 //
 // measure.label of both maps (inst_metrics.py:12-13) only serves to IDENTIFY the components the pair matrix is indexed
-// by; no per-pixel label map is ever needed.  So instead of labelling both maps to per-pixel forests (write 4 B/px
-// each), flattening them (read + write 8 B/px each) and re-reading both forests for the pair histogram (8 B/px), ONE
-// kernel reads the two instance maps once (8 B/px) and per 32 x 128 tile
-//   * runs the shared-memory union-find of k_ccl_local on the gt map, then on the pred map (same shared arrays),
-//     keeping each pixel's LOCAL root in registers;
-//   * counts the area of every local component in shared memory;
-//   * posts one (local gt root, local pred root, length) entry per horizontal run of a constant pair into hash table 1;
-//   * writes `par` only where the cross-tile merge needs it: at the local roots and on the four edges of the tile
-//     (~ 20 % of the forest), plus the bitmap of the local roots and their areas.
-// k_ccl_border then merges across tiles exactly as for the per-pixel forests, k_lroot_resolve points every local root at
-// its final root (summing the areas, leaving the bitmap of the FINAL roots for the raster-order ranking), and
-// k_pair_rekey moves table 1 into table 2 keyed by the dense raster-order ids (rank of the final root) that the
-// evaluation kernels below expect.  Everything after the first kernel touches O(components) data.
+// by; no per-pixel label map is needed.  Both instance maps are read ONCE (k_eqbits_i32, 4 B/px each) into equality bit
+// planes; the union-find, the cross-tile merges, the final-root bitmaps and their raster-order ranks work on words and
+// runs; and the pair histogram is accumulated by one thread per 32-pixel word from the planes of the two maps: a piece
+// of a row on which both labels are constant is delimited with bit operations, the component ids of its two runs are
+// looked up at the run starts, and one set of atomics is posted per piece (areas by id + the (gt, pred) hash table).
 // =====================================================================================================================
-struct PairLocalOut {
-    int* par;            // [2, N, P]   map 0 = gt, 1 = pred; valid at local roots and tile-edge pixels only
-    int* area;           // [2, N, P]   valid at local roots (after k_lroot_resolve: at final roots = the component area)
-    unsigned* lbits;     // [2, N, H, SEG] bitmap of the local roots
-};
-
-__device__ __forceinline__ int tile_goff(int q, int W, int off) { return (q >> 7) * W + (q & (CCL_TW - 1)) + off; }
-
-// local union-find of one map on the CTA's tile (phases A, B, C1 of k_ccl_local, 8-connectivity, background 0) and the
-// outputs of that map.  pk[r] = (local index of the local root + 1) of the thread's four pixels of row r as four
-// 16-bit fields (0 on the background): (px0 | px1 << 16), (px2 | px3 << 16).
-__device__ __forceinline__ void pair_tile_uf(const Geom& g, const int32_t* __restrict__ tile, int* __restrict__ par, int* __restrict__ area,
-                                             unsigned* __restrict__ lbits, int yt, int tx, int warp, int lane, int* sval, int* slab,
-                                             unsigned (&pk)[CCL_RPW][2]) {
-    const int x0 = tx * CCL_TW + lane * 4;
-    const int off = yt * g.W + tx * CCL_TW;
-    int v[CCL_RPW][4];
-    unsigned cm[CCL_RPW], fgm[CCL_RPW];
-    int ext[CCL_RPW];                   // pixels beyond my pixel 3 that continue its run (inside the warp's 128 pixels)
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int y = yt + r * CCL_WARPS + warp;
-        const int32_t* rp = tile + (long long)y * g.W + x0;
-        int b[4];
-        if (y < g.H && x0 + 3 < g.W && quad_i32(rp, b)) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[r][k] = b[k] != 0 ? b[k] : CCL_BG;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int t = 0;
-                if (y < g.H && x0 + k < g.W) t = rp[k];
-                v[r][k] = t != 0 ? t : CCL_BG;
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int row = r * CCL_WARPS + warp, li0 = row * CCL_TW + lane * 4;
-        int left = __shfl_up_sync(0xffffffffu, v[r][3], 1);
-        if (lane == 0) left = CCL_BG;
-        const unsigned f = (v[r][0] != CCL_BG ? 1u : 0u) | (v[r][1] != CCL_BG ? 2u : 0u) | (v[r][2] != CCL_BG ? 4u : 0u) |
-                           (v[r][3] != CCL_BG ? 8u : 0u);
-        const unsigned c = ((v[r][0] == left ? 1u : 0u) | (v[r][1] == v[r][0] ? 2u : 0u) | (v[r][2] == v[r][1] ? 4u : 0u) |
-                            (v[r][3] == v[r][2] ? 8u : 0u)) & f;
-        fgm[r] = f; cm[r] = c;
-        const unsigned full = __ballot_sync(0xffffffffu, c == 15u);
-        const unsigned lower = ~full & ((1u << lane) - 1u);
-        const int src = lower ? 31 - __clz(lower) : 0;
-        const int s3 = 31 - __clz((~c & 15u) | 1u);
-        const int inherited = __shfl_sync(0xffffffffu, li0 + s3, src);
-        const int l0 = (c & 1u) ? inherited : li0;
-        {   // run extension beyond my last pixel (as quad_runs)
-            const unsigned rest = lane < 31 ? full >> (lane + 1) : 0u;
-            const int nfull = __ffs(~rest) - 1, next = lane + 1 + nfull;
-            const int lead = __ffs(~c) - 1;
-            const int nl = __shfl_sync(0xffffffffu, lead, next < 32 ? next : 31);
-            ext[r] = 4 * nfull + (next < 32 ? nl : 0);
-        }
-        const unsigned brk = ~c & 15u;
-        int4 lab;
-        lab.x = (f & 1u) ? l0 : -1;
-        lab.y = (f & 2u) ? ((brk & 2u) ? li0 + 1 : l0) : -1;
-        lab.z = (f & 4u) ? ((brk & 4u) ? li0 + 2 : (brk & 2u) ? li0 + 1 : l0) : -1;
-        lab.w = (f & 8u) ? ((brk & 14u) ? li0 + s3 : l0) : -1;
-        *reinterpret_cast<int4*>(&sval[li0]) = make_int4(v[r][0], v[r][1], v[r][2], v[r][3]);
-        *reinterpret_cast<int4*>(&slab[li0]) = lab;
-    }
-    __syncthreads();
-    // merge with the row above (rule as in k_ccl_local / k_ccl_border)
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int row = r * CCL_WARPS + warp, li0 = row * CCL_TW + lane * 4;
-        if (row == 0 || !fgm[r]) continue;
-        const int4 up = *reinterpret_cast<const int4*>(&sval[li0 - CCL_TW]);
-        const int ul = lane > 0 ? sval[li0 - CCL_TW - 1] : CCL_BG;
-        const int ur = lane < 31 ? sval[li0 - CCL_TW + 4] : CCL_BG;
-        const unsigned eU = ((up.x == v[r][0] ? 1u : 0u) | (up.y == v[r][1] ? 2u : 0u) | (up.z == v[r][2] ? 4u : 0u) |
-                             (up.w == v[r][3] ? 8u : 0u)) & fgm[r];
-        const unsigned eL = ((ul == v[r][0] ? 1u : 0u) | (up.x == v[r][1] ? 2u : 0u) | (up.y == v[r][2] ? 4u : 0u) |
-                             (up.z == v[r][3] ? 8u : 0u)) & fgm[r];
-        const unsigned eR = ((up.y == v[r][0] ? 1u : 0u) | (up.z == v[r][1] ? 2u : 0u) | (up.w == v[r][2] ? 4u : 0u) |
-                             (ur == v[r][3] ? 8u : 0u)) & fgm[r];
-        const unsigned need_u = eU & ~(cm[r] & eL), need_l = ~eU & eL & ~cm[r], need_r = ~eU & eR;
-        unsigned todo = need_u | (need_l << 4) | (need_r << 8);
-        while (todo) {
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int k = b & 3, li = li0 + k;
-            uf_union_tile(slab, li, li - CCL_TW + (b >> 2 == 0 ? 0 : b >> 2 == 1 ? -1 : 1));
-        }
-    }
-    __syncthreads();
-    // run starts point at their local root; the value tile is dead now and becomes the per-component area counter
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int li0 = (r * CCL_WARPS + warp) * CCL_TW + lane * 4;
-        unsigned starts = fgm[r] & ~cm[r];
-        while (starts) {
-            const int k = __ffs(starts) - 1;
-            starts &= starts - 1;
-            const int root = uf_find(slab, li0 + k);
-            if (root != li0 + k) slab[li0 + k] = root;
-        }
-        *reinterpret_cast<int4*>(&sval[li0]) = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int li0 = (r * CCL_WARPS + warp) * CCL_TW + lane * 4;
-        const int4 lab = *reinterpret_cast<const int4*>(&slab[li0]);
-        const unsigned q0 = lab.x >= 0 ? (unsigned)slab[lab.x] + 1u : 0u, q1 = lab.y >= 0 ? (unsigned)slab[lab.y] + 1u : 0u;
-        const unsigned q2 = lab.z >= 0 ? (unsigned)slab[lab.z] + 1u : 0u, q3 = lab.w >= 0 ? (unsigned)slab[lab.w] + 1u : 0u;
-        pk[r][0] = q0 | (q1 << 16); pk[r][1] = q2 | (q3 << 16);
-        unsigned starts = fgm[r] & ~cm[r];
-        while (starts) {
-            const int k = __ffs(starts) - 1;
-            starts &= starts - 1;
-            int len = __ffs(~(cm[r] >> (k + 1)));                 // pixels of the run inside this thread
-            if (k + len == 4) len += ext[r];
-            atomicAdd(&sval[slab[li0 + k]], len);                   // (a run start holds its root since the last phase)
-        }
-    }
-    __syncthreads();
-    // outputs of this map: local roots (par, area, bitmap) and the tile's edge pixels (par)
-#pragma unroll
-    for (int r = 0; r < CCL_RPW; ++r) {
-        const int row = r * CCL_WARPS + warp, y = yt + row, li0 = row * CCL_TW + lane * 4;
-        const int q[4] = {(int)(pk[r][0] & 0xffffu) - 1, (int)(pk[r][0] >> 16) - 1, (int)(pk[r][1] & 0xffffu) - 1, (int)(pk[r][1] >> 16) - 1};
-        unsigned rootnib = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (q[k] == li0 + k) {
-                rootnib |= 1u << k;
-                const int gi = y * g.W + x0 + k;
-                par[gi] = gi;
-                area[gi] = sval[li0 + k];
-            }
-        }
-        // eight lanes x four pixels -> one 32-bit word of the bitmap
-        const unsigned word = __reduce_or_sync(0xffu << (lane & 24), rootnib << ((lane & 7) * 4));
-        const int seg = tx * (CCL_TW / 32) + (lane >> 3);
-        if ((lane & 7) == 0 && y < g.H && seg < g.SEG) lbits[(long long)y * g.SEG + seg] = word;
-        if (y >= g.H) continue;
-        const bool edge_row = row == 0 || row == CCL_TH - 1;
-        if (edge_row) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (x0 + k < g.W && q[k] >= 0) par[y * g.W + x0 + k] = tile_goff(q[k], g.W, off);
-        } else {
-            if (lane == 0 && q[0] >= 0) par[y * g.W + x0] = tile_goff(q[0], g.W, off);
-            if (lane == 31 && x0 + 3 < g.W && q[3] >= 0) par[y * g.W + x0 + 3] = tile_goff(q[3], g.W, off);
-        }
-    }
+__device__ __forceinline__ int find_ro(const int* __restrict__ par, int x) {
+    int q = par[x];
+    while (q != x) { x = q; q = par[x]; }
+    return x;
 }
 
-// pairs of one tile are first merged in a shared-memory table (PL_SLOTS entries: key = local gt root | local pred root
-// << 12, + 1), so that the global table sees one atomic per DISTINCT pair of the tile, issued by 256 threads in parallel,
-// instead of one per horizontal run, issued serially by the thread that owns the run
-#define PL_SLOTS 1024
-#define PL_PROBES 8
-
-// BIG = false: every tile, table 1 = the small table.  BIG = true: the redo into the always-sufficient table, a
-// persistent grid that does nothing unless the first pass overflowed.
+// p: planes of 2N tile-batch entries (gt tiles, then pred tiles); par / rank: [2N, P]
 template <bool BIG>
-__global__ void __launch_bounds__(32 * CCL_WARPS, 4)
-k_pair_local(Geom g, const int32_t* __restrict__ gt, const int32_t* __restrict__ pred, PairLocalOut o, PairTab t, int* lost) {
-    __shared__ __align__(16) int sval[CCL_TH * CCL_TW];
-    __shared__ __align__(16) int slab[CCL_TH * CCL_TW];
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_pair_bits(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restrict__ rank, InstState s, PairTab t, int* lost) {
     if (BIG && !*t.overflow) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tilesX = (g.W + CCL_TW - 1) / CCL_TW, tilesY = (g.H + CCL_TH - 1) / CCL_TH, tpt = tilesX * tilesY;
     const long long words = (long long)g.H * g.SEG;
-    for (long long job = BIG ? blockIdx.x : (long long)blockIdx.y * tpt + blockIdx.x; job < (long long)g.N * tpt;
-         job += BIG ? gridDim.x : (long long)g.N * tpt) {
-        const int n = (int)(job / tpt), tl = (int)(job - (long long)n * tpt);
-        const int ty = tl / tilesX, tx = tl - ty * tilesX, yt = ty * CCL_TH;
-        const long long base = (long long)n * g.P, mstride = (long long)g.N * g.P;
-        unsigned rg[CCL_RPW][2], rp[CCL_RPW][2];
-        pair_tile_uf(g, gt + base, o.par + base, o.area + base, o.lbits + (long long)n * words, yt, tx, warp, lane, sval, slab, rg);
-        __syncthreads();
-        pair_tile_uf(g, pred + base, o.par + mstride + base, o.area + mstride + base, o.lbits + ((long long)g.N + n) * words, yt,
-                     tx, warp, lane, sval, slab, rp);
-        const int off = yt * g.W + tx * CCL_TW;
-        const PairTabView tv = BIG ? t.big : t.small;
-        int* ovf = BIG ? lost : t.overflow;
-        unsigned* skey = reinterpret_cast<unsigned*>(sval);
-        int* scnt = sval + PL_SLOTS;
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * PL_SLOTS; i += blockDim.x) sval[i] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < CCL_RPW; ++r) {
-            unsigned key[4];
-            {
-                const unsigned g0 = rg[r][0] & 0xffffu, g1 = rg[r][0] >> 16, g2 = rg[r][1] & 0xffffu, g3 = rg[r][1] >> 16;
-                const unsigned p0 = rp[r][0] & 0xffffu, p1 = rp[r][0] >> 16, p2 = rp[r][1] & 0xffffu, p3 = rp[r][1] >> 16;
-                key[0] = (g0 && p0) ? ((g0 - 1u) | ((p0 - 1u) << 12)) + 1u : 0u;
-                key[1] = (g1 && p1) ? ((g1 - 1u) | ((p1 - 1u) << 12)) + 1u : 0u;
-                key[2] = (g2 && p2) ? ((g2 - 1u) | ((p2 - 1u) << 12)) + 1u : 0u;
-                key[3] = (g3 && p3) ? ((g3 - 1u) | ((p3 - 1u) << 12)) + 1u : 0u;
-            }
-            if (!__any_sync(0xffffffffu, (key[0] | key[1] | key[2] | key[3]) != 0u)) continue;      // (uniform)
-            const QuadRuns qr = quad_runs(key, 0u, lane);
-            FOR_QUAD_RUNS(qr, k, len) {
-                const unsigned kk = k == 0 ? key[0] : k == 1 ? key[1] : k == 2 ? key[2] : key[3];
-                unsigned sl = (kk * 2654435761u) >> 22;
-                bool done = false;
-                for (int pr = 0; pr < PL_PROBES && !done; ++pr) {
-                    const unsigned old = atomicCAS(&skey[sl], 0u, kk);
-                    if (old == 0u || old == kk) { atomicAdd(&scnt[sl], (int)len); done = true; }
-                    sl = (sl + 1) & (PL_SLOTS - 1);
-                }
-                if (!done)      // a crowded tile: straight to the global table
-                    pair_add(tv, n, (unsigned)tile_goff((int)((kk - 1u) & 0xfffu), g.W, off) + 1u,
-                             (unsigned)tile_goff((int)((kk - 1u) >> 12), g.W, off) + 1u, (int)len, ovf);
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < PL_SLOTS; i += blockDim.x) {
-            const unsigned kk = skey[i];
-            if (kk)
-                pair_add(tv, n, (unsigned)tile_goff((int)((kk - 1u) & 0xfffu), g.W, off) + 1u,
-                         (unsigned)tile_goff((int)((kk - 1u) >> 12), g.W, off) + 1u, scnt[i], ovf);
-        }
-        if (BIG) __syncthreads();
-    }
-}
-
-// Every local root points at its final root and hands it its area; fbits = bitmap of the final roots.
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_lroot_resolve(Geom g, int* par, int* area, const unsigned* __restrict__ lbits, unsigned* __restrict__ fbits) {
-    const long long words = (long long)g.H * g.SEG;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= words) return;
-    const int n = blockIdx.y;                                   // 0 .. 2N-1: gt tiles, then pred tiles
-    unsigned m = lbits[(long long)n * words + t], keep = m;
-    if (m) {
-        const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-        int* tp = par + (long long)n * g.P;
-        int* ta = area + (long long)n * g.P;
-        const int idx0 = y * g.W + seg * 32;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int r = idx0 + b, G = uf_find(tp, r);
-            if (G != r) { tp[r] = G; atomicAdd(&ta[G], ta[r]); keep &= ~(1u << b); }
-        }
-    }
-    fbits[(long long)n * words + t] = keep;
-}
-
-// dense areas by raster-order id from the sparse ones at the final roots
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_area_dense(Geom g, const int* __restrict__ area, const int* __restrict__ rank, const unsigned* __restrict__ fbits, InstState s) {
-    const long long words = (long long)g.H * g.SEG;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= words) return;
-    const int n2 = blockIdx.y, N = gridDim.y >> 1, n = n2 >= N ? n2 - N : n2;
-    unsigned m = fbits[(long long)n2 * words + t];
-    if (!m) return;
-    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-    const long long pb = (long long)n2 * g.P;
-    int* dst = (n2 >= N ? s.area_p : s.area_g) + (long long)n * s.KS;
-    while (m) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const int n = blockIdx.y, N = gridDim.y;
+    const long long wg = (long long)n * words, wp = (long long)(N + n) * words;
+    const unsigned Fg = p.F[wg + w], Fp = p.F[wp + w];
+    const unsigned fany = Fg | Fp;
+    if (!fany) return;
+    const int y = (int)(w / g.SEG), seg = (int)(w - (long long)y * g.SEG);
+    const unsigned Cg = p.C[wg + w], Cp = p.C[wp + w];
+    const unsigned cg = seg > 0 ? p.F[wg + w - 1] >> 31 : 0u, cp = seg > 0 ? p.F[wp + w - 1] >> 31 : 0u;
+    // "same label as the pixel to the left" on each side (background next to background counts as the same label)
+    const unsigned same_g = Cg | (~Fg & ~((Fg << 1) | cg)), same_p = Cp | (~Fp & ~((Fp << 1) | cp));
+    const unsigned starts = fany & (~(same_g & same_p) | 1u);            // pieces are also cut at the word boundary
+    const PairTabView tv = BIG ? t.big : t.small;
+    int* ovf = BIG ? lost : t.overflow;
+    const long long o = (long long)n * s.KS;
+    const long long pg = (long long)n * g.P, pp = (long long)(N + n) * g.P;
+    for (unsigned m = starts; m; m &= m - 1) {
         const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int r = y * g.W + seg * 32 + b;
-        dst[rank[pb + r]] = area[pb + r];
+        const unsigned rest = b == 31 ? 0u : (starts | ~fany) >> (b + 1);
+        const int len = rest ? __ffs(rest) : 32 - b;
+        const int x = seg * 32 + b;
+        int gid = 0, pid = 0;
+        if ((Fg >> b) & 1u) gid = rank[pg + find_ro(par + pg, bit_node_of(p, g, wg, y, x))];
+        if ((Fp >> b) & 1u) pid = rank[pp + find_ro(par + pp, bit_node_of(p, g, wp, y, x))];
+        if (!BIG) {
+            if (gid) atomicAdd(&s.area_g[o + gid], len);
+            if (pid) atomicAdd(&s.area_p[o + pid], len);
+        }
+        if (gid && pid) pair_add(tv, n, (unsigned)gid, (unsigned)pid, len, ovf);
     }
 }
-
-// table 1 (local gt root + 1, local pred root + 1) -> table 2 (gt id, pred id)
-__global__ void __launch_bounds__(256)
-k_pair_rekey(Geom g, PairTab t1, PairTab t2, const int* __restrict__ par, const int* __restrict__ rank, int* lost) {
-    const bool big = *t1.overflow != 0;
-    const PairTabView a = big ? t1.big : t1.small, b = big ? t2.big : t2.small;
-    const int n = blockIdx.y;
-    const long long pg = (long long)n * g.P, pp = ((long long)gridDim.y + n) * g.P;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < a.cap; slot += gridDim.x * blockDim.x) {
-        const unsigned long long k = a.key[(long long)n * a.cap + slot];
-        if (!k) continue;
-        const int lg = (int)(k >> 32) - 1, lp = (int)(unsigned)k - 1;
-        const unsigned gid = (unsigned)rank[pg + par[pg + lg]], pid = (unsigned)rank[pp + par[pp + lp]];
-        pair_add(b, n, gid, pid, a.cnt[(long long)n * a.cap + slot], lost);
-    }
-}
-
-// the instance maps as one batch of 2N tiles (gt tiles, then pred tiles) for the cross-tile merge
-struct ImgEqI32Two {
-    const int32_t* a; const int32_t* b; int N; long long P;
-    __device__ __forceinline__ bool operator()(int n, long long gi, int& v) const {
-        v = n < N ? a[gi] : b[gi - (long long)N * P];
-        return v != 0;
-    }
-};
 
 // pass A over the table: best AJI IoU per gt (atomicMax on fp64 bits: positive doubles order like integers),
 // and the PQ matches (IoU > 0.5 is unique per gt and per pred)
@@ -936,44 +677,42 @@ static int pair_table_build_legacy(tiseg_ctx* c, const Geom& g, const int32_t* d
     return TISEG_OK;
 }
 
-// fused path: see the comment above k_pair_local
+// default path: bit planes (see the comment above k_pair_bits)
 static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, const int32_t* d_gt, PairWork& w,
                             PairRoots* roots) {
     static const bool legacy = getenv("TISEG_PAIR_LEGACY") != nullptr;
     if (legacy) return pair_table_build_legacy(c, g, d_pred, d_gt, w, roots);
     const int N = g.N;
     const size_t total = (size_t)N * g.P, words = (size_t)N * g.H * g.SEG;
-    PairLocalOut o;
-    o.par = ws<int>(c, 2 * total);
-    o.area = ws<int>(c, 2 * total);
-    o.lbits = ws<unsigned>(c, 2 * words);
-    unsigned* fbits = ws<unsigned>(c, 2 * words);
+    BitPlanesW pw;
+    TISEG_TRY(bitplanes_alloc(c, g, 2, pw));
+    int* par = ws<int>(c, 2 * total);
     int* rank = ws<int>(c, 2 * total);
+    unsigned* lbits = ws<unsigned>(c, 2 * words);
+    unsigned* fbits = ws<unsigned>(c, 2 * words);
     int *ng, *np, *overflow;
-    if (!o.par || !o.area || !o.lbits || !fbits || !rank) return TISEG_ERR_CUDA;
+    if (!par || !rank || !lbits || !fbits) return TISEG_ERR_CUDA;
     TISEG_TRY(pair_state_alloc(c, g, w, &ng, &np, &overflow));
     InstState& s = w.s;
-    PairTab t1;
-    PairTab& t2 = w.t;
-    TISEG_TRY(pair_tab_alloc(c, g, t1, overflow));
-    TISEG_TRY(pair_tab_alloc(c, g, t2, overflow));
+    PairTab& t = w.t;
+    TISEG_TRY(pair_tab_alloc(c, g, t, overflow));
     TISEG_TRY(zero(c, overflow, sizeof(int)));
-    const int tilesY = (g.H + CCL_TH - 1) / CCL_TH, tilesX = (g.W + CCL_TW - 1) / CCL_TW;
-    TISEG_LAUNCH(c, k_pair_local<false>, dim3((unsigned)(tilesX * tilesY), (unsigned)N), 32 * CCL_WARPS, 0, g, d_gt, d_pred, o, t1, c->d_err + 1);
-    // a pathological input overflowed the small table: clear both big tables and redo (persistent grids, idle otherwise)
-    TISEG_LAUNCH(c, k_pair_zero_big, c->sm_count * 8, TISEG_THREADS, 0, t1, t2, N);
-    TISEG_LAUNCH(c, k_pair_local<true>, c->sm_count * 4, 32 * CCL_WARPS, 0, g, d_gt, d_pred, o, t1, c->d_err + 1);
-    // cross-tile merges of both forests in one launch (2N tiles: gt, then pred)
-    Geom g2 = make_geom(2 * N, g.H, g.W);
-    const int nb = (tilesY - 1) * g.W + (tilesX - 1) * g.H * 2;
-    if (nb > 0) TISEG_LAUNCH(c, (k_ccl_border<ImgEqI32Two, 2, false>), dim3((nb + 255) / 256, 2 * N), 256, 0, g2,
-                             (ImgEqI32Two{d_gt, d_pred, N, (long long)g.P}), o.par);
-    const dim3 word_grid((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)(2 * N));
-    TISEG_LAUNCH(c, k_lroot_resolve, word_grid, TISEG_THREADS, 0, g, o.par, o.area, o.lbits, fbits);
-    TISEG_TRY(rank_from_bits(c, g2, fbits, rank, ng));                    // counts: ng[0..N) then np[0..N)
-    TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 0);
-    TISEG_LAUNCH(c, k_area_dense, word_grid, TISEG_THREADS, 0, g, o.area, rank, fbits, s);
-    TISEG_LAUNCH(c, k_pair_rekey, dim3((t1.small.cap + 255) / 256, N), 256, 0, g, t1, t2, o.par, rank, c->d_err + 1);
+    // measure.label(inst.copy()) on both maps (inst_metrics.py:12-13): equal-value, 8-connected, background 0
+    const long long warps = (long long)g.SEG * ((g.H + EQ_BAND - 1) / EQ_BAND);
+    const dim3 eg((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N);
+    BitPlanesW pwp = {pw.F + words, pw.C + words, pw.EU + words, pw.EL + words, pw.ER + words};
+    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_gt, pw);
+    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_pred, pwp);
+    const BitPlanes p = as_const(pw);
+    Geom g2 = make_geom(2 * N, g.H, g.W);                  // both maps as one batch: gt tiles, then pred tiles
+    TISEG_TRY(bitccl_build(c, g2, p, 2, par, lbits, fbits));
+    TISEG_TRY(rank_from_bits(c, g2, fbits, rank, ng));     // counts: ng[0..N) then np[0..N)
+    TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 1);
+    const dim3 wgrid((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_pair_bits<false>, wgrid, TISEG_THREADS, 0, g, p, par, rank, s, t, c->d_err + 1);
+    // a pathological input overflowed the small table: clear the always-sufficient one and redo (idle otherwise)
+    TISEG_LAUNCH(c, k_pair_zero_big, c->sm_count * 8, TISEG_THREADS, 0, t, t, N);
+    TISEG_LAUNCH(c, k_pair_bits<true>, wgrid, TISEG_THREADS, 0, g, p, par, rank, s, t, c->d_err + 1);
     if (roots) *roots = PairRoots{nullptr, rank, nullptr, rank + total, fbits, fbits + words};
     return TISEG_OK;
 }
