@@ -51,6 +51,13 @@ inline int bitplanes_alloc(tiseg_ctx* c, const Geom& g, int maps, BitPlanesW& p)
 }
 
 #ifdef __CUDACC__
+// read-only find (the forest is final: no concurrent unions)
+__device__ __forceinline__ int find_ro(const int* __restrict__ par, int x) {
+    int q = par[x];
+    while (q != x) { x = q; q = par[x]; }
+    return x;
+}
+
 struct Masks { unsigned f, c, eu, el, er; };
 
 // the five masks of word (y, seg) of tile-batch entry `n` (wo = n * H * SEG), as the image defines them (not cut at
@@ -100,7 +107,7 @@ __device__ __forceinline__ int bit_node_of(const BitPlanes& p, const Geom& g, lo
 // registers, so every pixel is loaded once (plus the two strip-edge columns); five ballots per row, lane k stores plane k.
 #define EQ_BAND 32
 #define EQ_UNROLL 8
-__global__ void __launch_bounds__(TISEG_THREADS)
+static __global__ void __launch_bounds__(TISEG_THREADS)
 k_eqbits_i32(Geom g, const int32_t* __restrict__ img, BitPlanesW out) {
     const int lane = threadIdx.x & 31;
     const int bands = (g.H + EQ_BAND - 1) / EQ_BAND;
@@ -267,7 +274,7 @@ k_bitccl_border(Geom g, BitPlanes p, int* par) {
 }
 
 // local roots -> final roots (path compression on the way); fbits = bitmap of the final roots
-__global__ void __launch_bounds__(TISEG_THREADS)
+static __global__ void __launch_bounds__(TISEG_THREADS)
 k_bitccl_resolve(Geom g, int* par, const unsigned* __restrict__ lbits, unsigned* __restrict__ fbits) {
     const long long words = (long long)g.H * g.SEG;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -15,21 +15,40 @@
 
 namespace tiseg {
 
+// level image + the F plane of the mask b = (I < 255): one warp = 128 pixels of a row, four per thread
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_dist_prep(long long total, const float* __restrict__ dist, uint8_t* __restrict__ I, bool vec) {
-    const long long i = flat4_index();
-    if (i >= total) return;
-    Pack4<float> d = ld4(dist, i, total, vec);
-    Pack4<uint8_t> o;
+k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, unsigned* __restrict__ F, bool vec) {
+    Quad q;
+    if (!warp_quad(g, q)) return;
+    const long long ro = q.base + (long long)q.y * g.W + q.x;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && q.x + 3 < g.W) { const float4 t = *reinterpret_cast<const float4*>(dist + ro); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (q.x + k < g.W) d[k] = dist[ro + k];
+    }
+    unsigned pack = 0, nib = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float v = d.v[k];
+        float v = d[k];
         if (v > 255.f) v = 255.f;      // dist.py:277-278 (comparisons are false for NaN, like numpy)
         if (v < 0.f) v = 0.f;
-        int t = (int)v;                // astype('int32'): truncation
-        o.v[k] = (uint8_t)(255 - (t & 255));
+        const int t = (int)v;          // astype('int32'): truncation
+        const unsigned lv = (unsigned)(255 - (t & 255)) & 255u;
+        pack |= lv << (8 * k);
+        if (q.x + k < g.W && lv < 255u) nib |= 1u << k;
     }
-    st4(I, i, total, vec, o);
+    if (vec && q.x + 3 < g.W) *reinterpret_cast<unsigned*>(I + ro) = pack;
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (q.x + k < g.W) I[ro + k] = (uint8_t)(pack >> (8 * k));
+    }
+    unsigned word = nib << ((q.lane & 7) * 4);
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    const int seg = q.x >> 5;
+    if ((q.lane & 7) == 0 && seg < g.SEG) F[((long long)q.n * g.H + q.y) * g.SEG + seg] = word;
 }
 
 // Regional-minimum plateaus without labelling every plateau of the image.  A pixel is a CANDIDATE if its value is
@@ -51,9 +70,9 @@ __device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ row, int
 // segment (bits[n, y, seg]) and touches `par` / `low` only at the first pixel of each in-word run of candidates (the
 // nodes of the union-find).  Adjacent candidates always carry the same level (the higher one would have a lower
 // neighbour), so the labelling is binary.
-//   k_plateau_bits         candidate bitmap + bitmap of the candidates that touch an equal-valued non-candidate; nodes
-//   k_bitccl_link          one thread per non-empty word: unions with the word to the left and the three words above
-//   k_bitccl_flatten       nodes point at their root; bitmap of the roots; low[root] = 1 for plateaus with a bad pixel
+//   k_plateau_bits         candidate bitmap + bitmap of the candidates that touch an equal-valued non-candidate
+//   bitccl_build           8-connected components of the candidate bitmap (bitccl.cuh: union-find over runs)
+//   k_plateau_low          low[root] = 1 for plateaus with a bad pixel; k_filter_root_bits drops them from the roots
 //   k_marker_scatter       the seed map (rank of the plateau's root on its pixels; zero elsewhere by memset)
 __device__ __forceinline__ int run_len_from(unsigned w, int a) {       // length of the run of ones starting at bit a
     const unsigned x = w >> a;
@@ -169,74 +188,25 @@ k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbi
     }
 }
 
+// a plateau with a pixel that touches an equal-valued non-candidate is not a regional minimum: low[root] = 1
 __global__ void __launch_bounds__(TISEG_THREADS)
-k_bitccl_link(Geom g, const unsigned* __restrict__ bits, int* par) {
+k_plateau_low(Geom g, BitPlanes p, const unsigned* __restrict__ badbits, const int* __restrict__ par, uint8_t* low) {
     const long long words = (long long)g.H * g.SEG;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= words) return;
     const int n = blockIdx.y;
-    const unsigned* B = bits + (long long)n * words;
-    const unsigned w = B[t];
-    if (!w) return;
+    const unsigned bad = badbits[(long long)n * words + t];
+    if (!bad) return;
+    const unsigned w = p.F[(long long)n * words + t];
     const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-    int* tp = par + (long long)n * g.P;
-    const int idx0 = y * g.W + seg * 32;
-    const unsigned lw = seg > 0 ? B[t - 1] : 0u;
-    unsigned up = 0, upl = 0, upr = 0;
-    if (y > 0) {
-        up = B[t - g.SEG];
-        if (seg > 0) upl = B[t - g.SEG - 1];
-        if (seg + 1 < g.SEG) upr = B[t - g.SEG + 1];
+    const long long base = (long long)n * g.P;
+    for (unsigned m = w & ~(w << 1); m; m &= m - 1) {           // run pieces of this word
+        const int a = __ffs(m) - 1, len = run_len_from(w, a);
+        const unsigned runmask = len == 32 ? 0xffffffffu : (((1u << len) - 1u) << a);
+        if (!(bad & runmask)) continue;
+        const int r = find_ro(par + base, bit_node_of(p, g, (long long)n * words, y, seg * 32 + a));
+        if (!low[base + r]) low[base + r] = 1;
     }
-    const int up0 = idx0 - g.W;
-    unsigned m = w;
-    while (m) {
-        const int a = __ffs(m) - 1, len = run_len_from(m, a), b = a + len - 1;
-        m = len == 32 ? 0u : m & ~(((1u << len) - 1u) << a);
-        const int node = idx0 + a;
-        if (a == 0 && (lw >> 31)) uf_union(tp, node, idx0 - 32 + run_start_of(lw, 31));
-        if (y == 0) continue;
-        if (a == 0 && (upl >> 31)) uf_union(tp, node, up0 - 32 + run_start_of(upl, 31));
-        if (b == 31 && (upr & 1u)) uf_union(tp, node, up0 + 32);
-        const int lo = a > 0 ? a - 1 : 0, hi = b < 31 ? b + 1 : 31;
-        const unsigned range = (hi - lo == 31) ? 0xffffffffu : (((1u << (hi - lo + 1)) - 1u) << lo);
-        unsigned um = up & range;
-        while (um) {
-            const int q = __ffs(um) - 1;
-            const int st = run_start_of(up, q), ul = run_len_from(up, st);
-            um = ul == 32 ? 0u : um & ~(((1u << ul) - 1u) << st);
-            uf_union(tp, node, up0 + st);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_bitccl_flatten(Geom g, const unsigned* __restrict__ bits, const unsigned* __restrict__ badbits, int* par, uint8_t* low,
-                 unsigned* __restrict__ rootbits) {
-    const long long words = (long long)g.H * g.SEG;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= words) return;
-    const int n = blockIdx.y;
-    const unsigned w = bits[(long long)n * words + t];
-    unsigned rb = 0;
-    if (w) {
-        const unsigned bad = badbits[(long long)n * words + t];
-        const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-        int* tp = par + (long long)n * g.P;
-        const int idx0 = y * g.W + seg * 32;
-        unsigned starts = w & ~(w << 1);
-        while (starts) {
-            const int a = __ffs(starts) - 1;
-            starts &= starts - 1;
-            const int r = uf_find(tp, idx0 + a);
-            if (r == idx0 + a) rb |= 1u << a; else tp[idx0 + a] = r;
-            const int len = run_len_from(w, a);
-            const unsigned runmask = len == 32 ? 0xffffffffu : (((1u << len) - 1u) << a);
-            // a plateau with a pixel that touches an equal-valued non-candidate is not a regional minimum
-            if ((bad & runmask) && !low[(long long)n * g.P + r]) low[(long long)n * g.P + r] = 1;
-        }
-    }
-    rootbits[(long long)n * words + t] = rb;
 }
 
 // seeds: rank of the plateau's root on the pixels of every run of a minimum plateau (the map is zeroed beforehand)
@@ -255,7 +225,8 @@ k_marker_scatter(Geom g, const unsigned* __restrict__ bits, const int* __restric
     while (w) {
         const int a = __ffs(w) - 1, len = run_len_from(w, a);
         w = len == 32 ? 0u : w & ~(((1u << len) - 1u) << a);
-        const int root = par[base + idx0 + a];
+        const int root = find_ro(par + base, bit_node_of(BitPlanes{bits, nullptr, nullptr, nullptr, nullptr}, g, (long long)n * words, y,
+                                                           seg * 32 + a));
         if (low[base + root]) continue;
         const int id = rank[base + root];
         for (int k = 0; k < len; ++k) markers[base + idx0 + a + k] = id;
@@ -439,6 +410,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
                       int32_t* ws_out) {
     int N = g.N, KS = g.P + 1;
     size_t total = (size_t)N * g.P;
+    const size_t nwords = (size_t)N * g.H * g.SEG;
     uint8_t* I0 = ws<uint8_t>(c, total);
     uint8_t* I = I0;
     uint8_t* low = ws<uint8_t>(c, total);
@@ -454,12 +426,18 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     int* hist = ws<int>(c, (size_t)N * KS);
     int* first = ws<int>(c, (size_t)N * KS);
     int* lut = ws<int>(c, (size_t)N * KS);
-    unsigned* fbits = ws<unsigned>(c, (size_t)N * g.H * g.SEG);
+    unsigned* fbits = ws<unsigned>(c, nwords);
+    unsigned* mbits = ws<unsigned>(c, nwords);           // F plane of the mask b = (I0 < 255)
+    unsigned* cbits = ws<unsigned>(c, nwords);
+    unsigned* rbits = ws<unsigned>(c, nwords);
+    unsigned* bbits = ws<unsigned>(c, nwords);
+    unsigned* lbits = ws<unsigned>(c, nwords);
     if (!I0 || !low || !par || !rank || !bpar || !brank || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
-        !first || !lut || !fbits) return TISEG_ERR_CUDA;
+        !first || !lut || !fbits || !mbits || !cbits || !rbits || !bbits || !lbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
 
-    TISEG_LAUNCH(c, k_dist_prep, flat4_grid((long long)total), TISEG_THREADS, 0, (long long)total, dist, I0, aligned16(dist) && (((uintptr_t)I0) & 3) == 0);
+    TISEG_LAUNCH(c, k_dist_prep, quad_grid(g), TISEG_THREADS, 0, g, dist, I0, mbits,
+                 (g.W % 4 == 0) && aligned16(dist) && (((uintptr_t)I0) & 3) == 0);
     // Hrecons (dist.py:120): the identity for the lambda = 0.0 the reference hard-codes (dist.py:281); a real
     // H-minima reconstruction otherwise.  Markers and flood levels come from it, the mask b from the image itself.
     if (lamb > 0) {
@@ -468,13 +446,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         TISEG_TRY(h_reconstruction_erosion_dev(c, g, I0, lamb, I));
     }
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
-    const size_t nwords = (size_t)N * g.H * g.SEG;
     const dim3 word_grid((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
-    unsigned* cbits = ws<unsigned>(c, nwords);
-    unsigned* rbits = ws<unsigned>(c, nwords);
-    if (!cbits || !rbits) return TISEG_ERR_CUDA;
-    unsigned* bbits = ws<unsigned>(c, nwords);
-    if (!bbits) return TISEG_ERR_CUDA;
     {
         static int PB_ROWS = 0;                  // rows per warp band (multiple of 4); TISEG_PB_ROWS for experiments
         if (!PB_ROWS) { const char* e = getenv("TISEG_PB_ROWS"); PB_ROWS = e ? atoi(e) : 32; if (PB_ROWS < 4 || PB_ROWS % 4) PB_ROWS = 32; }
@@ -482,18 +454,23 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         TISEG_LAUNCH(c, k_plateau_bits, dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N),
                      TISEG_THREADS, 0, g, I, cbits, bbits, par, low, (g.W % 4 == 0) && (((uintptr_t)I) & 3) == 0, PB_ROWS);
     }
-    TISEG_LAUNCH(c, k_bitccl_link, word_grid, TISEG_THREADS, 0, g, cbits, par);
-    TISEG_LAUNCH(c, k_bitccl_flatten, word_grid, TISEG_THREADS, 0, g, cbits, bbits, par, low, rbits);
+    const BitPlanes cand = {cbits, nullptr, nullptr, nullptr, nullptr};
+    TISEG_TRY(bitccl_build(c, g, cand, 2, par, lbits, rbits));
+    TISEG_LAUNCH(c, k_plateau_low, word_grid, TISEG_THREADS, 0, g, cand, bbits, par, low);
     TISEG_LAUNCH(c, k_filter_root_bits, word_grid, TISEG_THREADS, 0, g, low, rbits);
     TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
     // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
     TISEG_TRY(zero(c, wsl, total * sizeof(int32_t)));
     TISEG_LAUNCH(c, k_marker_scatter, word_grid, TISEG_THREADS, 0, g, cbits, par, low, rank, wsl);
     if (markers_out) TISEG_CHECK(cudaMemcpyAsync(markers_out, wsl, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
-    // flood inside b, blob by blob
+    // blobs of b from its bit plane; blobs with one marker are filled, the others flooded in the (value, age) order
+    const BitPlanes mask = {mbits, nullptr, nullptr, nullptr, nullptr};
     BlobInfo b;
-    TISEG_TRY(blobs_build(c, g, ImgBelowU8{I0, 255}, bpar, brank, b, false));
-    TISEG_TRY(watershed_u8_dev(c, g, I, bpar, brank, b, wsl));
+    TISEG_TRY(blobs_from_planes(c, g, mask, cbits, wsl, bpar, brank, b));
+    BlobMember bm;
+    bm.par = bpar; bm.mask_img = I0; bm.planes = mask;
+    TISEG_TRY(watershed_u8_masked_dev(c, g, I, bm, b, wsl));
+    TISEG_TRY(blobs_fill_single(c, g, mask, bpar, brank, b, wsl));
     // arrange_label
     TISEG_TRY(zero(c, nflagged, sizeof(int)));
     TISEG_TRY(zero(c, fbits, (size_t)N * g.H * g.SEG * sizeof(unsigned)));

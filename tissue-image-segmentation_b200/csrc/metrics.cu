@@ -181,11 +181,6 @@ k_pair_accumulate_big(Geom g, const int* __restrict__ par_g, const int* __restri
 // of a row on which both labels are constant is delimited with bit operations, the component ids of its two runs are
 // looked up at the run starts, and one set of atomics is posted per piece (areas by id + the (gt, pred) hash table).
 // =====================================================================================================================
-__device__ __forceinline__ int find_ro(const int* __restrict__ par, int x) {
-    int q = par[x];
-    while (q != x) { x = q; q = par[x]; }
-    return x;
-}
 
 // p: planes of 2N tile-batch entries (gt tiles, then pred tiles); par / rank: [2N, P]
 template <bool BIG>

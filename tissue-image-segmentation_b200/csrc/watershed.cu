@@ -15,6 +15,7 @@ __global__ void k_blob_init(BlobInfo b, int W) {
     int k = b.count[n];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= k; i += gridDim.x * blockDim.x) {
         b.root[o + i] = 0; b.ymax[o + i] = -1; b.xmin[o + i] = W; b.xmax[o + i] = -1; b.area[o + i] = 0;
+        if (b.lmin) { b.lmin[o + i] = 0x7fffffff; b.lmax[o + i] = 0; }
     }
 }
 
@@ -80,6 +81,70 @@ __global__ void k_blob_offsets(BlobInfo b) {
         __syncthreads();
         if (threadIdx.x == 255) carry = c0 + incl;
         __syncthreads();
+    }
+}
+
+// ---- blobs from bit planes (DIST) ---------------------------------------------------------------------------------------
+// id of the blob that holds mask pixel (y, x)
+__device__ __forceinline__ int blob_id_at(const BitPlanes& p, const Geom& g, int n, const int* __restrict__ par,
+                                          const int* __restrict__ rank, int y, int x) {
+    const long long base = (long long)n * g.P;
+    return rank[base + find_ro(par + base, bit_node_of(p, g, (long long)n * g.H * g.SEG, y, x))];
+}
+
+// every run piece of marker pixels reports its label to the blob it lies in (marker_bits: bitmap of a superset of the
+// marker pixels, e.g. the minimum candidates; seeds: the marker map, 0 where there is no marker)
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_blob_mark(Geom g, const unsigned* __restrict__ marker_bits, const int32_t* __restrict__ seeds, BitPlanes p,
+            const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    const unsigned w = marker_bits[(long long)n * words + t];
+    if (!w) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    for (unsigned m = w & ~(w << 1); m; m &= m - 1) {          // a piece is 4-connected: one label, one blob
+        const int x = seg * 32 + __ffs(m) - 1;
+        const int lab = seeds[(long long)n * g.P + y * g.W + x];
+        if (lab == 0) continue;
+        const long long o = (long long)n * b.KS + blob_id_at(p, g, n, par, rank, y, x);
+        atomicMin(&b.lmin[o], lab);
+        atomicMax(&b.lmax[o], lab);
+    }
+}
+
+// one thread per word of the mask, one step per run piece.  FILL = false: bounding box + area of the blobs that will be
+// flooded (two or more markers).  FILL = true: the pixels of single-marker blobs take the marker's label.
+template <bool FILL>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_blob_runs(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b, int32_t* __restrict__ out) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int n = blockIdx.y;
+    const unsigned F = p.F[(long long)n * words + t];
+    if (!F) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    for (unsigned m = F & ~(F << 1); m; m &= m - 1) {
+        const int a = __ffs(m) - 1;
+        const unsigned rest = ~F >> a;                        // (bit 0 is clear: a is in the mask)
+        const int len = rest ? __ffs(rest) - 1 : 32 - a;
+        const int x = seg * 32 + a;
+        const long long o = (long long)n * b.KS + blob_id_at(p, g, n, par, rank, y, x);
+        const int lo = b.lmin[o], hi = b.lmax[o];
+        if (!FILL) {
+            if (lo >= hi) continue;
+            atomicMax(&b.ymax[o], y);
+            atomicMin(&b.xmin[o], x);
+            atomicMax(&b.xmax[o], x + len - 1);
+            atomicAdd(&b.area[o], len);
+        } else {
+            if (lo != hi) continue;
+            const int lab = lo;
+            int32_t* dst = out + (long long)n * g.P + (long long)y * g.W + x;
+            for (int k = 0; k < len; ++k) dst[k] = lab;
+        }
     }
 }
 
@@ -155,6 +220,7 @@ __global__ void k_flood_count(BlobInfo b, int W, FloodWork wk, int arena, int sl
     long long ko = (long long)n * b.KS;
     int B = b.count[n];
     for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        if (b.lmin && b.lmin[ko + bid] >= b.lmax[ko + bid]) continue;
         int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
         if (cls >= 0) atomicAdd(&wk.count[cls], 1);
     }
@@ -170,6 +236,7 @@ __global__ void k_flood_scatter(BlobInfo b, int W, FloodWork wk, int arena, int 
     long long ko = (long long)n * b.KS;
     int B = b.count[n];
     for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
+        if (b.lmin && b.lmin[ko + bid] >= b.lmax[ko + bid]) continue;
         int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
         long long item = ((long long)n << 32) | (unsigned)bid;
         if (cls >= 0) wk.items[wk.offset[cls] + atomicAdd(&wk.fill[cls], 1)] = item;
@@ -185,9 +252,25 @@ __device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulh
 // Per-thread by-products (the caller reduces them if it wants them): the range [lmn, lmx] of the seed labels seen and
 // the lowest seed cell — a blob whose seeds all carry ONE label needs no ordered flood at all.
 struct SeedStats { int lmn, lmx, jseed; };
-template <class IT, class LT>
-__device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const IT* __restrict__ I,
-                                                const int* __restrict__ tp, const int32_t* __restrict__ o, int root,
+// membership of a staged cell (see BlobMember in watershed.cuh)
+struct InForest {
+    const int* tp; int root;
+    __device__ __forceinline__ int load(int gi) const { return tp[gi]; }
+    __device__ __forceinline__ bool in(int v) const { return v == root; }
+    __device__ __forceinline__ bool own_seed(int) const { return true; }
+};
+struct InMask {
+    const uint8_t* m; const int* par; BitPlanes planes; long long wo; Geom g; int root;
+    __device__ __forceinline__ int load(int gi) const { return m[gi]; }
+    __device__ __forceinline__ bool in(int v) const { return v < 255; }
+    __device__ __forceinline__ bool own_seed(int gi) const {
+        const int y = gi / g.W;
+        return find_ro(par, bit_node_of(planes, g, wo, y, gi - y * g.W)) == root;
+    }
+};
+template <class IT, class LT, class MB>
+__device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const IT* __restrict__ I, const MB mb,
+                                                const int32_t* __restrict__ o, int root,
                                                 int y0, int x0, int w, int h, unsigned short* lab, LT* lvl) {
     SeedStats st; st.lmn = 0x7fffffff; st.lmx = 0; st.jseed = 0x7fffffff;
     const int wp = w + 2, cells = wp * (h + 2);
@@ -205,15 +288,16 @@ __device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const 
         int tpv[8], ov[8];
         IT iv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { tpv[u] = tp[gi[u]]; iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+        for (int u = 0; u < 8; ++u) { tpv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * nthr + tid;
             if (j < cells) {
-                const bool inblob = in[u] && tpv[u] == root;
-                lab[j] = (unsigned short)(inblob ? (ov[u] != 0 ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
+                const bool inblob = in[u] && mb.in(tpv[u]);
+                const bool seed = inblob && ov[u] != 0 && mb.own_seed(gi[u]);
+                lab[j] = (unsigned short)(inblob ? (seed ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
                 lvl[j] = (LT)iv[u];
-                if (inblob && ov[u] != 0) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
+                if (seed) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
             }
         }
     }
@@ -357,8 +441,9 @@ __device__ __forceinline__ void stage_writeback(int tid, int nthr, int W, int32_
 }
 
 // The same flood in global memory (framed bounding box too large for shared memory); head/tail are int[256].
+template <class MB>
 __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const uint8_t* __restrict__ I,
-                                                  const int* __restrict__ tp, int32_t* o, int* nx, int root, int y0,
+                                                  const MB mb, int32_t* o, int* nx, int root, int y0,
                                                   int y1, int x0, int x1, int* head, int* tail) {
     for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
     __syncwarp();
@@ -370,7 +455,7 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
             int lv = 0;
             if (x <= x1) {
                 int idx = y * W + x;
-                if (tp[idx] == root && o[idx] != 0) { seed = true; lv = I[idx]; }
+                if (mb.in(mb.load(idx)) && o[idx] != 0 && mb.own_seed(idx)) { seed = true; lv = I[idx]; }
             }
             unsigned m = __ballot_sync(FULL, seed);
             while (m) {
@@ -400,15 +485,16 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
             const int y = pix / W, x = pix - y * W;
             const int nb[4] = {pix - W, pix - 1, pix + 1, pix + W};
             const bool ok[4] = {y > 0, x > 0, x + 1 < W, y + 1 < H};
-            int pv[4], ov[4], lv[4];
+            int ov[4], lv[4];
+            bool pin[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                pv[k] = -1; ov[k] = 1; lv[k] = 0;
-                if (ok[k]) { pv[k] = tp[nb[k]]; ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
+                pin[k] = false; ov[k] = 1; lv[k] = 0;
+                if (ok[k]) { pin[k] = mb.in(mb.load(nb[k])); ov[k] = o[nb[k]]; lv[k] = I[nb[k]]; }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (pv[k] >= 0 && ov[k] == 0) {
+                if (pin[k] && ov[k] == 0) {
                     o[nb[k]] = lab_g;
                     nx[nb[k]] = -1;
                     int t = tail[lv[k]];
@@ -429,7 +515,8 @@ template <int SLOTS> struct BucketSlot {    // heads of one level are contiguous
 };
 
 // General path: one blob per CTA at a time, staged by all warps into one WG_CAP-cell slice with all 256 buckets.
-__device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __restrict__ image, const int* __restrict__ par,
+template <bool MASKED>
+__device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __restrict__ image, const BlobMember& bm,
                                               const BlobInfo& b, const long long* list, int count, int* cursor, int* next,
                                               int* gheads, int32_t* out) {
     __shared__ int s_item;
@@ -450,19 +537,25 @@ __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __re
         const int n = (int)(item >> 32), bid = (int)(item & 0xffffffffll);
         const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
         const uint8_t* I = image + base;
-        const int* tp = par + base;
         int32_t* o = out + base;
         const int root = b.root[ko + bid];
         const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
         const int w = x1 - x0 + 1, h = y1 - y0 + 1;
         const long long cells = (long long)(w + 2) * (h + 2);
+        const InForest inf = {bm.par + base, root};
+        const InMask inm = {MASKED ? bm.mask_img + base : nullptr, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
         if (cells > WG_CAP) {         // does not fit: the same flood in global memory, by one lane
-            if (warp == 0) flood_blob_global(lane, W, H, I, tp, o, next + base, root, y0, y1, x0, x1,
-                                             gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+            if (warp == 0) {
+                if (MASKED) flood_blob_global(lane, W, H, I, inm, o, next + base, root, y0, y1, x0, x1,
+                                              gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+                else flood_blob_global(lane, W, H, I, inf, o, next + base, root, y0, y1, x0, x1,
+                                       gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+            }
             continue;
         }
         for (int i = threadIdx.x; i < 256; i += blockDim.x) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
-        stage_copy(threadIdx.x, blockDim.x, W, I, tp, o, root, y0, x0, w, h, lab, lvl);
+        if (MASKED) stage_copy(threadIdx.x, blockDim.x, W, I, inm, o, root, y0, x0, w, h, lab, lvl);
+        else stage_copy(threadIdx.x, blockDim.x, W, I, inf, o, root, y0, x0, w, h, lab, lvl);
         __syncthreads();
         if (warp == 0) {
             int vmin, vmax, vsmin;
@@ -478,17 +571,17 @@ __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __re
 // The flood kernel.  CTAs below `gen_first` start with the general list (the few largest blobs begin at t = 0), every
 // CTA then drains the multi-slot classes from the largest to the smallest (`do_multi`), and finally helps with what
 // is left of the general list.
-template <int WARPS, int ARENA, int SLOTS, bool PROF>
+template <int WARPS, int ARENA, int SLOTS, bool PROF, bool MASKED>
 __global__ void __launch_bounds__(32 * WARPS, 1)
-k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__ par, BlobInfo b, FloodWork wk,
+k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInfo b, FloodWork wk,
               int* next, int* gheads, int32_t* out, int gen_first, int do_multi, long long* prof) {
     constexpr size_t WARP_BYTES = (size_t)ARENA * 4 + (size_t)WM_R * SLOTS * 4;
     if (!do_multi) {       // second launch: what the first one found too wide in levels
-        general_drain(g, image, par, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
+        general_drain<MASKED>(g, image, bm, b, wk.ovf, wk.ngen[1], wk.gcursor + 1, next, gheads, out);
         return;
     }
     const int ngen = wk.ngen[0];
-    if ((int)blockIdx.x < min(gen_first, ngen) && ngen > 0) general_drain(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    if ((int)blockIdx.x < min(gen_first, ngen) && ngen > 0) general_drain<MASKED>(g, image, bm, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
     {
         __syncthreads();
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -531,10 +624,16 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
                     const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     const long long base = (long long)n * g.P;
-                    const SeedStats st = stage_copy(lane, 32, W, image + base, par + base, out + base, root, y0, x0, w, h,
-                                                    lab + s * cap, lvl + s * cap);
-                    __syncwarp();
-                    if (fill_if_single_marker(lane, st, (w + 2) * (h + 2), lab + s * cap)) single |= 1u << s;
+                    if (MASKED) {       // (blobs with a single marker never get here: nothing to short-cut)
+                        const InMask inm = {bm.mask_img + base, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+                        stage_copy(lane, 32, W, image + base, inm, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
+                    } else {
+                        const InForest inf = {bm.par + base, root};
+                        const SeedStats st = stage_copy(lane, 32, W, image + base, inf, out + base, root, y0, x0, w, h,
+                                                        lab + s * cap, lvl + s * cap);
+                        __syncwarp();
+                        if (fill_if_single_marker(lane, st, (w + 2) * (h + 2), lab + s * cap)) single |= 1u << s;
+                    }
                 }
                 __syncwarp();
                 int lmin = WS_LVL_NONE, lmax = -1, smin = WS_LVL_NONE;        // of slot `lane`
@@ -582,7 +681,7 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, const int* __restrict__
             p[0] = t_stage; p[1] = t_flood; p[2] = t_wb; p[3] = clock64() - t_all; p[4] = iters;
         }
     }
-    if (ngen > 0) general_drain(g, image, par, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
+    if (ngen > 0) general_drain<MASKED>(g, image, bm, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
 }
 
 // ---- fp64 values, fast path: per-blob dense ranks + the same bucket flood ---------------------------------------------
@@ -756,7 +855,7 @@ __device__ __forceinline__ void general_drain_ranked(const Geom& g, const unsign
         const int w = b.xmax[ko + bid] - x0 + 1, h = b.ymax[ko + bid] - y0 + 1;
         const int cells = (w + 2) * (h + 2);
         for (int i = threadIdx.x; i < cells; i += blockDim.x) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
-        stage_copy(threadIdx.x, blockDim.x, W, level + base, par + base, out + base, root, y0, x0, w, h, lab, lvl);
+        stage_copy(threadIdx.x, blockDim.x, W, level + base, InForest{par + base, root}, out + base, root, y0, x0, w, h, lab, lvl);
         __syncthreads();
         if (warp == 0) {
             int vmin, vmax, vsmin;
@@ -811,7 +910,7 @@ k_ws_flood_ranked(Geom g, const unsigned short* __restrict__ level, const int* _
                     const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     const long long base = (long long)n * g.P;
-                    const SeedStats st = stage_copy(lane, 32, W, level + base, par + base, out + base, root, y0, x0, w, h,
+                    const SeedStats st = stage_copy(lane, 32, W, level + base, InForest{par + base, root}, out + base, root, y0, x0, w, h,
                                                     lab + s * cap, lvl + s * cap);
                     __syncwarp();
                     if (fill_if_single_marker(lane, st, (w + 2) * (h + 2), lab + s * cap)) single |= 1u << s;
@@ -982,8 +1081,8 @@ static inline int flood_blocks(tiseg_ctx* c, int N) {
     return per_tile;
 }
 
-template <int WARPS, int ARENA, int SLOTS>
-static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const BlobInfo& b,
+template <int WARPS, int ARENA, int SLOTS, bool MASKED>
+static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const BlobMember& par, const BlobInfo& b,
                         FloodWork wk, int* next, int* gheads, int32_t* out, int* ints, bool debug) {
     static_assert(SLOTS <= WS_MAXCLS, "slots");
     constexpr size_t MULTI = (size_t)WARPS * ((size_t)ARENA * 4 + (size_t)WM_R * SLOTS * 4);
@@ -994,8 +1093,8 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
     static bool attr_set = false;
     if (!attr_set) {
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, false, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, true, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     const int gen_first = c->sm_count >= 8 ? c->sm_count / 4 : 1;     // at most this many CTAs, one per listed blob
@@ -1003,14 +1102,14 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     if (debug) {
         prof = ws<long long>(c, (size_t)c->sm_count * WARPS * 5);
         if (!prof) return TISEG_ERR_CUDA;
-        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, true>), c->sm_count, 32 * WARPS, SMEM, g,
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, true, MASKED>), c->sm_count, 32 * WARPS, SMEM, g,
                         image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     } else {
-        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false>), c->sm_count, 32 * WARPS, SMEM, g,
+        TISEG_LAUNCH_AS(c, "k_ws_flood_u8", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false, MASKED>), c->sm_count, 32 * WARPS, SMEM, g,
                         image, par, b, wk, next, gheads, out, gen_first, 1, prof);
     }
     // blobs found too wide in levels after the other CTAs had left the general list; exits at once if there are none
-    TISEG_LAUNCH_AS(c, "k_ws_flood_u8(level-span overflow)", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false>), c->sm_count,
+    TISEG_LAUNCH_AS(c, "k_ws_flood_u8(level-span overflow)", (k_ws_flood_u8<WARPS, ARENA, SLOTS, false, MASKED>), c->sm_count,
                     32 * WARPS, SMEM, g, image, par, b, wk, next, gheads, out, 0, 0, nullptr);
     if (debug) {                                  // work-list census on stderr (synchronises; diagnostics only)
         int h[WK_INTS];
@@ -1030,9 +1129,8 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     return TISEG_OK;
 }
 
-int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
-                     const BlobInfo& b, int32_t* out) {
-    (void)rank;
+template <bool MASKED>
+static int watershed_u8_any(tiseg_ctx* c, const Geom& g, const uint8_t* image, const BlobMember& bm, const BlobInfo& b, int32_t* out) {
     const int N = g.N;
     const size_t max_blobs = (size_t)N * ((size_t)g.P / 2 + 1);      // a checkerboard is the worst case
     FloodWork wk;
@@ -1049,12 +1147,52 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
     switch (variant) {            // arena geometries kept for tuning on other blob-size distributions
-        case 1: return flood_launch<13, 3840, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 2: return flood_launch<12, 4096, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 3: return flood_launch<10, 5120, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        case 4: return flood_launch<12, 4224, 12>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
-        default: return flood_launch<12, 4224, 16>(c, g, image, par, b, wk, next, gheads, out, ints, debug);
+        case 1: return flood_launch<13, 3840, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
+        case 2: return flood_launch<12, 4096, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
+        case 3: return flood_launch<10, 5120, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
+        case 4: return flood_launch<12, 4224, 12, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
+        default: return flood_launch<12, 4224, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
     }
+}
+
+int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
+                     const BlobInfo& b, int32_t* out) {
+    (void)rank;
+    BlobMember bm;
+    bm.par = par; bm.mask_img = nullptr; bm.planes = BitPlanes{nullptr, nullptr, nullptr, nullptr, nullptr};
+    return watershed_u8_any<false>(c, g, image, bm, b, out);
+}
+
+int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const BlobMember& bm, const BlobInfo& b, int32_t* out) {
+    return watershed_u8_any<true>(c, g, image, bm, b, out);
+}
+
+int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
+                      int* par, int* rank, BlobInfo& b) {
+    const int N = g.N, KS = g.P + 1;
+    const size_t ks = (size_t)N * KS, words = (size_t)N * g.H * g.SEG;
+    int* count = ws<int>(c, (size_t)N);
+    b.root = ws<int>(c, ks); b.ymax = ws<int>(c, ks); b.xmin = ws<int>(c, ks); b.xmax = ws<int>(c, ks);
+    b.area = ws<int>(c, ks); b.off = nullptr; b.lmin = ws<int>(c, ks); b.lmax = ws<int>(c, ks);
+    b.KS = KS; b.count = count;
+    unsigned* lbits = ws<unsigned>(c, words);
+    unsigned* fbits = ws<unsigned>(c, words);
+    if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || !b.lmin || !b.lmax || !lbits || !fbits) return TISEG_ERR_CUDA;
+    TISEG_TRY(bitccl_build(c, g, planes, 1, par, lbits, fbits));           // 4-connected components of the mask
+    TISEG_TRY(rank_from_bits(c, g, fbits, rank, count));
+    const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
+    TISEG_LAUNCH(c, k_blob_init, dim3(8, N), 256, 0, b, g.W);
+    TISEG_LAUNCH(c, k_blob_roots, wg, TISEG_THREADS, 0, g, fbits, rank, b);
+    TISEG_LAUNCH(c, k_blob_mark, wg, TISEG_THREADS, 0, g, marker_bits, seeds, planes, par, rank, b);
+    TISEG_LAUNCH(c, k_blob_runs<false>, wg, TISEG_THREADS, 0, g, planes, par, rank, b, (int32_t*)nullptr);
+    return TISEG_OK;
+}
+
+int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
+                      int32_t* out) {
+    const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
+    TISEG_LAUNCH(c, k_blob_runs<true>, wg, TISEG_THREADS, 0, g, planes, par, rank, b, out);
+    return TISEG_OK;
 }
 
 int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,

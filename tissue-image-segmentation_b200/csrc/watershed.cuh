@@ -14,6 +14,7 @@
 //   fp64 images (HoVer):   per-blob binary heap keyed (value, age) in a global arena slice sized by the
 //                          blob's area.
 #pragma once
+#include "bitccl.cuh"
 #include "ccl.cuh"
 
 namespace tiseg {
@@ -27,6 +28,24 @@ struct BlobInfo {
     int* off;    // [N, KS] exclusive prefix of areas (fp64 heap slices)
     const int* count;  // [N] number of blobs
     int KS;
+    // run-based blobs (DIST): smallest and largest marker label seen on the blob's pixels; NULL on the forest path.
+    // A blob whose seeds all carry ONE label (lmin == lmax) is simply filled with it and never enters the flood; the
+    // flood's work lists only take blobs with lmin < lmax.  (Counted over the marker PIXELS, not the marker roots: a
+    // marker plateau is 8-connected and can reach into a second 4-connected blob through a diagonal.)
+    int* lmin;   // [N, KS]
+    int* lmax;   // [N, KS]
+};
+
+// How the flood decides which cells of a staged bounding box belong to the blob.
+//   forest: a flattened per-pixel forest of the mask (tiseg_watershed_*, HoVer-Net): in the blob <=> tp[pixel] == root.
+//   mask:   no per-pixel forest exists (DIST, blobs from bit planes).  Every in-mask cell of the box is staged; cells of
+//           OTHER blobs are never reached (blobs are 4-connected components and the flood moves by 4-neighbours), stay
+//           unlabelled and are not written back.  Only the seeds must be the blob's own: a seed candidate is looked up
+//           in the run forest (a handful of cells per blob).
+struct BlobMember {
+    const int* par;           // forest mode: flattened per-pixel forest; mask mode: run forest (par at run starts)
+    const uint8_t* mask_img;  // mask mode: pixel is in the mask <=> mask_img[pixel] < 255; NULL selects forest mode
+    BitPlanes planes;         // mask mode: planes of the mask (F only)
 };
 
 // mask functor -> flattened blob forest `par`, blob ids `rank` (at roots), BlobInfo
@@ -36,6 +55,15 @@ int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, 
 
 int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const int* par, const int* rank,
                      const BlobInfo& b, int32_t* out);
+// the same flood with blobs described by bit planes + run forest (mask mode of BlobMember)
+int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const BlobMember& mb, const BlobInfo& b, int32_t* out);
+// blob table from the planes of the mask: forest over runs, ids, root, marker label range and bounding boxes of the blobs
+// that hold two or more marker labels.  seeds: the marker map (0 = no marker).
+int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
+                      int* par, int* rank, BlobInfo& b);
+// single-marker blobs: every pixel takes the marker's label (after the flood of the others)
+int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
+                      int32_t* out);
 int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,
                       const BlobInfo& b, int32_t* out);
 
@@ -55,7 +83,7 @@ int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, 
     int* count = ws<int>(c, (size_t)N);
     b.root = ws<int>(c, ks); b.ymax = ws<int>(c, ks); b.xmin = ws<int>(c, ks); b.xmax = ws<int>(c, ks);
     b.area = ws<int>(c, ks); b.off = want_offsets ? ws<int>(c, ks) : nullptr;
-    b.KS = KS; b.count = count;
+    b.KS = KS; b.count = count; b.lmin = nullptr; b.lmax = nullptr;
     if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || (want_offsets && !b.off)) return TISEG_ERR_CUDA;
     TISEG_TRY(ccl_build(c, g, mask, conn, par));
     const unsigned* root_bits = (const unsigned*)c->rootblk;      // left by the flatten; rank_roots consumes the same bitmap
