@@ -684,6 +684,346 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInfo
     if (ngen > 0) general_drain<MASKED>(g, image, bm, b, wk.gen, ngen, wk.gcursor, next, gheads, out);
 }
 
+// ---- uint8 levels, warp-cooperative flood ---------------------------------------------------------------------------------
+// The lane-per-blob flood above advances one pixel per ~500 cycles and blob, so a cluster of touching nuclei (a blob of
+// 2-3 thousand pixels) alone lasts as long as the whole kernel (profiles/r2_flood_debug.txt: mean 0.73 M cycles per
+// warp, max 1.04 M).  Here ONE WARP floods one blob and pops up to 32 pixels of the current level per step, with exactly
+// the sequential result:
+//   * queues are ARRAYS: every cell is pushed at most once, so level v never receives more entries than the blob has
+//     cells of level v; the staging pass counts them and the queue storage is cut into one segment per level.  The
+//     first B <= 32 entries e_0 .. e_{B-1} of the current level are read by lanes 0 .. B-1.
+//   * a cell is packed into one 32-bit word, state << 16 | level (state: NOTIN, UNLAB or the cell index of the seed whose
+//     label it inherits).  Lane i claims each unlabelled neighbour k with atomicMin(cell, (4 i + k) << 16 | level): the
+//     sequential flood would have given the cell to the first entry in queue order, and to its first neighbour slot, that
+//     reaches it — the smallest key.  After a warp barrier the winners are the claims that read their own key back.
+//   * pushes enter the queue of their level in (i, k) order: per target level a ballot prefix gives every winner its slot.
+//   * if a winner's cell lies BELOW the current level, the sequential flood leaves the current level right after that
+//     entry: the step is cut after the first such lane i* (lanes above it put their claims back and stay in the queue),
+//     and the flood continues at the lowest new level.
+// Cost per step ~ a few hundred cycles whether 1 or 32 pixels are popped, so long queues (big blobs) run ~20x faster and
+// short ones no slower.
+// Every phase of a blob (staging, queue set-up, flood steps, write-back) is a chain of memory latencies, so the SM wants
+// as many blobs in flight as shared memory allows: 4 warps own a big arena (the largest size classes), 12 warps a small
+// one (a third of it: size classes >= 2, most blobs).
+#define WP_WARPS 16
+#define WP_BIG_WARPS 4
+#define WP_ARENA 4224                                   // cells of a big warp arena (4 B cell + 2 B queue slot)
+#define WP_SMALL_ARENA (WP_ARENA / 3)                   // cells of a small one: size classes >= 2
+#define WP_SMALL_CLS 2
+#define WP_META_BYTES (256 * 2 * 2 + 128 * 4)           // head, tail (u16 x 256 each), level counts (u16 x 256)
+#define WP_GEN_CAP (WP_ARENA * WP_BIG_WARPS + WP_SMALL_ARENA * (WP_WARPS - WP_BIG_WARPS))     // cells of the CTA-wide slice
+#define WP_SMEM_BYTES ((size_t)WP_GEN_CAP * 6 + (size_t)WP_META_BYTES * WP_WARPS)
+#define WPC_NOTIN 0xFFFFu
+#define WPC_UNLAB 0xFFFEu
+
+template <class MB>
+__device__ __forceinline__ SeedStats wp_stage(int tid, int nthr, int W, const uint8_t* __restrict__ I, const MB mb,
+                                              const int32_t* __restrict__ o, int root, int y0, int x0, int w, int h,
+                                              unsigned* cell, unsigned* cnt32) {
+    SeedStats st; st.lmn = 0x7fffffff; st.lmx = 0; st.jseed = 0x7fffffff;
+    const int wp = w + 2, cells = wp * (h + 2);
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
+    for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
+        int gi[8];
+        bool in[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            const int ly = fdiv(j, magic), lx = j - ly * wp;
+            in[u] = j < cells && ly >= 1 && ly <= h && lx >= 1 && lx <= w;
+            gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
+        }
+        int mv[8], ov[8];
+        unsigned iv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { mv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            if (j < cells) {
+                const bool inblob = in[u] && mb.in(mv[u]);
+                const bool seed = inblob && ov[u] != 0 && mb.own_seed(gi[u]);
+                cell[j] = ((inblob ? (seed ? (unsigned)j : WPC_UNLAB) : WPC_NOTIN) << 16) | iv[u];
+                if (inblob) atomicAdd(&cnt32[iv[u] >> 1], 1u << (16 * (iv[u] & 1u)));
+                if (seed) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
+            }
+        }
+    }
+    return st;
+}
+
+// one warp: queue segments from the level counts, then the seeds in raster order.  Returns the lowest seed level (256 if
+// the blob has no seed).
+__device__ __forceinline__ int wp_prepare(int lane, int cells, const unsigned* cell, unsigned short* Q, unsigned short* head,
+                                          unsigned short* tail, const unsigned* cnt32) {
+    // exclusive prefix of the 256 counts: lane l owns levels 8 l .. 8 l + 7
+    int c[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned t = cnt32[lane * 4 + k];
+        c[2 * k] = (int)(t & 0xffffu); c[2 * k + 1] = (int)(t >> 16);
+        tot += c[2 * k] + c[2 * k + 1];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    int off = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { head[lane * 8 + k] = (unsigned short)off; tail[lane * 8 + k] = (unsigned short)off; off += c[k]; }
+    __syncwarp();
+    int smin = 256;
+    for (int j0 = 0; j0 < cells; j0 += 32) {
+        const int j = j0 + lane;
+        const unsigned cw = j < cells ? cell[j] : (WPC_NOTIN << 16);
+        const bool seed = (cw >> 16) == (unsigned)j;
+        if (!__ballot_sync(FULL, seed)) continue;
+        const int v = (int)(cw & 0xffffu);
+        const unsigned peers = __match_any_sync(FULL, seed ? v : (0x100 | lane));
+        if (seed) {
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int t = tail[v];                                   // (every peer reads the same value)
+            Q[t + rank] = (unsigned short)j;
+            smin = min(smin, v);
+            __syncwarp(peers);
+            if (lane == leader) tail[v] = (unsigned short)(t + __popc(peers));
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) smin = min(smin, __shfl_xor_sync(FULL, smin, d));
+    return smin;
+}
+
+__device__ __forceinline__ void wp_flood(int lane, int wp, unsigned* cell, unsigned short* Q, unsigned short* head,
+                                         unsigned short* tail, int cur) {
+    const int offs[4] = {-wp, -1, 1, wp};
+    for (;;) {
+        const int h = head[cur], t = tail[cur];
+        if (h == t) {                                   // next non-empty level (uniform)
+            int nxt = -1;
+            for (int base = cur + 1; base < 256 && nxt < 0; base += 32) {
+                const int l = base + lane;
+                const unsigned m = __ballot_sync(FULL, l < 256 && head[l] != tail[l]);
+                if (m) nxt = base + __ffs(m) - 1;
+            }
+            if (nxt < 0) return;
+            cur = nxt;
+            continue;
+        }
+        const int B = min(t - h, 32);
+        const bool act = lane < B;
+        const int e = act ? (int)Q[h + lane] : 0;
+        const unsigned L = act ? cell[e] >> 16 : 0u;
+        unsigned ck[4];
+        bool want[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ck[k] = act ? cell[e + offs[k]] : (WPC_NOTIN << 16);
+            want[k] = (ck[k] >> 16) == WPC_UNLAB;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (want[k]) atomicMin(&cell[e + offs[k]], ((unsigned)(lane * 4 + k) << 16) | (ck[k] & 0xffffu));
+        __syncwarp();
+        unsigned won = 0;
+        bool desc = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (want[k] && (cell[e + offs[k]] >> 16) == (unsigned)(lane * 4 + k)) {
+                won |= 1u << k;
+                desc |= (int)(ck[k] & 0xffffu) < cur;
+            }
+        const unsigned dm = __ballot_sync(FULL, desc);
+        const int istar = dm ? __ffs(dm) - 1 : B - 1;       // the step ends after the first entry that opens a lower level
+        __syncwarp();                                       // every key has been read back before a label replaces one
+        const bool keep = lane <= istar;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((won >> k) & 1u) cell[e + offs[k]] = ((keep ? L : WPC_UNLAB) << 16) | (ck[k] & 0xffffu);
+        unsigned pend = keep ? won : 0u;
+        int newcur = cur;
+        for (;;) {
+            const unsigned anyp = __ballot_sync(FULL, pend != 0u);
+            if (!anyp) break;
+            const int k0 = __ffs(pend) - 1;                  // (pend == 0: unused)
+            const int myv = pend ? (int)((k0 == 0 ? ck[0] : k0 == 1 ? ck[1] : k0 == 2 ? ck[2] : ck[3]) & 0xffffu) : 0;
+            const int v = __shfl_sync(FULL, myv, __ffs(anyp) - 1);
+            unsigned mine = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (((pend >> k) & 1u) && (int)(ck[k] & 0xffffu) == v) mine |= 1u << k;
+            const unsigned b0 = __ballot_sync(FULL, mine & 1u), b1 = __ballot_sync(FULL, mine & 2u);
+            const unsigned b2 = __ballot_sync(FULL, mine & 4u), b3 = __ballot_sync(FULL, mine & 8u);
+            const unsigned below = (1u << lane) - 1u;
+            const int pre = __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
+            const int tot = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            const int tv = tail[v];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((mine >> k) & 1u) Q[tv + pre + __popc(mine & ((1u << k) - 1u))] = (unsigned short)(e + offs[k]);
+            __syncwarp();
+            if (lane == 0) tail[v] = (unsigned short)(tv + tot);
+            pend &= ~mine;
+            newcur = min(newcur, v);
+            __syncwarp();
+        }
+        if (lane == 0) head[cur] = (unsigned short)(h + istar + 1);
+        __syncwarp();
+        cur = newcur;
+    }
+}
+
+// every labelled cell takes the marker label of its seed pixel
+__device__ __forceinline__ void wp_writeback(int tid, int nthr, int W, int32_t* o, int y0, int x0, int w, int h, const unsigned* cell) {
+    const int wp = w + 2, cells = wp * (h + 2), anchor = y0 * W + x0;
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
+    for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
+        int dst[8], src[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr + tid;
+            dst[u] = -1; src[u] = anchor;
+            if (j < cells) {
+                const unsigned L = cell[j] >> 16;
+                if (L < WPC_UNLAB && L != (unsigned)j) {
+                    const int ly = fdiv(j, magic), lx = j - ly * wp, sy = fdiv((int)L, magic), sx = (int)L - sy * wp;
+                    dst[u] = (y0 + ly - 1) * W + x0 + lx - 1;
+                    src[u] = (y0 + sy - 1) * W + x0 + sx - 1;
+                }
+            }
+        }
+        int val[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) val[u] = o[src[u]];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (dst[u] >= 0) o[dst[u]] = val[u];
+    }
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(32 * WP_WARPS, 1)
+k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInfo b, FloodWork wk, int* next, int* gheads,
+               int32_t* out, long long* prof) {
+    __shared__ int s_item;
+    long long t_gen = 0, t_stage = 0, t_prep = 0, t_flood = 0, t_wb = 0, t0 = 0, t_all = prof ? clock64() : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = g.W, H = g.H;
+    // ---- blobs beyond one warp arena: the whole CTA stages, one warp floods (largest first: they start at t = 0)
+    {
+        unsigned* cell = reinterpret_cast<unsigned*>(ws_smem);
+        unsigned short* Q = reinterpret_cast<unsigned short*>(cell + WP_GEN_CAP);
+        unsigned short* head = reinterpret_cast<unsigned short*>(ws_smem + (size_t)WP_GEN_CAP * 6);
+        unsigned short* tail = head + 256;
+        unsigned* cnt32 = reinterpret_cast<unsigned*>(tail + 256);
+        const int ngen = wk.ngen[0];
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_item = atomicAdd(wk.gcursor, 1);
+            __syncthreads();
+            const int k = s_item;
+            if (k >= ngen) break;
+            const long long item = wk.gen[k];
+            const int n = (int)(item >> 32), bid = (int)(item & 0xffffffffll);
+            const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+            const int root = b.root[ko + bid];
+            const int y0 = root / W, y1 = b.ymax[ko + bid], x0 = b.xmin[ko + bid], x1 = b.xmax[ko + bid];
+            const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+            const long long cells = (long long)(w + 2) * (h + 2);
+            const InForest inf = {bm.par + base, root};
+            const InMask inm = {MASKED ? bm.mask_img + base : nullptr, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+            if (cells > WP_GEN_CAP) {     // does not fit: the sequential flood in global memory, by one lane
+                if (warp == 0) {
+                    if (MASKED) flood_blob_global(lane, W, H, image + base, inm, out + base, next + base, root, y0, y1, x0, x1,
+                                                  gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+                    else flood_blob_global(lane, W, H, image + base, inf, out + base, next + base, root, y0, y1, x0, x1,
+                                           gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+                }
+                continue;
+            }
+            for (int i = threadIdx.x; i < 128; i += blockDim.x) cnt32[i] = 0u;
+            __syncthreads();
+            if (MASKED) wp_stage(threadIdx.x, blockDim.x, W, image + base, inm, out + base, root, y0, x0, w, h, cell, cnt32);
+            else wp_stage(threadIdx.x, blockDim.x, W, image + base, inf, out + base, root, y0, x0, w, h, cell, cnt32);
+            __syncthreads();
+            if (warp == 0) {
+                const int smin = wp_prepare(lane, (int)cells, cell, Q, head, tail, cnt32);
+                if (smin < 256) wp_flood(lane, w + 2, cell, Q, head, tail, smin);
+            }
+            __syncthreads();
+            wp_writeback(threadIdx.x, blockDim.x, W, out + base, y0, x0, w, h, cell);
+        }
+        __syncthreads();
+    }
+    if (prof) t_gen = clock64() - t_all;
+    // ---- one blob per warp, size classes from the largest to the smallest
+    const bool big = warp < WP_BIG_WARPS;
+    const int arena = big ? WP_ARENA : WP_SMALL_ARENA;
+    unsigned char* wbase = ws_smem + (big ? (size_t)warp * WP_ARENA * 6
+                                          : (size_t)WP_BIG_WARPS * WP_ARENA * 6 + (size_t)(warp - WP_BIG_WARPS) * WP_SMALL_ARENA * 6);
+    unsigned* cell = reinterpret_cast<unsigned*>(wbase);
+    unsigned short* Q = reinterpret_cast<unsigned short*>(cell + arena);
+    unsigned short* head = reinterpret_cast<unsigned short*>(ws_smem + (size_t)WP_GEN_CAP * 6 + (size_t)warp * WP_META_BYTES);
+    unsigned short* tail = head + 256;
+    unsigned* cnt32 = reinterpret_cast<unsigned*>(tail + 256);
+    for (int cls = big ? 0 : WP_SMALL_CLS; cls < WS_MAXCLS; ++cls) {
+        const int cnt = wk.count[cls];
+        const long long* list = wk.items + wk.offset[cls];
+        for (;;) {
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&wk.cursor[cls], 1);
+            k = __shfl_sync(FULL, k, 0);
+            if (k >= cnt) break;
+            const long long item = list[k];
+            const int n = (int)(item >> 32), bid = (int)(item & 0xffffffffll);
+            const long long base = (long long)n * g.P, ko = (long long)n * b.KS;
+            const int root = b.root[ko + bid];
+            const int y0 = root / W, x0 = b.xmin[ko + bid];
+            const int w = b.xmax[ko + bid] - x0 + 1, h = b.ymax[ko + bid] - y0 + 1;
+            const int cells = (w + 2) * (h + 2);
+            for (int i = lane; i < 128; i += 32) cnt32[i] = 0u;
+            __syncwarp();
+            if (prof) t0 = clock64();
+            bool flood = true;
+            if (MASKED) {
+                const InMask inm = {bm.mask_img + base, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+                wp_stage(lane, 32, W, image + base, inm, out + base, root, y0, x0, w, h, cell, cnt32);
+            } else {
+                const InForest inf = {bm.par + base, root};
+                SeedStats st = wp_stage(lane, 32, W, image + base, inf, out + base, root, y0, x0, w, h, cell, cnt32);
+                // all seeds carry one label: a 4-connected blob is flooded completely from any seed, nothing to order
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    st.lmn = min(st.lmn, __shfl_xor_sync(FULL, st.lmn, d));
+                    st.lmx = max(st.lmx, __shfl_xor_sync(FULL, st.lmx, d));
+                    st.jseed = min(st.jseed, __shfl_xor_sync(FULL, st.jseed, d));
+                }
+                __syncwarp();
+                if (st.lmx != 0 && st.lmn == st.lmx) {
+                    for (int j = lane; j < cells; j += 32)
+                        if ((cell[j] >> 16) == WPC_UNLAB) cell[j] = ((unsigned)st.jseed << 16) | (cell[j] & 0xffffu);
+                    flood = false;
+                }
+            }
+            __syncwarp();
+            if (prof) { const long long t = clock64(); t_stage += t - t0; t0 = t; }
+            if (flood) {
+                const int smin = wp_prepare(lane, cells, cell, Q, head, tail, cnt32);
+                if (prof) { const long long t = clock64(); t_prep += t - t0; t0 = t; }
+                if (smin < 256) wp_flood(lane, w + 2, cell, Q, head, tail, smin);
+            }
+            __syncwarp();
+            if (prof) { const long long t = clock64(); t_flood += t - t0; t0 = t; }
+            wp_writeback(lane, 32, W, out + base, y0, x0, w, h, cell);
+            __syncwarp();
+            if (prof) t_wb += clock64() - t0;
+        }
+    }
+    if (prof && lane == 0) {
+        long long* p = prof + ((size_t)blockIdx.x * WP_WARPS + warp) * 6;
+        p[0] = t_gen; p[1] = t_stage; p[2] = t_prep; p[3] = t_flood; p[4] = t_wb; p[5] = clock64() - t_all;
+    }
+}
+
 // ---- fp64 values, fast path: per-blob dense ranks + the same bucket flood ---------------------------------------------
 // The (value, age) order of the flood only compares values INSIDE one blob, so the fp64 image can be replaced, blob
 // by blob, by the dense rank of each pixel's value among the blob's distinct values (equal doubles -> equal rank):
@@ -1146,7 +1486,40 @@ static int watershed_u8_any(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
     TISEG_TRY(zero(c, ints, WK_INTS * sizeof(int)));
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
-    switch (variant) {            // arena geometries kept for tuning on other blob-size distributions
+    static const bool sequential = getenv("TISEG_FLOOD_SEQ") != nullptr || debug || variant != 0;
+    if (!sequential) {            // warp-cooperative flood (default)
+        static_assert(WP_SMEM_BYTES + 64 <= 232448, "shared memory");
+        TISEG_LAUNCH(c, k_flood_count, dim3(8, g.N), 256, 0, b, g.W, wk, WP_ARENA, WS_MAXCLS);
+        TISEG_LAUNCH(c, k_flood_offsets, 1, 32, 0, wk);
+        TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, WP_ARENA, WS_MAXCLS);
+        static bool attr_set = false;
+        if (!attr_set) {
+            TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_par<MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM_BYTES));
+            attr_set = true;
+        }
+        static const bool par_prof = getenv("TISEG_PROF_FLOOD") != nullptr;
+        long long* prof = nullptr;
+        if (par_prof) { prof = ws<long long>(c, (size_t)c->sm_count * WP_WARPS * 6); if (!prof) return TISEG_ERR_CUDA; }
+        TISEG_LAUNCH_AS(c, "k_ws_flood_par", (k_ws_flood_par<MASKED>), c->sm_count, 32 * WP_WARPS, WP_SMEM_BYTES, g, image, bm, b,
+                        wk, next, gheads, out, prof);
+        if (par_prof) {                           // diagnostics only (synchronises)
+            int hh[WK_INTS];
+            TISEG_CHECK(cudaMemcpyAsync(hh, ints, sizeof(hh), cudaMemcpyDeviceToHost, c->stream));
+            std::vector<long long> hp((size_t)c->sm_count * WP_WARPS * 6);
+            TISEG_CHECK(cudaMemcpyAsync(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            TISEG_CHECK(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[tiseg flood par] N=%d classes:", g.N);
+            for (int k = 0; k < WS_MAXCLS; ++k) fprintf(stderr, " %d", hh[k]);
+            fprintf(stderr, " | general: %d\n", hh[4 * WS_MAXCLS]);
+            long long sum[6] = {0, 0, 0, 0, 0, 0}, mx[6] = {0, 0, 0, 0, 0, 0};
+            for (size_t i = 0; i < hp.size(); ++i) { sum[i % 6] += hp[i]; if (hp[i] > mx[i % 6]) mx[i % 6] = hp[i]; }
+            const double nw = (double)c->sm_count * WP_WARPS;
+            fprintf(stderr, "[tiseg flood par] per-warp cycles mean (max): general %.0f (%lld) stage %.0f (%lld) prepare %.0f (%lld) flood %.0f (%lld) writeback %.0f (%lld) total %.0f (%lld)\n",
+                    sum[0] / nw, mx[0], sum[1] / nw, mx[1], sum[2] / nw, mx[2], sum[3] / nw, mx[3], sum[4] / nw, mx[4], sum[5] / nw, mx[5]);
+        }
+        return TISEG_OK;
+    }
+    switch (variant) {            // lane-per-blob flood; arena geometries kept for tuning on other blob-size distributions
         case 1: return flood_launch<13, 3840, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
         case 2: return flood_launch<12, 4096, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
         case 3: return flood_launch<10, 5120, 16, MASKED>(c, g, image, bm, b, wk, next, gheads, out, ints, debug);
