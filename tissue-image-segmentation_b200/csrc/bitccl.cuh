@@ -103,60 +103,84 @@ __device__ __forceinline__ int bit_node_of(const BitPlanes& p, const Geom& g, lo
 }
 
 // ---- streaming pass: int32 label map -> planes (equal-value components, background 0) ---------------------------------
-// One warp = one 32-pixel column strip x EQ_BAND rows, walking down: the row above and its two shuffled copies stay in
-// registers, so every pixel is loaded once (plus the two strip-edge columns); five ballots per row, lane k stores plane k.
+// One warp = one 128-pixel column strip x EQ_BAND rows, walking down, four pixels per thread (one 128-bit load per row:
+// the pass is bound by the bytes it keeps in flight, a 4-byte load per lane reached a fifth of the HBM rate).  The row
+// above stays in registers, so every pixel is loaded once (plus the two strip-edge columns); a thread's four compare
+// results per plane form a nibble, eight lanes OR their nibbles into one 32-bit word.
 #define EQ_BAND 32
-#define EQ_UNROLL 8
+#define EQ_UNROLL 4
+__device__ __forceinline__ unsigned eq_nib(bool a, bool b, bool c, bool d) {
+    return (a ? 1u : 0u) | (b ? 2u : 0u) | (c ? 4u : 0u) | (d ? 8u : 0u);
+}
+__device__ __forceinline__ unsigned eq_word(unsigned nib, int lane) {      // valid in lanes 0, 8, 16, 24
+    unsigned w = nib << ((lane & 7) * 4);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    return w;
+}
 static __global__ void __launch_bounds__(TISEG_THREADS)
-k_eqbits_i32(Geom g, const int32_t* __restrict__ img, BitPlanesW out) {
+k_eqbits_i32(Geom g, const int32_t* __restrict__ img, BitPlanesW out, bool vec) {
     const int lane = threadIdx.x & 31;
-    const int bands = (g.H + EQ_BAND - 1) / EQ_BAND;
+    const int bands = (g.H + EQ_BAND - 1) / EQ_BAND, strips = (g.W + 127) >> 7;
     const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (wi >= (long long)g.SEG * bands) return;
-    const int band = (int)(wi / g.SEG), seg = (int)(wi - (long long)band * g.SEG), n = blockIdx.y;
-    const int x = seg * 32 + lane, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
+    if (wi >= (long long)strips * bands) return;
+    const int band = (int)(wi / strips), strip = (int)(wi - (long long)band * strips), n = blockIdx.y;
+    const int x = strip * 128 + lane * 4, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
     const int32_t* t = img + (long long)n * g.P;
-    const bool okx = x < g.W;
+    const bool full = vec && x + 3 < g.W;
     // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
-    const int xe = lane == 0 ? x - 1 : x + 1;
+    const int xe = lane == 0 ? x - 1 : x + 4;
     const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
-    int prev = 0, prevL = 0, prevR = 0;
+    auto load4 = [&](int y, int (&v)[4]) {
+        const int32_t* rp = t + (long long)y * g.W + x;
+        if (full) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = x + k < g.W ? rp[k] : 0;
+        }
+    };
+    int pv[4] = {0, 0, 0, 0}, pvL = 0, pvR = 0;
     if (y0 > 0) {
-        const long long ro = (long long)(y0 - 1) * g.W;
-        prev = okx ? t[ro + x] : 0;
-        const int e = oke ? t[ro + xe] : 0;
-        prevL = __shfl_up_sync(0xffffffffu, prev, 1);
-        prevR = __shfl_down_sync(0xffffffffu, prev, 1);
-        if (lane == 0) prevL = e;
-        if (lane == 31) prevR = e;
+        load4(y0 - 1, pv);
+        const int e = oke ? t[(long long)(y0 - 1) * g.W + xe] : 0;
+        pvL = __shfl_up_sync(0xffffffffu, pv[3], 1);
+        pvR = __shfl_down_sync(0xffffffffu, pv[0], 1);
+        if (lane == 0) pvL = e;
+        if (lane == 31) pvR = e;
     }
-    unsigned* const plane = lane == 0 ? out.F : lane == 1 ? out.C : lane == 2 ? out.EU : lane == 3 ? out.EL : out.ER;
+    const int seg = strip * 4 + (lane >> 3);
+    const bool writer = (lane & 7) == 0 && seg < g.SEG;
     for (int yb = y0; yb < y1; yb += EQ_UNROLL) {
-        int cur[EQ_UNROLL], ext[EQ_UNROLL];
+        int cur[EQ_UNROLL][4], ext[EQ_UNROLL];
 #pragma unroll
         for (int u = 0; u < EQ_UNROLL; ++u) {
             const int y = yb + u;
-            const long long ro = (long long)y * g.W;
-            cur[u] = (okx && y < y1) ? t[ro + x] : 0;
-            ext[u] = (oke && y < y1) ? t[ro + xe] : 0;
+            if (y < y1) { load4(y, cur[u]); ext[u] = oke ? t[(long long)y * g.W + xe] : 0; }
+            else { cur[u][0] = cur[u][1] = cur[u][2] = cur[u][3] = 0; ext[u] = 0; }
         }
 #pragma unroll
         for (int u = 0; u < EQ_UNROLL; ++u) {
             const int y = yb + u;
             if (y >= y1) break;                                  // (uniform)
-            const int v = cur[u];
-            int vL = __shfl_up_sync(0xffffffffu, v, 1), vR = __shfl_down_sync(0xffffffffu, v, 1);
+            const int v0 = cur[u][0], v1 = cur[u][1], v2 = cur[u][2], v3 = cur[u][3];
+            int vL = __shfl_up_sync(0xffffffffu, v3, 1), vR = __shfl_down_sync(0xffffffffu, v0, 1);
             if (lane == 0) vL = ext[u];
             if (lane == 31) vR = ext[u];
-            const bool f = v != 0;
-            const unsigned mF = __ballot_sync(0xffffffffu, f);
-            const unsigned mC = __ballot_sync(0xffffffffu, f && v == vL);
-            const unsigned mU = __ballot_sync(0xffffffffu, f && v == prev);
-            const unsigned mL = __ballot_sync(0xffffffffu, f && v == prevL);
-            const unsigned mR = __ballot_sync(0xffffffffu, f && v == prevR);
-            const unsigned mine = lane == 0 ? mF : lane == 1 ? mC : lane == 2 ? mU : lane == 3 ? mL : mR;
-            if (lane < 5) plane[((long long)n * g.H + y) * g.SEG + seg] = mine;
-            prev = v; prevL = vL; prevR = vR;
+            const bool f0 = v0 != 0, f1 = v1 != 0, f2 = v2 != 0, f3 = v3 != 0;
+            unsigned wF = 0, wC = 0, wU = 0, wL = 0, wR = 0;
+            if (__any_sync(0xffffffffu, f0 | f1 | f2 | f3)) {    // (uniform) rows of background cost two instructions
+                wF = eq_word(eq_nib(f0, f1, f2, f3), lane);
+                wC = eq_word(eq_nib(f0 && v0 == vL, f1 && v1 == v0, f2 && v2 == v1, f3 && v3 == v2), lane);
+                wU = eq_word(eq_nib(f0 && v0 == pv[0], f1 && v1 == pv[1], f2 && v2 == pv[2], f3 && v3 == pv[3]), lane);
+                wL = eq_word(eq_nib(f0 && v0 == pvL, f1 && v1 == pv[0], f2 && v2 == pv[1], f3 && v3 == pv[2]), lane);
+                wR = eq_word(eq_nib(f0 && v0 == pv[1], f1 && v1 == pv[2], f2 && v2 == pv[3], f3 && v3 == pvR), lane);
+            }
+            if (writer) {
+                const long long o = ((long long)n * g.H + y) * g.SEG + seg;
+                out.F[o] = wF; out.C[o] = wC; out.EU[o] = wU; out.EL[o] = wL; out.ER[o] = wR;
+            }
+            pv[0] = v0; pv[1] = v1; pv[2] = v2; pv[3] = v3; pvL = vL; pvR = vR;
         }
     }
 }

@@ -15,40 +15,60 @@
 
 namespace tiseg {
 
-// level image + the F plane of the mask b = (I < 255): one warp = 128 pixels of a row, four per thread
+// level image + the F plane of the mask b = (I < 255): one warp = 128 columns x DP_ROWS rows, four pixels per thread and
+// row, all loads of the thread issued before the first is used
+#define DP_ROWS 4
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, unsigned* __restrict__ F, bool vec) {
-    Quad q;
-    if (!warp_quad(g, q)) return;
-    const long long ro = q.base + (long long)q.y * g.W + q.x;
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec && q.x + 3 < g.W) { const float4 t = *reinterpret_cast<const float4*>(dist + ro); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
-    else {
+    const int lane = threadIdx.x & 31;
+    const int strips = (g.W + 127) >> 7, chunks = (g.H + DP_ROWS - 1) / DP_ROWS;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (wi >= (long long)strips * chunks) return;
+    const int ch = (int)(wi / strips), strip = (int)(wi - (long long)ch * strips), n = blockIdx.y;
+    const int x = strip * 128 + lane * 4, y0 = ch * DP_ROWS;
+    const bool full = vec && x + 3 < g.W;
+    float d[DP_ROWS][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (q.x + k < g.W) d[k] = dist[ro + k];
-    }
-    unsigned pack = 0, nib = 0;
+    for (int r = 0; r < DP_ROWS; ++r) {
+        const int y = y0 + r;
+        const long long ro = (long long)n * g.P + (long long)y * g.W + x;
+        d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
+        if (y < g.H) {
+            if (full) { const float4 t = *reinterpret_cast<const float4*>(dist + ro); d[r][0] = t.x; d[r][1] = t.y; d[r][2] = t.z; d[r][3] = t.w; }
+            else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float v = d[k];
-        if (v > 255.f) v = 255.f;      // dist.py:277-278 (comparisons are false for NaN, like numpy)
-        if (v < 0.f) v = 0.f;
-        const int t = (int)v;          // astype('int32'): truncation
-        const unsigned lv = (unsigned)(255 - (t & 255)) & 255u;
-        pack |= lv << (8 * k);
-        if (q.x + k < g.W && lv < 255u) nib |= 1u << k;
+                for (int k = 0; k < 4; ++k) if (x + k < g.W) d[r][k] = dist[ro + k];
+            }
+        }
     }
-    if (vec && q.x + 3 < g.W) *reinterpret_cast<unsigned*>(I + ro) = pack;
-    else {
+    const int seg = x >> 5;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (q.x + k < g.W) I[ro + k] = (uint8_t)(pack >> (8 * k));
+    for (int r = 0; r < DP_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= g.H) break;                       // (uniform)
+        const long long ro = (long long)n * g.P + (long long)y * g.W + x;
+        unsigned pack = 0, nib = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = d[r][k];
+            if (v > 255.f) v = 255.f;      // dist.py:277-278 (comparisons are false for NaN, like numpy)
+            if (v < 0.f) v = 0.f;
+            const int t = (int)v;          // astype('int32'): truncation
+            const unsigned lv = (unsigned)(255 - (t & 255)) & 255u;
+            pack |= lv << (8 * k);
+            if (x + k < g.W && lv < 255u) nib |= 1u << k;
+        }
+        if (full) *reinterpret_cast<unsigned*>(I + ro) = pack;
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < g.W) I[ro + k] = (uint8_t)(pack >> (8 * k));
+        }
+        unsigned word = nib << ((lane & 7) * 4);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((lane & 7) == 0 && seg < g.SEG) F[((long long)n * g.H + y) * g.SEG + seg] = word;
     }
-    unsigned word = nib << ((q.lane & 7) * 4);
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    word |= __shfl_xor_sync(0xffffffffu, word, 2);
-    word |= __shfl_xor_sync(0xffffffffu, word, 4);
-    const int seg = q.x >> 5;
-    if ((q.lane & 7) == 0 && seg < g.SEG) F[((long long)q.n * g.H + q.y) * g.SEG + seg] = word;
 }
 
 // Regional-minimum plateaus without labelling every plateau of the image.  A pixel is a CANDIDATE if its value is
@@ -436,8 +456,11 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         !first || !lut || !fbits || !mbits || !cbits || !rbits || !bbits || !lbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
 
-    TISEG_LAUNCH(c, k_dist_prep, quad_grid(g), TISEG_THREADS, 0, g, dist, I0, mbits,
-                 (g.W % 4 == 0) && aligned16(dist) && (((uintptr_t)I0) & 3) == 0);
+    {
+        const long long warps = (long long)((g.W + 127) / 128) * ((g.H + DP_ROWS - 1) / DP_ROWS);
+        TISEG_LAUNCH(c, k_dist_prep, dim3((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N),
+                     TISEG_THREADS, 0, g, dist, I0, mbits, (g.W % 4 == 0) && aligned16(dist) && (((uintptr_t)I0) & 3) == 0);
+    }
     // Hrecons (dist.py:120): the identity for the lambda = 0.0 the reference hard-codes (dist.py:281); a real
     // H-minima reconstruction otherwise.  Markers and flood levels come from it, the mask b from the image itself.
     if (lamb > 0) {

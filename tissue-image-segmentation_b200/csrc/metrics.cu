@@ -693,11 +693,11 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
     TISEG_TRY(pair_tab_alloc(c, g, t, overflow));
     TISEG_TRY(zero(c, overflow, sizeof(int)));
     // measure.label(inst.copy()) on both maps (inst_metrics.py:12-13): equal-value, 8-connected, background 0
-    const long long warps = (long long)g.SEG * ((g.H + EQ_BAND - 1) / EQ_BAND);
+    const long long warps = (long long)((g.W + 127) / 128) * ((g.H + EQ_BAND - 1) / EQ_BAND);
     const dim3 eg((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N);
     BitPlanesW pwp = {pw.F + words, pw.C + words, pw.EU + words, pw.EL + words, pw.ER + words};
-    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_gt, pw);
-    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_pred, pwp);
+    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_gt, pw, (g.W % 4 == 0) && aligned16(d_gt));
+    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_pred, pwp, (g.W % 4 == 0) && aligned16(d_pred));
     const BitPlanes p = as_const(pw);
     Geom g2 = make_geom(2 * N, g.H, g.W);                  // both maps as one batch: gt tiles, then pred tiles
     TISEG_TRY(bitccl_build(c, g2, p, 2, par, lbits, fbits));
