@@ -71,6 +71,17 @@ k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, uns
     }
 }
 
+// pixels of the mask per tile (decides below whether the flood labels can outnumber the background)
+__global__ void __launch_bounds__(TISEG_THREADS) k_mask_area(Geom g, const unsigned* __restrict__ F, int* __restrict__ marea) {
+    const long long words = (long long)g.H * g.SEG;
+    const int n = blockIdx.y;
+    int a = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (long long)gridDim.x * blockDim.x)
+        a += __popc(F[(long long)n * words + i]);
+    a = __reduce_add_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&marea[n], a);
+}
+
 // Regional-minimum plateaus without labelling every plateau of the image.  A pixel is a CANDIDATE if its value is
 // below 255 and no 8-neighbour is strictly lower.  A plateau P (maximal 8-connected set of equal values) is a regional
 // minimum iff all its pixels are candidates.  Label the candidates only (equal value, 8-connected): if P is a
@@ -274,19 +285,23 @@ k_filter_root_bits(Geom g, const uint8_t* __restrict__ low, unsigned* bits) {
 
 // histogram of the flood labels (values 0..K) and the first raster pixel of each label, one pair of atomics per
 // in-segment run
+template <bool LISTED>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ws_hist(Geom g, const int32_t* __restrict__ ws, int* hist, int* first, int KS, bool vec) {
     Quad q;
     if (!warp_quad(g, q)) return;
-    int v[4];
-    quad_load_i32(g, q, ws + q.base, 0, vec, v);
-    // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
-    if (!__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) return;
-    const QuadRuns r = quad_runs(v, 0, q.lane);
-    FOR_QUAD_RUNS(r, k, len) {
-        const long long o = (long long)q.n * KS + v[k];
-        atomicAdd(&hist[o], (int)len);
-        atomicMin(&first[o], q.y * g.W + q.x + (int)k);
+    FOR_TILES(LISTED, g, n) {
+        q.n = n; q.base = (long long)n * g.P;
+        int v[4];
+        quad_load_i32(g, q, ws + q.base, 0, vec, v);
+        // label 0 (the background, by far the longest runs) is not counted: its total is P minus the others
+        if (!__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) continue;
+        const QuadRuns r = quad_runs(v, 0, q.lane);
+        FOR_QUAD_RUNS(r, k, len) {
+            const long long o = (long long)q.n * KS + v[k];
+            atomicAdd(&hist[o], (int)len);
+            atomicMin(&first[o], q.y * g.W + q.x + (int)k);
+        }
     }
 }
 
@@ -302,11 +317,22 @@ __global__ void k_init_label_tables(int* hist, int* first, int KS, const int* __
 // arrange_label's background: np.unique(return_counts) + argmax => the most frequent value, smallest value on ties.
 // Tiles whose background is NOT 0 (one flood region larger than everything unlabelled) go on the list of the
 // general relabelling path.
+// A flood label covers at most the mask and the value 0 at least its complement, so with a mask of at most half the tile
+// the background of arrange_label is 0 without counting anything (ties go to the smallest value).  Only denser tiles go on
+// the list of the histogram pass.
+__global__ void k_dense_tiles(const int* __restrict__ marea, int N, int P, int* bg, int* dense, int* ndense) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    bg[n] = 0;
+    if (2ll * marea[n] > (long long)P) dense[atomicAdd(ndense, 1)] = n;
+}
+
 __global__ void k_pick_bg(const int* __restrict__ hist, int KS, const int* __restrict__ counts, int P, int* bg,
-                          int* flagged, int* nflagged) {
+                          int* flagged, int* nflagged, const int* __restrict__ dense, const int* __restrict__ ndense) {
     __shared__ unsigned long long s[256];
     __shared__ long long tot[256];
-    int n = blockIdx.x;
+    if (dense && (int)blockIdx.x >= *ndense) return;
+    int n = dense ? dense[blockIdx.x] : blockIdx.x;
     int k = counts[n];
     // key = (count << 32) | (0xffffffff - value): max key = largest count, then smallest value
     unsigned long long best = 0;
@@ -455,6 +481,11 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     if (!I0 || !low || !par || !rank || !bpar || !brank || !wsl || !arranged || !nmark || !bg || !flagged || !hist ||
         !first || !lut || !fbits || !mbits || !cbits || !rbits || !bbits || !lbits) return TISEG_ERR_CUDA;
     int* nflagged = flagged + N;
+    int* marea = ws<int>(c, 2 * (size_t)N + 2);          // mask pixels per tile; list of the dense tiles + its length
+    if (!marea) return TISEG_ERR_CUDA;
+    int* dense = marea + N;
+    int* ndense = dense + N;
+    TISEG_TRY(zero(c, marea, (2 * (size_t)N + 2) * sizeof(int)));
 
     {
         const long long warps = (long long)((g.W + 127) / 128) * ((g.H + DP_ROWS - 1) / DP_ROWS);
@@ -489,17 +520,28 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     // blobs of b from its bit plane; blobs with one marker are filled, the others flooded in the (value, age) order
     const BitPlanes mask = {mbits, nullptr, nullptr, nullptr, nullptr};
     BlobInfo b;
-    TISEG_TRY(blobs_from_planes(c, g, mask, cbits, wsl, bpar, brank, b));
+    TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);      // first[label] = INT_MAX
+    TISEG_TRY(blobs_from_planes(c, g, mask, cbits, wsl, bpar, brank, first, b));
     BlobMember bm;
     bm.par = bpar; bm.mask_img = I0; bm.planes = mask;
     TISEG_TRY(watershed_u8_masked_dev(c, g, I, bm, b, wsl));
     TISEG_TRY(blobs_fill_single(c, g, mask, bpar, brank, b, wsl));
-    // arrange_label
+    // arrange_label: the first raster pixel of every flood label came with the fill / the flood's write-back; the
+    // background is 0 unless the mask covers more than half of a tile (then the histogram decides, on those tiles only)
+    static const bool seq_flood = getenv("TISEG_FLOOD_SEQ") != nullptr || getenv("TISEG_DEBUG_FLOOD") != nullptr ||
+                                  getenv("TISEG_FLOOD_VARIANT") != nullptr;        // (the lane-per-blob flood keeps no `first`)
     TISEG_TRY(zero(c, nflagged, sizeof(int)));
     TISEG_TRY(zero(c, fbits, (size_t)N * g.H * g.SEG * sizeof(unsigned)));
-    TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);
-    TISEG_LAUNCH(c, k_ws_hist, quad_grid(g), TISEG_THREADS, 0, g, wsl, hist, first, KS, (g.W % 4 == 0) && aligned16(wsl));
-    TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged);
+    if (seq_flood) {
+        TISEG_LAUNCH(c, k_ws_hist<false>, quad_grid(g), TISEG_THREADS, 0, g, wsl, hist, first, KS, (g.W % 4 == 0) && aligned16(wsl));
+        TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged, (const int*)nullptr, (const int*)nullptr);
+    } else {
+        TISEG_LAUNCH(c, k_mask_area, dim3(8, N), TISEG_THREADS, 0, g, mbits, marea);
+        TISEG_LAUNCH(c, k_dense_tiles, (N + 255) / 256, 256, 0, marea, N, g.P, bg, dense, ndense);
+        Geom gd = listed_geom(g, dense, ndense);
+        TISEG_LAUNCH(c, k_ws_hist<true>, dim3(quad_grid(g).x, 1), TISEG_THREADS, 0, gd, wsl, hist, first, KS, (g.W % 4 == 0) && aligned16(wsl));
+        TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged, (const int*)dense, (const int*)ndense);
+    }
     //   background 0 (every tile but degenerate ones): ids = rank of each region's first pixel; watershed lines
     //   are found on the flood labels themselves (the renumbering is a bijection)
     TISEG_LAUNCH(c, k_first_bits, dim3(8, N), 256, 0, g, first, KS, nmark, fbits);

@@ -446,6 +446,45 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
         int trips = 0;
         const bool vec16 = vec && (P % 16 == 0) && ((((uintptr_t)(pred + base)) | ((uintptr_t)(gt + base))) & 15) == 0;
         const long long step16 = (long long)gridDim.x * blockDim.x * 16;
+        // all-vector case: four 128-bit loads per map in flight per thread (the pass is bound by bytes in flight)
+        if (vec16) {
+            const long long step64 = (long long)gridDim.x * blockDim.x * 64;
+            for (long long i0 = (long long)blockIdx.x * blockDim.x * 64; i0 < P; i0 += step64) {
+                uint4 a[4], b[4];
+                int npx[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = i0 + ((long long)u * blockDim.x + threadIdx.x) * 16;
+                    npx[u] = i < P ? 16 : 0;                     // (P % 16 == 0)
+                    a[u] = make_uint4(0u, 0u, 0u, 0u); b[u] = a[u];
+                    if (npx[u]) { a[u] = *reinterpret_cast<const uint4*>(pred + base + i); b[u] = *reinterpret_cast<const uint4*>(gt + base + i); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (npx[u]) {
+                        const unsigned pw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, tw[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const int p = (pw[k >> 2] >> (8 * (k & 3))) & 255, t = (tw[k >> 2] >> (8 * (k & 3))) & 255;
+                            if (t != ignore) {
+                                const int key = min(t, C) * C1 + min(p, C);
+                                const unsigned long long one = 1ull << ((key & 7) * 8);
+                                if (key < 8) a0 += one; else a1 += one;
+                            }
+                        }
+                    }
+                    if (++trips == 15 || (u == 3 && i0 + step64 >= P)) {
+#pragma unroll
+                        for (int key = 0; key < 16; ++key) {
+                            const unsigned f = (unsigned)(((key < 8 ? a0 : a1) >> ((key & 7) * 8)) & 0xffull);
+                            const unsigned tot = __reduce_add_sync(0xffffffffu, f);
+                            if (lane == 0 && tot && key < C1 * C1) atomicAdd(&h[key], tot);
+                        }
+                        a0 = a1 = 0ull; trips = 0;
+                    }
+                }
+            }
+        } else
         for (long long i0 = (long long)blockIdx.x * blockDim.x * 16; i0 < P; i0 += step16) {
             const long long i = i0 + (long long)threadIdx.x * 16;
             unsigned pw[4] = {0u, 0u, 0u, 0u}, tw[4] = {0u, 0u, 0u, 0u};
@@ -882,6 +921,12 @@ int tiseg_sem_counts(tiseg_ctx* c, const uint8_t* pred, const uint8_t* gt, int N
     // the 16-pixel path: few blocks per tile with many trips each — every block ends with 5C + 1 global atomics on the
     // handful of cache lines that hold the counters, and those serialise in L2
     if ((C + 1) * (C + 1) <= 16 && gx > 16) gx = 16;
+    if ((C + 1) * (C + 1) <= 16 && (long long)N * gx < 4ll * c->sm_count) {          // few tiles: more blocks per tile
+        const long long want = (4ll * c->sm_count + N - 1) / N, most = ((long long)g.P + 64 * TISEG_THREADS - 1) / (64 * TISEG_THREADS);
+        gx = (unsigned)(want < most ? want : most);
+        if (gx < 1) gx = 1;
+    }
+    if (getenv("TISEG_SEM_GX")) gx = (unsigned)atoi(getenv("TISEG_SEM_GX"));
     bool vec = (g.P % 4 == 0) && ((((uintptr_t)d_pred) | ((uintptr_t)d_gt)) & 3) == 0;
     TISEG_LAUNCH(c, k_sem_counts, dim3(gx, N), TISEG_THREADS, 0, (long long)g.P, d_pred, d_gt, C, ignore_index,
                  (unsigned long long*)d_counts, (unsigned long long*)d_valid, vec);

@@ -220,7 +220,12 @@ __global__ void k_flood_count(BlobInfo b, int W, FloodWork wk, int arena, int sl
     long long ko = (long long)n * b.KS;
     int B = b.count[n];
     for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
-        if (b.lmin && b.lmin[ko + bid] >= b.lmax[ko + bid]) continue;
+        if (b.lmin && b.lmin[ko + bid] >= b.lmax[ko + bid]) {
+            // a single-marker blob is one region of that label: its first pixel is the blob's
+            if (b.first && b.lmax[ko + bid] > 0 && b.lmin[ko + bid] == b.lmax[ko + bid])
+                atomicMin(&b.first[ko + b.lmax[ko + bid]], b.root[ko + bid]);
+            continue;
+        }
         int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
         if (cls >= 0) atomicAdd(&wk.count[cls], 1);
     }
@@ -444,7 +449,7 @@ __device__ __forceinline__ void stage_writeback(int tid, int nthr, int W, int32_
 template <class MB>
 __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const uint8_t* __restrict__ I,
                                                   const MB mb, int32_t* o, int* nx, int root, int y0,
-                                                  int y1, int x0, int x1, int* head, int* tail) {
+                                                  int y1, int x0, int x1, int* head, int* tail, int* first = nullptr) {
     for (int i = lane; i < 256; i += 32) { head[i] = -1; tail[i] = -1; }
     __syncwarp();
     int cur = 256;
@@ -464,6 +469,7 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
                 int slv = __shfl_sync(FULL, lv, src);
                 if (lane == 0) {
                     int pix = y * W + xb + src;
+                    if (first) atomicMin(&first[o[pix]], pix);
                     nx[pix] = -1;
                     int t = tail[slv];
                     if (t < 0) head[slv] = pix; else nx[t] = pix;
@@ -496,6 +502,7 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
             for (int k = 0; k < 4; ++k) {
                 if (pin[k] && ov[k] == 0) {
                     o[nb[k]] = lab_g;
+                    if (first) atomicMin(&first[lab_g], nb[k]);
                     nx[nb[k]] = -1;
                     int t = tail[lv[k]];
                     if (t < 0) head[lv[k]] = nb[k]; else nx[t] = nb[k];
@@ -873,22 +880,26 @@ __device__ __forceinline__ void wp_flood(int lane, int wp, unsigned* cell, unsig
     }
 }
 
-// every labelled cell takes the marker label of its seed pixel
-__device__ __forceinline__ void wp_writeback(int tid, int nthr, int W, int32_t* o, int y0, int x0, int w, int h, const unsigned* cell) {
+// every labelled cell takes the marker label of its seed pixel; `first` (may be NULL): lowest flat index per label, one
+// atomic per run of equal labels along the staged rows
+__device__ __forceinline__ void wp_writeback(int tid, int nthr, int W, int32_t* o, int y0, int x0, int w, int h, const unsigned* cell,
+                                             int* first) {
     const int wp = w + 2, cells = wp * (h + 2), anchor = y0 * W + x0;
     const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
     for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
         int dst[8], src[8];
+        bool store[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * nthr + tid;
-            dst[u] = -1; src[u] = anchor;
+            dst[u] = -1; src[u] = anchor; store[u] = false;
             if (j < cells) {
                 const unsigned L = cell[j] >> 16;
-                if (L < WPC_UNLAB && L != (unsigned)j) {
+                if (L < WPC_UNLAB) {
                     const int ly = fdiv(j, magic), lx = j - ly * wp, sy = fdiv((int)L, magic), sx = (int)L - sy * wp;
                     dst[u] = (y0 + ly - 1) * W + x0 + lx - 1;
                     src[u] = (y0 + sy - 1) * W + x0 + sx - 1;
+                    store[u] = L != (unsigned)j;
                 }
             }
         }
@@ -896,7 +907,15 @@ __device__ __forceinline__ void wp_writeback(int tid, int nthr, int W, int32_t* 
 #pragma unroll
         for (int u = 0; u < 8; ++u) val[u] = o[src[u]];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) if (dst[u] >= 0) o[dst[u]] = val[u];
+        for (int u = 0; u < 8; ++u) if (store[u]) o[dst[u]] = val[u];
+        if (first) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int key = dst[u] >= 0 ? val[u] : 0;
+                const int left = __shfl_up_sync(FULL, key, 1);
+                if (key != 0 && ((tid & 31) == 0 || left != key)) atomicMin(&first[key], dst[u]);
+            }
+        }
     }
 }
 
@@ -933,10 +952,11 @@ k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInf
             const InMask inm = {MASKED ? bm.mask_img + base : nullptr, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
             if (cells > WP_GEN_CAP) {     // does not fit: the sequential flood in global memory, by one lane
                 if (warp == 0) {
+                    int* fst = b.first ? b.first + ko : nullptr;
                     if (MASKED) flood_blob_global(lane, W, H, image + base, inm, out + base, next + base, root, y0, y1, x0, x1,
-                                                  gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+                                                  gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256, fst);
                     else flood_blob_global(lane, W, H, image + base, inf, out + base, next + base, root, y0, y1, x0, x1,
-                                           gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256);
+                                           gheads + (size_t)blockIdx.x * 512, gheads + (size_t)blockIdx.x * 512 + 256, fst);
                 }
                 continue;
             }
@@ -950,7 +970,7 @@ k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInf
                 if (smin < 256) wp_flood(lane, w + 2, cell, Q, head, tail, smin);
             }
             __syncthreads();
-            wp_writeback(threadIdx.x, blockDim.x, W, out + base, y0, x0, w, h, cell);
+            wp_writeback(threadIdx.x, blockDim.x, W, out + base, y0, x0, w, h, cell, b.first ? b.first + ko : nullptr);
         }
         __syncthreads();
     }
@@ -1013,7 +1033,7 @@ k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInf
             }
             __syncwarp();
             if (prof) { const long long t = clock64(); t_flood += t - t0; t0 = t; }
-            wp_writeback(lane, 32, W, out + base, y0, x0, w, h, cell);
+            wp_writeback(lane, 32, W, out + base, y0, x0, w, h, cell, b.first ? b.first + ko : nullptr);
             __syncwarp();
             if (prof) t_wb += clock64() - t0;
         }
@@ -1541,13 +1561,13 @@ int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
 }
 
 int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
-                      int* par, int* rank, BlobInfo& b) {
+                      int* par, int* rank, int* first, BlobInfo& b) {
     const int N = g.N, KS = g.P + 1;
     const size_t ks = (size_t)N * KS, words = (size_t)N * g.H * g.SEG;
     int* count = ws<int>(c, (size_t)N);
     b.root = ws<int>(c, ks); b.ymax = ws<int>(c, ks); b.xmin = ws<int>(c, ks); b.xmax = ws<int>(c, ks);
     b.area = ws<int>(c, ks); b.off = nullptr; b.lmin = ws<int>(c, ks); b.lmax = ws<int>(c, ks);
-    b.KS = KS; b.count = count;
+    b.KS = KS; b.count = count; b.first = first;
     unsigned* lbits = ws<unsigned>(c, words);
     unsigned* fbits = ws<unsigned>(c, words);
     if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || !b.lmin || !b.lmax || !lbits || !fbits) return TISEG_ERR_CUDA;

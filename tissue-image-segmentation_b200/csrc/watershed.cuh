@@ -34,6 +34,10 @@ struct BlobInfo {
     // marker plateau is 8-connected and can reach into a second 4-connected blob through a diagonal.)
     int* lmin;   // [N, KS]
     int* lmax;   // [N, KS]
+    // optional by-product for a caller that renumbers the flood's regions in raster order (DIST's arrange_label):
+    // first[n, label] = lowest flat index of a pixel carrying `label` (initialised to INT_MAX by the caller).  The fill
+    // of single-marker blobs and the flood's write-back keep it up to date; NULL = not wanted.
+    int* first;  // [N, KS]
 };
 
 // How the flood decides which cells of a staged bounding box belong to the blob.
@@ -60,7 +64,7 @@ int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
 // blob table from the planes of the mask: forest over runs, ids, root, marker label range and bounding boxes of the blobs
 // that hold two or more marker labels.  seeds: the marker map (0 = no marker).
 int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
-                      int* par, int* rank, BlobInfo& b);
+                      int* par, int* rank, int* first, BlobInfo& b);
 // single-marker blobs: every pixel takes the marker's label (after the flood of the others)
 int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
                       int32_t* out);
@@ -83,7 +87,7 @@ int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, 
     int* count = ws<int>(c, (size_t)N);
     b.root = ws<int>(c, ks); b.ymax = ws<int>(c, ks); b.xmin = ws<int>(c, ks); b.xmax = ws<int>(c, ks);
     b.area = ws<int>(c, ks); b.off = want_offsets ? ws<int>(c, ks) : nullptr;
-    b.KS = KS; b.count = count; b.lmin = nullptr; b.lmax = nullptr;
+    b.KS = KS; b.count = count; b.lmin = nullptr; b.lmax = nullptr; b.first = nullptr;
     if (!count || !b.root || !b.ymax || !b.xmin || !b.xmax || !b.area || (want_offsets && !b.off)) return TISEG_ERR_CUDA;
     TISEG_TRY(ccl_build(c, g, mask, conn, par));
     const unsigned* root_bits = (const unsigned*)c->rootblk;      // left by the flatten; rank_roots consumes the same bitmap
