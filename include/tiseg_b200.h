@@ -75,6 +75,12 @@ int tiseg_softmax_argmax_tta(tiseg_ctx* ctx, const float* logits, int N, int T, 
                              const int* rotate_degrees, const int* flips, int window, int overlap,
                              float* prob, uint8_t* cls);
 
+/* The plain (no softmax) TTA mean of a regression head with the same stitch + reverse-transform indexing:
+ * `sum(dist_logit_list) / len(dist_logit_list)` of dist.py:398-410; hovernet.py:406 keeps variant 0 only (T = 1).
+ * maps laid out like the logits of tiseg_softmax_argmax_tta; mean_out [N, C, H, W]. */
+int tiseg_tta_mean(tiseg_ctx* ctx, const float* maps, int N, int T, int C, int H, int W, const int* rotate_degrees,
+                   const int* flips, int window, int overlap, float* mean_out);
+
 /* ---- A5 / A6 / A15: connected-component labelling ---------------------------------------------
  * skimage.measure.label(img, background=bg, connectivity=conn) (unet.py:85, dist.py:107,123,
  * multi_task_unet.py:101, inst_metrics.py:12-13,142-143) and scipy.ndimage.label (hovernet.py:296,358;
@@ -167,6 +173,20 @@ int tiseg_cdnet_refine(tiseg_ctx* ctx, const float* sem_logits, const float* dir
                        int N, int T, int C, int D, int H, int W, int if_ddm, float* sem_prob_out, uint8_t* cls_out,
                        uint8_t* dir_map_out, float* dd_out);
 
+/* _ddm_enhencement alone, IN PLACE on sem_prob [N,C,H,W]: mode 0 = CDNet (cdnet.py:354-367), mode 1 = MultiTaskCDNet
+ * (multi_task_cdnet.py:548-564).  dd [N,H,W] mean DDM, point [N,H,W] TTA-mean point map (channel 0 of point_logit). */
+int tiseg_ddm_enhance(tiseg_ctx* ctx, float* sem_prob, const float* dd, const float* point, int N, int C, int H, int W, int mode);
+/* The tail of MultiTaskCDNet.inference after the CNN (multi_task_cdnet.py:262-330, use_regression = False): softmax +
+ * TTA mean of the three-class (tc) and semantic heads, TTA mean of the point head, per variant dir[:,0] *= tc[:,0] ->
+ * argmax -> DDM, mean DDM, its own _ddm_enhencement (:548-564) on the tc probabilities.  tc_logits [N,T,Ctc,H,W],
+ * sem_logits [N,T,Csem,H,W], dir_logits [N,T,9,H,W], point_logits [N,T,1,H,W].  Outputs (any may be NULL): tc_prob_out
+ * [N,Ctc,H,W] refined, tc_cls_out / sem_cls_out [N,H,W] the argmax maps postprocess consumes (:209-213), sem_prob_out
+ * [N,Csem,H,W], dir_map_out [N,H,W] direction map of variant 0, dd_out [N,H,W]. */
+int tiseg_mtcdnet_refine(tiseg_ctx* ctx, const float* tc_logits, const float* sem_logits, const float* dir_logits,
+                         const float* point_logits, int N, int T, int Ctc, int Csem, int D, int H, int W, int if_ddm,
+                         float* tc_prob_out, uint8_t* tc_cls_out, float* sem_prob_out, uint8_t* sem_cls_out,
+                         uint8_t* dir_map_out, float* dd_out);
+
 /* ---- A13: align_foreground (tiseg/models/utils/postprocess.py:123-155) -----------------------------------
  * Ordered multi-source BFS growing the labels of `pred` into `foreground` (8-neighbourhood, first claimant
  * wins, at most time-1 rounds).  pred [N,H,W] int32 is modified in place; foreground uint8. */
@@ -182,10 +202,13 @@ int tiseg_postproc_multitask(tiseg_ctx* ctx, const uint8_t* inner, const uint8_t
 /* ---- A16 / A17: pre_eval_bin_aji + pre_eval_bin_pq (inst_metrics.py:10-92, 138-229) ---------------
  * pred / gt [N,H,W] int32 instance maps with arbitrary ids (the relabelling the reference does with
  * re_instance + measure.label is done inside).  aji [N,2] fp64 = (overall_inter, overall_union);
- * pq [N,4] fp64 = (tp, fp, fn, iou_sum).  Either output may be NULL.  match_iou is fixed at the
- * reference default 0.5 (the Hungarian branch is unreachable with it). */
+ * pq [N,4] fp64 = (tp, fp, fn, iou_sum).  Either output may be NULL.  match_iou is the reference default 0.5 (the
+ * Hungarian branch for match_iou < 0.5 is reached by no caller of the reference and is not built). */
 int tiseg_pair_metrics_bin(tiseg_ctx* ctx, const int32_t* pred, const int32_t* gt, int N, int H, int W,
                            double* aji, double* pq);
+/* the same with pre_eval_bin_pq's match_iou (>= 0.5; a pair matches when iou > match_iou, inst_metrics.py:197-203) */
+int tiseg_pair_metrics_bin_iou(tiseg_ctx* ctx, const int32_t* pred, const int32_t* gt, int N, int H, int W, double match_iou,
+                               double* aji, double* pq);
 
 /* ---- A18: CoNIC multi-class evaluation (conic.py:165-188) -----------------------------------------------
  * assign_sem_class_to_insts (datasets/utils/instance_semantic.py:68-93) on both sides, then pre_eval_aji /

@@ -323,6 +323,71 @@ def cdnet_inference_tail(sem_logit_list, dir_logit_list, point_logit_list, if_dd
     return sem, dir_maps[0], dd_map
 
 
+def ddm_enhancement(sem_prob, dd_map, point, mode=0):
+    """``_ddm_enhencement``: mode 0 = cdnet.py:354-367, mode 1 = multi_task_cdnet.py:548-564.  sem_prob [C,H,W] fp32
+    probabilities, dd_map [H,W], point [H,W] (channel 0 of the TTA-mean point map).  fp32, the reference's operation order;
+    returns a new array."""
+    sem = np.array(sem_prob, np.float32, copy=True)
+    one = np.float32(1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if mode == 0:
+            point_map = (point / point.max()) > np.float32(0.2)
+            dd2 = (dd_map - (dd_map * point_map.astype(np.float32))).astype(np.float32)
+            sem[-1] = ((sem[-1] + dd2).astype(np.float32) * (one + dd2)).astype(np.float32)
+        else:
+            dist_map = (point + np.float32(0.2)).astype(np.float32)
+            t = (dist_map / dist_map.max()).astype(np.float32)
+            fprob = (t * t).astype(np.float32)                         # torch ``** 2``
+            fmap = fprob > np.float32(0.6)
+            w0 = (one - fprob).astype(np.float32)
+            dd1 = (dd_map - (dd_map * fmap.astype(np.float32))).astype(np.float32)
+            e = ((sem[-1] * (one + dd1)).astype(np.float32) * w0).astype(np.float32)
+            e[e >= one] = np.float32(0.95)
+            sem[-1] = e                                                # (:562 compares a bool map with 0.8: never true)
+    return sem
+
+
+def mtcdnet_inference_tail(tc_logit_list, sem_logit_list, dir_logit_list, point_logit_list, if_ddm=True):
+    """multi_task_cdnet.py:262-330 after the CNN, use_regression = False: softmax + TTA mean of tc and sem; point mean;
+    per variant ``dir[:,0] *= tc[:,0]`` -> argmax -> DDM; mean DDM; optional ``_ddm_enhencement`` (:548-564) on tc.
+    Inputs: lists of [C,H,W] fp32 logits (already reverse-transformed).  Returns (tc_prob, sem_prob, dir_map of the first
+    variant, dd_map)."""
+    tc = softmax_tta_mean(tc_logit_list)
+    sem = softmax_tta_mean(sem_logit_list)
+    point = None
+    for p in point_logit_list:
+        point = p.astype(np.float32) if point is None else (point + p).astype(np.float32)
+    point = (point / np.float32(len(point_logit_list))).astype(np.float32)
+    dd_sum, dir_maps = None, []
+    for dl in dir_logit_list:
+        d = softmax(dl, axis=0)
+        d[0] = d[0] * tc[0]
+        dir_map = np.argmax(d, axis=0)
+        dir_maps.append(dir_map)
+        dd = direction_differential_map(dir_map, 9)
+        dd_sum = dd if dd_sum is None else (dd_sum + dd).astype(np.float32)
+    dd_map = (dd_sum / np.float32(len(dir_logit_list))).astype(np.float32)
+    if if_ddm:
+        tc = ddm_enhancement(tc, dd_map, point[0], mode=1)
+    return tc, sem, dir_maps[0], dd_map
+
+
+def tta_plain_mean(reversed_list):
+    """``sum(list) / len(list)`` of already reverse-transformed fp32 maps (the regression heads: dist.py:398-406)."""
+    acc = None
+    for x in reversed_list:
+        acc = np.asarray(x, np.float32) if acc is None else (acc + x).astype(np.float32)
+    return (acc / np.float32(len(reversed_list))).astype(np.float32)
+
+
+def three_class_gt(sem_gt_w_bound, num_classes):
+    """multi_task_cdnet_debug.py:164-168: 0 background, 1 inside, boundary label (== num_classes) -> 2."""
+    tc = np.array(sem_gt_w_bound, copy=True)
+    tc[(tc != 0) * (tc != num_classes)] = 1
+    tc[tc > 1] = 2
+    return tc
+
+
 # --------------------------------------------------------------------------- A13 multi-task
 def multitask_postprocess(inner_pred, sem_pred, variant="unet"):
     """multi_task_unet.py:84-106, multi_task_cunet.py:86-108 (variant 'cunet': tc map with edge

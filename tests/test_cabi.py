@@ -59,3 +59,23 @@ def test_label_maker_classes_mirror_the_reference_constructors():
     assert lm.BoundLabelMake(selem_radius=2).radius == (2, 2)
     with pytest.raises(NotImplementedError):
         lm.UNetLabelMake(wc={1: 2.0})
+
+
+def test_reference_signatures():
+    """The reference-named entry points take the reference's parameters, in the reference's order (no GPU needed):
+    inst_metrics.py:95,138,232; direct_diff_map.py:95; cdnet.py:354; multi_task_cdnet.py:548,220."""
+    import inspect
+    import tiseg_b200  # noqa: F401
+    from tiseg_b200 import metrics as M, segmentors as S
+    names = lambda f: list(inspect.signature(f).parameters)
+    assert names(M.pre_eval_aji) == ["inst_pred", "inst_gt", "pred_id_list_per_class", "gt_id_list_per_class", "num_classes",
+                                     "reduce_zero_label"]
+    assert names(M.pre_eval_pq) == names(M.pre_eval_aji)
+    assert names(M.pre_eval_bin_pq) == ["inst_pred", "inst_gt", "match_iou"]
+    assert inspect.signature(M.pre_eval_bin_pq).parameters["match_iou"].default == 0.5
+    assert names(S.generate_direction_differential_map) == ["dir_map", "direction_classes", "background", "use_reg"]
+    for cls in (S.CDNet, S.MultiTaskCDNet):
+        assert names(cls._ddm_enhencement) == ["sem_logit", "dd_map", "point_logit"]
+    assert names(S.MultiTaskCDNet.postprocess)[1:] == ["inner_pred", "sem_pred"] or names(S.MultiTaskCDNet.postprocess)[1:] == ["tc_pred", "sem_pred"]
+    assert names(M.pre_eval_all_semantic_metric)[:4] == ["pred_label", "target_label", "num_classes", "ignore_index"]
+

@@ -846,3 +846,151 @@ def test_convenience_scores_match_reference():
         p, r = M.precision_recall(sp, sg, 4)
         _diff(np.asarray(p), m["s%d_precision" % j], "precision %d" % j)
         _diff(np.asarray(r), m["s%d_recall" % j], "recall %d" % j)
+
+
+# --------------------------------------------------------------------------- round-2 vectors (r2_ref.npz): the reference's
+# own argument shapes through the reference-named entry points
+def test_mtcdnet_tail_matches_reference_source_golden():
+    """MultiTaskCDNet.inference tail (multi_task_cdnet.py:262-330) + its _ddm_enhencement (:548-564) vs the method executed
+    from source; argmax maps as postprocess consumes them."""
+    from test_oracle_golden import _mt_case
+    from tiseg_b200 import segmentors
+    m = np.load(os.path.join(G, "r2_ref.npz"))
+    for j in range(3):
+        tc, sem, dirs, pts, if_ddm, rots, flips = _mt_case(m, j)
+        rev = lambda lst: np.stack([opp.reverse_tta_transform(x, int(r), str(f)) for x, r, f in zip(lst, rots, flips)])
+        r = ops.mtcdnet_refine(rev(tc), rev(sem), rev(dirs), rev(pts), if_ddm=if_ddm, want_sem_prob=True)
+        _check_class_map(r["tc_cls"], r["tc_prob"], m["m%d_tc_out" % j], "mtcdnet tc %d" % j)
+        _check_class_map(r["sem_cls"], r["sem_prob"], m["m%d_sem_out" % j], "mtcdnet sem %d" % j)
+        assert (r["dir_map"] != m["m%d_dir_out" % j]).mean() < 1e-3
+        seg = segmentors.MultiTaskCDNet(num_classes=sem[0].shape[0], if_ddm=if_ddm)
+        tcp, sem_cls, dir_map, tc_cls = seg.inference_tail(rev(tc), rev(sem), rev(dirs), rev(pts))
+        assert np.array_equal(tc_cls, r["tc_cls"]) and np.array_equal(sem_cls, r["sem_cls"])
+        out = seg.forward_eval(rev(tc), rev(sem), rev(dirs), rev(pts))
+        want_sem, want_inst = opp.multitask_postprocess(np.asarray(r["tc_cls"]).astype(np.int64), np.asarray(r["sem_cls"]).astype(np.int64), "cdnet")
+        _diff(out[0]["inst_pred"], want_inst, "MultiTaskCDNet.forward_eval inst %d" % j)
+        _diff(out[0]["sem_pred"], want_sem, "MultiTaskCDNet.forward_eval sem %d" % j)
+
+
+def test_mtcdnet_tail_vs_oracle_batched():
+    rng = np.random.default_rng(91)
+    for T, (H, W) in [(1, (64, 80)), (2, (96, 70))]:
+        tiles = []
+        for n in range(3):
+            t = synth.gt_and_pred(8100 + 10 * T + n, H, W, num_classes=3)
+            tc = [synth.sem_logits(rng, synth.three_class_map(t["pred_inst"]), 3) for _ in range(T)]
+            sem = [synth.sem_logits(rng, t["pred_sem"], 3) for _ in range(T)]
+            dirs, pts = zip(*[synth.direction_logits(rng, t["pred_inst"]) for _ in range(T)])
+            tiles.append((np.stack(tc), np.stack(sem), np.stack(dirs), np.stack(pts)))
+        batch = [np.stack([t[k] for t in tiles]) for k in range(4)]
+        for if_ddm in (True, False):
+            r = ops.mtcdnet_refine(*batch, if_ddm=if_ddm, want_sem_prob=True)
+            for n in range(3):
+                w_tc, w_sem, w_dir, w_dd = opp.mtcdnet_inference_tail(list(tiles[n][0]), list(tiles[n][1]), list(tiles[n][2]),
+                                                                      list(tiles[n][3]), if_ddm)
+                _diff(r["dir_map"][n], w_dir, "mtcdnet dir map")
+                _diff(r["dd"][n], w_dd, "mtcdnet dd")
+                _check_class_map(r["tc_cls"][n], r["tc_prob"][n], w_tc, "mtcdnet tc T=%d" % T)
+                _check_class_map(r["sem_cls"][n], r["sem_prob"][n], w_sem, "mtcdnet sem T=%d" % T)
+
+
+def test_ddm_enhencement_reference_argument_shapes():
+    """CDNet._ddm_enhencement / MultiTaskCDNet._ddm_enhencement called like the reference: torch tensors [1,C,H,W],
+    [1,H,W], [1,1,H,W], in place, on the CPU and on the GPU."""
+    import torch
+    from tiseg_b200 import segmentors
+    m = np.load(os.path.join(G, "r2_ref.npz"))
+    for j in range(2):
+        for key, cls in (("cdnet", segmentors.CDNet), ("mtcdnet", segmentors.MultiTaskCDNet)):
+            for dev in ("cpu", "cuda"):
+                prob = torch.from_numpy(m["e%d_prob" % j].copy()).to(dev)
+                got = cls._ddm_enhencement(prob, torch.from_numpy(m["e%d_dd" % j]).to(dev), torch.from_numpy(m["e%d_pt" % j]).to(dev))
+                assert got is prob                                          # modified in place and returned, like the reference
+                np.testing.assert_allclose(got.cpu().numpy(), m["e%d_%s" % (j, key)], rtol=1e-6, atol=0, err_msg="%s %d %s" % (key, j, dev))
+
+
+def test_generate_direction_differential_map_reference_name():
+    import torch
+    from tiseg_b200 import segmentors
+    o = np.load(os.path.join(G, "ordered_ref.npz"))
+    for j in range(3):
+        d = o["dd%d_dir" % j]
+        got = segmentors.generate_direction_differential_map(torch.from_numpy(d.astype(np.int64))[None].cuda(), 9)
+        assert tuple(got.shape) == (1,) + d.shape and got.dtype == torch.float32 and got.is_cuda
+        _diff(got[0].cpu().numpy(), o["dd%d_out" % j], "generate_direction_differential_map (cuda tensor) %d" % j)
+        got = segmentors.generate_direction_differential_map(d)                 # HxW numpy, like label_to_vector accepts
+        _diff(got[0].numpy(), o["dd%d_out" % j], "generate_direction_differential_map (numpy) %d" % j)
+    with pytest.raises(NotImplementedError):
+        segmentors.generate_direction_differential_map(o["dd0_dir"], 9, use_reg=True)
+
+
+def test_regression_head_tta_matches_reference_source_golden():
+    """DIST.inference / HoverNet.inference executed from source (recorder network, whole and split inference): the
+    distance head is the plain TTA mean, the hv head is variant 0, the foreground head a softmax mean."""
+    from test_oracle_golden import _reg_case
+    from tiseg_b200 import segmentors
+    m = np.load(os.path.join(G, "r2_ref.npz"))
+    for j in range(3):
+        H, W, window, overlap, dv, rots, flips = _reg_case(m, "d", j, 1)
+        _, _, _, _, sv, _, _ = _reg_case(m, "d", j, 0)
+        seg = segmentors.Dist(2, test_cfg=dict(rotate_degrees=sorted(set(rots), key=rots.index), flip_directions=sorted(set(flips), key=flips.index)))
+        sem_pred, dist = seg.inference_tail(sv, dv, (H, W), window, overlap)
+        assert np.array_equal(dist, m["d%d_out1" % j][:, 0]), "dist head TTA mean %d" % j        # quarter-integers: exact
+        got_mean = ops.tta_mean(dv, rots, flips, (H, W), window, overlap)
+        assert np.array_equal(got_mean, m["d%d_out1" % j])
+        want_p = m["d%d_out0" % j]
+        top2 = np.sort(want_p, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert np.array_equal(sem_pred[clear], want_p.argmax(1).astype(np.uint8)[clear])
+        # HoVer-Net: hv = variant 0 only
+        _, _, _, _, hv, hrots, hflips = _reg_case(m, "h", j, 1)
+        _, _, _, _, hs, _, _ = _reg_case(m, "h", j, 0)
+        _, _, _, _, hf, _, _ = _reg_case(m, "h", j, 2)
+        hseg = segmentors.HoverNet(3, test_cfg=dict(rotate_degrees=sorted(set(hrots), key=hrots.index), flip_directions=sorted(set(hflips), key=hflips.index)))
+        sem_pred, hv_map, fore = hseg.inference_tail(hs, hv, hf, (H, W), window, overlap)
+        assert np.array_equal(np.moveaxis(hv_map, -1, 1), m["h%d_out1" % j]), "hv head (variant 0) %d" % j
+        np.testing.assert_allclose(fore, m["h%d_out2" % j][:, 1], rtol=1e-5, atol=1e-7)
+
+
+def test_debug_tail_three_class_target():
+    from tiseg_b200 import segmentors
+    m = np.load(os.path.join(G, "r2_ref.npz"))
+    for j in range(3):
+        assert np.array_equal(segmentors.three_class_gt(m["g%d_wb" % j], int(m["g%d_nc" % j])), m["g%d_tc" % j])
+    t = synth.gt_and_pred(8200, 64, 80, num_classes=3)
+    rng = np.random.default_rng(92)
+    tc_l = synth.sem_logits(rng, synth.three_class_map(t["pred_inst"]), 3)[None]
+    sem_l = synth.sem_logits(rng, t["pred_sem"], 3)[None]
+    wb = np.where(synth.three_class_map(t["gt_inst"]) == 2, 2, t["gt_sem"]).astype(np.int64)
+    seg = segmentors.MultiTaskCUNetDebug(2)
+    out = seg.forward_eval_debug(wb, tc_l, sem_l)
+    assert set(out[0]) == {"tc_pred", "tc_gt", "sem_pred", "inst_pred"}
+    assert np.array_equal(out[0]["tc_gt"], opp.three_class_gt(wb, 2))
+    assert np.array_equal(out[0]["tc_pred"], ops.softmax_argmax(tc_l))
+
+
+def test_pre_eval_reference_signatures_with_id_dictionaries_and_match_iou():
+    """pre_eval_aji / pre_eval_pq fed the exact objects conic.py:178-188 feeds the reference (re_instance'd maps + the two
+    id dictionaries), hand-made dictionaries included, and pre_eval_bin_pq with match_iou in (0.5, 1)."""
+    from test_oracle_golden import _id_dict
+    from tiseg_b200 import metrics as M
+    m = np.load(os.path.join(G, "r2_ref.npz"))
+    for k in range(int(m["n_pair_cases"])):
+        n = "p%d" % k
+        ip, ig = m[n + "_ip"], m[n + "_ig"]
+        dp, dg = _id_dict(m, n, "dp"), _id_dict(m, n, "dg")
+        for rz in (True, False):
+            got = M.pre_eval_aji(ip, ig, dp, dg, 4, reduce_zero_label=rz)
+            assert all(g.dtype == np.float32 for g in got)
+            _diff(np.stack(got), m[n + "_aji_rz%d" % rz], "pre_eval_aji(dicts) %s rz=%s" % (n, rz))
+            got = M.pre_eval_pq(ip, ig, dp, dg, 4, reduce_zero_label=rz)
+            _diff(np.stack(got), m[n + "_pq_rz%d" % rz], "pre_eval_pq(dicts) %s rz=%s" % (n, rz))
+        for mi in (0.5, 0.6, 0.75, 0.9):
+            got = M.pre_eval_bin_pq(ip, ig, mi)
+            assert tuple(np.float64(v) for v in got) == tuple(m[n + "_binpq_%d" % int(mi * 100)]), (n, mi, got)
+        # the library's own class assignment gives the reference's dictionaries back
+        if k == 0:
+            assert M.assign_sem_class_to_insts(ip, np.zeros_like(ip, np.uint8), 4) == {0: [0] + sorted(set(np.unique(ip)) - {0})}
+    with pytest.raises(NotImplementedError):
+        M.pre_eval_bin_pq(m["p0_ip"], m["p0_ig"], 0.3)
+

@@ -354,3 +354,89 @@ def test_monuseg_debug_evaluate_matches_reference_source():
     ev, _ = ds.evaluate(results, logger="silent")
     assert list(ev.keys()) == m["monuseg_eval_keys"].tolist()
     np.testing.assert_allclose(np.array([float(v) for v in ev.values()]), m["monuseg_eval_values"], rtol=0, atol=1e-9)
+
+
+# --------------------------------------------------------------------------- round-2 vectors (r2_ref.npz)
+def _r2():
+    return np.load(os.path.join(G, "r2_ref.npz"))
+
+
+def _mt_case(m, j):
+    T = len(m["m%d_flips" % j])
+    f32 = lambda key: [m["m%d_%s%d" % (j, key, t)].astype(np.float32) for t in range(T)]
+    return f32("tc"), f32("sem"), f32("dir"), f32("pt"), bool(m["m%d_if_ddm" % j]), list(m["m%d_rots" % j]), list(m["m%d_flips" % j])
+
+
+def test_oracle_mtcdnet_tail_matches_reference_source():
+    """The restatement of MultiTaskCDNet.inference's tail vs the method executed from source (recorder network)."""
+    m = _r2()
+    for j in range(3):
+        tc, sem, dirs, pts, if_ddm, rots, flips = _mt_case(m, j)
+        rev = lambda lst: [opp.reverse_tta_transform(x, int(r), str(f)) for x, r, f in zip(lst, rots, flips)]
+        got_tc, got_sem, got_dir, _ = opp.mtcdnet_inference_tail(rev(tc), rev(sem), rev(dirs), rev(pts), if_ddm)
+        np.testing.assert_allclose(got_tc, m["m%d_tc_out" % j], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got_sem, m["m%d_sem_out" % j], rtol=1e-5, atol=1e-7)
+        assert (got_dir != m["m%d_dir_out" % j]).mean() < 1e-3          # argmax of fp32 products: libm-level ties only
+
+
+def test_oracle_ddm_enhancement_both_variants():
+    m = _r2()
+    for j in range(2):
+        for key, mode in (("cdnet", 0), ("mtcdnet", 1)):
+            got = opp.ddm_enhancement(m["e%d_prob" % j][0], m["e%d_dd" % j][0], m["e%d_pt" % j][0, 0], mode)
+            assert np.array_equal(got, m["e%d_%s" % (j, key)][0]), (j, key)
+
+
+def _reg_case(m, name, j, h):
+    H, W, window, overlap, T = [int(v) for v in m["%s%d_meta" % (name, j)]]
+    variants = [m["%s%d_h%d_v%d" % (name, j, h, t)].astype(np.float32) / 4.0 for t in range(T)]
+    return H, W, window, overlap, variants, [int(r) for r in m["%s%d_rots" % (name, j)]], [str(f) for f in m["%s%d_flips" % (name, j)]]
+
+
+def test_oracle_regression_head_tta_mean():
+    """dist.py:398-406 (plain mean of the reversed distance maps) and hovernet.py:406 (variant 0 only), from source."""
+    m = _r2()
+    for j in range(3):
+        for name, h, first_only in (("d", 1, False), ("h", 1, True)):
+            H, W, window, overlap, variants, rots, flips = _reg_case(m, name, j, h)
+            rev = []
+            for v, r, f in zip(variants, rots, flips):
+                Ht, Wt = (W, H) if (r // 90) % 2 else (H, W)
+                full = opp.split_stitch(v[0], Ht, Wt, window, overlap) if window else v[0]
+                rev.append(opp.reverse_tta_transform(full, r, f))
+            want = m["%s%d_out%d" % (name, j, h)][0]
+            got = rev[0] if first_only else opp.tta_plain_mean(rev)
+            assert np.array_equal(got, want), (name, j)
+
+
+def test_oracle_three_class_gt():
+    m = _r2()
+    for j in range(3):
+        assert np.array_equal(opp.three_class_gt(m["g%d_wb" % j], int(m["g%d_nc" % j])), m["g%d_tc" % j])
+
+
+def _id_dict(m, n, side):
+    keys, lens, ids = m[n + "_" + side + "_keys"], m[n + "_" + side + "_lens"], m[n + "_" + side + "_ids"]
+    out, o = {}, 0
+    for k, l in zip(keys, lens):
+        out[int(k)] = [int(v) for v in ids[o:o + l]]
+        o += int(l)
+    return out
+
+
+def test_oracle_pre_eval_with_id_dictionaries_and_match_iou():
+    """pre_eval_aji / pre_eval_pq called the way conic.py:178-188 calls them, and pre_eval_bin_pq(match_iou > 0.5)."""
+    m = _r2()
+    for k in range(int(m["n_pair_cases"])):
+        n = "p%d" % k
+        ip, ig = m[n + "_ip"], m[n + "_ig"]
+        dp, dg = _id_dict(m, n, "dp"), _id_dict(m, n, "dg")
+        for rz in (True, False):
+            got = np.stack(om.pre_eval_aji(ip, ig, dp, dg, 4, reduce_zero_label=rz, literal=False))
+            assert np.array_equal(got, m[n + "_aji_rz%d" % rz]), (n, rz)
+            got = np.stack(om.pre_eval_pq(ip, ig, dp, dg, 4, reduce_zero_label=rz, literal=False))
+            assert np.array_equal(got, m[n + "_pq_rz%d" % rz]), (n, rz)
+        for mi in (0.5, 0.6, 0.75, 0.9):
+            got = np.array(om.pre_eval_bin_pq(ip, ig, mi, literal=False), np.float64)
+            assert np.array_equal(got, m[n + "_binpq_%d" % int(mi * 100)]), (n, mi)
+

@@ -29,6 +29,10 @@ SIGNATURES = {
     "tiseg_softmax_argmax": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_tta_input_elems": [_i, _i, _i, _i, _vp, _i, _i],
     "tiseg_softmax_argmax_tta": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "tiseg_tta_mean": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp],
+    "tiseg_ddm_enhance": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i],
+    "tiseg_mtcdnet_refine": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tiseg_pair_metrics_bin_iou": [_vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _vp, _vp],
     "tiseg_label": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_label_u8": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_re_instance": [_vp, _vp, _i, _i, _i, _vp, _vp],

@@ -169,21 +169,35 @@ k_point_mean(Geom g, const float* __restrict__ point_logits, int T, float* __res
     if (px.lane == 0 && k > pmax_key[px.n]) atomicMax(&pmax_key[px.n], k);
 }
 
-// _ddm_enhencement + argmax: the last semantic channel becomes (p + dd') * (1 + dd'), dd' = dd - dd * point_map
+// _ddm_enhencement + argmax.
+//   mode 0 (cdnet.py:354-367):            p[-1] = (p[-1] + dd') * (1 + dd'),  dd' = dd - dd * (point / max(point) > 0.2)
+//   mode 1 (multi_task_cdnet.py:548-564): f = ((point + 0.2) / max(point + 0.2))^2,  dd' = dd - dd * (f > 0.6),
+//                                         p[-1] = p[-1] * (1 + dd') * (1 - f), values >= 1 become 0.95
+//         (its last line, `sem_logit[:, -2][foreground_map == 0.8] = 1`, compares a bool map with 0.8 and never fires)
+// fp32 throughout, operations in the reference's order; max(point + 0.2) = fl(max(point) + 0.2f) because fp32 addition is
+// monotone.
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ddm_enhance(Geom g, float* __restrict__ sem_prob, int C, const float* __restrict__ dd, const float* __restrict__ pmean,
-              const int* __restrict__ pmax_key, int if_ddm, uint8_t* __restrict__ cls) {
+              const int* __restrict__ pmax_key, int if_ddm, int mode, uint8_t* __restrict__ cls) {
     Pix px;
     if (!warp_pixel(g, px) || !px.ok) return;
     const long long P = g.P;
     float* sp = sem_prob + (long long)px.n * C * P + px.idx;
     if (if_ddm) {
-        float pm = float_from_key(pmax_key[px.n]);
-        float pmap = (pmean[px.base + px.idx] / pm) > 0.2f ? 1.f : 0.f;
-        float d = dd[px.base + px.idx];
-        float d2 = d - d * pmap;
-        float e = (sp[(C - 1) * P] + d2) * (1.f + d2);
-        sp[(C - 1) * P] = e;
+        const float pm = float_from_key(pmax_key[px.n]);
+        const float d = dd[px.base + px.idx];
+        if (mode == 0) {
+            const float pmap = (pmean[px.base + px.idx] / pm) > 0.2f ? 1.f : 0.f;
+            const float d2 = d - d * pmap;
+            sp[(C - 1) * P] = (sp[(C - 1) * P] + d2) * (1.f + d2);
+        } else {
+            const float t = (pmean[px.base + px.idx] + 0.2f) / (pm + 0.2f);
+            const float f = t * t;
+            const float d2 = d - d * (f > 0.6f ? 1.f : 0.f);
+            float e = (sp[(C - 1) * P] * (1.f + d2)) * (1.f - f);
+            if (e >= 1.f) e = 0.95f;
+            sp[(C - 1) * P] = e;
+        }
     }
     if (cls) {
         int best = 0;
@@ -255,9 +269,79 @@ int tiseg_cdnet_refine(tiseg_ctx* c, const float* sem_logits, const float* dir_l
     TISEG_TRY(ddm_dev(c, g, dir_all, T, d_dd));
     TISEG_LAUNCH(c, k_key_init, (N + 255) / 256, 256, 0, pmax, N);
     TISEG_LAUNCH(c, k_point_mean, warp_grid(g), TISEG_THREADS, 0, g, d_pt, T, pmean, pmax);
-    TISEG_LAUNCH(c, k_ddm_enhance, warp_grid(g), TISEG_THREADS, 0, g, d_prob, C, d_dd, pmean, pmax, if_ddm, d_cls);
+    TISEG_LAUNCH(c, k_ddm_enhance, warp_grid(g), TISEG_THREADS, 0, g, d_prob, C, d_dd, pmean, pmax, if_ddm, 0, d_cls);
     if (dir_map_out) {
         // dir_map_list[0] of every tile (cdnet.py:217)
+        uint8_t* d_dm = tiseg::out(c, dir_map_out, total);
+        if (!d_dm) return TISEG_ERR_CUDA;
+        TISEG_CHECK(cudaMemcpy2DAsync(d_dm, g.P, dir_all, (size_t)T * g.P, g.P, N, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return end_call(c);
+}
+
+int tiseg_ddm_enhance(tiseg_ctx* c, float* sem_prob, const float* dd, const float* point, int N, int C, int H, int W, int mode) {
+    if (!c || !sem_prob || !dd || !point || C < 2 || C > 16 || (mode != 0 && mode != 1)) {
+        set_error("tiseg_ddm_enhance: bad argument (2 <= C <= 16, mode 0 | 1)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    const size_t total = (size_t)N * g.P;
+    float* d_prob = (float*)inout_ptr(c, sem_prob, total * C * sizeof(float));
+    const float* d_dd = in(c, dd, total);
+    const float* d_pt = in(c, point, total);
+    float* pmean = ws<float>(c, total);
+    int* pmax = ws<int>(c, (size_t)N);
+    if (!d_prob || !d_dd || !d_pt || !pmean || !pmax) return TISEG_ERR_CUDA;
+    TISEG_LAUNCH(c, k_key_init, (N + 255) / 256, 256, 0, pmax, N);
+    TISEG_LAUNCH(c, k_point_mean, warp_grid(g), TISEG_THREADS, 0, g, d_pt, 1, pmean, pmax);
+    TISEG_LAUNCH(c, k_ddm_enhance, warp_grid(g), TISEG_THREADS, 0, g, d_prob, C, d_dd, pmean, pmax, 1, mode, (uint8_t*)nullptr);
+    return end_call(c);
+}
+
+int tiseg_mtcdnet_refine(tiseg_ctx* c, const float* tc_logits, const float* sem_logits, const float* dir_logits,
+                         const float* point_logits, int N, int T, int Ctc, int Csem, int D, int H, int W, int if_ddm,
+                         float* tc_prob_out, uint8_t* tc_cls_out, float* sem_prob_out, uint8_t* sem_cls_out,
+                         uint8_t* dir_map_out, float* dd_out) {
+    if (!c || !tc_logits || !sem_logits || !dir_logits || !point_logits || T <= 0 || Ctc < 2 || Ctc > 16 || Csem < 1 ||
+        Csem > 16 || D != 9) {
+        set_error("tiseg_mtcdnet_refine: bad argument (2 <= Ctc <= 16, 1 <= Csem <= 16, D == 9)");
+        return TISEG_ERR_ARG;
+    }
+    TISEG_TRY(check_geom(N * T, H, W));
+    begin_call(c);
+    Geom g = make_geom(N, H, W);
+    const size_t total = (size_t)N * g.P;
+    const float* d_tc = in(c, tc_logits, total * T * Ctc);
+    const float* d_sem = in(c, sem_logits, total * T * Csem);
+    const float* d_dir = in(c, dir_logits, total * T * D);
+    const float* d_pt = in(c, point_logits, total * T);
+    float* d_tcp = tc_prob_out ? tiseg::out(c, tc_prob_out, total * Ctc) : ws<float>(c, total * Ctc);
+    uint8_t* d_tcc = tc_cls_out ? tiseg::out(c, tc_cls_out, total) : nullptr;
+    float* d_semp = sem_prob_out ? tiseg::out(c, sem_prob_out, total * Csem) : nullptr;
+    uint8_t* d_semc = sem_cls_out ? tiseg::out(c, sem_cls_out, total) : nullptr;
+    float* d_dd = dd_out ? tiseg::out(c, dd_out, total) : ws<float>(c, total);
+    uint8_t* dir_all = ws<uint8_t>(c, total * T);
+    float* pmean = ws<float>(c, total);
+    int* pmax = ws<int>(c, (size_t)N);
+    if (!d_tc || !d_sem || !d_dir || !d_pt || !d_tcp || !d_dd || !dir_all || !pmean || !pmax) return TISEG_ERR_CUDA;
+    // softmax + TTA mean of the three-class and of the semantic head (multi_task_cdnet.py:283-294)
+    TISEG_TRY(softmax_argmax_dev(c, g, d_tc, T, Ctc, d_tcp, nullptr));
+    if (d_semp || d_semc) {
+        float* sp = d_semp;
+        if (!sp && T > 1) { sp = ws<float>(c, total * Csem); if (!sp) return TISEG_ERR_CUDA; }      // (T == 1: streaming argmax)
+        TISEG_TRY(softmax_argmax_dev(c, g, d_sem, T, Csem, sp, d_semc));
+    }
+    {   // per variant: dir[:, 0] *= tc[:, 0]; argmax; DDM (:318-322)
+        const bool v4 = (g.P % 4 == 0) && aligned16(d_dir, d_tcp) && (((uintptr_t)dir_all) & 3) == 0;
+        TISEG_LAUNCH(c, k_dir_map<9>, dim3(flat4_grid(g.P), (unsigned)N), TISEG_THREADS, 0, (long long)g.P, d_dir, d_tcp, T, D, Ctc, dir_all, v4);
+    }
+    TISEG_TRY(ddm_dev(c, g, dir_all, T, d_dd));
+    TISEG_LAUNCH(c, k_key_init, (N + 255) / 256, 256, 0, pmax, N);
+    TISEG_LAUNCH(c, k_point_mean, warp_grid(g), TISEG_THREADS, 0, g, d_pt, T, pmean, pmax);
+    TISEG_LAUNCH(c, k_ddm_enhance, warp_grid(g), TISEG_THREADS, 0, g, d_tcp, Ctc, d_dd, pmean, pmax, if_ddm, 1, d_tcc);
+    if (dir_map_out) {
         uint8_t* d_dm = tiseg::out(c, dir_map_out, total);
         if (!d_dm) return TISEG_ERR_CUDA;
         TISEG_CHECK(cudaMemcpy2DAsync(d_dm, g.P, dir_all, (size_t)T * g.P, g.P, N, cudaMemcpyDeviceToDevice, c->stream));

@@ -223,7 +223,7 @@ k_pair_bits(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restr
 
 // pass A over the table: best AJI IoU per gt (atomicMax on fp64 bits: positive doubles order like integers),
 // and the PQ matches (IoU > 0.5 is unique per gt and per pred)
-__global__ void k_pair_best(PairTab tt, InstState s, int* tp) {
+__global__ void k_pair_best(PairTab tt, InstState s, int* tp, double match_iou) {
     const PairTabView t = tt.view();
     int n = blockIdx.y;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < t.cap; slot += gridDim.x * blockDim.x) {
@@ -238,7 +238,7 @@ __global__ void k_pair_best(PairTab tt, InstState s, int* tp) {
     double iou_aji = inter / ((tot - inter) + 1.0e-6);      // inst_metrics.py:69
     atomicMax(&s.best[o + gid], (unsigned long long)__double_as_longlong(iou_aji));
     double iou_pq = inter / (tot - inter);                  // inst_metrics.py:194
-    if (iou_pq > 0.5) { s.pqiou[o + gid] = iou_pq; atomicAdd(&tp[n * s.C + cg], 1); }
+    if (iou_pq > match_iou) { s.pqiou[o + gid] = iou_pq; atomicAdd(&tp[n * s.C + cg], 1); }     // inst_metrics.py:197-203, match_iou >= 0.5
     }
 }
 
@@ -753,7 +753,7 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
 
 // AJI / PQ records from a built table; cls_* NULL = binary
 static int pair_eval(tiseg_ctx* c, const Geom& g, PairWork& w, const uint8_t* cls_g, const uint8_t* cls_p, int C,
-                     const ClassInfo& ci, bool first_eval, double* d_aji, double* d_pq) {
+                     const ClassInfo& ci, bool first_eval, double* d_aji, double* d_pq, double match_iou = 0.5) {
     int N = g.N;
     InstState s = w.s;
     s.cls_g = cls_g; s.cls_p = cls_p; s.C = C;
@@ -764,7 +764,7 @@ static int pair_eval(tiseg_ctx* c, const Geom& g, PairWork& w, const uint8_t* cl
     TISEG_TRY(zero(c, tp, (size_t)N * C * sizeof(int)));
     if (!first_eval) TISEG_LAUNCH(c, k_inst_init, dim3(16, N), 256, 0, s, 0);
     dim3 tg((w.t.small.cap + 255) / 256, N);                 // the kernels stride over the table in force
-    TISEG_LAUNCH(c, k_pair_best, tg, 256, 0, w.t, s, tp);
+    TISEG_LAUNCH(c, k_pair_best, tg, 256, 0, w.t, s, tp, match_iou);
     TISEG_LAUNCH(c, k_pair_argbest, tg, 256, 0, w.t, s);
     TISEG_LAUNCH(c, k_aji_gt, dim3(8, N), 256, 0, w.t, s, IU);
     TISEG_LAUNCH(c, k_aji_pred, dim3(8, N), 256, 0, s, IU);
@@ -844,7 +844,15 @@ int tiseg_assign_sem_class(tiseg_ctx* c, const int32_t* inst, const uint8_t* sem
 
 int tiseg_pair_metrics_bin(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, int N, int H, int W,
                            double* aji, double* pq) {
-    if (!c || !pred || !gt) { set_error("tiseg_pair_metrics_bin: bad argument"); return TISEG_ERR_ARG; }
+    return tiseg_pair_metrics_bin_iou(c, pred, gt, N, H, W, 0.5, aji, pq);
+}
+
+int tiseg_pair_metrics_bin_iou(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, int N, int H, int W, double match_iou,
+                               double* aji, double* pq) {
+    if (!c || !pred || !gt || !(match_iou >= 0.5)) {
+        set_error("tiseg_pair_metrics_bin: bad argument (match_iou >= 0.5: below it the reference switches to Hungarian matching)");
+        return TISEG_ERR_ARG;
+    }
     TISEG_TRY(check_geom(N, H, W));
     begin_call(c);
     Geom g = make_geom(N, H, W);
@@ -857,7 +865,7 @@ int tiseg_pair_metrics_bin(tiseg_ctx* c, const int32_t* pred, const int32_t* gt,
     PairWork w;
     TISEG_TRY(pair_table_build(c, g, d_pred, d_gt, w, nullptr));
     ClassInfo ci = {nullptr, nullptr, nullptr, nullptr};
-    TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, ci, true, d_aji, d_pq));
+    TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, ci, true, d_aji, d_pq, match_iou));
     return end_call(c);
 }
 

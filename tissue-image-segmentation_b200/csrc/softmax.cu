@@ -184,7 +184,9 @@ __device__ __forceinline__ long long window_source(const TtaPlan& p, int C, int 
     return ((long long)(my * Mx + mx) * C) * win * win + (long long)(Y - my * st) * win + (X - mx * st);
 }
 
-template <int CMAX>
+// SOFTMAX = false: the plain mean of the reverse-transformed variants, what the reference does with its regression heads
+// (`sum(dist_logit_list) / len(dist_logit_list)`, dist.py:398-410; hovernet.py:406 keeps variant 0 only, i.e. T = 1)
+template <int CMAX, bool SOFTMAX>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_softmax_argmax_tta(Geom g, const float* __restrict__ in, TtaPlan plan, int C, float* __restrict__ prob,
                      uint8_t* __restrict__ cls) {
@@ -199,11 +201,16 @@ k_softmax_argmax_tta(Geom g, const float* __restrict__ in, TtaPlan plan, int C, 
         float xv[CMAX], m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) if (c < C) { xv[c] = src[c * cs]; m = fmaxf(m, xv[c]); }
-        float sum = 0.f;
+        if (SOFTMAX) {
+            float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) if (c < C) { xv[c] = expf(xv[c] - m); sum = sum + xv[c]; }
+            for (int c = 0; c < CMAX; ++c) if (c < C) { xv[c] = expf(xv[c] - m); sum = sum + xv[c]; }
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) if (c < C) acc[c] = (t == 0) ? xv[c] / sum : acc[c] + xv[c] / sum;
+            for (int c = 0; c < CMAX; ++c) if (c < C) acc[c] = (t == 0) ? xv[c] / sum : acc[c] + xv[c] / sum;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < C) acc[c] = (t == 0) ? xv[c] : acc[c] + xv[c];
+        }
     }
     const float tf = (float)plan.T;
     int best = 0;
@@ -241,9 +248,8 @@ extern "C" long long tiseg_tta_input_elems(int T, int C, int H, int W, const int
     return n;
 }
 
-extern "C" int tiseg_softmax_argmax_tta(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W,
-                                        const int* rotate_degrees, const int* flips, int window, int overlap,
-                                        float* prob, uint8_t* cls) {
+static int tta_entry(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W, const int* rotate_degrees,
+                     const int* flips, int window, int overlap, float* prob, uint8_t* cls, bool softmax) {
     if (!c || !logits || !rotate_degrees || !flips || T <= 0 || T > 16 || C <= 0 || C > 16 || (!prob && !cls) ||
         window < 0 || (window > 0 && (overlap < 0 || overlap >= window))) {
         set_error("tiseg_softmax_argmax_tta: bad argument (1 <= T, C <= 16, 0 <= overlap < window)");
@@ -269,10 +275,28 @@ extern "C" int tiseg_softmax_argmax_tta(tiseg_ctx* c, const float* logits, int N
     float* d_prob = prob ? tiseg::out(c, prob, total * C) : nullptr;
     uint8_t* d_cls = cls ? tiseg::out(c, cls, total) : nullptr;
     if (!d_in) return TISEG_ERR_CUDA;
-    if (C <= 4) TISEG_LAUNCH(c, k_softmax_argmax_tta<4>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
-    else if (C <= 8) TISEG_LAUNCH(c, k_softmax_argmax_tta<8>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
-    else TISEG_LAUNCH(c, k_softmax_argmax_tta<16>, warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    if (softmax) {
+        if (C <= 4) TISEG_LAUNCH(c, (k_softmax_argmax_tta<4, true>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+        else if (C <= 8) TISEG_LAUNCH(c, (k_softmax_argmax_tta<8, true>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+        else TISEG_LAUNCH(c, (k_softmax_argmax_tta<16, true>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    } else {
+        if (C <= 4) TISEG_LAUNCH(c, (k_softmax_argmax_tta<4, false>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+        else if (C <= 8) TISEG_LAUNCH(c, (k_softmax_argmax_tta<8, false>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+        else TISEG_LAUNCH(c, (k_softmax_argmax_tta<16, false>), warp_grid(g), TISEG_THREADS, 0, g, d_in, plan, C, d_prob, d_cls);
+    }
     return end_call(c);
+}
+
+extern "C" int tiseg_softmax_argmax_tta(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W,
+                                        const int* rotate_degrees, const int* flips, int window, int overlap,
+                                        float* prob, uint8_t* cls) {
+    return tta_entry(c, logits, N, T, C, H, W, rotate_degrees, flips, window, overlap, prob, cls, true);
+}
+
+extern "C" int tiseg_tta_mean(tiseg_ctx* c, const float* maps, int N, int T, int C, int H, int W, const int* rotate_degrees,
+                              const int* flips, int window, int overlap, float* mean_out) {
+    if (!mean_out) { set_error("tiseg_tta_mean: null output"); return TISEG_ERR_ARG; }
+    return tta_entry(c, maps, N, T, C, H, W, rotate_degrees, flips, window, overlap, mean_out, nullptr, false);
 }
 
 extern "C" int tiseg_softmax_argmax(tiseg_ctx* c, const float* logits, int N, int T, int C, int H, int W,

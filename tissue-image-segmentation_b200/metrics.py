@@ -40,13 +40,13 @@ def pre_eval_bin_aji(inst_pred, inst_gt):
 
 
 def pre_eval_bin_pq(inst_pred, inst_gt, match_iou=0.5):
-    """inst_metrics.py:138-229 -> (tp, fp, fn, iou_sum).  Only the reference default ``match_iou=0.5`` is
-    implemented on the device (the Hungarian branch for match_iou < 0.5 is never reached by the reference's
-    callers)."""
+    """inst_metrics.py:138-229 -> (tp, fp, fn, iou_sum).  ``match_iou >= 0.5`` as in the reference's unique-matching
+    branch (:197-203); below 0.5 the reference switches to Hungarian matching (:204-218), which none of its callers
+    reaches and which is not built."""
     assert match_iou >= 0.0, "Cant' be negative"
-    if match_iou != 0.5:
-        raise NotImplementedError("tiseg_b200 implements the reference default match_iou=0.5 only")
-    _, pq = ops.pair_metrics_bin(inst_pred, inst_gt)
+    if match_iou < 0.5:
+        raise NotImplementedError("match_iou < 0.5 (Hungarian matching, inst_metrics.py:204-218) is not implemented")
+    _, pq = ops.pair_metrics_bin(inst_pred, inst_gt, match_iou)
     pq = _host(pq)
     if pq.ndim == 2:
         return [(int(r[0]), int(r[1]), int(r[2]), np.float64(r[3])) for r in pq]
@@ -59,17 +59,56 @@ def _split_multiclass(rec, reduce_zero_label):
     return tuple(c[..., 1:] for c in cols) if reduce_zero_label else cols
 
 
-def pre_eval_aji(inst_pred, inst_gt, sem_pred, sem_gt, num_classes, reduce_zero_label=True):
-    """inst_metrics.py:95-135 with the class assignment of instance_semantic.py:68-93 done on the device:
-    pass the semantic maps instead of the per-class id dictionaries.  -> (inter[C-1], union[C-1]) float32."""
-    r = ops.pair_metrics_multiclass(inst_pred, sem_pred, inst_gt, sem_gt, num_classes, want_bin=False)
-    return _split_multiclass(r["aji"], reduce_zero_label)
+def _maps_from_id_lists(inst, id_list_per_class, num_classes):
+    """The reference's ``{class: [instance ids]}`` form (what ``assign_sem_class_to_insts`` returns,
+    instance_semantic.py:68-93) -> (instance map with unlisted ids removed, class map): every listed instance is painted
+    with its class, so the device-side majority vote reproduces the dictionary exactly; ids that appear in no list do not
+    take part in the reference's sums at all (inst_metrics.py:103-131) and are zeroed."""
+    inst = np.asarray(_host(inst))
+    top = int(inst.max()) if inst.size else 0
+    lut = np.full(top + 2, -1, np.int64)
+    for cls, ids in id_list_per_class.items():
+        if not 0 <= int(cls) < num_classes:
+            raise IndexError("class id %r outside [0, %d)" % (cls, num_classes))     # the reference indexes [num_classes] arrays
+        for i in ids:
+            i = int(i)
+            if 0 < i <= top:
+                if lut[i] not in (-1, int(cls)):
+                    raise ValueError("instance id %d is listed under two classes" % i)
+                lut[i] = int(cls)
+    cls_of = lut[np.clip(inst, 0, top + 1)]
+    keep = (cls_of >= 0) & (inst > 0)
+    return np.where(keep, inst, 0).astype(np.int32), np.where(keep, cls_of, 0).astype(np.uint8)
 
 
-def pre_eval_pq(inst_pred, inst_gt, sem_pred, sem_gt, num_classes, reduce_zero_label=True):
-    """inst_metrics.py:232-280 -> (tp, fp, fn, iou)[C-1] float32."""
-    r = ops.pair_metrics_multiclass(inst_pred, sem_pred, inst_gt, sem_gt, num_classes, want_bin=False)
-    return _split_multiclass(r["pq"], reduce_zero_label)
+def _multiclass(inst_pred, inst_gt, a, b, num_classes):
+    """dispatch on the reference's argument form (id dictionaries) vs the semantic maps themselves"""
+    if isinstance(a, dict) and isinstance(b, dict):
+        ip, sp = _maps_from_id_lists(inst_pred, a, num_classes)
+        ig, sg = _maps_from_id_lists(inst_gt, b, num_classes)
+        r = ops.pair_metrics_multiclass(ip, sp, ig, sg, num_classes, want_bin=False)
+        aji, pq = _host(r["aji"]).copy(), _host(r["pq"]).copy()
+        # slot 0 of PQ counts the LIST entries of class 0 (inst_metrics.py:249-252), id 0 included only if it is listed
+        if 0 in a or 0 in b:
+            pq[0, :] = 0
+            pq[0, 1], pq[0, 2] = len(a[0]), len(b[0])       # (KeyError like the reference if only one side lists class 0)
+        return aji, pq
+    r = ops.pair_metrics_multiclass(inst_pred, a, inst_gt, b, num_classes, want_bin=False)
+    return r["aji"], r["pq"]
+
+
+def pre_eval_aji(inst_pred, inst_gt, pred_id_list_per_class, gt_id_list_per_class, num_classes, reduce_zero_label=True):
+    """inst_metrics.py:95-135 -> (inter[C-1], union[C-1]) float32.  Called like the reference (conic.py:178-188) with the
+    two ``{class: [instance ids]}`` dictionaries of ``assign_sem_class_to_insts``; the two semantic maps may be passed in
+    their place, the class assignment (instance_semantic.py:68-93) then runs on the device as well."""
+    aji, _ = _multiclass(inst_pred, inst_gt, pred_id_list_per_class, gt_id_list_per_class, num_classes)
+    return _split_multiclass(aji, reduce_zero_label)
+
+
+def pre_eval_pq(inst_pred, inst_gt, pred_id_list_per_class, gt_id_list_per_class, num_classes, reduce_zero_label=True):
+    """inst_metrics.py:232-280 -> (tp, fp, fn, iou)[C-1] float32; arguments as ``pre_eval_aji``."""
+    _, pq = _multiclass(inst_pred, inst_gt, pred_id_list_per_class, gt_id_list_per_class, num_classes)
+    return _split_multiclass(pq, reduce_zero_label)
 
 
 def pre_eval_all_semantic_metric(pred_label, target_label, num_classes, ignore_index=255, reduce_zero_label=True):

@@ -166,8 +166,9 @@ def postproc_dist(dist, debug=False, lamb=0):
     return _unbatch(inst, was2d)
 
 
-def pair_metrics_bin(inst_pred, inst_gt):
-    """A16 + A17 in one pass.  -> (aji [N,2] fp64 = (inter, union), pq [N,4] fp64 = (tp, fp, fn, iou))."""
+def pair_metrics_bin(inst_pred, inst_gt, match_iou=0.5):
+    """A16 + A17 in one pass.  -> (aji [N,2] fp64 = (inter, union), pq [N,4] fp64 = (tp, fp, fn, iou)).
+    ``match_iou`` >= 0.5: a pair counts as a PQ match when its IoU is greater (inst_metrics.py:197-203)."""
     p, was2d = batched(as_input(inst_pred, np.int32))
     g, _ = batched(as_input(inst_gt, np.int32))
     if tuple(p.shape) != tuple(g.shape):
@@ -175,7 +176,8 @@ def pair_metrics_bin(inst_pred, inst_gt):
     N, H, W = p.shape
     aji = empty_like_kind(p, (N, 2), np.float64)
     pq = empty_like_kind(p, (N, 4), np.float64)
-    get_ctx(_dev(p)).call("tiseg_pair_metrics_bin", ptr(p), ptr(g), N, H, W, ptr(aji), ptr(pq))
+    import ctypes
+    get_ctx(_dev(p)).call("tiseg_pair_metrics_bin_iou", ptr(p), ptr(g), N, H, W, ctypes.c_double(float(match_iou)), ptr(aji), ptr(pq))
     return (aji[0], pq[0]) if was2d else (aji, pq)
 
 
@@ -239,6 +241,50 @@ def cdnet_refine(sem_logits, dir_logits, point_logits, if_ddm=True):
     get_ctx(_dev(s)).call("tiseg_cdnet_refine", ptr(s), ptr(d), ptr(p), N, T, C, D, H, W, 1 if if_ddm else 0,
                           ptr(prob), ptr(cls), ptr(dm), ptr(dd))
     out = dict(sem_prob=prob, cls=cls, dir_map=dm, dd=dd)
+    return {k: v[0] for k, v in out.items()} if single else out
+
+
+def ddm_enhance(sem_prob, dd_map, point_map, mode=0):
+    """``_ddm_enhencement`` IN PLACE on ``sem_prob`` [N,C,H,W] / [C,H,W] fp32 (C-contiguous array or tensor): mode 0 =
+    CDNet (cdnet.py:354-367), mode 1 = MultiTaskCDNet (multi_task_cdnet.py:548-564).  dd_map / point_map [N,H,W] / [H,W]."""
+    x = _inplace_arg(sem_prob, np.float32, "ddm_enhance: sem_prob")
+    single = x.ndim == 3
+    xb = x[None] if single else x
+    d = as_input(dd_map, np.float32)
+    q = as_input(point_map, np.float32)
+    if single:
+        d, q = d.reshape((1,) + tuple(d.shape[-2:])), q.reshape((1,) + tuple(q.shape[-2:]))
+    N, C, H, W = xb.shape
+    if tuple(d.shape) != (N, H, W) or tuple(q.shape) != (N, H, W):
+        raise ValueError("dd_map / point_map must be [N,H,W] matching sem_prob, got %r / %r" % (tuple(d.shape), tuple(q.shape)))
+    get_ctx(_dev(xb)).call("tiseg_ddm_enhance", ptr(xb), ptr(d), ptr(q), N, C, H, W, int(mode))
+    return sem_prob
+
+
+def mtcdnet_refine(tc_logits, sem_logits, dir_logits, point_logits, if_ddm=True, want_sem_prob=False):
+    """MultiTaskCDNet.inference tail (multi_task_cdnet.py:262-330, use_regression = False).  tc_logits [N,T,Ctc,H,W],
+    sem_logits [N,T,Csem,H,W], dir_logits [N,T,9,H,W], point_logits [N,T,1,H,W] (or without the leading N) ->
+    dict(tc_prob, tc_cls, sem_cls, dir_map, dd[, sem_prob])."""
+    t = as_input(tc_logits, np.float32)
+    s = as_input(sem_logits, np.float32)
+    d = as_input(dir_logits, np.float32)
+    p = as_input(point_logits, np.float32)
+    single = t.ndim == 4
+    if single:
+        t, s, d, p = t[None], s[None], d[None], p[None]
+    N, T, Ctc, H, W = t.shape
+    Csem, D = s.shape[2], d.shape[2]
+    tcp = empty_like_kind(t, (N, Ctc, H, W), np.float32)
+    tcc = empty_like_kind(t, (N, H, W), np.uint8)
+    semc = empty_like_kind(t, (N, H, W), np.uint8)
+    semp = empty_like_kind(t, (N, Csem, H, W), np.float32) if want_sem_prob else None
+    dm = empty_like_kind(t, (N, H, W), np.uint8)
+    dd = empty_like_kind(t, (N, H, W), np.float32)
+    get_ctx(_dev(t)).call("tiseg_mtcdnet_refine", ptr(t), ptr(s), ptr(d), ptr(p), N, T, Ctc, Csem, D, H, W, 1 if if_ddm else 0,
+                          ptr(tcp), ptr(tcc), ptr(semp), ptr(semc), ptr(dm), ptr(dd))
+    out = dict(tc_prob=tcp, tc_cls=tcc, sem_cls=semc, dir_map=dm, dd=dd)
+    if want_sem_prob:
+        out["sem_prob"] = semp
     return {k: v[0] for k, v in out.items()} if single else out
 
 
@@ -351,6 +397,33 @@ def softmax_argmax_tta(variants, rotate_degrees, flip_directions, ori_hw, window
     get_ctx(_dev(packed)).call("tiseg_softmax_argmax_tta", ptr(packed), N, T, C, H, W, rots, flips, int(window),
                                int(overlap), ptr(prob), ptr(cls))
     return (cls, prob) if want_prob else cls
+
+
+def tta_mean(variants, rotate_degrees, flip_directions, ori_hw, window=0, overlap=0):
+    """Window stitch + TTA reverse + PLAIN mean of a regression head (dist.py:398-410: ``sum(dist_logit_list) /
+    len(dist_logit_list)``; hovernet.py:406 keeps ``hv_logit_list[0]``: pass that one variant).  Arguments as
+    ``softmax_argmax_tta``.  -> [N, C, H, W] fp32."""
+    import ctypes
+    T = len(variants)
+    if not (T == len(rotate_degrees) == len(flip_directions)):
+        raise ValueError("one rotate_degree and one flip_direction per variant")
+    H, W = int(ori_hw[0]), int(ori_hw[1])
+    vs = [as_input(v, np.float32) for v in variants]
+    N = int(vs[0].shape[0])
+    C = int(vs[0].shape[1] if window == 0 else vs[0].shape[2])
+    rots = (ctypes.c_int * T)(*[int(r) for r in rotate_degrees])
+    flips = (ctypes.c_int * T)(*[_FLIPS[f] for f in flip_directions])
+    per_tile = int(_lib.load().tiseg_tta_input_elems(T, C, H, W, rots, int(window), int(overlap)))
+    if sum(int(np.prod(v.shape[1:])) for v in vs) != per_tile:
+        raise ValueError("variant shapes do not match the transforms / window geometry")
+    if _lib_is_torch(vs[0]):
+        import torch
+        packed = torch.cat([v.reshape(N, -1) for v in vs], dim=1).contiguous()
+    else:
+        packed = np.ascontiguousarray(np.concatenate([v.reshape(N, -1) for v in vs], axis=1))
+    out = empty_like_kind(packed, (N, C, H, W), np.float32)
+    get_ctx(_dev(packed)).call("tiseg_tta_mean", ptr(packed), N, T, C, H, W, rots, flips, int(window), int(overlap), ptr(out))
+    return out
 
 
 def mudslide_watershed(seg, dir_graph, fore):
