@@ -121,3 +121,55 @@ def test_device_resident_path_matches_host_path():
     for x, y in zip(a, b):
         assert dev[0]['inst_pred'].is_cuda
         same_result(x, y)
+
+
+def test_host_feed_chunks_equal_single_call():
+    """parallel.HostFeed (the caller loop for host-resident inputs): 40 host tiles fed in chunks of 8
+    alternating over 4 lanes (own stream + own workspace each) give, tile by tile, the records of ONE call on the whole
+    batch, and the oracle's records on two of them."""
+    import torch
+    from tiseg_b200 import _lib, ops, parallel
+    from oracle import metrics as om
+    H = W = 256
+    base = [synth.tile_dist(2, 700 + j, H=H, W=W) for j in range(10)]
+    n = 40
+    var = lambda a, k: np.ascontiguousarray(np.rot90(a, k % 4, axes=(-2, -1))[..., ::-1] if k >= 4 else np.rot90(a, k % 4, axes=(-2, -1)))
+    arrays = {key: np.stack([var(base[i % 10][key], i // 10) for i in range(n)]) for key in ("sem_logit", "dist_logit", "gt_inst", "gt_sem")}
+    arrays["sem_logit"] = arrays["sem_logit"][:, None]
+    pinned = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in arrays.items()}
+
+    def records(src):
+        cls = ops.softmax_argmax(src["sem_logit"])
+        inst = ops.postproc_dist(src["dist_logit"])
+        aji, pq = ops.pair_metrics_bin(inst, src["gt_inst"])
+        counts, valid = ops.sem_counts(cls, src["gt_sem"], 2)
+        return inst, aji, pq, counts
+
+    with _lib.device_outputs():
+        inst1, aji1, pq1, cnt1 = records(pinned)
+    torch.cuda.synchronize()
+    feed = parallel.HostFeed(0, lanes=4, chunk=8)
+    dev = torch.device("cuda", 0)
+    out = dict(inst=torch.zeros(n, H, W, dtype=torch.int32, device=dev), aji=torch.zeros(n, 2, dtype=torch.float64, device=dev),
+               pq=torch.zeros(n, 4, dtype=torch.float64, device=dev), cnt=torch.zeros(n, 5, 2, dtype=torch.int64, device=dev))
+    cursor = [0]
+
+    def chunk_fn(src, lane):
+        lo = cursor[0]
+        inst, aji, pq, counts = records(src)
+        k = inst.shape[0]
+        out["inst"][lo:lo + k], out["aji"][lo:lo + k], out["pq"][lo:lo + k], out["cnt"][lo:lo + k] = inst, aji, pq, counts
+        cursor[0] = lo + k
+
+    for _ in range(2):                      # twice: the second pass reuses every lane's workspace
+        cursor[0] = 0
+        feed.run(pinned, chunk_fn)
+    torch.cuda.synchronize()
+    assert cursor[0] == n
+    assert torch.equal(out["inst"], inst1) and torch.equal(out["aji"], aji1) and torch.equal(out["pq"], pq1) and torch.equal(out["cnt"], cnt1)
+    for j in (3, 27):
+        _, want_inst = opp.dist_postprocess(None, arrays["dist_logit"][j], literal=False)
+        assert np.array_equal(out["inst"][j].cpu().numpy(), want_inst)
+        assert tuple(out["aji"][j].cpu().numpy()) == tuple(np.float64(om.pre_eval_bin_aji(want_inst, arrays["gt_inst"][j], literal=False)))
+        assert tuple(out["pq"][j].cpu().numpy()) == tuple(np.float64(om.pre_eval_bin_pq(want_inst, arrays["gt_inst"][j], literal=False)))
+
