@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""ncu metrics pass of ONE whole step (scripts/full_pass.py, second pass captured) -> per-kernel DRAM bytes, L2 bytes,
-warp instructions and time: profiles/<tag>_step_traffic.json.  bench.py reads the file named by its workload to report
-`roofline.step_dram_bytes` / `traffic_ratio` and each kernel's fraction on min(algorithmic, measured) bytes.
+"""ncu metrics pass over scripts/step_pass.py (two identical steps; the SECOND is kept) -> per-kernel DRAM bytes, L2
+bytes, warp instructions and time of ONE whole step: profiles/r2_step_traffic_<workload>.json.  bench.py reads the file
+named by its workload to report `roofline.step_dram_bytes` / `traffic_ratio` and each kernel's fraction on
+min(algorithmic, measured) bytes.
 
-    python scripts/digest_step_traffic.py gpurun_out/r2_base_step_traffic.csv profiles/r2_base_step_traffic.json 64 22
+    python scripts/digest_step_traffic.py gpurun_out/r2_step_dist.csv profiles/r2_step_traffic_dist_monuseg_1000.json 64 22 1000 dist_monuseg_1000 [all]
 """
 import collections, csv, json, re, sys
 
@@ -24,6 +25,11 @@ for r in rows:
     k = per.setdefault((r["ID"], short), {})
     v = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1)
     k[r["Metric Name"]] = v
+if not (len(sys.argv) > 7 and sys.argv[7] == "all"):       # two steps were captured: keep the second (the capture
+    items = list(per.items())                                # starts with a launch sequence that repeats right after itself)
+    names = [k[1] for k, _ in items]
+    L = next(l for l in range(8, len(names) // 2 + 1) if names[l:2 * l] == names[:l])
+    per = collections.OrderedDict(items[L:2 * L])
 agg = collections.OrderedDict()
 for (_, short), m in per.items():
     a = agg.setdefault(short, {"launches": 0, "us": 0.0, "dram_bytes": 0.0, "l2_bytes": 0.0, "warp_inst": 0.0})
@@ -37,8 +43,8 @@ tot_us = sum(a["us"] for a in agg.values())
 alg = pipe_bpp * H * W * batch
 out = {"workload": workload, "batch": batch, "tile": [H, W],
        "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,"
-              "smsp__inst_executed.sum --clock-control none over the second pass of scripts/full_pass.py (one whole step; "
-              "per-launch times under ncu are serialised and cold-cache)",
+              "smsp__inst_executed.sum --clock-control none over the second of two steps of scripts/step_pass.py (one whole "
+              "step; per-launch times under ncu are serialised and cold-cache; cudaMemset is not a kernel and is not listed)",
        "launches": sum(a["launches"] for a in agg.values()), "step_dram_bytes": tot, "step_us_serialised": tot_us,
        "algorithmic_bytes": alg, "traffic_ratio": tot / alg,
        "kernels": {k: {kk: (round(vv, 1) if isinstance(vv, float) else vv) for kk, vv in a.items()}
