@@ -209,6 +209,10 @@ int tiseg_pair_metrics_bin(tiseg_ctx* ctx, const int32_t* pred, const int32_t* g
 /* the same with pre_eval_bin_pq's match_iou (>= 0.5; a pair matches when iou > match_iou, inst_metrics.py:197-203) */
 int tiseg_pair_metrics_bin_iou(tiseg_ctx* ctx, const int32_t* pred, const int32_t* gt, int N, int H, int W, double match_iou,
                                double* aji, double* pq);
+/* the same with the ground truth shipped as uint16 (ids below 65536: every dataset the reference converts,
+ * tools/convert_dataset/*.py): half the host-to-device bytes of the largest evaluation input */
+int tiseg_pair_metrics_bin_u16gt(tiseg_ctx* ctx, const int32_t* pred, const uint16_t* gt, int N, int H, int W, double match_iou,
+                                 double* aji, double* pq);
 
 /* ---- A18: CoNIC multi-class evaluation (conic.py:165-188) -----------------------------------------------
  * assign_sem_class_to_insts (datasets/utils/instance_semantic.py:68-93) on both sides, then pre_eval_aji /

@@ -994,3 +994,21 @@ def test_pre_eval_reference_signatures_with_id_dictionaries_and_match_iou():
     with pytest.raises(NotImplementedError):
         M.pre_eval_bin_pq(m["p0_ip"], m["p0_ig"], 0.3)
 
+
+def test_pair_metrics_uint16_ground_truth():
+    """A ground truth shipped as uint16 (ids < 65536) gives the records of the int32 map, host and device buffers."""
+    import torch
+    tiles = [synth.gt_and_pred(6100 + j, 200, 260) for j in range(4)]
+    p = np.stack([t["pred_inst"] for t in tiles]).astype(np.int32)
+    g = np.stack([t["gt_inst"] for t in tiles]).astype(np.int32)
+    g[1] = np.where(g[1] > 0, g[1] + 60000, 0)                       # large ids still below 65536
+    aji, pq = ops.pair_metrics_bin(p, g)
+    aji16, pq16 = ops.pair_metrics_bin(p, g.astype(np.uint16))
+    assert np.array_equal(aji, aji16) and np.array_equal(pq, pq16)
+    a2, q2 = ops.pair_metrics_bin(torch.from_numpy(p).cuda(), torch.from_numpy(g.astype(np.uint16)).cuda(), 0.6)
+    a3, q3 = ops.pair_metrics_bin(p, g, 0.6)
+    assert np.array_equal(a2.cpu().numpy(), a3) and np.array_equal(q2.cpu().numpy(), q3)
+    odd = (np.arange(37 * 53).reshape(37, 53) % 7).astype(np.int32)   # ragged width: the scalar load path
+    assert all(np.array_equal(x, y) for x, y in zip(ops.pair_metrics_bin(odd, odd[::-1].copy()),
+                                                    ops.pair_metrics_bin(odd, odd[::-1].astype(np.uint16))))
+

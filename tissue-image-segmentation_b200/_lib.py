@@ -33,6 +33,7 @@ SIGNATURES = {
     "tiseg_ddm_enhance": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i],
     "tiseg_mtcdnet_refine": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "tiseg_pair_metrics_bin_iou": [_vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _vp, _vp],
+    "tiseg_pair_metrics_bin_u16gt": [_vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _vp, _vp],
     "tiseg_label": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_label_u8": [_vp, _vp, _i, _i, _i, ctypes.c_int32, _i, _vp, _vp],
     "tiseg_re_instance": [_vp, _vp, _i, _i, _i, _vp, _vp],
@@ -227,7 +228,8 @@ def _torch_dtype(np_dtype):
     global _NP2T
     import torch
     if _NP2T is None:
-        _NP2T = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+        _NP2T = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16, np.dtype(np.int32): torch.int32,
+                 np.dtype(np.int64): torch.int64,
                  np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
     return _NP2T[np.dtype(np_dtype)]
 

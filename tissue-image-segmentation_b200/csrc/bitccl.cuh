@@ -119,23 +119,27 @@ __device__ __forceinline__ unsigned eq_word(unsigned nib, int lane) {      // va
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
     return w;
 }
-static __global__ void __launch_bounds__(TISEG_THREADS)
-k_eqbits_i32(Geom g, const int32_t* __restrict__ img, BitPlanesW out, bool vec) {
+// T = int32_t, or uint16_t (instance maps with ids below 65536 shipped at half the bytes)
+template <class T>
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_eqbits(Geom g, const T* __restrict__ img, BitPlanesW out, bool vec) {
     const int lane = threadIdx.x & 31;
     const int bands = (g.H + EQ_BAND - 1) / EQ_BAND, strips = (g.W + 127) >> 7;
     const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (wi >= (long long)strips * bands) return;
     const int band = (int)(wi / strips), strip = (int)(wi - (long long)band * strips), n = blockIdx.y;
     const int x = strip * 128 + lane * 4, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
-    const int32_t* t = img + (long long)n * g.P;
+    const T* t = img + (long long)n * g.P;
     const bool full = vec && x + 3 < g.W;
     // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
     const int xe = lane == 0 ? x - 1 : x + 4;
     const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
     auto load4 = [&](int y, int (&v)[4]) {
-        const int32_t* rp = t + (long long)y * g.W + x;
-        if (full) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-        else {
+        const T* rp = t + (long long)y * g.W + x;
+        if (full) {
+            if (sizeof(T) == 4) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+            else { const uint2 q = *reinterpret_cast<const uint2*>(rp); v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16; }
+        } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = x + k < g.W ? rp[k] : 0;
         }

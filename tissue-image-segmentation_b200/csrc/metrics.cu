@@ -175,7 +175,7 @@ k_pair_accumulate_big(Geom g, const int* __restrict__ par_g, const int* __restri
 // Pair table from bit planes (the default path of tiseg_pair_metrics_*; bitccl.cuh).
 //
 // measure.label of both maps (inst_metrics.py:12-13) only serves to IDENTIFY the components the pair matrix is indexed
-// by; no per-pixel label map is needed.  Both instance maps are read ONCE (k_eqbits_i32, 4 B/px each) into equality bit
+// by; no per-pixel label map is needed.  Both instance maps are read ONCE (k_eqbits, 4 B/px each) into equality bit
 // planes; the union-find, the cross-tile merges, the final-root bitmaps and their raster-order ranks work on words and
 // runs; and the pair histogram is accumulated by one thread per 32-pixel word from the planes of the two maps: a piece
 // of a row on which both labels are constant is delimited with bit operations, the component ids of its two runs are
@@ -713,9 +713,9 @@ static int pair_table_build_legacy(tiseg_ctx* c, const Geom& g, const int32_t* d
 
 // default path: bit planes (see the comment above k_pair_bits)
 static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, const int32_t* d_gt, PairWork& w,
-                            PairRoots* roots) {
+                            PairRoots* roots, const uint16_t* d_gt16 = nullptr) {
     static const bool legacy = getenv("TISEG_PAIR_LEGACY") != nullptr;
-    if (legacy) return pair_table_build_legacy(c, g, d_pred, d_gt, w, roots);
+    if (legacy && !d_gt16) return pair_table_build_legacy(c, g, d_pred, d_gt, w, roots);
     const int N = g.N;
     const size_t total = (size_t)N * g.P, words = (size_t)N * g.H * g.SEG;
     BitPlanesW pw;
@@ -735,8 +735,9 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
     const long long warps = (long long)((g.W + 127) / 128) * ((g.H + EQ_BAND - 1) / EQ_BAND);
     const dim3 eg((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N);
     BitPlanesW pwp = {pw.F + words, pw.C + words, pw.EU + words, pw.EL + words, pw.ER + words};
-    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_gt, pw, (g.W % 4 == 0) && aligned16(d_gt));
-    TISEG_LAUNCH(c, k_eqbits_i32, eg, TISEG_THREADS, 0, g, d_pred, pwp, (g.W % 4 == 0) && aligned16(d_pred));
+    if (d_gt16) TISEG_LAUNCH(c, k_eqbits<uint16_t>, eg, TISEG_THREADS, 0, g, d_gt16, pw, (g.W % 4 == 0) && (((uintptr_t)d_gt16) & 7) == 0);
+    else TISEG_LAUNCH(c, k_eqbits<int32_t>, eg, TISEG_THREADS, 0, g, d_gt, pw, (g.W % 4 == 0) && aligned16(d_gt));
+    TISEG_LAUNCH(c, k_eqbits<int32_t>, eg, TISEG_THREADS, 0, g, d_pred, pwp, (g.W % 4 == 0) && aligned16(d_pred));
     const BitPlanes p = as_const(pw);
     Geom g2 = make_geom(2 * N, g.H, g.W);                  // both maps as one batch: gt tiles, then pred tiles
     TISEG_TRY(bitccl_build(c, g2, p, 2, par, lbits, fbits));
@@ -847,9 +848,22 @@ int tiseg_pair_metrics_bin(tiseg_ctx* c, const int32_t* pred, const int32_t* gt,
     return tiseg_pair_metrics_bin_iou(c, pred, gt, N, H, W, 0.5, aji, pq);
 }
 
+static int pair_metrics_bin_any(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, const uint16_t* gt16, int N, int H, int W,
+                                double match_iou, double* aji, double* pq);
+
 int tiseg_pair_metrics_bin_iou(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, int N, int H, int W, double match_iou,
                                double* aji, double* pq) {
-    if (!c || !pred || !gt || !(match_iou >= 0.5)) {
+    return pair_metrics_bin_any(c, pred, gt, nullptr, N, H, W, match_iou, aji, pq);
+}
+
+int tiseg_pair_metrics_bin_u16gt(tiseg_ctx* c, const int32_t* pred, const uint16_t* gt, int N, int H, int W, double match_iou,
+                                 double* aji, double* pq) {
+    return pair_metrics_bin_any(c, pred, nullptr, gt, N, H, W, match_iou, aji, pq);
+}
+
+static int pair_metrics_bin_any(tiseg_ctx* c, const int32_t* pred, const int32_t* gt, const uint16_t* gt16, int N, int H, int W,
+                                double match_iou, double* aji, double* pq) {
+    if (!c || !pred || (!gt && !gt16) || !(match_iou >= 0.5)) {
         set_error("tiseg_pair_metrics_bin: bad argument (match_iou >= 0.5: below it the reference switches to Hungarian matching)");
         return TISEG_ERR_ARG;
     }
@@ -858,12 +872,13 @@ int tiseg_pair_metrics_bin_iou(tiseg_ctx* c, const int32_t* pred, const int32_t*
     Geom g = make_geom(N, H, W);
     size_t total = (size_t)N * g.P;
     const int32_t* d_pred = in(c, pred, total);
-    const int32_t* d_gt = in(c, gt, total);
+    const int32_t* d_gt = gt ? in(c, gt, total) : nullptr;
+    const uint16_t* d_gt16 = gt16 ? in(c, gt16, total) : nullptr;
     double* d_aji = aji ? tiseg::out(c, aji, 2 * (size_t)N) : nullptr;
     double* d_pq = pq ? tiseg::out(c, pq, 4 * (size_t)N) : nullptr;
-    if (!d_pred || !d_gt) return TISEG_ERR_CUDA;
+    if (!d_pred || (!d_gt && !d_gt16)) return TISEG_ERR_CUDA;
     PairWork w;
-    TISEG_TRY(pair_table_build(c, g, d_pred, d_gt, w, nullptr));
+    TISEG_TRY(pair_table_build(c, g, d_pred, d_gt, w, nullptr, d_gt16));
     ClassInfo ci = {nullptr, nullptr, nullptr, nullptr};
     TISEG_TRY(pair_eval(c, g, w, nullptr, nullptr, 2, ci, true, d_aji, d_pq, match_iou));
     return end_call(c);

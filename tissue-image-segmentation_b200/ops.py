@@ -170,14 +170,17 @@ def pair_metrics_bin(inst_pred, inst_gt, match_iou=0.5):
     """A16 + A17 in one pass.  -> (aji [N,2] fp64 = (inter, union), pq [N,4] fp64 = (tp, fp, fn, iou)).
     ``match_iou`` >= 0.5: a pair counts as a PQ match when its IoU is greater (inst_metrics.py:197-203)."""
     p, was2d = batched(as_input(inst_pred, np.int32))
-    g, _ = batched(as_input(inst_gt, np.int32))
+    # a uint16 ground truth (ids < 65536) is taken as it is: half the bytes to upload
+    gt16 = str(getattr(inst_gt, "dtype", "")) in ("uint16", "torch.uint16")
+    g, _ = batched(as_input(inst_gt, np.uint16 if gt16 else np.int32))
     if tuple(p.shape) != tuple(g.shape):
         raise ValueError("prediction / ground-truth shape mismatch: %r vs %r" % (tuple(p.shape), tuple(g.shape)))
     N, H, W = p.shape
     aji = empty_like_kind(p, (N, 2), np.float64)
     pq = empty_like_kind(p, (N, 4), np.float64)
     import ctypes
-    get_ctx(_dev(p)).call("tiseg_pair_metrics_bin_iou", ptr(p), ptr(g), N, H, W, ctypes.c_double(float(match_iou)), ptr(aji), ptr(pq))
+    get_ctx(_dev(p)).call("tiseg_pair_metrics_bin_u16gt" if gt16 else "tiseg_pair_metrics_bin_iou", ptr(p), ptr(g), N, H, W,
+                          ctypes.c_double(float(match_iou)), ptr(aji), ptr(pq))
     return (aji[0], pq[0]) if was2d else (aji, pq)
 
 
