@@ -240,16 +240,20 @@ k_plateau_low(Geom g, BitPlanes p, const unsigned* __restrict__ badbits, const i
     }
 }
 
-// seeds: rank of the plateau's root on the pixels of every run of a minimum plateau (the map is zeroed beforehand)
+// seeds: rank of the plateau's root on the pixels of every run of a minimum plateau (the map is zeroed beforehand).  Every
+// seed run also reports to the blob of the mask it lies in: the blob's marker label range (lmin / lmax: one label = the blob
+// is simply filled) and, at the seed pixels, the blob id the flood's staging compares with (a run is 4-connected: one blob)
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_marker_scatter(Geom g, const unsigned* __restrict__ bits, const int* __restrict__ par, const uint8_t* __restrict__ low,
-                 const int* __restrict__ rank, int32_t* __restrict__ markers) {
+                 const int* __restrict__ rank, int32_t* __restrict__ markers, BitPlanes mask, const int* __restrict__ bpar,
+                 const int* __restrict__ brank, BlobInfo b, int* __restrict__ seed_blob, unsigned* __restrict__ seed_bits) {
     const long long words = (long long)g.H * g.SEG;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= words) return;
     const int n = blockIdx.y;
     unsigned w = bits[(long long)n * words + t];
-    if (!w) return;
+    if (!w) { seed_bits[(long long)n * words + t] = 0u; return; }
+    unsigned smask = 0u;
     const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
     const long long base = (long long)n * g.P;
     const int idx0 = y * g.W + seg * 32;
@@ -260,8 +264,14 @@ k_marker_scatter(Geom g, const unsigned* __restrict__ bits, const int* __restric
                                                            seg * 32 + a));
         if (low[base + root]) continue;
         const int id = rank[base + root];
-        for (int k = 0; k < len; ++k) markers[base + idx0 + a + k] = id;
+        const int bid = blob_id_at(mask, g, n, bpar, brank, y, seg * 32 + a);
+        const long long o = (long long)n * b.KS + bid;
+        atomicMin(&b.lmin[o], id);
+        atomicMax(&b.lmax[o], id);
+        for (int k = 0; k < len; ++k) { markers[base + idx0 + a + k] = id; seed_blob[base + idx0 + a + k] = bid; }
+        smask |= len == 32 ? 0xffffffffu : (((1u << len) - 1u) << a);
     }
+    seed_bits[(long long)n * words + t] = smask;
 }
 
 // clear, in the bitmap of the roots that ccl_flatten left, the roots whose component is not a minimum plateau
@@ -499,6 +509,13 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         if (!I) return TISEG_ERR_CUDA;
         TISEG_TRY(h_reconstruction_erosion_dev(c, g, I0, lamb, I));
     }
+    // blobs of the mask b from its bit plane (4-connected); their tables are filled by the seed scatter below
+    const BitPlanes mask = {mbits, nullptr, nullptr, nullptr, nullptr};
+    BlobInfo b;
+    int* seed_blob = ws<int>(c, total);
+    unsigned* sbits = ws<unsigned>(c, nwords);
+    if (!seed_blob || !sbits) return TISEG_ERR_CUDA;
+    TISEG_TRY(blobs_ccl(c, g, mask, bpar, brank, first, b));
     // markers: regional-minimum plateaus (8-connected, equal value) of I below 255, via the candidate pixels
     const dim3 word_grid((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
     {
@@ -513,17 +530,15 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     TISEG_LAUNCH(c, k_plateau_low, word_grid, TISEG_THREADS, 0, g, cand, bbits, par, low);
     TISEG_LAUNCH(c, k_filter_root_bits, word_grid, TISEG_THREADS, 0, g, low, rbits);
     TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
+    TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);      // first[label] = INT_MAX
     // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
     TISEG_TRY(zero(c, wsl, total * sizeof(int32_t)));
-    TISEG_LAUNCH(c, k_marker_scatter, word_grid, TISEG_THREADS, 0, g, cbits, par, low, rank, wsl);
+    TISEG_LAUNCH(c, k_marker_scatter, word_grid, TISEG_THREADS, 0, g, cbits, par, low, rank, wsl, mask, bpar, brank, b, seed_blob, sbits);
     if (markers_out) TISEG_CHECK(cudaMemcpyAsync(markers_out, wsl, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
-    // blobs of b from its bit plane; blobs with one marker are filled, the others flooded in the (value, age) order
-    const BitPlanes mask = {mbits, nullptr, nullptr, nullptr, nullptr};
-    BlobInfo b;
-    TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);      // first[label] = INT_MAX
-    TISEG_TRY(blobs_from_planes(c, g, mask, cbits, wsl, bpar, brank, first, b));
+    // blobs with one marker label are filled, the others flooded in the (value, age) order
+    TISEG_TRY(blobs_boxes(c, g, mask, bpar, brank, b));
     BlobMember bm;
-    bm.par = bpar; bm.mask_img = I0; bm.planes = mask;
+    bm.par = nullptr; bm.mask_img = I0; bm.seed_blob = seed_blob; bm.seed_bits = sbits;
     TISEG_TRY(watershed_u8_masked_dev(c, g, I, bm, b, wsl));
     TISEG_TRY(blobs_fill_single(c, g, mask, bpar, brank, b, wsl));
     // arrange_label: the first raster pixel of every flood label came with the fill / the flood's write-back; the

@@ -85,35 +85,6 @@ __global__ void k_blob_offsets(BlobInfo b) {
 }
 
 // ---- blobs from bit planes (DIST) ---------------------------------------------------------------------------------------
-// id of the blob that holds mask pixel (y, x)
-__device__ __forceinline__ int blob_id_at(const BitPlanes& p, const Geom& g, int n, const int* __restrict__ par,
-                                          const int* __restrict__ rank, int y, int x) {
-    const long long base = (long long)n * g.P;
-    return rank[base + find_ro(par + base, bit_node_of(p, g, (long long)n * g.H * g.SEG, y, x))];
-}
-
-// every run piece of marker pixels reports its label to the blob it lies in (marker_bits: bitmap of a superset of the
-// marker pixels, e.g. the minimum candidates; seeds: the marker map, 0 where there is no marker)
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_blob_mark(Geom g, const unsigned* __restrict__ marker_bits, const int32_t* __restrict__ seeds, BitPlanes p,
-            const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b) {
-    const long long words = (long long)g.H * g.SEG;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= words) return;
-    const int n = blockIdx.y;
-    const unsigned w = marker_bits[(long long)n * words + t];
-    if (!w) return;
-    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-    for (unsigned m = w & ~(w << 1); m; m &= m - 1) {          // a piece is 4-connected: one label, one blob
-        const int x = seg * 32 + __ffs(m) - 1;
-        const int lab = seeds[(long long)n * g.P + y * g.W + x];
-        if (lab == 0) continue;
-        const long long o = (long long)n * b.KS + blob_id_at(p, g, n, par, rank, y, x);
-        atomicMin(&b.lmin[o], lab);
-        atomicMax(&b.lmax[o], lab);
-    }
-}
-
 // one thread per word of the mask, one step per run piece.  FILL = false: bounding box + area of the blobs that will be
 // flooded (two or more markers).  FILL = true: the pixels of single-marker blobs take the marker's label.
 template <bool FILL>
@@ -259,18 +230,22 @@ __device__ __forceinline__ int fdiv(int j, unsigned magic) { return (int)__umulh
 struct SeedStats { int lmn, lmx, jseed; };
 // membership of a staged cell (see BlobMember in watershed.cuh)
 struct InForest {
+    static constexpr bool kMasked = false;
     const int* tp; int root;
     __device__ __forceinline__ int load(int gi) const { return tp[gi]; }
     __device__ __forceinline__ bool in(int v) const { return v == root; }
-    __device__ __forceinline__ bool own_seed(int) const { return true; }
+    // seed <=> the label map holds a label there (ov); the label range of the blob's seeds is a by-product
+    __device__ __forceinline__ bool seed(int, unsigned, int, int ov) const { return ov != 0; }
+    __device__ __forceinline__ unsigned seed_word(int, int) const { return 0u; }
 };
 struct InMask {
-    const uint8_t* m; const int* par; BitPlanes planes; long long wo; Geom g; int root;
+    static constexpr bool kMasked = true;
+    const uint8_t* m; const int* seed_blob; const unsigned* sbits; int SEG; int bid;
     __device__ __forceinline__ int load(int gi) const { return m[gi]; }
     __device__ __forceinline__ bool in(int v) const { return v < 255; }
-    __device__ __forceinline__ bool own_seed(int gi) const {
-        const int y = gi / g.W;
-        return find_ro(par, bit_node_of(planes, g, wo, y, gi - y * g.W)) == root;
+    __device__ __forceinline__ unsigned seed_word(int y, int x) const { return sbits[y * SEG + (x >> 5)]; }
+    __device__ __forceinline__ bool seed(int gi, unsigned word, int x, int) const {
+        return ((word >> (x & 31)) & 1u) && seed_blob[gi] == bid;
     }
 };
 template <class IT, class LT, class MB>
@@ -293,13 +268,14 @@ __device__ __forceinline__ SeedStats stage_copy(int tid, int nthr, int W, const 
         int tpv[8], ov[8];
         IT iv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { tpv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+        for (int u = 0; u < 8; ++u) { tpv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = MB::kMasked ? 0 : o[gi[u]]; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * nthr + tid;
             if (j < cells) {
                 const bool inblob = in[u] && mb.in(tpv[u]);
-                const bool seed = inblob && ov[u] != 0 && mb.own_seed(gi[u]);
+                const int gy = gi[u] / W, gx = gi[u] - gy * W;
+                const bool seed = inblob && mb.seed(gi[u], MB::kMasked ? mb.seed_word(gy, gx) : 0u, gx, ov[u]);
                 lab[j] = (unsigned short)(inblob ? (seed ? (unsigned)j : WS_UNLAB) : WS_NOTIN);
                 lvl[j] = (LT)iv[u];
                 if (seed) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
@@ -460,7 +436,7 @@ __device__ __forceinline__ void flood_blob_global(int lane, int W, int H, const 
             int lv = 0;
             if (x <= x1) {
                 int idx = y * W + x;
-                if (mb.in(mb.load(idx)) && o[idx] != 0 && mb.own_seed(idx)) { seed = true; lv = I[idx]; }
+                if (mb.in(mb.load(idx)) && mb.seed(idx, MB::kMasked ? mb.seed_word(y, x) : 0u, x, o[idx])) { seed = true; lv = I[idx]; }
             }
             unsigned m = __ballot_sync(FULL, seed);
             while (m) {
@@ -550,7 +526,8 @@ __device__ __forceinline__ void general_drain(const Geom& g, const uint8_t* __re
         const int w = x1 - x0 + 1, h = y1 - y0 + 1;
         const long long cells = (long long)(w + 2) * (h + 2);
         const InForest inf = {bm.par + base, root};
-        const InMask inm = {MASKED ? bm.mask_img + base : nullptr, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+        const InMask inm = {MASKED ? bm.mask_img + base : nullptr, MASKED ? bm.seed_blob + base : nullptr,
+                                MASKED ? bm.seed_bits + (long long)n * g.H * g.SEG : nullptr, g.SEG, bid};
         if (cells > WG_CAP) {         // does not fit: the same flood in global memory, by one lane
             if (warp == 0) {
                 if (MASKED) flood_blob_global(lane, W, H, I, inm, o, next + base, root, y0, y1, x0, x1,
@@ -613,26 +590,26 @@ k_ws_flood_u8(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInfo
                 if (k0 >= cnt) break;
                 const int m = min(slots, cnt - k0);
                 // lane s < m holds the description of the blob in slot s
-                int mn = 0, mroot = 0, my0 = 0, mx0 = 0, mw = 0, mh = 0;
+                int mn = 0, mroot = 0, my0 = 0, mx0 = 0, mw = 0, mh = 0, mbid = 0;
                 if (lane < m) {
                     const long long item = list[k0 + lane];
                     mn = (int)(item >> 32);
-                    const int bid = (int)(item & 0xffffffffll);
+                    mbid = (int)(item & 0xffffffffll);
                     const long long ko = (long long)mn * b.KS;
-                    mroot = b.root[ko + bid];
-                    my0 = mroot / W; mx0 = b.xmin[ko + bid];
-                    mw = b.xmax[ko + bid] - mx0 + 1; mh = b.ymax[ko + bid] - my0 + 1;
+                    mroot = b.root[ko + mbid];
+                    my0 = mroot / W; mx0 = b.xmin[ko + mbid];
+                    mw = b.xmax[ko + mbid] - mx0 + 1; mh = b.ymax[ko + mbid] - my0 + 1;
                 }
                 for (int i = lane; i < WM_R * SLOTS; i += 32) { head[i] = (unsigned short)WS_END; tail[i] = (unsigned short)WS_END; }
                 if (PROF) t0 = clock64();
                 unsigned single = 0;                                           // slots whose blob has one marker label
                 for (int s = 0; s < m; ++s) {
-                    const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s);
+                    const int n = __shfl_sync(FULL, mn, s), root = __shfl_sync(FULL, mroot, s), bid = __shfl_sync(FULL, mbid, s);
                     const int y0 = __shfl_sync(FULL, my0, s), x0 = __shfl_sync(FULL, mx0, s);
                     const int w = __shfl_sync(FULL, mw, s), h = __shfl_sync(FULL, mh, s);
                     const long long base = (long long)n * g.P;
                     if (MASKED) {       // (blobs with a single marker never get here: nothing to short-cut)
-                        const InMask inm = {bm.mask_img + base, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+                        const InMask inm = {bm.mask_img + base, bm.seed_blob + base, bm.seed_bits + (long long)n * g.H * g.SEG, g.SEG, bid};
                         stage_copy(lane, 32, W, image + base, inm, out + base, root, y0, x0, w, h, lab + s * cap, lvl + s * cap);
                     } else {
                         const InForest inf = {bm.par + base, root};
@@ -731,25 +708,30 @@ __device__ __forceinline__ SeedStats wp_stage(int tid, int nthr, int W, const ui
     const int wp = w + 2, cells = wp * (h + 2);
     const unsigned magic = 0xFFFFFFFFu / (unsigned)wp + 1u;
     for (int j0 = 0; j0 < cells; j0 += 8 * nthr) {
-        int gi[8];
+        int gi[8], gy[8], gx[8];
         bool in[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * nthr + tid;
             const int ly = fdiv(j, magic), lx = j - ly * wp;
             in[u] = j < cells && ly >= 1 && ly <= h && lx >= 1 && lx <= w;
-            gi[u] = in[u] ? (y0 + ly - 1) * W + x0 + lx - 1 : root;
+            gy[u] = y0 + ly - 1; gx[u] = x0 + lx - 1;
+            gi[u] = in[u] ? gy[u] * W + gx[u] : root;
         }
         int mv[8], ov[8];
-        unsigned iv[8];
+        unsigned iv[8], sw[8];
+        // (all loads of the eight cells in flight together; the seed bitmap word instead of the label map in mask mode)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { mv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = o[gi[u]]; }
+        for (int u = 0; u < 8; ++u) {
+            mv[u] = mb.load(gi[u]); iv[u] = I[gi[u]]; ov[u] = MB::kMasked ? 0 : o[gi[u]];
+            sw[u] = (MB::kMasked && in[u]) ? mb.seed_word(gy[u], gx[u]) : 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * nthr + tid;
             if (j < cells) {
                 const bool inblob = in[u] && mb.in(mv[u]);
-                const bool seed = inblob && ov[u] != 0 && mb.own_seed(gi[u]);
+                const bool seed = inblob && mb.seed(gi[u], sw[u], gx[u], ov[u]);
                 cell[j] = ((inblob ? (seed ? (unsigned)j : WPC_UNLAB) : WPC_NOTIN) << 16) | iv[u];
                 if (inblob) atomicAdd(&cnt32[iv[u] >> 1], 1u << (16 * (iv[u] & 1u)));
                 if (seed) { st.lmn = min(st.lmn, ov[u]); st.lmx = max(st.lmx, ov[u]); st.jseed = min(st.jseed, j); }
@@ -949,7 +931,8 @@ k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInf
             const int w = x1 - x0 + 1, h = y1 - y0 + 1;
             const long long cells = (long long)(w + 2) * (h + 2);
             const InForest inf = {bm.par + base, root};
-            const InMask inm = {MASKED ? bm.mask_img + base : nullptr, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+            const InMask inm = {MASKED ? bm.mask_img + base : nullptr, MASKED ? bm.seed_blob + base : nullptr,
+                                MASKED ? bm.seed_bits + (long long)n * g.H * g.SEG : nullptr, g.SEG, bid};
             if (cells > WP_GEN_CAP) {     // does not fit: the sequential flood in global memory, by one lane
                 if (warp == 0) {
                     int* fst = b.first ? b.first + ko : nullptr;
@@ -1005,7 +988,7 @@ k_ws_flood_par(Geom g, const uint8_t* __restrict__ image, BlobMember bm, BlobInf
             if (prof) t0 = clock64();
             bool flood = true;
             if (MASKED) {
-                const InMask inm = {bm.mask_img + base, bm.par + base, bm.planes, (long long)n * g.H * g.SEG, g, root};
+                const InMask inm = {bm.mask_img + base, bm.seed_blob + base, bm.seed_bits + (long long)n * g.H * g.SEG, g.SEG, bid};
                 wp_stage(lane, 32, W, image + base, inm, out + base, root, y0, x0, w, h, cell, cnt32);
             } else {
                 const InForest inf = {bm.par + base, root};
@@ -1552,7 +1535,7 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
                      const BlobInfo& b, int32_t* out) {
     (void)rank;
     BlobMember bm;
-    bm.par = par; bm.mask_img = nullptr; bm.planes = BitPlanes{nullptr, nullptr, nullptr, nullptr, nullptr};
+    bm.par = par; bm.mask_img = nullptr; bm.seed_blob = nullptr; bm.seed_bits = nullptr;
     return watershed_u8_any<false>(c, g, image, bm, b, out);
 }
 
@@ -1560,8 +1543,7 @@ int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
     return watershed_u8_any<true>(c, g, image, bm, b, out);
 }
 
-int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
-                      int* par, int* rank, int* first, BlobInfo& b) {
+int blobs_ccl(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, int* par, int* rank, int* first, BlobInfo& b) {
     const int N = g.N, KS = g.P + 1;
     const size_t ks = (size_t)N * KS, words = (size_t)N * g.H * g.SEG;
     int* count = ws<int>(c, (size_t)N);
@@ -1576,7 +1558,11 @@ int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, cons
     const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
     TISEG_LAUNCH(c, k_blob_init, dim3(8, N), 256, 0, b, g.W);
     TISEG_LAUNCH(c, k_blob_roots, wg, TISEG_THREADS, 0, g, fbits, rank, b);
-    TISEG_LAUNCH(c, k_blob_mark, wg, TISEG_THREADS, 0, g, marker_bits, seeds, planes, par, rank, b);
+    return TISEG_OK;
+}
+
+int blobs_boxes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b) {
+    const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
     TISEG_LAUNCH(c, k_blob_runs<false>, wg, TISEG_THREADS, 0, g, planes, par, rank, b, (int32_t*)nullptr);
     return TISEG_OK;
 }

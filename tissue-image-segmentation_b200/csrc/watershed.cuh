@@ -44,12 +44,14 @@ struct BlobInfo {
 //   forest: a flattened per-pixel forest of the mask (tiseg_watershed_*, HoVer-Net): in the blob <=> tp[pixel] == root.
 //   mask:   no per-pixel forest exists (DIST, blobs from bit planes).  Every in-mask cell of the box is staged; cells of
 //           OTHER blobs are never reached (blobs are 4-connected components and the flood moves by 4-neighbours), stay
-//           unlabelled and are not written back.  Only the seeds must be the blob's own: a seed candidate is looked up
-//           in the run forest (a handful of cells per blob).
+//           unlabelled and are not written back.  Only the seeds must be the blob's own: the kernel that wrote the
+//           seeds also wrote, at the same pixels, the id of the blob each of them lies in.
 struct BlobMember {
-    const int* par;           // forest mode: flattened per-pixel forest; mask mode: run forest (par at run starts)
+    const int* par;           // forest mode: flattened per-pixel forest; mask mode: unused
     const uint8_t* mask_img;  // mask mode: pixel is in the mask <=> mask_img[pixel] < 255; NULL selects forest mode
-    BitPlanes planes;         // mask mode: planes of the mask (F only)
+    const int* seed_blob;     // mask mode: id of the blob every SEED pixel lies in (written where the seeds were written)
+    const unsigned* seed_bits;// mask mode: bitmap of the seed pixels [N, H, SEG] (the flood rewrites the label map while
+                              // other blobs are still being staged, so "label != 0" cannot tell a seed there)
 };
 
 // mask functor -> flattened blob forest `par`, blob ids `rank` (at roots), BlobInfo
@@ -61,10 +63,12 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
                      const BlobInfo& b, int32_t* out);
 // the same flood with blobs described by bit planes + run forest (mask mode of BlobMember)
 int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const BlobMember& mb, const BlobInfo& b, int32_t* out);
-// blob table from the planes of the mask: forest over runs, ids, root, marker label range and bounding boxes of the blobs
-// that hold two or more marker labels.  seeds: the marker map (0 = no marker).
-int blobs_from_planes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const unsigned* marker_bits, const int32_t* seeds,
-                      int* par, int* rank, int* first, BlobInfo& b);
+// blob table from the planes of the mask, in two steps with the seed scatter of the caller in between:
+//   blobs_ccl     forest over runs, ids, roots; lmin / lmax / first-pixel tables initialised
+//   (caller)      writes the seeds and, through blob_id_at, reports every seed run to its blob (lmin / lmax, seed_blob)
+//   blobs_boxes   bounding boxes + areas of the blobs that hold two or more marker labels
+int blobs_ccl(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, int* par, int* rank, int* first, BlobInfo& b);
+int blobs_boxes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b);
 // single-marker blobs: every pixel takes the marker's label (after the flood of the others)
 int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
                       int32_t* out);
@@ -78,6 +82,12 @@ int blobs_describe(tiseg_ctx* c, const Geom& g, const int* par, const int* rank,
                    bool want_offsets);
 
 #ifdef __CUDACC__
+// id of the blob that holds mask pixel (y, x)
+__device__ __forceinline__ int blob_id_at(const BitPlanes& p, const Geom& g, int n, const int* __restrict__ par,
+                                          const int* __restrict__ rank, int y, int x) {
+    const long long base = (long long)n * g.P;
+    return rank[base + find_ro(par + base, bit_node_of(p, g, (long long)n * g.H * g.SEG, y, x))];
+}
 
 template <class MaskImg>
 int blobs_build(tiseg_ctx* c, const Geom& g, MaskImg mask, int* par, int* rank, BlobInfo& b, bool want_offsets,
