@@ -250,20 +250,20 @@ def stack_batch(tiles, batch, dihedral=True):
     return {k: np.stack(v) for k, v in out.items()}
 
 
-# Algorithmic bytes per pixel of every kernel's own inputs + outputs, touched once, summed over the launches of that
-# kernel in ONE step of the workload.  None = the kernel works on O(components) / O(words) tables, not on
-# pixels: no per-pixel roofline applies (its time still counts in the step).  A kernel name that is not listed is an
-# error: nothing gets a default.
+# Algorithmic bytes per pixel and LAUNCH of every kernel's own inputs + outputs, touched once; a step's
+# bytes are that times the pixels of the batch times the launches of the kernel in the step.  None = the kernel works on
+# O(components) / O(words) tables, not on pixels: no per-pixel roofline applies (its time still counts in the step).  A
+# kernel name that is not listed is an error: nothing gets a default.
 _T = None
 KERNEL_BYTES_COMMON = {
     # streaming front
     "k_argmax_logits": "4*C+1", "k_softmax_argmax": "4*C+1+4*C", "k_sem_counts": 2, "memset": _T,
     # bit-plane CCL (bitccl.cuh): planes in, bitmap out
-    "k_eqbits": 2 * (4 + 5 / 8.0), "k_bitccl_tile": _T, "k_bitccl_border": _T, "k_bitccl_resolve": _T,
-    "k_rank_rowtot": _T, "k_rank_rowscan": _T, "k_rank_place_bits": _T, "k_rank_bits": 4,
+    "k_eqbits": 4 + 5 / 8.0, "k_bitccl_tile": _T, "k_bitccl_border": _T, "k_bitccl_resolve": _T,
+    "k_rank_rowtot": _T, "k_rank_rowscan": _T, "k_rank_place_bits": _T, "k_rank_fused": _T, "k_rank_bits": 4,
     # pair metrics
     "k_pair_bits": _T, "k_pair_zero_big": _T, "k_inst_init": _T, "k_pair_best": _T, "k_pair_argbest": _T, "k_aji_gt": _T,
-    "k_aji_pred": _T, "k_metrics_final": _T, "k_inst_class_hist": 5, "k_inst_class_pick": _T, "k_comp_class_bits": _T,
+    "k_aji_pred": _T, "k_metrics_final": _T, "k_inst_class_hist": 5, "k_inst_class_pick": _T, "k_comp_class_bits": _T, "k_max_id": 4, "k_zero_class_hist": _T,
     # pixel forests (labelling API, UNet family, HoVer-Net)
     "(k_ccl_local<Img, 2": 8, "(k_ccl_local<Img, 1": 5, "(k_ccl_border": _T, "k_ccl_flatten": 8, "k_apply_rank": 8,
     "k_ccl_areas": 4, "k_keep_large": 5, "k_border_touch": _T, "k_fill_from_forest": 6, "k_grey_morph": 8,
@@ -661,7 +661,7 @@ def run_b200(a):
         ms_step = kms / 2
         ent = {"ms_per_step": round(ms_step, 4), "launches_per_step": cnt / 2}
         if bpp is not None:
-            alg = bpp * px
+            alg = bpp * px * cnt / 2
             meas = measured_bytes(k)
             used = min(alg, meas) if meas else alg
             ent.update(alg_bytes=alg, dram_bytes=meas, frac=round(used / (ms_step / 1e3) / 1e9 / peak, 4))

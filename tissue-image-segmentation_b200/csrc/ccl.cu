@@ -1,5 +1,7 @@
 // K3 — connected-component labelling entry points (tiseg_label*, tiseg_re_instance) and the
 // non-template parts of the CCL toolbox declared in ccl.cuh.
+#include <cstdlib>
+
 #include "ccl.cuh"
 
 namespace tiseg {
@@ -175,7 +177,102 @@ int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
     return TISEG_OK;
 }
 
+// The three passes above in ONE launch, one 1024-thread CTA per tile: row totals (one warp per row, four rows of loads in
+// flight), block scan over the rows, then the placement.  The bitmap of a tile is P / 8 bytes (125 KB at 1000^2): the
+// second read comes from L1 / L2.  Three launches of ~10 us each, four times per DIST step, become one of ~10 us.
+#define RF_ROWS 4096                    // rows scanned per round (4 per thread)
+template <bool LISTED>
+__global__ void __launch_bounds__(1024) k_rank_fused(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rank, int* counts) {
+    __shared__ int srow[RF_ROWS];
+    __shared__ int wsum[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FOR_TILES_OF(LISTED, g, (int)blockIdx.x, n) {
+    const unsigned* B = bits + (long long)n * g.H * g.SEG;
+    int* out = rank + (long long)n * g.P;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < g.H; base += RF_ROWS) {
+        const int rows = min(RF_ROWS, g.H - base);
+        // row totals
+        for (int r0 = warp; r0 < rows; r0 += 128) {
+            int v[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 32 * u;
+                if (r < rows) for (int k = lane; k < g.SEG; k += 32) v[u] += __popc(B[(long long)(base + r) * g.SEG + k]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], d);
+                if (lane == 0 && r0 + 32 * u < rows) srow[r0 + 32 * u] = v[u];
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the row totals (four rows per thread)
+        int a[4], tot = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int r = threadIdx.x * 4 + u; a[u] = r < rows ? srow[r] : 0; tot += a[u]; }
+        int incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        const int c0 = s_carry;
+        int run = c0 + wsum[warp] + incl - tot;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int r = threadIdx.x * 4 + u; if (r < rows) srow[r] = run; run += a[u]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = run;
+        // placement: one warp per row, four rows of loads in flight
+        for (int r0 = warp; r0 < rows; r0 += 128) {
+            int pre[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pre[u] = r0 + 32 * u < rows ? srow[r0 + 32 * u] : 0;
+            for (int k0 = 0; k0 < g.SEG; k0 += 32) {
+                const int seg = k0 + lane;
+                unsigned m[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + 32 * u;
+                    m[u] = (r < rows && seg < g.SEG) ? B[(long long)(base + r) * g.SEG + seg] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + 32 * u;
+                    if (r >= rows) break;                            // (uniform)
+                    int inc = __popc(m[u]);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                    int k = pre[u] + inc - __popc(m[u]);
+                    int* dst = out + (long long)(base + r) * g.W + seg * 32;
+                    for (unsigned q = m[u]; q; q &= q - 1) dst[__ffs(q) - 1] = ++k;
+                    pre[u] += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && counts) counts[n] = s_carry;
+    __syncthreads();
+    }
+}
+
 int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts) {
+    static const bool split = getenv("TISEG_RANK_SPLIT") != nullptr;       // the three-launch form, for comparison
+    if (!split) {
+        TISEG_LAUNCH_TILES(c, k_rank_fused, g, grid_tiles(g), 1024, 0, g, bits, rank, counts);
+        return TISEG_OK;
+    }
     int* rowpre = ws<int>(c, (size_t)g.N * g.H);
     if (!rowpre) return TISEG_ERR_CUDA;
     TISEG_LAUNCH_TILES(c, k_rank_rowtot, g, dim3((g.H + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK, grid_tiles(g)), TISEG_THREADS, 0,

@@ -583,10 +583,31 @@ k_inst_class_hist(Geom g, const int32_t* __restrict__ inst, const uint8_t* __res
     }
 }
 
-__global__ void k_inst_class_pick(const int* __restrict__ hist, int C, int VM, uint8_t* cls_inst, int* ninst) {
+// The class tables are addressed by instance id with a stride of VM = max(P + 1, 65536) entries per tile, but only the ids
+// that occur can be touched: the largest id of every tile is found first, and clearing / scanning stop there (a CoNIC
+// batch of 512 tiles has ~60 instances each: 1 GB of table shrinks to a few hundred KB of traffic).
+__global__ void __launch_bounds__(TISEG_THREADS) k_max_id(Geom g, const int32_t* __restrict__ inst, int* __restrict__ maxid) {
+    const int n = blockIdx.y;
+    const int32_t* t = inst + (long long)n * g.P;
+    int m = 0;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < g.P; i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < g.P && ((((uintptr_t)t) | (g.P * 4ull)) & 15) == 0) { const int4 q = *reinterpret_cast<const int4*>(t + i); m = max(max(m, max(q.x, q.y)), max(q.z, q.w)); }
+        else for (int k = 0; k < 4 && i + k < g.P; ++k) m = max(m, t[i + k]);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&maxid[n], m);
+}
+__global__ void k_zero_class_hist(int* __restrict__ hist, int C, int VM, const int* __restrict__ maxid) {
+    const int n = blockIdx.y;
+    const long long top = (long long)min(maxid[n], VM - 1) * (C + 1) + C;              // last entry that can be touched
+    int* h = hist + (long long)n * VM * (C + 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= top; i += (long long)gridDim.x * blockDim.x) h[i] = 0;
+}
+
+__global__ void k_inst_class_pick(const int* __restrict__ hist, int C, int VM, uint8_t* cls_inst, int* ninst, const int* __restrict__ maxid) {
     int n = blockIdx.y;
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= VM) return;
+    const int top = min(maxid[n], VM - 1);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= top; v += gridDim.x * blockDim.x) {
     int cls = -1;
     if (v == 0) cls = 0;                                     // id 0 is always listed under class 0
     else {
@@ -599,6 +620,7 @@ __global__ void k_inst_class_pick(const int* __restrict__ hist, int C, int VM, u
         }
     }
     if (cls >= 0) { cls_inst[(long long)n * VM + v] = (uint8_t)cls; atomicAdd(&ninst[n * C + cls], 1); }
+    }
 }
 
 // class of every connected component = class of the instance value at its root pixel
@@ -785,12 +807,15 @@ static int side_classes(tiseg_ctx* c, const Geom& g, const int32_t* inst, const 
     uint8_t* cls_comp = ws<uint8_t>(c, (size_t)N * KS);
     int* ncomp = ws<int>(c, (size_t)N * C);
     int* ninst = ws<int>(c, (size_t)N * C);
-    if (!hist || !cls_inst || !cls_comp || !ncomp || !ninst) return TISEG_ERR_CUDA;
-    TISEG_TRY(zero(c, hist, (size_t)N * VM * (C + 1) * sizeof(int)));
+    int* maxid = ws<int>(c, (size_t)N);
+    if (!hist || !cls_inst || !cls_comp || !ncomp || !ninst || !maxid) return TISEG_ERR_CUDA;
     TISEG_TRY(zero(c, ncomp, (size_t)N * C * sizeof(int)));
     TISEG_TRY(zero(c, ninst, (size_t)N * C * sizeof(int)));
+    TISEG_TRY(zero(c, maxid, (size_t)N * sizeof(int)));
+    TISEG_LAUNCH(c, k_max_id, dim3(8, N), TISEG_THREADS, 0, g, inst, maxid);
+    TISEG_LAUNCH(c, k_zero_class_hist, dim3(8, N), 256, 0, hist, C, VM, maxid);
     TISEG_LAUNCH(c, k_inst_class_hist, warp_grid(g), TISEG_THREADS, 0, g, inst, sem, C, VM, hist, bad);
-    TISEG_LAUNCH(c, k_inst_class_pick, dim3((VM + 255) / 256, N), 256, 0, hist, C, VM, cls_inst, ninst);
+    TISEG_LAUNCH(c, k_inst_class_pick, dim3(8, N), 256, 0, hist, C, VM, cls_inst, ninst, maxid);
     if (rootbits)
         TISEG_LAUNCH(c, k_comp_class_bits, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N),
                      TISEG_THREADS, 0, g, inst, rootbits, rank, cls_inst, VM, C, cls_comp, KS, ncomp);
