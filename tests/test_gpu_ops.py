@@ -301,6 +301,45 @@ def test_postproc_dist_edge_cases():
         _diff(ops.postproc_dist(d), opp.dist_postprocess(None, d, literal=False)[1], "dist %dx%d" % (H, W))
 
 
+def _dense_dist(H, W, seed, floor):
+    """a tile whose mask covers nearly everything as ONE blob with many markers (beyond the shared-memory flood: it is
+    flooded in global memory, on the label map), with holes that hold small islands (other blobs inside its bounding box:
+    single-marker fills, multi-marker floods) — the consumers of the label map that read outside their own writes"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    d = np.full((H, W), floor, np.float32)
+    for _ in range(25):
+        cy, cx, h, r = rng.integers(10, H - 10), rng.integers(10, W - 10), rng.integers(3, 9), rng.integers(6, 20)
+        d = np.maximum(d, floor + h * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2.0 * r * r)))
+    for _ in range(6):
+        cy, cx, r = rng.integers(30, H - 30), rng.integers(30, W - 30), rng.integers(12, 22)
+        rr = np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)
+        d[rr < r] = 0.0                                                    # a hole ...
+        d[rr < r - 6] = 2.0 + 3.0 * np.exp(-rr[rr < r - 6] ** 2 / 18.0)        # ... with an island
+        if r > 16:                                                         # a second peak: the island is flooded, not filled
+            d[(np.abs(yy - cy) < 3) & (np.abs(xx - cx - 5) < 3)] = 6.0
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("H,W,floor", [(400, 400, 3.0), (230, 310, 1.5), (400, 400, 0.0)])
+def test_postproc_dist_dense_mask_and_huge_blob(H, W, floor):
+    """the label map of the flood is not zero-filled: check the paths that depend on zeros elsewhere — the flood in global
+    memory (a blob beyond the CTA-wide slice), the histogram of tiles whose mask covers more than half (background = most
+    frequent label), the general relabelling — alone, in a batch with ordinary tiles, and with the debug outputs"""
+    d = _dense_dist(H, W, 11, floor)
+    _, want = opp.dist_postprocess(None, d, literal=False)
+    _diff(ops.postproc_dist(d), want, "dense dist inst")
+    got, mk, ws = ops.postproc_dist(d, debug=True)
+    _diff(got, want, "dense dist inst (debug outputs)")
+    inv = 255 - np.clip(d, 0, 255).astype("int32").astype(np.uint8)
+    _diff(ws, sk.watershed(inv, mk, mask=(np.clip(d, 0, 255).astype("int32") > 0.5) + 0), "dense dist raw flood")
+    other = synth.tile_dist(2, 3, H=H, W=W)["dist_logit"]
+    batch = np.stack([other, d, other[::-1].copy(), d[:, ::-1].copy()])
+    got = ops.postproc_dist(batch)
+    for j in range(4):
+        _diff(got[j], opp.dist_postprocess(None, batch[j], literal=False)[1], "dense dist batch entry %d" % j)
+
+
 # --------------------------------------------------------------------------- A16 / A17 / A19
 def test_pair_metrics_golden():
     mref = np.load(os.path.join(G, "metrics_ref.npz"))

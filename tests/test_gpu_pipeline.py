@@ -173,3 +173,36 @@ def test_host_feed_chunks_equal_single_call():
         assert tuple(out["aji"][j].cpu().numpy()) == tuple(np.float64(om.pre_eval_bin_aji(want_inst, arrays["gt_inst"][j], literal=False)))
         assert tuple(out["pq"][j].cpu().numpy()) == tuple(np.float64(om.pre_eval_bin_pq(want_inst, arrays["gt_inst"][j], literal=False)))
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("multi", [False, True])
+def test_batched_records_equal_per_image_dictionaries(multi):
+    """Dataset.pre_eval_records (one [n, R] tensor, no per-image Python) carries exactly what pre_eval puts in the
+    per-image dictionaries, for stacked CUDA ground truth (contiguous slice) and for list ground truth."""
+    import torch
+    from tiseg_b200 import ops, parallel
+    C = 7 if multi else 2
+    tiles = [synth.tile_unet(5 if multi else 1, j, 256, 256, C) for j in range(6)]
+    post = segmentors.UNet(C)
+    sem_pred, inst_pred = post.postprocess(ops.softmax_argmax(
+        torch.from_numpy(np.stack([t['sem_logit'][None] for t in tiles])).cuda()))
+    cls = datasets.CoNICDataset if multi else datasets.CPM17Dataset
+    gsem = torch.from_numpy(np.stack([t['gt_sem'] for t in tiles])).cuda()
+    ginst = torch.from_numpy(np.stack([t['gt_inst'] for t in tiles]).astype(np.int32)).cuda()
+    names = ["t%d" % i for i in range(len(tiles))]
+    stacked = cls(sem_gts=gsem, inst_gts=ginst, names=names)
+    listed = cls(sem_gts=[t['gt_sem'] for t in tiles], inst_gts=[t['gt_inst'] for t in tiles], names=names)
+    preds = [dict(sem_pred=sem_pred[i], inst_pred=inst_pred[i]) for i in range(len(tiles))]
+    want = parallel.pack_results(listed.pre_eval(preds, list(range(len(tiles)))), C)
+    rec = stacked.pre_eval_records(sem_pred, inst_pred, range(len(tiles)))
+    assert rec.dtype == torch.float64 and rec.is_cuda and tuple(rec.shape) == want.shape
+    assert np.array_equal(rec.cpu().numpy(), want)
+    part = stacked.pre_eval_records(sem_pred[2:5], inst_pred[2:5], [2, 3, 4])
+    assert np.array_equal(part.cpu().numpy(), want[2:5])
+    scattered = listed.pre_eval_records(sem_pred[[4, 1]], inst_pred[[4, 1]], [4, 1])
+    assert np.array_equal(scattered.cpu().numpy(), want[[4, 1]])
+    back = parallel.unpack_results(rec.cpu().numpy(), C, None if multi else names)
+    ev_a, _ = listed.evaluate(back, logger="silent")
+    ev_b, _ = listed.evaluate(listed.pre_eval(preds, list(range(len(tiles)))), logger="silent")
+    assert ev_a == ev_b

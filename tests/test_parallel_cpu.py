@@ -98,3 +98,41 @@ def test_gt_prefetch_reads_the_reference_file_layout(tmp_path):
         nm = os.path.basename(ds.data_infos[i]['sem_file_name'])[:-len('_sem.png')]
         assert np.array_equal(sem, want[nm][0]) and np.array_equal(inst, want[nm][1])
     assert not ds._pending
+
+
+def _records_worker(rank, world, port, n, width, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch
+        full = np.random.default_rng(3).integers(0, 1 << 40, size=(n, width)).astype(np.float64) + 0.25
+        mine = parallel.shard_indices(n, rank, world)
+        got = parallel.gather_records(torch.from_numpy(full[mine]), mine, n)
+        assert got.dtype == np.float64 and np.array_equal(got, full)
+        if rank == 1:                       # a rank that lost a tile is an error on every rank, not a silent zero row
+            mine = mine[:-1]
+        try:
+            parallel.gather_records(torch.from_numpy(full[mine]), mine, n)
+            raise AssertionError("missing record not detected")
+        except RuntimeError as e:
+            assert "no record" in str(e)
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_records_gloo_world2():
+    """records kept as one [n, R] tensor per rank (Dataset.pre_eval_records): one all-gather, rows at dataset index"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    procs = [ctx.Process(target=_records_worker, args=(r, 2, port, 7, 78, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in got), got

@@ -119,7 +119,108 @@ __device__ __forceinline__ unsigned eq_word(unsigned nib, int lane) {      // va
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
     return w;
 }
+// Five planes at once.  The pass is ISSUE-bound (profiles/r2_*: 180 warp instructions per 128-pixel row at 2.5 IPC), so
+// the compare results are gathered with one predicated OR each and the words are assembled by a reduce-scatter:
+//   * per pixel k, eq_px<k> ORs bit k of byte 0 / 1 / 2 of A (planes F, C, EU) and of byte 0 / 1 of B (EL, ER): one
+//     ISETP (the "pixel is foreground" predicate rides along as the AND input) + one predicated LOP3 per plane;
+//   * eq_words5: three shuffles over the eight lanes of a word group instead of three per plane —
+//       step 1 (lane ^ 1): even lanes collect the bytes of F, C, EU, odd lanes those of EL, ER
+//       step 2 (lane ^ 2): the 16-bit halves: bit1 = 0 keeps the first plane of its set, bit1 = 1 the other(s)
+//       step 3 (lane ^ 4): the words; lane (group + 0, 2, 6, 1, 3) ends with the word of (F, C, EU, EL, ER) and stores it.
+template <int K>
+__device__ __forceinline__ void eq_px(int v, int left, int up, int upl, int upr, unsigned& A, unsigned& B) {
+    asm("{\n\t.reg .pred pf, p;\n\t"
+        "setp.ne.s32 pf, %2, 0;\n\t"
+        "@pf or.b32 %0, %0, %7;\n\t"
+        "setp.eq.and.s32 p, %2, %3, pf;\n\t"
+        "@p or.b32 %0, %0, %8;\n\t"
+        "setp.eq.and.s32 p, %2, %4, pf;\n\t"
+        "@p or.b32 %0, %0, %9;\n\t"
+        "setp.eq.and.s32 p, %2, %5, pf;\n\t"
+        "@p or.b32 %1, %1, %7;\n\t"
+        "setp.eq.and.s32 p, %2, %6, pf;\n\t"
+        "@p or.b32 %1, %1, %8;\n\t}"
+        : "+r"(A), "+r"(B)
+        : "r"(v), "r"(left), "r"(up), "r"(upl), "r"(upr), "n"(1 << K), "n"(256 << K), "n"(65536 << K));
+}
+__device__ __forceinline__ unsigned eq_words5(unsigned A, unsigned B, bool b0, bool b1, bool b2) {
+    const unsigned r1 = __shfl_xor_sync(0xffffffffu, b0 ? A : B, 1), own = b0 ? B : A;
+    const unsigned X = (b0 ? r1 : own) + 16u * (b0 ? own : r1);          // bytes: (F, C, EU) or (EL, ER) of two lanes
+    const unsigned r2 = __shfl_xor_sync(0xffffffffu, b1 ? (X & 0xffu) : (X >> 8), 2);
+    const unsigned Y = b1 ? __byte_perm(r2, X >> 8, 0x5140) : __byte_perm(X, r2, 0x6540);
+    const unsigned r3 = __shfl_xor_sync(0xffffffffu, b1 ? (b2 ? (Y & 0xffffu) : (Y >> 16)) : Y, 4);
+    return b2 ? __byte_perm(r3, Y, 0x7610) : __byte_perm(Y, r3, 0x5410);
+}
 // T = int32_t, or uint16_t (instance maps with ids below 65536 shipped at half the bytes)
+template <class T, bool FULL>
+__device__ __forceinline__ void eq_load4(const T* __restrict__ rp, int x, int W, int (&v)[4]) {
+    if (FULL) {
+        if (sizeof(T) == 4) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else { const uint2 q = *reinterpret_cast<const uint2*>(rp); v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = x + k < W ? (int)rp[k] : 0;
+    }
+}
+struct EqRow { int pv[4], pvL, pvR; };
+// one row: the words of the five planes from the row `v` (+ the strip's outer neighbour `e`) and the row above (st)
+__device__ __forceinline__ void eq_row(const int (&v)[4], int e, EqRow& st, int lane, bool b0, bool b1, bool b2, unsigned* mp) {
+    int vL = __shfl_up_sync(0xffffffffu, v[3], 1), vR = __shfl_down_sync(0xffffffffu, v[0], 1);
+    if (lane == 0) vL = e;
+    if (lane == 31) vR = e;
+    unsigned word = 0;
+    if (__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) {   // (uniform) rows of background cost a few instructions
+        unsigned A = 0u, B = 0u;
+        eq_px<0>(v[0], vL, st.pv[0], st.pvL, st.pv[1], A, B);
+        eq_px<1>(v[1], v[0], st.pv[1], st.pv[0], st.pv[2], A, B);
+        eq_px<2>(v[2], v[1], st.pv[2], st.pv[1], st.pv[3], A, B);
+        eq_px<3>(v[3], v[2], st.pv[3], st.pv[2], st.pvR, A, B);
+        word = eq_words5(A, B, b0, b1, b2);
+    }
+    if (mp) *mp = word;
+    st.pv[0] = v[0]; st.pv[1] = v[1]; st.pv[2] = v[2]; st.pv[3] = v[3]; st.pvL = vL; st.pvR = vR;
+}
+template <class T, bool FULL>
+__device__ __forceinline__ void eq_strip(const Geom& g, const T* __restrict__ t, int lane, int x, int y0, int y1, unsigned* mp) {
+    // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
+    const int xe = lane == 0 ? x - 1 : x + 4;
+    const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+    const T* rp = t + (long long)y0 * g.W + x;            // walks down one row at a time
+    const T* ep = t + (long long)y0 * g.W + xe;
+    EqRow st = {{0, 0, 0, 0}, 0, 0};
+    if (y0 > 0) {
+        eq_load4<T, FULL>(rp - g.W, x, g.W, st.pv);
+        const int e = oke ? (int)*(ep - g.W) : 0;
+        st.pvL = __shfl_up_sync(0xffffffffu, st.pv[3], 1);
+        st.pvR = __shfl_down_sync(0xffffffffu, st.pv[0], 1);
+        if (lane == 0) st.pvL = e;
+        if (lane == 31) st.pvR = e;
+    }
+    int y = y0;
+    for (; y + EQ_UNROLL <= y1; y += EQ_UNROLL) {
+        int cur[EQ_UNROLL][4], ext[EQ_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {                // all loads of the chunk in flight before the first is used
+            eq_load4<T, FULL>(rp + (long long)u * g.W, x, g.W, cur[u]);
+            ext[u] = oke ? (int)ep[(long long)u * g.W] : 0;
+        }
+        rp += (long long)EQ_UNROLL * g.W; ep += (long long)EQ_UNROLL * g.W;
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {
+            eq_row(cur[u], ext[u], st, lane, b0, b1, b2, mp);
+            if (mp) mp += g.SEG;
+        }
+    }
+    for (; y < y1; ++y) {
+        int cur[4];
+        eq_load4<T, FULL>(rp, x, g.W, cur);
+        const int e = oke ? (int)*ep : 0;
+        rp += g.W; ep += g.W;
+        eq_row(cur, e, st, lane, b0, b1, b2, mp);
+        if (mp) mp += g.SEG;
+    }
+}
 template <class T>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_eqbits(Geom g, const T* __restrict__ img, BitPlanesW out, bool vec) {
@@ -130,63 +231,16 @@ k_eqbits(Geom g, const T* __restrict__ img, BitPlanesW out, bool vec) {
     const int band = (int)(wi / strips), strip = (int)(wi - (long long)band * strips), n = blockIdx.y;
     const int x = strip * 128 + lane * 4, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
     const T* t = img + (long long)n * g.P;
-    const bool full = vec && x + 3 < g.W;
-    // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
-    const int xe = lane == 0 ? x - 1 : x + 4;
-    const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
-    auto load4 = [&](int y, int (&v)[4]) {
-        const T* rp = t + (long long)y * g.W + x;
-        if (full) {
-            if (sizeof(T) == 4) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-            else { const uint2 q = *reinterpret_cast<const uint2*>(rp); v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x + k < g.W ? rp[k] : 0;
-        }
-    };
-    int pv[4] = {0, 0, 0, 0}, pvL = 0, pvR = 0;
-    if (y0 > 0) {
-        load4(y0 - 1, pv);
-        const int e = oke ? t[(long long)(y0 - 1) * g.W + xe] : 0;
-        pvL = __shfl_up_sync(0xffffffffu, pv[3], 1);
-        pvR = __shfl_down_sync(0xffffffffu, pv[0], 1);
-        if (lane == 0) pvL = e;
-        if (lane == 31) pvR = e;
-    }
     const int seg = strip * 4 + (lane >> 3);
-    const bool writer = (lane & 7) == 0 && seg < g.SEG;
-    for (int yb = y0; yb < y1; yb += EQ_UNROLL) {
-        int cur[EQ_UNROLL][4], ext[EQ_UNROLL];
-#pragma unroll
-        for (int u = 0; u < EQ_UNROLL; ++u) {
-            const int y = yb + u;
-            if (y < y1) { load4(y, cur[u]); ext[u] = oke ? t[(long long)y * g.W + xe] : 0; }
-            else { cur[u][0] = cur[u][1] = cur[u][2] = cur[u][3] = 0; ext[u] = 0; }
-        }
-#pragma unroll
-        for (int u = 0; u < EQ_UNROLL; ++u) {
-            const int y = yb + u;
-            if (y >= y1) break;                                  // (uniform)
-            const int v0 = cur[u][0], v1 = cur[u][1], v2 = cur[u][2], v3 = cur[u][3];
-            int vL = __shfl_up_sync(0xffffffffu, v3, 1), vR = __shfl_down_sync(0xffffffffu, v0, 1);
-            if (lane == 0) vL = ext[u];
-            if (lane == 31) vR = ext[u];
-            const bool f0 = v0 != 0, f1 = v1 != 0, f2 = v2 != 0, f3 = v3 != 0;
-            unsigned wF = 0, wC = 0, wU = 0, wL = 0, wR = 0;
-            if (__any_sync(0xffffffffu, f0 | f1 | f2 | f3)) {    // (uniform) rows of background cost two instructions
-                wF = eq_word(eq_nib(f0, f1, f2, f3), lane);
-                wC = eq_word(eq_nib(f0 && v0 == vL, f1 && v1 == v0, f2 && v2 == v1, f3 && v3 == v2), lane);
-                wU = eq_word(eq_nib(f0 && v0 == pv[0], f1 && v1 == pv[1], f2 && v2 == pv[2], f3 && v3 == pv[3]), lane);
-                wL = eq_word(eq_nib(f0 && v0 == pvL, f1 && v1 == pv[0], f2 && v2 == pv[1], f3 && v3 == pv[2]), lane);
-                wR = eq_word(eq_nib(f0 && v0 == pv[1], f1 && v1 == pv[2], f2 && v2 == pv[3], f3 && v3 == pvR), lane);
-            }
-            if (writer) {
-                const long long o = ((long long)n * g.H + y) * g.SEG + seg;
-                out.F[o] = wF; out.C[o] = wC; out.EU[o] = wU; out.EL[o] = wL; out.ER[o] = wR;
-            }
-            pv[0] = v0; pv[1] = v1; pv[2] = v2; pv[3] = v3; pvL = vL; pvR = vR;
-        }
+    unsigned* mp = nullptr;                         // the plane whose words this lane ends up with (eq_words5)
+    if (seg < g.SEG) {
+        const int role = lane & 7;
+        mp = role == 0 ? out.F : role == 2 ? out.C : role == 6 ? out.EU : role == 1 ? out.EL : role == 3 ? out.ER : nullptr;
+        if (mp) mp += ((long long)n * g.H + y0) * g.SEG + seg;
     }
+    // (a warp-uniform choice: all four pixels of every lane inside the row and 16-byte aligned, or the guarded scalar loads)
+    if (vec && strip * 128 + 127 < g.W) eq_strip<T, true>(g, t, lane, x, y0, y1, mp);
+    else eq_strip<T, false>(g, t, lane, x, y0, y1, mp);
 }
 
 // ---- tile union-find on the planes -------------------------------------------------------------------------------------

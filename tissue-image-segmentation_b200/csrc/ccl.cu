@@ -2,6 +2,7 @@
 // non-template parts of the CCL toolbox declared in ccl.cuh.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
 #include "ccl.cuh"
 
 namespace tiseg {
@@ -177,23 +178,57 @@ int ccl_flatten(tiseg_ctx* c, const Geom& g, int* par) {
     return TISEG_OK;
 }
 
-// The three passes above in ONE launch, one 1024-thread CTA per tile: row totals (one warp per row, four rows of loads in
-// flight), block scan over the rows, then the placement.  The bitmap of a tile is P / 8 bytes (125 KB at 1000^2): the
-// second read comes from L1 / L2.  Three launches of ~10 us each, four times per DIST step, become one of ~10 us.
+// The three passes above in ONE launch.  A tile belongs to a thread-block CLUSTER of RF_CTAS 1024-thread CTAs (a tile
+// per CTA left 84 of the 148 SMs idle on a 64-tile batch): every CTA ranks a quarter of the rows — row totals (one warp
+// per row, four rows of loads in flight), block scan over its rows, placement — and the CTAs exchange their totals
+// through distributed shared memory: the ranks of CTA r start after the set bits of CTAs 0 .. r-1.  The bitmap of a
+// tile is P / 8 bytes (125 KB at 1000^2): the second read comes from L1 / L2.
 #define RF_ROWS 4096                    // rows scanned per round (4 per thread)
+#define RF_CTAS 4
 template <bool LISTED>
-__global__ void __launch_bounds__(1024) k_rank_fused(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rank, int* counts) {
+__global__ void __cluster_dims__(RF_CTAS, 1, 1) __launch_bounds__(1024, 2)
+k_rank_fused(Geom g, const unsigned* __restrict__ bits, int* __restrict__ rank, int* counts) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ int srow[RF_ROWS];
     __shared__ int wsum[32];
     __shared__ int s_carry;
+    __shared__ int s_total;             // set bits of this CTA's rows (read by the other CTAs of the cluster)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FOR_TILES_OF(LISTED, g, (int)blockIdx.x, n) {
+    const int cr = (int)cluster.block_rank();
+    const int ya = (int)((long long)g.H * cr / RF_CTAS), yb = (int)((long long)g.H * (cr + 1) / RF_CTAS);     // this CTA's rows
+    FOR_TILES_OF(LISTED, g, (int)(blockIdx.x / RF_CTAS), n) {
     const unsigned* B = bits + (long long)n * g.H * g.SEG;
     int* out = rank + (long long)n * g.P;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < g.H; base += RF_ROWS) {
-        const int rows = min(RF_ROWS, g.H - base);
+    // set bits of the own rows -> the start of the own ranks
+    {
+        int t = 0;
+        for (long long k = (long long)ya * g.SEG + threadIdx.x; k < (long long)yb * g.SEG; k += 1024) t += __popc(B[k]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) wsum[warp] = t;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+            if (lane == 0) s_total = w;
+        }
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        int before = 0, all = 0;
+        for (int r = 0; r < RF_CTAS; ++r) {
+            const int t = *cluster.map_shared_rank(&s_total, r);
+            if (r < cr) before += t;
+            all += t;
+        }
+        s_carry = before;
+        if (cr == 0 && counts) counts[n] = all;
+    }
+    cluster.sync();                     // (nobody rewrites s_total, or leaves, while it is being read)
+    for (int base = ya; base < yb; base += RF_ROWS) {
+        const int rows = min(RF_ROWS, yb - base);
         // row totals
         for (int r0 = warp; r0 < rows; r0 += 128) {
             int v[4] = {0, 0, 0, 0};
@@ -204,8 +239,7 @@ __global__ void __launch_bounds__(1024) k_rank_fused(Geom g, const unsigned* __r
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int d = 16; d; d >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], d);
+                v[u] = (int)__reduce_add_sync(0xffffffffu, (unsigned)v[u]);
                 if (lane == 0 && r0 + 32 * u < rows) srow[r0 + 32 * u] = v[u];
             }
         }
@@ -250,6 +284,7 @@ __global__ void __launch_bounds__(1024) k_rank_fused(Geom g, const unsigned* __r
                 for (int u = 0; u < 4; ++u) {
                     const int r = r0 + 32 * u;
                     if (r >= rows) break;                            // (uniform)
+                    if (!__any_sync(0xffffffffu, m[u] != 0u)) continue;  // (uniform) nothing to place in this piece of the row
                     int inc = __popc(m[u]);
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -262,15 +297,13 @@ __global__ void __launch_bounds__(1024) k_rank_fused(Geom g, const unsigned* __r
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && counts) counts[n] = s_carry;
-    __syncthreads();
     }
 }
 
 int rank_from_bits(tiseg_ctx* c, const Geom& g, const unsigned* bits, int* rank, int* counts) {
     static const bool split = getenv("TISEG_RANK_SPLIT") != nullptr;       // the three-launch form, for comparison
     if (!split) {
-        TISEG_LAUNCH_TILES(c, k_rank_fused, g, grid_tiles(g), 1024, 0, g, bits, rank, counts);
+        TISEG_LAUNCH_TILES(c, k_rank_fused, g, grid_tiles(g) * RF_CTAS, 1024, 0, g, bits, rank, counts);
         return TISEG_OK;
     }
     int* rowpre = ws<int>(c, (size_t)g.N * g.H);

@@ -395,68 +395,188 @@ __global__ void k_arrange_lut(Geom g, const int* __restrict__ first, const int* 
     }
 }
 
-// generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128)
-// `lut` (may be null): the id of each label value, applied to the pixels that survive.
-// Four pixels per thread: three 128-bit row loads + the two columns beside them, one 128-bit store (a pixel-per-lane
-// version was issue-bound at 29 % of the HBM rate, profiles/r1_wsl_remove_*).
-template <bool LISTED>
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const int* __restrict__ lut, int KS, int32_t* __restrict__ out, bool vec) {
-    const int W4 = (g.W + 3) >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)W4 * g.H) return;
-    const int y = (int)(t / W4), x = (int)(t - (long long)y * W4) * 4;
-    FOR_TILES(LISTED, g, n) {
-    const int32_t* tile = lab + (long long)n * g.P;
-    int32_t* dst = out + (long long)n * g.P + (long long)y * g.W + x;
-    int c[4];
-    {
-        const int32_t* rp = tile + (long long)y * g.W + x;
-        if (vec) { const int4 v = *reinterpret_cast<const int4*>(rp); c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; }
-        else {
+// generate_wsl + "arranged[wsl > 0] = 0" (dist.py:83-98, 128): a pixel whose 3x3 window holds another non-zero label is a
+// watershed line.  `lut` (may be null): the id of each label value, applied to the pixels that survive.
+// `mask` (may be null): F plane of the pixels of `lab` that carry a value — everything else counts as 0 whatever the map
+// holds there (the flood output is only ever written inside the mask b, so the label map needs no zero fill).
+// One warp = a 128-column strip x WR_BAND rows walking down, four pixels per thread (one 128-bit load per row).  With u = label - 1 as unsigned (0 -> 0xffffffff) "another non-zero
+// label in the window" is  max3x3(label) != v  or  umin3x3(u) != v - 1,  and both are separable: the row aggregates of
+// the last two rows stay in registers, the horizontal neighbours come from the adjacent lanes (the strip's outer columns
+// from one extra load in lanes 0 / 31).  Every row is loaded once; the earlier version (a 3x3 window per thread: three row
+// loads + six scalar loads) ran at half the HBM rate (profiles/r2_*).
+#define WR_BAND 32
+#define WR_AHEAD 4               // rows of loads in flight per thread
+struct WrAgg { int hx[4]; unsigned hn[4]; };                 // per pixel: max / (unsigned) min of (label - 1) over the row's 3 columns
+__device__ __forceinline__ void wr_agg(const int (&v)[4], int e, int lane, WrAgg& a) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] = x + k < g.W ? rp[k] : 0;
-        }
-    }
-    int o[4] = {0, 0, 0, 0};
-    if (c[0] | c[1] | c[2] | c[3]) {
-        int w[3][6];                                 // rows y-1 .. y+1, columns x-1 .. x+4 (0 outside the image)
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            const bool ok = yy >= 0 && yy < g.H;
-            const int32_t* rp = tile + (long long)yy * g.W + x;
-            if (dy == 0) { w[1][1] = c[0]; w[1][2] = c[1]; w[1][3] = c[2]; w[1][4] = c[3]; }
-            else if (ok && vec) {
-                const int4 v = *reinterpret_cast<const int4*>(rp);
-                w[dy + 1][1] = v.x; w[dy + 1][2] = v.y; w[dy + 1][3] = v.z; w[dy + 1][4] = v.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) w[dy + 1][k + 1] = (ok && x + k < g.W) ? rp[k] : 0;
-            }
-            w[dy + 1][0] = (ok && x > 0) ? rp[-1] : 0;
-            w[dy + 1][5] = (ok && x + 4 < g.W) ? rp[4] : 0;
-        }
+    for (int k = 0; k < 4; ++k) { a.hx[k] = 0; a.hn[k] = ~0u; }
+    if (__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3] | e) != 0)) {       // (uniform)
+        int c[6];
+        c[0] = __shfl_up_sync(0xffffffffu, v[3], 1);
+        c[5] = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (lane == 0) c[0] = e;
+        if (lane == 31) c[5] = e;
+        c[1] = v[0]; c[2] = v[1]; c[3] = v[2]; c[4] = v[3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int v = c[k];
-            if (v == 0) continue;
-            bool line = false;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int nb = w[dy][k + dx];
-                    line |= nb != 0 && nb != v;
-                }
-            o[k] = line ? 0 : (lut ? lut[(long long)n * KS + v] : v);
+            a.hx[k] = max(max(c[k], c[k + 1]), c[k + 2]);
+            a.hn[k] = min(min((unsigned)(c[k] - 1), (unsigned)(c[k + 1] - 1)), (unsigned)(c[k + 2] - 1));
         }
     }
-    if (vec) *reinterpret_cast<int4*>(dst) = make_int4(o[0], o[1], o[2], o[3]);
+}
+// the finished row: v with the aggregates of the rows above (a2), of its own row (a1) and below (a0)
+template <bool FULL, bool LUT>
+__device__ __forceinline__ void wr_emit(const int (&v)[4], const WrAgg& a2, const WrAgg& a1, const WrAgg& a0, const int* __restrict__ tl,
+                                        int32_t* __restrict__ dst, int x, int W) {
+    int o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int M = max(max(a2.hx[k], a1.hx[k]), a0.hx[k]);
+        const unsigned m = min(min(a2.hn[k], a1.hn[k]), a0.hn[k]);
+        const bool keep = M == v[k] && m == (unsigned)(v[k] - 1);          // (false for v = 0: m <= 0xffffffff - ... never v - 1 = ~0u with M == 0 unless all zero)
+        o[k] = keep ? v[k] : 0;
+    }
+    if (LUT) {
+        if (o[0] | o[1] | o[2] | o[3]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = tl[o[k]];                   // (lut[0] = 0)
+        }
+    }
+    if (FULL) *reinterpret_cast<int4*>(dst) = make_int4(o[0], o[1], o[2], o[3]);
     else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (x + k < g.W) dst[k] = o[k];
+        for (int k = 0; k < 4; ++k) if (x + k < W) dst[k] = o[k];
     }
+}
+// a row as it comes from memory: the thread's four labels, its mask word, and (lanes 0 / 31) the strip's outer neighbour with
+// the mask word that covers it.  The labels are loaded whether or not the mask has them (the values are discarded in
+// wr_finish): a load that waits for the mask word doubles the latency chain of this latency-bound walk.
+struct WrRaw { int q[4]; unsigned mw, mew; int e; };
+template <bool FULL, bool MASKED>
+__device__ __forceinline__ void wr_issue(const int32_t* __restrict__ tile, const unsigned* __restrict__ mt, int y, int H, int po, int eo,
+                                         int mo, int meo, bool hasw, bool oke, int x, int W, WrRaw& r) {
+    r.q[0] = r.q[1] = r.q[2] = r.q[3] = 0; r.mw = 0u; r.mew = 0u; r.e = 0;
+    if (y >= 0 && y < H) {                       // (uniform)
+        if (MASKED) {
+            if (hasw) r.mw = mt[mo];
+            if (oke) r.mew = mt[meo];
+        }
+        if (FULL) { const int4 t = *reinterpret_cast<const int4*>(tile + po); r.q[0] = t.x; r.q[1] = t.y; r.q[2] = t.z; r.q[3] = t.w; }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < W) r.q[k] = tile[po + k];
+        }
+        if (oke) r.e = tile[eo];
+    }
+}
+template <bool MASKED>
+__device__ __forceinline__ void wr_finish(const WrRaw& r, int sh, int eb, int (&v)[4], int& e) {
+    if (MASKED) {
+        const unsigned nib = r.mw >> sh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = r.q[k];
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tselp.s32 %0, %0, 0, p;\n\t}"
+                : "+r"(v[k]) : "r"(nib), "r"(1u << k));
+        }
+        e = (r.mew >> eb) & 1u ? r.e : 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = r.q[k];
+        e = r.e;
+    }
+}
+template <bool FULL, bool MASKED, bool LUT>
+__device__ __forceinline__ void wr_strip(const Geom& g, const int32_t* __restrict__ tile, const unsigned* __restrict__ mt,
+                                         const int* __restrict__ tl, int32_t* __restrict__ otile, int lane, int x, int y0, int y1) {
+    const int W = g.W, SEG = g.SEG, H = g.H;
+    const int xe = lane == 0 ? x - 1 : x + 4;
+    const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < W;
+    const bool hasw = (x >> 5) < SEG;
+    const int sh = (lane & 7) * 4, eb = xe & 31;
+    // the next row to load and the 32-bit offsets of this thread's pixels / mask words in it (tile-local: P < 2^30)
+    int yn = y0 - 1, po = yn * W + x, eo = yn * W + xe, mo = yn * SEG + (x >> 5), meo = yn * SEG + (xe >> 5);
+    auto issue = [&](WrRaw& r) {
+        wr_issue<FULL, MASKED>(tile, mt, yn, H, po, eo, mo, meo, hasw, oke, x, W, r);
+        ++yn; po += W; eo += W; mo += SEG; meo += SEG;
+    };
+    int oo = y0 * W + x;                         // offset of the next output row
+    WrAgg a2, a1, a0;
+    int v1[4], v0[4], e;
+    WrRaw r[WR_AHEAD];
+    issue(r[0]); issue(r[1]);                    // rows y0 - 1 (zeros outside the image) and y0
+    wr_finish<MASKED>(r[0], sh, eb, v0, e);
+    wr_agg(v0, e, lane, a2);
+    wr_finish<MASKED>(r[1], sh, eb, v1, e);
+    wr_agg(v1, e, lane, a1);
+#pragma unroll
+    for (int u = 0; u < WR_AHEAD; ++u) issue(r[u]);       // always WR_AHEAD rows ahead of the arithmetic
+    int y = y0;
+    for (; y + WR_AHEAD <= y1; y += WR_AHEAD) {  // rows y + 1 .. y + WR_AHEAD complete rows y .. y + WR_AHEAD - 1
+        int v[WR_AHEAD][4], ee[WR_AHEAD];
+#pragma unroll
+        for (int u = 0; u < WR_AHEAD; ++u) wr_finish<MASKED>(r[u], sh, eb, v[u], ee[u]);
+        if (y + WR_AHEAD < y1) {                 // (rows beyond y1 are never used)
+#pragma unroll
+            for (int u = 0; u < WR_AHEAD; ++u) issue(r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < WR_AHEAD; ++u) {
+            wr_agg(v[u], ee[u], lane, a0);
+            wr_emit<FULL, LUT>(v1, a2, a1, a0, tl, otile + oo, x, W);
+            oo += W;
+            a2 = a1; a1 = a0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v1[k] = v[u][k];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < WR_AHEAD - 1; ++u) {     // (the rest of a short band: r[u] holds row y + 1)
+        if (y < y1) {
+            wr_finish<MASKED>(r[u], sh, eb, v0, e);
+            wr_agg(v0, e, lane, a0);
+            wr_emit<FULL, LUT>(v1, a2, a1, a0, tl, otile + oo, x, W);
+            oo += W; ++y;
+            a2 = a1; a1 = a0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v1[k] = v0[k];
+        }
+    }
+}
+// (two blocks per SM: the look-ahead needs ~120 registers; three blocks with spills measured 45 % slower)
+template <bool LISTED, int MINB>
+__global__ void __launch_bounds__(TISEG_THREADS, MINB)
+k_wsl_remove(Geom g, const int32_t* __restrict__ lab, const unsigned* __restrict__ mask, const int* __restrict__ lut, int KS,
+             int32_t* __restrict__ out, bool vec) {
+    const int lane = threadIdx.x & 31;
+    const int strips = (g.W + 127) >> 7, bands = (g.H + WR_BAND - 1) / WR_BAND;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (wi >= (long long)strips * bands) return;
+    const int band = (int)(wi / strips), strip = (int)(wi - (long long)band * strips);
+    const int x = strip * 128 + lane * 4, y0 = band * WR_BAND, y1 = min(y0 + WR_BAND, g.H);
+    const bool full = vec && strip * 128 + 127 < g.W;          // (warp-uniform)
+    FOR_TILES(LISTED, g, n) {
+        // (the tile bases are made opaque register pairs: the compiler otherwise re-derives base + n * P + offset in 64-bit
+        //  arithmetic at every access of this issue-bound loop; now an access is one IMAD.WIDE)
+        const int32_t* tile = lab + (long long)n * g.P;
+        int32_t* otile = out + (long long)n * g.P;
+        asm volatile("" : "+l"(tile));
+        asm volatile("" : "+l"(otile));
+        __builtin_assume(__isGlobal(tile));
+        __builtin_assume(__isGlobal(otile));
+        if (!LISTED) {                                         // the flood output: inside the mask, ids through the table
+            const unsigned* mt = mask + (long long)n * g.H * g.SEG;
+            const int* tl = lut + (long long)n * KS;
+            asm volatile("" : "+l"(mt));
+            asm volatile("" : "+l"(tl));
+            __builtin_assume(__isGlobal(mt));
+            __builtin_assume(__isGlobal(tl));
+            if (full) wr_strip<true, true, true>(g, tile, mt, tl, otile, lane, x, y0, y1);
+            else wr_strip<false, true, true>(g, tile, mt, tl, otile, lane, x, y0, y1);
+        } else {                                               // the general relabelling: a complete map, final ids
+            if (full) wr_strip<true, false, false>(g, tile, nullptr, nullptr, otile, lane, x, y0, y1);
+            else wr_strip<false, false, false>(g, tile, nullptr, nullptr, otile, lane, x, y0, y1);
+        }
     }
 }
 
@@ -467,6 +587,8 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     int N = g.N, KS = g.P + 1;
     size_t total = (size_t)N * g.P;
     const size_t nwords = (size_t)N * g.H * g.SEG;
+    static const bool seq_flood = getenv("TISEG_FLOOD_SEQ") != nullptr || getenv("TISEG_DEBUG_FLOOD") != nullptr ||
+                                  getenv("TISEG_FLOOD_VARIANT") != nullptr;        // (the lane-per-blob flood keeps no `first`)
     uint8_t* I0 = ws<uint8_t>(c, total);
     uint8_t* I = I0;
     uint8_t* low = ws<uint8_t>(c, total);
@@ -532,19 +654,19 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
     TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);      // first[label] = INT_MAX
     // every marker pixel lies inside the mask b = (I < 255), so the markers are the flood's seed map as they are
-    TISEG_TRY(zero(c, wsl, total * sizeof(int32_t)));
+    // (the flood writes inside the mask only and the passes below read inside it only: the full map is zero-filled just
+    //  when the caller asked for it)
+    if (ws_out || markers_out || seq_flood) TISEG_TRY(zero(c, wsl, total * sizeof(int32_t)));
     TISEG_LAUNCH(c, k_marker_scatter, word_grid, TISEG_THREADS, 0, g, cbits, par, low, rank, wsl, mask, bpar, brank, b, seed_blob, sbits);
     if (markers_out) TISEG_CHECK(cudaMemcpyAsync(markers_out, wsl, total * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     // blobs with one marker label are filled, the others flooded in the (value, age) order
-    TISEG_TRY(blobs_boxes(c, g, mask, bpar, brank, b));
+    TISEG_TRY(blobs_boxes_fill(c, g, mask, bpar, brank, b, wsl));
     BlobMember bm;
     bm.par = nullptr; bm.mask_img = I0; bm.seed_blob = seed_blob; bm.seed_bits = sbits;
+    bm.mask_bits = mbits; bm.bpar = bpar; bm.brank = brank;
     TISEG_TRY(watershed_u8_masked_dev(c, g, I, bm, b, wsl));
-    TISEG_TRY(blobs_fill_single(c, g, mask, bpar, brank, b, wsl));
     // arrange_label: the first raster pixel of every flood label came with the fill / the flood's write-back; the
     // background is 0 unless the mask covers more than half of a tile (then the histogram decides, on those tiles only)
-    static const bool seq_flood = getenv("TISEG_FLOOD_SEQ") != nullptr || getenv("TISEG_DEBUG_FLOOD") != nullptr ||
-                                  getenv("TISEG_FLOOD_VARIANT") != nullptr;        // (the lane-per-blob flood keeps no `first`)
     TISEG_TRY(zero(c, nflagged, sizeof(int)));
     TISEG_TRY(zero(c, fbits, (size_t)N * g.H * g.SEG * sizeof(unsigned)));
     if (seq_flood) {
@@ -554,6 +676,7 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
         TISEG_LAUNCH(c, k_mask_area, dim3(8, N), TISEG_THREADS, 0, g, mbits, marea);
         TISEG_LAUNCH(c, k_dense_tiles, (N + 255) / 256, 256, 0, marea, N, g.P, bg, dense, ndense);
         Geom gd = listed_geom(g, dense, ndense);
+        TISEG_TRY(label_clean_listed(c, g, dense, ndense, mbits, wsl));    // (the histogram reads whole tiles)
         TISEG_LAUNCH(c, k_ws_hist<true>, dim3(quad_grid(g).x, 1), TISEG_THREADS, 0, gd, wsl, hist, first, KS, (g.W % 4 == 0) && aligned16(wsl));
         TISEG_LAUNCH(c, k_pick_bg, N, 256, 0, hist, KS, nmark, g.P, bg, flagged, nflagged, (const int*)dense, (const int*)ndense);
     }
@@ -562,14 +685,16 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
     TISEG_LAUNCH(c, k_first_bits, dim3(8, N), 256, 0, g, first, KS, nmark, fbits);
     TISEG_TRY(rank_from_bits(c, g, fbits, rank, nullptr));
     TISEG_LAUNCH(c, k_arrange_lut, dim3(8, N), 256, 0, g, first, rank, KS, nmark, lut);
-    const dim3 px4_grid((unsigned)(((long long)((g.W + 3) / 4) * g.H + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)N);
-    TISEG_LAUNCH(c, k_wsl_remove<false>, px4_grid, TISEG_THREADS, 0, g, wsl, lut, KS, inst, (g.W % 4 == 0) && aligned16(wsl, inst));
+    const dim3 px4_grid((unsigned)(((long long)((g.W + 127) / 128) * ((g.H + WR_BAND - 1) / WR_BAND) + TISEG_WARPS_PER_BLOCK - 1) /
+                                   TISEG_WARPS_PER_BLOCK), (unsigned)N);
+    TISEG_LAUNCH_AS(c, "k_wsl_remove<false>", (k_wsl_remove<false, 2>), px4_grid, TISEG_THREADS, 0, g, wsl, (const unsigned*)mbits, lut, KS, inst,
+                 (g.W % 4 == 0) && aligned16(wsl, inst));
     //   any other background: the general relabelling, on the listed tiles only (no blocks do anything otherwise)
     Geom gl = listed_geom(g, flagged, nflagged);
     TISEG_TRY(ccl_build(c, gl, ImgEqI32TileBg{wsl, bg}, 2, par));
     TISEG_TRY(rank_roots(c, gl, par, rank, nullptr));
     TISEG_TRY(apply_rank(c, gl, par, rank, arranged));
-    TISEG_LAUNCH(c, k_wsl_remove<true>, dim3(px4_grid.x, 1), TISEG_THREADS, 0, gl, arranged, (const int*)nullptr, 0, inst,
+    TISEG_LAUNCH_AS(c, "k_wsl_remove<true>", (k_wsl_remove<true, 2>), dim3(px4_grid.x, 1), TISEG_THREADS, 0, gl, arranged, (const unsigned*)nullptr, (const int*)nullptr, 0, inst,
                  (g.W % 4 == 0) && aligned16(arranged, inst));
     return TISEG_OK;
 }

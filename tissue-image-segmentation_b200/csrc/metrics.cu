@@ -448,6 +448,10 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
         const long long step16 = (long long)gridDim.x * blockDim.x * 16;
         // all-vector case: four 128-bit loads per map in flight per thread (the pass is bound by bytes in flight)
         if (vec16) {
+            // two classes, sixteen pixels whose bytes are all 0 / 1: the four words of each map fold into one (bit k of
+            // byte j = pixel 4k + j) and the joint counts are three population counts
+            const bool bin = C == 2 && ignore > 1;
+            unsigned n11 = 0, n01 = 0, n10 = 0, n00 = 0;         // (gt, pred)
             const long long step64 = (long long)gridDim.x * blockDim.x * 64;
             for (long long i0 = (long long)blockIdx.x * blockDim.x * 64; i0 < P; i0 += step64) {
                 uint4 a[4], b[4];
@@ -461,6 +465,12 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    if (npx[u] && bin && !((a[u].x | a[u].y | a[u].z | a[u].w | b[u].x | b[u].y | b[u].z | b[u].w) & 0xfefefefeu)) {
+                        const unsigned pp = a[u].x | a[u].y << 1 | a[u].z << 2 | a[u].w << 3;
+                        const unsigned tt = b[u].x | b[u].y << 1 | b[u].z << 2 | b[u].w << 3;
+                        const unsigned c11 = __popc(pp & tt), cp = __popc(pp), ct = __popc(tt);
+                        n11 += c11; n01 += cp - c11; n10 += ct - c11; n00 += 16u - cp - ct + c11;
+                    } else
                     if (npx[u]) {
                         const unsigned pw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, tw[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
 #pragma unroll
@@ -482,6 +492,16 @@ k_sem_counts(long long P, const uint8_t* __restrict__ pred, const uint8_t* __res
                         }
                         a0 = a1 = 0ull; trips = 0;
                     }
+                }
+            }
+            if (bin) {                                           // (uniform; C1 = 3: key = gt * 3 + pred)
+                n00 = __reduce_add_sync(0xffffffffu, n00); n01 = __reduce_add_sync(0xffffffffu, n01);
+                n10 = __reduce_add_sync(0xffffffffu, n10); n11 = __reduce_add_sync(0xffffffffu, n11);
+                if (lane == 0) {
+                    if (n00) atomicAdd(&h[0], n00);
+                    if (n01) atomicAdd(&h[1], n01);
+                    if (n10) atomicAdd(&h[3], n10);
+                    if (n11) atomicAdd(&h[4], n11);
                 }
             }
         } else

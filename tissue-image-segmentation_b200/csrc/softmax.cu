@@ -125,7 +125,8 @@ int softmax_argmax_dev(tiseg_ctx* c, const Geom& g, const float* d_in, int T, in
     const bool vec = (P % 4 == 0) && aligned16(d_in, d_prob) && (((uintptr_t)d_cls) & 3) == 0;
     dim3 grid(flat4_grid(P), (unsigned)g.N);
     if (T == 1 && !d_prob) {
-        if (C <= 4) TISEG_LAUNCH(c, k_argmax_logits<4>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
+        if (C <= 2) TISEG_LAUNCH(c, k_argmax_logits<2>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);   // (no dead class slots: issue-bound)
+        else if (C <= 4) TISEG_LAUNCH(c, k_argmax_logits<4>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
         else if (C <= 8) TISEG_LAUNCH(c, k_argmax_logits<8>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
         else TISEG_LAUNCH(c, k_argmax_logits<16>, grid, TISEG_THREADS, 0, P, d_in, C, d_cls, vec);
         return TISEG_OK;

@@ -85,9 +85,9 @@ __global__ void k_blob_offsets(BlobInfo b) {
 }
 
 // ---- blobs from bit planes (DIST) ---------------------------------------------------------------------------------------
-// one thread per word of the mask, one step per run piece.  FILL = false: bounding box + area of the blobs that will be
-// flooded (two or more markers).  FILL = true: the pixels of single-marker blobs take the marker's label.
-template <bool FILL>
+// one thread per word of the mask, one step per run piece: the blobs that will be flooded (two or more marker labels)
+// collect bounding box + area; the pixels of the others take their label now — the one marker's, or 0 without a marker
+// (the label map is not zero-filled, so every mask pixel is written by somebody: here or by the flood).
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_blob_runs(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b, int32_t* __restrict__ out) {
     const long long words = (long long)g.H * g.SEG;
@@ -104,21 +104,18 @@ k_blob_runs(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restr
         const int x = seg * 32 + a;
         const long long o = (long long)n * b.KS + blob_id_at(p, g, n, par, rank, y, x);
         const int lo = b.lmin[o], hi = b.lmax[o];
-        if (!FILL) {
-            if (lo >= hi) continue;
+        if (lo < hi) {
             atomicMax(&b.ymax[o], y);
             atomicMin(&b.xmin[o], x);
             atomicMax(&b.xmax[o], x + len - 1);
             atomicAdd(&b.area[o], len);
         } else {
-            if (lo != hi) continue;
-            const int lab = lo;
+            const int lab = lo == hi ? lo : 0;
             int32_t* dst = out + (long long)n * g.P + (long long)y * g.W + x;
             for (int k = 0; k < len; ++k) dst[k] = lab;
         }
     }
 }
-
 // out = markers * mask (skimage: markers outside the mask are dropped)
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_ws_seed(long long total, const int32_t* __restrict__ markers, const int* __restrict__ par, int32_t* __restrict__ out, bool vec) {
@@ -186,6 +183,32 @@ __device__ __forceinline__ int blob_class(long long cells, int arena, int slots)
     return cls >= slots ? slots - 1 : cls;
 }
 
+// listed tiles (those with a blob beyond `gen_cap` framed cells, flooded in global memory ON the label map): the non-seed
+// pixels of exactly those blobs become 0 = "not reached yet"
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_huge_clean(Geom g, BitPlanes p, const int* __restrict__ par, const int* __restrict__ rank, BlobInfo b,
+             const unsigned* __restrict__ seed_bits, long long gen_cap, int32_t* __restrict__ out) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= words) return;
+    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
+    FOR_TILES(true, g, n) {
+        const unsigned F = p.F[(long long)n * words + t];
+        const unsigned seeds = seed_bits[(long long)n * words + t];
+        for (unsigned m = F & ~(F << 1); m; m &= m - 1) {
+            const int a = __ffs(m) - 1;
+            const unsigned rest = ~F >> a;
+            const int len = rest ? __ffs(rest) - 1 : 32 - a;
+            const int x = seg * 32 + a;
+            const long long ko = (long long)n * b.KS;
+            const int bid = blob_id_at(p, g, n, par, rank, y, x);
+            if (b.lmin[ko + bid] >= b.lmax[ko + bid] || blob_cells(b, ko, bid, g.W) <= gen_cap) continue;
+            int32_t* dst = out + (long long)n * g.P + (long long)y * g.W + x;
+            for (int k = 0; k < len; ++k) if (!((seeds >> (a + k)) & 1u)) dst[k] = 0;
+        }
+    }
+}
+
 __global__ void k_flood_count(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
     int n = blockIdx.y;
     long long ko = (long long)n * b.KS;
@@ -207,17 +230,42 @@ __global__ void k_flood_offsets(FloodWork wk) {
         for (int k = 0; k < WS_MAXCLS; ++k) { wk.offset[k] = acc; acc += wk.count[k]; }
     }
 }
-__global__ void k_flood_scatter(BlobInfo b, int W, FloodWork wk, int arena, int slots) {
+// `huge` (may be null): [N] flags, [N] list, [1] length — the tiles that hold a blob beyond `gen_cap` cells (those are
+// flooded in global memory, on the label map itself, which must then be clean around the seeds: label_clean_listed)
+__global__ void k_flood_scatter(BlobInfo b, int W, FloodWork wk, int arena, int slots, long long gen_cap, int* huge) {
     int n = blockIdx.y;
     long long ko = (long long)n * b.KS;
     int B = b.count[n];
     for (int bid = 1 + blockIdx.x * blockDim.x + threadIdx.x; bid <= B; bid += gridDim.x * blockDim.x) {
         if (b.lmin && b.lmin[ko + bid] >= b.lmax[ko + bid]) continue;
-        int cls = blob_class(blob_cells(b, ko, bid, W), arena, slots);
+        const long long cells = blob_cells(b, ko, bid, W);
+        int cls = blob_class(cells, arena, slots);
         long long item = ((long long)n << 32) | (unsigned)bid;
         if (cls >= 0) wk.items[wk.offset[cls] + atomicAdd(&wk.fill[cls], 1)] = item;
-        else wk.gen[atomicAdd(wk.ngen, 1)] = item;
+        else {
+            wk.gen[atomicAdd(wk.ngen, 1)] = item;
+            if (huge && cells > gen_cap && atomicExch(&huge[n], 1) == 0) huge[gridDim.y + atomicAdd(&huge[2 * gridDim.y], 1)] = n;
+        }
     }
+}
+// label map of the listed tiles: zero wherever `keep` (a bit plane) is clear
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_label_clean(Geom g, const unsigned* __restrict__ keep, int32_t* __restrict__ lab) {
+    const long long words = (long long)g.H * g.SEG;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wi >= words) return;
+    const int y = (int)(wi / g.SEG), seg = (int)(wi - (long long)y * g.SEG), x = seg * 32 + lane;
+    FOR_TILES(true, g, n) {
+        const unsigned w = keep[(long long)n * words + wi];
+        if (x < g.W && !((w >> lane) & 1u)) lab[(long long)n * g.P + (long long)y * g.W + x] = 0;
+    }
+}
+int label_clean_listed(tiseg_ctx* c, const Geom& g, const int* list, const int* count, const unsigned* keep, int32_t* lab) {
+    Geom gl = listed_geom(g, list, count);
+    TISEG_LAUNCH(c, k_label_clean, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), 1),
+                 TISEG_THREADS, 0, gl, keep, lab);
+    return TISEG_OK;
 }
 
 // floor(j / wp) for j * wp < 2^32 with magic = 0xFFFFFFFF / wp + 1
@@ -1433,7 +1481,7 @@ static int flood_launch(tiseg_ctx* c, const Geom& g, const uint8_t* image, const
     static_assert(SMEM + 64 <= 232448, "shared memory");
     TISEG_LAUNCH(c, k_flood_count, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
     TISEG_LAUNCH(c, k_flood_offsets, 1, 32, 0, wk);
-    TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS);
+    TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, ARENA, SLOTS, 0ll, (int*)nullptr);
     static bool attr_set = false;
     if (!attr_set) {
         TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_u8<WARPS, ARENA, SLOTS, false, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -1480,13 +1528,14 @@ static int watershed_u8_any(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
     wk.items = ws<long long>(c, max_blobs);
     wk.gen = ws<long long>(c, max_blobs);
     wk.ovf = ws<long long>(c, max_blobs);
-    int* ints = ws<int>(c, WK_INTS);
+    int* ints = ws<int>(c, WK_INTS + 2 * (size_t)N + 1);
     int* next = ws<int>(c, (size_t)N * g.P);
     int* gheads = ws<int>(c, (size_t)c->sm_count * 512);
     if (!wk.items || !wk.gen || !wk.ovf || !ints || !next || !gheads) return TISEG_ERR_CUDA;
     wk.count = ints; wk.offset = ints + WS_MAXCLS; wk.fill = ints + 2 * WS_MAXCLS; wk.cursor = ints + 3 * WS_MAXCLS;
     wk.ngen = ints + 4 * WS_MAXCLS; wk.gcursor = wk.ngen + 2;
-    TISEG_TRY(zero(c, ints, WK_INTS * sizeof(int)));
+    int* huge = ints + WK_INTS;                 // tiles with a blob that is flooded in global memory
+    TISEG_TRY(zero(c, ints, (WK_INTS + 2 * (size_t)N + 1) * sizeof(int)));
     static const bool debug = getenv("TISEG_DEBUG_FLOOD") != nullptr;
     static const int variant = getenv("TISEG_FLOOD_VARIANT") ? atoi(getenv("TISEG_FLOOD_VARIANT")) : 0;
     static const bool sequential = getenv("TISEG_FLOOD_SEQ") != nullptr || debug || variant != 0;
@@ -1494,7 +1543,14 @@ static int watershed_u8_any(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
         static_assert(WP_SMEM_BYTES + 64 <= 232448, "shared memory");
         TISEG_LAUNCH(c, k_flood_count, dim3(8, g.N), 256, 0, b, g.W, wk, WP_ARENA, WS_MAXCLS);
         TISEG_LAUNCH(c, k_flood_offsets, 1, 32, 0, wk);
-        TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, WP_ARENA, WS_MAXCLS);
+        TISEG_LAUNCH(c, k_flood_scatter, dim3(8, g.N), 256, 0, b, g.W, wk, WP_ARENA, WS_MAXCLS, (long long)WP_GEN_CAP, MASKED ? huge : (int*)nullptr);
+        // mask mode: the label map holds the seeds and is otherwise unwritten; the flood in global memory reads it
+        if (MASKED) {
+            Geom gh = listed_geom(g, huge + N, huge + 2 * N);
+            const BitPlanes mp = {const_cast<unsigned*>(bm.mask_bits), nullptr, nullptr, nullptr, nullptr};
+            TISEG_LAUNCH(c, k_huge_clean, dim3((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), 1), TISEG_THREADS, 0,
+                         gh, mp, bm.bpar, bm.brank, b, bm.seed_bits, (long long)WP_GEN_CAP, out);
+        }
         static bool attr_set = false;
         if (!attr_set) {
             TISEG_CHECK(cudaFuncSetAttribute(k_ws_flood_par<MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM_BYTES));
@@ -1535,7 +1591,7 @@ int watershed_u8_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, const in
                      const BlobInfo& b, int32_t* out) {
     (void)rank;
     BlobMember bm;
-    bm.par = par; bm.mask_img = nullptr; bm.seed_blob = nullptr; bm.seed_bits = nullptr;
+    bm.par = par; bm.mask_img = nullptr; bm.seed_blob = nullptr; bm.seed_bits = nullptr; bm.mask_bits = nullptr; bm.bpar = nullptr; bm.brank = nullptr;
     return watershed_u8_any<false>(c, g, image, bm, b, out);
 }
 
@@ -1561,16 +1617,10 @@ int blobs_ccl(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, int* par, in
     return TISEG_OK;
 }
 
-int blobs_boxes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b) {
+int blobs_boxes_fill(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
+                     int32_t* out) {
     const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
-    TISEG_LAUNCH(c, k_blob_runs<false>, wg, TISEG_THREADS, 0, g, planes, par, rank, b, (int32_t*)nullptr);
-    return TISEG_OK;
-}
-
-int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
-                      int32_t* out) {
-    const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
-    TISEG_LAUNCH(c, k_blob_runs<true>, wg, TISEG_THREADS, 0, g, planes, par, rank, b, out);
+    TISEG_LAUNCH(c, k_blob_runs, wg, TISEG_THREADS, 0, g, planes, par, rank, b, out);
     return TISEG_OK;
 }
 

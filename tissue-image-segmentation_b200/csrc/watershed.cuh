@@ -52,7 +52,13 @@ struct BlobMember {
     const int* seed_blob;     // mask mode: id of the blob every SEED pixel lies in (written where the seeds were written)
     const unsigned* seed_bits;// mask mode: bitmap of the seed pixels [N, H, SEG] (the flood rewrites the label map while
                               // other blobs are still being staged, so "label != 0" cannot tell a seed there)
+    const unsigned* mask_bits;// mask mode: F plane of the mask and the blob forest / ids over its runs (blob_id_at): used to
+    const int* bpar;          // clean the label map under the rare blobs that are flooded in global memory
+    const int* brank;
 };
+
+// label map of the tiles list[0 .. *count): zero wherever the bit plane `keep` is clear (empty blocks when *count == 0)
+int label_clean_listed(tiseg_ctx* c, const Geom& g, const int* list, const int* count, const unsigned* keep, int32_t* lab);
 
 // mask functor -> flattened blob forest `par`, blob ids `rank` (at roots), BlobInfo
 template <class MaskImg>
@@ -66,12 +72,12 @@ int watershed_u8_masked_dev(tiseg_ctx* c, const Geom& g, const uint8_t* image, c
 // blob table from the planes of the mask, in two steps with the seed scatter of the caller in between:
 //   blobs_ccl     forest over runs, ids, roots; lmin / lmax / first-pixel tables initialised
 //   (caller)      writes the seeds and, through blob_id_at, reports every seed run to its blob (lmin / lmax, seed_blob)
-//   blobs_boxes   bounding boxes + areas of the blobs that hold two or more marker labels
+//   blobs_boxes_fill   boxes + areas of the blobs with two or more marker labels; the others are filled
 int blobs_ccl(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, int* par, int* rank, int* first, BlobInfo& b);
-int blobs_boxes(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b);
-// single-marker blobs: every pixel takes the marker's label (after the flood of the others)
-int blobs_fill_single(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
-                      int32_t* out);
+// bounding boxes + areas of the blobs that hold two or more marker labels (those are flooded); the pixels of all other
+// blobs take their label at once: the single marker's, or 0
+int blobs_boxes_fill(tiseg_ctx* c, const Geom& g, const BitPlanes& planes, const int* par, const int* rank, const BlobInfo& b,
+                     int32_t* out);
 int watershed_f64_dev(tiseg_ctx* c, const Geom& g, const double* image, const int* par, const int* rank,
                       const BlobInfo& b, int32_t* out);
 

@@ -165,6 +165,43 @@ class CustomDataset:
                     sem_pre_eval_res=sem_res[j])
         return out
 
+    # ---- batched records (no per-image Python): what a multi-GPU sweep accumulates and exchanges
+    def _gt_batch(self, indices):
+        """ground truth of `indices` as two stacked arrays; a contiguous range of GT held as one stacked tensor / array
+        is a slice, not a copy"""
+        sem, inst = self._sem_gts, self._inst_gts
+        contiguous = len(indices) > 0 and list(indices) == list(range(indices[0], indices[0] + len(indices)))
+        if inst is not None and not isinstance(inst, (list, tuple)) and contiguous:
+            return sem[indices[0]:indices[0] + len(indices)], inst[indices[0]:indices[0] + len(indices)]
+        sg, ig = zip(*[self._load_gt(i) for i in indices])
+        return self._stack(list(sg), np.uint8), self._stack(list(ig), np.int32)
+
+    def pre_eval_records(self, sem_pred, inst_pred, indices):
+        """``pre_eval`` for a whole batch ``[n, H, W]`` without a Python loop over the images: returns ONE float64 array
+        / tensor ``[n, R]`` in the layout of ``parallel.pack_results`` (bin aji 2, bin pq 4, sem 6 x (C-1), and for
+        multi-class datasets aji 2 x (C-1), pq 4 x (C-1)); ``parallel.unpack_results`` turns rows back into the
+        per-image dictionaries ``evaluate`` takes.  Values are what ``pre_eval`` would have put in the dictionaries."""
+        import torch
+        C = len(self.CLASSES)
+        sem_g, inst_g = self._gt_batch(list(indices))
+        multi = isinstance(self, CoNICDataset)
+        counts, _ = ops.sem_counts(sem_pred, sem_g, C)
+        if multi:
+            r = ops.pair_metrics_multiclass(inst_pred, sem_pred, inst_g, sem_g, C)
+            baji, bpq, caji, cpq = r['bin_aji'], r['bin_pq'], r['aji'], r['pq']
+        else:
+            baji, bpq = ops.pair_metrics_bin(inst_pred, inst_g)
+        t = (lambda a: a if is_torch(a) else torch.from_numpy(np.asarray(a)))
+        counts = t(counts).float()                                      # the reference keeps these in float32
+        tp, fp, fn, pr, gt = (counts[:, k] for k in range(5))
+        tn = pr.sum(1, keepdim=True) - (tp + fp + fn)                   # sem_metrics.py:43
+        f32 = lambda a: a.float().double()
+        parts = [t(baji), t(bpq)] + [x[:, 1:].double() for x in (tp, tn, fp, fn, pr, gt)]
+        if multi:
+            ca, cq = t(caji), t(cpq)
+            parts += [f32(ca[:, 1:, k]) for k in range(2)] + [f32(cq[:, 1:, k]) for k in range(4)]
+        return torch.cat(parts, dim=1)
+
     @staticmethod
     def _columns(results):
         cols = {}

@@ -152,6 +152,39 @@ def gather_results(results, indices, n_total, num_classes, names=None):
     return unpack_results(full, num_classes, names)
 
 
+def gather_records(records, indices, n_total):
+    """``gather_results`` for records kept as one ``[n, R]`` float64 tensor per rank (``Dataset.pre_eval_records``): one
+    all-gather, rows placed at their dataset index; returns the full ``[n_total, R]`` numpy array on every rank."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    dev = _device_for_backend()
+    rec = records.to(dev) if hasattr(records, "to") else torch.as_tensor(np.asarray(records), device=dev)
+    n, width = int(rec.shape[0]), int(rec.shape[1])
+    meta = torch.tensor([n, width], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    counts = [int(m[0]) for m in metas]
+    width = max(int(m[1]) for m in metas)
+    cap = max(counts)
+    buf = torch.zeros((cap, width + 1), dtype=torch.float64, device=dev)
+    if n:
+        buf[:n, 0] = torch.as_tensor(np.asarray(indices, np.float64), device=dev)
+        buf[:n, 1:] = rec
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    allrows = torch.cat([b[:c] for b, c in zip(bufs, counts)]).cpu().numpy()
+    full = np.zeros((n_total, width), np.float64)
+    idx = allrows[:, 0].astype(np.int64)
+    ok = (idx >= 0) & (idx < n_total)
+    full[idx[ok]] = allrows[ok, 1:]                      # (duplicates from sampler padding carry identical rows)
+    seen = np.zeros(n_total, bool)
+    seen[idx[ok]] = True
+    if not seen.all():
+        raise RuntimeError("gather_records: %d tiles have no record" % int((~seen).sum()))
+    return full
+
+
 def all_reduce_sums(int_sums, float_sums=None):
     """Sum integer accumulators (exact, int64) and optional fp64 accumulators over the ranks; returns numpy."""
     import torch
