@@ -273,7 +273,7 @@ KERNEL_BYTES_COMMON = {
 }
 KERNEL_BYTES = {
     "dist_monuseg_1000": {
-        "k_dist_prep": 4 + 1 + 1 / 8.0, "k_plateau_bits": 1 + 2 / 8.0, "k_plateau_low": _T, "k_filter_root_bits": _T,
+        "k_dist_prep": 4 + 1 + 1 / 8.0, "k_plateau_bits": 1 + 2 / 8.0, "k_filter_root_bits": _T,
         "k_marker_scatter": _T, "k_mask_area": _T, "k_label_clean": _T, "k_dense_tiles": _T, "k_init_label_tables": _T,
         "k_blob_init": _T, "k_blob_roots": _T, "k_blob_mark": _T, "k_blob_runs": _T, "k_huge_clean": _T, "k_flood_count": _T, "k_flood_offsets": _T,
         "k_flood_scatter": _T, "k_ws_flood_par": 1 + 4 + 4,        # level image + seeds in, labels out (mask pixels dominate)

@@ -255,9 +255,12 @@ __device__ __forceinline__ int bt_node_of(const unsigned (*sS)[BT_TWW], int row,
 }
 
 // p: planes of `g.N` tile-batch entries; par [g.N, P]; lbits [g.N, H, SEG].  conn 1: 4-neighbourhood, 2: 8.
+// `bad` / `low` (may be null): a bit plane of flagged pixels; low[local root] = 1 for every tile component that holds one
+// (k_bitccl_resolve carries the flags on to the final roots).  `low` must be 0 at every node beforehand.
 template <int CONN>
 __global__ void __launch_bounds__(BT_THREADS)
-k_bitccl_tile(Geom g, BitPlanes p, int* __restrict__ par, unsigned* __restrict__ lbits) {
+k_bitccl_tile(Geom g, BitPlanes p, int* __restrict__ par, unsigned* __restrict__ lbits, const unsigned* __restrict__ bad,
+              uint8_t* __restrict__ low) {
     __shared__ int spar[BT_TH * BT_TW];
     __shared__ unsigned sS[BT_TH][BT_TWW];
     const int tilesX = (g.SEG + BT_TWW - 1) / BT_TWW;
@@ -305,6 +308,17 @@ k_bitccl_tile(Geom g, BitPlanes p, int* __restrict__ par, unsigned* __restrict__
         tp[y * g.W + gx0 + w * 32 + b] = (gy0 + root / BT_TW) * g.W + gx0 + (root & (BT_TW - 1));
     }
     if (live) lbits[wo + (long long)y * g.SEG + seg] = roots;
+    if (bad && live) {
+        unsigned bw = bad[wo + (long long)y * g.SEG + seg] & m.f;
+        while (bw) {                                         // one step per run piece that holds a flagged pixel
+            const int b = __ffs(bw) - 1;
+            const unsigned rest = ~m.f >> b;
+            const int len = rest ? __ffs(rest) - 1 : 32 - b;
+            bw = (b + len >= 32) ? 0u : bw & (0xffffffffu << (b + len));
+            const int root = uf_find(spar, bt_node_of(sS, r, w * 32 + b));
+            low[(long long)n * g.P + (gy0 + root / BT_TW) * g.W + gx0 + (root & (BT_TW - 1))] = 1;
+        }
+    }
 }
 
 // unions across tile edges.  Work items per tile-batch entry: (a) every word of every tile-top row (rows BT_TH * k,
@@ -357,7 +371,7 @@ k_bitccl_border(Geom g, BitPlanes p, int* par) {
 
 // local roots -> final roots (path compression on the way); fbits = bitmap of the final roots
 static __global__ void __launch_bounds__(TISEG_THREADS)
-k_bitccl_resolve(Geom g, int* par, const unsigned* __restrict__ lbits, unsigned* __restrict__ fbits) {
+k_bitccl_resolve(Geom g, int* par, const unsigned* __restrict__ lbits, unsigned* __restrict__ fbits, uint8_t* low) {
     const long long words = (long long)g.H * g.SEG;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= words) return;
@@ -371,27 +385,31 @@ k_bitccl_resolve(Geom g, int* par, const unsigned* __restrict__ lbits, unsigned*
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const int r = idx0 + b, G = uf_find(tp, r);
-            if (G != r) { tp[r] = G; keep &= ~(1u << b); }
+            if (G != r) {
+                tp[r] = G; keep &= ~(1u << b);
+                if (low && low[(long long)n * g.P + r]) low[(long long)n * g.P + G] = 1;
+            }
         }
     }
     fbits[(long long)n * words + t] = keep;
 }
 
 // planes -> forest (par at run starts) + bitmap of the final roots.  lbits / fbits: [g.N, H, SEG] scratch / output.
-inline int bitccl_build(tiseg_ctx* c, const Geom& g, const BitPlanes& p, int conn, int* par, unsigned* lbits, unsigned* fbits) {
+inline int bitccl_build(tiseg_ctx* c, const Geom& g, const BitPlanes& p, int conn, int* par, unsigned* lbits, unsigned* fbits,
+                        const unsigned* bad = nullptr, uint8_t* low = nullptr) {
     const int tilesX = (g.SEG + BT_TWW - 1) / BT_TWW, tilesY = (g.H + BT_TH - 1) / BT_TH;
     const dim3 tg((unsigned)(tilesX * tilesY), (unsigned)g.N);
     const int nb = (tilesY - 1) * g.SEG + g.H * (tilesX - 1);
     const dim3 bg((unsigned)((nb + 255) / 256), (unsigned)g.N);
     if (conn == 2) {
-        TISEG_LAUNCH(c, k_bitccl_tile<2>, tg, BT_THREADS, 0, g, p, par, lbits);
+        TISEG_LAUNCH(c, k_bitccl_tile<2>, tg, BT_THREADS, 0, g, p, par, lbits, bad, low);
         if (nb > 0) TISEG_LAUNCH(c, k_bitccl_border<2>, bg, 256, 0, g, p, par);
     } else {
-        TISEG_LAUNCH(c, k_bitccl_tile<1>, tg, BT_THREADS, 0, g, p, par, lbits);
+        TISEG_LAUNCH(c, k_bitccl_tile<1>, tg, BT_THREADS, 0, g, p, par, lbits, bad, low);
         if (nb > 0) TISEG_LAUNCH(c, k_bitccl_border<1>, bg, 256, 0, g, p, par);
     }
     const dim3 wg((unsigned)(((long long)g.H * g.SEG + TISEG_THREADS - 1) / TISEG_THREADS), (unsigned)g.N);
-    TISEG_LAUNCH(c, k_bitccl_resolve, wg, TISEG_THREADS, 0, g, par, lbits, fbits);
+    TISEG_LAUNCH(c, k_bitccl_resolve, wg, TISEG_THREADS, 0, g, par, lbits, fbits, low);
     return TISEG_OK;
 }
 #endif

@@ -18,35 +18,30 @@ namespace tiseg {
 // level image + the F plane of the mask b = (I < 255): one warp = 128 columns x DP_ROWS rows, four pixels per thread and
 // row, all loads of the thread issued before the first is used
 #define DP_ROWS 4
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, unsigned* __restrict__ F, bool vec) {
-    const int lane = threadIdx.x & 31;
-    const int strips = (g.W + 127) >> 7, chunks = (g.H + DP_ROWS - 1) / DP_ROWS;
-    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (wi >= (long long)strips * chunks) return;
-    const int ch = (int)(wi / strips), strip = (int)(wi - (long long)ch * strips), n = blockIdx.y;
-    const int x = strip * 128 + lane * 4, y0 = ch * DP_ROWS;
-    const bool full = vec && x + 3 < g.W;
+template <bool FULL>
+__device__ __forceinline__ void dp_rows(const Geom& g, const float* __restrict__ dt, uint8_t* __restrict__ It, unsigned* __restrict__ Ft,
+                                        int lane, int x, int y0) {
+    const int W = g.W;
     float d[DP_ROWS][4];
 #pragma unroll
     for (int r = 0; r < DP_ROWS; ++r) {
         const int y = y0 + r;
-        const long long ro = (long long)n * g.P + (long long)y * g.W + x;
         d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
-        if (y < g.H) {
-            if (full) { const float4 t = *reinterpret_cast<const float4*>(dist + ro); d[r][0] = t.x; d[r][1] = t.y; d[r][2] = t.z; d[r][3] = t.w; }
+        if (y < g.H) {                               // (uniform)
+            const int ro = y * W + x;
+            if (FULL) { const float4 t = *reinterpret_cast<const float4*>(dt + ro); d[r][0] = t.x; d[r][1] = t.y; d[r][2] = t.z; d[r][3] = t.w; }
             else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (x + k < g.W) d[r][k] = dist[ro + k];
+                for (int k = 0; k < 4; ++k) if (x + k < W) d[r][k] = dt[ro + k];
             }
         }
     }
-    const int seg = x >> 5;
+    const int seg = x >> 5, sh = (lane & 7) * 4;
 #pragma unroll
     for (int r = 0; r < DP_ROWS; ++r) {
         const int y = y0 + r;
-        if (y >= g.H) break;                       // (uniform)
-        const long long ro = (long long)n * g.P + (long long)y * g.W + x;
+        if (y >= g.H) break;                         // (uniform)
+        const int ro = y * W + x;
         unsigned pack = 0, nib = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -56,19 +51,35 @@ k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, uns
             const int t = (int)v;          // astype('int32'): truncation
             const unsigned lv = (unsigned)(255 - (t & 255)) & 255u;
             pack |= lv << (8 * k);
-            if (x + k < g.W && lv < 255u) nib |= 1u << k;
+            if ((FULL || x + k < W) && lv < 255u) nib |= 1u << k;
         }
-        if (full) *reinterpret_cast<unsigned*>(I + ro) = pack;
+        if (FULL) *reinterpret_cast<unsigned*>(It + ro) = pack;
         else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (x + k < g.W) I[ro + k] = (uint8_t)(pack >> (8 * k));
+            for (int k = 0; k < 4; ++k) if (x + k < W) It[ro + k] = (uint8_t)(pack >> (8 * k));
         }
-        unsigned word = nib << ((lane & 7) * 4);
+        unsigned word = nib << sh;
         word |= __shfl_xor_sync(0xffffffffu, word, 1);
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
         word |= __shfl_xor_sync(0xffffffffu, word, 4);
-        if ((lane & 7) == 0 && seg < g.SEG) F[((long long)n * g.H + y) * g.SEG + seg] = word;
+        if ((lane & 7) == 0 && seg < g.SEG) Ft[y * g.SEG + seg] = word;
     }
+}
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_dist_prep(Geom g, const float* __restrict__ dist, uint8_t* __restrict__ I, unsigned* __restrict__ F, bool vec) {
+    const int lane = threadIdx.x & 31;
+    const int strips = (g.W + 127) >> 7, chunks = (g.H + DP_ROWS - 1) / DP_ROWS;
+    const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (wi >= (long long)strips * chunks) return;
+    const int ch = (int)(wi / strips), strip = (int)(wi - (long long)ch * strips), n = blockIdx.y;
+    // (tile bases as opaque register pairs + 32-bit offsets: one IMAD.WIDE per access)
+    const float* dt = dist + (long long)n * g.P;
+    uint8_t* It = I + (long long)n * g.P;
+    unsigned* Ft = F + (long long)n * g.H * g.SEG;
+    asm volatile("" : "+l"(dt)); asm volatile("" : "+l"(It)); asm volatile("" : "+l"(Ft));
+    __builtin_assume(__isGlobal(dt)); __builtin_assume(__isGlobal(It)); __builtin_assume(__isGlobal(Ft));
+    if (vec && strip * 128 + 127 < g.W) dp_rows<true>(g, dt, It, Ft, lane, strip * 128 + lane * 4, ch * DP_ROWS);
+    else dp_rows<false>(g, dt, It, Ft, lane, strip * 128 + lane * 4, ch * DP_ROWS);
 }
 
 // pixels of the mask per tile (decides below whether the flood labels can outnumber the background)
@@ -103,7 +114,7 @@ __device__ __forceinline__ unsigned ld_u8x4(const uint8_t* __restrict__ row, int
 // neighbour), so the labelling is binary.
 //   k_plateau_bits         candidate bitmap + bitmap of the candidates that touch an equal-valued non-candidate
 //   bitccl_build           8-connected components of the candidate bitmap (bitccl.cuh: union-find over runs)
-//   k_plateau_low          low[root] = 1 for plateaus with a bad pixel; k_filter_root_bits drops them from the roots
+//   (bitccl_build)         low[root] = 1 for plateaus with a bad pixel; k_filter_root_bits drops them from the roots
 //   k_marker_scatter       the seed map (rank of the plateau's root on its pixels; zero elsewhere by memset)
 __device__ __forceinline__ int run_len_from(unsigned w, int a) {       // length of the run of ones starting at bit a
     const unsigned x = w >> a;
@@ -152,7 +163,15 @@ k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbi
     const int col = lane < 28 ? lane : lane - 32;
     const int x = (st * 24 + col) * 4, y0 = band * PB_ROWS;
     const bool inx = x >= 0 && x < g.W;
+    // (tile bases as opaque register pairs + 32-bit offsets: one IMAD.WIDE per access in this issue-bound loop)
     const uint8_t* It = I + (long long)n * g.P;
+    unsigned* cb = cbits + (long long)n * g.H * g.SEG;
+    unsigned* bb = badbits + (long long)n * g.H * g.SEG;
+    int* parn = par + (long long)n * g.P;
+    uint8_t* lown = low + (long long)n * g.P;
+    asm volatile("" : "+l"(It)); asm volatile("" : "+l"(cb)); asm volatile("" : "+l"(bb)); asm volatile("" : "+l"(parn)); asm volatile("" : "+l"(lown));
+    __builtin_assume(__isGlobal(It)); __builtin_assume(__isGlobal(cb)); __builtin_assume(__isGlobal(bb));
+    __builtin_assume(__isGlobal(parn)); __builtin_assume(__isGlobal(lown));
     const int seg = st * 3 + (lane >> 3);
     const bool writer = lane < 24 && (lane & 7) == 0 && seg < g.SEG;
     const Px4 FF = {0x00ff00ffu, 0x00ff00ffu};
@@ -166,7 +185,7 @@ k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbi
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                    // four independent loads in flight
             const int r = r0 + k;
-            cw[k] = (inx && r >= 0 && r < g.H) ? ld_u8x4(It + (long long)r * g.W, x, g.W, 255u, vec) : 0xffffffffu;
+            cw[k] = (inx && r >= 0 && r < g.H) ? ld_u8x4(It + r * g.W, x, g.W, 255u, vec) : 0xffffffffu;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -200,43 +219,21 @@ k_plateau_bits(Geom g, const uint8_t* __restrict__ I, unsigned* __restrict__ cbi
                 const unsigned o = __shfl_xor_sync(0xffffffffu, w, 4);
                 if (writer) {
                     const unsigned cwd = (w & 0xffffu) | (o << 16), bwd = (w >> 16) | (o & 0xffff0000u);
-                    const long long wo = ((long long)n * g.H + y) * g.SEG + seg;
-                    cbits[wo] = cwd;
-                    badbits[wo] = bwd;
+                    const int wo = y * g.SEG + seg;
+                    cb[wo] = cwd;
+                    bb[wo] = bwd;
                     unsigned starts = cwd & ~(cwd << 1);
-                    const long long po = (long long)n * g.P;
                     const int idx0 = y * g.W + seg * 32;
                     while (starts) {
                         const int a = __ffs(starts) - 1;
                         starts &= starts - 1;
-                        par[po + idx0 + a] = idx0 + a;
-                        low[po + idx0 + a] = 0;
+                        parn[idx0 + a] = idx0 + a;
+                        lown[idx0 + a] = 0;
                     }
                 }
             }
             hI2 = hI1; hI1 = hI0; hJ2 = hJ1; hJ1 = hJ0; I2 = I1; I1 = c; C2 = C1;
         }
-    }
-}
-
-// a plateau with a pixel that touches an equal-valued non-candidate is not a regional minimum: low[root] = 1
-__global__ void __launch_bounds__(TISEG_THREADS)
-k_plateau_low(Geom g, BitPlanes p, const unsigned* __restrict__ badbits, const int* __restrict__ par, uint8_t* low) {
-    const long long words = (long long)g.H * g.SEG;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= words) return;
-    const int n = blockIdx.y;
-    const unsigned bad = badbits[(long long)n * words + t];
-    if (!bad) return;
-    const unsigned w = p.F[(long long)n * words + t];
-    const int y = (int)(t / g.SEG), seg = (int)(t - (long long)y * g.SEG);
-    const long long base = (long long)n * g.P;
-    for (unsigned m = w & ~(w << 1); m; m &= m - 1) {           // run pieces of this word
-        const int a = __ffs(m) - 1, len = run_len_from(w, a);
-        const unsigned runmask = len == 32 ? 0xffffffffu : (((1u << len) - 1u) << a);
-        if (!(bad & runmask)) continue;
-        const int r = find_ro(par + base, bit_node_of(p, g, (long long)n * words, y, seg * 32 + a));
-        if (!low[base + r]) low[base + r] = 1;
     }
 }
 
@@ -648,8 +645,9 @@ int postproc_dist_dev(tiseg_ctx* c, const Geom& g, const float* dist, int lamb, 
                      TISEG_THREADS, 0, g, I, cbits, bbits, par, low, (g.W % 4 == 0) && (((uintptr_t)I) & 3) == 0, PB_ROWS);
     }
     const BitPlanes cand = {cbits, nullptr, nullptr, nullptr, nullptr};
-    TISEG_TRY(bitccl_build(c, g, cand, 2, par, lbits, rbits));
-    TISEG_LAUNCH(c, k_plateau_low, word_grid, TISEG_THREADS, 0, g, cand, bbits, par, low);
+    // (a plateau with a pixel that touches an equal-valued non-candidate is not a regional minimum: low[root] = 1, set
+    //  inside the labelling from the tile-local roots in shared memory)
+    TISEG_TRY(bitccl_build(c, g, cand, 2, par, lbits, rbits, bbits, low));
     TISEG_LAUNCH(c, k_filter_root_bits, word_grid, TISEG_THREADS, 0, g, low, rbits);
     TISEG_TRY(rank_from_bits(c, g, rbits, rank, nmark));
     TISEG_LAUNCH(c, k_init_label_tables, dim3(8, N), 256, 0, hist, first, KS, nmark);      // first[label] = INT_MAX
