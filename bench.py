@@ -761,7 +761,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=2, help="tiles timed for the cpu_baseline leg (and verified against it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of a CUDA-graph replay of the step")
-    ap.add_argument("--value-lanes", type=int, default=2, help="resident-input steps alternate between this many streams")
+    ap.add_argument("--value-lanes", type=int, default=3, help="resident-input steps alternate between this many streams")
     a = ap.parse_args()
     rc = run_reference(a) if a.impl == "reference" else run_b200(a)
     sys.exit(rc or 0)

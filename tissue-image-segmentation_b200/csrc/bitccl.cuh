@@ -103,30 +103,18 @@ __device__ __forceinline__ int bit_node_of(const BitPlanes& p, const Geom& g, lo
 }
 
 // ---- streaming pass: int32 label map -> planes (equal-value components, background 0) ---------------------------------
-// One warp = one 128-pixel column strip x EQ_BAND rows, walking down, four pixels per thread (one 128-bit load per row:
-// the pass is bound by the bytes it keeps in flight, a 4-byte load per lane reached a fifth of the HBM rate).  The row
-// above stays in registers, so every pixel is loaded once (plus the two strip-edge columns); a thread's four compare
-// results per plane form a nibble, eight lanes OR their nibbles into one 32-bit word.
-#define EQ_BAND 32
-#define EQ_UNROLL 4
-__device__ __forceinline__ unsigned eq_nib(bool a, bool b, bool c, bool d) {
-    return (a ? 1u : 0u) | (b ? 2u : 0u) | (c ? 4u : 0u) | (d ? 8u : 0u);
-}
-__device__ __forceinline__ unsigned eq_word(unsigned nib, int lane) {      // valid in lanes 0, 8, 16, 24
-    unsigned w = nib << ((lane & 7) * 4);
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    return w;
-}
-// Five planes at once.  The pass is ISSUE-bound (profiles/r2_*: 180 warp instructions per 128-pixel row at 2.5 IPC), so
-// the compare results are gathered with one predicated OR each and the words are assembled by a reduce-scatter:
+// One warp = one 256-pixel column strip x EQ_BAND rows, walking down, EIGHT pixels per thread (two 128-bit loads per row).
+// The row above stays in registers, so every pixel is loaded once (plus the two strip-edge columns).  The pass is
+// ISSUE-bound (profiles/r2_*: 180 warp instructions per 128 pixels of a row at 2.5 IPC in its first form), so
 //   * per pixel k, eq_px<k> ORs bit k of byte 0 / 1 / 2 of A (planes F, C, EU) and of byte 0 / 1 of B (EL, ER): one
 //     ISETP (the "pixel is foreground" predicate rides along as the AND input) + one predicated LOP3 per plane;
-//   * eq_words5: three shuffles over the eight lanes of a word group instead of three per plane —
-//       step 1 (lane ^ 1): even lanes collect the bytes of F, C, EU, odd lanes those of EL, ER
-//       step 2 (lane ^ 2): the 16-bit halves: bit1 = 0 keeps the first plane of its set, bit1 = 1 the other(s)
-//       step 3 (lane ^ 4): the words; lane (group + 0, 2, 6, 1, 3) ends with the word of (F, C, EU, EL, ER) and stores it.
+//   * eq_words5 assembles the 32-bit words of the five planes from the bytes of the four lanes of a word group with a
+//     reduce-scatter — TWO shuffles instead of two per plane: step 1 (lane ^ 1) even lanes collect the 16-bit halves of
+//     F, C, EU, odd lanes those of EL, ER; step 2 (lane ^ 2) the words.  Lane (group + 0) ends with the words of F and C,
+//     lanes + 2, + 1, + 3 with EU, EL, ER, and each stores its own;
+//   * eight pixels per thread halve the per-row overhead (neighbour shuffles, vote, assembly, stores) per pixel.
+#define EQ_BAND 32
+#define EQ_UNROLL 2
 template <int K>
 __device__ __forceinline__ void eq_px(int v, int left, int up, int upl, int upr, unsigned& A, unsigned& B) {
     asm("{\n\t.reg .pred pf, p;\n\t"
@@ -143,104 +131,135 @@ __device__ __forceinline__ void eq_px(int v, int left, int up, int upl, int upr,
         : "+r"(A), "+r"(B)
         : "r"(v), "r"(left), "r"(up), "r"(upl), "r"(upr), "n"(1 << K), "n"(256 << K), "n"(65536 << K));
 }
-__device__ __forceinline__ unsigned eq_words5(unsigned A, unsigned B, bool b0, bool b1, bool b2) {
+// -> w0: the word of F (lane & 3 == 0), EL (1), EU (2), ER (3); w1: the word of C (lane & 3 == 0)
+__device__ __forceinline__ void eq_words5(unsigned A, unsigned B, bool b0, bool b1, unsigned& w0, unsigned& w1) {
     const unsigned r1 = __shfl_xor_sync(0xffffffffu, b0 ? A : B, 1), own = b0 ? B : A;
-    const unsigned X = (b0 ? r1 : own) + 16u * (b0 ? own : r1);          // bytes: (F, C, EU) or (EL, ER) of two lanes
-    const unsigned r2 = __shfl_xor_sync(0xffffffffu, b1 ? (X & 0xffu) : (X >> 8), 2);
-    const unsigned Y = b1 ? __byte_perm(r2, X >> 8, 0x5140) : __byte_perm(X, r2, 0x6540);
-    const unsigned r3 = __shfl_xor_sync(0xffffffffu, b1 ? (b2 ? (Y & 0xffffu) : (Y >> 16)) : Y, 4);
-    return b2 ? __byte_perm(r3, Y, 0x7610) : __byte_perm(Y, r3, 0x5410);
+    const unsigned lo = b0 ? r1 : own, hi = b0 ? own : r1;
+    const unsigned Xlo = __byte_perm(lo, hi, 0x5140), Xhi = __byte_perm(lo, hi, 0x3362);
+    const unsigned r2 = __shfl_xor_sync(0xffffffffu, b0 ? (b1 ? (Xlo & 0xffffu) : (Xlo >> 16)) : (b1 ? Xlo : Xhi), 2);
+    w0 = b1 ? (b0 ? __byte_perm(r2, Xlo, 0x7610) : __byte_perm(r2, Xhi, 0x5410)) : __byte_perm(Xlo, r2, 0x5410);
+    w1 = __byte_perm(Xlo, r2, 0x7632);
 }
-// T = int32_t, or uint16_t (instance maps with ids below 65536 shipped at half the bytes)
-template <class T, bool FULL>
-__device__ __forceinline__ void eq_load4(const T* __restrict__ rp, int x, int W, int (&v)[4]) {
-    if (FULL) {
-        if (sizeof(T) == 4) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-        else { const uint2 q = *reinterpret_cast<const uint2*>(rp); v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16; }
+// T = int32_t, or uint16_t (instance maps with ids below 65536 shipped at half the bytes).  VEC: rows are 16-byte aligned
+// and W % 4 == 0, so each aligned group of four pixels is inside the row or outside it as a whole.
+template <class T, bool VEC>
+__device__ __forceinline__ void eq_load8(const T* __restrict__ rp, int x, int W, int (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0;
+    if (VEC) {
+        if (sizeof(T) == 4) {
+            if (x + 3 < W) { const int4 q = *reinterpret_cast<const int4*>(rp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+            if (x + 7 < W) { const int4 q = *reinterpret_cast<const int4*>(rp + 4); v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w; }
+        } else {
+            if (x + 3 < W) { const uint2 q = *reinterpret_cast<const uint2*>(rp); v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16; }
+            if (x + 7 < W) { const uint2 q = *reinterpret_cast<const uint2*>(rp + 4); v[4] = q.x & 0xffffu; v[5] = q.x >> 16; v[6] = q.y & 0xffffu; v[7] = q.y >> 16; }
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = x + k < W ? (int)rp[k] : 0;
+        for (int k = 0; k < 8; ++k) if (x + k < W) v[k] = (int)rp[k];
     }
 }
-struct EqRow { int pv[4], pvL, pvR; };
+struct EqRow { int pv[8], pvL, pvR; };
 // one row: the words of the five planes from the row `v` (+ the strip's outer neighbour `e`) and the row above (st)
-__device__ __forceinline__ void eq_row(const int (&v)[4], int e, EqRow& st, int lane, bool b0, bool b1, bool b2, unsigned* mp) {
-    int vL = __shfl_up_sync(0xffffffffu, v[3], 1), vR = __shfl_down_sync(0xffffffffu, v[0], 1);
+__device__ __forceinline__ void eq_row(const int (&v)[8], int e, EqRow& st, int lane, bool b0, bool b1, unsigned* mp, unsigned* mp2) {
+    int vL = __shfl_up_sync(0xffffffffu, v[7], 1), vR = __shfl_down_sync(0xffffffffu, v[0], 1);
     if (lane == 0) vL = e;
     if (lane == 31) vR = e;
-    unsigned word = 0;
-    if (__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0)) {   // (uniform) rows of background cost a few instructions
+    unsigned w0 = 0u, w1 = 0u;
+    if (__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) != 0)) {   // (uniform) background rows are cheap
         unsigned A = 0u, B = 0u;
         eq_px<0>(v[0], vL, st.pv[0], st.pvL, st.pv[1], A, B);
         eq_px<1>(v[1], v[0], st.pv[1], st.pv[0], st.pv[2], A, B);
         eq_px<2>(v[2], v[1], st.pv[2], st.pv[1], st.pv[3], A, B);
-        eq_px<3>(v[3], v[2], st.pv[3], st.pv[2], st.pvR, A, B);
-        word = eq_words5(A, B, b0, b1, b2);
+        eq_px<3>(v[3], v[2], st.pv[3], st.pv[2], st.pv[4], A, B);
+        eq_px<4>(v[4], v[3], st.pv[4], st.pv[3], st.pv[5], A, B);
+        eq_px<5>(v[5], v[4], st.pv[5], st.pv[4], st.pv[6], A, B);
+        eq_px<6>(v[6], v[5], st.pv[6], st.pv[5], st.pv[7], A, B);
+        eq_px<7>(v[7], v[6], st.pv[7], st.pv[6], st.pvR, A, B);
+        eq_words5(A, B, b0, b1, w0, w1);
     }
-    if (mp) *mp = word;
-    st.pv[0] = v[0]; st.pv[1] = v[1]; st.pv[2] = v[2]; st.pv[3] = v[3]; st.pvL = vL; st.pvR = vR;
+    if (mp) *mp = w0;
+    if (mp2) *mp2 = w1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st.pv[k] = v[k];
+    st.pvL = vL; st.pvR = vR;
 }
-template <class T, bool FULL>
-__device__ __forceinline__ void eq_strip(const Geom& g, const T* __restrict__ t, int lane, int x, int y0, int y1, unsigned* mp) {
+template <class T, bool VEC>
+__device__ __forceinline__ void eq_strip(const Geom& g, const T* __restrict__ t, int lane, int x, int y0, int y1, unsigned* mp, unsigned* mp2) {
     // the strip's outer neighbours: lane 0 looks one pixel to the left of the strip, lane 31 one to the right
-    const int xe = lane == 0 ? x - 1 : x + 4;
+    const int xe = lane == 0 ? x - 1 : x + 8;
     const bool oke = (lane == 0 || lane == 31) && xe >= 0 && xe < g.W;
-    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+    const bool b0 = lane & 1, b1 = lane & 2;
     const T* rp = t + (long long)y0 * g.W + x;            // walks down one row at a time
     const T* ep = t + (long long)y0 * g.W + xe;
-    EqRow st = {{0, 0, 0, 0}, 0, 0};
+    EqRow st;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st.pv[k] = 0;
+    st.pvL = st.pvR = 0;
     if (y0 > 0) {
-        eq_load4<T, FULL>(rp - g.W, x, g.W, st.pv);
+        eq_load8<T, VEC>(rp - g.W, x, g.W, st.pv);
         const int e = oke ? (int)*(ep - g.W) : 0;
-        st.pvL = __shfl_up_sync(0xffffffffu, st.pv[3], 1);
+        st.pvL = __shfl_up_sync(0xffffffffu, st.pv[7], 1);
         st.pvR = __shfl_down_sync(0xffffffffu, st.pv[0], 1);
         if (lane == 0) st.pvL = e;
         if (lane == 31) st.pvR = e;
     }
-    int y = y0;
-    for (; y + EQ_UNROLL <= y1; y += EQ_UNROLL) {
-        int cur[EQ_UNROLL][4], ext[EQ_UNROLL];
-#pragma unroll
-        for (int u = 0; u < EQ_UNROLL; ++u) {                // all loads of the chunk in flight before the first is used
-            eq_load4<T, FULL>(rp + (long long)u * g.W, x, g.W, cur[u]);
-            ext[u] = oke ? (int)ep[(long long)u * g.W] : 0;
-        }
-        rp += (long long)EQ_UNROLL * g.W; ep += (long long)EQ_UNROLL * g.W;
+    // software pipeline: the loads of chunk i + 1 are issued before the arithmetic of chunk i (a warp's walk is a chain of
+    // load latencies otherwise: 16 iterations x ~2 us left the pass at 40 % of the HBM rate)
+    int nxt[EQ_UNROLL][8], next[EQ_UNROLL];
+    auto issue = [&](int yy) {                               // rows yy .. yy + EQ_UNROLL - 1 (zeros beyond y1)
 #pragma unroll
         for (int u = 0; u < EQ_UNROLL; ++u) {
-            eq_row(cur[u], ext[u], st, lane, b0, b1, b2, mp);
-            if (mp) mp += g.SEG;
+            if (yy + u < y1) {
+                eq_load8<T, VEC>(rp + (long long)u * g.W, x, g.W, nxt[u]);
+                next[u] = oke ? (int)ep[(long long)u * g.W] : 0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nxt[u][k] = 0;
+                next[u] = 0;
+            }
         }
-    }
-    for (; y < y1; ++y) {
-        int cur[4];
-        eq_load4<T, FULL>(rp, x, g.W, cur);
-        const int e = oke ? (int)*ep : 0;
-        rp += g.W; ep += g.W;
-        eq_row(cur, e, st, lane, b0, b1, b2, mp);
-        if (mp) mp += g.SEG;
+        rp += (long long)EQ_UNROLL * g.W; ep += (long long)EQ_UNROLL * g.W;
+    };
+    issue(y0);
+    for (int y = y0; y < y1; y += EQ_UNROLL) {
+        int cur[EQ_UNROLL][8], ext[EQ_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[u][k] = nxt[u][k];
+            ext[u] = next[u];
+        }
+        if (y + EQ_UNROLL < y1) issue(y + EQ_UNROLL);
+#pragma unroll
+        for (int u = 0; u < EQ_UNROLL; ++u) {
+            if (y + u >= y1) break;                           // (uniform)
+            eq_row(cur[u], ext[u], st, lane, b0, b1, mp, mp2);
+            if (mp) mp += g.SEG;
+            if (mp2) mp2 += g.SEG;
+        }
     }
 }
 template <class T>
 __global__ void __launch_bounds__(TISEG_THREADS)
 k_eqbits(Geom g, const T* __restrict__ img, BitPlanesW out, bool vec) {
     const int lane = threadIdx.x & 31;
-    const int bands = (g.H + EQ_BAND - 1) / EQ_BAND, strips = (g.W + 127) >> 7;
+    const int bands = (g.H + EQ_BAND - 1) / EQ_BAND, strips = (g.W + 255) >> 8;
     const long long wi = (long long)blockIdx.x * TISEG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (wi >= (long long)strips * bands) return;
     const int band = (int)(wi / strips), strip = (int)(wi - (long long)band * strips), n = blockIdx.y;
-    const int x = strip * 128 + lane * 4, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
+    const int x = strip * 256 + lane * 8, y0 = band * EQ_BAND, y1 = min(y0 + EQ_BAND, g.H);
     const T* t = img + (long long)n * g.P;
-    const int seg = strip * 4 + (lane >> 3);
-    unsigned* mp = nullptr;                         // the plane whose words this lane ends up with (eq_words5)
+    const int seg = strip * 8 + (lane >> 2);
+    unsigned *mp = nullptr, *mp2 = nullptr;         // the plane(s) whose words this lane ends up with (eq_words5)
     if (seg < g.SEG) {
-        const int role = lane & 7;
-        mp = role == 0 ? out.F : role == 2 ? out.C : role == 6 ? out.EU : role == 1 ? out.EL : role == 3 ? out.ER : nullptr;
-        if (mp) mp += ((long long)n * g.H + y0) * g.SEG + seg;
+        const int role = lane & 3;
+        const long long o = ((long long)n * g.H + y0) * g.SEG + seg;
+        mp = (role == 0 ? out.F : role == 2 ? out.EU : role == 1 ? out.EL : out.ER) + o;
+        if (role == 0) mp2 = out.C + o;
     }
-    // (a warp-uniform choice: all four pixels of every lane inside the row and 16-byte aligned, or the guarded scalar loads)
-    if (vec && strip * 128 + 127 < g.W) eq_strip<T, true>(g, t, lane, x, y0, y1, mp);
-    else eq_strip<T, false>(g, t, lane, x, y0, y1, mp);
+    if (vec) eq_strip<T, true>(g, t, lane, x, y0, y1, mp, mp2);
+    else eq_strip<T, false>(g, t, lane, x, y0, y1, mp, mp2);
 }
 
 // ---- tile union-find on the planes -------------------------------------------------------------------------------------

@@ -774,7 +774,7 @@ static int pair_table_build(tiseg_ctx* c, const Geom& g, const int32_t* d_pred, 
     TISEG_TRY(pair_tab_alloc(c, g, t, overflow));
     TISEG_TRY(zero(c, overflow, sizeof(int)));
     // measure.label(inst.copy()) on both maps (inst_metrics.py:12-13): equal-value, 8-connected, background 0
-    const long long warps = (long long)((g.W + 127) / 128) * ((g.H + EQ_BAND - 1) / EQ_BAND);
+    const long long warps = (long long)((g.W + 255) / 256) * ((g.H + EQ_BAND - 1) / EQ_BAND);
     const dim3 eg((unsigned)((warps + TISEG_WARPS_PER_BLOCK - 1) / TISEG_WARPS_PER_BLOCK), (unsigned)N);
     BitPlanesW pwp = {pw.F + words, pw.C + words, pw.EU + words, pw.EL + words, pw.ER + words};
     if (d_gt16) TISEG_LAUNCH(c, k_eqbits<uint16_t>, eg, TISEG_THREADS, 0, g, d_gt16, pw, (g.W % 4 == 0) && (((uintptr_t)d_gt16) & 7) == 0);
