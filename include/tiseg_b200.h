@@ -275,6 +275,21 @@ int tiseg_bound_label(tiseg_ctx* ctx, const uint8_t* sem, const int32_t* inst, i
 int tiseg_unet_weight_map(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, double w0, double sigma,
                           int32_t* inner_out, double* wmap_out);
 
+/* DirectionLabelMake.__call__ after _fix_inst, to_center = True (datasets/ops/direction_map.py:36-193; the per-pixel
+ * centerness search of datasets/utils/center_calculation.py:8-54, the 11x11 gradient of gradient_calculation.py:8-50, the
+ * angle binning of direction_calculation.py:60-121) on a batch of fixed instance maps:
+ *   dist_out  [N,H,W] fp32  sqrt(1 - d(centre) / (max d + 1e-7)) * 10 inside the instances     (data['dist_gt'])
+ *   point_out [N,H,W] fp32  gaussian_filter(255 at the centres, sigma) with the given kernel    (data['point_gt'])
+ *   dir_out   [N,H,W] u8    0 = background, 1 + direction class (num_angles classes)            (data['dir_gt'])
+ *   reg_dir_out [N,H,W] fp32 angle of the gradient in [0, 2 pi)                                 (data['reg_dir_gt'])
+ *   weight_out [N,H,W] fp32 dilation(ddm(dir) * (10 - dist), disk(1)) * 2 + 1; NULL unless num_angles == 8
+ * gauss_weights: HOST array of 2 * gauss_radius + 1 doubles (scipy's _gaussian_kernel1d(sigma, 0, radius)).
+ * Centres, dist_out and point_out follow the reference bit for bit; the gradient is a float32 sum whose order in the
+ * reference is torch's convolution backend's, so angles (and classes on a bin edge) agree to float tolerance. */
+int tiseg_direction_labels(tiseg_ctx* ctx, const int32_t* inst, int N, int H, int W, int num_angles,
+                           const double* gauss_weights, int gauss_radius, float* dist_out, float* point_out,
+                           uint8_t* dir_out, float* reg_dir_out, float* weight_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -644,3 +644,111 @@ def unet_weight_map(inst_gt, w0=10.0, sigma=5.0):
     pen = w0 * np.exp(-pen**2 / 2)
     pen[inner > 0] = 0
     return inner, pen + 1
+
+
+# --------------------------------------------------------------------------- DirectionLabelMake (direction_map.py)
+def _centerness_point(mask, H, W):
+    """calculate_centerpoint (center_calculation.py:8-54): FCOS centerness by binary search along eight directions
+    (float64 arithmetic, round-half-even like Python's round); first maximum in raster order."""
+    import math
+    dirs = [(math.sin(2 * math.pi / 8 * i), math.cos(2 * math.pi / 8 * i)) for i in range(8)]
+    best, bx, by = -1, -1, -1
+    ys, xs = np.nonzero(mask)
+    for i, j in zip(ys.tolist(), xs.tolist()):
+        max_d, min_d = 0, 10000000
+        for k in range(8):
+            lo, hi = 0, 1000000
+            while abs(lo - hi) > 0.1:
+                mid = (lo + hi) / 2
+                xo, yo = round(i + dirs[k][0] * mid), round(j + dirs[k][1] * mid)
+                if xo >= 0 and yo < W and yo >= 0 and xo < H and mask[xo][yo] > 0:
+                    lo = mid
+                else:
+                    hi = mid
+            max_d, min_d = max(max_d, hi), min(min_d, lo)
+        c = min_d / max_d
+        if c > best:
+            best, bx, by = c, i, j
+    return bx, by
+
+
+def sobel_kernel_11():
+    """Sobel.kernel (gradient_calculation.py:13-38): [2, 11, 11] float32, channel 0 = d/d(row), channel 1 = d/d(column)"""
+    k = np.zeros((2, 11, 11), np.float32)
+    for j in range(11):
+        for i in range(11):
+            j_, i_ = j - 5, i - 5
+            if j_ == 0 and i_ == 0:
+                continue
+            k[0, j, i] = j_ / float(i_ * i_ + j_ * j_)
+            k[1, j, i] = i_ / float(i_ * i_ + j_ * j_)
+    return k
+
+
+def direction_bins(angle_deg, num_angles):
+    """align_angle (direction_calculation.py:60-73) index: bin 0 wraps around +-180, bin i is centred on -180 + step * i"""
+    step = 360 / num_angles
+    a = np.asarray(angle_deg)
+    idx = np.zeros(a.shape, np.int64)
+    for i in range(1, num_angles):
+        middle = -180 + step * i
+        idx[(a > (middle - step / 2)) & (a <= (middle + step / 2))] = i
+    return idx
+
+
+def direction_label_make(inst_gt, sem_gt, num_angles=8, to_center=True):
+    """DirectionLabelMake.__call__ (direction_map.py:36-84) -> dict(sem_gt, inst_gt, dist_gt, point_gt, dir_gt, reg_dir_gt,
+    loss_weight_map, centers).  The gradient is the 11x11 correlation in float32 (the reference: torch F.conv2d, whose
+    accumulation order is the backend's: float tolerance); dir_gt quantises its angle, so it can differ from the
+    reference where the angle sits on a bin edge."""
+    from scipy.ndimage import gaussian_filter, distance_transform_edt, correlate, grey_dilation
+    inst = fix_inst(inst_gt)
+    sem = np.array(sem_gt, copy=True)
+    sem[inst == 0] = 0
+    H, W = inst.shape
+    dmap = np.zeros((H, W), np.float32)
+    grad = np.zeros((H, W, 2), np.float32)
+    point = np.zeros((H, W), np.float32)
+    ker = sobel_kernel_11()
+    centers = []
+    yy, xx = np.mgrid[0:H, 0:W]
+    for k in np.unique(inst):
+        if k == 0:
+            continue
+        m = (inst == k).astype(np.uint8)
+        cy, cx = _centerness_point(m, H, W)
+        centers.append((int(k), cy, cx))
+        point[cy, cx] = 1
+        if to_center:
+            d = np.sqrt(((yy - cy) ** 2 + (xx - cx) ** 2).astype(np.float64)) * m
+            di = (1 - d / (d.max() + 0.0000001)) * m
+        else:
+            d = distance_transform_edt(m) * m
+            di = (d / (d.max() + 0.0000001)) * m
+        dmap += di
+        d32 = di.astype(np.float32)
+        g = np.stack([correlate(d32, ker[c], mode="constant", cval=0.0) for c in range(2)], -1).astype(np.float32)
+        g[m == 0] = 0
+        grad[m != 0] = 0
+        grad += g
+    point_g = gaussian_filter(point * 255, sigma=2, order=0).astype(np.float32)
+    dist = (dmap ** 0.5) * 10
+    angle = np.degrees(np.arctan2(grad[:, :, 0], grad[:, :, 1]))
+    a0 = angle.copy()
+    a0[inst == 0] = 0
+    dir_map = direction_bins(a0, num_angles)
+    dir_map[inst == 0] = -1
+    dir_map = dir_map + 1
+    reg = angle.copy()
+    reg[reg < 0] += 360
+    reg[inst == 0] = 0
+    reg = reg / 180 * np.pi
+    if num_angles == 8:
+        dd = direction_differential_map(dir_map, num_angles + 1)
+        w = dd * (10 - dist)
+        w = grey_dilation(w, footprint=disk(1))
+        w = w.astype(np.float32) * 2 + 1.0
+    else:
+        w = np.zeros_like(dir_map)
+    return dict(sem_gt=sem, inst_gt=inst, dist_gt=dist, point_gt=point_g, dir_gt=dir_map, reg_dir_gt=reg.astype(np.float32),
+                loss_weight_map=w, centers=centers, angle=angle, grad=grad)

@@ -1051,3 +1051,73 @@ def test_pair_metrics_uint16_ground_truth():
     assert all(np.array_equal(x, y) for x, y in zip(ops.pair_metrics_bin(odd, odd[::-1].copy()),
                                                     ops.pair_metrics_bin(odd, odd[::-1].astype(np.uint16))))
 
+
+
+# --------------------------------------------------------------------------- (f)4 DirectionLabelMake
+def _dir_case(g, j):
+    p = "d%d_" % j
+    return p, int(g[p + "num_angles"]), bool(g[p + "to_center"])
+
+
+def test_direction_label_make_matches_reference_golden():
+    """DirectionLabelMake run from the reference's own files (tests/golden/make_golden_dir.py): the centre points, dist_gt
+    and point_gt are reproduced bit for bit; the 11x11 gradient is a float32 sum whose order in the reference is torch's
+    convolution backend's, so reg_dir_gt agrees to 2e-4 rad (circular) wherever the gradient is not ~0, dir_gt wherever the
+    angle is not within 0.01 degrees of a class edge, and loss_weight_map away from those pixels."""
+    from tiseg_b200 import label_makers
+    g = np.load(os.path.join(G, "dirlabel_ref.npz"))
+    checked = 0
+    for j in range(int(g["n_cases"])):
+        p, A, to_center = _dir_case(g, j)
+        if not to_center:
+            with pytest.raises(NotImplementedError):
+                label_makers.DirectionLabelMake(to_center=False)
+            continue
+        data = dict(sem_gt=g[p + "sem"].copy(), inst_gt=g[p + "inst"].copy(), seg_fields=[])
+        out = label_makers.DirectionLabelMake(num_angles=A)(data)
+        fixed = g[p + "fixed"]
+        assert np.array_equal(out["sem_gt"], g[p + "sem_gt"]) and out["sem_gt"].dtype == g[p + "sem_gt"].dtype
+        assert out["dist_gt"].dtype == np.float32 and np.array_equal(out["dist_gt"], g[p + "dist_gt"]), "dist_gt case %d" % j
+        assert out["point_gt"].dtype == np.float32 and np.array_equal(out["point_gt"], g[p + "point_gt"]), "point_gt case %d" % j
+        assert out["dir_gt"].dtype == g[p + "dir_gt"].dtype and out["loss_weight_map"].dtype == g[p + "loss_weight_map"].dtype
+        # conditioning of the angle, from the oracle's restatement of the same arithmetic
+        o = opp.direction_label_make(g[p + "inst"], g[p + "sem"], A, True)
+        step = 360.0 / A
+        edge = np.abs(((o["angle"].astype(np.float64) + 180.0 - step / 2) / step) - np.round((o["angle"] + 180.0 - step / 2) / step)) * step
+        soft = (np.abs(o["grad"]).max(-1) < 1e-4) | (edge < 0.01) | (fixed == 0)
+        d = np.abs(out["reg_dir_gt"].astype(np.float64) - g[p + "reg_dir_gt"])
+        d = np.minimum(d, 2 * np.pi - d)
+        assert d[~soft].max() < 2e-4, ("reg_dir_gt", j, d[~soft].max())
+        assert np.all(out["reg_dir_gt"][fixed == 0] == 0) and np.all(out["dir_gt"][fixed == 0] == 0)
+        bad = out["dir_gt"] != g[p + "dir_gt"]
+        assert not np.any(bad & ~soft), ("dir_gt", j, int((bad & ~soft).sum()))
+        assert bad.sum() <= max(4, 0.01 * (fixed > 0).sum())
+        if A == 8:
+            near = ndi.binary_dilation(bad, structure=np.ones((3, 3), bool), iterations=2) if bad.any() else bad
+            dw = np.abs(out["loss_weight_map"].astype(np.float64) - g[p + "loss_weight_map"])
+            if not bad.any():
+                assert dw.max() < 1e-5, ("loss_weight_map", j, dw.max())
+            else:       # (the DDM is normalised by its tile extrema: a flipped class can only matter next to it)
+                assert dw[~near].max() < 1e-5, ("loss_weight_map", j, dw[~near].max())
+        else:
+            assert not out["loss_weight_map"].any()
+        checked += 1
+    assert checked >= 5
+
+
+def test_direction_labels_vs_oracle_batch():
+    """a batch of larger tiles against the oracle restatement (same tolerances), incl. an instance that touches the border"""
+    tiles = [synth.gt_and_pred(9960 + k, 128, 128, n=30)["gt_inst"].astype(np.int32) for k in range(3)]
+    tiles[2][0:20, 100:128] = 500
+    fixed = np.stack([opp.fix_inst(t) for t in tiles])
+    assert np.array_equal(ops.fix_inst(np.stack(tiles)), fixed)
+    r = ops.direction_labels(fixed, 8)
+    for k in range(3):
+        o = opp.direction_label_make(tiles[k], (tiles[k] > 0).astype(np.uint8), 8, True)
+        assert np.array_equal(r["dist_gt"][k], o["dist_gt"]), k
+        assert np.array_equal(r["point_gt"][k], o["point_gt"]), k
+        soft = (np.abs(o["grad"]).max(-1) < 1e-4) | (fixed[k] == 0)
+        d = np.abs(r["reg_dir_gt"][k].astype(np.float64) - o["reg_dir_gt"])
+        d = np.minimum(d, 2 * np.pi - d)
+        assert d[~soft].max() < 2e-4, (k, d[~soft].max())
+        assert (r["dir_gt"][k] != o["dir_gt"]).sum() <= 0.01 * (fixed[k] > 0).sum()

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tiseg_instance_distance_map": [_vp, _vp, _i, _i, _i, _i, _vp],
     "tiseg_fix_inst": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_unet_weight_map": [_vp, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp],
+    "tiseg_direction_labels": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "tiseg_bound_label": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "tiseg_distance_transform_edt": [_vp, _vp, _i, _i, _i, _vp],
     "tiseg_distance_transform_cdt": [_vp, _vp, _i, _i, _i, _vp],

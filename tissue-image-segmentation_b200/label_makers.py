@@ -2,8 +2,7 @@
 
 Same class names, constructor arguments and ``data`` dict protocol as the reference (``DistanceLabelMake``:
 datasets/ops/distance_map.py:23-142, ``HVLabelMake``: hv_map.py:100-114, ``BoundLabelMake``: bound_map.py:6-89).
-``UNetLabelMake``: unet_map.py:7-127).  ``DirectionLabelMake`` (per-pixel binary-search centre points, OpenCV Sobel-11
-gradients) is not built.
+``UNetLabelMake``: unet_map.py:7-127, ``DirectionLabelMake``: direction_map.py:11-193 with ``to_center=True``).
 """
 import numpy as np
 
@@ -66,4 +65,28 @@ class UNetLabelMake(object):
         data["loss_weight_map"] = wmap
         data["sem_gt_inner"] = np.where(inner == 0, 0, sem_gt).astype(sem_gt.dtype)
         data["seg_fields"].append("sem_gt_inner")
+        return data
+
+
+class DirectionLabelMake(object):
+    """build direction label & point label for any dataset (direction_map.py:11-84)."""
+
+    def __init__(self, to_center=True, num_angles=8):
+        if not to_center:
+            # calculate_distance_to_centralridge (direction_map.py:172-183): no config of the reference selects it
+            raise NotImplementedError("DirectionLabelMake(to_center=False) is not built")
+        self.to_center = to_center
+        self.num_angles = num_angles
+
+    def __call__(self, data):
+        sem_gt = np.asarray(data["sem_gt"])
+        inst_gt = ops.fix_inst(data["inst_gt"])
+        data["sem_gt"] = np.where(inst_gt == 0, 0, sem_gt).astype(sem_gt.dtype)
+        r = ops.direction_labels(inst_gt, self.num_angles)
+        data["dist_gt"] = r["dist_gt"]
+        data["point_gt"] = r["point_gt"]
+        data["dir_gt"] = r["dir_gt"].astype(np.int64)
+        data["reg_dir_gt"] = r["reg_dir_gt"]
+        # direction_map.py:73-76: np.zeros_like(dir_map) (int64) unless there are eight angles
+        data["loss_weight_map"] = r["loss_weight_map"] if self.num_angles == 8 else np.zeros_like(data["dir_gt"])
         return data

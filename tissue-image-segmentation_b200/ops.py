@@ -515,3 +515,30 @@ def unet_weight_map(inst, w0=10.0, sigma=5.0):
     wmap = empty_like_kind(x, (N, H, W), np.float64)
     get_ctx(_dev(x)).call("tiseg_unet_weight_map", ptr(x), N, H, W, float(w0), float(sigma), ptr(inner), ptr(wmap))
     return _unbatch(inner, was2d), _unbatch(wmap, was2d)
+
+
+def gaussian_kernel1d(sigma, radius):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius)[::-1], the weights gaussian_filter1d correlates with"""
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi_x = np.exp(-0.5 / sigma2 * x ** 2)
+    phi_x = phi_x / phi_x.sum()
+    return np.ascontiguousarray(phi_x[::-1], dtype=np.float64)
+
+
+def direction_labels(inst, num_angles=8, sigma=2.0, truncate=4.0):
+    """DirectionLabelMake after ``_fix_inst``, to_center = True (datasets/ops/direction_map.py:36-193) ->
+    dict(dist_gt fp32, point_gt fp32, dir_gt uint8, reg_dir_gt fp32, loss_weight_map fp32 | None (only for 8 angles))."""
+    x, was2d = batched(as_input(inst, np.int32))
+    N, H, W = x.shape
+    radius = int(truncate * float(sigma) + 0.5)
+    gw = gaussian_kernel1d(float(sigma), radius)
+    dist = empty_like_kind(x, (N, H, W), np.float32)
+    point = empty_like_kind(x, (N, H, W), np.float32)
+    dirm = empty_like_kind(x, (N, H, W), np.uint8)
+    reg = empty_like_kind(x, (N, H, W), np.float32)
+    wmap = empty_like_kind(x, (N, H, W), np.float32) if int(num_angles) == 8 else None
+    get_ctx(_dev(x)).call("tiseg_direction_labels", ptr(x), N, H, W, int(num_angles), gw.ctypes.data, radius, ptr(dist),
+                          ptr(point), ptr(dirm), ptr(reg), ptr(wmap))
+    out = dict(dist_gt=dist, point_gt=point, dir_gt=dirm, reg_dir_gt=reg, loss_weight_map=wmap)
+    return {k: (_unbatch(v, was2d) if v is not None else None) for k, v in out.items()}
