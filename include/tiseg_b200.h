@@ -176,7 +176,9 @@ int tiseg_cdnet_refine(tiseg_ctx* ctx, const float* sem_logits, const float* dir
 /* _ddm_enhencement alone, IN PLACE on sem_prob [N,C,H,W]: mode 0 = CDNet (cdnet.py:354-367), mode 1 = MultiTaskCDNet
  * (multi_task_cdnet.py:548-564).  dd [N,H,W] mean DDM, point [N,H,W] TTA-mean point map (channel 0 of point_logit). */
 int tiseg_ddm_enhance(tiseg_ctx* ctx, float* sem_prob, const float* dd, const float* point, int N, int C, int H, int W, int mode);
-/* The tail of MultiTaskCDNet.inference after the CNN (multi_task_cdnet.py:262-330, use_regression = False): softmax +
+/* The tail of MultiTaskCDNet.inference after the CNN (multi_task_cdnet.py:262-330; D == 9: use_regression = False;
+ * D == 1: use_regression = True, dir_logits [N,T,1,H,W] is the angle head in radians and every variant's direction map
+ * is 1 + the class of the clamped angle with eight angles, 0 on the background of the mean tc map, :304-315): softmax +
  * TTA mean of the three-class (tc) and semantic heads, TTA mean of the point head, per variant dir[:,0] *= tc[:,0] ->
  * argmax -> DDM, mean DDM, its own _ddm_enhencement (:548-564) on the tc probabilities.  tc_logits [N,T,Ctc,H,W],
  * sem_logits [N,T,Csem,H,W], dir_logits [N,T,9,H,W], point_logits [N,T,1,H,W].  Outputs (any may be NULL): tc_prob_out

@@ -347,9 +347,26 @@ def ddm_enhancement(sem_prob, dd_map, point, mode=0):
     return sem
 
 
-def mtcdnet_inference_tail(tc_logit_list, sem_logit_list, dir_logit_list, point_logit_list, if_ddm=True):
-    """multi_task_cdnet.py:262-330 after the CNN, use_regression = False: softmax + TTA mean of tc and sem; point mean;
-    per variant ``dir[:,0] *= tc[:,0]`` -> argmax -> DDM; mean DDM; optional ``_ddm_enhencement`` (:548-564) on tc.
+def regression_dir_map(angle_rad, background, num_angles=8):
+    """multi_task_cdnet.py:304-315: the regression head's angle (radians, fp32) -> direction classes.  Clamp to [0, 2 pi],
+    degrees, (180, 360] -> (-180, 0], background 0, class = 1 + bin of align_angle (direction_calculation.py:60-73;
+    angle_to_vector + vector_to_label snap to the bin centre and bin again, which is the same bin), background class 0."""
+    a = np.array(angle_rad, np.float32, copy=True)
+    a[a < 0] = 0
+    a[a > np.float32(2 * np.pi)] = np.float32(2 * np.pi)
+    deg = (a * np.float32(180)) / np.float32(np.pi)
+    deg[deg > 180] -= 360
+    deg[background] = 0
+    d = direction_bins(deg, num_angles)
+    d[background] = -1
+    return d + 1
+
+
+def mtcdnet_inference_tail(tc_logit_list, sem_logit_list, dir_logit_list, point_logit_list, if_ddm=True, use_regression=False,
+                           num_angles=8):
+    """multi_task_cdnet.py:262-330 after the CNN: softmax + TTA mean of tc and sem; point mean;
+    per variant ``dir[:,0] *= tc[:,0]`` -> argmax (or, with use_regression, the angle head -> classes, :304-315) -> DDM;
+    mean DDM; optional ``_ddm_enhencement`` (:548-564) on tc.
     Inputs: lists of [C,H,W] fp32 logits (already reverse-transformed).  Returns (tc_prob, sem_prob, dir_map of the first
     variant, dd_map)."""
     tc = softmax_tta_mean(tc_logit_list)
@@ -360,11 +377,14 @@ def mtcdnet_inference_tail(tc_logit_list, sem_logit_list, dir_logit_list, point_
     point = (point / np.float32(len(point_logit_list))).astype(np.float32)
     dd_sum, dir_maps = None, []
     for dl in dir_logit_list:
-        d = softmax(dl, axis=0)
-        d[0] = d[0] * tc[0]
-        dir_map = np.argmax(d, axis=0)
+        if use_regression:
+            dir_map = regression_dir_map(dl[0], np.argmax(tc, axis=0) == 0, num_angles)
+        else:
+            d = softmax(dl, axis=0)
+            d[0] = d[0] * tc[0]
+            dir_map = np.argmax(d, axis=0)
         dir_maps.append(dir_map)
-        dd = direction_differential_map(dir_map, 9)
+        dd = direction_differential_map(dir_map, num_angles + 1)
         dd_sum = dd if dd_sum is None else (dd_sum + dd).astype(np.float32)
     dd_map = (dd_sum / np.float32(len(dir_logit_list))).astype(np.float32)
     if if_ddm:

@@ -1121,3 +1121,27 @@ def test_direction_labels_vs_oracle_batch():
         d = np.minimum(d, 2 * np.pi - d)
         assert d[~soft].max() < 2e-4, (k, d[~soft].max())
         assert (r["dir_gt"][k] != o["dir_gt"]).sum() <= 0.01 * (fixed[k] > 0).sum()
+
+
+def test_mtcdnet_regression_tail_matches_reference_source_golden():
+    """MultiTaskCDNet(use_regression=True): the one-channel angle head (multi_task_cdnet.py:304-315) vs the method executed
+    from source; direction classes identical (the vectors hold angles on class edges, below 0 and above 2 pi)."""
+    from test_oracle_golden import _regr_case
+    from tiseg_b200 import segmentors
+    m = np.load(os.path.join(G, "reg_ref.npz"))
+    for j in range(int(m["n_cases"])):
+        tc, sem, dirs, pts, if_ddm, rots, flips = _regr_case(m, j)
+        rev = lambda lst: np.stack([opp.reverse_tta_transform(x, int(r), str(f)) for x, r, f in zip(lst, rots, flips)])
+        r = ops.mtcdnet_refine(rev(tc), rev(sem), rev(dirs), rev(pts), if_ddm=if_ddm, want_sem_prob=True)
+        # (the background of the direction map is the argmax of the mean tc probabilities: compare where that is clear-cut)
+        w_tc, _, w_dir, w_dd = opp.mtcdnet_inference_tail(list(rev(tc)), list(rev(sem)), list(rev(dirs)), list(rev(pts)), if_ddm,
+                                                          use_regression=True)
+        assert np.array_equal(w_dir, m["g%d_dir_out" % j])
+        assert (r["dir_map"] != m["g%d_dir_out" % j]).mean() < 1e-3, j
+        _check_class_map(r["tc_cls"], r["tc_prob"], m["g%d_tc_out" % j], "mtcdnet regression tc %d" % j)
+        _check_class_map(r["sem_cls"], r["sem_prob"], m["g%d_sem_out" % j], "mtcdnet regression sem %d" % j)
+        seg = segmentors.MultiTaskCDNet(num_classes=sem[0].shape[0], if_ddm=if_ddm, use_regression=True)
+        _, sem_cls, dir_map, tc_cls = seg.inference_tail(rev(tc), rev(sem), rev(dirs), rev(pts))
+        assert np.array_equal(tc_cls, r["tc_cls"]) and np.array_equal(dir_map, r["dir_map"])
+        with pytest.raises(ValueError):
+            segmentors.MultiTaskCDNet(num_classes=sem[0].shape[0], use_regression=False).inference_tail(rev(tc), rev(sem), rev(dirs), rev(pts))

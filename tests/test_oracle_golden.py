@@ -461,3 +461,23 @@ def test_direction_label_make_oracle_vs_reference_golden():
         d = np.minimum(d, 2 * np.pi - d)
         assert (d > 2e-4).sum() <= max(4, fg // 100)
         assert r["loss_weight_map"].dtype == g[p + "loss_weight_map"].dtype
+
+
+def _regr_case(m, j):
+    T = len(m["g%d_flips" % j])
+    f32 = lambda key: [m["g%d_%s%d" % (j, key, t)].astype(np.float32) for t in range(T)]
+    return f32("tc"), f32("sem"), f32("dir"), f32("pt"), bool(m["g%d_if_ddm" % j]), list(m["g%d_rots" % j]), list(m["g%d_flips" % j])
+
+
+def test_oracle_mtcdnet_regression_tail_matches_reference_source():
+    """use_regression = True (multi_task_cdnet.py:304-315) vs the method executed from source (make_golden_reg.py): the
+    angle head is clamped, binned into eight classes and fed to the same DDM + enhancement; angles exactly on class edges
+    and outside [0, 2 pi] are part of the vectors, so the class map must be identical."""
+    m = np.load(os.path.join(G, "reg_ref.npz"))
+    for j in range(int(m["n_cases"])):
+        tc, sem, dirs, pts, if_ddm, rots, flips = _regr_case(m, j)
+        rev = lambda lst: [opp.reverse_tta_transform(x, int(r), str(f)) for x, r, f in zip(lst, rots, flips)]
+        got_tc, got_sem, got_dir, _ = opp.mtcdnet_inference_tail(rev(tc), rev(sem), rev(dirs), rev(pts), if_ddm, use_regression=True)
+        assert np.array_equal(got_dir, m["g%d_dir_out" % j]), j
+        np.testing.assert_allclose(got_tc, m["g%d_tc_out" % j], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got_sem, m["g%d_sem_out" % j], rtol=1e-5, atol=1e-7)

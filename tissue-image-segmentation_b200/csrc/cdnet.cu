@@ -300,13 +300,46 @@ int tiseg_ddm_enhance(tiseg_ctx* c, float* sem_prob, const float* dd, const floa
     return end_call(c);
 }
 
+}  // extern "C"
+
+namespace tiseg {
+// use_regression (multi_task_cdnet.py:304-315): the direction head is ONE channel, an angle in radians.  Per variant:
+// clamp to [0, 2 pi], degrees, (180, 360] -> (-180, 0], class = 1 + bin of align_angle with eight angles
+// (direction_calculation.py:60-73); background (first maximum of the mean three-class probabilities is class 0) -> 0.
+__global__ void __launch_bounds__(TISEG_THREADS)
+k_reg_dir_map(Geom g, const float* __restrict__ reg, const float* __restrict__ tc_prob, int T, int C, uint8_t* __restrict__ dir_map) {
+    Pix px;
+    if (!warp_pixel(g, px) || !px.ok) return;
+    const float* tp = tc_prob + (long long)px.n * C * g.P + px.idx;
+    float best = tp[0];
+    bool bg = true;
+    for (int k = 1; k < C; ++k) if (tp[(long long)k * g.P] > best) { best = tp[(long long)k * g.P]; bg = false; }
+    for (int t = 0; t < T; ++t) {
+        const long long tile = (long long)px.n * T + t;
+        float a = reg[tile * g.P + px.idx];
+        if (a < 0.f) a = 0.f;
+        if (a > 6.28318548202514648f) a = 6.28318548202514648f;
+        float deg = (a * 180.f) / 3.14159274101257324f;
+        if (deg > 180.f) deg -= 360.f;
+        int idx = 0;
+        for (int i = 1; i < 8; ++i) {
+            const float middle = -180.f + 45.f * (float)i;
+            if (deg > middle - 22.5f && deg <= middle + 22.5f) idx = i;
+        }
+        dir_map[tile * g.P + px.idx] = bg ? (uint8_t)0 : (uint8_t)(idx + 1);
+    }
+}
+}  // namespace tiseg
+
+extern "C" {
+
 int tiseg_mtcdnet_refine(tiseg_ctx* c, const float* tc_logits, const float* sem_logits, const float* dir_logits,
                          const float* point_logits, int N, int T, int Ctc, int Csem, int D, int H, int W, int if_ddm,
                          float* tc_prob_out, uint8_t* tc_cls_out, float* sem_prob_out, uint8_t* sem_cls_out,
                          uint8_t* dir_map_out, float* dd_out) {
     if (!c || !tc_logits || !sem_logits || !dir_logits || !point_logits || T <= 0 || Ctc < 2 || Ctc > 16 || Csem < 1 ||
-        Csem > 16 || D != 9) {
-        set_error("tiseg_mtcdnet_refine: bad argument (2 <= Ctc <= 16, 1 <= Csem <= 16, D == 9)");
+        Csem > 16 || (D != 9 && D != 1)) {
+        set_error("tiseg_mtcdnet_refine: bad argument (2 <= Ctc <= 16, 1 <= Csem <= 16, D == 9, or D == 1: the regression head)");
         return TISEG_ERR_ARG;
     }
     TISEG_TRY(check_geom(N * T, H, W));
@@ -333,7 +366,9 @@ int tiseg_mtcdnet_refine(tiseg_ctx* c, const float* tc_logits, const float* sem_
         if (!sp && T > 1) { sp = ws<float>(c, total * Csem); if (!sp) return TISEG_ERR_CUDA; }      // (T == 1: streaming argmax)
         TISEG_TRY(softmax_argmax_dev(c, g, d_sem, T, Csem, sp, d_semc));
     }
-    {   // per variant: dir[:, 0] *= tc[:, 0]; argmax; DDM (:318-322)
+    if (D == 1) {   // use_regression: the angle head -> classes (:304-315)
+        TISEG_LAUNCH(c, k_reg_dir_map, warp_grid(g), TISEG_THREADS, 0, g, d_dir, d_tcp, T, Ctc, dir_all);
+    } else {   // per variant: dir[:, 0] *= tc[:, 0]; argmax; DDM (:318-322)
         const bool v4 = (g.P % 4 == 0) && aligned16(d_dir, d_tcp) && (((uintptr_t)dir_all) & 3) == 0;
         TISEG_LAUNCH(c, k_dir_map<9>, dim3(flat4_grid(g.P), (unsigned)N), TISEG_THREADS, 0, (long long)g.P, d_dir, d_tcp, T, D, Ctc, dir_all, v4);
     }

@@ -265,8 +265,9 @@ def ddm_enhance(sem_prob, dd_map, point_map, mode=0):
 
 
 def mtcdnet_refine(tc_logits, sem_logits, dir_logits, point_logits, if_ddm=True, want_sem_prob=False):
-    """MultiTaskCDNet.inference tail (multi_task_cdnet.py:262-330, use_regression = False).  tc_logits [N,T,Ctc,H,W],
-    sem_logits [N,T,Csem,H,W], dir_logits [N,T,9,H,W], point_logits [N,T,1,H,W] (or without the leading N) ->
+    """MultiTaskCDNet.inference tail (multi_task_cdnet.py:262-330).  tc_logits [N,T,Ctc,H,W], sem_logits [N,T,Csem,H,W],
+    dir_logits [N,T,9,H,W] (or [N,T,1,H,W]: the angle head of use_regression = True), point_logits [N,T,1,H,W] (or without
+    the leading N) ->
     dict(tc_prob, tc_cls, sem_cls, dir_map, dd[, sem_prob])."""
     t = as_input(tc_logits, np.float32)
     s = as_input(sem_logits, np.float32)

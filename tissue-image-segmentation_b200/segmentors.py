@@ -237,13 +237,17 @@ class MultiTaskCDNet(MultiTaskCUNet):
 
     def __init__(self, num_classes, num_angles=8, test_cfg=None, if_ddm=False, use_regression=False):
         super().__init__(num_classes, test_cfg)
-        if use_regression:
-            raise NotImplementedError("use_regression=True (angle regression, multi_task_cdnet.py:304-317) is not built")
-        self.num_angles, self.if_ddm = num_angles, if_ddm
+        if num_angles != 8:
+            raise NotImplementedError("the direction differential map is built for eight angles (nine classes)")
+        # use_regression (multi_task_cdnet.py:304-315): dir_logit is then the ONE-channel angle head, in radians
+        self.num_angles, self.if_ddm, self.use_regression = num_angles, if_ddm, use_regression
 
     def inference_tail(self, tc_logit, sem_logit, dir_logit, point_logit):
         """raw head outputs of the T TTA variants (already reverse-transformed; [T, C, H, W] or [N, T, C, H, W]) ->
         (refined tc probabilities, sem class map, dir_map of variant 0, tc class map)."""
+        if np.shape(dir_logit)[-3] != (1 if self.use_regression else self.num_angles + 1):
+            raise ValueError("dir_logit has %d channels; use_regression=%s expects %d" % (
+                np.shape(dir_logit)[-3], self.use_regression, 1 if self.use_regression else self.num_angles + 1))
         r = ops.mtcdnet_refine(tc_logit, sem_logit, dir_logit, point_logit, if_ddm=self.if_ddm)
         return r['tc_prob'], r['sem_cls'], r['dir_map'], r['tc_cls']
 
