@@ -1053,6 +1053,40 @@ def test_pair_metrics_uint16_ground_truth():
 
 
 
+@pytest.mark.parametrize("H,W", [(1, 1), (5, 7), (37, 53), (64, 131), (33, 260), (40, 1000), (3, 257), (70, 252)])
+def test_pair_metrics_ragged_shapes_vs_oracle(H, W):
+    """the plane builder walks 256-column strips, eight pixels per thread, with vector loads when W % 4 == 0: widths that
+    end inside a thread's eight pixels, inside a vector, inside a word, one pixel past a strip; heights below the cluster
+    size of the ranking kernel; int32 and uint16 ground truth; batch entries that differ"""
+    t = [synth.gt_and_pred(6300 + H + W + k, max(H, 8), max(W, 8), n=max(1, H * W // 600)) for k in range(3)]
+    p = np.stack([x["pred_inst"][:H, :W] for x in t]).astype(np.int32)
+    g = np.stack([x["gt_inst"][:H, :W] for x in t]).astype(np.int32)
+    g[2] = p[2]                                        # identical maps: every pair matches
+    p[1, :, -1] = 9                                    # a one-pixel-wide instance on the last column
+    aji, pq = ops.pair_metrics_bin(p, g)
+    aji16, pq16 = ops.pair_metrics_bin(p, g.astype(np.uint16))
+    assert np.array_equal(aji, aji16) and np.array_equal(pq, pq16)
+    for n in range(3):
+        assert tuple(aji[n]) == tuple(np.float64(om.pre_eval_bin_aji(p[n], g[n], literal=False))), (H, W, n)
+        assert tuple(pq[n]) == tuple(np.float64(om.pre_eval_bin_pq(p[n], g[n], literal=False))), (H, W, n)
+    # the other streaming passes of the headline step on the same shapes
+    rng = np.random.default_rng(H * 1000 + W)
+    lg = (rng.standard_normal((3, 1, 2, H, W)) * 2).astype(np.float32)
+    lg[0, 0, 1] = lg[0, 0, 0]                          # exact ties everywhere: the tie-band path of the two-class argmax
+    cls = ops.softmax_argmax(lg)
+    for n in range(3):
+        assert np.array_equal(cls[n], opp.argmax_classes(opp.softmax(lg[n, 0])).astype(np.uint8)), (H, W, n)
+    sp, sg = (p > 0).astype(np.uint8), (g > 0).astype(np.uint8)
+    sg[0, 0, 0] = 255                                  # ignore_index in a two-class map: the generic counting path
+    counts, valid = ops.sem_counts(sp, sg, 2)
+    for n in range(3):
+        ok = sg[n] != 255
+        want = [[((sp[n] == c) & (sg[n] == c) & ok).sum() for c in range(2)], [((sp[n] == c) & (sg[n] != c) & ok).sum() for c in range(2)],
+                [((sp[n] != c) & (sg[n] == c) & ok).sum() for c in range(2)], [((sp[n] == c) & ok).sum() for c in range(2)],
+                [((sg[n] == c) & ok).sum() for c in range(2)]]
+        assert np.array_equal(np.asarray(counts[n]), np.array(want)) and int(valid[n]) == int(ok.sum()), (H, W, n)
+
+
 # --------------------------------------------------------------------------- (f)4 DirectionLabelMake
 def _dir_case(g, j):
     p = "d%d_" % j
