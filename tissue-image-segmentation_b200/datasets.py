@@ -176,11 +176,14 @@ class CustomDataset:
         sg, ig = zip(*[self._load_gt(i) for i in indices])
         return self._stack(list(sg), np.uint8), self._stack(list(ig), np.int32)
 
-    def pre_eval_records(self, sem_pred, inst_pred, indices):
+    def pre_eval_records(self, sem_pred, inst_pred, indices, check=True):
         """``pre_eval`` for a whole batch ``[n, H, W]`` without a Python loop over the images: returns ONE float64 array
         / tensor ``[n, R]`` in the layout of ``parallel.pack_results`` (bin aji 2, bin pq 4, sem 6 x (C-1), and for
         multi-class datasets aji 2 x (C-1), pq 4 x (C-1)); ``parallel.unpack_results`` turns rows back into the
-        per-image dictionaries ``evaluate`` takes.  Values are what ``pre_eval`` would have put in the dictionaries."""
+        per-image dictionaries ``evaluate`` takes.  Values are what ``pre_eval`` would have put in the dictionaries.
+        ``check``: synchronise the library context before returning device results, so that errors only a kernel can
+        detect (an instance id outside the supported range) are raised here, once per batch; pass False to keep the
+        batch asynchronous and call ``tiseg_b200._lib.get_ctx(device).synchronize()`` yourself before reading."""
         import torch
         C = len(self.CLASSES)
         sem_g, inst_g = self._gt_batch(list(indices))
@@ -200,7 +203,10 @@ class CustomDataset:
         if multi:
             ca, cq = t(caji), t(cpq)
             parts += [f32(ca[:, 1:, k]) for k in range(2)] + [f32(cq[:, 1:, k]) for k in range(4)]
-        return torch.cat(parts, dim=1)
+        rec = torch.cat(parts, dim=1)
+        if check and rec.is_cuda:
+            _lib.get_ctx(rec.device.index).synchronize()
+        return rec
 
     @staticmethod
     def _columns(results):
