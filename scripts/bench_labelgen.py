@@ -30,8 +30,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--size", type=int, default=1000)
+    ap.add_argument("--only", default="", help="substring of the label maker to time")
     a = ap.parse_args()
-    tiles = [synth.gt_and_pred(4200 + j, 1000, 1000, n=900) for j in range(4)]
+    S = a.size
+    tiles = [synth.gt_and_pred(4200 + j, S, S, n=max(1, 900 * S * S // 1000000)) for j in range(4)]
     inst_np = np.stack([tiles[b % 4]["gt_inst"].astype(np.int32) for b in range(a.batch)])
     sem_np = (inst_np > 0).astype(np.uint8)
     inst, sem = torch.from_numpy(inst_np).cuda(), torch.from_numpy(sem_np).cuda()
@@ -43,10 +46,14 @@ def main():
             ("DistanceLabelMake (fix_inst + distance map)", lambda: ops.instance_distance_map(ops.fix_inst(inst), True)),
             ("BoundLabelMake (fix_inst + boundary label)", lambda: ops.bound_label(sem, ops.fix_inst(inst), 2, 3)),
             ("UNetLabelMake (fix_inst + weight map)", lambda: ops.unet_weight_map(ops.fix_inst(inst), 10.0, 5.0)),
+            ("DirectionLabelMake (fix_inst + centre / distance / direction / point / weight maps)",
+             lambda: ops.direction_labels(ops.fix_inst(inst), 8)),
         ]
         for name, fn in cases:
+            if a.only and a.only not in name:
+                continue
             ms = timed(fn, a.steps)
-            print(json.dumps({"label_maker": name, "tile": [1000, 1000], "tiles_per_step": a.batch, "ms_per_step": ms,
+            print(json.dumps({"label_maker": name, "tile": [S, S], "tiles_per_step": a.batch, "ms_per_step": ms,
                               "tiles_per_s": a.batch / (ms / 1e3)}), flush=True)
 
 
