@@ -78,4 +78,14 @@ def test_reference_signatures():
         assert names(cls._ddm_enhencement) == ["sem_logit", "dd_map", "point_logit"]
     assert names(S.MultiTaskCDNet.postprocess)[1:] == ["inner_pred", "sem_pred"] or names(S.MultiTaskCDNet.postprocess)[1:] == ["tc_pred", "sem_pred"]
     assert names(M.pre_eval_all_semantic_metric)[:4] == ["pred_label", "target_label", "num_classes", "ignore_index"]
+    # label makers: constructor arguments and defaults of tiseg/datasets/ops/{direction_map.py:14, distance_map.py:37,
+    # bound_map.py:12, unet_map.py:30}
+    from tiseg_b200 import label_makers as L
+    sig = lambda cls: [(k, v.default) for k, v in inspect.signature(cls.__init__).parameters.items() if k != "self"]
+    assert sig(L.DirectionLabelMake) == [("to_center", True), ("num_angles", 8)]
+    assert sig(L.DistanceLabelMake) == [("inst_norm", True)]
+    assert sig(L.BoundLabelMake) == [("edge_id", 2), ("selem_radius", 3)]
+    assert sig(L.UNetLabelMake) == [("wc", None), ("w0", 10.0), ("sigma", 5.0)]
+    assert [k for k in inspect.signature(S.MultiTaskCDNet.__init__).parameters][1:] == ["num_classes", "num_angles", "test_cfg", "if_ddm",
+                                                                                       "use_regression"]
 
